@@ -1,0 +1,484 @@
+"""fealess_b200 - B200-native LINE-MOD + ICP hot path of rlvc/FEALESS behind the reference's call surface.
+
+The product is ``libfealess_b200.so`` (hand-written CUDA for sm_100a + a C ABI, ``include/fealess_b200.h``).
+This package is the thin Python host side used by the tests and the benchmark: a ctypes binding plus mirrors
+of the reference's interface for this path (same names and argument meaning):
+
+    Detector.match                 cup_linemod::Detector::match          linemod/linemod.hpp:324-327
+    Detector.addSyntheticTemplate  Detector::addSyntheticTemplate        linemod/linemod.cpp:1636-1642
+    detection                      detection()                           ICP/detection.h:9-11
+    icpCloudToCloud_Ex             icpCloudToCloud_Ex                    ICP/ICP.h:165-172
+    depthTo3d                      cup_d2pc::depthTo3d                   ICP/depth_to_3d.h:12-13
+    nonMaximumSuppression          nonMaximumSuppression                 ICP/NMS.h:14-16
+
+There is NO CPU fallback: importing works anywhere, but creating a handle raises unless the CUDA library is
+built and a GPU is present.  Nothing here imports ``oracle/``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import synth  # noqa: F401  (synthetic inputs; numpy only)
+
+__all__ = ["lib", "Handle", "Detector", "Match", "detection", "icpCloudToCloud_Ex", "depthTo3d",
+           "nonMaximumSuppression", "FealessError", "MATCH_DTYPE", "ICP_RESULT_DTYPE", "library_path"]
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libfealess_b200.so")
+
+FL_OK, FL_ERR_SIZE, FL_ERR_GEOMETRY, FL_ERR_ROI, FL_ERR_FEATURES = 0, -1, -2, -3, -4
+FL_ERR_ARG, FL_ERR_CAPACITY, FL_ERR_CUDA, FL_ERR_STATE = -5, -6, -7, -8
+FL_DBG_QUANTIZED, FL_DBG_SPREAD, FL_DBG_LINEAR_MEMORY, FL_DBG_SIMILARITY = 0, 1, 2, 3
+
+MATCH_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("similarity", "<f4"), ("class_idx", "<i4"), ("template_id", "<i4")])
+ICP_RESULT_DTYPE = np.dtype([("R", "<f4", (9,)), ("T", "<f4", (3,)), ("dist_mean", "<f4"), ("inlier_ratio", "<f4"),
+                             ("iterations", "<i4"), ("n_points", "<i4"), ("status", "<i4")])
+
+# every symbol include/fealess_b200.h declares (tests check that the built library exports all of them)
+EXPORTED_SYMBOLS = [
+    "fl_default_params", "fl_create", "fl_destroy", "fl_last_error", "fl_version", "fl_sync", "fl_stream",
+    "fl_upload_templates", "fl_num_templates", "fl_get_pose_info", "fl_match", "fl_match_device", "fl_match_fetch",
+    "fl_match_shard_device", "fl_sort_unique_device", "fl_depth_to_3d", "fl_icp_cloud_to_cloud_ex",
+    "fl_detection_batch", "fl_detection", "fl_nms", "fl_debug_keep_spread", "fl_debug_get", "fl_launch_count",
+    "fl_profile", "fl_last_stage_ms",
+]
+
+
+class FealessError(RuntimeError):
+    def __init__(self, rc: int, where: str, detail: str = ""):
+        super().__init__("%s failed with status %d%s" % (where, rc, (": " + detail) if detail else ""))
+        self.rc = rc
+
+
+class Params(C.Structure):
+    _fields_ = [("n_levels", C.c_int32), ("T", C.c_int32 * 8), ("n_modalities", C.c_int32), ("modality_kind", C.c_int32 * 4),
+                ("weak_threshold", C.c_float), ("distance_threshold", C.c_int32), ("difference_threshold", C.c_int32),
+                ("max_width", C.c_int32), ("max_height", C.c_int32), ("max_candidates", C.c_int32), ("device", C.c_int32)]
+
+
+class Intrinsics(C.Structure):
+    _fields_ = [("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float)]
+
+
+class Rect(C.Structure):
+    _fields_ = [("x", C.c_int32), ("y", C.c_int32), ("width", C.c_int32), ("height", C.c_int32)]
+
+
+class IcpParams(C.Structure):
+    _fields_ = [("icp_it_thr", C.c_int32), ("dist_mean_thr", C.c_float), ("dist_diff_thr", C.c_float)]
+
+
+def library_path() -> str:
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    """The loaded C-ABI library.  Raises if it has not been built: there is no fallback path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            raise FealessError(FL_ERR_STATE, "load", "%s is missing - run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(nvcc, sm_100a).  fealess_b200 has no CPU fallback." % _SO)
+        L = C.CDLL(_SO)
+        L.fl_last_error.restype = C.c_char_p
+        L.fl_version.restype = C.c_char_p
+        L.fl_stream.restype = C.c_void_p
+        L.fl_launch_count.restype = C.c_int64
+        L.fl_stream.argtypes = [C.c_void_p]
+        L.fl_launch_count.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def _check(rc: int, where: str, ok=(FL_OK,)):
+    if rc not in ok:
+        raise FealessError(rc, where, lib().fl_last_error().decode(errors="replace"))
+    return rc
+
+
+class Handle:
+    """Owns one ``fl_handle`` (one GPU, one stream)."""
+
+    def __init__(self, T: Sequence[int] = (5, 8), modality_kind: Sequence[int] = (0, 1), max_width=640, max_height=480,
+                 max_candidates=1 << 16, device=0, weak_threshold=10.0, distance_threshold=2000, difference_threshold=50):
+        L = lib()
+        p = Params()
+        L.fl_default_params(C.byref(p))
+        p.n_levels = len(T)
+        for i, t in enumerate(T):
+            p.T[i] = int(t)
+        p.n_modalities = len(modality_kind)
+        for i, k in enumerate(modality_kind):
+            p.modality_kind[i] = int(k)
+        p.weak_threshold = weak_threshold
+        p.distance_threshold = distance_threshold
+        p.difference_threshold = difference_threshold
+        p.max_width, p.max_height, p.max_candidates, p.device = max_width, max_height, max_candidates, device
+        self.params = p
+        self.T = tuple(int(t) for t in T)
+        self.L = len(T)
+        self.M = len(modality_kind)
+        self._h = C.c_void_p()
+        rc = L.fl_create(C.byref(p), C.byref(self._h))
+        if rc != FL_OK:
+            msg = L.fl_last_error().decode(errors="replace")
+            if self._h:
+                L.fl_destroy(self._h)
+            self._h = None
+            raise FealessError(rc, "fl_create", msg)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().fl_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- templates -------------------------------------------------------------------------------
+    def upload_templates(self, tset) -> None:
+        hdr = np.ascontiguousarray(tset.headers, np.int32)
+        ft = np.ascontiguousarray(tset.features, np.int32)
+        co = np.ascontiguousarray(tset.class_of, np.int32)
+        pose = None if tset.pose13 is None else np.ascontiguousarray(tset.pose13, np.float32)
+        _check(lib().fl_upload_templates(self._h, int(tset.n_templates), _p(hdr), _p(ft), int(ft.shape[0]), _p(co), _p(pose)),
+               "fl_upload_templates")
+
+    def num_templates(self) -> int:
+        return lib().fl_num_templates(self._h)
+
+    def get_pose_info(self, class_idx: int, template_id: int) -> np.ndarray:
+        out = np.zeros(13, np.float32)
+        _check(lib().fl_get_pose_info(self._h, class_idx, template_id, _p(out)), "fl_get_pose_info")
+        return out
+
+    # ---- match -----------------------------------------------------------------------------------
+    def match(self, bgr: Optional[np.ndarray], depth: Optional[np.ndarray], threshold: float,
+              class_filter: Optional[Sequence[int]] = None, masks: Optional[Sequence[Optional[np.ndarray]]] = None,
+              want_quantized: bool = False, capacity: int = 1 << 16):
+        """fl_match with host buffers.  Returns (rc, matches[, quantized list]); rc -1 / -2 mirror the reference's
+        ``return -1`` / CV_Assert cases instead of raising."""
+        ref = depth if depth is not None else bgr
+        H, W = ref.shape[:2]
+        bgr_c = None if bgr is None else np.ascontiguousarray(bgr, np.uint8)
+        dep_c = None if depth is None else np.ascontiguousarray(depth, np.uint16)
+        out = np.zeros(capacity, MATCH_DTYPE)
+        cnt = C.c_int32(0)
+        cf = None if not class_filter else np.ascontiguousarray(class_filter, np.int32)
+        marr = None
+        keep = []
+        if masks:
+            if len(masks) != self.M:
+                return (FL_ERR_SIZE, out[:0]) + (([],) if want_quantized else ())   # linemod.cpp:1374-1377
+            keep = [None if m is None else np.ascontiguousarray(m, np.uint8) for m in masks]
+            marr = (C.c_void_p * self.M)(*[None if m is None else m.ctypes.data for m in keep])
+        qarr, qbufs = None, []
+        if want_quantized:
+            qbufs = [np.zeros(((H >> l), (W >> l)), np.uint8) for l in range(self.L) for _ in range(self.M)]
+            qarr = (C.c_void_p * (self.L * self.M))(*[q.ctypes.data for q in qbufs])
+        rc = lib().fl_match(self._h, _p(bgr_c), C.c_size_t(0 if bgr_c is None else W * 3), _p(dep_c),
+                            C.c_size_t(0 if dep_c is None else W * 2), W, H, marr, C.c_float(threshold), _p(cf),
+                            0 if cf is None else int(cf.size), _p(out), capacity, C.byref(cnt), qarr)
+        if rc not in (FL_OK, FL_ERR_SIZE, FL_ERR_GEOMETRY, FL_ERR_CAPACITY):
+            _check(rc, "fl_match")
+        res = out[:min(cnt.value, capacity)].copy()
+        return (rc, res, qbufs) if want_quantized else (rc, res)
+
+    def match_device(self, d_bgr: int, d_depth: int, W: int, H: int, threshold: float, class_filter=None) -> None:
+        """Frame already in device memory (raw device pointers, dense rows); results stay on the device."""
+        cf = None if not class_filter else np.ascontiguousarray(class_filter, np.int32)
+        _check(lib().fl_match_device(self._h, C.c_void_p(d_bgr), C.c_void_p(d_depth), W, H, None, C.c_float(threshold), _p(cf),
+                                     0 if cf is None else int(cf.size)), "fl_match_device")
+
+    def match_fetch(self, capacity: int = 1 << 16) -> np.ndarray:
+        out = np.zeros(capacity, MATCH_DTYPE)
+        cnt = C.c_int32(0)
+        _check(lib().fl_match_fetch(self._h, _p(out), capacity, C.byref(cnt)), "fl_match_fetch", ok=(FL_OK, FL_ERR_CAPACITY))
+        return out[:min(cnt.value, capacity)].copy()
+
+    def match_shard_device(self, d_bgr: int, d_depth: int, W: int, H: int, threshold: float, d_candidates: int, capacity: int,
+                           d_count: int, class_filter=None) -> None:
+        cf = None if not class_filter else np.ascontiguousarray(class_filter, np.int32)
+        _check(lib().fl_match_shard_device(self._h, C.c_void_p(d_bgr), C.c_void_p(d_depth), W, H, None, C.c_float(threshold), _p(cf),
+                                           0 if cf is None else int(cf.size), C.c_void_p(d_candidates), capacity, C.c_void_p(d_count)),
+               "fl_match_shard_device")
+
+    def sort_unique_device(self, d_in: int, n_lists: int, list_capacity: int, d_n_in: int, d_out: int, out_capacity: int,
+                           d_out_count: int) -> None:
+        _check(lib().fl_sort_unique_device(self._h, C.c_void_p(d_in), n_lists, list_capacity, C.c_void_p(d_n_in), C.c_void_p(d_out),
+                                           out_capacity, C.c_void_p(d_out_count)), "fl_sort_unique_device")
+
+    def sync(self):
+        _check(lib().fl_sync(self._h), "fl_sync")
+
+    def stream_ptr(self) -> int:
+        return int(lib().fl_stream(self._h) or 0)
+
+    def launch_count(self) -> int:
+        return int(lib().fl_launch_count(self._h))
+
+    def profile(self, enable=True):
+        _check(lib().fl_profile(self._h, int(enable)), "fl_profile")
+
+    def last_stage_ms(self) -> np.ndarray:
+        out = np.zeros(4, np.float32)
+        _check(lib().fl_last_stage_ms(self._h, _p(out)), "fl_last_stage_ms")
+        return out
+
+    # ---- debug exports ---------------------------------------------------------------------------
+    def keep_spread(self, enable=True):
+        _check(lib().fl_debug_keep_spread(self._h, int(enable)), "fl_debug_keep_spread")
+
+    def debug_quantized(self, level, modality, W, H, spread=False) -> np.ndarray:
+        out = np.zeros((H >> level, W >> level), np.uint8)
+        _check(lib().fl_debug_get(self._h, FL_DBG_SPREAD if spread else FL_DBG_QUANTIZED, level, modality, 0, _p(out),
+                                  C.c_size_t(out.nbytes)), "fl_debug_get")
+        return out
+
+    def debug_lm(self, level, modality, label, W, H) -> np.ndarray:
+        T = self.T[level]
+        out = np.zeros((T * T, ((W >> level) // T) * ((H >> level) // T)), np.uint8)
+        _check(lib().fl_debug_get(self._h, FL_DBG_LINEAR_MEMORY, level, modality, label, _p(out), C.c_size_t(out.nbytes)), "fl_debug_get")
+        return out
+
+    def debug_similarity(self, t, W, H) -> np.ndarray:
+        l = self.L - 1
+        T = self.T[l]
+        out = np.zeros(((H >> l) // T, (W >> l) // T), np.uint16)
+        _check(lib().fl_debug_get(self._h, FL_DBG_SIMILARITY, t, 0, 0, _p(out), C.c_size_t(out.nbytes)), "fl_debug_get")
+        return out
+
+    # ---- ICP -------------------------------------------------------------------------------------
+    def depth_to_3d(self, depth: np.ndarray, K) -> np.ndarray:
+        d = np.ascontiguousarray(depth, np.uint16)
+        H, W = d.shape
+        out = np.zeros((H, W, 3), np.float32)
+        _check(lib().fl_depth_to_3d(self._h, _p(d), C.c_size_t(W * 2), W, H, Intrinsics(*[float(v) for v in K]), _p(out)), "fl_depth_to_3d")
+        return out
+
+    def icp_cloud_to_cloud_ex(self, pts_ref, pts_model, icp_it_thr=4, dist_mean_thr=0.0, dist_diff_thr=0.0) -> np.ndarray:
+        pr = np.ascontiguousarray(pts_ref, np.float32).reshape(-1, 3)
+        pm = np.ascontiguousarray(pts_model, np.float32).reshape(-1, 3)
+        out = np.zeros(1, ICP_RESULT_DTYPE)
+        _check(lib().fl_icp_cloud_to_cloud_ex(self._h, _p(pr), pr.shape[0], _p(pm), pm.shape[0],
+                                              IcpParams(icp_it_thr, dist_mean_thr, dist_diff_thr), _p(out)), "fl_icp_cloud_to_cloud_ex")
+        return out[0]
+
+    def detection_batch(self, ref_depth, K_ref, model_depths: Sequence[np.ndarray], rects_model, rects_ref, r_match=None, t_match=None,
+                        icp_it_thr=10, dist_mean_thr=0.5, dist_diff_thr=0.01) -> np.ndarray:
+        ref = np.ascontiguousarray(ref_depth, np.uint16)
+        H, W = ref.shape
+        n = len(model_depths)
+        mds = [np.ascontiguousarray(m, np.uint16) for m in model_depths]
+        ptrs = (C.c_void_p * max(n, 1))(*[m.ctypes.data for m in mds])
+        strides = (C.c_size_t * max(n, 1))(*[m.strides[0] for m in mds])
+        rm = np.ascontiguousarray(rects_model, np.int32).reshape(-1, 4)
+        rr = np.ascontiguousarray(rects_ref, np.int32).reshape(-1, 4)
+        rmat = None if r_match is None else np.ascontiguousarray(r_match, np.float32).reshape(-1, 9)
+        tvec = None if t_match is None else np.ascontiguousarray(t_match, np.float32).reshape(-1, 3)
+        out = np.zeros(max(n, 1), ICP_RESULT_DTYPE)
+        _check(lib().fl_detection_batch(self._h, _p(ref), C.c_size_t(W * 2), W, H, Intrinsics(*[float(v) for v in K_ref]), ptrs, strides,
+                                        _p(rm), _p(rr), _p(rmat), _p(tvec), None, n, IcpParams(icp_it_thr, dist_mean_thr, dist_diff_thr),
+                                        _p(out)), "fl_detection_batch")
+        return out[:n]
+
+    def nms(self, t3, n_model_pts, icp_dist, th_obj_dist) -> np.ndarray:
+        t = np.ascontiguousarray(t3, np.float32).reshape(-1, 3)
+        nm = np.ascontiguousarray(n_model_pts, np.int32)
+        dd = np.ascontiguousarray(icp_dist, np.float32)
+        out = np.zeros(max(len(nm), 1), np.int32)
+        n = lib().fl_nms(self._h, _p(t), _p(nm), _p(dd), len(nm), C.c_float(th_obj_dist), _p(out))
+        if n < 0:
+            _check(n, "fl_nms")
+        return out[:n].copy()
+
+
+# --------------------------------------------------------------------------------------------------
+# mirrors of the reference interface
+# --------------------------------------------------------------------------------------------------
+class Match:
+    """cup_linemod::Match (linemod/linemod.hpp:253-286)."""
+    __slots__ = ("x", "y", "similarity", "class_id", "template_id")
+
+    def __init__(self, x, y, similarity, class_id, template_id):
+        self.x, self.y, self.similarity, self.class_id, self.template_id = int(x), int(y), float(similarity), class_id, int(template_id)
+
+    def __repr__(self):
+        return "Match(x=%d, y=%d, similarity=%.4f, class_id=%r, template_id=%d)" % (self.x, self.y, self.similarity, self.class_id, self.template_id)
+
+
+_MODALITY_KIND = {"ColorGradient": 0, "DepthNormal": 1}
+
+
+class Detector:
+    """Host-side mirror of ``cup_linemod::Detector`` for the matching path (linemod/linemod.hpp:292-412).
+
+    Templates are added with ``addSyntheticTemplate`` (one TemplatePyramid = list of (width, height, offset_x,
+    offset_y, pyramid_level, features[(x, y, label)]) in the order L0-M0, L0-M1, L1-M0 ...) or in bulk from a
+    ``synth.TemplateSet``; classes iterate in sorted name order like the reference's ``std::map``.
+    """
+
+    def __init__(self, modalities: Sequence[str] = ("ColorGradient", "DepthNormal"), T_pyramid: Sequence[int] = (5, 8),
+                 max_width=640, max_height=480, device=0, max_candidates=1 << 16):
+        self.modalities = list(modalities)
+        self.T_at_level = [int(t) for t in T_pyramid]
+        self._handle = Handle(self.T_at_level, [_MODALITY_KIND[m] for m in modalities], max_width, max_height, max_candidates, device)
+        self._classes = {}          # class_id -> list of template pyramids
+        self._poses = {}            # class_id -> list of 13-float arrays
+        self._dirty = True
+        self._class_order: List[str] = []
+
+    # -- accessors (linemod.hpp:357-381) --
+    def getModalities(self):
+        return self.modalities
+
+    def getT(self, pyramid_level):
+        return self.T_at_level[pyramid_level]
+
+    def pyramidLevels(self):
+        return len(self.T_at_level)
+
+    def numClasses(self):
+        return len(self._classes)
+
+    def numTemplates(self, class_id=None):
+        if class_id is None:
+            return sum(len(v) for v in self._classes.values())
+        return len(self._classes.get(class_id, []))
+
+    def classIds(self):
+        return sorted(self._classes)
+
+    def getTemplates(self, class_id, template_id):
+        return self._classes[class_id][template_id]
+
+    def getPoseInfo(self, template_id, class_id=None):
+        cid = class_id if class_id is not None else self.classIds()[0]
+        return self._poses[cid][template_id]
+
+    def addSyntheticTemplate(self, templates, class_id, pose_info=None) -> int:
+        lst = self._classes.setdefault(class_id, [])
+        self._poses.setdefault(class_id, []).append(np.zeros(13, np.float32) if pose_info is None else np.asarray(pose_info, np.float32))
+        lst.append(templates)
+        self._dirty = True
+        return len(lst) - 1
+
+    def add_template_set(self, tset) -> None:
+        LM = tset.n_levels * tset.n_modalities
+        for t in range(tset.n_templates):
+            pyr = []
+            for e in range(LM):
+                h = tset.headers[t * LM + e]
+                pyr.append((int(h[0]), int(h[1]), int(h[2]), int(h[3]), int(h[4]), tset.features[h[5]:h[5] + h[6]].copy()))
+            self.addSyntheticTemplate(pyr, tset.class_names[int(tset.class_of[t])], tset.pose13[t])
+
+    def _upload(self):
+        names = self.classIds()
+        hdrs, feats, class_of, poses, pos = [], [], [], [], 0
+        for ci, name in enumerate(names):
+            for tid, pyr in enumerate(self._classes[name]):
+                for (w, h, ox, oy, lvl, f) in pyr:
+                    f = np.asarray(f, np.int32).reshape(-1, 3)
+                    hdrs.append((w, h, ox, oy, lvl, pos, len(f)))
+                    feats.append(f)
+                    pos += len(f)
+                class_of.append(ci)
+                poses.append(self._poses[name][tid])
+        ts = synth.TemplateSet(len(self.T_at_level), len(self.modalities), tuple(self.T_at_level), names,
+                               np.array(hdrs, np.int32).reshape(-1, 7),
+                               np.concatenate(feats).astype(np.int32) if feats else np.zeros((0, 3), np.int32),
+                               np.array(class_of, np.int32), np.array(poses, np.float32).reshape(-1, 13))
+        self._handle.upload_templates(ts)
+        self._class_order = names
+        self._dirty = False
+
+    def match(self, sources: Sequence[np.ndarray], threshold: float, class_ids: Sequence[str] = (),
+              quantized_images: Optional[list] = None, masks: Sequence[Optional[np.ndarray]] = ()):
+        """Returns (status, matches): status 0 or -1 exactly where the reference returns them (linemod.cpp:1364-1378);
+        geometry violations that are CV_Asserts in the reference raise ``FealessError``."""
+        if len(sources) != len(self.modalities):
+            return -1, []
+        if masks and len(masks) != len(self.modalities):
+            return -1, []
+        if self._dirty:
+            self._upload()
+        bgr = depth = None
+        for m, s in zip(self.modalities, sources):
+            if m == "ColorGradient":
+                bgr = s
+            else:
+                depth = s
+        filt = None
+        if class_ids:
+            filt = [self._class_order.index(c) for c in class_ids if c in self._class_order]
+            if not filt:
+                return 0, []
+        r = self._handle.match(bgr, depth, threshold, filt, list(masks) if masks else None, want_quantized=quantized_images is not None)
+        rc, recs = r[0], r[1]
+        if rc in (FL_ERR_GEOMETRY, FL_ERR_CAPACITY):
+            raise FealessError(rc, "Detector.match", "geometry (W%T, H%T, W*H%16) or capacity")
+        if rc != FL_OK:
+            return -1, []
+        if quantized_images is not None:
+            quantized_images[:] = r[2]
+        return 0, [Match(m["x"], m["y"], m["similarity"], self._class_order[m["class_idx"]], m["template_id"]) for m in recs]
+
+
+_default_handle = None
+
+
+def _handle() -> Handle:
+    global _default_handle
+    if _default_handle is None:
+        _default_handle = Handle()
+    return _default_handle
+
+
+def depthTo3d(depth, K, handle: Optional[Handle] = None) -> np.ndarray:
+    """cup_d2pc::depthTo3d for a 16UC1 image; K = 3x3 matrix or (fx, fy, cx, cy).  Metres, 0 -> NaN."""
+    K = np.asarray(K, np.float64)
+    if K.shape == (3, 3):
+        K = (K[0, 0], K[1, 1], K[0, 2], K[1, 2])
+    return (handle or _handle()).depth_to_3d(depth, K)
+
+
+def icpCloudToCloud_Ex(pts_ref, pts_model, icp_it_thr=4, dist_mean_thr=0.0, dist_diff_thr=0.0, handle: Optional[Handle] = None):
+    """Returns (dist_mean, R 3x3, T 3, px_inliers_ratio) like the reference's return value + out-params."""
+    r = (handle or _handle()).icp_cloud_to_cloud_ex(pts_ref, pts_model, icp_it_thr, dist_mean_thr, dist_diff_thr)
+    return float(r["dist_mean"]), r["R"].reshape(3, 3).copy(), r["T"].copy(), float(r["inlier_ratio"])
+
+
+def detection(depImg_model_raw, depImg_ref_raw, tCamIntrinsic, rect_model_final, rect_ref_final, icp_it_thr, dist_mean_thr,
+              dist_diff_thr, r_match, t_match, d_match=0.0, handle: Optional[Handle] = None):
+    """detection() (ICP/detection.h:9-11): returns (T_final, R_final); raises on a rect outside the image
+    (the reference throws a cv::Exception there, detection.cpp:43-44)."""
+    r = (handle or _handle()).detection_batch(depImg_ref_raw, tCamIntrinsic, [depImg_model_raw], [rect_model_final], [rect_ref_final],
+                                              [r_match], [t_match], icp_it_thr, dist_mean_thr, dist_diff_thr)[0]
+    if r["status"] != FL_OK:
+        raise FealessError(int(r["status"]), "detection", "rect outside the image")
+    return r["T"].copy(), r["R"].reshape(3, 3).copy()
+
+
+def nonMaximumSuppression(objs: List[dict], th_obj_dist: float, handle: Optional[Handle] = None) -> List[dict]:
+    """objs: dicts with match_class, match_sim, r, t, pts_model (array or count), icp_dist; sets 'check_done' like the
+    reference mutates obj_data, returns the emitted pose results (object id, confidence, R, T)."""
+    if not objs:
+        return []
+    t3 = np.array([np.asarray(o["t"], np.float32).reshape(3) for o in objs], np.float32)
+    nm = [int(o["pts_model"]) if np.isscalar(o["pts_model"]) else len(o["pts_model"]) for o in objs]
+    idx = (handle or _handle()).nms(t3, nm, [o["icp_dist"] for o in objs], th_obj_dist)
+    return [dict(object_id=objs[i]["match_class"], confidence=objs[i]["match_sim"], R=objs[i]["r"], T=objs[i]["t"], index=int(i)) for i in idx]

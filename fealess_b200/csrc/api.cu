@@ -1,0 +1,618 @@
+// C ABI of fealess_b200 (include/fealess_b200.h): handle lifecycle, device workspaces, and the orchestration of the
+// kernels in frontend.cu / similarity.cu / icp.cu on the handle's stream.  CUDA only - there is no CPU path here.
+#include "fl_internal.cuh"
+#include <stdarg.h>
+#include <string.h>
+#include <algorithm>
+#include <new>
+#include <vector>
+
+int fl_launch_sort_unique_big(fl_sort_key* keys, int key_cap, int n_live, fl_match_t* d_out, int out_cap, int* d_out_count, cudaStream_t s);
+
+static thread_local char g_err[512] = "";
+void fl_set_error(const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
+}
+extern "C" const char* fl_last_error(void) { return g_err; }
+extern "C" const char* fl_version(void) { return "fealess_b200 0.1 (sm_100a)"; }
+
+#define FETCH_FIRST 1024   // matches copied back together with the count in the common case
+
+struct fl_handle {
+  fl_params_t p;
+  cudaStream_t stream;
+  int64_t launches;
+  // template database
+  int n_templates, n_features, n_classes;
+  fl_template_hdr_t* d_hdr; fl_feature_t* d_feat; int32_t* d_class_of; int32_t* d_class_first; uint8_t* d_class_enabled;
+  fl_pfeat* d_pfeat;
+  std::vector<int32_t> class_first_h, class_of_h;
+  std::vector<float> pose13_h;
+  std::vector<uint8_t> class_enabled_h;
+  // geometry of the last frame
+  int gW, gH; bool packed;
+  fl_level_geom geom[FL_MAX_LEVELS]; fl_level_geom* d_geom;
+  // frame-sized buffers
+  uint8_t* d_in_bgr; uint16_t* d_in_depth;                 // staging for host-input calls
+  uint8_t* d_bgr[FL_MAX_LEVELS];                           // colour pyramid, levels >= 1
+  uint8_t* d_q[FL_MAX_LEVELS][FL_MAX_MODALITIES];          // quantised images (unmasked)
+  uint8_t* d_qm[FL_MAX_LEVELS][FL_MAX_MODALITIES];         // masked copies (allocated on first use)
+  uint8_t* d_mask[FL_MAX_LEVELS][FL_MAX_MODALITIES];
+  uint8_t* d_spread[FL_MAX_LEVELS][FL_MAX_MODALITIES];     // debug only
+  uint8_t* d_lm[FL_MAX_LEVELS]; size_t lm_bytes[FL_MAX_LEVELS];
+  bool used_mask[FL_MAX_MODALITIES]; bool keep_spread;
+  // candidates / matches
+  fl_match_t* d_cand; int* d_count; fl_sort_key* d_keys; int key_cap; fl_match_t* d_out; int* d_out_count;
+  // pinned host staging
+  uint8_t* h_bgr; uint16_t* h_depth; uint8_t* h_mask; int* h_small; fl_match_t* h_first; uint8_t* h_class_enabled;
+  bool have_result;
+  // profiling
+  bool profile; cudaEvent_t ev[5]; float stage_ms[4];
+  // ICP workspace (grown on demand)
+  int icp_hyp_cap, icp_pts_cap;
+  fl_icp_ws icp; fl_icp_hyp* d_hyps; float* d_t_init; fl_icp_result_t* d_results; uint16_t* d_model_crops; uint16_t* d_ref_depth;
+  size_t ref_depth_cap;
+  uint16_t* h_model_crops; fl_icp_hyp* h_hyps; fl_icp_result_t* h_results; size_t h_crop_cap;
+};
+
+template <typename T> static int dalloc(T** p, size_t n) {
+  *p = nullptr;
+  if (n == 0) n = 1;
+  FL_CUDA(cudaMalloc((void**)p, n * sizeof(T)));
+  return FL_OK;
+}
+template <typename T> static int halloc(T** p, size_t n) {
+  *p = nullptr;
+  if (n == 0) n = 1;
+  FL_CUDA(cudaMallocHost((void**)p, n * sizeof(T)));
+  return FL_OK;
+}
+#define TRY(x) do { int rc__ = (x); if (rc__ != FL_OK) return rc__; } while (0)
+
+extern "C" void fl_default_params(fl_params_t* p) {
+  memset(p, 0, sizeof *p);
+  p->n_levels = 2; p->T[0] = 5; p->T[1] = 8;                                   // T_DEFAULTS, linemod.cpp:1820
+  p->n_modalities = 2; p->modality_kind[0] = FL_MODALITY_COLOR_GRADIENT; p->modality_kind[1] = FL_MODALITY_DEPTH_NORMAL;
+  p->weak_threshold = 10.0f; p->distance_threshold = 2000; p->difference_threshold = 50;
+  p->max_width = 640; p->max_height = 480; p->max_candidates = 1 << 16; p->device = 0;
+}
+
+static size_t level_lm_bytes(const fl_params_t& p, int l, int W, int H, fl_level_geom* g) {
+  fl_level_geom gg;
+  gg.W = W >> l; gg.H = H >> l; gg.T = p.T[l];
+  gg.Wd = gg.W / gg.T; gg.Hd = gg.H / gg.T; gg.cells = gg.Wd * gg.Hd;
+  size_t ls = (size_t)gg.T * gg.T * gg.cells + FL_LM_PAD;
+  gg.label_stride = (ls + 15) & ~(size_t)15;
+  gg.mod_stride = gg.label_stride * 8;
+  if (g) *g = gg;
+  return gg.mod_stride * p.n_modalities;
+}
+
+extern "C" int fl_create(const fl_params_t* params, fl_handle** out) {
+  if (!params || !out) return FL_ERR_ARG;
+  *out = nullptr;
+  const fl_params_t& p = *params;
+  if (p.n_levels < 1 || p.n_levels > FL_MAX_LEVELS || p.n_modalities < 1 || p.n_modalities > FL_MAX_MODALITIES) return FL_ERR_ARG;
+  for (int l = 0; l < p.n_levels; ++l) if (p.T[l] < 1 || p.T[l] > FL_MAX_T) return FL_ERR_ARG;
+  for (int m = 0; m < p.n_modalities; ++m) if (p.modality_kind[m] != FL_MODALITY_COLOR_GRADIENT && p.modality_kind[m] != FL_MODALITY_DEPTH_NORMAL) return FL_ERR_ARG;
+  if (p.max_width < 16 || p.max_height < 16 || p.max_candidates < 1) return FL_ERR_ARG;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0 || p.device < 0 || p.device >= ndev) {
+    fl_set_error("no usable CUDA device (count=%d, requested %d): %s", ndev, p.device, cudaGetErrorString(e));
+    return FL_ERR_CUDA;
+  }
+  FL_CUDA(cudaSetDevice(p.device));
+  fl_handle* h = new (std::nothrow) fl_handle();
+  if (!h) return FL_ERR_ARG;
+  h->p = p; h->launches = 0; h->gW = h->gH = 0; h->packed = false; h->have_result = false; h->profile = false; h->keep_spread = false;
+  h->n_templates = h->n_features = h->n_classes = 0;
+  h->d_hdr = nullptr; h->d_feat = nullptr; h->d_class_of = nullptr; h->d_class_first = nullptr; h->d_class_enabled = nullptr; h->d_pfeat = nullptr;
+  h->icp_hyp_cap = h->icp_pts_cap = 0; memset(&h->icp, 0, sizeof h->icp);
+  h->d_hyps = nullptr; h->d_t_init = nullptr; h->d_results = nullptr; h->d_model_crops = nullptr; h->d_ref_depth = nullptr; h->ref_depth_cap = 0;
+  h->h_model_crops = nullptr; h->h_hyps = nullptr; h->h_results = nullptr; h->h_crop_cap = 0;
+  memset(h->d_bgr, 0, sizeof h->d_bgr); memset(h->d_q, 0, sizeof h->d_q); memset(h->d_qm, 0, sizeof h->d_qm);
+  memset(h->d_mask, 0, sizeof h->d_mask); memset(h->d_spread, 0, sizeof h->d_spread); memset(h->d_lm, 0, sizeof h->d_lm);
+  memset(h->used_mask, 0, sizeof h->used_mask); memset(h->stage_ms, 0, sizeof h->stage_ms);
+  *out = h;
+  FL_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 5; ++i) FL_CUDA(cudaEventCreate(&h->ev[i]));
+  TRY(fl_launch_tables_init());
+  const size_t npx = (size_t)p.max_width * p.max_height;
+  TRY(dalloc(&h->d_in_bgr, npx * 3)); TRY(dalloc(&h->d_in_depth, npx));
+  TRY(dalloc(&h->d_geom, FL_MAX_LEVELS));
+  for (int l = 0; l < p.n_levels; ++l) {
+    size_t n = (size_t)(p.max_width >> l) * (p.max_height >> l);
+    if (l > 0) TRY(dalloc(&h->d_bgr[l], n * 3));
+    for (int m = 0; m < p.n_modalities; ++m) TRY(dalloc(&h->d_q[l][m], n));
+    // linear memories: T need not divide the maximum size, so bound the cell count from above
+    int T = p.T[l];
+    size_t cells = (size_t)(((p.max_width >> l) + T - 1) / T) * (((p.max_height >> l) + T - 1) / T);
+    size_t ls = (((size_t)T * T * cells + FL_LM_PAD) + 15) & ~(size_t)15;
+    h->lm_bytes[l] = ls * 8 * p.n_modalities + 64;
+    TRY(dalloc(&h->d_lm[l], h->lm_bytes[l]));
+  }
+  TRY(dalloc(&h->d_cand, (size_t)p.max_candidates)); TRY(dalloc(&h->d_count, 4));
+  int kc = 2; while (kc < p.max_candidates) kc <<= 1;
+  h->key_cap = kc;
+  TRY(dalloc(&h->d_keys, (size_t)kc + 1));      // + room for the two scratch ints behind the keys
+  TRY(dalloc(&h->d_out, (size_t)p.max_candidates)); TRY(dalloc(&h->d_out_count, 4));
+  TRY(halloc(&h->h_bgr, npx * 3)); TRY(halloc(&h->h_depth, npx)); TRY(halloc(&h->h_mask, npx * p.n_modalities));
+  TRY(halloc(&h->h_small, 16)); TRY(halloc(&h->h_first, FETCH_FIRST)); TRY(halloc(&h->h_class_enabled, 4096));
+  return FL_OK;
+}
+
+static void icp_free(fl_handle* h) {
+  cudaFree(h->icp.pts_ref); cudaFree(h->icp.pts_mod); cudaFree(h->icp.cor_m); cudaFree(h->icp.cor_r); cudaFree(h->icp.dist);
+  cudaFree(h->icp.grid_pts); cudaFree(h->icp.cell_start); cudaFree(h->icp.n_ref); cudaFree(h->icp.n_mod);
+  cudaFree(h->d_hyps); cudaFree(h->d_t_init); cudaFree(h->d_results); cudaFree(h->d_model_crops);
+  cudaFreeHost(h->h_model_crops); cudaFreeHost(h->h_hyps); cudaFreeHost(h->h_results);
+  memset(&h->icp, 0, sizeof h->icp);
+  h->d_hyps = nullptr; h->d_t_init = nullptr; h->d_results = nullptr; h->d_model_crops = nullptr;
+  h->h_model_crops = nullptr; h->h_hyps = nullptr; h->h_results = nullptr; h->h_crop_cap = 0;
+  h->icp_hyp_cap = h->icp_pts_cap = 0;
+}
+
+static void free_templates(fl_handle* h) {
+  cudaFree(h->d_hdr); cudaFree(h->d_feat); cudaFree(h->d_class_of); cudaFree(h->d_class_first); cudaFree(h->d_class_enabled); cudaFree(h->d_pfeat);
+  h->d_hdr = nullptr; h->d_feat = nullptr; h->d_class_of = nullptr; h->d_class_first = nullptr; h->d_class_enabled = nullptr; h->d_pfeat = nullptr;
+  h->n_templates = h->n_features = h->n_classes = 0; h->packed = false;
+}
+
+extern "C" int fl_destroy(fl_handle* h) {
+  if (!h) return FL_OK;
+  cudaSetDevice(h->p.device);
+  cudaStreamSynchronize(h->stream);
+  free_templates(h); icp_free(h);
+  cudaFree(h->d_ref_depth);
+  cudaFree(h->d_in_bgr); cudaFree(h->d_in_depth); cudaFree(h->d_geom);
+  for (int l = 0; l < FL_MAX_LEVELS; ++l) {
+    cudaFree(h->d_bgr[l]); cudaFree(h->d_lm[l]);
+    for (int m = 0; m < FL_MAX_MODALITIES; ++m) { cudaFree(h->d_q[l][m]); cudaFree(h->d_qm[l][m]); cudaFree(h->d_mask[l][m]); cudaFree(h->d_spread[l][m]); }
+  }
+  cudaFree(h->d_cand); cudaFree(h->d_count); cudaFree(h->d_keys); cudaFree(h->d_out); cudaFree(h->d_out_count);
+  cudaFreeHost(h->h_bgr); cudaFreeHost(h->h_depth); cudaFreeHost(h->h_mask); cudaFreeHost(h->h_small); cudaFreeHost(h->h_first); cudaFreeHost(h->h_class_enabled);
+  for (int i = 0; i < 5; ++i) cudaEventDestroy(h->ev[i]);
+  cudaStreamDestroy(h->stream);
+  delete h;
+  return FL_OK;
+}
+
+extern "C" int fl_sync(fl_handle* h) { if (!h) return FL_ERR_ARG; FL_CUDA(cudaStreamSynchronize(h->stream)); return FL_OK; }
+extern "C" void* fl_stream(fl_handle* h) { return h ? (void*)h->stream : nullptr; }
+extern "C" int64_t fl_launch_count(fl_handle* h) { return h ? h->launches : 0; }
+extern "C" int fl_profile(fl_handle* h, int enable) { if (!h) return FL_ERR_ARG; h->profile = enable != 0; return FL_OK; }
+extern "C" int fl_last_stage_ms(fl_handle* h, float out4[4]) { if (!h || !out4) return FL_ERR_ARG; memcpy(out4, h->stage_ms, sizeof h->stage_ms); return FL_OK; }
+extern "C" int fl_debug_keep_spread(fl_handle* h, int enable) { if (!h) return FL_ERR_ARG; h->keep_spread = enable != 0; return FL_OK; }
+extern "C" int fl_num_templates(fl_handle* h) { return h ? h->n_templates : FL_ERR_ARG; }
+
+// ---------------------------------------------------------------------------------------------------
+extern "C" int fl_upload_templates(fl_handle* h, int32_t n_templates, const fl_template_hdr_t* headers, const fl_feature_t* features,
+                                   int32_t n_features, const int32_t* class_of, const float* pose13) {
+  if (!h || n_templates < 0 || n_features < 0 || (n_templates > 0 && (!headers || !class_of)) || (n_features > 0 && !features)) return FL_ERR_ARG;
+  FL_CUDA(cudaSetDevice(h->p.device));
+  const int L = h->p.n_levels, M = h->p.n_modalities;
+  const size_t ne = (size_t)n_templates * L * M;
+  int nc = 0;
+  for (int t = 0; t < n_templates; ++t) { if (class_of[t] < 0) return FL_ERR_ARG; nc = std::max(nc, class_of[t] + 1); }
+  if (nc > 4096) return FL_ERR_ARG;
+  std::vector<int32_t> first(nc, -1);
+  for (int t = 0; t < n_templates; ++t) {
+    int c = class_of[t];
+    if (first[c] < 0) first[c] = t; else if (class_of[t - 1] != c) { fl_set_error("templates of class %d are not contiguous", c); return FL_ERR_ARG; }
+  }
+  for (size_t e = 0; e < ne; ++e) {
+    const fl_template_hdr_t& hd = headers[e];
+    if (hd.feature_begin < 0 || hd.feature_count < 0 || (int64_t)hd.feature_begin + hd.feature_count > n_features) return FL_ERR_ARG;
+    if (hd.feature_count > 63) return FL_ERR_FEATURES;                          // CV_Assert(features.size() <= 63)
+    for (int k = 0; k < hd.feature_count; ++k) { int lab = features[hd.feature_begin + k].label; if (lab < 0 || lab > 7) return FL_ERR_ARG; }
+  }
+  FL_CUDA(cudaStreamSynchronize(h->stream));
+  free_templates(h);
+  TRY(dalloc(&h->d_hdr, ne)); TRY(dalloc(&h->d_feat, (size_t)n_features)); TRY(dalloc(&h->d_class_of, (size_t)n_templates));
+  TRY(dalloc(&h->d_class_first, (size_t)nc)); TRY(dalloc(&h->d_class_enabled, (size_t)std::max(nc, 1))); TRY(dalloc(&h->d_pfeat, (size_t)n_features));
+  if (ne) FL_CUDA(cudaMemcpy(h->d_hdr, headers, ne * sizeof(fl_template_hdr_t), cudaMemcpyHostToDevice));
+  if (n_features) FL_CUDA(cudaMemcpy(h->d_feat, features, (size_t)n_features * sizeof(fl_feature_t), cudaMemcpyHostToDevice));
+  if (n_templates) FL_CUDA(cudaMemcpy(h->d_class_of, class_of, (size_t)n_templates * sizeof(int32_t), cudaMemcpyHostToDevice));
+  if (nc) FL_CUDA(cudaMemcpy(h->d_class_first, first.data(), (size_t)nc * sizeof(int32_t), cudaMemcpyHostToDevice));
+  h->n_templates = n_templates; h->n_features = n_features; h->n_classes = nc;
+  h->class_first_h = first; h->class_of_h.assign(class_of, class_of + n_templates);
+  h->pose13_h.clear();
+  if (pose13) h->pose13_h.assign(pose13, pose13 + (size_t)n_templates * 13);
+  h->class_enabled_h.assign((size_t)std::max(nc, 1), 1);
+  h->packed = false;
+  return FL_OK;
+}
+
+extern "C" int fl_get_pose_info(fl_handle* h, int32_t class_idx, int32_t template_id, float out13[13]) {
+  if (!h || !out13 || class_idx < 0 || class_idx >= h->n_classes || h->pose13_h.empty()) return FL_ERR_ARG;
+  // the reference keeps ONE flat TemplatePoseInfo indexed by the per-class template_id (linemod.cpp:1624-1634), which is
+  // wrong for more than one class (SURVEY A.6 iv); this ABI keys the pose by (class, template_id).
+  int t = h->class_first_h[class_idx] + template_id;
+  if (template_id < 0 || t >= h->n_templates || h->class_of_h[t] != class_idx) return FL_ERR_ARG;
+  memcpy(out13, &h->pose13_h[(size_t)t * 13], 13 * sizeof(float));
+  return FL_OK;
+}
+
+static fl_tdb make_tdb(fl_handle* h) {
+  fl_tdb db;
+  db.n_templates = h->n_templates; db.L = h->p.n_levels; db.M = h->p.n_modalities; db.n_classes = h->n_classes;
+  db.hdr = h->d_hdr; db.feat = h->d_feat; db.class_of = h->d_class_of; db.class_first = h->d_class_first;
+  db.class_enabled = h->d_class_enabled; db.pfeat = h->d_pfeat;
+  return db;
+}
+
+static int ensure_geometry(fl_handle* h, int W, int H) {
+  const fl_params_t& p = h->p;
+  if (W <= 0 || H <= 0 || W > p.max_width || H > p.max_height) { fl_set_error("frame %dx%d exceeds handle capacity %dx%d", W, H, p.max_width, p.max_height); return FL_ERR_SIZE; }
+  for (int l = 0; l < p.n_levels; ++l) {                                        // CV_Asserts :981, :1062-1063
+    int w = W >> l, hh = H >> l, T = p.T[l];
+    if (w < 1 || hh < 1 || w % T || hh % T || (w * hh) % 16) return FL_ERR_GEOMETRY;
+  }
+  if (W != h->gW || H != h->gH) {
+    for (int l = 0; l < p.n_levels; ++l) {
+      size_t need = level_lm_bytes(p, l, W, H, &h->geom[l]);
+      if (need > h->lm_bytes[l]) { fl_set_error("internal: LM capacity"); return FL_ERR_CAPACITY; }
+      FL_CUDA(cudaMemsetAsync(h->d_lm[l], 0, h->lm_bytes[l], h->stream));       // pads must read as zero
+    }
+    FL_CUDA(cudaMemcpyAsync(h->d_geom, h->geom, sizeof(fl_level_geom) * p.n_levels, cudaMemcpyHostToDevice, h->stream));
+    FL_CUDA(cudaStreamSynchronize(h->stream));                                  // h->geom is pageable
+    h->gW = W; h->gH = H; h->packed = false;
+  }
+  if (!h->packed && h->n_templates > 0) {
+    fl_launch_pack_features(make_tdb(h), h->d_geom, h->n_features, h->stream); ++h->launches;
+    h->packed = true;
+  }
+  return FL_OK;
+}
+
+// front end + matchClass on the handle's templates; candidates land in (cand, count)
+static int run_match_stages(fl_handle* h, const uint8_t* d_bgr, const uint16_t* d_depth, int W, int H, const void* const* d_masks,
+                            float threshold, const int32_t* class_filter, int n_filter, fl_match_t* cand, int cap, int* d_count) {
+  const fl_params_t& p = h->p;
+  FL_CUDA(cudaSetDevice(p.device));
+  TRY(ensure_geometry(h, W, H));
+  cudaStream_t s = h->stream;
+  for (int m = 0; m < p.n_modalities; ++m) {
+    if (p.modality_kind[m] == FL_MODALITY_COLOR_GRADIENT && !d_bgr) return FL_ERR_SIZE;
+    if (p.modality_kind[m] == FL_MODALITY_DEPTH_NORMAL && !d_depth) return FL_ERR_SIZE;
+  }
+  // class filter (Detector::match :1418-1434): unknown ids are ignored, empty = all
+  if (h->n_classes > 0) {
+    for (int c = 0; c < h->n_classes; ++c) h->h_class_enabled[c] = (n_filter > 0 && class_filter) ? 0 : 1;
+    if (n_filter > 0 && class_filter) for (int k = 0; k < n_filter; ++k) if (class_filter[k] >= 0 && class_filter[k] < h->n_classes) h->h_class_enabled[class_filter[k]] = 1;
+    FL_CUDA(cudaMemcpyAsync(h->d_class_enabled, h->h_class_enabled, (size_t)h->n_classes, cudaMemcpyHostToDevice, s));
+  }
+  if (h->profile) cudaEventRecord(h->ev[0], s);
+  const float thr_sq = p.weak_threshold * p.weak_threshold;
+  bool color_pyr_done = false;
+  for (int l = 0; l < p.n_levels; ++l) {
+    const fl_level_geom& g = h->geom[l];
+    const size_t npx = (size_t)g.W * g.H;
+    for (int m = 0; m < p.n_modalities; ++m) {
+      const bool has_mask = d_masks && d_masks[m];
+      h->used_mask[m] = has_mask;
+      if (p.modality_kind[m] == FL_MODALITY_COLOR_GRADIENT) {
+        const uint8_t* src = d_bgr;
+        if (l > 0) {
+          if (!color_pyr_done) {                                                // one colour pyramid shared by all colour modalities
+            const uint8_t* prev = l == 1 ? d_bgr : h->d_bgr[l - 1];
+            fl_launch_pyrdown_bgr(prev, h->geom[l - 1].W, h->geom[l - 1].H, h->d_bgr[l], s); ++h->launches;
+            color_pyr_done = true;
+          }
+          src = h->d_bgr[l];
+        }
+        fl_launch_color_quantize(src, g.W, g.H, thr_sq, h->d_q[l][m], s); ++h->launches;
+      } else {
+        if (l == 0) { fl_launch_depth_quantize(d_depth, g.W, g.H, p.distance_threshold, p.difference_threshold, h->d_q[0][m], s); ++h->launches; }
+        else { fl_launch_resize_nn_half(h->d_q[l - 1][m], h->geom[l - 1].W, h->geom[l - 1].H, h->d_q[l][m], s); ++h->launches; }
+      }
+      const uint8_t* qsrc = h->d_q[l][m];
+      if (has_mask) {
+        if (!h->d_mask[l][m]) { size_t n = (size_t)(p.max_width >> l) * (p.max_height >> l); TRY(dalloc(&h->d_mask[l][m], n)); TRY(dalloc(&h->d_qm[l][m], n)); }
+        const uint8_t* mk = (const uint8_t*)d_masks[m];
+        if (l > 0) { fl_launch_resize_nn_half(l == 1 ? (const uint8_t*)d_masks[m] : h->d_mask[l - 1][m], h->geom[l - 1].W, h->geom[l - 1].H, h->d_mask[l][m], s); ++h->launches; mk = h->d_mask[l][m]; }
+        fl_launch_apply_mask(h->d_q[l][m], mk, (int)npx, h->d_qm[l][m], s); ++h->launches;
+        qsrc = h->d_qm[l][m];
+      }
+      uint8_t* spread = nullptr;
+      if (h->keep_spread) { if (!h->d_spread[l][m]) TRY(dalloc(&h->d_spread[l][m], (size_t)(p.max_width >> l) * (p.max_height >> l))); spread = h->d_spread[l][m]; }
+      fl_launch_spread_lm(qsrc, g, h->d_lm[l] + (size_t)m * g.mod_stride, spread, s); ++h->launches;
+    }
+    color_pyr_done = false;
+  }
+  if (h->profile) cudaEventRecord(h->ev[1], s);
+  FL_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), s));
+  if (h->n_templates > 0) {
+    fl_tdb db = make_tdb(h);
+    const int lowest = p.n_levels - 1;
+    fl_launch_similarity_global(db, h->geom[lowest], h->d_lm[lowest], threshold, cand, cap, d_count, s); ++h->launches;
+    if (h->profile) cudaEventRecord(h->ev[2], s);
+    for (int l = p.n_levels - 2; l >= 0; --l) { fl_launch_refine_level(db, h->geom[l], l, h->d_lm[l], threshold, cand, cap, d_count, s); ++h->launches; }
+  } else if (h->profile) cudaEventRecord(h->ev[2], s);
+  if (h->profile) cudaEventRecord(h->ev[3], s);
+  FL_CUDA(cudaGetLastError());
+  return FL_OK;
+}
+
+// sort + unique of candidate lists into (d_out, d_out_count); handles the rare > 2048 path; leaves h_small = {count, n_live, flag}
+static int run_sort_unique(fl_handle* h, const fl_match_t* d_in, int n_lists, int list_cap, const int* d_n_in, fl_match_t* d_out, int out_cap,
+                           int* d_out_count, bool fetch_first) {
+  cudaStream_t s = h->stream;
+  if ((int64_t)n_lists * list_cap > h->key_cap) { fl_set_error("sort capacity %d < %lld", h->key_cap, (long long)n_lists * list_cap); return FL_ERR_CAPACITY; }
+  h->launches += fl_launch_sort_unique(d_in, n_lists, list_cap, d_n_in, h->d_keys, h->key_cap, d_out, out_cap, d_out_count, s);
+  int* d_scratch = reinterpret_cast<int*>(h->d_keys + h->key_cap);
+  FL_CUDA(cudaMemcpyAsync(h->h_small + 1, d_scratch, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  FL_CUDA(cudaMemcpyAsync(h->h_small, d_out_count, sizeof(int), cudaMemcpyDeviceToHost, s));
+  if (fetch_first) FL_CUDA(cudaMemcpyAsync(h->h_first, d_out, sizeof(fl_match_t) * std::min(FETCH_FIRST, out_cap), cudaMemcpyDeviceToHost, s));
+  if (h->profile) cudaEventRecord(h->ev[4], s);
+  FL_CUDA(cudaStreamSynchronize(s));
+  if (h->h_small[2]) {                                                          // more than 2048 live candidates: multi-kernel sort
+    int rc = fl_launch_sort_unique_big(h->d_keys, h->key_cap, std::min(h->h_small[1], h->key_cap), d_out, out_cap, d_out_count, s);
+    if (rc < 0) return FL_ERR_CAPACITY;
+    h->launches += rc;
+    FL_CUDA(cudaMemcpyAsync(h->h_small, d_out_count, sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (fetch_first) FL_CUDA(cudaMemcpyAsync(h->h_first, d_out, sizeof(fl_match_t) * std::min(FETCH_FIRST, out_cap), cudaMemcpyDeviceToHost, s));
+    if (h->profile) cudaEventRecord(h->ev[4], s);
+    FL_CUDA(cudaStreamSynchronize(s));
+  }
+  if (h->profile) for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&h->stage_ms[i], h->ev[i], h->ev[i + 1]);
+  FL_CUDA(cudaGetLastError());
+  return FL_OK;
+}
+
+extern "C" int fl_match_device(fl_handle* h, const void* d_bgr, const void* d_depth, int32_t W, int32_t H, const void* const* d_masks,
+                               float threshold, const int32_t* class_filter, int32_t n_filter) {
+  if (!h) return FL_ERR_ARG;
+  h->have_result = false;
+  TRY(run_match_stages(h, (const uint8_t*)d_bgr, (const uint16_t*)d_depth, W, H, d_masks, threshold, class_filter, n_filter, h->d_cand,
+                       h->p.max_candidates, h->d_count));
+  TRY(run_sort_unique(h, h->d_cand, 1, h->p.max_candidates, h->d_count, h->d_out, h->p.max_candidates, h->d_out_count, true));
+  h->have_result = true;
+  return FL_OK;
+}
+
+extern "C" int fl_match_fetch(fl_handle* h, fl_match_t* out, int32_t capacity, int32_t* count) {
+  if (!h || !count || capacity < 0 || (capacity > 0 && !out)) return FL_ERR_ARG;
+  if (!h->have_result) return FL_ERR_STATE;
+  const int n = h->h_small[0];
+  *count = n;
+  const int ncopy = std::min(std::min(n, (int)capacity), h->p.max_candidates);
+  const int nfirst = std::min(ncopy, FETCH_FIRST);
+  if (nfirst > 0) memcpy(out, h->h_first, sizeof(fl_match_t) * nfirst);
+  if (ncopy > nfirst) {
+    FL_CUDA(cudaMemcpyAsync(out + nfirst, h->d_out + nfirst, sizeof(fl_match_t) * (size_t)(ncopy - nfirst), cudaMemcpyDeviceToHost, h->stream));
+    FL_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  return (n > capacity || n > h->p.max_candidates) ? FL_ERR_CAPACITY : FL_OK;
+}
+
+extern "C" int fl_match(fl_handle* h, const uint8_t* bgr, size_t bgr_stride, const uint16_t* depth, size_t depth_stride, int32_t W, int32_t H,
+                        const uint8_t* const* masks, float threshold, const int32_t* class_filter, int32_t n_filter, fl_match_t* out,
+                        int32_t capacity, int32_t* count, uint8_t* const* quantized_out) {
+  if (!h || !count) return FL_ERR_ARG;
+  *count = 0;
+  const fl_params_t& p = h->p;
+  if (W <= 0 || H <= 0 || W > p.max_width || H > p.max_height) return FL_ERR_SIZE;
+  FL_CUDA(cudaSetDevice(p.device));
+  cudaStream_t s = h->stream;
+  const uint8_t* d_bgr = nullptr; const uint16_t* d_depth = nullptr;
+  if (bgr) {
+    if (bgr_stride < (size_t)W * 3) return FL_ERR_SIZE;
+    for (int y = 0; y < H; ++y) memcpy(h->h_bgr + (size_t)y * W * 3, bgr + (size_t)y * bgr_stride, (size_t)W * 3);
+    FL_CUDA(cudaMemcpyAsync(h->d_in_bgr, h->h_bgr, (size_t)W * H * 3, cudaMemcpyHostToDevice, s));
+    d_bgr = h->d_in_bgr;
+  }
+  if (depth) {
+    if (depth_stride < (size_t)W * 2) return FL_ERR_SIZE;
+    for (int y = 0; y < H; ++y) memcpy(h->h_depth + (size_t)y * W, (const uint8_t*)depth + (size_t)y * depth_stride, (size_t)W * 2);
+    FL_CUDA(cudaMemcpyAsync(h->d_in_depth, h->h_depth, (size_t)W * H * 2, cudaMemcpyHostToDevice, s));
+    d_depth = h->d_in_depth;
+  }
+  const void* d_masks[FL_MAX_MODALITIES] = {nullptr, nullptr, nullptr, nullptr};
+  bool any_mask = false;
+  if (masks) for (int m = 0; m < p.n_modalities; ++m) if (masks[m]) {
+    if (!h->d_mask[0][m]) { size_t n = (size_t)p.max_width * p.max_height; TRY(dalloc(&h->d_mask[0][m], n)); TRY(dalloc(&h->d_qm[0][m], n)); }
+    memcpy(h->h_mask + (size_t)m * W * H, masks[m], (size_t)W * H);
+    FL_CUDA(cudaMemcpyAsync(h->d_mask[0][m], h->h_mask + (size_t)m * W * H, (size_t)W * H, cudaMemcpyHostToDevice, s));
+    d_masks[m] = h->d_mask[0][m]; any_mask = true;
+  }
+  int rc = fl_match_device(h, d_bgr, d_depth, W, H, any_mask ? d_masks : nullptr, threshold, class_filter, n_filter);
+  if (rc != FL_OK) return rc;
+  rc = fl_match_fetch(h, out, capacity, count);
+  if (quantized_out) {
+    for (int l = 0; l < p.n_levels; ++l) for (int m = 0; m < p.n_modalities; ++m) {
+      uint8_t* dst = quantized_out[l * p.n_modalities + m];
+      if (!dst) continue;
+      const uint8_t* src = h->used_mask[m] ? h->d_qm[l][m] : h->d_q[l][m];
+      FL_CUDA(cudaMemcpyAsync(dst, src, (size_t)h->geom[l].W * h->geom[l].H, cudaMemcpyDeviceToHost, s));
+    }
+    FL_CUDA(cudaStreamSynchronize(s));
+  }
+  return rc;
+}
+
+extern "C" int fl_match_shard_device(fl_handle* h, const void* d_bgr, const void* d_depth, int32_t W, int32_t H, const void* const* d_masks,
+                                     float threshold, const int32_t* class_filter, int32_t n_filter, fl_match_t* d_candidates,
+                                     int32_t capacity, int32_t* d_count) {
+  if (!h || !d_candidates || !d_count || capacity < 1) return FL_ERR_ARG;
+  return run_match_stages(h, (const uint8_t*)d_bgr, (const uint16_t*)d_depth, W, H, d_masks, threshold, class_filter, n_filter, d_candidates,
+                          capacity, d_count);
+}
+
+extern "C" int fl_sort_unique_device(fl_handle* h, const fl_match_t* d_in, int32_t n_lists, int32_t list_capacity, const int32_t* d_n_in,
+                                     fl_match_t* d_out, int32_t out_capacity, int32_t* d_out_count) {
+  if (!h || !d_in || !d_n_in || !d_out || !d_out_count || n_lists < 1 || list_capacity < 1 || out_capacity < 1) return FL_ERR_ARG;
+  FL_CUDA(cudaSetDevice(h->p.device));
+  return run_sort_unique(h, d_in, n_lists, list_capacity, d_n_in, d_out, out_capacity, d_out_count, false);
+}
+
+// ---------------------------------------------------------------------------------------------------
+extern "C" int fl_debug_get(fl_handle* h, int what, int32_t a, int32_t b, int32_t c, void* host_out, size_t bytes) {
+  if (!h || !host_out) return FL_ERR_ARG;
+  if (h->gW == 0) return FL_ERR_STATE;
+  const fl_params_t& p = h->p;
+  FL_CUDA(cudaSetDevice(p.device));
+  FL_CUDA(cudaStreamSynchronize(h->stream));
+  if (what == FL_DBG_QUANTIZED || what == FL_DBG_SPREAD) {
+    if (a < 0 || a >= p.n_levels || b < 0 || b >= p.n_modalities) return FL_ERR_ARG;
+    size_t n = (size_t)h->geom[a].W * h->geom[a].H;
+    if (bytes < n) return FL_ERR_CAPACITY;
+    const uint8_t* src = what == FL_DBG_SPREAD ? h->d_spread[a][b] : (h->used_mask[b] ? h->d_qm[a][b] : h->d_q[a][b]);
+    if (!src) return FL_ERR_STATE;
+    FL_CUDA(cudaMemcpy(host_out, src, n, cudaMemcpyDeviceToHost));
+    return FL_OK;
+  }
+  if (what == FL_DBG_LINEAR_MEMORY) {
+    if (a < 0 || a >= p.n_levels || b < 0 || b >= p.n_modalities || c < 0 || c > 7) return FL_ERR_ARG;
+    const fl_level_geom& g = h->geom[a];
+    size_t n = (size_t)g.T * g.T * g.cells;
+    if (bytes < n) return FL_ERR_CAPACITY;
+    FL_CUDA(cudaMemcpy(host_out, h->d_lm[a] + (size_t)b * g.mod_stride + (size_t)c * g.label_stride, n, cudaMemcpyDeviceToHost));
+    return FL_OK;
+  }
+  if (what == FL_DBG_SIMILARITY) {
+    if (a < 0 || a >= h->n_templates) return FL_ERR_ARG;
+    const fl_level_geom& g = h->geom[p.n_levels - 1];
+    if (bytes < (size_t)g.cells * 2) return FL_ERR_CAPACITY;
+    uint16_t* d_tmp = reinterpret_cast<uint16_t*>(h->d_keys);                   // scratch
+    if ((size_t)g.cells * 2 > (size_t)h->key_cap * sizeof(fl_sort_key)) return FL_ERR_CAPACITY;
+    fl_launch_similarity_debug(make_tdb(h), g, h->d_lm[p.n_levels - 1], a, d_tmp, h->stream); ++h->launches;
+    FL_CUDA(cudaStreamSynchronize(h->stream));
+    FL_CUDA(cudaMemcpy(host_out, d_tmp, (size_t)g.cells * 2, cudaMemcpyDeviceToHost));
+    return FL_OK;
+  }
+  return FL_ERR_ARG;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// ICP
+// ---------------------------------------------------------------------------------------------------
+static int icp_reserve(fl_handle* h, int n_hyp, int max_pts) {
+  if (n_hyp <= h->icp_hyp_cap && max_pts <= h->icp_pts_cap) { h->icp.n_hyp = n_hyp; return FL_OK; }
+  int nh = std::max(n_hyp, h->icp_hyp_cap), np = std::max(max_pts, h->icp_pts_cap);
+  FL_CUDA(cudaStreamSynchronize(h->stream));
+  icp_free(h);
+  size_t tot = (size_t)nh * np;
+  TRY(dalloc(&h->icp.pts_ref, tot * 3)); TRY(dalloc(&h->icp.pts_mod, tot * 3)); TRY(dalloc(&h->icp.cor_m, tot * 3)); TRY(dalloc(&h->icp.cor_r, tot * 3));
+  TRY(dalloc(&h->icp.dist, tot)); TRY(dalloc(&h->icp.grid_pts, tot)); TRY(dalloc(&h->icp.cell_start, (size_t)nh * (FL_ICP_CELLS + 1)));
+  TRY(dalloc(&h->icp.n_ref, (size_t)nh)); TRY(dalloc(&h->icp.n_mod, (size_t)nh));
+  TRY(dalloc(&h->d_hyps, (size_t)nh)); TRY(dalloc(&h->d_t_init, (size_t)nh * 3)); TRY(dalloc(&h->d_results, (size_t)nh)); TRY(dalloc(&h->d_model_crops, tot));
+  TRY(halloc(&h->h_model_crops, tot)); TRY(halloc(&h->h_hyps, (size_t)nh)); TRY(halloc(&h->h_results, (size_t)nh));
+  h->icp_hyp_cap = nh; h->icp_pts_cap = np; h->icp.max_pts = np; h->icp.n_hyp = n_hyp;
+  return FL_OK;
+}
+
+extern "C" int fl_depth_to_3d(fl_handle* h, const uint16_t* depth, size_t depth_stride, int32_t W, int32_t H, fl_intrinsics_t K, float* out3) {
+  if (!h || !depth || !out3 || W <= 0 || H <= 0 || depth_stride < (size_t)W * 2) return FL_ERR_ARG;
+  FL_CUDA(cudaSetDevice(h->p.device));
+  size_t n = (size_t)W * H;
+  uint16_t* d_d = nullptr; float* d_o = nullptr;
+  TRY(dalloc(&d_d, n)); TRY(dalloc(&d_o, n * 3));
+  FL_CUDA(cudaMemcpy2DAsync(d_d, (size_t)W * 2, depth, depth_stride, (size_t)W * 2, H, cudaMemcpyHostToDevice, h->stream));
+  fl_launch_depth_to_3d(d_d, W, H, K, d_o, h->stream); ++h->launches;
+  FL_CUDA(cudaMemcpyAsync(out3, d_o, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  FL_CUDA(cudaStreamSynchronize(h->stream));
+  cudaFree(d_d); cudaFree(d_o);
+  return FL_OK;
+}
+
+extern "C" int fl_icp_cloud_to_cloud_ex(fl_handle* h, const float* pts_ref, int32_t n_ref, const float* pts_model, int32_t n_model,
+                                        fl_icp_params_t prm, fl_icp_result_t* out) {
+  if (!h || !out || n_ref < 0 || n_model < 0 || (n_ref > 0 && !pts_ref) || (n_model > 0 && !pts_model)) return FL_ERR_ARG;
+  if (n_ref >= 3 && n_model >= 3 && n_ref < n_model) { fl_set_error("icpCloudToCloud_Ex walks both clouds in lock step: n_ref (%d) must be >= n_model (%d)", n_ref, n_model); return FL_ERR_SIZE; }
+  FL_CUDA(cudaSetDevice(h->p.device));
+  cudaStream_t s = h->stream;
+  TRY(icp_reserve(h, 1, std::max(std::max(n_ref, n_model), 16)));
+  if (n_ref) FL_CUDA(cudaMemcpyAsync(h->icp.pts_ref, pts_ref, (size_t)n_ref * 12, cudaMemcpyHostToDevice, s));
+  if (n_model) FL_CUDA(cudaMemcpyAsync(h->icp.pts_mod, pts_model, (size_t)n_model * 12, cudaMemcpyHostToDevice, s));
+  FL_CUDA(cudaMemcpyAsync(h->icp.n_ref, &n_ref, 4, cudaMemcpyHostToDevice, s));
+  FL_CUDA(cudaMemcpyAsync(h->icp.n_mod, &n_model, 4, cudaMemcpyHostToDevice, s));
+  FL_CUDA(cudaStreamSynchronize(s));                                            // &n_ref / &n_model are stack addresses
+  fl_launch_icp_run(h->icp, prm, nullptr, nullptr, h->d_results, s); ++h->launches;
+  FL_CUDA(cudaMemcpyAsync(h->h_results, h->d_results, sizeof(fl_icp_result_t), cudaMemcpyDeviceToHost, s));
+  FL_CUDA(cudaStreamSynchronize(s));
+  FL_CUDA(cudaGetLastError());
+  *out = h->h_results[0];
+  return FL_OK;
+}
+
+extern "C" int fl_detection_batch(fl_handle* h, const uint16_t* ref_depth, size_t ref_stride, int32_t W, int32_t H, fl_intrinsics_t K_ref,
+                                  const uint16_t* const* model_depth, const size_t* model_stride, const fl_rect_t* rect_model,
+                                  const fl_rect_t* rect_ref, const float* r_match9, const float* t_match3, const float* d_match, int32_t n,
+                                  fl_icp_params_t prm, fl_icp_result_t* out) {
+  (void)d_match;   // detection() receives d_match but its live branch (test_id == 2) never reads it (detection.cpp:147, 175-178)
+  if (!h || !ref_depth || !model_depth || !model_stride || !rect_model || !rect_ref || !out || n < 0 || W <= 0 || H <= 0 || ref_stride < (size_t)W * 2) return FL_ERR_ARG;
+  if (n == 0) return FL_OK;
+  FL_CUDA(cudaSetDevice(h->p.device));
+  cudaStream_t s = h->stream;
+  int max_pts = 16;
+  std::vector<int> st(n, FL_OK);
+  for (int i = 0; i < n; ++i) {
+    const fl_rect_t& a = rect_model[i]; const fl_rect_t& b = rect_ref[i];
+    bool ok = a.x >= 0 && a.y >= 0 && a.width >= 0 && a.height >= 0 && a.x + a.width <= W && a.y + a.height <= H &&
+              b.x >= 0 && b.y >= 0 && b.width >= 0 && b.height >= 0 && b.x + b.width <= W && b.y + b.height <= H && model_depth[i];
+    if (!ok) { st[i] = FL_ERR_ROI; continue; }                                  // cv::Mat ROI throw (detection.cpp:43-44)
+    max_pts = std::max(max_pts, std::max(a.width * a.height, b.width * b.height));
+  }
+  TRY(icp_reserve(h, n, max_pts));
+  const int mp = h->icp.max_pts;
+  if ((size_t)W * H > h->ref_depth_cap) { cudaFree(h->d_ref_depth); TRY(dalloc(&h->d_ref_depth, (size_t)W * H)); h->ref_depth_cap = (size_t)W * H; }
+  FL_CUDA(cudaMemcpy2DAsync(h->d_ref_depth, (size_t)W * 2, ref_depth, ref_stride, (size_t)W * 2, H, cudaMemcpyHostToDevice, s));
+  for (int i = 0; i < n; ++i) {
+    fl_icp_hyp& hy = h->h_hyps[i];
+    hy.model_depth = h->d_model_crops + (size_t)i * mp;
+    hy.rect_model = rect_model[i]; hy.rect_ref = rect_ref[i]; hy.status = st[i];
+    for (int k = 0; k < 9; ++k) hy.r_match[k] = r_match9 ? r_match9[9 * i + k] : (k % 4 == 0 ? 1.f : 0.f);
+    for (int k = 0; k < 3; ++k) hy.t_match[k] = t_match3 ? t_match3[3 * i + k] : 0.f;
+    if (st[i] != FL_OK) continue;
+    const fl_rect_t& a = rect_model[i];
+    uint16_t* dst = h->h_model_crops + (size_t)i * mp;
+    for (int y = 0; y < a.height; ++y)
+      memcpy(dst + (size_t)y * a.width, (const uint8_t*)model_depth[i] + (size_t)(a.y + y) * model_stride[i] + (size_t)a.x * 2, (size_t)a.width * 2);
+    FL_CUDA(cudaMemcpyAsync(h->d_model_crops + (size_t)i * mp, dst, (size_t)a.width * a.height * 2, cudaMemcpyHostToDevice, s));
+  }
+  FL_CUDA(cudaMemcpyAsync(h->d_hyps, h->h_hyps, sizeof(fl_icp_hyp) * (size_t)n, cudaMemcpyHostToDevice, s));
+  fl_launch_icp_prepare(h->d_ref_depth, W, H, K_ref, h->d_hyps, h->icp, h->d_t_init, s); ++h->launches;
+  fl_launch_icp_run(h->icp, prm, h->d_hyps, h->d_t_init, h->d_results, s); ++h->launches;
+  FL_CUDA(cudaMemcpyAsync(h->h_results, h->d_results, sizeof(fl_icp_result_t) * (size_t)n, cudaMemcpyDeviceToHost, s));
+  FL_CUDA(cudaStreamSynchronize(s));
+  FL_CUDA(cudaGetLastError());
+  memcpy(out, h->h_results, sizeof(fl_icp_result_t) * (size_t)n);
+  return FL_OK;
+}
+
+extern "C" int fl_detection(fl_handle* h, const uint16_t* model_depth, size_t model_stride, const uint16_t* ref_depth, size_t ref_stride,
+                            int32_t W, int32_t H, fl_intrinsics_t K_ref, fl_rect_t rect_model, fl_rect_t rect_ref, int32_t icp_it_thr,
+                            float dist_mean_thr, float dist_diff_thr, const float r_match[9], const float t_match[3], float d_match,
+                            float T_final[3], float R_final[9]) {
+  if (!T_final || !R_final) return FL_ERR_ARG;
+  fl_icp_params_t prm = {icp_it_thr, dist_mean_thr, dist_diff_thr};
+  fl_icp_result_t r;
+  int rc = fl_detection_batch(h, ref_depth, ref_stride, W, H, K_ref, &model_depth, &model_stride, &rect_model, &rect_ref, r_match, t_match,
+                              &d_match, 1, prm, &r);
+  if (rc != FL_OK) return rc;
+  if (r.status != FL_OK) return r.status;
+  memcpy(T_final, r.T, 12); memcpy(R_final, r.R, 36);
+  return FL_OK;
+}
+
+extern "C" int fl_nms(fl_handle* h, const float* t3, const int32_t* n_model_pts, const float* icp_dist, int32_t n, float th, int32_t* out_idx) {
+  if (!h || n < 0 || (n > 0 && (!t3 || !n_model_pts || !icp_dist || !out_idx))) return FL_ERR_ARG;
+  if (n == 0) return 0;
+  FL_CUDA(cudaSetDevice(h->p.device));
+  cudaStream_t s = h->stream;
+  float* d_t = nullptr; int32_t* d_n = nullptr; float* d_d = nullptr; int32_t* d_o = nullptr;
+  TRY(dalloc(&d_t, (size_t)n * 3)); TRY(dalloc(&d_n, (size_t)n)); TRY(dalloc(&d_d, (size_t)n)); TRY(dalloc(&d_o, (size_t)2 * n + 2));
+  FL_CUDA(cudaMemcpyAsync(d_t, t3, (size_t)n * 12, cudaMemcpyHostToDevice, s));
+  FL_CUDA(cudaMemcpyAsync(d_n, n_model_pts, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+  FL_CUDA(cudaMemcpyAsync(d_d, icp_dist, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+  int32_t* d_cnt = d_o + 2 * n + 1;
+  fl_launch_nms(d_t, d_n, d_d, n, th, d_o, d_cnt, s); ++h->launches;
+  int32_t cnt = 0;
+  FL_CUDA(cudaMemcpyAsync(out_idx, d_o, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+  FL_CUDA(cudaMemcpyAsync(&cnt, d_cnt, 4, cudaMemcpyDeviceToHost, s));
+  FL_CUDA(cudaStreamSynchronize(s));
+  cudaFree(d_t); cudaFree(d_n); cudaFree(d_d); cudaFree(d_o);
+  return cnt;
+}

@@ -1,0 +1,91 @@
+// fealess_b200 internal declarations shared by the .cu translation units (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/fealess_b200.h"
+
+#define FL_LM_PAD 4096          // zero bytes after each label's linear memory (flat-addressing over-read)
+#define FL_MAX_T 16
+#define FL_SKIP 0xFFFFFFFFu     // packed-feature offset of a feature that falls outside the image
+
+// packed feature for one pyramid level and one frame geometry: lm_off is the byte offset of the feature's first
+// response inside the (level, modality) linear-memory block = label*label_stride + row*cells + (y/T)*W' + x/T
+// (accessLinearMemory, reference linemod/linemod.cpp:1094-1117); x,y kept for the in-image test of similarityLocal.
+struct __align__(8) fl_pfeat { uint32_t lm_off; int16_t x, y; };
+
+struct fl_level_geom {
+  int W, H, T, Wd, Hd, cells;      // image size at the level, sampling step, decimated size
+  size_t label_stride;             // bytes per label (T*T*cells + pad, 16-aligned)
+  size_t mod_stride;               // bytes per modality = 8 * label_stride
+};
+
+struct fl_sort_key { unsigned long long hi, lo; };
+
+void fl_set_error(const char* fmt, ...);
+
+#define FL_CUDA(call)                                                                  \
+  do {                                                                                 \
+    cudaError_t e__ = (call);                                                          \
+    if (e__ != cudaSuccess) {                                                          \
+      fl_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return FL_ERR_CUDA;                                                              \
+    }                                                                                  \
+  } while (0)
+
+// ---- front end (frontend.cu) -------------------------------------------------------------------
+int fl_launch_tables_init();   // uploads the two LUTs to __constant__ memory of the current device
+void fl_launch_color_quantize(const uint8_t* bgr, int W, int H, float thr_sq, uint8_t* q, cudaStream_t s);
+void fl_launch_pyrdown_bgr(const uint8_t* src, int W, int H, uint8_t* dst, cudaStream_t s);
+void fl_launch_depth_quantize(const uint16_t* depth, int W, int H, int dist_thr, int diff_thr, uint8_t* q, cudaStream_t s);
+void fl_launch_resize_nn_half(const uint8_t* src, int W, int H, uint8_t* dst, cudaStream_t s);
+void fl_launch_apply_mask(const uint8_t* q, const uint8_t* mask, int n, uint8_t* out, cudaStream_t s);
+void fl_launch_spread_lm(const uint8_t* q, fl_level_geom g, uint8_t* lm_mod, uint8_t* spread_or_null, cudaStream_t s);
+
+// ---- similarity / refinement / sort (similarity.cu) ---------------------------------------------
+struct fl_tdb {                     // device template database
+  int n_templates, L, M, n_classes;
+  const fl_template_hdr_t* hdr;     // [n_templates*L*M]
+  const fl_feature_t* feat;         // [n_features]
+  const int32_t* class_of;          // [n_templates]
+  const int32_t* class_first;       // [n_classes]
+  const uint8_t* class_enabled;     // [n_classes] (class filter of the current call)
+  fl_pfeat* pfeat;                  // [n_features] packed for the current geometry
+};
+void fl_launch_pack_features(fl_tdb db, const fl_level_geom* d_geom, int n_features_total, cudaStream_t s);
+void fl_launch_similarity_global(fl_tdb db, fl_level_geom g, const uint8_t* lm_level, float threshold,
+                                 fl_match_t* cand, int cap, int* d_count, cudaStream_t s);
+void fl_launch_similarity_debug(fl_tdb db, fl_level_geom g, const uint8_t* lm_level, int t, uint16_t* out, cudaStream_t s);
+void fl_launch_refine_level(fl_tdb db, fl_level_geom g, int level, const uint8_t* lm_level, float threshold,
+                            fl_match_t* cand, int cap, const int* d_count, cudaStream_t s);
+// sort + unique: n_lists lists of list_cap records at d_in (counts in d_n_in); result in d_out/d_out_count.
+// Returns the number of kernels launched.  key workspace must hold next_pow2(total capacity) keys.
+int fl_launch_sort_unique(const fl_match_t* d_in, int n_lists, int list_cap, const int* d_n_in, fl_sort_key* keys,
+                          int key_cap, fl_match_t* d_out, int out_cap, int* d_out_count, cudaStream_t s);
+
+// ---- ICP (icp.cu) --------------------------------------------------------------------------------
+struct fl_icp_hyp {                 // one hypothesis of a batch, device-visible
+  const uint16_t* model_depth;      // device, dense crop rows of rect_model.width (NULL for cloud mode)
+  fl_rect_t rect_model, rect_ref;
+  float r_match[9], t_match[3];
+  int status;
+};
+struct fl_icp_ws {                  // per-batch workspace, all device pointers
+  int n_hyp, max_pts;
+  float* pts_ref;                   // [n_hyp][max_pts][3]
+  float* pts_mod;                   // [n_hyp][max_pts][3]  (pts_model_tmp)
+  float* cor_m; float* cor_r;       // [n_hyp][max_pts][3]  ordered correspondences
+  float* dist;                      // [n_hyp][max_pts]     per-point paired distance (NaN-coded skips)
+  float4* grid_pts;                 // [n_hyp][max_pts]     ref points sorted by cell (x,y,z,index)
+  int* cell_start;                  // [n_hyp][FL_ICP_CELLS+1]
+  int* n_ref; int* n_mod;           // [n_hyp]
+};
+#define FL_ICP_GRID 64
+#define FL_ICP_CELLS (FL_ICP_GRID * FL_ICP_GRID)
+void fl_launch_depth_to_3d(const uint16_t* depth, int W, int H, fl_intrinsics_t K, float* out3, cudaStream_t s);
+void fl_launch_icp_prepare(const uint16_t* ref_depth, int W, int H, fl_intrinsics_t K_ref, const fl_icp_hyp* hyps,
+                           fl_icp_ws ws, float* t_init_out, cudaStream_t s);
+void fl_launch_icp_run(fl_icp_ws ws, fl_icp_params_t p, const fl_icp_hyp* hyps_or_null, const float* t_init_or_null,
+                       fl_icp_result_t* results, cudaStream_t s);
+void fl_launch_nms(const float* t3, const int32_t* n_model, const float* icp_dist, int n, float th, int32_t* out_idx,
+                   int32_t* out_count, cudaStream_t s);

@@ -1,0 +1,411 @@
+// LINE-MOD modality extraction on sm_100a: colour-gradient quantisation, depth-normal quantisation, pyramids, and the
+// fused spread -> response-map -> linear-memory kernel.  Integer/byte work, HBM-bound at best and launch-bound at VGA:
+// every stage is one tiled kernel with a shared-memory halo so each input byte is read from HBM once.
+//
+// Reference semantics (paths relative to /root/reference):
+//   colour : quantizedOrientations + hysteresisGradient      linemod/linemod.cpp:230-385
+//   pyramid: ColorGradientPyramid::pyrDown (cv::pyrDown)      linemod.cpp:434-453
+//   depth  : quantizedNormals (+ medianBlur 5)                linemod.cpp:567-685, table linemod/normal_lut.i
+//   depth pyramid / masks: resize(INTER_NEAREST), copyTo(mask) linemod.cpp:448, 455-459, 721-745
+//   spread / computeResponseMaps / linearize                  linemod.cpp:950-965, 979-1048, 1060-1088
+// Compiled with -fmad=false: the fp32 expressions below must round exactly like the (uncontracted) reference.
+#include "fl_internal.cuh"
+#include <math.h>
+
+// ------------------------------------------------------------------------------------------------
+// tables: NORMAL_LUT depends only on (v2, v1) -> 400 bytes; response table packs the 8 per-label responses of one
+// spread byte into a uint2 (labels 0-3 in .x, 4-7 in .y), i.e. SIMILARITY_LUT (linemod.cpp:970) re-indexed by pixel value.
+// ------------------------------------------------------------------------------------------------
+__constant__ uint8_t c_normal_plane[400];
+__constant__ uint2 c_resp8[256];
+
+int fl_launch_tables_init() {
+  uint8_t plane[400];
+  for (int v2 = 0; v2 < 20; ++v2)
+    for (int v1 = 0; v1 < 20; ++v1) {
+      // one-hot 45-degree sector of atan2(v2-10, v1-10) + 22.5 deg: closed form of normal_lut.i:4 (sha256-pinned in tests)
+      double a = atan2((double)(v2 - 10), (double)(v1 - 10)) * (180.0 / 3.14159265358979323846) + 22.5;
+      a = fmod(a + 360.0, 360.0);
+      plane[v2 * 20 + v1] = (uint8_t)(1u << (((int)floor(a / 45.0)) & 7));
+    }
+  uint2 resp[256];
+  for (int v = 0; v < 256; ++v) {
+    uint32_t w[2] = {0, 0};
+    for (int i = 0; i < 8; ++i) {
+      int best = 0;
+      for (int j = 0; j < 8; ++j)
+        if (v >> j & 1) {
+          int d = i > j ? i - j : j - i;
+          if (8 - d < d) d = 8 - d;
+          int g = d == 0 ? 4 : (d == 1 ? 2 : (d == 2 ? 1 : 0));   // response per circular label distance
+          if (g > best) best = g;
+        }
+      w[i >> 2] |= (uint32_t)best << (8 * (i & 3));
+    }
+    resp[v] = make_uint2(w[0], w[1]);
+  }
+  FL_CUDA(cudaMemcpyToSymbol(c_normal_plane, plane, sizeof plane));
+  FL_CUDA(cudaMemcpyToSymbol(c_resp8, resp, sizeof resp));
+  return FL_OK;
+}
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+
+// ------------------------------------------------------------------------------------------------
+// K1 colour quantisation: blur7 -> sobel3 -> strongest channel -> 16-bin angle -> &7 -> 3x3 majority vote, one kernel.
+// Tile = CQ_TW x CQ_TH output pixels; halo 5 = 3 (blur) + 1 (sobel) + 1 (vote).
+// ------------------------------------------------------------------------------------------------
+#define CQ_TW 32
+#define CQ_TH 16
+#define CQ_THREADS 256
+
+// OpenCV fastAtan2 (cv::phase, angleInDegrees) in fp32, then convertTo(CV_8U, 16/360) = rint-half-even, saturate.
+__device__ __forceinline__ int angle_q16(float x, float y) {
+  const float scale = (float)(180.0 / 3.14159265358979323846);
+  const float p1 = 0.9997878412794807f * scale, p3 = -0.3258083974640975f * scale;
+  const float p5 = 0.1555786518463281f * scale, p7 = -0.04432655554792128f * scale;
+  const float eps = 2.220446049250313e-16f;
+  float ax = fabsf(x), ay = fabsf(y), a, c, c2;
+  if (ax >= ay) {
+    c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+    c2 = __fmul_rn(c, c);
+    a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+  } else {
+    c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+    c2 = __fmul_rn(c, c);
+    a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+  }
+  if (x < 0) a = __fsub_rn(180.f, a);
+  if (y < 0) a = __fsub_rn(360.f, a);
+  int r = __float2int_rn(__fmul_rn(a, (float)(16.0 / 360.0)));
+  return min(max(r, 0), 255);
+}
+
+__global__ void __launch_bounds__(CQ_THREADS) k_color_quantize(const uint8_t* __restrict__ bgr, int W, int H, float thr_sq,
+                                                               uint8_t* __restrict__ q) {
+  constexpr int SW = CQ_TW + 10, SH = CQ_TH + 10;   // source tile
+  constexpr int BW = CQ_TW + 4, BH = CQ_TH + 4;     // blurred tile (positions x0-2 .. x0+TW+1)
+  constexpr int QW = CQ_TW + 2, QH = CQ_TH + 2;     // unfiltered-bin tile (positions x0-1 .. x0+TW)
+  __shared__ uint8_t s_src[SH][SW * 3];
+  __shared__ uint16_t s_h[SH][BW * 3];
+  __shared__ uint8_t s_b[BH][BW * 3];
+  __shared__ uint8_t s_q[QH][QW];                   // bits 0-2 bin, bit 7 = magnitude above threshold
+  const int x0 = blockIdx.x * CQ_TW, y0 = blockIdx.y * CQ_TH;
+  const int tid = threadIdx.x;
+
+  // 1. source tile with BORDER_REPLICATE
+  for (int i = tid; i < SH * SW; i += CQ_THREADS) {
+    int r = i / SW, c = i - r * SW;
+    int sy = clampi(y0 - 5 + r, 0, H - 1), sx = clampi(x0 - 5 + c, 0, W - 1);
+    const uint8_t* p = bgr + ((size_t)sy * W + sx) * 3;
+    s_src[r][c * 3 + 0] = p[0]; s_src[r][c * 3 + 1] = p[1]; s_src[r][c * 3 + 2] = p[2];
+  }
+  __syncthreads();
+  // 2. horizontal 7-tap {8,28,56,72,56,28,8}: exact integers (<= 65280).  A blurred position outside the image stands
+  //    for the replicated border pixel of the BLURRED image (Sobel's own BORDER_REPLICATE), so it is evaluated at the
+  //    clamped position.
+  for (int i = tid; i < SH * BW; i += CQ_THREADS) {
+    int r = i / BW, bx = i - r * BW;
+    int cpx = clampi(x0 - 2 + bx, 0, W - 1);
+    int c0 = cpx - 3 - (x0 - 5);
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      const uint8_t* p = &s_src[r][c0 * 3 + ch];
+      int s = 8 * (p[0] + p[18]) + 28 * (p[3] + p[15]) + 56 * (p[6] + p[12]) + 72 * p[9];
+      s_h[r][bx * 3 + ch] = (uint16_t)s;
+    }
+  }
+  __syncthreads();
+  // 3. vertical 7-tap, single rounding (sum + 2^15) >> 16
+  for (int i = tid; i < BH * BW * 3; i += CQ_THREADS) {
+    int by = i / (BW * 3), k = i - by * (BW * 3);
+    int cpy = clampi(y0 - 2 + by, 0, H - 1);
+    int r0 = cpy - 3 - (y0 - 5);
+    int s = 8 * (s_h[r0][k] + s_h[r0 + 6][k]) + 28 * (s_h[r0 + 1][k] + s_h[r0 + 5][k]) + 56 * (s_h[r0 + 2][k] + s_h[r0 + 4][k]) +
+            72 * s_h[r0 + 3][k];
+    s_b[by][k] = (uint8_t)((s + 32768) >> 16);
+  }
+  __syncthreads();
+  // 4. Sobel 3x3 per channel on the blurred tile, strongest channel (ties: first, linemod.cpp:275-292), angle bin
+  for (int i = tid; i < QH * QW; i += CQ_THREADS) {
+    int qy = i / QW, qx = i - qy * QW;
+    int sx = x0 - 1 + qx, sy = y0 - 1 + qy;
+    uint8_t v = 0;
+    if (sx > 0 && sx < W - 1 && sy > 0 && sy < H - 1) {   // the 1-px frame of quantized_unfiltered is zeroed (:318-325)
+      int bx = qx + 1, by = qy + 1;                        // blurred-tile index of this position
+      int best_m = -1, best_dx = 0, best_dy = 0;
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        int a00 = s_b[by - 1][(bx - 1) * 3 + ch], a01 = s_b[by - 1][bx * 3 + ch], a02 = s_b[by - 1][(bx + 1) * 3 + ch];
+        int a10 = s_b[by][(bx - 1) * 3 + ch], a12 = s_b[by][(bx + 1) * 3 + ch];
+        int a20 = s_b[by + 1][(bx - 1) * 3 + ch], a21 = s_b[by + 1][bx * 3 + ch], a22 = s_b[by + 1][(bx + 1) * 3 + ch];
+        int dx = (a02 + 2 * a12 + a22) - (a00 + 2 * a10 + a20);
+        int dy = (a20 + 2 * a21 + a22) - (a00 + 2 * a01 + a02);
+        int m = dx * dx + dy * dy;
+        if (m > best_m) { best_m = m; best_dx = dx; best_dy = dy; }   // strict > keeps the earliest channel on ties
+      }
+      v = (uint8_t)(angle_q16((float)best_dx, (float)best_dy) & 7);
+      if ((float)best_m > thr_sq) v |= 0x80;
+    }
+    s_q[qy][qx] = v;
+  }
+  __syncthreads();
+  // 5. 3x3 histogram vote: majority (>= 5 of 9) of the bins, lowest bin wins ties (:346-381)
+  for (int i = tid; i < CQ_TH * CQ_TW; i += CQ_THREADS) {
+    int oy = i / CQ_TW, ox = i - oy * CQ_TW;
+    int x = x0 + ox, y = y0 + oy;
+    if (x >= W || y >= H) continue;
+    uint8_t out = 0;
+    if (x > 0 && x < W - 1 && y > 0 && y < H - 1 && (s_q[oy + 1][ox + 1] & 0x80)) {
+      uint32_t hist = 0;   // eight 4-bit counters
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) hist += 1u << (4 * (s_q[oy + j][ox + k] & 7));
+      int best = 0, idx = 0;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        int c = (hist >> (4 * b)) & 15;
+        if (c > best) { best = c; idx = b; }
+      }
+      if (best >= 5) out = (uint8_t)(1u << idx);
+    }
+    q[(size_t)y * W + x] = out;
+  }
+}
+
+void fl_launch_color_quantize(const uint8_t* bgr, int W, int H, float thr_sq, uint8_t* q, cudaStream_t s) {
+  dim3 grid((W + CQ_TW - 1) / CQ_TW, (H + CQ_TH - 1) / CQ_TH);
+  k_color_quantize<<<grid, CQ_THREADS, 0, s>>>(bgr, W, H, thr_sq, q);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 cv::pyrDown of the BGR image: 5x5 [1 4 6 4 1]^2, BORDER_REFLECT_101, (sum + 128) >> 8
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int reflect101(int p, int n) {
+  if (n == 1) return 0;
+  while (p < 0 || p >= n) p = p < 0 ? -p : 2 * n - 2 - p;
+  return p;
+}
+
+__global__ void __launch_bounds__(256) k_pyrdown_bgr(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ dst) {
+  const int dw = W / 2, dh = H / 2;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;   // one thread per output byte (pixel*3 + channel): coalesced stores
+  if (i >= dw * dh * 3) return;
+  int ch = i % 3, px = i / 3;
+  int x = px % dw, y = px / dw;
+  const int k[5] = {1, 4, 6, 4, 1};
+  int cx[5];
+#pragma unroll
+  for (int t = 0; t < 5; ++t) cx[t] = reflect101(2 * x + t - 2, W) * 3 + ch;
+  int s = 0;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    const uint8_t* row = src + (size_t)reflect101(2 * y + j - 2, H) * W * 3;
+    int rs = 0;
+#pragma unroll
+    for (int t = 0; t < 5; ++t) rs += k[t] * row[cx[t]];
+    s += k[j] * rs;
+  }
+  dst[i] = (uint8_t)((s + 128) >> 8);
+}
+
+void fl_launch_pyrdown_bgr(const uint8_t* src, int W, int H, uint8_t* dst, cudaStream_t s) {
+  int n = (W / 2) * (H / 2) * 3;
+  k_pyrdown_bgr<<<(n + 255) / 256, 256, 0, s>>>(src, W, H, dst);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3 depth normals: 8-tap bilateral least squares -> normal -> NORMAL_LUT, then 5x5 median, fused (halo 2 + 5).
+// ------------------------------------------------------------------------------------------------
+#define DQ_TW 32
+#define DQ_TH 16
+#define DQ_THREADS 256
+
+__global__ void __launch_bounds__(DQ_THREADS) k_depth_quantize(const uint16_t* __restrict__ depth, int W, int H, int dist_thr,
+                                                               int diff_thr, uint8_t* __restrict__ q) {
+  constexpr int RW = DQ_TW + 4, RH = DQ_TH + 4;      // raw label tile (median halo 2)
+  constexpr int SW = RW + 10, SH = RH + 10;          // depth tile (tap radius 5)
+  __shared__ uint16_t s_d[SH][SW];
+  __shared__ uint8_t s_r[RH][RW];
+  const int x0 = blockIdx.x * DQ_TW, y0 = blockIdx.y * DQ_TH;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < SH * SW; i += DQ_THREADS) {
+    int r = i / SW, c = i - r * SW;
+    int sy = y0 - 7 + r, sx = x0 - 7 + c;
+    s_d[r][c] = (sx >= 0 && sx < W && sy >= 0 && sy < H) ? depth[(size_t)sy * W + sx] : (uint16_t)0;
+  }
+  __syncthreads();
+  for (int i = tid; i < RH * RW; i += DQ_THREADS) {
+    int ry = i / RW, rx = i - ry * RW;
+    // medianBlur replicates the border of the label image; border labels are 0 (loop bounds :619, :624), so any
+    // position outside [5, W-7] x [5, H-7] - inside or outside the image - contributes 0.
+    int px = x0 - 2 + rx, py = y0 - 2 + ry;
+    uint8_t v = 0;
+    if (px >= 5 && px < W - 6 && py >= 5 && py < H - 6) {
+      int cy = ry + 5, cx = rx + 5;
+      int d = s_d[cy][cx];
+      if (d < dist_thr) {
+        int A0 = 0, A1 = 0, A3 = 0, b0 = 0, b1 = 0;
+#pragma unroll
+        for (int j = -5; j <= 5; j += 5)
+#pragma unroll
+          for (int ii = -5; ii <= 5; ii += 5) {
+            if (ii == 0 && j == 0) continue;
+            int delta = (int)s_d[cy + j][cx + ii] - d;
+            int f = abs(delta) < diff_thr ? 1 : 0;           // accumBilateral :567-579
+            A0 += f * ii * ii; A1 += f * ii * j; A3 += f * j * j;
+            b0 += f * ii * delta; b1 += f * j * delta;
+          }
+        int det = A0 * A3 - A1 * A1;                          // all fit int32
+        int ddx = A3 * b0 - A1 * b1;
+        int ddy = -A1 * b0 + A0 * b1;
+        float nx = (float)(617 * ddx), ny = (float)(617 * ddy), nz = (float)(-det * d);
+        float s = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(nx, nx), __fmul_rn(ny, ny)), __fmul_rn(nz, nz)));
+        if (s > 0.f) {
+          float inv = __fdiv_rn(1.0f, s);
+          nx = __fmul_rn(nx, inv); ny = __fmul_rn(ny, inv);
+          int v1 = (int)__fadd_rn(__fmul_rn(nx, 10.f), 10.f);   // C truncation :665-667
+          int v2 = (int)__fadd_rn(__fmul_rn(ny, 10.f), 10.f);
+          v = c_normal_plane[clampi(v2, 0, 19) * 20 + clampi(v1, 0, 19)];   // table is v3-independent
+        }
+      }
+    }
+    s_r[ry][rx] = v;
+  }
+  __syncthreads();
+  for (int i = tid; i < DQ_TH * DQ_TW; i += DQ_THREADS) {
+    int oy = i / DQ_TW, ox = i - oy * DQ_TW;
+    int x = x0 + ox, y = y0 + oy;
+    if (x >= W || y >= H) continue;
+    // exact median of 25 bytes by MSB-first radix selection of the 13th smallest
+    uint32_t vals[25];
+#pragma unroll
+    for (int j = 0; j < 5; ++j)
+#pragma unroll
+      for (int k = 0; k < 5; ++k) vals[j * 5 + k] = s_r[oy + j][ox + k];
+    uint32_t prefix = 0, mask = 0;
+    int need = 13;
+#pragma unroll
+    for (int bit = 7; bit >= 0; --bit) {
+      uint32_t m2 = mask | (1u << bit);
+      int zeros = 0;
+#pragma unroll
+      for (int t = 0; t < 25; ++t) zeros += ((vals[t] & m2) == prefix) ? 1 : 0;   // matches prefix and has this bit clear
+      if (need > zeros) { need -= zeros; prefix |= 1u << bit; }
+      mask = m2;
+    }
+    q[(size_t)y * W + x] = (uint8_t)prefix;
+  }
+}
+
+void fl_launch_depth_quantize(const uint16_t* depth, int W, int H, int dist_thr, int diff_thr, uint8_t* q, cudaStream_t s) {
+  dim3 grid((W + DQ_TW - 1) / DQ_TW, (H + DQ_TH - 1) / DQ_TH);
+  k_depth_quantize<<<grid, DQ_THREADS, 0, s>>>(depth, W, H, dist_thr, diff_thr, q);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4 nearest-neighbour x1/2 (cv::resize INTER_NEAREST to (W/2, H/2)) and mask application (copyTo(dst, mask))
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_resize_nn_half(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ dst) {
+  const int dw = W / 2, dh = H / 2;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= dw * dh) return;
+  int x = i % dw, y = i / dw;
+  int sx = min((int)floor(x * ((double)W / dw)), W - 1);
+  int sy = min((int)floor(y * ((double)H / dh)), H - 1);
+  dst[i] = src[(size_t)sy * W + sx];
+}
+void fl_launch_resize_nn_half(const uint8_t* src, int W, int H, uint8_t* dst, cudaStream_t s) {
+  int n = (W / 2) * (H / 2);
+  k_resize_nn_half<<<(n + 255) / 256, 256, 0, s>>>(src, W, H, dst);
+}
+
+__global__ void __launch_bounds__(256) k_apply_mask(const uint8_t* __restrict__ q, const uint8_t* __restrict__ mask, int n,
+                                                    uint8_t* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = mask[i] ? q[i] : (uint8_t)0;
+}
+void fl_launch_apply_mask(const uint8_t* q, const uint8_t* mask, int n, uint8_t* out, cudaStream_t s) {
+  k_apply_mask<<<(n + 255) / 256, 256, 0, s>>>(q, mask, n, out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5 spread + response maps + linearize, fused.  One CTA = one row of the decimated grid (T image rows) x SL_CW cells.
+//   spread(y,x) = OR over the forward TxT window (clipped at the image end)                          :950-965
+//   response_i  = table lookup of the spread byte (all 8 labels at once)                              :979-1048
+//   LM_i[(y%T)*T + x%T][(y/T)*W' + x/T] = response_i(y,x)                                            :1060-1088
+// HBM traffic = W*H read + 8*W*H written; each (label, grid-row) run of SL_CW output bytes is one full 32 B sector.
+// ------------------------------------------------------------------------------------------------
+#define SL_CW 32
+#define SL_THREADS 256
+
+__global__ void __launch_bounds__(SL_THREADS) k_spread_lm(const uint8_t* __restrict__ q, fl_level_geom g, uint8_t* __restrict__ lm,
+                                                          uint8_t* __restrict__ spread_out) {
+  extern __shared__ uint8_t s_raw[];                    // [(2T-1)][tw] input (later reused for the final spread), then [(2T-1)][pw]
+  __shared__ uint2 s_resp[256];
+  const int T = g.T, W = g.W, H = g.H, Wd = g.Wd;
+  const int gy = blockIdx.y, cx0 = blockIdx.x * SL_CW;
+  const int ncell = min(SL_CW, Wd - cx0);
+  const int pw = ncell * T;                             // pixels owned by this CTA per row
+  const int tw = pw + T - 1, th = 2 * T - 1;
+  const int px0 = cx0 * T, py0 = gy * T;
+  const int tid = threadIdx.x;
+  uint8_t* s_in = s_raw;                                // th x tw
+  uint8_t* s_hor = s_raw + (size_t)(2 * T - 1) * (SL_CW * T + T - 1);   // th x pw horizontal OR
+  for (int i = tid; i < 256; i += SL_THREADS) s_resp[i] = c_resp8[i];
+  for (int i = tid; i < th * tw; i += SL_THREADS) {
+    int r = i / tw, c = i - r * tw;
+    int y = py0 + r, x = px0 + c;
+    s_in[r * tw + c] = (x < W && y < H) ? q[(size_t)y * W + x] : (uint8_t)0;   // clipped window == OR with zeros
+  }
+  __syncthreads();
+  for (int i = tid; i < th * pw; i += SL_THREADS) {
+    int r = i / pw, c = i - r * pw;
+    uint32_t v = 0;
+    for (int k = 0; k < T; ++k) v |= s_in[r * tw + c + k];
+    s_hor[r * pw + c] = (uint8_t)v;
+  }
+  __syncthreads();
+  uint8_t* s_sp = s_in;                                 // T x pw final spread values (s_in is dead)
+  for (int i = tid; i < T * pw; i += SL_THREADS) {
+    int r = i / pw, c = i - r * pw;
+    uint32_t v = 0;
+    for (int k = 0; k < T; ++k) v |= s_hor[(r + k) * pw + c];
+    s_sp[r * pw + c] = (uint8_t)v;
+    if (spread_out) spread_out[(size_t)(py0 + r) * W + px0 + c] = (uint8_t)v;
+  }
+  __syncthreads();
+  // scatter: item = (grid row ry, grid col rx, group of 4 cells); 8 labels -> 8 word stores per item
+  const int ngrp = (ncell + 3) / 4;
+  const int items = T * T * ngrp;
+  const size_t cells = (size_t)g.cells;
+  for (int i = tid; i < items; i += SL_THREADS) {
+    int rr = i / ngrp, c4 = i - rr * ngrp;
+    int ry = rr / T, rx = rr - ry * T;
+    uint32_t lo[4], hi[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int c = c4 * 4 + k;
+      uint2 r8 = c < ncell ? s_resp[s_sp[ry * pw + c * T + rx]] : make_uint2(0, 0);
+      lo[k] = r8.x; hi[k] = r8.y;
+    }
+    size_t off = (size_t)rr * cells + (size_t)gy * Wd + cx0 + c4 * 4;
+    int nvalid = min(4, ncell - c4 * 4);
+#pragma unroll
+    for (int lab = 0; lab < 8; ++lab) {
+      const uint32_t* src = lab < 4 ? lo : hi;
+      int sh = 8 * (lab & 3);
+      uint32_t w = ((src[0] >> sh) & 0xFF) | (((src[1] >> sh) & 0xFF) << 8) | (((src[2] >> sh) & 0xFF) << 16) | (((src[3] >> sh) & 0xFF) << 24);
+      uint8_t* dst = lm + (size_t)lab * g.label_stride + off;
+      if (nvalid == 4 && (((uintptr_t)dst) & 3) == 0) *reinterpret_cast<uint32_t*>(dst) = w;
+      else for (int k = 0; k < nvalid; ++k) dst[k] = (uint8_t)(w >> (8 * k));
+    }
+  }
+}
+
+void fl_launch_spread_lm(const uint8_t* q, fl_level_geom g, uint8_t* lm_mod, uint8_t* spread_or_null, cudaStream_t s) {
+  size_t smem = (size_t)(2 * g.T - 1) * (SL_CW * g.T + g.T - 1) + (size_t)(2 * g.T - 1) * (SL_CW * g.T);   // <= 33 KB at T = 16
+  dim3 grid((g.Wd + SL_CW - 1) / SL_CW, g.Hd);
+  k_spread_lm<<<grid, SL_THREADS, smem, s>>>(q, g, lm_mod, spread_or_null);
+}

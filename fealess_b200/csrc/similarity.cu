@@ -1,0 +1,360 @@
+// LINE-MOD template matching on sm_100a: global similarity at the coarsest pyramid level with fused threshold ->
+// candidate emission, local 16x16 refinement up the pyramid, and the final sort + duplicate pruning.
+//
+// Reference semantics (paths relative to /root/reference):
+//   accessLinearMemory linemod/linemod.cpp:1094-1117   similarity :1130-1214   similarityLocal :1226-1300
+//   addSimilarities :1322-1338   matchClass :1451-1577   Match ordering linemod/linemod.hpp:262-274, sort/unique :1437-1439
+//
+// Byte-lane arithmetic: a template has <= 63 features per modality (CV_Assert :1137) and a response is <= 4, so four
+// packed u8 sums in one 32-bit register never carry across lanes (63*4 = 252): one IADD adds four cells.
+#include "fl_internal.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// per-geometry feature packing (runs once per frame size, not per frame)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pack_features(fl_tdb db, const fl_level_geom* __restrict__ geom, int n_entries) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;       // one thread per (template, level, modality) entry
+  if (e >= n_entries) return;
+  const fl_template_hdr_t h = db.hdr[e];
+  const int level = (e / db.M) % db.L;
+  const fl_level_geom g = geom[level];
+  for (int k = 0; k < h.feature_count; ++k) {
+    const fl_feature_t f = db.feat[h.feature_begin + k];
+    fl_pfeat p;
+    p.x = (int16_t)max(min(f.x, 32767), -32768);
+    p.y = (int16_t)max(min(f.y, 32767), -32768);
+    if (f.x < 0 || f.y < 0 || f.x >= g.W || f.y >= g.H) p.lm_off = FL_SKIP;          // :1179
+    else p.lm_off = (uint32_t)((size_t)f.label * g.label_stride + (size_t)((f.y % g.T) * g.T + (f.x % g.T)) * g.cells +
+                               (size_t)(f.y / g.T) * g.Wd + f.x / g.T);
+    db.pfeat[h.feature_begin + k] = p;
+  }
+}
+
+void fl_launch_pack_features(fl_tdb db, const fl_level_geom* d_geom, int n_features_total, cudaStream_t s) {
+  (void)n_features_total;
+  int n = db.n_templates * db.L * db.M;
+  if (n > 0) k_pack_features<<<(n + 255) / 256, 256, 0, s>>>(db, d_geom, n);
+}
+
+// unaligned 4-byte window at byte offset a of a 4-byte-aligned buffer
+__device__ __forceinline__ uint32_t load_u8x4(const uint8_t* __restrict__ base, uint32_t a) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(base) + (a >> 2);
+  uint32_t lo = __ldg(w), hi = __ldg(w + 1);
+  return __funnelshift_r(lo, hi, (a & 3) * 8);
+}
+
+__device__ __forceinline__ int raw_threshold_of(int nf, float threshold) {
+  // int(2*nf + (threshold/100)*(2*nf) + 0.5f) in fp32, truncation (:1487)
+  return (int)__fadd_rn(__fadd_rn((float)(2 * nf), __fmul_rn(__fdiv_rn(threshold, 100.f), (float)(2 * nf))), 0.5f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6 (baseline variant): one CTA per template, one thread per group of 4 cells, responses read through L1/L2.
+// ------------------------------------------------------------------------------------------------
+#define SG_THREADS 128
+
+template <bool kDebug>
+__global__ void __launch_bounds__(SG_THREADS) k_similarity_global(fl_tdb db, fl_level_geom g, const uint8_t* __restrict__ lm_level,
+                                                                  float threshold, fl_match_t* __restrict__ cand, int cap,
+                                                                  int* __restrict__ d_count, int t_debug, uint16_t* __restrict__ dbg) {
+  const int t = kDebug ? t_debug : blockIdx.x;
+  const int cls = db.class_of[t];
+  if (!kDebug && !db.class_enabled[cls]) return;
+  const int level = db.L - 1;
+  const fl_template_hdr_t* hdr = db.hdr + ((size_t)t * db.L + level) * db.M;
+  const int cells = g.cells;
+  int nf = 0;
+  for (int m = 0; m < db.M; ++m) nf += hdr[m].feature_count;
+  const int raw_thr = raw_threshold_of(nf, threshold);
+  const int off = g.T / 2 + (g.T % 2 - 1);
+  const int ngroups = (cells + 3) / 4;
+  for (int grp = threadIdx.x; grp < ngroups; grp += SG_THREADS) {
+    uint32_t tot_lo = 0, tot_hi = 0;   // u16 x 2 each: cells (0,1) and (2,3)
+    for (int m = 0; m < db.M; ++m) {
+      const fl_template_hdr_t h = hdr[m];
+      const int wf = (h.width - 1) / g.T + 1, hf = (h.height - 1) / g.T + 1;          // :1145-1146
+      int tp = (g.Hd - hf) * g.Wd + (g.Wd - wf) + 1;                                  // template_positions :1155
+      tp = min(tp, cells);
+      const int j0 = grp * 4;
+      if (j0 >= tp) continue;                                                          // cells beyond stay 0
+      const uint8_t* lm_mod = lm_level + (size_t)m * g.mod_stride;
+      const fl_pfeat* pf = db.pfeat + h.feature_begin;
+      uint32_t acc = 0;
+      for (int k = 0; k < h.feature_count; ++k) {
+        uint32_t o = __ldg(&pf[k].lm_off);
+        if (o == FL_SKIP) continue;
+        acc += load_u8x4(lm_mod, o + j0);                                              // four wrapping u8 adds (:1195)
+      }
+      if (j0 + 4 > tp) acc &= 0xFFFFFFFFu >> (8 * (j0 + 4 - tp));                      // mask lanes >= tp
+      tot_lo += (acc & 0xFF) | ((acc & 0xFF00) << 8);                                  // widen to u16 lanes (:1322-1338)
+      tot_hi += ((acc >> 16) & 0xFF) | ((acc >> 24) << 16);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int j = grp * 4 + k;
+      if (j >= cells) break;
+      int raw = (k < 2 ? tot_lo >> (16 * k) : tot_hi >> (16 * (k - 2))) & 0xFFFF;
+      if (kDebug) { dbg[j] = (uint16_t)raw; continue; }
+      if (raw > raw_thr) {                                                             // :1497-1504
+        int r = j / g.Wd, c = j - r * g.Wd;
+        int slot = atomicAdd(d_count, 1);
+        if (slot < cap) {
+          fl_match_t mt;
+          mt.x = c * g.T + off; mt.y = r * g.T + off;
+          mt.similarity = __fadd_rn(__fdiv_rn(__fmul_rn((float)raw, 100.f), (float)(4 * nf)), 0.5f);
+          mt.class_idx = cls; mt.template_id = t - db.class_first[cls];
+          cand[slot] = mt;
+        }
+      }
+    }
+  }
+}
+
+void fl_launch_similarity_global(fl_tdb db, fl_level_geom g, const uint8_t* lm_level, float threshold, fl_match_t* cand, int cap,
+                                 int* d_count, cudaStream_t s) {
+  if (db.n_templates > 0)
+    k_similarity_global<false><<<db.n_templates, SG_THREADS, 0, s>>>(db, g, lm_level, threshold, cand, cap, d_count, 0, nullptr);
+}
+void fl_launch_similarity_debug(fl_tdb db, fl_level_geom g, const uint8_t* lm_level, int t, uint16_t* out, cudaStream_t s) {
+  k_similarity_global<true><<<1, SG_THREADS, 0, s>>>(db, g, lm_level, 0.f, nullptr, 0, nullptr, t, out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7 local refinement of every candidate at one finer level: 16x16 patch of total similarity, first maximum wins.
+// One CTA of 64 threads per candidate: thread = (patch row, 4-cell column group).
+// ------------------------------------------------------------------------------------------------
+#define RF_THREADS 64
+
+__global__ void __launch_bounds__(RF_THREADS) k_refine_level(fl_tdb db, fl_level_geom g, int level, const uint8_t* __restrict__ lm_level,
+                                                             float threshold, fl_match_t* __restrict__ cand, int cap,
+                                                             const int* __restrict__ d_count) {
+  const int n = min(*d_count, cap);
+  const int row = threadIdx.x >> 2, cg = threadIdx.x & 3;
+  __shared__ uint32_t s_best[2];
+  for (int ci = blockIdx.x; ci < n; ci += gridDim.x) {
+    fl_match_t mt = cand[ci];
+    if (mt.template_id < 0) continue;                              // dropped at a coarser level (:1570-1572)
+    const int t = db.class_first[mt.class_idx] + mt.template_id;
+    const fl_template_hdr_t* hdr = db.hdr + ((size_t)t * db.L + level) * db.M;
+    const int T = g.T, border = 8 * T;
+    int x = mt.x * 2 + 1, y = mt.y * 2 + 1;                        // :1525-1534
+    x = max(x, border); y = max(y, border);
+    x = min(x, g.W - hdr[0].width - border);
+    y = min(y, g.H - hdr[0].height - border);
+    const int ox = (x / T - 8) * T, oy = (y / T - 8) * T;          // :1240-1241 (C division truncates towards zero)
+    const int delta = (oy / T) * g.Wd + ox / T + row * g.Wd + cg * 4;
+    uint32_t tot_lo = 0, tot_hi = 0;
+    int nf = 0;
+    for (int m = 0; m < db.M; ++m) {
+      const fl_template_hdr_t h = hdr[m];
+      nf += h.feature_count;
+      const uint8_t* lm_mod = lm_level + (size_t)m * g.mod_stride;
+      const fl_pfeat* pf = db.pfeat + h.feature_begin;
+      uint32_t acc = 0;
+      for (int k = 0; k < h.feature_count; ++k) {
+        fl_pfeat p = pf[k];
+        int fx = p.x + ox, fy = p.y + oy;
+        if (fx < 0 || fy < 0 || fx >= g.W || fy >= g.H) continue;  // :1257
+        // the packed offset was computed for (x, y); shifting by a multiple of T moves only the cell index
+        uint32_t o = p.lm_off;
+        if (o == FL_SKIP) {                                        // feature outside the image unshifted, inside when shifted
+          o = (uint32_t)((size_t)db.feat[h.feature_begin + k].label * g.label_stride +
+                         (size_t)((p.y % T + T) % T * T + (p.x % T + T) % T) * g.cells + (size_t)(fy / T) * g.Wd + fx / T);
+          acc += load_u8x4(lm_mod, o + row * g.Wd + cg * 4);
+        } else {
+          acc += load_u8x4(lm_mod, (uint32_t)((int)o + delta));
+        }
+      }
+      tot_lo += (acc & 0xFF) | ((acc & 0xFF00) << 8);
+      tot_hi += ((acc >> 16) & 0xFF) | ((acc >> 24) << 16);
+    }
+    // first maximum in row-major order: key = score << 8 | (255 - index); all-zero patch -> best 0 at (-1,-1) (:1547-1562)
+    uint32_t key = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint32_t sc = (k < 2 ? tot_lo >> (16 * k) : tot_hi >> (16 * (k - 2))) & 0xFFFF;
+      uint32_t idx = row * 16 + cg * 4 + k;
+      uint32_t kk = (sc << 8) | (255 - idx);
+      if (sc > 0 && kk > key) key = kk;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) key = max(key, __shfl_xor_sync(0xffffffffu, key, o));
+    if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = key;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t kb = max(s_best[0], s_best[1]);
+      int best = (int)(kb >> 8), br = -1, bc = -1;
+      if (best > 0) { int idx = 255 - (int)(kb & 255); br = idx >> 4; bc = idx & 15; }
+      const int off = T / 2 + (T % 2 - 1);
+      mt.x = (x / T - 8 + bc) * T + off;                           // :1564-1566
+      mt.y = (y / T - 8 + br) * T + off;
+      mt.similarity = __fdiv_rn(__fmul_rn((float)best, 100.f), (float)(4 * nf));
+      if (mt.similarity < threshold) mt.template_id = -1 - mt.template_id;   // mark dropped (remove_if :1570)
+      cand[ci] = mt;
+    }
+    __syncthreads();
+  }
+}
+
+void fl_launch_refine_level(fl_tdb db, fl_level_geom g, int level, const uint8_t* lm_level, float threshold, fl_match_t* cand,
+                            int cap, const int* d_count, cudaStream_t s) {
+  int grid = min(cap, 148 * 16);
+  if (grid > 0) k_refine_level<<<grid, RF_THREADS, 0, s>>>(db, g, level, lm_level, threshold, cand, cap, d_count);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K8 sort + unique under the canonical total order (similarity desc, template_id asc, class asc, y asc, x asc), then
+// adjacent-unique on (x, y, similarity, class) (linemod.hpp:262-274).  The whole record fits a 128-bit key, so the
+// sort moves keys only and the records are rebuilt from them.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ fl_sort_key make_key(const fl_match_t& m) {
+  fl_sort_key k;
+  k.hi = ((unsigned long long)(~__float_as_uint(m.similarity)) << 32) | (uint32_t)m.template_id;
+  k.lo = ((unsigned long long)(uint32_t)m.class_idx << 32) | ((unsigned long long)((uint32_t)(m.y + 32768) & 0xFFFF) << 16) |
+         ((uint32_t)(m.x + 32768) & 0xFFFF);
+  return k;
+}
+__device__ __forceinline__ fl_match_t key_to_match(const fl_sort_key& k) {
+  fl_match_t m;
+  m.similarity = __uint_as_float(~(uint32_t)(k.hi >> 32));
+  m.template_id = (int)(uint32_t)k.hi;
+  m.class_idx = (int)(uint32_t)(k.lo >> 32);
+  m.y = (int)((k.lo >> 16) & 0xFFFF) - 32768;
+  m.x = (int)(k.lo & 0xFFFF) - 32768;
+  return m;
+}
+__device__ __forceinline__ bool key_less(const fl_sort_key& a, const fl_sort_key& b) { return a.hi < b.hi || (a.hi == b.hi && a.lo < b.lo); }
+__device__ __forceinline__ bool key_dup(const fl_sort_key& a, const fl_sort_key& b) {
+  // equal x, y, similarity, class; template_id ignored (linemod.hpp:271-274)
+  return (a.hi >> 32) == (b.hi >> 32) && a.lo == b.lo;
+}
+#define KEY_SENTINEL_HI 0xFFFFFFFFFFFFFFFFull
+
+// gather live candidates of all lists into the key array [0, n_pad), sentinel-padded; *d_n_live = number of live keys
+__global__ void __launch_bounds__(256) k_build_keys(const fl_match_t* __restrict__ in, int n_lists, int list_cap,
+                                                    const int* __restrict__ n_in, fl_sort_key* __restrict__ keys, int key_cap,
+                                                    int* __restrict__ d_n_live) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_lists * list_cap) return;
+  int l = i / list_cap, k = i - l * list_cap;
+  int n = min(n_in[l], list_cap);
+  if (k >= n) return;
+  fl_match_t m = in[i];
+  if (m.template_id < 0) return;
+  int slot = atomicAdd(d_n_live, 1);
+  if (slot < key_cap) keys[slot] = make_key(m);
+}
+
+#define SORT_SMEM_N 2048
+// whole sort + unique in one CTA for n_live <= SORT_SMEM_N; otherwise sets *d_flag_big = 1 and leaves the work to the
+// multi-kernel path.
+__global__ void __launch_bounds__(1024) k_sort_unique_small(fl_sort_key* __restrict__ keys, const int* __restrict__ d_n_live,
+                                                            int key_cap, fl_match_t* __restrict__ out, int out_cap,
+                                                            int* __restrict__ d_out_count, int* __restrict__ d_flag_big) {
+  __shared__ fl_sort_key s_k[SORT_SMEM_N];
+  __shared__ int s_scan[1024 + 1];
+  const int n = min(*d_n_live, key_cap);
+  if (n > SORT_SMEM_N) { if (threadIdx.x == 0) *d_flag_big = 1; return; }
+  if (threadIdx.x == 0) *d_flag_big = 0;
+  int n_pad = 1;
+  while (n_pad < n) n_pad <<= 1;
+  n_pad = max(n_pad, 2);
+  for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
+    fl_sort_key k; k.hi = KEY_SENTINEL_HI; k.lo = KEY_SENTINEL_HI;
+    if (i < n) k = keys[i];
+    s_k[i] = k;
+  }
+  __syncthreads();
+  for (int k = 2; k <= n_pad; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
+        int p = i ^ j;
+        if (p > i) {
+          bool up = (i & k) == 0;
+          fl_sort_key a = s_k[i], b = s_k[p];
+          if (key_less(b, a) == up) { s_k[i] = b; s_k[p] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  // adjacent unique + ordered compaction: each thread owns a contiguous pair of slots
+  const int per = (n_pad + blockDim.x - 1) / blockDim.x;
+  const int b0 = threadIdx.x * per;
+  int cnt = 0;
+  for (int i = b0; i < min(b0 + per, n); ++i) cnt += (i == 0 || !key_dup(s_k[i - 1], s_k[i])) ? 1 : 0;
+  s_scan[threadIdx.x + 1] = cnt;
+  if (threadIdx.x == 0) s_scan[0] = 0;
+  __syncthreads();
+  if (threadIdx.x == 0) for (int i = 1; i <= (int)blockDim.x; ++i) s_scan[i] += s_scan[i - 1];   // 1024 adds; negligible
+  __syncthreads();
+  int pos = s_scan[threadIdx.x];
+  for (int i = b0; i < min(b0 + per, n); ++i)
+    if (i == 0 || !key_dup(s_k[i - 1], s_k[i])) { if (pos < out_cap) out[pos] = key_to_match(s_k[i]); ++pos; }
+  if (threadIdx.x == 0) *d_out_count = s_scan[blockDim.x];
+}
+
+// large path: global bitonic steps + serial-chunk unique
+__global__ void __launch_bounds__(256) k_pad_keys(fl_sort_key* keys, const int* d_n_live, int key_cap, int n_pad) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int n = min(*d_n_live, key_cap);
+  if (i >= n && i < n_pad) { keys[i].hi = KEY_SENTINEL_HI; keys[i].lo = KEY_SENTINEL_HI; }
+}
+__global__ void __launch_bounds__(256) k_bitonic_step(fl_sort_key* keys, int n_pad, int k, int j) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pad) return;
+  int p = i ^ j;
+  if (p > i) {
+    bool up = (i & k) == 0;
+    fl_sort_key a = keys[i], b = keys[p];
+    if (key_less(b, a) == up) { keys[i] = b; keys[p] = a; }
+  }
+}
+__global__ void __launch_bounds__(1024) k_unique_big(const fl_sort_key* __restrict__ keys, const int* __restrict__ d_n_live, int key_cap,
+                                                     fl_match_t* __restrict__ out, int out_cap, int* __restrict__ d_out_count) {
+  __shared__ int s_scan[1024 + 1];
+  __shared__ int s_base;
+  const int n = min(*d_n_live, key_cap);
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  for (int c0 = 0; c0 < n; c0 += 1024) {
+    int i = c0 + threadIdx.x;
+    int keep = (i < n && (i == 0 || !key_dup(keys[i - 1], keys[i]))) ? 1 : 0;
+    s_scan[threadIdx.x + 1] = keep;
+    if (threadIdx.x == 0) s_scan[0] = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) for (int t = 1; t <= 1024; ++t) s_scan[t] += s_scan[t - 1];
+    __syncthreads();
+    int pos = s_base + s_scan[threadIdx.x];
+    if (keep && pos < out_cap) out[pos] = key_to_match(keys[i]);
+    __syncthreads();
+    if (threadIdx.x == 0) s_base += s_scan[1024];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *d_out_count = s_base;
+}
+
+// Host orchestration.  The scratch ints live right after the key array: [n_live, flag_big].
+int fl_launch_sort_unique(const fl_match_t* d_in, int n_lists, int list_cap, const int* d_n_in, fl_sort_key* keys, int key_cap,
+                          fl_match_t* d_out, int out_cap, int* d_out_count, cudaStream_t s) {
+  int launches = 0;
+  int* d_scratch = reinterpret_cast<int*>(keys + key_cap);
+  cudaMemsetAsync(d_scratch, 0, 2 * sizeof(int), s);
+  int total = n_lists * list_cap;
+  if (total > 0) { k_build_keys<<<(total + 255) / 256, 256, 0, s>>>(d_in, n_lists, list_cap, d_n_in, keys, key_cap, d_scratch); ++launches; }
+  k_sort_unique_small<<<1, 1024, 0, s>>>(keys, d_scratch, key_cap, d_out, out_cap, d_out_count, d_scratch + 1); ++launches;
+  return launches;
+}
+
+// second stage, only when the small kernel reported n_live > SORT_SMEM_N (host has read the two scratch ints)
+int fl_launch_sort_unique_big(fl_sort_key* keys, int key_cap, int n_live, fl_match_t* d_out, int out_cap, int* d_out_count, cudaStream_t s) {
+  int launches = 0;
+  int* d_scratch = reinterpret_cast<int*>(keys + key_cap);
+  int n_pad = 2;
+  while (n_pad < n_live) n_pad <<= 1;
+  if (n_pad > key_cap) return -1;
+  k_pad_keys<<<(n_pad + 255) / 256, 256, 0, s>>>(keys, d_scratch, key_cap, n_pad); ++launches;
+  for (int k = 2; k <= n_pad; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) { k_bitonic_step<<<(n_pad + 255) / 256, 256, 0, s>>>(keys, n_pad, k, j); ++launches; }
+  k_unique_big<<<1, 1024, 0, s>>>(keys, d_scratch, key_cap, d_out, out_cap, d_out_count); ++launches;
+  return launches;
+}

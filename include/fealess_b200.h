@@ -1,0 +1,184 @@
+/* fealess_b200 - C ABI of the B200-native LINE-MOD + ICP hot path (drop-in boundary for rlvc/FEALESS).
+ *
+ * Every entry point is plain C: raw pointers, sizes, POD structs, an int status; nothing throws across
+ * it and no OpenCV / torch type appears.  It is what a maintainer of the reference binds instead of the
+ * CPU bodies of (paths relative to /root/reference):
+ *
+ *   fl_create / fl_upload_templates ...... cup_linemod::Detector(modalities, T_pyramid) linemod/linemod.cpp:1348-1354,
+ *                                          addSyntheticTemplate :1636-1642, readClass :1700-1762 (readLinemod
+ *                                          linemod/linemod_if.cpp:36-47 fills the same structures)
+ *   fl_match ............................. cup_linemod::Detector::match linemod/linemod.hpp:324-327, linemod.cpp:1356-1441
+ *   fl_match_shard_device /
+ *   fl_sort_unique_device ................ the two halves of match() (matchClass :1451-1577 | sort+unique :1437-1439)
+ *                                          exposed separately so template shards on several GPUs can exchange
+ *                                          candidate lists in between
+ *   fl_depth_to_3d ....................... cup_d2pc::depthTo3d ICP/depth_to_3d.h:12-13, depth_to_3d.cpp:190-221
+ *   fl_icp_cloud_to_cloud_ex ............. icpCloudToCloud_Ex ICP/ICP.h:165-172, ICP/ICP.cpp:617-809
+ *   fl_detection / fl_detection_batch .... detection() ICP/detection.h:9-11, ICP/detection.cpp:11-254
+ *   fl_nms ............................... nonMaximumSuppression ICP/NMS.h:14-16, ICP/NMS.cpp:6-39
+ *   fl_debug_get ......................... stage-level exports for bit-exact parity checks (no reference equivalent)
+ *
+ * The library is CUDA-only (sm_100a): there is no CPU fallback; every call fails with FL_ERR_CUDA if no
+ * usable device is present.  One handle = one GPU + one stream; calls on a handle are serialised by the
+ * caller, independent handles may be used concurrently.  All functions are synchronous unless their
+ * name ends in _device (those enqueue on the handle's stream and return; fl_sync waits).
+ */
+#ifndef FEALESS_B200_H
+#define FEALESS_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FL_MAX_LEVELS 8
+#define FL_MAX_MODALITIES 4
+
+/* status codes */
+enum {
+  FL_OK = 0,
+  FL_ERR_SIZE = -1,        /* sources/masks count or size mismatch: Detector::match returns -1 (linemod.cpp:1364-1378) */
+  FL_ERR_GEOMETRY = -2,    /* W % T, H % T or (W*H) % 16 violated: CV_Assert in linearize / computeResponseMaps (:1062-1063, :981) */
+  FL_ERR_ROI = -3,         /* rect leaves the image: cv::Mat ROI throw in detection() (ICP/detection.cpp:43-44) */
+  FL_ERR_FEATURES = -4,    /* more than 63 features in a template: CV_Assert (:1137, :1231) */
+  FL_ERR_ARG = -5,         /* null / out-of-range argument */
+  FL_ERR_CAPACITY = -6,    /* an internal or caller buffer was too small; *count still reports the needed size */
+  FL_ERR_CUDA = -7,        /* CUDA runtime error or no device; fl_last_error() has the text */
+  FL_ERR_STATE = -8        /* call order violated (e.g. match before upload) */
+};
+
+enum { FL_MODALITY_COLOR_GRADIENT = 0, FL_MODALITY_DEPTH_NORMAL = 1 };
+
+/* cup_linemod::Match (linemod.hpp:253-286) with class_id as an index into the uploaded class list */
+typedef struct { int32_t x, y; float similarity; int32_t class_idx; int32_t template_id; } fl_match_t;
+
+/* cup_linemod::Feature (linemod.hpp:32-43) */
+typedef struct { int32_t x, y, label; } fl_feature_t;
+
+/* cup_linemod::Template (linemod.hpp:47-58); features are [feature_begin, feature_begin+feature_count) of the feature array */
+typedef struct { int32_t width, height, offset_x, offset_y, pyramid_level, feature_begin, feature_count; } fl_template_hdr_t;
+
+typedef struct {
+  int32_t n_levels;                         /* T_at_level.size() */
+  int32_t T[FL_MAX_LEVELS];                 /* default {5, 8} (linemod.cpp:1820) */
+  int32_t n_modalities;
+  int32_t modality_kind[FL_MAX_MODALITIES]; /* default {COLOR_GRADIENT, DEPTH_NORMAL} (getDefaultLINEMOD :1829-1835) */
+  float   weak_threshold;                   /* ColorGradient: 10 (:515-520) */
+  int32_t distance_threshold;               /* DepthNormal: 2000 (:827-833) */
+  int32_t difference_threshold;             /* DepthNormal: 50 */
+  int32_t max_width, max_height;            /* largest frame the handle must accept (workspace is sized once) */
+  int32_t max_candidates;                   /* capacity of the candidate / match buffers on the device */
+  int32_t device;                           /* CUDA device ordinal */
+} fl_params_t;
+
+typedef struct { float fx, fy, cx, cy; } fl_intrinsics_t;      /* TCamIntrinsicParam (CadReco/lotus_common.h:41-50), the 4 used fields */
+typedef struct { int32_t x, y, width, height; } fl_rect_t;     /* cv::Rect_<int> */
+typedef struct { int32_t icp_it_thr; float dist_mean_thr, dist_diff_thr; } fl_icp_params_t;  /* 10, 0.5, 0.01 (CadReco/obj_reco_lmicp.cpp:52-55) */
+
+typedef struct {
+  float R[9];            /* R_final row-major (detection) or R (icpCloudToCloud_Ex) */
+  float T[3];            /* T_final / T, millimetres */
+  float dist_mean;       /* return value of icpCloudToCloud_Ex (-1 if fewer than 3 points) */
+  float inlier_ratio;    /* px_inliers_ratio */
+  int32_t iterations;
+  int32_t n_points;      /* paired valid points that entered ICP */
+  int32_t status;        /* FL_OK or FL_ERR_ROI for this hypothesis */
+} fl_icp_result_t;
+
+typedef struct fl_handle fl_handle;
+
+/* ---- lifecycle ---------------------------------------------------------------------------------- */
+void fl_default_params(fl_params_t* p);
+int  fl_create(const fl_params_t* params, fl_handle** out);
+int  fl_destroy(fl_handle* h);
+const char* fl_last_error(void);
+const char* fl_version(void);
+int  fl_sync(fl_handle* h);
+/* the CUDA stream (cudaStream_t) every _device call of this handle is enqueued on */
+void* fl_stream(fl_handle* h);
+
+/* ---- template database ---------------------------------------------------------------------------
+ * headers: n_templates * n_levels * n_modalities entries, template-major then level*n_modalities + modality
+ * (the TemplatePyramid order of linemod.hpp:370-375); class_of[t] = class index of template t, templates of one
+ * class contiguous, template_id = rank inside its class (matchClass, linemod.cpp:1458); pose13 (nullable) =
+ * 13 floats per template (TemplatePoseInfo, :1617-1634) kept host-side for fl_get_pose_info. */
+int fl_upload_templates(fl_handle* h, int32_t n_templates, const fl_template_hdr_t* headers,
+                        const fl_feature_t* features, int32_t n_features, const int32_t* class_of,
+                        const float* pose13);
+int fl_num_templates(fl_handle* h);
+int fl_get_pose_info(fl_handle* h, int32_t class_idx, int32_t template_id, float out13[13]);
+
+/* ---- Detector::match -------------------------------------------------------------------------------
+ * Host buffers in, host matches out (sorted by the canonical total order, duplicates pruned).
+ * bgr: 8UC3 rows of bgr_stride bytes; depth: 16UC1 rows of depth_stride bytes (mm); either may be NULL if no
+ * modality of that kind is configured.  masks: NULL or n_modalities pointers (each NULL or W*H dense u8, nonzero =
+ * keep).  class_filter: NULL/0 = all classes.  quantized_out: NULL or n_levels*n_modalities host pointers
+ * (index level*n_modalities + modality) receiving the quantised images, each (W>>l)*(H>>l) bytes.
+ * *count = number of matches found (may exceed capacity -> FL_ERR_CAPACITY, first `capacity` are written). */
+int fl_match(fl_handle* h, const uint8_t* bgr, size_t bgr_stride, const uint16_t* depth, size_t depth_stride,
+             int32_t W, int32_t H, const uint8_t* const* masks, float threshold,
+             const int32_t* class_filter, int32_t n_filter,
+             fl_match_t* out, int32_t capacity, int32_t* count, uint8_t* const* quantized_out);
+
+/* Same computation with the frame already resident in device memory (dense rows).  d_masks as above but device
+ * pointers.  Results stay on the device; fl_match_fetch copies them out (and synchronises). */
+int fl_match_device(fl_handle* h, const void* d_bgr, const void* d_depth, int32_t W, int32_t H,
+                    const void* const* d_masks, float threshold, const int32_t* class_filter, int32_t n_filter);
+int fl_match_fetch(fl_handle* h, fl_match_t* out, int32_t capacity, int32_t* count);
+
+/* Template-sharded matching (one handle per GPU holds a shard of the templates):
+ * fl_match_shard_device runs the front end + matchClass over this handle's templates and writes the UNSORTED
+ * candidates into d_candidates[capacity] and their number into d_count[1] (both device memory, caller owned,
+ * e.g. torch tensors that are then all-gathered).  fl_sort_unique_device sorts + prunes n_in records of d_in
+ * (device) into d_out / d_out_count (device; d_out may alias d_in).  n_in is read from d_n_in[0..n_lists) when
+ * d_n_in is not NULL: d_in then holds n_lists lists of `list_capacity` records each (the all-gather layout). */
+int fl_match_shard_device(fl_handle* h, const void* d_bgr, const void* d_depth, int32_t W, int32_t H,
+                          const void* const* d_masks, float threshold, const int32_t* class_filter, int32_t n_filter,
+                          fl_match_t* d_candidates, int32_t capacity, int32_t* d_count);
+int fl_sort_unique_device(fl_handle* h, const fl_match_t* d_in, int32_t n_lists, int32_t list_capacity,
+                          const int32_t* d_n_in, fl_match_t* d_out, int32_t out_capacity, int32_t* d_out_count);
+
+/* ---- ICP ------------------------------------------------------------------------------------------ */
+/* cup_d2pc::depthTo3d for 16UC1 input: out3 = H*W*3 floats in METRES, 0 depth -> NaN (depth_to_3d.cpp:99-137, 244-260) */
+int fl_depth_to_3d(fl_handle* h, const uint16_t* depth, size_t depth_stride, int32_t W, int32_t H,
+                   fl_intrinsics_t K, float* out3);
+/* icpCloudToCloud_Ex on host clouds (n*3 floats each, mm).  Requires n_ref >= n_model (the reference's lock-step loops). */
+int fl_icp_cloud_to_cloud_ex(fl_handle* h, const float* pts_ref, int32_t n_ref, const float* pts_model, int32_t n_model,
+                             fl_icp_params_t p, fl_icp_result_t* out);
+/* detection() for n hypotheses against one reference depth frame.  model_depth[i] points at pixel (0,0) of the i-th
+ * rendered template depth image (u16 mm, rows of model_stride[i] bytes, same W x H as the frame); only rect_model[i] is read. */
+int fl_detection_batch(fl_handle* h, const uint16_t* ref_depth, size_t ref_stride, int32_t W, int32_t H, fl_intrinsics_t K_ref,
+                       const uint16_t* const* model_depth, const size_t* model_stride,
+                       const fl_rect_t* rect_model, const fl_rect_t* rect_ref,
+                       const float* r_match9, const float* t_match3, const float* d_match, int32_t n,
+                       fl_icp_params_t p, fl_icp_result_t* out);
+/* single-hypothesis convenience with the reference's argument order (ICP/detection.h:9-11) */
+int fl_detection(fl_handle* h, const uint16_t* model_depth, size_t model_stride, const uint16_t* ref_depth, size_t ref_stride,
+                 int32_t W, int32_t H, fl_intrinsics_t K_ref, fl_rect_t rect_model, fl_rect_t rect_ref,
+                 int32_t icp_it_thr, float dist_mean_thr, float dist_diff_thr,
+                 const float r_match[9], const float t_match[3], float d_match, float T_final[3], float R_final[9]);
+/* nonMaximumSuppression over n refined objects given in the caller's order: t3 (n*3), number of model points, icp_dist.
+ * out_idx receives, per emitted PoseResult, the index of the object it was taken from; returns the count (>= 0) or < 0. */
+int fl_nms(fl_handle* h, const float* t3, const int32_t* n_model_pts, const float* icp_dist, int32_t n,
+           float th_obj_dist, int32_t* out_idx);
+
+/* ---- stage-level debug exports (host copies of device intermediates of the LAST match call) -------- */
+enum {
+  FL_DBG_QUANTIZED = 0,     /* (level, modality)         -> (W>>l)*(H>>l) u8 */
+  FL_DBG_SPREAD = 1,        /* (level, modality)         -> same size u8 (only kept when fl_debug_keep_spread(h,1)) */
+  FL_DBG_LINEAR_MEMORY = 2, /* (level, modality, label)  -> T*T*(W/T)*(H/T) u8 */
+  FL_DBG_SIMILARITY = 3     /* (template index)          -> (W/T)*(H/T) u16 total similarity at the coarsest level */
+};
+int fl_debug_keep_spread(fl_handle* h, int enable);
+int fl_debug_get(fl_handle* h, int what, int32_t a, int32_t b, int32_t c, void* host_out, size_t bytes);
+/* number of kernels launched by this handle since creation (bench.py reports the per-step delta) */
+int64_t fl_launch_count(fl_handle* h);
+/* per-stage device timing of the last fl_match*(): ms for front end, global similarity, refinement, sort (needs fl_profile(h,1)) */
+int fl_profile(fl_handle* h, int enable);
+int fl_last_stage_ms(fl_handle* h, float out4[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FEALESS_B200_H */

@@ -786,7 +786,7 @@ void flo_svd3_rot(const float cov[9], float R[9]) {
         for (int k = 0; k < 3; ++k) p += (double)At[i][k] * At[j][k];
         if (fabs(p) <= eps * sqrt(a * b)) continue;
         p *= 2;
-        double beta = a - b, gamma = hypot(p, beta);
+        double beta = a - b, gamma = sqrt(p * p + beta * beta);   /* (OpenCV calls hypot; same to well below fp32 resolution, and sqrt is bit-reproducible on the GPU) */
         float c, s;
         if (beta < 0) { double delta = (gamma - beta) * 0.5; s = (float)sqrt(delta / gamma); c = (float)(p / (gamma * s * 2)); }
         else { c = (float)sqrt((gamma + beta) / (gamma * 2)); s = (float)(p / (gamma * c * 2)); }
