@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py - the hot-path benchmark of fealess_b200 (contract: see the task statement / DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--templates n]
+
+Workload (BASELINE.json configs[1], "C2"): LINE-MOD match-only on a synthetic 640x480 RGB-D frame against 8,000
+templates (2 pyramid levels, T = {5, 8}, colour-gradient + depth-normal modalities), threshold 75 %.  A "step" is one
+pass of ``Detector::match`` over one frame: front end (quantise, spread, response maps, linear memories), global
+similarity of every template at the coarsest level, local refinement of the candidates, sort + duplicate pruning.
+
+* ``value``  : template.px evals/s with the frame already resident in HBM (device-timed, CUDA events on the launching
+               stream, L2 flushed between steps).  One eval = one (template, coarsest-level cell) total-similarity
+               evaluation: 8,000 x 1,200 = 9.6 M per frame per GPU.
+* ``e2e``    : the same metric through the reference-facing C-ABI call ``fl_match`` with HOST buffers (host->device
+               copy of the frame and device->host read of the match list inside the timed region).
+* N > 1      : weak scaling, templates sharded (every rank holds 8,000 templates of an N x 8,000 set and sees the
+               same frame), one NCCL all-gather of candidate blocks per frame, sort + unique on every rank.
+* ``--impl reference``: the reference's CPU path (the C restatement under oracle/, since the reference itself cannot be
+               built here) on the host cores, OpenMP over templates, same metric and workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+W, H, T = 640, 480, (5, 8)
+THRESHOLD = 75.0
+FEATURES_COARSE = 62            # 2 modalities x 31 features at the coarsest of 2 levels
+CELLS = (W // 2 // T[1]) * (H // 2 // T[1])     # 40 x 30 = 1,200
+FRONT_END_BYTES = 5 * W * H + 2 * 8 * (W * H + (W // 2) * (H // 2))   # 7,680,000 B
+N_FRAMES = 8                    # distinct synthetic frames cycled through the steps
+METRIC = "template.px evals/s (LINE-MOD match, 640x480, 8k templates/GPU)"
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), float(p.get("sm_max_mhz", 1965.0)), "measured"
+    except Exception:
+        return 6650.0, 1965.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples = []
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.samples.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(s[0]) for s in self.samples if len(s) >= 6 and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) >= 6 and s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples if len(s) >= 6 for i in range(4) if s[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def make_inputs(n_templates: int, seed: int = 1):
+    """Frames + a template set with ~1 % planted templates.  The quantised images used for planting come from the product's
+    own front end when a GPU is present (our arm) or from the CPU path (reference arm); both are bit-identical."""
+    from fealess_b200 import synth
+    frames = [synth.make_frame(W, H, i) for i in range(N_FRAMES)]
+    return frames, synth
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: oracle/ (C restatement of the reference's CPU path)
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_time_frames(frames, tset, n_threads: int, steps: int, warmup: int):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import fl_oracle_py as F
+    det = F.Detector(T)
+    det.set_templates(tset)
+    times = []
+    n_matches = 0
+    for i in range(warmup + steps):
+        b, d = frames[i % len(frames)]
+        t0 = time.perf_counter()
+        det.process(b, d)
+        m = det.match(THRESHOLD, n_threads=n_threads)
+        t1 = time.perf_counter()
+        if i >= warmup:
+            times.append(t1 - t0)
+            n_matches = len(m)
+    return times, n_matches
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import fl_oracle_py as F
+    frames, synth = make_inputs(args.templates)
+    det = F.Detector(T)
+    det.process(*frames[0])
+    q = [det.quantized(l, m) for l in range(2) for m in range(2)]
+    tset = synth.make_templates(args.templates, W, H, T, seed=1, quantized=q, planted_fraction=0.01)
+    cores = os.cpu_count() or 1
+    times, n_matches = cpu_time_frames(frames, tset, cores, args.steps, args.warmup)
+    tot = float(np.sum(times))
+    evals = args.templates * CELLS * args.steps
+    v = evals / tot
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "C2: LINE-MOD match-only, 640x480, %d templates, L=2, T={5,8}, threshold 75" % args.templates,
+                       "frames_per_s": args.steps / tot, "matches_last_frame": n_matches},
+            "cpu_baseline": {"value": v, "unit": "evals/s", "cores": cores, "kind": "port",
+                             "sample": "full workload, every step = one whole frame over all %d templates; front end single-threaded, "
+                                       "matchClass OpenMP over templates (the reference itself is single-threaded)" % args.templates},
+            "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import fealess_b200 as fb
+    from fealess_b200 import sharded
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - fealess_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    hbm_gbs, sm_max_mhz, peak_src = load_peaks()
+
+    frames, synth = make_inputs(args.templates)
+    n_total = args.templates * world                                   # weak scaling: per-GPU work fixed
+    cap = 1 << 14
+    h = fb.Handle(T, (0, 1), W, H, max_candidates=max(1 << 16, world * (cap + 1) + 16), device=local)
+    # quantised images for planting come from the product's own front end (empty template set)
+    h.upload_templates(synth.make_templates(0))
+    rc, _, q = h.match(frames[0][0], frames[0][1], THRESHOLD, want_quantized=True)
+    assert rc == 0
+    tset = synth.make_templates(n_total, W, H, T, seed=1, quantized=q, planted_fraction=0.01)
+    sm = sharded.ShardedMatcher(h, tset, rank, world, capacity=cap, device=dev)
+    stream = sm.stream
+    d_frames = [(torch.from_numpy(b).to(dev), torch.from_numpy(d.view(np.int16)).to(dev)) for b, d in frames]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+    torch.cuda.synchronize()
+    h.profile(True)
+
+    def step(i, timed):
+        tb, td = d_frames[i % N_FRAMES]
+        with torch.cuda.stream(stream):
+            flush.zero_()                                               # L2 flush between steps, outside the timed events
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+        if world == 1:
+            h.match_device(tb.data_ptr(), td.data_ptr(), W, H, THRESHOLD)
+        else:
+            sm.match_device(tb.data_ptr(), td.data_ptr(), W, H, THRESHOLD)
+        with torch.cuda.stream(stream):
+            e1.record(stream)
+        return e0, e1
+
+    for i in range(args.warmup):
+        step(i, False)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    torch.cuda.synchronize()
+    launches0 = h.launch_count()
+    evs, stage = [], np.zeros(4)
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        evs.append(step(args.warmup + i, True))
+        stage += h.last_stage_ms() if world == 1 else 0
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall1 = time.perf_counter()
+    launches = h.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = float(sum(a.elapsed_time(b) for a, b in evs))
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    n_matches = len(h.match_fetch()) if world == 1 else len(sm.fetch())
+    evals_per_step = args.templates * world * CELLS
+    value = evals_per_step * args.steps / (dev_ms * 1e-3)
+
+    # ---- e2e: host buffers through the C ABI (rank-local; N > 1 adds the host copies to the sharded path) ----
+    e2e = None
+    if world == 1:
+        for i in range(3):
+            h.match(frames[i % N_FRAMES][0], frames[i % N_FRAMES][1], THRESHOLD, capacity=4096)
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            b, d = frames[i % N_FRAMES]
+            rc, m = h.match(b, d, THRESHOLD, capacity=4096)
+        t1 = time.perf_counter()
+        e2e = {"value": evals_per_step * args.steps / (t1 - t0), "unit": "evals/s", "h2d_bytes_per_step": W * H * 5,
+               "d2h_bytes_per_step": 12 + 1024 * 20, "frames_per_s": args.steps / (t1 - t0), "timer": "host wall clock around fl_match"}
+    else:
+        pin = [(torch.from_numpy(b).pin_memory(), torch.from_numpy(d.view(np.int16)).pin_memory()) for b, d in frames]
+        tb, td = d_frames[0]
+        torch.cuda.synchronize(); dist.barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            pb, pd = pin[i % N_FRAMES]
+            with torch.cuda.stream(stream):
+                tb.copy_(pb, non_blocking=True); td.copy_(pd, non_blocking=True)
+            sm.match_device(tb.data_ptr(), td.data_ptr(), W, H, THRESHOLD)
+            m = sm.fetch()
+        torch.cuda.synchronize(); dist.barrier()
+        t1 = time.perf_counter()
+        tt = torch.tensor([t1 - t0], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": evals_per_step * args.steps / float(tt.item()), "unit": "evals/s", "h2d_bytes_per_step": W * H * 5,
+               "d2h_bytes_per_step": 4 + len(m) * 20, "frames_per_s": args.steps / float(tt.item()), "timer": "host wall clock, max over ranks"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (global similarity) + the HBM-bound front end ----
+    roofline = None
+    extra = {}
+    if world == 1:
+        st = stage / args.steps                                          # ms: front end, similarity, refine, sort
+        sm_clk = (clocks or {}).get("sm_mhz") or sm_max_mhz
+        smem_peak = 148 * 128 * sm_clk * 1e6 / 1e9                       # GB/s: 148 SMs x 128 B/clk x achieved SM clock
+        alg_bytes = args.templates * CELLS * FEATURES_COARSE             # 62 B per eval
+        ach = alg_bytes / (st[1] * 1e-3) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get("k_similarity_global")
+        except Exception:
+            pass
+        roofline = {"kernel": "similarity_global", "bound": "smem", "achieved": ach, "peak": smem_peak, "unit": "GB/s", "frac": ach / smem_peak,
+                    "traffic": traffic, "kernel_ms": float(st[1]), "peak_source": "148 SM x 128 B/clk x %.0f MHz (SM clock sampled under load); "
+                    "MEASURED_PEAKS.json has no shared-memory figure" % sm_clk, "algorithmic_bytes_per_launch": alg_bytes}
+        fe = FRONT_END_BYTES / (st[0] * 1e-3) / 1e9
+        extra["roofline_front_end"] = {"kernels": "color_quantize, pyrdown, depth_quantize, resize_nn, spread_lm (x4)", "bound": "hbm",
+                                       "achieved": fe, "peak": hbm_gbs, "unit": "GB/s", "frac": fe / hbm_gbs, "stage_ms": float(st[0]),
+                                       "algorithmic_bytes": FRONT_END_BYTES, "peak_source": peak_src + " MEASURED_PEAKS.json hbm_gbs",
+                                       "note": "7.7 MB per VGA frame = 1.2 us at peak: this stage is launch-latency bound, not bandwidth bound"}
+        extra["stage_ms"] = {"front_end": float(st[0]), "similarity_global": float(st[1]), "refine": float(st[2]), "sort_unique_and_fetch": float(st[3])}
+
+    # ---- CPU baseline (rank 0, N = 1 only): the C restatement, single thread = the reference's execution model ----
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        ct, _ = cpu_time_frames(frames, tset, 1, 8, 2)
+        cv = args.templates * CELLS * len(ct) / float(np.sum(ct))
+        cpu = {"value": cv, "unit": "evals/s", "cores": 1, "kind": "port", "frames_per_s": len(ct) / float(np.sum(ct)),
+               "sample": "8 whole frames (after 2 warm-up) of the same workload, all %d templates, single thread" % args.templates}
+
+    # ---- ICP (BASELINE configs[2], C3): 256 hypotheses x ~10k points, reported beside the headline ----
+    icp = None
+    if world == 1 and not args.no_icp:
+        icp = bench_icp(h, synth)
+
+    line = {"metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic",
+            "config": {"workload": "C2: LINE-MOD match-only, 640x480, %d templates per GPU (%d total), L=2, T={5,8}, threshold 75" % (args.templates, n_total),
+                       "l2": "flushed between steps (256 MB write)", "frames_per_s": args.steps / (dev_ms * 1e-3),
+                       "matches_last_frame": n_matches, "parallelism": "template-sharded x%d, 1 all-gather/frame" % world if world > 1 else "single GPU"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "wall_s_timed_region": wall1 - wall0}
+    line.update(extra)
+    if icp:
+        line["icp"] = icp
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_icp(h, synth, n_hyp: int = 256):
+    """C3: n_hyp pose hypotheses, 100x100-pixel crops (~10k points each) against one 640x480 reference depth frame."""
+    import torch
+    base = [synth.make_icp_pair(W, H, seed=s, max_rot_deg=8, max_shift_mm=10, rect_wh=(100, 100)) for s in range(16)]
+    ref = base[0][1]
+    mds, rms, rrs, Rs, ts = [], [], [], [], []
+    for i in range(n_hyp):
+        md, rf, rm, rr, p = base[i % 16]
+        mds.append(md); rms.append(rm); rrs.append(rr)
+        Rs.append(p[:12].reshape(3, 4)[:, :3]); ts.append(p[:12].reshape(3, 4)[:, 3])
+    K = (608.0, 608.0, 320.0, 240.0)
+    h.detection_batch(ref, K, mds, rms, rrs, Rs, ts)          # warm-up (allocates the workspace)
+    times = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        res = h.detection_batch(ref, K, mds, rms, rrs, Rs, ts)
+        times.append(time.perf_counter() - t0)
+    its = int(res["iterations"].sum())
+    t = float(np.min(times))
+    return {"workload": "C3: %d hypotheses x 100x100 crops (~%d points) vs one 640x480 depth frame, <=10 iterations" % (n_hyp, int(res["n_points"].mean())),
+            "icp_iters_per_s": its / t, "hypotheses_per_s": n_hyp / t, "total_iterations": its, "batch_ms": 1e3 * t,
+            "timer": "host wall clock around fl_detection_batch (includes H2D of crops and D2H of poses)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--templates", type=int, default=8000, help="templates per GPU")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-icp", action="store_true", help="skip the ICP side benchmark")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)            # ~0.1 s per step on 8 host threads: the default run ends within seconds
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

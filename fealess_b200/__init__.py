@@ -41,7 +41,7 @@ ICP_RESULT_DTYPE = np.dtype([("R", "<f4", (9,)), ("T", "<f4", (3,)), ("dist_mean
 # every symbol include/fealess_b200.h declares (tests check that the built library exports all of them)
 EXPORTED_SYMBOLS = [
     "fl_default_params", "fl_create", "fl_destroy", "fl_last_error", "fl_version", "fl_sync", "fl_stream",
-    "fl_upload_templates", "fl_num_templates", "fl_get_pose_info", "fl_match", "fl_match_device", "fl_match_fetch",
+    "fl_upload_templates", "fl_set_template_ids", "fl_num_templates", "fl_get_pose_info", "fl_match", "fl_match_device", "fl_match_fetch",
     "fl_match_shard_device", "fl_sort_unique_device", "fl_depth_to_3d", "fl_icp_cloud_to_cloud_ex",
     "fl_detection_batch", "fl_detection", "fl_nms", "fl_debug_keep_spread", "fl_debug_get", "fl_launch_count",
     "fl_profile", "fl_last_stage_ms",
@@ -157,6 +157,10 @@ class Handle:
         pose = None if tset.pose13 is None else np.ascontiguousarray(tset.pose13, np.float32)
         _check(lib().fl_upload_templates(self._h, int(tset.n_templates), _p(hdr), _p(ft), int(ft.shape[0]), _p(co), _p(pose)),
                "fl_upload_templates")
+
+    def set_template_ids(self, ids) -> None:
+        a = np.ascontiguousarray(ids, np.int32)
+        _check(lib().fl_set_template_ids(self._h, _p(a)), "fl_set_template_ids")
 
     def num_templates(self) -> int:
         return lib().fl_num_templates(self._h)
@@ -336,11 +340,18 @@ class Detector:
                  max_width=640, max_height=480, device=0, max_candidates=1 << 16):
         self.modalities = list(modalities)
         self.T_at_level = [int(t) for t in T_pyramid]
-        self._handle = Handle(self.T_at_level, [_MODALITY_KIND[m] for m in modalities], max_width, max_height, max_candidates, device)
+        self._handle_args = (self.T_at_level, [_MODALITY_KIND[m] for m in modalities], max_width, max_height, max_candidates, device)
+        self._handle_obj = None     # created on first use so that argument checks behave like the reference without a GPU
         self._classes = {}          # class_id -> list of template pyramids
         self._poses = {}            # class_id -> list of 13-float arrays
         self._dirty = True
         self._class_order: List[str] = []
+
+    @property
+    def _handle(self) -> Handle:
+        if self._handle_obj is None:
+            self._handle_obj = Handle(*self._handle_args)
+        return self._handle_obj
 
     # -- accessors (linemod.hpp:357-381) --
     def getModalities(self):

@@ -25,7 +25,8 @@ struct fl_handle {
   // template database
   int n_templates, n_features, n_classes;
   fl_template_hdr_t* d_hdr; fl_feature_t* d_feat; int32_t* d_class_of; int32_t* d_class_first; uint8_t* d_class_enabled;
-  fl_pfeat* d_pfeat;
+  fl_pfeat* d_pfeat; int32_t* d_tid_of;
+  std::vector<int32_t> tid_of_h;
   std::vector<int32_t> class_first_h, class_of_h;
   std::vector<float> pose13_h;
   std::vector<uint8_t> class_enabled_h;
@@ -108,6 +109,7 @@ extern "C" int fl_create(const fl_params_t* params, fl_handle** out) {
   h->p = p; h->launches = 0; h->gW = h->gH = 0; h->packed = false; h->have_result = false; h->profile = false; h->keep_spread = false;
   h->n_templates = h->n_features = h->n_classes = 0;
   h->d_hdr = nullptr; h->d_feat = nullptr; h->d_class_of = nullptr; h->d_class_first = nullptr; h->d_class_enabled = nullptr; h->d_pfeat = nullptr;
+  h->d_tid_of = nullptr;
   h->icp_hyp_cap = h->icp_pts_cap = 0; memset(&h->icp, 0, sizeof h->icp);
   h->d_hyps = nullptr; h->d_t_init = nullptr; h->d_results = nullptr; h->d_model_crops = nullptr; h->d_ref_depth = nullptr; h->ref_depth_cap = 0;
   h->h_model_crops = nullptr; h->h_hyps = nullptr; h->h_results = nullptr; h->h_crop_cap = 0;
@@ -155,7 +157,9 @@ static void icp_free(fl_handle* h) {
 
 static void free_templates(fl_handle* h) {
   cudaFree(h->d_hdr); cudaFree(h->d_feat); cudaFree(h->d_class_of); cudaFree(h->d_class_first); cudaFree(h->d_class_enabled); cudaFree(h->d_pfeat);
+  cudaFree(h->d_tid_of);
   h->d_hdr = nullptr; h->d_feat = nullptr; h->d_class_of = nullptr; h->d_class_first = nullptr; h->d_class_enabled = nullptr; h->d_pfeat = nullptr;
+  h->d_tid_of = nullptr;
   h->n_templates = h->n_features = h->n_classes = 0; h->packed = false;
 }
 
@@ -215,6 +219,10 @@ extern "C" int fl_upload_templates(fl_handle* h, int32_t n_templates, const fl_t
   if (n_features) FL_CUDA(cudaMemcpy(h->d_feat, features, (size_t)n_features * sizeof(fl_feature_t), cudaMemcpyHostToDevice));
   if (n_templates) FL_CUDA(cudaMemcpy(h->d_class_of, class_of, (size_t)n_templates * sizeof(int32_t), cudaMemcpyHostToDevice));
   if (nc) FL_CUDA(cudaMemcpy(h->d_class_first, first.data(), (size_t)nc * sizeof(int32_t), cudaMemcpyHostToDevice));
+  h->tid_of_h.resize((size_t)n_templates);
+  for (int t = 0; t < n_templates; ++t) h->tid_of_h[t] = t - first[class_of[t]];                // matchClass numbering (:1458)
+  TRY(dalloc(&h->d_tid_of, (size_t)n_templates));
+  if (n_templates) FL_CUDA(cudaMemcpy(h->d_tid_of, h->tid_of_h.data(), (size_t)n_templates * sizeof(int32_t), cudaMemcpyHostToDevice));
   h->n_templates = n_templates; h->n_features = n_features; h->n_classes = nc;
   h->class_first_h = first; h->class_of_h.assign(class_of, class_of + n_templates);
   h->pose13_h.clear();
@@ -224,12 +232,25 @@ extern "C" int fl_upload_templates(fl_handle* h, int32_t n_templates, const fl_t
   return FL_OK;
 }
 
+extern "C" int fl_set_template_ids(fl_handle* h, const int32_t* template_ids) {
+  if (!h || !template_ids) return FL_ERR_ARG;
+  if (h->n_templates == 0) return FL_OK;
+  FL_CUDA(cudaSetDevice(h->p.device));
+  FL_CUDA(cudaStreamSynchronize(h->stream));
+  for (int t = 0; t < h->n_templates; ++t) if (template_ids[t] < 0) return FL_ERR_ARG;
+  h->tid_of_h.assign(template_ids, template_ids + h->n_templates);
+  FL_CUDA(cudaMemcpy(h->d_tid_of, template_ids, (size_t)h->n_templates * sizeof(int32_t), cudaMemcpyHostToDevice));
+  return FL_OK;
+}
+
 extern "C" int fl_get_pose_info(fl_handle* h, int32_t class_idx, int32_t template_id, float out13[13]) {
   if (!h || !out13 || class_idx < 0 || class_idx >= h->n_classes || h->pose13_h.empty()) return FL_ERR_ARG;
   // the reference keeps ONE flat TemplatePoseInfo indexed by the per-class template_id (linemod.cpp:1624-1634), which is
   // wrong for more than one class (SURVEY A.6 iv); this ABI keys the pose by (class, template_id).
-  int t = h->class_first_h[class_idx] + template_id;
-  if (template_id < 0 || t >= h->n_templates || h->class_of_h[t] != class_idx) return FL_ERR_ARG;
+  int t = -1;
+  for (int k = h->class_first_h[class_idx]; k >= 0 && k < h->n_templates && h->class_of_h[k] == class_idx; ++k)
+    if (h->tid_of_h[k] == template_id) { t = k; break; }
+  if (t < 0) return FL_ERR_ARG;
   memcpy(out13, &h->pose13_h[(size_t)t * 13], 13 * sizeof(float));
   return FL_OK;
 }
@@ -238,7 +259,7 @@ static fl_tdb make_tdb(fl_handle* h) {
   fl_tdb db;
   db.n_templates = h->n_templates; db.L = h->p.n_levels; db.M = h->p.n_modalities; db.n_classes = h->n_classes;
   db.hdr = h->d_hdr; db.feat = h->d_feat; db.class_of = h->d_class_of; db.class_first = h->d_class_first;
-  db.class_enabled = h->d_class_enabled; db.pfeat = h->d_pfeat;
+  db.class_enabled = h->d_class_enabled; db.pfeat = h->d_pfeat; db.tid_of = h->d_tid_of;
   return db;
 }
 

@@ -49,6 +49,7 @@ struct fl_tdb {                     // device template database
   const fl_feature_t* feat;         // [n_features]
   const int32_t* class_of;          // [n_templates]
   const int32_t* class_first;       // [n_classes]
+  const int32_t* tid_of;            // [n_templates] per-class template_id reported in matches (global id for shards)
   const uint8_t* class_enabled;     // [n_classes] (class filter of the current call)
   fl_pfeat* pfeat;                  // [n_features] packed for the current geometry
 };

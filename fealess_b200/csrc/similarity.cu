@@ -102,7 +102,9 @@ __global__ void __launch_bounds__(SG_THREADS) k_similarity_global(fl_tdb db, fl_
           fl_match_t mt;
           mt.x = c * g.T + off; mt.y = r * g.T + off;
           mt.similarity = __fadd_rn(__fdiv_rn(__fmul_rn((float)raw, 100.f), (float)(4 * nf)), 0.5f);
-          mt.class_idx = cls; mt.template_id = t - db.class_first[cls];
+          // candidates carry the handle-local template index until the last stage rewrites it to the per-class
+          // template_id (which may be a global id when this handle holds only a shard of the templates)
+          mt.class_idx = cls; mt.template_id = db.L == 1 ? db.tid_of[t] : t;
           cand[slot] = mt;
         }
       }
@@ -134,7 +136,7 @@ __global__ void __launch_bounds__(RF_THREADS) k_refine_level(fl_tdb db, fl_level
   for (int ci = blockIdx.x; ci < n; ci += gridDim.x) {
     fl_match_t mt = cand[ci];
     if (mt.template_id < 0) continue;                              // dropped at a coarser level (:1570-1572)
-    const int t = db.class_first[mt.class_idx] + mt.template_id;
+    const int t = mt.template_id;                                  // handle-local template index (see k_similarity_global)
     const fl_template_hdr_t* hdr = db.hdr + ((size_t)t * db.L + level) * db.M;
     const int T = g.T, border = 8 * T;
     int x = mt.x * 2 + 1, y = mt.y * 2 + 1;                        // :1525-1534
@@ -189,7 +191,8 @@ __global__ void __launch_bounds__(RF_THREADS) k_refine_level(fl_tdb db, fl_level
       mt.x = (x / T - 8 + bc) * T + off;                           // :1564-1566
       mt.y = (y / T - 8 + br) * T + off;
       mt.similarity = __fdiv_rn(__fmul_rn((float)best, 100.f), (float)(4 * nf));
-      if (mt.similarity < threshold) mt.template_id = -1 - mt.template_id;   // mark dropped (remove_if :1570)
+      if (mt.similarity < threshold) mt.template_id = -1;         // mark dropped (remove_if :1570)
+      else if (level == 0) mt.template_id = db.tid_of[t];         // final per-class template_id
       cand[ci] = mt;
     }
     __syncthreads();

@@ -1,0 +1,123 @@
+"""Template-sharded matching across GPUs: one process per GPU, ``torch.distributed`` for the plumbing.
+
+Templates are independent units (the ``matchClass`` loop, reference linemod/linemod.cpp:1458), so they are dealt
+round-robin by global template index; every rank runs the (cheap) front end on the whole frame redundantly and
+``matchClass`` on its shard.  The only exchange step of the path is the candidate list: ONE all-gather per frame of a
+fixed-capacity block ``[header | records]`` (20-byte ``fl_match_t`` records, count in the header), after which every rank
+sorts + prunes the union redundantly (``fl_sort_unique_device``), so no broadcast is needed and the result is
+shard-invariant.
+
+The block packing / gathering / splitting helpers work on CPU tensors with the ``gloo`` backend too; that is how the
+N > 1 host logic is tested without GPUs (tests/test_sharding_gloo.py).
+"""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import numpy as np
+
+from . import synth
+
+RECORD_INTS = 5  # fl_match_t = 5 x int32-sized fields
+
+
+def shard_indices(n_templates: int, rank: int, world: int) -> np.ndarray:
+    """Global template indices owned by ``rank`` (round-robin balances the data-dependent candidate counts)."""
+    return np.arange(rank, n_templates, world, dtype=np.int64)
+
+
+def shard_template_set(tset: "synth.TemplateSet", rank: int, world: int) -> Tuple["synth.TemplateSet", np.ndarray]:
+    """Returns (shard, template_ids): ``template_ids[i]`` is the GLOBAL per-class template_id of shard template i, to be
+    installed with ``Handle.set_template_ids`` so gathered candidates carry shard-invariant ids."""
+    idx = shard_indices(tset.n_templates, rank, world)
+    first = {}
+    for t in range(tset.n_templates):
+        first.setdefault(int(tset.class_of[t]), t)
+    gids = np.array([t - first[int(tset.class_of[t])] for t in idx], np.int32)
+    return tset.subset(idx.tolist()), gids
+
+
+def block_ints(capacity: int) -> int:
+    return (capacity + 1) * RECORD_INTS
+
+
+def pack_block(block, records, count) -> None:
+    """``block``: int32 tensor [(capacity+1)*5]; writes the count into the header record.  ``records`` is a view of
+    block[5:] that the producer already filled (the CUDA path writes candidates straight into it)."""
+    block[0] = count
+
+
+def records_view(block):
+    return block[RECORD_INTS:]
+
+
+def gather_blocks(block, world: int, group=None):
+    """One collective per frame: all-gather of the fixed-size blocks.  Returns an int32 tensor [world, capacity+1, 5]."""
+    import torch
+    import torch.distributed as dist
+    out = torch.empty((world,) + tuple(block.shape), dtype=block.dtype, device=block.device)
+    if world == 1 or not dist.is_initialized():
+        out[0].copy_(block)
+    else:
+        dist.all_gather_into_tensor(out.view(-1), block.contiguous(), group=group)
+    return out.view(world, -1, RECORD_INTS)
+
+
+def split_blocks(gathered) -> Tuple["object", "object"]:
+    """(counts[world] int32 contiguous, records[world, capacity, 5]) views/copies of a gathered tensor."""
+    counts = gathered[:, 0, 0].contiguous()
+    return counts, gathered[:, 1:, :]
+
+
+def merge_on_host(gathered_np: np.ndarray) -> np.ndarray:
+    """Reference merge used by the CPU tests: concatenate live records of all blocks -> structured array (unsorted)."""
+    from . import MATCH_DTYPE
+    recs = []
+    for b in gathered_np:
+        n = int(b[0, 0])
+        r = np.ascontiguousarray(b[1:1 + n]).view(MATCH_DTYPE).reshape(-1)
+        recs.append(r[r["template_id"] >= 0])
+    return np.concatenate(recs) if recs else np.zeros(0, MATCH_DTYPE)
+
+
+class ShardedMatcher:
+    """One rank of a template-sharded detector.  ``match_device`` = front end + matchClass on the local shard,
+    all-gather of candidate blocks over NCCL (NVLink / NVSwitch), sort + unique of the union on every rank."""
+
+    def __init__(self, handle, tset, rank: int, world: int, capacity: int = 1 << 14, device=None):
+        import torch
+        self.h, self.rank, self.world, self.cap = handle, rank, world, capacity
+        shard, gids = shard_template_set(tset, rank, world)
+        handle.upload_templates(shard)
+        handle.set_template_ids(gids)
+        self.n_local = shard.n_templates
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.block = torch.zeros(block_ints(capacity), dtype=torch.int32, device=dev)
+        self.out = torch.zeros(world * capacity * RECORD_INTS, dtype=torch.int32, device=dev)
+        self.out_count = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.stream = torch.cuda.ExternalStream(handle.stream_ptr(), device=dev)
+        self._torch = torch
+
+    def match_device(self, d_bgr: int, d_depth: int, W: int, H: int, threshold: float):
+        """Enqueue one frame.  Returns (out_records tensor [world*cap, 5] int32, out_count tensor) on the device."""
+        torch = self._torch
+        recs = records_view(self.block)
+        # the count lives in the header record of the block, so the candidates + count travel in one collective
+        self.h.match_shard_device(d_bgr, d_depth, W, H, threshold, recs.data_ptr(), self.cap, self.block.data_ptr())
+        with torch.cuda.stream(self.stream):
+            gathered = gather_blocks(self.block, self.world)
+            counts, _ = split_blocks(gathered)
+            counts = counts.clamp(max=self.cap)          # a shard that overflowed reports more than it stored
+            self._keep = (gathered, counts)
+            # lists are `cap + 1` records apart inside `gathered`; pass the first record of list 0 and that stride
+            base = gathered.data_ptr() + RECORD_INTS * 4
+            self.h.sort_unique_device(base, self.world, self.cap + 1, counts.data_ptr(), self.out.data_ptr(),
+                                      self.world * self.cap, self.out_count.data_ptr())
+        return self.out.view(-1, RECORD_INTS), self.out_count
+
+    def fetch(self) -> np.ndarray:
+        from . import MATCH_DTYPE
+        self.h.sync()
+        n = int(self.out_count[0].item())
+        a = self.out.view(-1, RECORD_INTS)[:n].cpu().numpy()
+        return np.ascontiguousarray(a).view(MATCH_DTYPE).reshape(-1)

@@ -106,6 +106,10 @@ void* fl_stream(fl_handle* h);
 int fl_upload_templates(fl_handle* h, int32_t n_templates, const fl_template_hdr_t* headers,
                         const fl_feature_t* features, int32_t n_features, const int32_t* class_of,
                         const float* pose13);
+/* Optional: the per-class template_id each uploaded template reports in its matches.  Default = rank inside its class
+ * in upload order.  A handle that holds only a shard of a class (template-sharded multi-GPU matching) sets the GLOBAL
+ * ids here so that gathered candidate lists are shard-invariant. */
+int fl_set_template_ids(fl_handle* h, const int32_t* template_ids);
 int fl_num_templates(fl_handle* h);
 int fl_get_pose_info(fl_handle* h, int32_t class_idx, int32_t template_id, float out13[13]);
 

@@ -1,0 +1,140 @@
+"""GPU (-m gpu): ICP / back-projection / NMS parity of the CUDA path through the C ABI.
+Tolerance from BASELINE.json north_star: 1e-4 rad rotation, 1e-4 m (= 0.1 mm) translation, same iteration count."""
+import os
+
+import numpy as np
+import pytest
+
+import fealess_b200 as fb
+import fl_oracle_py as F
+from fealess_b200 import synth
+from helpers import rot_err
+
+pytestmark = pytest.mark.gpu
+
+ROT_TOL = 1e-4      # rad
+T_TOL = 0.1         # mm  (= 1e-4 m)
+K = (608.0, 608.0, 320.0, 240.0)
+
+
+@pytest.fixture(scope="module")
+def h():
+    return fb.Handle()
+
+
+def _rt(p):
+    return p[:12].reshape(3, 4)[:, :3].copy(), p[:12].reshape(3, 4)[:, 3].copy()
+
+
+def test_detection_matches_oracle_and_golden(h, golden_dir):
+    z = np.load(os.path.join(golden_dir, "icp_small.npz"))
+    Kz = tuple(float(v) for v in z["K"])
+    for i in range(int(z["n_cases"])):
+        R0, t0 = _rt(z["rt_match_%d" % i])
+        rm, rr = z["rects_%d" % i]
+        g = h.detection_batch(z["ref_%d" % i], Kz, [z["model_%d" % i]], [rm], [rr], [R0], [t0])[0]
+        o = F.detection(z["model_%d" % i], z["ref_%d" % i], Kz, rm, rr, r_match=R0, t_match=t0)
+        dm, ratio, it, npts = z["scalars_%d" % i]
+        assert g["status"] == 0 and g["n_points"] == int(npts) == o["n_points"]
+        assert g["iterations"] == int(it) == o["iterations"], "case %d" % i
+        # against the C oracle the CUDA path is designed to be bit-identical (same fp32 chains, same SVD)
+        assert rot_err(g["R"], o["R"]) < 1e-6 and np.abs(g["T"] - o["T"]).max() < 1e-3
+        # against the cv2-evaluated golden: the task tolerance
+        assert rot_err(g["R"], z["R_%d" % i]) < ROT_TOL
+        assert np.abs(g["T"] - z["T_%d" % i]).max() < T_TOL
+        assert abs(float(g["dist_mean"]) - dm) < 1e-3 and abs(float(g["inlier_ratio"]) - ratio) < 1e-4
+
+
+def test_batched_hypotheses_equal_single_calls(h):
+    cases = [synth.make_icp_pair(seed=s, max_rot_deg=r, max_shift_mm=sh, rect_wh=wh)
+             for s, (r, sh, wh) in enumerate([(3, 6, (100, 100)), (8, 10, (80, 120)), (12, 15, (64, 64)), (5, 3, (120, 90)), (2, 2, (50, 70)),
+                                              (10, 5, (100, 100)), (15, 20, (90, 90)), (6, 12, (110, 60))])]
+    ref = cases[0][1]
+    # all hypotheses against ONE reference frame (the batch API's contract): re-use frame 0's reference depth
+    mds, rms, rrs, Rs, ts = [], [], [], [], []
+    for md, rf, rm, rr, p in cases:
+        R0, t0 = _rt(p)
+        mds.append(md); rms.append(rm); rrs.append(rr); Rs.append(R0); ts.append(t0)
+    batch = h.detection_batch(ref, K, mds, rms, rrs, Rs, ts)
+    for i in range(len(cases)):
+        o = F.detection(mds[i], ref, K, rms[i], rrs[i], r_match=Rs[i], t_match=ts[i])
+        g = batch[i]
+        assert g["iterations"] == o["iterations"] and g["n_points"] == o["n_points"]
+        assert rot_err(g["R"], o["R"]) < ROT_TOL and np.abs(g["T"] - o["T"]).max() < T_TOL
+        assert abs(float(g["dist_mean"]) - float(o["dist_mean"])) < 1e-3 or (np.isnan(g["dist_mean"]) and np.isnan(o["dist_mean"]))
+        single = h.detection_batch(ref, K, [mds[i]], [rms[i]], [rrs[i]], [Rs[i]], [ts[i]])[0]
+        assert single["R"].tobytes() == g["R"].tobytes() and single["T"].tobytes() == g["T"].tobytes()   # batching does not change a result
+
+
+def test_reference_signature_wrappers(h):
+    md, rf, rm, rr, p = synth.make_icp_pair(seed=3, max_rot_deg=8, max_shift_mm=10)
+    R0, t0 = _rt(p)
+    T_final, R_final = fb.detection(md, rf, K, rm, rr, 10, 0.5, 0.01, R0, t0, float(p[12]), handle=h)
+    o = F.detection(md, rf, K, rm, rr, r_match=R0, t_match=t0)
+    assert rot_err(R_final, o["R"]) < ROT_TOL and np.abs(T_final - o["T"]).max() < T_TOL
+    with pytest.raises(fb.FealessError) as e:                       # cv::Mat ROI throw in the reference (detection.cpp:43-44)
+        fb.detection(md, rf, K, (600, 10, 100, 100), rr, 10, 0.5, 0.01, R0, t0, handle=h)
+    assert e.value.rc == fb.FL_ERR_ROI
+
+
+def test_cloud_api_matches_oracle(h):
+    rng = np.random.default_rng(1)
+    for n, ang, noise in [(5000, 0.03, 0.2), (1200, 0.08, 0.5), (20000, 0.02, 0.1)]:
+        g = int(np.sqrt(n))
+        yy, xx = np.mgrid[0:g, 0:g].astype(np.float32)
+        ref = np.stack([xx.ravel() * 1.1 - 50, yy.ravel() * 1.1 - 40, 600 + 15 * np.sin(xx.ravel() / 9) * np.cos(yy.ravel() / 7)], 1).astype(np.float32)
+        c, s = np.cos(ang), np.sin(ang)
+        Rz = np.array([[c, -s, 0], [s, c, 0], [0, 0, 1]], np.float32)
+        mod = ((ref - ref.mean(0)) @ Rz.T + ref.mean(0) + rng.normal(0, noise, ref.shape) + [1.5, -1.0, 0.8]).astype(np.float32)
+        o = F.icp_cloud_to_cloud_ex(ref, mod, 10, 0.5, 0.01, want_trace=True)
+        dist_mean, R, T, ratio = fb.icpCloudToCloud_Ex(ref, mod, 10, 0.5, 0.01, handle=h)
+        r = h.icp_cloud_to_cloud_ex(ref, mod, 10, 0.5, 0.01)
+        assert r["iterations"] == o["iterations"] >= 1
+        assert rot_err(R, o["R"]) < ROT_TOL and np.abs(T - o["T"]).max() < T_TOL
+        assert abs(dist_mean - float(o["dist_mean"])) < 1e-3 and abs(ratio - float(o["inlier_ratio"])) < 1e-4
+
+
+def test_cloud_api_edge_cases(h):
+    r = h.icp_cloud_to_cloud_ex(np.zeros((2, 3), np.float32), np.zeros((2, 3), np.float32))
+    assert r["dist_mean"] == -1 and r["iterations"] == 0 and not r["R"].any()          # ICP.cpp:633-638
+    with pytest.raises(fb.FealessError):                                                 # lock-step loops need n_ref >= n_model
+        h.icp_cloud_to_cloud_ex(np.zeros((5, 3), np.float32), np.zeros((9, 3), np.float32))
+    # points beyond the 900 mm validity limit are ignored by the paired statistics but still queried (ICP.cpp:193-279)
+    rng = np.random.default_rng(2)
+    ref = rng.uniform(-40, 40, (3000, 3)).astype(np.float32) + [0, 0, 850]
+    mod = (ref + rng.normal(0, 0.4, ref.shape) + [0.8, 0.5, 0.3]).astype(np.float32)
+    o = F.icp_cloud_to_cloud_ex(ref, mod, 10, 0.5, 0.01)
+    r = h.icp_cloud_to_cloud_ex(ref, mod, 10, 0.5, 0.01)
+    assert r["iterations"] == o["iterations"]
+    assert rot_err(r["R"], o["R"]) < ROT_TOL and np.abs(r["T"] - o["T"]).max() < T_TOL
+    # identical clouds: dist_mean 0 -> loop never runs, R = I
+    r = h.icp_cloud_to_cloud_ex(ref[:100], ref[:100], 10, 0.5, 0.01)
+    assert r["iterations"] == 0 and np.array_equal(r["R"].reshape(3, 3), np.eye(3, dtype=np.float32)) and r["dist_mean"] == 0
+
+
+def test_depth_to_3d_bit_exact(h):
+    _, d = synth.make_frame(640, 480, 2)
+    for Kc in (K, (525.3, 531.7, 311.2, 247.9)):
+        got = fb.depthTo3d(d, Kc, handle=h)
+        want_mm = F.depth_to_3d_mm(d, *Kc)
+        # the oracle exports millimetres (depthTo3d followed by scale_mat_vec3f); metres * 1000 must reproduce it bit for bit
+        assert np.array_equal(np.isnan(got[..., 2]), d == 0)
+        assert np.array_equal((got * np.float32(1000.0))[d > 0], want_mm[d > 0])
+    K3 = np.array([[608.0, 0, 320.0], [0, 608.0, 240.0], [0, 0, 1]])
+    assert np.array_equal(np.nan_to_num(fb.depthTo3d(d, K3, handle=h)), np.nan_to_num(fb.depthTo3d(d, K, handle=h)))
+
+
+def test_nms_matches_oracle_and_golden(h, golden_dir):
+    z = np.load(os.path.join(golden_dir, "icp_small.npz"))
+    assert np.array_equal(h.nms(z["nms_t3"], z["nms_n"], z["nms_dist"], 25.0), z["nms_out_th25"])
+    assert np.array_equal(h.nms(z["nms_t3"], z["nms_n"], z["nms_dist"], 8.0), z["nms_out_th8"])
+    rng = np.random.default_rng(11)
+    for n in (1, 2, 50, 300):
+        t3 = rng.uniform(0, 100, (n, 3)).astype(np.float32)
+        nm = rng.integers(100, 2000, n).astype(np.int32)
+        dd = rng.uniform(0.1, 5, n).astype(np.float32)
+        for th in (0.0, 15.0, 1e9):
+            assert np.array_equal(h.nms(t3, nm, dd, th), F.nms(t3, nm, dd, th))
+    objs = [dict(match_class=i % 3, match_sim=90.0 - i, r=np.eye(3), t=z["nms_t3"][i], pts_model=int(z["nms_n"][i]), icp_dist=float(z["nms_dist"][i])) for i in range(24)]
+    res = fb.nonMaximumSuppression(objs, 25.0, handle=h)
+    assert [r["index"] for r in res] == list(z["nms_out_th25"])
