@@ -27,6 +27,8 @@ struct fl_handle {
   fl_template_hdr_t* d_hdr; fl_feature_t* d_feat; int32_t* d_class_of; int32_t* d_class_first; uint8_t* d_class_enabled;
   fl_pfeat* d_pfeat; int32_t* d_tid_of;
   std::vector<int32_t> tid_of_h;
+  bool staged_eligible, use_staged; int n_sm; int force_baseline;   // staged global-similarity kernel (similarity_staged.cu)
+  fl_staged_plan plan;
   std::vector<int32_t> class_first_h, class_of_h;
   std::vector<float> pose13_h;
   std::vector<uint8_t> class_enabled_h;
@@ -46,7 +48,7 @@ struct fl_handle {
   fl_match_t* d_cand; int* d_count; fl_sort_key* d_keys; int key_cap; fl_match_t* d_out; int* d_out_count;
   // pinned host staging
   uint8_t* h_bgr; uint16_t* h_depth; uint8_t* h_mask; int* h_small; fl_match_t* h_first; uint8_t* h_class_enabled;
-  bool have_result;
+  bool have_result, overflow;
   // profiling
   bool profile; cudaEvent_t ev[5]; float stage_ms[4];
   // ICP workspace (grown on demand)
@@ -110,6 +112,8 @@ extern "C" int fl_create(const fl_params_t* params, fl_handle** out) {
   h->n_templates = h->n_features = h->n_classes = 0;
   h->d_hdr = nullptr; h->d_feat = nullptr; h->d_class_of = nullptr; h->d_class_first = nullptr; h->d_class_enabled = nullptr; h->d_pfeat = nullptr;
   h->d_tid_of = nullptr;
+  h->staged_eligible = false; h->use_staged = false; h->force_baseline = 0; memset(&h->plan, 0, sizeof h->plan);
+  { cudaDeviceProp prop; FL_CUDA(cudaGetDeviceProperties(&prop, p.device)); h->n_sm = prop.multiProcessorCount; }
   h->icp_hyp_cap = h->icp_pts_cap = 0; memset(&h->icp, 0, sizeof h->icp);
   h->d_hyps = nullptr; h->d_t_init = nullptr; h->d_results = nullptr; h->d_model_crops = nullptr; h->d_ref_depth = nullptr; h->ref_depth_cap = 0;
   h->h_model_crops = nullptr; h->h_hyps = nullptr; h->h_results = nullptr; h->h_crop_cap = 0;
@@ -131,7 +135,7 @@ extern "C" int fl_create(const fl_params_t* params, fl_handle** out) {
     int T = p.T[l];
     size_t cells = (size_t)(((p.max_width >> l) + T - 1) / T) * (((p.max_height >> l) + T - 1) / T);
     size_t ls = (((size_t)T * T * cells + FL_LM_PAD) + 15) & ~(size_t)15;
-    h->lm_bytes[l] = ls * 8 * p.n_modalities + 64;
+    h->lm_bytes[l] = ls * 8 * p.n_modalities + cells + 256;   // slack: windowed reads may run one map past the last label
     TRY(dalloc(&h->d_lm[l], h->lm_bytes[l]));
   }
   TRY(dalloc(&h->d_cand, (size_t)p.max_candidates)); TRY(dalloc(&h->d_count, 4));
@@ -157,7 +161,8 @@ static void icp_free(fl_handle* h) {
 
 static void free_templates(fl_handle* h) {
   cudaFree(h->d_hdr); cudaFree(h->d_feat); cudaFree(h->d_class_of); cudaFree(h->d_class_first); cudaFree(h->d_class_enabled); cudaFree(h->d_pfeat);
-  cudaFree(h->d_tid_of);
+  cudaFree(h->d_tid_of); cudaFree(h->plan.gfeat); cudaFree(h->plan.ph_off);
+  h->plan.gfeat = nullptr; h->plan.ph_off = nullptr; h->use_staged = false; h->staged_eligible = false;
   h->d_hdr = nullptr; h->d_feat = nullptr; h->d_class_of = nullptr; h->d_class_first = nullptr; h->d_class_enabled = nullptr; h->d_pfeat = nullptr;
   h->d_tid_of = nullptr;
   h->n_templates = h->n_features = h->n_classes = 0; h->packed = false;
@@ -187,6 +192,9 @@ extern "C" void* fl_stream(fl_handle* h) { return h ? (void*)h->stream : nullptr
 extern "C" int64_t fl_launch_count(fl_handle* h) { return h ? h->launches : 0; }
 extern "C" int fl_profile(fl_handle* h, int enable) { if (!h) return FL_ERR_ARG; h->profile = enable != 0; return FL_OK; }
 extern "C" int fl_last_stage_ms(fl_handle* h, float out4[4]) { if (!h || !out4) return FL_ERR_ARG; memcpy(out4, h->stage_ms, sizeof h->stage_ms); return FL_OK; }
+// 1 = always use the baseline (L1/L2-fed) global similarity kernel; 0 = use the shared-memory-staged kernel when eligible
+extern "C" int fl_debug_force_baseline(fl_handle* h, int enable) { if (!h) return FL_ERR_ARG; h->force_baseline = enable != 0; h->packed = false; return FL_OK; }
+extern "C" int fl_debug_uses_staged(fl_handle* h) { return h ? (h->use_staged ? 1 : 0) : FL_ERR_ARG; }
 extern "C" int fl_debug_keep_spread(fl_handle* h, int enable) { if (!h) return FL_ERR_ARG; h->keep_spread = enable != 0; return FL_OK; }
 extern "C" int fl_num_templates(fl_handle* h) { return h ? h->n_templates : FL_ERR_ARG; }
 
@@ -211,8 +219,25 @@ extern "C" int fl_upload_templates(fl_handle* h, int32_t n_templates, const fl_t
     if (hd.feature_count > 63) return FL_ERR_FEATURES;                          // CV_Assert(features.size() <= 63)
     for (int k = 0; k < hd.feature_count; ++k) { int lab = features[hd.feature_begin + k].label; if (lab < 0 || lab > 7) return FL_ERR_ARG; }
   }
+  // eligibility for the shared-memory-staged global similarity kernel: u8 totals cannot overflow, one template_positions
+  // per template, and every coarsest-level feature inside its template's box (keeps flat over-reads within the staged halo)
+  bool eligible = n_templates > 0;
+  for (int t = 0; t < n_templates && eligible; ++t) {
+    const fl_template_hdr_t* hd = headers + ((size_t)t * L + (L - 1)) * M;
+    int nf = 0;
+    for (int m = 0; m < M; ++m) {
+      nf += hd[m].feature_count;
+      if (hd[m].width != hd[0].width || hd[m].height != hd[0].height || hd[m].width < 1 || hd[m].height < 1) eligible = false;
+      for (int k = 0; k < hd[m].feature_count; ++k) {
+        const fl_feature_t& f = features[hd[m].feature_begin + k];
+        if (f.x < 0 || f.y < 0 || f.x > hd[m].width || f.y > hd[m].height) eligible = false;
+      }
+    }
+    if (nf > 63) eligible = false;
+  }
   FL_CUDA(cudaStreamSynchronize(h->stream));
   free_templates(h);
+  h->staged_eligible = eligible;
   TRY(dalloc(&h->d_hdr, ne)); TRY(dalloc(&h->d_feat, (size_t)n_features)); TRY(dalloc(&h->d_class_of, (size_t)n_templates));
   TRY(dalloc(&h->d_class_first, (size_t)nc)); TRY(dalloc(&h->d_class_enabled, (size_t)std::max(nc, 1))); TRY(dalloc(&h->d_pfeat, (size_t)n_features));
   if (ne) FL_CUDA(cudaMemcpy(h->d_hdr, headers, ne * sizeof(fl_template_hdr_t), cudaMemcpyHostToDevice));
@@ -282,6 +307,17 @@ static int ensure_geometry(fl_handle* h, int W, int H) {
   }
   if (!h->packed && h->n_templates > 0) {
     fl_launch_pack_features(make_tdb(h), h->d_geom, h->n_features, h->stream); ++h->launches;
+    h->use_staged = false;
+    fl_staged_plan plan;
+    if (h->staged_eligible && !h->force_baseline && h->n_templates >= 256 &&
+        fl_plan_staged(h->geom[p.n_levels - 1], p.n_modalities, h->n_templates, h->n_sm, &plan)) {
+      cudaFree(h->plan.gfeat); cudaFree(h->plan.ph_off);
+      h->plan = plan;
+      TRY(dalloc(&h->plan.gfeat, (size_t)h->n_templates * 64));
+      TRY(dalloc(&h->plan.ph_off, (size_t)h->n_templates * (plan.n_phases + 1)));
+      fl_launch_pack_staged(make_tdb(h), h->geom[p.n_levels - 1], h->plan, h->stream); ++h->launches;
+      h->use_staged = true;
+    }
     h->packed = true;
   }
   return FL_OK;
@@ -347,7 +383,14 @@ static int run_match_stages(fl_handle* h, const uint8_t* d_bgr, const uint16_t* 
   if (h->n_templates > 0) {
     fl_tdb db = make_tdb(h);
     const int lowest = p.n_levels - 1;
-    fl_launch_similarity_global(db, h->geom[lowest], h->d_lm[lowest], threshold, cand, cap, d_count, s); ++h->launches;
+    if (h->use_staged) {
+      if (fl_launch_similarity_staged(db, h->geom[lowest], h->d_lm[lowest], threshold, cand, cap, d_count, h->plan, s) != 0) {
+        fl_set_error("staged similarity kernel could not be configured"); return FL_ERR_CUDA;
+      }
+    } else {
+      fl_launch_similarity_global(db, h->geom[lowest], h->d_lm[lowest], threshold, cand, cap, d_count, s);
+    }
+    ++h->launches;
     if (h->profile) cudaEventRecord(h->ev[2], s);
     for (int l = p.n_levels - 2; l >= 0; --l) { fl_launch_refine_level(db, h->geom[l], l, h->d_lm[l], threshold, cand, cap, d_count, s); ++h->launches; }
   } else if (h->profile) cudaEventRecord(h->ev[2], s);
@@ -365,9 +408,12 @@ static int run_sort_unique(fl_handle* h, const fl_match_t* d_in, int n_lists, in
   int* d_scratch = reinterpret_cast<int*>(h->d_keys + h->key_cap);
   FL_CUDA(cudaMemcpyAsync(h->h_small + 1, d_scratch, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
   FL_CUDA(cudaMemcpyAsync(h->h_small, d_out_count, sizeof(int), cudaMemcpyDeviceToHost, s));
+  FL_CUDA(cudaMemcpyAsync(h->h_small + 3, d_n_in, sizeof(int) * std::min(n_lists, 12), cudaMemcpyDeviceToHost, s));   // raw counts (overflow check)
   if (fetch_first) FL_CUDA(cudaMemcpyAsync(h->h_first, d_out, sizeof(fl_match_t) * std::min(FETCH_FIRST, out_cap), cudaMemcpyDeviceToHost, s));
   if (h->profile) cudaEventRecord(h->ev[4], s);
   FL_CUDA(cudaStreamSynchronize(s));
+  h->overflow = false;
+  for (int i = 0; i < std::min(n_lists, 12); ++i) if (h->h_small[3 + i] > list_cap) h->overflow = true;
   if (h->h_small[2]) {                                                          // more than 2048 live candidates: multi-kernel sort
     int rc = fl_launch_sort_unique_big(h->d_keys, h->key_cap, std::min(h->h_small[1], h->key_cap), d_out, out_cap, d_out_count, s);
     if (rc < 0) return FL_ERR_CAPACITY;
@@ -405,7 +451,8 @@ extern "C" int fl_match_fetch(fl_handle* h, fl_match_t* out, int32_t capacity, i
     FL_CUDA(cudaMemcpyAsync(out + nfirst, h->d_out + nfirst, sizeof(fl_match_t) * (size_t)(ncopy - nfirst), cudaMemcpyDeviceToHost, h->stream));
     FL_CUDA(cudaStreamSynchronize(h->stream));
   }
-  return (n > capacity || n > h->p.max_candidates) ? FL_ERR_CAPACITY : FL_OK;
+  // overflow: matchClass produced more candidates than the device buffer holds (the list is then incomplete)
+  return (n > capacity || n > h->p.max_candidates || h->overflow) ? FL_ERR_CAPACITY : FL_OK;
 }
 
 extern "C" int fl_match(fl_handle* h, const uint8_t* bgr, size_t bgr_stride, const uint16_t* depth, size_t depth_stride, int32_t W, int32_t H,

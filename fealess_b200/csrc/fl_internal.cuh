@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 #include "../../include/fealess_b200.h"
 
 #define FL_LM_PAD 4096          // zero bytes after each label's linear memory (flat-addressing over-read)
@@ -53,6 +54,19 @@ struct fl_tdb {                     // device template database
   const uint8_t* class_enabled;     // [n_classes] (class filter of the current call)
   fl_pfeat* pfeat;                  // [n_features] packed for the current geometry
 };
+// plan of the shared-memory-staged global similarity kernel (similarity_staged.cu) for one frame geometry
+struct fl_staged_plan {
+  int phase_rows, n_rowblocks, n_phases;   // a phase = phase_rows linear-memory rows of one (modality, label)
+  int halo_bytes, buf_bytes, n_buf;        // bytes staged past the last row; size and number of the smem ring buffers
+  int n_words, nw_template, tpw;           // 32-bit words per similarity map; template parameters of the instantiation used
+  int tpc, n_cta, block_threads;           // templates per CTA, grid, block
+  uint32_t* gfeat;                         // [n_templates][64] per-phase byte offsets of the features, sorted by phase
+  uint8_t* ph_off;                         // [n_templates][n_phases + 1] prefix offsets into gfeat rows
+};
+bool fl_plan_staged(const fl_level_geom& g, int M, int n_templates, int n_sm, fl_staged_plan* plan);
+void fl_launch_pack_staged(fl_tdb db, fl_level_geom g, fl_staged_plan plan, cudaStream_t s);
+int fl_launch_similarity_staged(fl_tdb db, fl_level_geom g, const uint8_t* lm_level, float threshold, fl_match_t* cand, int cap,
+                                int* d_count, fl_staged_plan plan, cudaStream_t s);
 void fl_launch_pack_features(fl_tdb db, const fl_level_geom* d_geom, int n_features_total, cudaStream_t s);
 void fl_launch_similarity_global(fl_tdb db, fl_level_geom g, const uint8_t* lm_level, float threshold,
                                  fl_match_t* cand, int cap, int* d_count, cudaStream_t s);

@@ -175,6 +175,11 @@ enum {
   FL_DBG_SIMILARITY = 3     /* (template index)          -> (W/T)*(H/T) u16 total similarity at the coarsest level */
 };
 int fl_debug_keep_spread(fl_handle* h, int enable);
+/* kernel selection of the global similarity stage: the shared-memory-staged kernel is used when the template set is
+ * eligible; force_baseline(1) pins the L1/L2-fed kernel (parity tests run both); uses_staged reports the
+ * choice made for the last frame geometry (1 / 0). */
+int fl_debug_force_baseline(fl_handle* h, int enable);
+int fl_debug_uses_staged(fl_handle* h);
 int fl_debug_get(fl_handle* h, int what, int32_t a, int32_t b, int32_t c, void* host_out, size_t bytes);
 /* number of kernels launched by this handle since creation (bench.py reports the per-step delta) */
 int64_t fl_launch_count(fl_handle* h);

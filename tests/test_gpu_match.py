@@ -109,6 +109,48 @@ def test_large_candidate_count_takes_the_multi_kernel_sort(vga):
         assert len(raw) > 2048
 
 
+def test_staged_and_baseline_similarity_kernels_agree(vga):
+    W, H, b, d, det, ts, h = vga
+    assert h.match(b, d, 60.0)[0] == 0
+    assert h.uses_staged()                       # 600 eligible templates at VGA -> shared-memory-staged kernel
+    staged = h.match(b, d, 60.0)[1]
+    h.force_baseline(True)
+    try:
+        rc, base = h.match(b, d, 60.0)
+        assert rc == 0 and not h.uses_staged()
+    finally:
+        h.force_baseline(False)
+    want = det.match(60.0)
+    assert np.array_equal(staged, want) and np.array_equal(base, want)
+
+
+def test_templates_with_features_on_the_box_border_and_ragged_sets(vga):
+    """Features at x == width / y == height make similarity() read past the end of a linear-memory row (flat addressing);
+    a template larger than the frame has no valid position at all; a set that is not eligible for the staged kernel (64+
+    coarse features in total is impossible, so: modalities with different boxes) must fall back to the baseline kernel."""
+    W, H, b, d, det0, _, _ = vga
+    T = (5, 8)
+    q = [det0.quantized(l, m) for l in range(2) for m in range(2)]
+    ts = synth.make_templates(300, W, H, T, seed=77, quantized=q, planted_fraction=0.2)
+    LM = 4
+    for t in range(0, 300, 3):                   # push some features onto the far corner of the box at both levels
+        for e in range(LM):
+            hd = ts.headers[t * LM + e]
+            ts.features[hd[5]] = (hd[0], hd[1], ts.features[hd[5], 2])
+            ts.features[hd[5] + 1] = (hd[0], 0, ts.features[hd[5] + 1, 2])
+    ts.headers[5 * LM + 2, 0] = ts.headers[5 * LM + 3, 0] = 400       # coarsest-level template wider than the 320-px level
+    det = F.Detector(T); det.process(b, d); det.set_templates(ts)
+    h = fb.Handle(T, (0, 1), W, H)
+    h.upload_templates(ts)
+    for thr in (70.0, 50.0):
+        rc, got = h.match(b, d, thr)
+        assert rc == 0 and h.uses_staged() and np.array_equal(got, det.match(thr))
+    ts.headers[7 * LM + 3, 0] += 8               # depth modality box differs from the colour one -> not eligible
+    det.set_templates(ts); h.upload_templates(ts)
+    rc, got = h.match(b, d, 50.0)
+    assert rc == 0 and not h.uses_staged() and np.array_equal(got, det.match(50.0))
+
+
 def test_class_filter(vga):
     W, H, b, d, det, ts, h = vga
     for filt in ([2], [0, 3], [1, 99]):
