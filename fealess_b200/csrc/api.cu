@@ -342,41 +342,77 @@ static int run_match_stages(fl_handle* h, const uint8_t* d_bgr, const uint16_t* 
   }
   if (h->profile) cudaEventRecord(h->ev[0], s);
   const float thr_sq = p.weak_threshold * p.weak_threshold;
-  bool color_pyr_done = false;
-  for (int l = 0; l < p.n_levels; ++l) {
-    const fl_level_geom& g = h->geom[l];
-    const size_t npx = (size_t)g.W * g.H;
-    for (int m = 0; m < p.n_modalities; ++m) {
-      const bool has_mask = d_masks && d_masks[m];
-      h->used_mask[m] = has_mask;
-      if (p.modality_kind[m] == FL_MODALITY_COLOR_GRADIENT) {
-        const uint8_t* src = d_bgr;
-        if (l > 0) {
-          if (!color_pyr_done) {                                                // one colour pyramid shared by all colour modalities
-            const uint8_t* prev = l == 1 ? d_bgr : h->d_bgr[l - 1];
-            fl_launch_pyrdown_bgr(prev, h->geom[l - 1].W, h->geom[l - 1].H, h->d_bgr[l], s); ++h->launches;
-            color_pyr_done = true;
+  bool any_mask = false;
+  for (int m = 0; m < p.n_modalities; ++m) { h->used_mask[m] = d_masks && d_masks[m]; any_mask |= h->used_mask[m]; }
+  int first_color = -1;
+  for (int m = 0; m < p.n_modalities; ++m) if (p.modality_kind[m] == FL_MODALITY_COLOR_GRADIENT && first_color < 0) first_color = m;
+  if (!any_mask) {
+    // wave schedule (frontend.cu): L + 1 launches for the whole front end
+    for (int wv = 0; wv <= p.n_levels; ++wv) {
+      fl_fe_wave w; w.n_jobs = 0; w.n_ctas = 0; w.smem = 0;
+      const int l = wv;                                       // level whose quantised images this wave produces
+      if (l < p.n_levels) {
+        const fl_level_geom& g = h->geom[l];
+        for (int m = 0; m < p.n_modalities; ++m) {
+          if (p.modality_kind[m] == FL_MODALITY_COLOR_GRADIENT) {
+            fl_fe_add_color(&w, l == 0 ? d_bgr : h->d_bgr[l], g.W, g.H, thr_sq, h->d_q[l][m]);
+          } else if (l == 0) {
+            fl_fe_add_depth(&w, d_depth, g.W, g.H, p.distance_threshold, p.difference_threshold, h->d_q[0][m]);
+          } else {
+            fl_fe_add_resize(&w, h->d_q[l - 1][m], h->geom[l - 1].W, h->geom[l - 1].H, h->d_q[l][m]);
           }
-          src = h->d_bgr[l];
         }
-        fl_launch_color_quantize(src, g.W, g.H, thr_sq, h->d_q[l][m], s); ++h->launches;
-      } else {
-        if (l == 0) { fl_launch_depth_quantize(d_depth, g.W, g.H, p.distance_threshold, p.difference_threshold, h->d_q[0][m], s); ++h->launches; }
-        else { fl_launch_resize_nn_half(h->d_q[l - 1][m], h->geom[l - 1].W, h->geom[l - 1].H, h->d_q[l][m], s); ++h->launches; }
+        if (first_color >= 0 && l + 1 < p.n_levels)           // colour pyramid for the next wave (shared by all colour modalities)
+          fl_fe_add_pyrdown(&w, l == 0 ? d_bgr : h->d_bgr[l], g.W, g.H, h->d_bgr[l + 1]);
       }
-      const uint8_t* qsrc = h->d_q[l][m];
-      if (has_mask) {
-        if (!h->d_mask[l][m]) { size_t n = (size_t)(p.max_width >> l) * (p.max_height >> l); TRY(dalloc(&h->d_mask[l][m], n)); TRY(dalloc(&h->d_qm[l][m], n)); }
-        const uint8_t* mk = (const uint8_t*)d_masks[m];
-        if (l > 0) { fl_launch_resize_nn_half(l == 1 ? (const uint8_t*)d_masks[m] : h->d_mask[l - 1][m], h->geom[l - 1].W, h->geom[l - 1].H, h->d_mask[l][m], s); ++h->launches; mk = h->d_mask[l][m]; }
-        fl_launch_apply_mask(h->d_q[l][m], mk, (int)npx, h->d_qm[l][m], s); ++h->launches;
-        qsrc = h->d_qm[l][m];
+      if (l >= 1) {
+        const fl_level_geom& g = h->geom[l - 1];
+        for (int m = 0; m < p.n_modalities; ++m) {
+          uint8_t* spread = nullptr;
+          if (h->keep_spread) { if (!h->d_spread[l - 1][m]) TRY(dalloc(&h->d_spread[l - 1][m], (size_t)(p.max_width >> (l - 1)) * (p.max_height >> (l - 1)))); spread = h->d_spread[l - 1][m]; }
+          fl_fe_add_spread(&w, h->d_q[l - 1][m], g, h->d_lm[l - 1] + (size_t)m * g.mod_stride, spread);
+        }
       }
-      uint8_t* spread = nullptr;
-      if (h->keep_spread) { if (!h->d_spread[l][m]) TRY(dalloc(&h->d_spread[l][m], (size_t)(p.max_width >> l) * (p.max_height >> l))); spread = h->d_spread[l][m]; }
-      fl_launch_spread_lm(qsrc, g, h->d_lm[l] + (size_t)m * g.mod_stride, spread, s); ++h->launches;
+      fl_launch_fe_wave(w, s); ++h->launches;
     }
-    color_pyr_done = false;
+  } else {
+    // masked path (rare): one kernel per stage, masks NN-downsampled per level and applied before spreading
+    bool color_pyr_done = false;
+    for (int l = 0; l < p.n_levels; ++l) {
+      const fl_level_geom& g = h->geom[l];
+      const size_t npx = (size_t)g.W * g.H;
+      for (int m = 0; m < p.n_modalities; ++m) {
+        const bool has_mask = h->used_mask[m];
+        if (p.modality_kind[m] == FL_MODALITY_COLOR_GRADIENT) {
+          const uint8_t* src = d_bgr;
+          if (l > 0) {
+            if (!color_pyr_done) {
+              const uint8_t* prev = l == 1 ? d_bgr : h->d_bgr[l - 1];
+              fl_launch_pyrdown_bgr(prev, h->geom[l - 1].W, h->geom[l - 1].H, h->d_bgr[l], s); ++h->launches;
+              color_pyr_done = true;
+            }
+            src = h->d_bgr[l];
+          }
+          fl_launch_color_quantize(src, g.W, g.H, thr_sq, h->d_q[l][m], s); ++h->launches;
+        } else {
+          if (l == 0) { fl_launch_depth_quantize(d_depth, g.W, g.H, p.distance_threshold, p.difference_threshold, h->d_q[0][m], s); ++h->launches; }
+          else { fl_launch_resize_nn_half(h->d_q[l - 1][m], h->geom[l - 1].W, h->geom[l - 1].H, h->d_q[l][m], s); ++h->launches; }
+        }
+        const uint8_t* qsrc = h->d_q[l][m];
+        if (has_mask) {
+          if (!h->d_mask[l][m]) { size_t n = (size_t)(p.max_width >> l) * (p.max_height >> l); TRY(dalloc(&h->d_mask[l][m], n)); }
+          if (!h->d_qm[l][m]) { size_t n = (size_t)(p.max_width >> l) * (p.max_height >> l); TRY(dalloc(&h->d_qm[l][m], n)); }
+          const uint8_t* mk = (const uint8_t*)d_masks[m];
+          if (l > 0) { fl_launch_resize_nn_half(l == 1 ? (const uint8_t*)d_masks[m] : h->d_mask[l - 1][m], h->geom[l - 1].W, h->geom[l - 1].H, h->d_mask[l][m], s); ++h->launches; mk = h->d_mask[l][m]; }
+          fl_launch_apply_mask(h->d_q[l][m], mk, (int)npx, h->d_qm[l][m], s); ++h->launches;
+          qsrc = h->d_qm[l][m];
+        }
+        uint8_t* spread = nullptr;
+        if (h->keep_spread) { if (!h->d_spread[l][m]) TRY(dalloc(&h->d_spread[l][m], (size_t)(p.max_width >> l) * (p.max_height >> l))); spread = h->d_spread[l][m]; }
+        fl_launch_spread_lm(qsrc, g, h->d_lm[l] + (size_t)m * g.mod_stride, spread, s); ++h->launches;
+      }
+      color_pyr_done = false;
+    }
   }
   if (h->profile) cudaEventRecord(h->ev[1], s);
   FL_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), s));

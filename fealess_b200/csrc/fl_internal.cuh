@@ -43,6 +43,23 @@ void fl_launch_resize_nn_half(const uint8_t* src, int W, int H, uint8_t* dst, cu
 void fl_launch_apply_mask(const uint8_t* q, const uint8_t* mask, int n, uint8_t* out, cudaStream_t s);
 void fl_launch_spread_lm(const uint8_t* q, fl_level_geom g, uint8_t* lm_mod, uint8_t* spread_or_null, cudaStream_t s);
 
+// one launch = several independent front-end jobs (see k_front_end_wave)
+enum { FL_JOB_COLOR = 0, FL_JOB_DEPTH = 1, FL_JOB_PYRDOWN = 2, FL_JOB_RESIZE = 3, FL_JOB_SPREAD = 4 };
+struct fl_fe_job {
+  int kind, cta_begin, gx, W, H, p0, p1;
+  float thr_sq;
+  const uint8_t* src; uint8_t* dst; uint8_t* dst2;
+  fl_level_geom g;
+};
+#define FL_FE_MAX_JOBS 10
+struct fl_fe_wave { int n_jobs, n_ctas; size_t smem; fl_fe_job job[FL_FE_MAX_JOBS]; };
+void fl_fe_add_color(fl_fe_wave* w, const uint8_t* bgr, int W, int H, float thr_sq, uint8_t* q);
+void fl_fe_add_depth(fl_fe_wave* w, const uint16_t* depth, int W, int H, int dist_thr, int diff_thr, uint8_t* q);
+void fl_fe_add_pyrdown(fl_fe_wave* w, const uint8_t* src, int W, int H, uint8_t* dst);
+void fl_fe_add_resize(fl_fe_wave* w, const uint8_t* src, int W, int H, uint8_t* dst);
+void fl_fe_add_spread(fl_fe_wave* w, const uint8_t* q, fl_level_geom g, uint8_t* lm_mod, uint8_t* spread_or_null);
+void fl_launch_fe_wave(const fl_fe_wave& w, cudaStream_t s);
+
 // ---- similarity / refinement / sort (similarity.cu) ---------------------------------------------
 struct fl_tdb {                     // device template database
   int n_templates, L, M, n_classes;

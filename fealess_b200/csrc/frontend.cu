@@ -81,16 +81,20 @@ __device__ __forceinline__ int angle_q16(float x, float y) {
   return min(max(r, 0), 255);
 }
 
-__global__ void __launch_bounds__(CQ_THREADS) k_color_quantize(const uint8_t* __restrict__ bgr, int W, int H, float thr_sq,
-                                                               uint8_t* __restrict__ q) {
+#define CQ_SMEM_BYTES ((CQ_TH + 10) * (CQ_TW + 10) * 3 + (CQ_TH + 10) * (CQ_TW + 4) * 3 * 2 + (CQ_TH + 4) * (CQ_TW + 4) * 3 + (CQ_TH + 2) * (CQ_TW + 2) + 16)
+
+// one CQ_TW x CQ_TH tile; smem = CQ_SMEM_BYTES bytes, 16-byte aligned
+__device__ __forceinline__ void dev_color_quantize(const uint8_t* __restrict__ bgr, int W, int H, float thr_sq, uint8_t* __restrict__ q,
+                                                   int bx, int by, uint8_t* smem) {
   constexpr int SW = CQ_TW + 10, SH = CQ_TH + 10;   // source tile
   constexpr int BW = CQ_TW + 4, BH = CQ_TH + 4;     // blurred tile (positions x0-2 .. x0+TW+1)
   constexpr int QW = CQ_TW + 2, QH = CQ_TH + 2;     // unfiltered-bin tile (positions x0-1 .. x0+TW)
-  __shared__ uint8_t s_src[SH][SW * 3];
-  __shared__ uint16_t s_h[SH][BW * 3];
-  __shared__ uint8_t s_b[BH][BW * 3];
-  __shared__ uint8_t s_q[QH][QW];                   // bits 0-2 bin, bit 7 = magnitude above threshold
-  const int x0 = blockIdx.x * CQ_TW, y0 = blockIdx.y * CQ_TH;
+  constexpr int OFF_H = (SH * SW * 3 + 15) & ~15;
+  uint8_t(*s_src)[SW * 3] = reinterpret_cast<uint8_t(*)[SW * 3]>(smem);
+  uint16_t(*s_h)[BW * 3] = reinterpret_cast<uint16_t(*)[BW * 3]>(smem + OFF_H);
+  uint8_t(*s_b)[BW * 3] = reinterpret_cast<uint8_t(*)[BW * 3]>(smem + OFF_H + SH * BW * 3 * 2);
+  uint8_t(*s_q)[QW] = reinterpret_cast<uint8_t(*)[QW]>(smem + OFF_H + SH * BW * 3 * 2 + BH * BW * 3);   // bits 0-2 bin, bit 7 = magnitude above threshold
+  const int x0 = bx * CQ_TW, y0 = by * CQ_TH;
   const int tid = threadIdx.x;
 
   // 1. source tile with BORDER_REPLICATE
@@ -174,6 +178,12 @@ __global__ void __launch_bounds__(CQ_THREADS) k_color_quantize(const uint8_t* __
   }
 }
 
+__global__ void __launch_bounds__(CQ_THREADS) k_color_quantize(const uint8_t* __restrict__ bgr, int W, int H, float thr_sq,
+                                                               uint8_t* __restrict__ q) {
+  __shared__ __align__(16) uint8_t smem[CQ_SMEM_BYTES];
+  dev_color_quantize(bgr, W, H, thr_sq, q, blockIdx.x, blockIdx.y, smem);
+}
+
 void fl_launch_color_quantize(const uint8_t* bgr, int W, int H, float thr_sq, uint8_t* q, cudaStream_t s) {
   dim3 grid((W + CQ_TW - 1) / CQ_TW, (H + CQ_TH - 1) / CQ_TH);
   k_color_quantize<<<grid, CQ_THREADS, 0, s>>>(bgr, W, H, thr_sq, q);
@@ -188,9 +198,9 @@ __device__ __forceinline__ int reflect101(int p, int n) {
   return p;
 }
 
-__global__ void __launch_bounds__(256) k_pyrdown_bgr(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ dst) {
+__device__ __forceinline__ void dev_pyrdown_bgr(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ dst, int bx) {
   const int dw = W / 2, dh = H / 2;
-  int i = blockIdx.x * blockDim.x + threadIdx.x;   // one thread per output byte (pixel*3 + channel): coalesced stores
+  int i = bx * 256 + threadIdx.x;                  // one thread per output byte (pixel*3 + channel): coalesced stores
   if (i >= dw * dh * 3) return;
   int ch = i % 3, px = i / 3;
   int x = px % dw, y = px / dw;
@@ -210,6 +220,10 @@ __global__ void __launch_bounds__(256) k_pyrdown_bgr(const uint8_t* __restrict__
   dst[i] = (uint8_t)((s + 128) >> 8);
 }
 
+__global__ void __launch_bounds__(256) k_pyrdown_bgr(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ dst) {
+  dev_pyrdown_bgr(src, W, H, dst, blockIdx.x);
+}
+
 void fl_launch_pyrdown_bgr(const uint8_t* src, int W, int H, uint8_t* dst, cudaStream_t s) {
   int n = (W / 2) * (H / 2) * 3;
   k_pyrdown_bgr<<<(n + 255) / 256, 256, 0, s>>>(src, W, H, dst);
@@ -222,13 +236,15 @@ void fl_launch_pyrdown_bgr(const uint8_t* src, int W, int H, uint8_t* dst, cudaS
 #define DQ_TH 16
 #define DQ_THREADS 256
 
-__global__ void __launch_bounds__(DQ_THREADS) k_depth_quantize(const uint16_t* __restrict__ depth, int W, int H, int dist_thr,
-                                                               int diff_thr, uint8_t* __restrict__ q) {
+#define DQ_SMEM_BYTES ((DQ_TH + 14) * (DQ_TW + 14) * 2 + (DQ_TH + 4) * (DQ_TW + 4) + 16)
+
+__device__ __forceinline__ void dev_depth_quantize(const uint16_t* __restrict__ depth, int W, int H, int dist_thr, int diff_thr,
+                                                   uint8_t* __restrict__ q, int bx, int by, uint8_t* smem) {
   constexpr int RW = DQ_TW + 4, RH = DQ_TH + 4;      // raw label tile (median halo 2)
   constexpr int SW = RW + 10, SH = RH + 10;          // depth tile (tap radius 5)
-  __shared__ uint16_t s_d[SH][SW];
-  __shared__ uint8_t s_r[RH][RW];
-  const int x0 = blockIdx.x * DQ_TW, y0 = blockIdx.y * DQ_TH;
+  uint16_t(*s_d)[SW] = reinterpret_cast<uint16_t(*)[SW]>(smem);
+  uint8_t(*s_r)[RW] = reinterpret_cast<uint8_t(*)[RW]>(smem + ((SH * SW * 2 + 15) & ~15));
+  const int x0 = bx * DQ_TW, y0 = by * DQ_TH;
   const int tid = threadIdx.x;
   for (int i = tid; i < SH * SW; i += DQ_THREADS) {
     int r = i / SW, c = i - r * SW;
@@ -299,6 +315,12 @@ __global__ void __launch_bounds__(DQ_THREADS) k_depth_quantize(const uint16_t* _
   }
 }
 
+__global__ void __launch_bounds__(DQ_THREADS) k_depth_quantize(const uint16_t* __restrict__ depth, int W, int H, int dist_thr,
+                                                               int diff_thr, uint8_t* __restrict__ q) {
+  __shared__ __align__(16) uint8_t smem[DQ_SMEM_BYTES];
+  dev_depth_quantize(depth, W, H, dist_thr, diff_thr, q, blockIdx.x, blockIdx.y, smem);
+}
+
 void fl_launch_depth_quantize(const uint16_t* depth, int W, int H, int dist_thr, int diff_thr, uint8_t* q, cudaStream_t s) {
   dim3 grid((W + DQ_TW - 1) / DQ_TW, (H + DQ_TH - 1) / DQ_TH);
   k_depth_quantize<<<grid, DQ_THREADS, 0, s>>>(depth, W, H, dist_thr, diff_thr, q);
@@ -307,14 +329,17 @@ void fl_launch_depth_quantize(const uint16_t* depth, int W, int H, int dist_thr,
 // ------------------------------------------------------------------------------------------------
 // K4 nearest-neighbour x1/2 (cv::resize INTER_NEAREST to (W/2, H/2)) and mask application (copyTo(dst, mask))
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_resize_nn_half(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ dst) {
+__device__ __forceinline__ void dev_resize_nn_half(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ dst, int bx) {
   const int dw = W / 2, dh = H / 2;
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int i = bx * 256 + threadIdx.x;
   if (i >= dw * dh) return;
   int x = i % dw, y = i / dw;
   int sx = min((int)floor(x * ((double)W / dw)), W - 1);
   int sy = min((int)floor(y * ((double)H / dh)), H - 1);
   dst[i] = src[(size_t)sy * W + sx];
+}
+__global__ void __launch_bounds__(256) k_resize_nn_half(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ dst) {
+  dev_resize_nn_half(src, W, H, dst, blockIdx.x);
 }
 void fl_launch_resize_nn_half(const uint8_t* src, int W, int H, uint8_t* dst, cudaStream_t s) {
   int n = (W / 2) * (H / 2);
@@ -340,12 +365,16 @@ void fl_launch_apply_mask(const uint8_t* q, const uint8_t* mask, int n, uint8_t*
 #define SL_CW 32
 #define SL_THREADS 256
 
-__global__ void __launch_bounds__(SL_THREADS) k_spread_lm(const uint8_t* __restrict__ q, fl_level_geom g, uint8_t* __restrict__ lm,
-                                                          uint8_t* __restrict__ spread_out) {
-  extern __shared__ uint8_t s_raw[];                    // [(2T-1)][tw] input (later reused for the final spread), then [(2T-1)][pw]
-  __shared__ uint2 s_resp[256];
+__host__ __device__ inline size_t spread_smem_bytes(int T) {
+  return 2048 + (size_t)(2 * T - 1) * (SL_CW * T + T - 1) + (size_t)(2 * T - 1) * (SL_CW * T);   // response table + two tiles; <= 35 KB at T = 16
+}
+
+__device__ __forceinline__ void dev_spread_lm(const uint8_t* __restrict__ q, const fl_level_geom& g, uint8_t* __restrict__ lm,
+                                              uint8_t* __restrict__ spread_out, int bx, int by, uint8_t* smem) {
+  uint2* s_resp = reinterpret_cast<uint2*>(smem);        // 256 x 8 B
+  uint8_t* s_raw = smem + 2048;                          // [(2T-1)][tw] input (later reused for the final spread), then [(2T-1)][pw]
   const int T = g.T, W = g.W, H = g.H, Wd = g.Wd;
-  const int gy = blockIdx.y, cx0 = blockIdx.x * SL_CW;
+  const int gy = by, cx0 = bx * SL_CW;
   const int ncell = min(SL_CW, Wd - cx0);
   const int pw = ncell * T;                             // pixels owned by this CTA per row
   const int tw = pw + T - 1, th = 2 * T - 1;
@@ -404,8 +433,71 @@ __global__ void __launch_bounds__(SL_THREADS) k_spread_lm(const uint8_t* __restr
   }
 }
 
+__global__ void __launch_bounds__(SL_THREADS) k_spread_lm(const uint8_t* __restrict__ q, fl_level_geom g, uint8_t* __restrict__ lm,
+                                                          uint8_t* __restrict__ spread_out) {
+  extern __shared__ __align__(16) uint8_t smem_dyn[];
+  dev_spread_lm(q, g, lm, spread_out, blockIdx.x, blockIdx.y, smem_dyn);
+}
+
 void fl_launch_spread_lm(const uint8_t* q, fl_level_geom g, uint8_t* lm_mod, uint8_t* spread_or_null, cudaStream_t s) {
-  size_t smem = (size_t)(2 * g.T - 1) * (SL_CW * g.T + g.T - 1) + (size_t)(2 * g.T - 1) * (SL_CW * g.T);   // <= 33 KB at T = 16
   dim3 grid((g.Wd + SL_CW - 1) / SL_CW, g.Hd);
-  k_spread_lm<<<grid, SL_THREADS, smem, s>>>(q, g, lm_mod, spread_or_null);
+  k_spread_lm<<<grid, SL_THREADS, spread_smem_bytes(g.T), s>>>(q, g, lm_mod, spread_or_null);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Wave kernel: at VGA every stage above moves a few hundred KB, i.e. ~1 us of HBM time against ~5-8 us of launch +
+// dependency latency, so the front end is launch bound.  All stages that are independent of each other at one point of
+// the pyramid recursion are therefore issued as ONE launch: the grid is the concatenation of the jobs' grids.
+//   wave 0      : colour quantise L0 | depth quantise L0 | pyrDown L0->L1
+//   wave k >= 1 : colour quantise Lk | NN-downsample depth labels Lk | pyrDown Lk->Lk+1 | spread+LM of level k-1 (all modalities)
+//   last wave   : spread+LM of the coarsest level
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_front_end_wave(fl_fe_wave w) {
+  extern __shared__ __align__(16) uint8_t smem_dyn[];
+  const int b = blockIdx.x;
+  int j = 0;
+#pragma unroll 1
+  while (j + 1 < w.n_jobs && b >= w.job[j + 1].cta_begin) ++j;
+  const fl_fe_job& jb = w.job[j];
+  const int local = b - jb.cta_begin;
+  switch (jb.kind) {
+    case FL_JOB_COLOR: dev_color_quantize(jb.src, jb.W, jb.H, jb.thr_sq, jb.dst, local % jb.gx, local / jb.gx, smem_dyn); break;
+    case FL_JOB_DEPTH: dev_depth_quantize(reinterpret_cast<const uint16_t*>(jb.src), jb.W, jb.H, jb.p0, jb.p1, jb.dst, local % jb.gx, local / jb.gx, smem_dyn); break;
+    case FL_JOB_PYRDOWN: dev_pyrdown_bgr(jb.src, jb.W, jb.H, jb.dst, local); break;
+    case FL_JOB_RESIZE: dev_resize_nn_half(jb.src, jb.W, jb.H, jb.dst, local); break;
+    case FL_JOB_SPREAD: dev_spread_lm(jb.src, jb.g, jb.dst, jb.dst2, local % jb.gx, local / jb.gx, smem_dyn); break;
+  }
+}
+
+void fl_fe_add_color(fl_fe_wave* w, const uint8_t* bgr, int W, int H, float thr_sq, uint8_t* q) {
+  fl_fe_job& j = w->job[w->n_jobs++];
+  j.kind = FL_JOB_COLOR; j.src = bgr; j.dst = q; j.dst2 = nullptr; j.W = W; j.H = H; j.thr_sq = thr_sq;
+  j.gx = (W + CQ_TW - 1) / CQ_TW; j.cta_begin = w->n_ctas; w->n_ctas += j.gx * ((H + CQ_TH - 1) / CQ_TH);
+  w->smem = w->smem > (size_t)CQ_SMEM_BYTES ? w->smem : (size_t)CQ_SMEM_BYTES;
+}
+void fl_fe_add_depth(fl_fe_wave* w, const uint16_t* depth, int W, int H, int dist_thr, int diff_thr, uint8_t* q) {
+  fl_fe_job& j = w->job[w->n_jobs++];
+  j.kind = FL_JOB_DEPTH; j.src = reinterpret_cast<const uint8_t*>(depth); j.dst = q; j.dst2 = nullptr; j.W = W; j.H = H; j.p0 = dist_thr; j.p1 = diff_thr;
+  j.gx = (W + DQ_TW - 1) / DQ_TW; j.cta_begin = w->n_ctas; w->n_ctas += j.gx * ((H + DQ_TH - 1) / DQ_TH);
+  w->smem = w->smem > (size_t)DQ_SMEM_BYTES ? w->smem : (size_t)DQ_SMEM_BYTES;
+}
+void fl_fe_add_pyrdown(fl_fe_wave* w, const uint8_t* src, int W, int H, uint8_t* dst) {
+  fl_fe_job& j = w->job[w->n_jobs++];
+  j.kind = FL_JOB_PYRDOWN; j.src = src; j.dst = dst; j.dst2 = nullptr; j.W = W; j.H = H; j.gx = 1;
+  j.cta_begin = w->n_ctas; w->n_ctas += ((W / 2) * (H / 2) * 3 + 255) / 256;
+}
+void fl_fe_add_resize(fl_fe_wave* w, const uint8_t* src, int W, int H, uint8_t* dst) {
+  fl_fe_job& j = w->job[w->n_jobs++];
+  j.kind = FL_JOB_RESIZE; j.src = src; j.dst = dst; j.dst2 = nullptr; j.W = W; j.H = H; j.gx = 1;
+  j.cta_begin = w->n_ctas; w->n_ctas += ((W / 2) * (H / 2) + 255) / 256;
+}
+void fl_fe_add_spread(fl_fe_wave* w, const uint8_t* q, fl_level_geom g, uint8_t* lm_mod, uint8_t* spread_or_null) {
+  fl_fe_job& j = w->job[w->n_jobs++];
+  j.kind = FL_JOB_SPREAD; j.src = q; j.dst = lm_mod; j.dst2 = spread_or_null; j.g = g; j.W = g.W; j.H = g.H;
+  j.gx = (g.Wd + SL_CW - 1) / SL_CW; j.cta_begin = w->n_ctas; w->n_ctas += j.gx * g.Hd;
+  size_t sm = spread_smem_bytes(g.T);
+  w->smem = w->smem > sm ? w->smem : sm;
+}
+void fl_launch_fe_wave(const fl_fe_wave& w, cudaStream_t s) {
+  if (w.n_ctas > 0) k_front_end_wave<<<w.n_ctas, 256, w.smem, s>>>(w);
 }

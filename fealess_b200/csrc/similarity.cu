@@ -125,13 +125,15 @@ void fl_launch_similarity_debug(fl_tdb db, fl_level_geom g, const uint8_t* lm_le
 // K7 local refinement of every candidate at one finer level: 16x16 patch of total similarity, first maximum wins.
 // One CTA of 64 threads per candidate: thread = (patch row, 4-cell column group).
 // ------------------------------------------------------------------------------------------------
-#define RF_THREADS 64
+#define RF_THREADS 256       // 4 feature groups x 64 (16 patch rows x 4 column groups of 4 cells)
 
 __global__ void __launch_bounds__(RF_THREADS) k_refine_level(fl_tdb db, fl_level_geom g, int level, const uint8_t* __restrict__ lm_level,
                                                              float threshold, fl_match_t* __restrict__ cand, int cap,
                                                              const int* __restrict__ d_count) {
   const int n = min(*d_count, cap);
-  const int row = threadIdx.x >> 2, cg = threadIdx.x & 3;
+  const int fgrp = threadIdx.x >> 6, cell = threadIdx.x & 63;
+  const int row = cell >> 2, cg = cell & 3;
+  __shared__ uint32_t s_part[3][64][2];
   __shared__ uint32_t s_best[2];
   for (int ci = blockIdx.x; ci < n; ci += gridDim.x) {
     fl_match_t mt = cand[ci];
@@ -153,35 +155,52 @@ __global__ void __launch_bounds__(RF_THREADS) k_refine_level(fl_tdb db, fl_level
       const uint8_t* lm_mod = lm_level + (size_t)m * g.mod_stride;
       const fl_pfeat* pf = db.pfeat + h.feature_begin;
       uint32_t acc = 0;
-      for (int k = 0; k < h.feature_count; ++k) {
-        fl_pfeat p = pf[k];
-        int fx = p.x + ox, fy = p.y + oy;
-        if (fx < 0 || fy < 0 || fx >= g.W || fy >= g.H) continue;  // :1257
-        // the packed offset was computed for (x, y); shifting by a multiple of T moves only the cell index
-        uint32_t o = p.lm_off;
-        if (o == FL_SKIP) {                                        // feature outside the image unshifted, inside when shifted
-          o = (uint32_t)((size_t)db.feat[h.feature_begin + k].label * g.label_stride +
-                         (size_t)((p.y % T + T) % T * T + (p.x % T + T) % T) * g.cells + (size_t)(fy / T) * g.Wd + fx / T);
-          acc += load_u8x4(lm_mod, o + row * g.Wd + cg * 4);
-        } else {
-          acc += load_u8x4(lm_mod, (uint32_t)((int)o + delta));
+      // each of the 4 feature groups takes every 4th feature; 4 independent windows are in flight per thread
+      for (int k0 = fgrp; k0 < h.feature_count; k0 += 16) {
+        uint32_t v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int k = k0 + 4 * u;
+          v[u] = 0;
+          if (k < h.feature_count) {
+            const fl_pfeat p = pf[k];
+            const int fx = p.x + ox, fy = p.y + oy;
+            if (fx >= 0 && fy >= 0 && fx < g.W && fy < g.H) {      // :1257
+              // the packed offset was computed for (x, y); shifting by a multiple of T moves only the cell index
+              uint32_t o = p.lm_off;
+              if (o == FL_SKIP)                                    // outside the image unshifted, inside when shifted
+                o = (uint32_t)((size_t)db.feat[h.feature_begin + k].label * g.label_stride +
+                               (size_t)((p.y % T + T) % T * T + (p.x % T + T) % T) * g.cells + (size_t)(fy / T) * g.Wd + fx / T) +
+                    (uint32_t)(row * g.Wd + cg * 4);
+              else
+                o = (uint32_t)((int)o + delta);
+              v[u] = load_u8x4(lm_mod, o);
+            }
+          }
         }
+        acc += v[0] + v[1] + v[2] + v[3];                          // u8 lanes: <= 63 features x 4, no carry
       }
       tot_lo += (acc & 0xFF) | ((acc & 0xFF00) << 8);
       tot_hi += ((acc >> 16) & 0xFF) | ((acc >> 24) << 16);
     }
-    // first maximum in row-major order: key = score << 8 | (255 - index); all-zero patch -> best 0 at (-1,-1) (:1547-1562)
-    uint32_t key = 0;
+    if (fgrp > 0) { s_part[fgrp - 1][cell][0] = tot_lo; s_part[fgrp - 1][cell][1] = tot_hi; }
+    __syncthreads();
+    if (fgrp == 0) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      uint32_t sc = (k < 2 ? tot_lo >> (16 * k) : tot_hi >> (16 * (k - 2))) & 0xFFFF;
-      uint32_t idx = row * 16 + cg * 4 + k;
-      uint32_t kk = (sc << 8) | (255 - idx);
-      if (sc > 0 && kk > key) key = kk;
+      for (int gq = 0; gq < 3; ++gq) { tot_lo += s_part[gq][cell][0]; tot_hi += s_part[gq][cell][1]; }   // u16 lanes
+      // first maximum in row-major order: key = score << 8 | (255 - index); all-zero patch -> best 0 at (-1,-1) (:1547-1562)
+      uint32_t key = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        uint32_t sc = (k < 2 ? tot_lo >> (16 * k) : tot_hi >> (16 * (k - 2))) & 0xFFFF;
+        uint32_t idx = row * 16 + cg * 4 + k;
+        uint32_t kk = (sc << 8) | (255 - idx);
+        if (sc > 0 && kk > key) key = kk;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) key = max(key, __shfl_xor_sync(0xffffffffu, key, o));
+      if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = key;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) key = max(key, __shfl_xor_sync(0xffffffffu, key, o));
-    if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = key;
     __syncthreads();
     if (threadIdx.x == 0) {
       uint32_t kb = max(s_best[0], s_best[1]);
@@ -201,7 +220,7 @@ __global__ void __launch_bounds__(RF_THREADS) k_refine_level(fl_tdb db, fl_level
 
 void fl_launch_refine_level(fl_tdb db, fl_level_geom g, int level, const uint8_t* lm_level, float threshold, fl_match_t* cand,
                             int cap, const int* d_count, cudaStream_t s) {
-  int grid = min(cap, 148 * 16);
+  int grid = min(cap, 148 * 4);
   if (grid > 0) k_refine_level<<<grid, RF_THREADS, 0, s>>>(db, g, level, lm_level, threshold, cand, cap, d_count);
 }
 
