@@ -27,6 +27,7 @@ struct fl_handle {
   fl_template_hdr_t* d_hdr; fl_feature_t* d_feat; int32_t* d_class_of; int32_t* d_class_first; uint8_t* d_class_enabled;
   fl_pfeat* d_pfeat; int32_t* d_tid_of;
   std::vector<int32_t> tid_of_h;
+  std::vector<int32_t> coarse_wh;                          // (width, height) of every template at the coarsest level
   bool staged_eligible, use_staged; int n_sm; int force_baseline;   // staged global-similarity kernel (similarity_staged.cu)
   fl_staged_plan plan;
   std::vector<int32_t> class_first_h, class_of_h;
@@ -161,8 +162,8 @@ static void icp_free(fl_handle* h) {
 
 static void free_templates(fl_handle* h) {
   cudaFree(h->d_hdr); cudaFree(h->d_feat); cudaFree(h->d_class_of); cudaFree(h->d_class_first); cudaFree(h->d_class_enabled); cudaFree(h->d_pfeat);
-  cudaFree(h->d_tid_of); cudaFree(h->plan.gfeat); cudaFree(h->plan.ph_off);
-  h->plan.gfeat = nullptr; h->plan.ph_off = nullptr; h->use_staged = false; h->staged_eligible = false;
+  cudaFree(h->d_tid_of); cudaFree(h->plan.gfeat);
+  h->plan.gfeat = nullptr; h->use_staged = false; h->staged_eligible = false;
   h->d_hdr = nullptr; h->d_feat = nullptr; h->d_class_of = nullptr; h->d_class_first = nullptr; h->d_class_enabled = nullptr; h->d_pfeat = nullptr;
   h->d_tid_of = nullptr;
   h->n_templates = h->n_features = h->n_classes = 0; h->packed = false;
@@ -238,6 +239,11 @@ extern "C" int fl_upload_templates(fl_handle* h, int32_t n_templates, const fl_t
   FL_CUDA(cudaStreamSynchronize(h->stream));
   free_templates(h);
   h->staged_eligible = eligible;
+  h->coarse_wh.resize((size_t)n_templates * 2);
+  for (int t = 0; t < n_templates; ++t) {
+    const fl_template_hdr_t& hd = headers[((size_t)t * L + (L - 1)) * M];
+    h->coarse_wh[2 * t] = hd.width; h->coarse_wh[2 * t + 1] = hd.height;
+  }
   TRY(dalloc(&h->d_hdr, ne)); TRY(dalloc(&h->d_feat, (size_t)n_features)); TRY(dalloc(&h->d_class_of, (size_t)n_templates));
   TRY(dalloc(&h->d_class_first, (size_t)nc)); TRY(dalloc(&h->d_class_enabled, (size_t)std::max(nc, 1))); TRY(dalloc(&h->d_pfeat, (size_t)n_features));
   if (ne) FL_CUDA(cudaMemcpy(h->d_hdr, headers, ne * sizeof(fl_template_hdr_t), cudaMemcpyHostToDevice));
@@ -288,6 +294,17 @@ static fl_tdb make_tdb(fl_handle* h) {
   return db;
 }
 
+// largest template_positions (linemod.cpp:1155) of the uploaded templates at the coarsest level of the current geometry
+static int max_positions(const fl_handle* h) {
+  const fl_level_geom& g = h->geom[h->p.n_levels - 1];
+  int best = 0;
+  for (size_t t = 0; t + 1 < h->coarse_wh.size(); t += 2) {
+    const int wf = (h->coarse_wh[t] - 1) / g.T + 1, hf = (h->coarse_wh[t + 1] - 1) / g.T + 1;
+    best = std::max(best, std::min((g.Hd - hf) * g.Wd + (g.Wd - wf) + 1, g.cells));
+  }
+  return best;
+}
+
 static int ensure_geometry(fl_handle* h, int W, int H) {
   const fl_params_t& p = h->p;
   if (W <= 0 || H <= 0 || W > p.max_width || H > p.max_height) { fl_set_error("frame %dx%d exceeds handle capacity %dx%d", W, H, p.max_width, p.max_height); return FL_ERR_SIZE; }
@@ -310,11 +327,10 @@ static int ensure_geometry(fl_handle* h, int W, int H) {
     h->use_staged = false;
     fl_staged_plan plan;
     if (h->staged_eligible && !h->force_baseline && h->n_templates >= 256 &&
-        fl_plan_staged(h->geom[p.n_levels - 1], p.n_modalities, h->n_templates, h->n_sm, &plan)) {
-      cudaFree(h->plan.gfeat); cudaFree(h->plan.ph_off);
+        fl_plan_staged(h->geom[p.n_levels - 1], p.n_modalities, h->n_templates, max_positions(h), h->n_sm, &plan)) {
+      cudaFree(h->plan.gfeat);
       h->plan = plan;
       TRY(dalloc(&h->plan.gfeat, (size_t)h->n_templates * 64));
-      TRY(dalloc(&h->plan.ph_off, (size_t)h->n_templates * (plan.n_phases + 1)));
       fl_launch_pack_staged(make_tdb(h), h->geom[p.n_levels - 1], h->plan, h->stream); ++h->launches;
       h->use_staged = true;
     }

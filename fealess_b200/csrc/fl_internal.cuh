@@ -77,10 +77,9 @@ struct fl_staged_plan {
   int halo_bytes, buf_bytes, n_buf;        // bytes staged past the last row; size and number of the smem ring buffers
   int n_words, nw_template, tpw;           // 32-bit words per similarity map; template parameters of the instantiation used
   int tpc, n_cta, block_threads;           // templates per CTA, grid, block
-  uint32_t* gfeat;                         // [n_templates][64] per-phase byte offsets of the features, sorted by phase
-  uint8_t* ph_off;                         // [n_templates][n_phases + 1] prefix offsets into gfeat rows
+  uint32_t* gfeat;                         // [n_templates][64] feature words sorted by phase: phase << 24 | byte offset in the phase buffer
 };
-bool fl_plan_staged(const fl_level_geom& g, int M, int n_templates, int n_sm, fl_staged_plan* plan);
+bool fl_plan_staged(const fl_level_geom& g, int M, int n_templates, int max_positions, int n_sm, fl_staged_plan* plan);
 void fl_launch_pack_staged(fl_tdb db, fl_level_geom g, fl_staged_plan plan, cudaStream_t s);
 int fl_launch_similarity_staged(fl_tdb db, fl_level_geom g, const uint8_t* lm_level, float threshold, fl_match_t* cand, int cap,
                                 int* d_count, fl_staged_plan plan, cudaStream_t s);

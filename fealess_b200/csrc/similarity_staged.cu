@@ -10,11 +10,12 @@
 //     packed-u8 similarity accumulators in registers for the whole kernel;
 //   * one elected thread streams phase p+2 into the free buffer with a single cp.async.bulk while all warps consume
 //     phase p; completion is signalled on an mbarrier (expect_tx);
-//   * features were bucketed by phase once per frame geometry (k_pack_staged), and a warp keeps its templates' feature
-//     words and per-phase offsets in registers (lane k holds feature k), broadcasting them with shuffles, so the inner
-//     loop touches global memory only through the bulk copies;
-//   * lane g owns the 32-bit words {g + 32 i} of the similarity map, so every LDS of a warp covers 32 consecutive words
-//     (bank-conflict free) at any feature offset; the byte misalignment is a funnel shift of two loaded words.
+//   * features were sorted by phase once per frame geometry (k_pack_staged; the phase id rides in the top byte of the
+//     feature word), and a warp keeps its templates' feature words in registers (lane k holds feature k), broadcasting
+//     the next one with a shuffle, so the inner loop touches global memory only through the bulk copies;
+//   * lane g owns the NW consecutive 32-bit words [g NW, (g+1) NW) of the similarity map (NW odd, so the 32 lanes of one
+//     LDS fall into 32 different banks at any feature offset); a byte-misaligned window costs NW + 1 loads, not 2 NW: the
+//     high word of one funnel shift is the low word of the next.
 //
 // Semantics are those of similarity() / addSimilarities / the scan in matchClass (reference linemod/linemod.cpp:1130-1214,
 // 1322-1338, 1487-1506) including flat addressing past a row end.  Eligibility (checked on the host): every
@@ -23,6 +24,8 @@
 #include "fl_internal.cuh"
 
 #define SS_MAXF 64                      // feature words per template (<= 63 used)
+#define SS_MAX_PHASES 254               // the phase id travels in the top byte of a feature word
+#define SS_NOFEAT 0xFFFFFFFFu           // padding word: phase 255 never comes up
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -59,20 +62,19 @@ __global__ void __launch_bounds__(128) k_pack_staged(fl_tdb db, fl_level_geom g,
   const int level = db.L - 1;
   const fl_template_hdr_t* hdr = db.hdr + ((size_t)t * db.L + level) * db.M;
   uint32_t* out = plan.gfeat + (size_t)t * SS_MAXF;
-  uint8_t* off = plan.ph_off + (size_t)t * (plan.n_phases + 1);
   // counting sort by phase (n <= 63): pass 1 counts, pass 2 places
-  for (int p = 0; p <= plan.n_phases; ++p) off[p] = 0;
+  uint8_t cur[SS_MAX_PHASES + 1];
+  for (int p = 0; p <= plan.n_phases; ++p) cur[p] = 0;
   for (int m = 0; m < db.M; ++m)
     for (int k = 0; k < hdr[m].feature_count; ++k) {
       const fl_feature_t f = db.feat[hdr[m].feature_begin + k];
       if (f.x < 0 || f.y < 0 || f.x >= g.W || f.y >= g.H) continue;                     // linemod.cpp:1179
       const int row = (f.y % g.T) * g.T + (f.x % g.T);
       const int ph = (m * 8 + f.label) * plan.n_rowblocks + row / plan.phase_rows;
-      ++off[ph + 1];
+      ++cur[ph + 1];
     }
-  for (int p = 0; p < plan.n_phases; ++p) off[p + 1] = (uint8_t)(off[p + 1] + off[p]);
-  uint8_t cur[8 * FL_MAX_MODALITIES * 16];                                              // n_phases <= 512 by construction
-  for (int p = 0; p < plan.n_phases; ++p) cur[p] = off[p];
+  for (int p = 0; p < plan.n_phases; ++p) cur[p + 1] = (uint8_t)(cur[p + 1] + cur[p]);   // cur[p] = first slot of phase p
+  const int total = cur[plan.n_phases];
   for (int m = 0; m < db.M; ++m)
     for (int k = 0; k < hdr[m].feature_count; ++k) {
       const fl_feature_t f = db.feat[hdr[m].feature_begin + k];
@@ -80,8 +82,10 @@ __global__ void __launch_bounds__(128) k_pack_staged(fl_tdb db, fl_level_geom g,
       const int row = (f.y % g.T) * g.T + (f.x % g.T);
       const int rb = row / plan.phase_rows;
       const int ph = (m * 8 + f.label) * plan.n_rowblocks + rb;
-      out[cur[ph]++] = (uint32_t)((row - rb * plan.phase_rows) * g.cells + (f.y / g.T) * g.Wd + f.x / g.T);
+      // feature word: phase in the top byte, byte offset of the feature's first response inside the phase buffer below
+      out[cur[ph]++] = ((uint32_t)ph << 24) | (uint32_t)((row - rb * plan.phase_rows) * g.cells + (f.y / g.T) * g.Wd + f.x / g.T);
     }
+  for (int k = total; k < SS_MAXF; ++k) out[k] = SS_NOFEAT;
 }
 
 void fl_launch_pack_staged(fl_tdb db, fl_level_geom g, fl_staged_plan plan, cudaStream_t s) {
@@ -95,21 +99,24 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// add N consecutive-by-32 words of one feature's response window into the accumulators (all loads first, then the adds)
-template <int N, int NW>
-__device__ __forceinline__ void accumulate_words(const uint32_t* __restrict__ base, uint32_t sh, uint32_t (&acc)[NW]) {
-  if (sh == 0) {                                              // word-aligned feature: one load per word
-    uint32_t v[N];
+// One feature of one template: lane g owns the NW consecutive 32-bit words [g*NW, (g+1)*NW) of the similarity map, so
+// its window is the NW + 1 consecutive words starting at its base + the feature's word offset: NW + 1 loads (instead of
+// two per word), one funnel shift and one add per word.  NW is odd, so the 32 lanes of one load hit 32 different banks.
+template <int NW>
+__device__ __forceinline__ void accumulate_feature(const uint8_t* __restrict__ lane_base, uint32_t a, uint32_t (&acc)[NW]) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(lane_base + (a & 0x00FFFFFCu));
+  const uint32_t sh = a << 3;                                 // funnel shift uses the low 5 bits: (a & 3) * 8
+  constexpr int CH = 12;                                      // loads in flight per chunk (register budget)
+  uint32_t carry = w[0];
 #pragma unroll
-    for (int i = 0; i < N; ++i) v[i] = base[32 * i];
+  for (int c = 0; c < NW; c += CH) {
+    uint32_t v[CH + 1];
+    v[0] = carry;
 #pragma unroll
-    for (int i = 0; i < N; ++i) acc[i] += v[i];
-  } else {
-    uint32_t lo[N], hi[N];
+    for (int i = 0; i < CH; ++i) if (c + i < NW) v[i + 1] = w[c + i + 1];
 #pragma unroll
-    for (int i = 0; i < N; ++i) { lo[i] = base[32 * i]; hi[i] = base[32 * i + 1]; }
-#pragma unroll
-    for (int i = 0; i < N; ++i) acc[i] += __funnelshift_r(lo[i], hi[i], sh);   // four u8 lanes, no carry (sums <= 252)
+    for (int i = 0; i < CH; ++i) if (c + i < NW) acc[c + i] += __funnelshift_r(v[i], v[i + 1], sh);   // four u8 lanes, no carry (sums <= 252)
+    carry = v[(NW - c) < CH ? (NW - c) : CH];
   }
 }
 
@@ -154,55 +161,49 @@ __global__ void __launch_bounds__(1024, 1) k_similarity_staged(fl_tdb db, fl_lev
     return;
   }
 
-  // ===== consumers: this warp's templates; feature words and phase offsets live in registers, one per lane =====
-  int tt[TPW], niw[TPW];
-  uint32_t fw0[TPW], fw1[TPW], po0[TPW], po1[TPW];
+  // ===== consumers: this warp's templates.  Feature words (phase-sorted, phase id in the top byte) live in registers,
+  // one per lane (fa: features 0-31, fb: 32-63); kcur walks them in this CTA's rotated phase order =====
+  int tt[TPW], kcur[TPW], nfeat[TPW], nleft[TPW];
+  uint32_t fa[TPW], fb[TPW], fnext[TPW];
   uint32_t acc[TPW][NW];
 #pragma unroll
   for (int s = 0; s < TPW; ++s) {
     const int t = t_begin + warp + s * n_cwarps;
     tt[s] = (t < t_end && db.class_enabled[db.class_of[t]]) ? t : -1;
-    fw0[s] = fw1[s] = po0[s] = po1[s] = 0;
-    niw[s] = 0;
+    fa[s] = fb[s] = fnext[s] = SS_NOFEAT;
+    kcur[s] = nfeat[s] = nleft[s] = 0;
     if (tt[s] >= 0) {
-      fw0[s] = plan.gfeat[(size_t)t * SS_MAXF + lane];
-      fw1[s] = plan.gfeat[(size_t)t * SS_MAXF + 32 + lane];
-      if (lane <= n_phases) po0[s] = plan.ph_off[(size_t)t * (n_phases + 1) + lane];
-      if (lane + 32 <= n_phases) po1[s] = plan.ph_off[(size_t)t * (n_phases + 1) + lane + 32];
-      // only the words holding cells < template_positions matter; the count of 32-word strides is warp uniform
-      const fl_template_hdr_t h0 = db.hdr[((size_t)t * db.L + level) * db.M];
-      const int wf = (h0.width - 1) / g.T + 1, hf = (h0.height - 1) / g.T + 1;
-      const int tp = min((g.Hd - hf) * g.Wd + (g.Wd - wf) + 1, g.cells);
-      niw[s] = tp > 0 ? ((tp + 3) / 4 + 31) / 32 : 0;
-      if (niw[s] == 0) tt[s] = -1;
+      fa[s] = plan.gfeat[(size_t)t * SS_MAXF + lane];
+      fb[s] = plan.gfeat[(size_t)t * SS_MAXF + 32 + lane];
+      nfeat[s] = __popc(__ballot_sync(0xffffffffu, fa[s] != SS_NOFEAT)) + __popc(__ballot_sync(0xffffffffu, fb[s] != SS_NOFEAT));
+      // first feature at or after phase `rot` (padding words carry phase 255 and never count)
+      kcur[s] = __popc(__ballot_sync(0xffffffffu, (int)(fa[s] >> 24) < rot)) + __popc(__ballot_sync(0xffffffffu, (int)(fb[s] >> 24) < rot));
+      if (kcur[s] >= nfeat[s]) kcur[s] = 0;
+      nleft[s] = nfeat[s];
+      if (nleft[s] > 0) fnext[s] = __shfl_sync(0xffffffffu, kcur[s] < 32 ? fa[s] : fb[s], kcur[s] & 31);
     }
 #pragma unroll
     for (int i = 0; i < NW; ++i) acc[s][i] = 0;
   }
 
+  int b = 0, p = rot;
+  uint32_t par = 0;
+  const uint8_t* lane_base0 = s_buf + lane * (NW * 4);
   for (int q = 0; q < n_phases; ++q) {
-    const int b = q % n_buf;
-    int p = q + rot; if (p >= n_phases) p -= n_phases;
-    mbar_wait(&s_full[b], (q / n_buf) & 1);
-    const uint32_t* sw = reinterpret_cast<const uint32_t*>(s_buf + (size_t)b * plan.buf_bytes) + lane;
+    mbar_wait(&s_full[b], par);
+    const uint8_t* lane_base = lane_base0 + b * plan.buf_bytes;
 #pragma unroll
     for (int s = 0; s < TPW; ++s) {
-      if (tt[s] < 0) continue;                                // warp-uniform
-      const int k0 = __shfl_sync(0xffffffffu, p < 32 ? po0[s] : po1[s], p & 31);
-      const int k1 = __shfl_sync(0xffffffffu, p + 1 < 32 ? po0[s] : po1[s], (p + 1) & 31);
-      for (int k = k0; k < k1; ++k) {
-        const uint32_t a = __shfl_sync(0xffffffffu, k < 32 ? fw0[s] : fw1[s], k & 31);
-        const uint32_t* base = sw + (a >> 2);
-        const uint32_t sh = (a & 3) * 8;
-        // three tiers of the (warp-uniform) stride count keep the loads unconditional; words past the template's range
-        // accumulate harmless response bytes (<= 4 each) that the emission step never looks at
-        if (NW > 4 && niw[s] <= NW - 4) accumulate_words<(NW > 4 ? NW - 4 : NW), NW>(base, sh, acc[s]);
-        else if (NW > 2 && niw[s] <= NW - 2) accumulate_words<(NW > 2 ? NW - 2 : NW), NW>(base, sh, acc[s]);
-        else accumulate_words<NW, NW>(base, sh, acc[s]);
+      while ((int)(fnext[s] >> 24) == p) {                    // warp-uniform
+        accumulate_feature<NW>(lane_base, fnext[s], acc[s]);
+        if (++kcur[s] == nfeat[s]) kcur[s] = 0;
+        fnext[s] = --nleft[s] > 0 ? __shfl_sync(0xffffffffu, kcur[s] < 32 ? fa[s] : fb[s], kcur[s] & 31) : SS_NOFEAT;
       }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&s_empty[b]);                  // this warp is done with buffer b
+    if (++b == n_buf) { b = 0; par ^= 1; }
+    if (++p == n_phases) p = 0;
   }
 
   // threshold + candidate emission (matchClass :1487-1506)
@@ -222,7 +223,7 @@ __global__ void __launch_bounds__(1024, 1) k_similarity_staged(fl_tdb db, fl_lev
     const uint32_t thr4 = raw_thr < 0 ? 0u : (uint32_t)raw_thr * 0x01010101u;
 #pragma unroll
     for (int i = 0; i < NW; ++i) {
-      const int w = lane + 32 * i;
+      const int w = lane * NW + i;
       if (4 * w >= tp) continue;
       const uint32_t v = acc[s][i];
       if (raw_thr >= 0 && !__vcmpgtu4(v, thr4)) continue;
@@ -260,20 +261,26 @@ static int launch_staged(fl_tdb db, fl_level_geom g, const uint8_t* lm_level, fl
   return 0;
 }
 
-// host planning: returns false if the geometry is not supported by the staged kernel
-bool fl_plan_staged(const fl_level_geom& g, int M, int n_templates, int n_sm, fl_staged_plan* plan) {
+// host planning: returns false if the geometry is not supported by the staged kernel.  max_positions = the largest
+// template_positions (linemod.cpp:1155) over the uploaded templates: only that many cells of a similarity map are ever
+// looked at, so the per-lane accumulator count NW is sized for it rather than for the whole grid.
+bool fl_plan_staged(const fl_level_geom& g, int M, int n_templates, int max_positions, int n_sm, fl_staged_plan* plan) {
+  static const int kNW[] = {5, 7, 9, 11, 13, 15, 19, 23, 29, 37};
   fl_staged_plan p;
   memset(&p, 0, sizeof p);
   const int T2 = g.T * g.T;
-  p.n_words = (g.cells + 3) / 4;
-  const int nw = (p.n_words + 31) / 32;
-  if (nw > 16) return false;                                   // accumulators would not fit the register budget
-  p.nw_template = nw <= 4 ? 4 : (nw <= 6 ? 6 : (nw <= 8 ? 8 : (nw <= 10 ? 10 : (nw <= 12 ? 12 : 16))));
-  p.tpw = p.nw_template > 10 ? 1 : 2;                          // register budget: 64 per thread at 1,024 threads
+  if (max_positions < 1 || n_templates < 1) return false;
+  if (max_positions > g.cells) max_positions = g.cells;
+  p.n_words = (max_positions + 3) / 4;
+  const int nw_min = (p.n_words + 31) / 32;
+  p.nw_template = 0;
+  for (int nw : kNW) if (nw >= nw_min) { p.nw_template = nw; break; }
+  if (!p.nw_template) return false;                            // accumulators would not fit the register budget
+  p.tpw = p.nw_template > 11 ? 1 : 2;                          // register budget: 64 per thread at 1,024 threads
   // bytes staged past the last row of a phase: a window starts at most at the last cell of the last row and the loads run
-  // unconditionally over 32 * NW words (+1 for the funnel shift)
+  // unconditionally over 32 * NW + 1 words
   p.halo_bytes = 32 * p.nw_template * 4 + 16;
-  if (p.halo_bytes + 16 > FL_LM_PAD || n_templates < 1) return false;
+  if (p.halo_bytes + 16 > FL_LM_PAD) return false;
   // rows per phase / number of buffers: 4 buffers of <= 48 KB when a (modality, label) splits evenly, else 2 of <= 100 KB;
   // a row block must start 16-byte aligned in global memory
   int pr = 0, nbuf = 0;
@@ -290,7 +297,8 @@ bool fl_plan_staged(const fl_level_geom& g, int M, int n_templates, int n_sm, fl
   p.phase_rows = pr;
   p.n_rowblocks = (T2 + pr - 1) / pr;
   p.n_phases = M * 8 * p.n_rowblocks;
-  if (p.n_phases + 1 > 64) return false;                       // per-phase prefix offsets are kept one per lane (2 registers)
+  if (p.n_phases > SS_MAX_PHASES) return false;                // the phase id travels in one byte of the feature word
+  if ((size_t)pr * g.cells + p.halo_bytes >= (1u << 24)) return false;
   p.n_buf = p.n_phases < nbuf ? p.n_phases : nbuf;
   p.buf_bytes = (int)((((size_t)pr * g.cells + p.halo_bytes + 15) & ~(size_t)15) + 127) & ~127;
   // CTAs: whole waves of the SM count, up to 31 consumer warps x TPW templates each (+ 1 producer warp)
@@ -308,12 +316,16 @@ bool fl_plan_staged(const fl_level_geom& g, int M, int n_templates, int n_sm, fl
 int fl_launch_similarity_staged(fl_tdb db, fl_level_geom g, const uint8_t* lm_level, float threshold, fl_match_t* cand, int cap,
                                 int* d_count, fl_staged_plan plan, cudaStream_t s) {
   switch (plan.nw_template) {
-    case 4: return launch_staged<4, 2>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
-    case 6: return launch_staged<6, 2>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
-    case 8: return launch_staged<8, 2>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
-    case 10: return launch_staged<10, 2>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
-    case 12: return launch_staged<12, 1>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
-    case 16: return launch_staged<16, 1>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
+    case 5: return launch_staged<5, 2>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
+    case 7: return launch_staged<7, 2>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
+    case 9: return launch_staged<9, 2>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
+    case 11: return launch_staged<11, 2>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
+    case 13: return launch_staged<13, 1>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
+    case 15: return launch_staged<15, 1>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
+    case 19: return launch_staged<19, 1>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
+    case 23: return launch_staged<23, 1>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
+    case 29: return launch_staged<29, 1>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
+    case 37: return launch_staged<37, 1>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
   }
   return -1;
 }
