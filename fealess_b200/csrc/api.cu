@@ -2,12 +2,12 @@
 // kernels in frontend.cu / similarity.cu / icp.cu on the handle's stream.  CUDA only - there is no CPU path here.
 #include "fl_internal.cuh"
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <new>
 #include <vector>
 
-int fl_launch_sort_unique_big(fl_sort_key* keys, int key_cap, int n_live, fl_match_t* d_out, int out_cap, int* d_out_count, cudaStream_t s);
 
 static thread_local char g_err[512] = "";
 void fl_set_error(const char* fmt, ...) {
@@ -46,9 +46,9 @@ struct fl_handle {
   uint8_t* d_lm[FL_MAX_LEVELS]; size_t lm_bytes[FL_MAX_LEVELS];
   bool used_mask[FL_MAX_MODALITIES]; bool keep_spread;
   // candidates / matches
-  fl_match_t* d_cand; int* d_count; fl_sort_key* d_keys; int key_cap; fl_match_t* d_out; int* d_out_count;
+  fl_match_t* d_cand; int* d_count; fl_sort_key* d_keys; int key_cap; uint8_t* d_outblk; fl_match_t* d_out; int* d_out_count;   // d_outblk = [16-int summary][matches]
   // pinned host staging
-  uint8_t* h_bgr; uint16_t* h_depth; uint8_t* h_mask; int* h_small; fl_match_t* h_first; uint8_t* h_class_enabled;
+  uint8_t* h_bgr; uint16_t* h_depth; uint8_t* h_mask; uint8_t* h_outblk; int* h_small; fl_match_t* h_first; uint8_t* h_class_enabled;   // h_small/h_first point into h_outblk
   bool have_result, overflow;
   // profiling
   bool profile; cudaEvent_t ev[5]; float stage_ms[4];
@@ -125,6 +125,7 @@ extern "C" int fl_create(const fl_params_t* params, fl_handle** out) {
   FL_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   for (int i = 0; i < 5; ++i) FL_CUDA(cudaEventCreate(&h->ev[i]));
   TRY(fl_launch_tables_init());
+  if (getenv("FL_CARVEOUT")) { fl_prefer_smem_carveout_frontend(); fl_prefer_smem_carveout_similarity(); }
   const size_t npx = (size_t)p.max_width * p.max_height;
   TRY(dalloc(&h->d_in_bgr, npx * 3)); TRY(dalloc(&h->d_in_depth, npx));
   TRY(dalloc(&h->d_geom, FL_MAX_LEVELS));
@@ -143,9 +144,11 @@ extern "C" int fl_create(const fl_params_t* params, fl_handle** out) {
   int kc = 2; while (kc < p.max_candidates) kc <<= 1;
   h->key_cap = kc;
   TRY(dalloc(&h->d_keys, (size_t)kc + 1));      // + room for the two scratch ints behind the keys
-  TRY(dalloc(&h->d_out, (size_t)p.max_candidates)); TRY(dalloc(&h->d_out_count, 4));
+  TRY(dalloc(&h->d_outblk, 64 + (size_t)p.max_candidates * sizeof(fl_match_t)));
+  h->d_out_count = reinterpret_cast<int*>(h->d_outblk); h->d_out = reinterpret_cast<fl_match_t*>(h->d_outblk + 64);
   TRY(halloc(&h->h_bgr, npx * 3)); TRY(halloc(&h->h_depth, npx)); TRY(halloc(&h->h_mask, npx * p.n_modalities));
-  TRY(halloc(&h->h_small, 16)); TRY(halloc(&h->h_first, FETCH_FIRST)); TRY(halloc(&h->h_class_enabled, 4096));
+  TRY(halloc(&h->h_outblk, 64 + FETCH_FIRST * sizeof(fl_match_t))); TRY(halloc(&h->h_class_enabled, 4096));
+  h->h_small = reinterpret_cast<int*>(h->h_outblk); h->h_first = reinterpret_cast<fl_match_t*>(h->h_outblk + 64);
   return FL_OK;
 }
 
@@ -162,8 +165,9 @@ static void icp_free(fl_handle* h) {
 
 static void free_templates(fl_handle* h) {
   cudaFree(h->d_hdr); cudaFree(h->d_feat); cudaFree(h->d_class_of); cudaFree(h->d_class_first); cudaFree(h->d_class_enabled); cudaFree(h->d_pfeat);
-  cudaFree(h->d_tid_of); cudaFree(h->plan.gfeat);
-  h->plan.gfeat = nullptr; h->use_staged = false; h->staged_eligible = false;
+  cudaFree(h->d_tid_of); cudaFree(h->plan.gfeat); cudaFree(h->plan.gpre); cudaFree(h->plan.gmeta); cudaFree(h->plan.trace);
+  h->plan.gfeat = nullptr; h->plan.gpre = nullptr; h->plan.gmeta = nullptr; h->plan.trace = nullptr;
+  h->use_staged = false; h->staged_eligible = false;
   h->d_hdr = nullptr; h->d_feat = nullptr; h->d_class_of = nullptr; h->d_class_first = nullptr; h->d_class_enabled = nullptr; h->d_pfeat = nullptr;
   h->d_tid_of = nullptr;
   h->n_templates = h->n_features = h->n_classes = 0; h->packed = false;
@@ -180,8 +184,8 @@ extern "C" int fl_destroy(fl_handle* h) {
     cudaFree(h->d_bgr[l]); cudaFree(h->d_lm[l]);
     for (int m = 0; m < FL_MAX_MODALITIES; ++m) { cudaFree(h->d_q[l][m]); cudaFree(h->d_qm[l][m]); cudaFree(h->d_mask[l][m]); cudaFree(h->d_spread[l][m]); }
   }
-  cudaFree(h->d_cand); cudaFree(h->d_count); cudaFree(h->d_keys); cudaFree(h->d_out); cudaFree(h->d_out_count);
-  cudaFreeHost(h->h_bgr); cudaFreeHost(h->h_depth); cudaFreeHost(h->h_mask); cudaFreeHost(h->h_small); cudaFreeHost(h->h_first); cudaFreeHost(h->h_class_enabled);
+  cudaFree(h->d_cand); cudaFree(h->d_count); cudaFree(h->d_keys); cudaFree(h->d_outblk);
+  cudaFreeHost(h->h_bgr); cudaFreeHost(h->h_depth); cudaFreeHost(h->h_mask); cudaFreeHost(h->h_outblk); cudaFreeHost(h->h_class_enabled);
   for (int i = 0; i < 5; ++i) cudaEventDestroy(h->ev[i]);
   cudaStreamDestroy(h->stream);
   delete h;
@@ -328,9 +332,15 @@ static int ensure_geometry(fl_handle* h, int W, int H) {
     fl_staged_plan plan;
     if (h->staged_eligible && !h->force_baseline && h->n_templates >= 256 &&
         fl_plan_staged(h->geom[p.n_levels - 1], p.n_modalities, h->n_templates, max_positions(h), h->n_sm, &plan)) {
-      cudaFree(h->plan.gfeat);
+      cudaFree(h->plan.gfeat); cudaFree(h->plan.gpre); cudaFree(h->plan.gmeta); cudaFree(h->plan.trace);
       h->plan = plan;
       TRY(dalloc(&h->plan.gfeat, (size_t)h->n_templates * 64));
+      TRY(dalloc(&h->plan.gpre, (size_t)h->n_templates * plan.pre_stride));
+      TRY(dalloc(&h->plan.gmeta, (size_t)h->n_templates));
+      if (getenv("FL_TRACE")) {                                                  // developer timeline of the staged kernel (FL_DBG_STAGED_TRACE)
+        TRY(dalloc(&h->plan.trace, (size_t)plan.n_cta * 72 + 8));                 // + stamps of a 1-thread kernel before / after the launch
+        FL_CUDA(cudaMemsetAsync(h->plan.trace, 0, ((size_t)plan.n_cta * 72 + 8) * sizeof(unsigned long long), h->stream));
+      }
       fl_launch_pack_staged(make_tdb(h), h->geom[p.n_levels - 1], h->plan, h->stream); ++h->launches;
       h->use_staged = true;
     }
@@ -362,10 +372,12 @@ static int run_match_stages(fl_handle* h, const uint8_t* d_bgr, const uint16_t* 
   for (int m = 0; m < p.n_modalities; ++m) { h->used_mask[m] = d_masks && d_masks[m]; any_mask |= h->used_mask[m]; }
   int first_color = -1;
   for (int m = 0; m < p.n_modalities; ++m) if (p.modality_kind[m] == FL_MODALITY_COLOR_GRADIENT && first_color < 0) first_color = m;
+  const bool zero_in_wave = !any_mask && getenv("FL_NO_MEMSET") != nullptr;
   if (!any_mask) {
     // wave schedule (frontend.cu): L + 1 launches for the whole front end
     for (int wv = 0; wv <= p.n_levels; ++wv) {
       fl_fe_wave w; w.n_jobs = 0; w.n_ctas = 0; w.smem = 0;
+      w.zero_me = (wv == 0 && zero_in_wave) ? d_count : nullptr;                // the candidate counter is reset by the first wave
       const int l = wv;                                       // level whose quantised images this wave produces
       if (l < p.n_levels) {
         const fl_level_geom& g = h->geom[l];
@@ -431,7 +443,7 @@ static int run_match_stages(fl_handle* h, const uint8_t* d_bgr, const uint16_t* 
     }
   }
   if (h->profile) cudaEventRecord(h->ev[1], s);
-  FL_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), s));
+  if (!zero_in_wave) FL_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), s));
   if (h->n_templates > 0) {
     fl_tdb db = make_tdb(h);
     const int lowest = p.n_levels - 1;
@@ -451,27 +463,29 @@ static int run_match_stages(fl_handle* h, const uint8_t* d_bgr, const uint16_t* 
   return FL_OK;
 }
 
-// sort + unique of candidate lists into (d_out, d_out_count); handles the rare > 2048 path; leaves h_small = {count, n_live, flag}
+// sort + unique of candidate lists into (d_out, d_out_count); handles the rare > 2048 path; leaves
+// h_small = {count, n_live, flag, raw list counts...} and, for the handle's own output block, the first matches in h_first
 static int run_sort_unique(fl_handle* h, const fl_match_t* d_in, int n_lists, int list_cap, const int* d_n_in, fl_match_t* d_out, int out_cap,
                            int* d_out_count, bool fetch_first) {
   cudaStream_t s = h->stream;
   if ((int64_t)n_lists * list_cap > h->key_cap) { fl_set_error("sort capacity %d < %lld", h->key_cap, (long long)n_lists * list_cap); return FL_ERR_CAPACITY; }
-  h->launches += fl_launch_sort_unique(d_in, n_lists, list_cap, d_n_in, h->d_keys, h->key_cap, d_out, out_cap, d_out_count, s);
-  int* d_scratch = reinterpret_cast<int*>(h->d_keys + h->key_cap);
-  FL_CUDA(cudaMemcpyAsync(h->h_small + 1, d_scratch, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
-  FL_CUDA(cudaMemcpyAsync(h->h_small, d_out_count, sizeof(int), cudaMemcpyDeviceToHost, s));
-  FL_CUDA(cudaMemcpyAsync(h->h_small + 3, d_n_in, sizeof(int) * std::min(n_lists, 12), cudaMemcpyDeviceToHost, s));   // raw counts (overflow check)
-  if (fetch_first) FL_CUDA(cudaMemcpyAsync(h->h_first, d_out, sizeof(fl_match_t) * std::min(FETCH_FIRST, out_cap), cudaMemcpyDeviceToHost, s));
+  int* d_hdr = reinterpret_cast<int*>(h->d_outblk);
+  h->launches += fl_launch_sort_unique(d_in, n_lists, list_cap, d_n_in, h->key_cap, d_out, out_cap, d_out_count, d_hdr, s);
+  const bool own = fetch_first && d_out == h->d_out;
+  // one D2H copy: the summary and (own output block) the first matches right behind it
+  FL_CUDA(cudaMemcpyAsync(h->h_outblk, h->d_outblk, own ? 64 + sizeof(fl_match_t) * (size_t)std::min(FETCH_FIRST, out_cap) : 64, cudaMemcpyDeviceToHost, s));
   if (h->profile) cudaEventRecord(h->ev[4], s);
   FL_CUDA(cudaStreamSynchronize(s));
   h->overflow = false;
-  for (int i = 0; i < std::min(n_lists, 12); ++i) if (h->h_small[3 + i] > list_cap) h->overflow = true;
-  if (h->h_small[2]) {                                                          // more than 2048 live candidates: multi-kernel sort
-    int rc = fl_launch_sort_unique_big(h->d_keys, h->key_cap, std::min(h->h_small[1], h->key_cap), d_out, out_cap, d_out_count, s);
+  int n_upper = 0;
+  for (int i = 0; i < std::min(n_lists, 12); ++i) { if (h->h_small[3 + i] > list_cap) h->overflow = true; n_upper += std::min(std::max(h->h_small[3 + i], 0), list_cap); }
+  if (n_lists > 12) n_upper = n_lists * list_cap;
+  if (h->h_small[2]) {                                                          // more than 2048 records: multi-kernel sort
+    int rc = fl_launch_sort_unique_big(d_in, n_lists, list_cap, d_n_in, h->d_keys, h->key_cap, n_upper, d_out, out_cap, d_out_count, s);
     if (rc < 0) return FL_ERR_CAPACITY;
     h->launches += rc;
     FL_CUDA(cudaMemcpyAsync(h->h_small, d_out_count, sizeof(int), cudaMemcpyDeviceToHost, s));
-    if (fetch_first) FL_CUDA(cudaMemcpyAsync(h->h_first, d_out, sizeof(fl_match_t) * std::min(FETCH_FIRST, out_cap), cudaMemcpyDeviceToHost, s));
+    if (own) FL_CUDA(cudaMemcpyAsync(h->h_first, d_out, sizeof(fl_match_t) * (size_t)std::min(FETCH_FIRST, out_cap), cudaMemcpyDeviceToHost, s));
     if (h->profile) cudaEventRecord(h->ev[4], s);
     FL_CUDA(cudaStreamSynchronize(s));
   }
@@ -601,6 +615,13 @@ extern "C" int fl_debug_get(fl_handle* h, int what, int32_t a, int32_t b, int32_
     FL_CUDA(cudaStreamSynchronize(h->stream));
     FL_CUDA(cudaMemcpy(host_out, d_tmp, (size_t)g.cells * 2, cudaMemcpyDeviceToHost));
     return FL_OK;
+  }
+  if (what == FL_DBG_STAGED_TRACE) {
+    if (!h->use_staged || !h->plan.trace) return FL_ERR_STATE;
+    size_t n = ((size_t)h->plan.n_cta * 72 + 8) * sizeof(unsigned long long);
+    if (bytes < n) return FL_ERR_CAPACITY;
+    FL_CUDA(cudaMemcpy(host_out, h->plan.trace, n, cudaMemcpyDeviceToHost));
+    return h->plan.n_cta;
   }
   return FL_ERR_ARG;
 }

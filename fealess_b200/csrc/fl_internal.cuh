@@ -52,13 +52,15 @@ struct fl_fe_job {
   fl_level_geom g;
 };
 #define FL_FE_MAX_JOBS 10
-struct fl_fe_wave { int n_jobs, n_ctas; size_t smem; fl_fe_job job[FL_FE_MAX_JOBS]; };
+struct fl_fe_wave { int n_jobs, n_ctas; size_t smem; int* zero_me; fl_fe_job job[FL_FE_MAX_JOBS]; };   // zero_me: int reset by CTA 0 (candidate counter), or NULL
 void fl_fe_add_color(fl_fe_wave* w, const uint8_t* bgr, int W, int H, float thr_sq, uint8_t* q);
 void fl_fe_add_depth(fl_fe_wave* w, const uint16_t* depth, int W, int H, int dist_thr, int diff_thr, uint8_t* q);
 void fl_fe_add_pyrdown(fl_fe_wave* w, const uint8_t* src, int W, int H, uint8_t* dst);
 void fl_fe_add_resize(fl_fe_wave* w, const uint8_t* src, int W, int H, uint8_t* dst);
 void fl_fe_add_spread(fl_fe_wave* w, const uint8_t* q, fl_level_geom g, uint8_t* lm_mod, uint8_t* spread_or_null);
 void fl_launch_fe_wave(const fl_fe_wave& w, cudaStream_t s);
+void fl_prefer_smem_carveout_frontend();
+void fl_prefer_smem_carveout_similarity();
 
 // ---- similarity / refinement / sort (similarity.cu) ---------------------------------------------
 struct fl_tdb {                     // device template database
@@ -77,7 +79,11 @@ struct fl_staged_plan {
   int halo_bytes, buf_bytes, n_buf;        // bytes staged past the last row; size and number of the smem ring buffers
   int n_words, nw_template, tpw;           // 32-bit words per similarity map; template parameters of the instantiation used
   int tpc, n_cta, block_threads;           // templates per CTA, grid, block
-  uint32_t* gfeat;                         // [n_templates][64] feature words sorted by phase: phase << 24 | byte offset in the phase buffer
+  int cluster, smem_bytes, pre_stride;     // CTAs per cluster (TMA multicast group); dynamic shared memory; bytes per gpre row
+  uint32_t* gfeat;                         // [n_templates][64] feature words sorted by phase: word offset in the phase buffer << 5 | 8 * byte misalignment
+  uint8_t* gpre;                           // [n_templates][pre_stride] prefix counts per phase
+  int4* gmeta;                             // [n_templates] {template_positions, n_features, class, 0}
+  unsigned long long* trace;               // developer timeline (FL_TRACE=1): 8 words per CTA, or NULL
 };
 bool fl_plan_staged(const fl_level_geom& g, int M, int n_templates, int max_positions, int n_sm, fl_staged_plan* plan);
 void fl_launch_pack_staged(fl_tdb db, fl_level_geom g, fl_staged_plan plan, cudaStream_t s);
@@ -89,10 +95,13 @@ void fl_launch_similarity_global(fl_tdb db, fl_level_geom g, const uint8_t* lm_l
 void fl_launch_similarity_debug(fl_tdb db, fl_level_geom g, const uint8_t* lm_level, int t, uint16_t* out, cudaStream_t s);
 void fl_launch_refine_level(fl_tdb db, fl_level_geom g, int level, const uint8_t* lm_level, float threshold,
                             fl_match_t* cand, int cap, const int* d_count, cudaStream_t s);
-// sort + unique: n_lists lists of list_cap records at d_in (counts in d_n_in); result in d_out/d_out_count.
-// Returns the number of kernels launched.  key workspace must hold next_pow2(total capacity) keys.
-int fl_launch_sort_unique(const fl_match_t* d_in, int n_lists, int list_cap, const int* d_n_in, fl_sort_key* keys,
-                          int key_cap, fl_match_t* d_out, int out_cap, int* d_out_count, cudaStream_t s);
+// sort + unique: n_lists lists of list_cap records at d_in (counts in d_n_in); result in d_out/d_out_count, summary in
+// d_hdr[16] = {unique count, live records, flag_big, raw counts...}.  One launch; when flag_big comes back set the host
+// runs fl_launch_sort_unique_big (key workspace: next_pow2(n_upper) keys + 1 int).  Both return the number of launches.
+int fl_launch_sort_unique(const fl_match_t* d_in, int n_lists, int list_cap, const int* d_n_in, int key_cap,
+                          fl_match_t* d_out, int out_cap, int* d_out_count, int* d_hdr, cudaStream_t s);
+int fl_launch_sort_unique_big(const fl_match_t* d_in, int n_lists, int list_cap, const int* d_n_in, fl_sort_key* keys, int key_cap,
+                              int n_upper, fl_match_t* d_out, int out_cap, int* d_out_count, cudaStream_t s);
 
 // ---- ICP (icp.cu) --------------------------------------------------------------------------------
 struct fl_icp_hyp {                 // one hypothesis of a batch, device-visible

@@ -455,6 +455,7 @@ void fl_launch_spread_lm(const uint8_t* q, fl_level_geom g, uint8_t* lm_mod, uin
 __global__ void __launch_bounds__(256) k_front_end_wave(fl_fe_wave w) {
   extern __shared__ __align__(16) uint8_t smem_dyn[];
   const int b = blockIdx.x;
+  if (w.zero_me && b == 0 && threadIdx.x == 0) *w.zero_me = 0;
   int j = 0;
 #pragma unroll 1
   while (j + 1 < w.n_jobs && b >= w.job[j + 1].cta_begin) ++j;
@@ -500,4 +501,13 @@ void fl_fe_add_spread(fl_fe_wave* w, const uint8_t* q, fl_level_geom g, uint8_t*
 }
 void fl_launch_fe_wave(const fl_fe_wave& w, cudaStream_t s) {
   if (w.n_ctas > 0) k_front_end_wave<<<w.n_ctas, 256, w.smem, s>>>(w);
+}
+
+// every hot kernel asks for the maximum shared-memory carveout so that the SMs never re-partition L1/shared memory between
+// the launches of one frame (the staged similarity kernel needs > 200 KB)
+void fl_prefer_smem_carveout_frontend() {
+  cudaFuncSetAttribute(k_front_end_wave, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaFuncSetAttribute(k_spread_lm, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaFuncSetAttribute(k_color_quantize, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaFuncSetAttribute(k_depth_quantize, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
 }

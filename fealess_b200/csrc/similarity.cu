@@ -268,51 +268,68 @@ __global__ void __launch_bounds__(256) k_build_keys(const fl_match_t* __restrict
 }
 
 #define SORT_SMEM_N 2048
-// whole sort + unique in one CTA for n_live <= SORT_SMEM_N; otherwise sets *d_flag_big = 1 and leaves the work to the
-// multi-kernel path.
-__global__ void __launch_bounds__(1024) k_sort_unique_small(fl_sort_key* __restrict__ keys, const int* __restrict__ d_n_live,
-                                                            int key_cap, fl_match_t* __restrict__ out, int out_cap,
-                                                            int* __restrict__ d_out_count, int* __restrict__ d_flag_big) {
+// Common case, ONE launch of one CTA: gather the live candidates of all lists, sort, prune duplicates.  When the lists hold
+// more than SORT_SMEM_N records it only sets *d_flag_big = 1 and the host runs the multi-kernel path (k_build_keys + global
+// bitonic steps + k_unique_big).  d_scratch = {n_live, flag_big}.
+__global__ void __launch_bounds__(1024) k_sort_unique_small(const fl_match_t* __restrict__ in, int n_lists, int list_cap,
+                                                            const int* __restrict__ n_in, int key_cap, fl_match_t* __restrict__ out,
+                                                            int out_cap, int* __restrict__ d_out_count, int* __restrict__ d_hdr) {
+  // d_hdr (16 ints, handle-owned) = {unique count, n_live, flag_big, raw n_in[0..11]}: one small D2H copy tells the host everything
   __shared__ fl_sort_key s_k[SORT_SMEM_N];
-  __shared__ int s_scan[1024 + 1];
-  const int n = min(*d_n_live, key_cap);
-  if (n > SORT_SMEM_N) { if (threadIdx.x == 0) *d_flag_big = 1; return; }
-  if (threadIdx.x == 0) *d_flag_big = 0;
-  int n_pad = 1;
-  while (n_pad < n) n_pad <<= 1;
-  n_pad = max(n_pad, 2);
-  for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
-    fl_sort_key k; k.hi = KEY_SENTINEL_HI; k.lo = KEY_SENTINEL_HI;
-    if (i < n) k = keys[i];
-    s_k[i] = k;
+  __shared__ int s_warp[32];
+  __shared__ int s_n;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int total = 0;
+  for (int l = 0; l < n_lists; ++l) total += min(max(n_in[l], 0), list_cap);
+  if (tid < 12) d_hdr[3 + tid] = tid < n_lists ? n_in[tid] : 0;
+  if (total > SORT_SMEM_N || total > key_cap) { if (tid == 0) { d_hdr[0] = 0; d_hdr[1] = total; d_hdr[2] = 1; } return; }
+  if (tid == 0) s_n = 0;
+  __syncthreads();
+  for (int i = tid; i < total; i += blockDim.x) {
+    int l = 0, k = i;
+    for (;;) { const int c = min(max(n_in[l], 0), list_cap); if (k < c) break; k -= c; ++l; }
+    const fl_match_t m = in[(size_t)l * list_cap + k];
+    if (m.template_id >= 0) s_k[atomicAdd(&s_n, 1)] = make_key(m);          // dropped candidates carry template_id -1
   }
+  __syncthreads();
+  const int n = s_n;
+  int n_pad = 2;
+  while (n_pad < n) n_pad <<= 1;
+  for (int i = n + tid; i < n_pad; i += blockDim.x) { s_k[i].hi = KEY_SENTINEL_HI; s_k[i].lo = KEY_SENTINEL_HI; }
   __syncthreads();
   for (int k = 2; k <= n_pad; k <<= 1)
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
-        int p = i ^ j;
+      for (int i = tid; i < n_pad; i += blockDim.x) {
+        const int p = i ^ j;
         if (p > i) {
-          bool up = (i & k) == 0;
-          fl_sort_key a = s_k[i], b = s_k[p];
+          const bool up = (i & k) == 0;
+          const fl_sort_key a = s_k[i], b = s_k[p];
           if (key_less(b, a) == up) { s_k[i] = b; s_k[p] = a; }
         }
       }
       __syncthreads();
     }
-  // adjacent unique + ordered compaction: each thread owns a contiguous pair of slots
+  // adjacent unique + ordered compaction: each thread owns a contiguous run of slots; block-wide exclusive scan of the kept counts
   const int per = (n_pad + blockDim.x - 1) / blockDim.x;
-  const int b0 = threadIdx.x * per;
+  const int b0 = tid * per;
   int cnt = 0;
   for (int i = b0; i < min(b0 + per, n); ++i) cnt += (i == 0 || !key_dup(s_k[i - 1], s_k[i])) ? 1 : 0;
-  s_scan[threadIdx.x + 1] = cnt;
-  if (threadIdx.x == 0) s_scan[0] = 0;
+  int inc = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+  if (lane == 31) s_warp[warp] = inc;
   __syncthreads();
-  if (threadIdx.x == 0) for (int i = 1; i <= (int)blockDim.x; ++i) s_scan[i] += s_scan[i - 1];   // 1024 adds; negligible
+  if (warp == 0) {
+    int w = s_warp[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+    s_warp[lane] = w;
+  }
   __syncthreads();
-  int pos = s_scan[threadIdx.x];
+  int pos = (warp > 0 ? s_warp[warp - 1] : 0) + inc - cnt;
   for (int i = b0; i < min(b0 + per, n); ++i)
     if (i == 0 || !key_dup(s_k[i - 1], s_k[i])) { if (pos < out_cap) out[pos] = key_to_match(s_k[i]); ++pos; }
-  if (threadIdx.x == 0) *d_out_count = s_scan[blockDim.x];
+  if (tid == 0) { *d_out_count = s_warp[31]; d_hdr[0] = s_warp[31]; d_hdr[1] = n; d_hdr[2] = 0; }
 }
 
 // large path: global bitonic steps + serial-chunk unique
@@ -333,50 +350,65 @@ __global__ void __launch_bounds__(256) k_bitonic_step(fl_sort_key* keys, int n_p
 }
 __global__ void __launch_bounds__(1024) k_unique_big(const fl_sort_key* __restrict__ keys, const int* __restrict__ d_n_live, int key_cap,
                                                      fl_match_t* __restrict__ out, int out_cap, int* __restrict__ d_out_count) {
-  __shared__ int s_scan[1024 + 1];
+  __shared__ int s_warp[32];
   __shared__ int s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = min(*d_n_live, key_cap);
-  if (threadIdx.x == 0) s_base = 0;
+  if (tid == 0) s_base = 0;
   __syncthreads();
   for (int c0 = 0; c0 < n; c0 += 1024) {
-    int i = c0 + threadIdx.x;
-    int keep = (i < n && (i == 0 || !key_dup(keys[i - 1], keys[i]))) ? 1 : 0;
-    s_scan[threadIdx.x + 1] = keep;
-    if (threadIdx.x == 0) s_scan[0] = 0;
+    const int i = c0 + tid;
+    const int keep = (i < n && (i == 0 || !key_dup(keys[i - 1], keys[i]))) ? 1 : 0;
+    int inc = keep;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) s_warp[warp] = inc;
     __syncthreads();
-    if (threadIdx.x == 0) for (int t = 1; t <= 1024; ++t) s_scan[t] += s_scan[t - 1];
+    if (warp == 0) {
+      int w = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+      s_warp[lane] = w;
+    }
     __syncthreads();
-    int pos = s_base + s_scan[threadIdx.x];
+    const int pos = s_base + (warp > 0 ? s_warp[warp - 1] : 0) + inc - keep;
     if (keep && pos < out_cap) out[pos] = key_to_match(keys[i]);
     __syncthreads();
-    if (threadIdx.x == 0) s_base += s_scan[1024];
+    if (tid == 0) s_base += s_warp[31];
     __syncthreads();
   }
-  if (threadIdx.x == 0) *d_out_count = s_base;
+  if (tid == 0) *d_out_count = s_base;
 }
 
-// Host orchestration.  The scratch ints live right after the key array: [n_live, flag_big].
-int fl_launch_sort_unique(const fl_match_t* d_in, int n_lists, int list_cap, const int* d_n_in, fl_sort_key* keys, int key_cap,
-                          fl_match_t* d_out, int out_cap, int* d_out_count, cudaStream_t s) {
-  int launches = 0;
-  int* d_scratch = reinterpret_cast<int*>(keys + key_cap);
-  cudaMemsetAsync(d_scratch, 0, 2 * sizeof(int), s);
-  int total = n_lists * list_cap;
-  if (total > 0) { k_build_keys<<<(total + 255) / 256, 256, 0, s>>>(d_in, n_lists, list_cap, d_n_in, keys, key_cap, d_scratch); ++launches; }
-  k_sort_unique_small<<<1, 1024, 0, s>>>(keys, d_scratch, key_cap, d_out, out_cap, d_out_count, d_scratch + 1); ++launches;
-  return launches;
+// Host orchestration.  Scratch int (n_live of the big path) lives right after the key array.
+int fl_launch_sort_unique(const fl_match_t* d_in, int n_lists, int list_cap, const int* d_n_in, int key_cap,
+                          fl_match_t* d_out, int out_cap, int* d_out_count, int* d_hdr, cudaStream_t s) {
+  k_sort_unique_small<<<1, 1024, 0, s>>>(d_in, n_lists, list_cap, d_n_in, key_cap, d_out, out_cap, d_out_count, d_hdr);
+  return 1;
 }
 
-// second stage, only when the small kernel reported n_live > SORT_SMEM_N (host has read the two scratch ints)
-int fl_launch_sort_unique_big(fl_sort_key* keys, int key_cap, int n_live, fl_match_t* d_out, int out_cap, int* d_out_count, cudaStream_t s) {
+// second stage, only when the small kernel reported more than SORT_SMEM_N records (the host has read the flag and the
+// record count n_upper)
+int fl_launch_sort_unique_big(const fl_match_t* d_in, int n_lists, int list_cap, const int* d_n_in, fl_sort_key* keys, int key_cap,
+                              int n_upper, fl_match_t* d_out, int out_cap, int* d_out_count, cudaStream_t s) {
   int launches = 0;
   int* d_scratch = reinterpret_cast<int*>(keys + key_cap);
+  cudaMemsetAsync(d_scratch, 0, sizeof(int), s);
+  const int total = n_lists * list_cap;
+  k_build_keys<<<(total + 255) / 256, 256, 0, s>>>(d_in, n_lists, list_cap, d_n_in, keys, key_cap, d_scratch); ++launches;
   int n_pad = 2;
-  while (n_pad < n_live) n_pad <<= 1;
+  while (n_pad < n_upper) n_pad <<= 1;
   if (n_pad > key_cap) return -1;
   k_pad_keys<<<(n_pad + 255) / 256, 256, 0, s>>>(keys, d_scratch, key_cap, n_pad); ++launches;
   for (int k = 2; k <= n_pad; k <<= 1)
     for (int j = k >> 1; j > 0; j >>= 1) { k_bitonic_step<<<(n_pad + 255) / 256, 256, 0, s>>>(keys, n_pad, k, j); ++launches; }
   k_unique_big<<<1, 1024, 0, s>>>(keys, d_scratch, key_cap, d_out, out_cap, d_out_count); ++launches;
   return launches;
+}
+
+void fl_prefer_smem_carveout_similarity() {
+  cudaFuncSetAttribute(k_refine_level, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaFuncSetAttribute(k_sort_unique_small, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaFuncSetAttribute(k_build_keys, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaFuncSetAttribute(k_similarity_global<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
 }

@@ -1,18 +1,21 @@
 // K6, staged variant: global similarity of all templates at the coarsest pyramid level with the linear memories staged
-// through shared memory by TMA bulk copies (cp.async.bulk + mbarrier), accumulators in registers.
+// through shared memory by TMA bulk copies (cp.async.bulk + mbarrier, multicast across a thread-block cluster),
+// accumulators in registers.
 //
 // Why: one template reads 62 byte streams of ~1,200 B from 62 of the 1,024 linear-memory rows (2 modalities x 8 labels x
 // T*T rows); over 8,000 templates that is ~0.6 GB of byte traffic per frame against a 1.2 MB working set, so the bound is
-// on-chip bandwidth, not HBM.  The working set does not fit one SM's shared memory, so the kernel walks it in PHASES
-// (one phase = the T*T rows of one (modality, label), or a block of them), double buffered:
+// on-chip bandwidth (shared memory, 128 B/clk/SM), not HBM.  The working set does not fit one SM's shared memory, so the
+// kernel walks it in PHASES (one phase = a block of the T*T rows of one (modality, label)) through a ring of buffers:
 //
 //   * a persistent CTA owns a batch of templates (one warp per template slot, TPW slots per warp) and keeps their
 //     packed-u8 similarity accumulators in registers for the whole kernel;
-//   * one elected thread streams phase p+2 into the free buffer with a single cp.async.bulk while all warps consume
-//     phase p; completion is signalled on an mbarrier (expect_tx);
-//   * features were sorted by phase once per frame geometry (k_pack_staged; the phase id rides in the top byte of the
-//     feature word), and a warp keeps its templates' feature words in registers (lane k holds feature k), broadcasting
-//     the next one with a shuffle, so the inner loop touches global memory only through the bulk copies;
+//   * one elected thread per CTA streams phase q + n_buf into the buffer that was just released; with a cluster of CL
+//     CTAs every CTA fetches 1/CL of the phase and multicasts it into the shared memory of all CL CTAs, so the L2 -> SM
+//     traffic of the kernel is (working set) x (number of CTAs) / CL.  Completion is counted in bytes on an mbarrier
+//     (expect_tx); a buffer is released when every consumer warp of every CTA of the cluster has arrived on "empty";
+//   * features were sorted by phase once per frame geometry (k_pack_staged).  A CTA copies its templates' feature words
+//     and per-phase prefix counts into shared memory, so the inner loop is: one broadcast LDS for the next feature word,
+//     NW + 1 LDS of linear-memory words, NW funnel shifts, NW adds;
 //   * lane g owns the NW consecutive 32-bit words [g NW, (g+1) NW) of the similarity map (NW odd, so the 32 lanes of one
 //     LDS fall into 32 different banks at any feature offset); a byte-misaligned window costs NW + 1 loads, not 2 NW: the
 //     high word of one funnel shift is the low word of the next.
@@ -22,10 +25,10 @@
 // template has <= 63 coarsest-level features over all modalities (so one u8 lane holds the total, 63*4 = 252) and the same
 // width/height for all modalities at that level (what cropTemplates :52-96 produces); otherwise the baseline kernel runs.
 #include "fl_internal.cuh"
+#include <stdlib.h>
 
 #define SS_MAXF 64                      // feature words per template (<= 63 used)
-#define SS_MAX_PHASES 254               // the phase id travels in the top byte of a feature word
-#define SS_NOFEAT 0xFFFFFFFFu           // padding word: phase 255 never comes up
+#define SS_MAX_PHASES 254
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -46,15 +49,54 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "WAIT_DONE:\n"
       "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// wait with cluster-scope acquire: the arrivals may come from the other CTAs of the cluster
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAITC_LOOP:\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAITC_DONE;\n"
+      "bra WAITC_LOOP;\n"
+      "WAITC_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(cta) : "memory");
+}
 // 1-D TMA: bulk copy global -> shared, completion counted in bytes on the mbarrier
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
                "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// the same copy delivered to the same offsets (data and barrier) of every CTA in cta_mask
+__device__ __forceinline__ void bulk_g2s_multicast(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
 // ------------------------------------------------------------------------------------------------
-// per-geometry packing for the staged kernel: for every template, the coarsest-level features of all modalities sorted
-// by phase, as byte offsets inside the phase buffer, plus the per-phase prefix offsets.
+// per-geometry packing for the staged kernel, one thread per template:
+//   gfeat[t][0..63]  coarsest-level features of all modalities sorted by phase; word = (byte offset of the 32-bit word
+//                    holding the feature's first response inside the phase buffer) << 5 | (8 x misalignment in bytes)
+//   gpre[t][0..P]    prefix counts: the features of phase p are gfeat[t][gpre[t][p] .. gpre[t][p+1])
+//   gmeta[t]         {template_positions (linemod.cpp:1155), number of features, class index, 0}
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_pack_staged(fl_tdb db, fl_level_geom g, fl_staged_plan plan) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -62,10 +104,13 @@ __global__ void __launch_bounds__(128) k_pack_staged(fl_tdb db, fl_level_geom g,
   const int level = db.L - 1;
   const fl_template_hdr_t* hdr = db.hdr + ((size_t)t * db.L + level) * db.M;
   uint32_t* out = plan.gfeat + (size_t)t * SS_MAXF;
+  uint8_t* pre = plan.gpre + (size_t)t * plan.pre_stride;
   // counting sort by phase (n <= 63): pass 1 counts, pass 2 places
-  uint8_t cur[SS_MAX_PHASES + 1];
+  uint8_t cur[SS_MAX_PHASES + 2];
   for (int p = 0; p <= plan.n_phases; ++p) cur[p] = 0;
-  for (int m = 0; m < db.M; ++m)
+  int nf = 0;
+  for (int m = 0; m < db.M; ++m) {
+    nf += hdr[m].feature_count;
     for (int k = 0; k < hdr[m].feature_count; ++k) {
       const fl_feature_t f = db.feat[hdr[m].feature_begin + k];
       if (f.x < 0 || f.y < 0 || f.x >= g.W || f.y >= g.H) continue;                     // linemod.cpp:1179
@@ -73,7 +118,9 @@ __global__ void __launch_bounds__(128) k_pack_staged(fl_tdb db, fl_level_geom g,
       const int ph = (m * 8 + f.label) * plan.n_rowblocks + row / plan.phase_rows;
       ++cur[ph + 1];
     }
+  }
   for (int p = 0; p < plan.n_phases; ++p) cur[p + 1] = (uint8_t)(cur[p + 1] + cur[p]);   // cur[p] = first slot of phase p
+  for (int p = 0; p <= plan.n_phases; ++p) pre[p] = cur[p];
   const int total = cur[plan.n_phases];
   for (int m = 0; m < db.M; ++m)
     for (int k = 0; k < hdr[m].feature_count; ++k) {
@@ -82,10 +129,13 @@ __global__ void __launch_bounds__(128) k_pack_staged(fl_tdb db, fl_level_geom g,
       const int row = (f.y % g.T) * g.T + (f.x % g.T);
       const int rb = row / plan.phase_rows;
       const int ph = (m * 8 + f.label) * plan.n_rowblocks + rb;
-      // feature word: phase in the top byte, byte offset of the feature's first response inside the phase buffer below
-      out[cur[ph]++] = ((uint32_t)ph << 24) | (uint32_t)((row - rb * plan.phase_rows) * g.cells + (f.y / g.T) * g.Wd + f.x / g.T);
+      const uint32_t a = (uint32_t)((row - rb * plan.phase_rows) * g.cells + (f.y / g.T) * g.Wd + f.x / g.T);
+      out[cur[ph]++] = ((a & ~3u) << 5) | ((a & 3u) << 3);
     }
-  for (int k = total; k < SS_MAXF; ++k) out[k] = SS_NOFEAT;
+  for (int k = total; k < SS_MAXF; ++k) out[k] = 0;
+  const int wf = (hdr[0].width - 1) / g.T + 1, hf = (hdr[0].height - 1) / g.T + 1;
+  const int tp = min((g.Hd - hf) * g.Wd + (g.Wd - wf) + 1, g.cells);                    // template_positions :1155
+  plan.gmeta[t] = make_int4(tp, nf, db.class_of[t], 0);
 }
 
 void fl_launch_pack_staged(fl_tdb db, fl_level_geom g, fl_staged_plan plan, cudaStream_t s) {
@@ -95,17 +145,12 @@ void fl_launch_pack_staged(fl_tdb db, fl_level_geom g, fl_staged_plan plan, cuda
 // ------------------------------------------------------------------------------------------------
 #define SS_NBUF_MAX 4
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
 // One feature of one template: lane g owns the NW consecutive 32-bit words [g*NW, (g+1)*NW) of the similarity map, so
 // its window is the NW + 1 consecutive words starting at its base + the feature's word offset: NW + 1 loads (instead of
 // two per word), one funnel shift and one add per word.  NW is odd, so the 32 lanes of one load hit 32 different banks.
 template <int NW>
-__device__ __forceinline__ void accumulate_feature(const uint8_t* __restrict__ lane_base, uint32_t a, uint32_t (&acc)[NW]) {
-  const uint32_t* w = reinterpret_cast<const uint32_t*>(lane_base + (a & 0x00FFFFFCu));
-  const uint32_t sh = a << 3;                                 // funnel shift uses the low 5 bits: (a & 3) * 8
+__device__ __forceinline__ void accumulate_feature(const uint8_t* __restrict__ lane_base, uint32_t fw, uint32_t (&acc)[NW]) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(lane_base + (fw >> 5));
   constexpr int CH = 12;                                      // loads in flight per chunk (register budget)
   uint32_t carry = w[0];
 #pragma unroll
@@ -115,155 +160,253 @@ __device__ __forceinline__ void accumulate_feature(const uint8_t* __restrict__ l
 #pragma unroll
     for (int i = 0; i < CH; ++i) if (c + i < NW) v[i + 1] = w[c + i + 1];
 #pragma unroll
-    for (int i = 0; i < CH; ++i) if (c + i < NW) acc[c + i] += __funnelshift_r(v[i], v[i + 1], sh);   // four u8 lanes, no carry (sums <= 252)
+    for (int i = 0; i < CH; ++i) if (c + i < NW) acc[c + i] += __funnelshift_r(v[i], v[i + 1], fw);   // shift = low 5 bits; four u8 lanes, no carry (sums <= 252)
     carry = v[(NW - c) < CH ? (NW - c) : CH];
   }
 }
 
-template <int NW, int TPW>
+// per-byte mask (0xFF where the cell is a candidate) of accumulator word w of a template: raw > raw_thr and cell < tp
+__device__ __forceinline__ uint32_t candidate_mask(uint32_t v, int w, int tp, int raw_thr, uint32_t thr4) {
+  if (4 * w >= tp) return 0u;
+  uint32_t m = raw_thr < 0 ? 0xFFFFFFFFu : __vcmpgtu4(v, thr4);
+  if (4 * w + 4 > tp) m &= 0xFFFFFFFFu >> (8 * (4 * w + 4 - tp));
+  return m;
+}
+
+template <int NW, int TPW, int CL>
 __global__ void __launch_bounds__(1024, 1) k_similarity_staged(fl_tdb db, fl_level_geom g, const uint8_t* __restrict__ lm_level, float threshold,
                                                                fl_match_t* __restrict__ cand, int cap, int* __restrict__ d_count,
                                                                fl_staged_plan plan) {
-  extern __shared__ __align__(128) uint8_t s_buf[];          // plan.n_buf x plan.buf_bytes
+  extern __shared__ __align__(128) uint8_t s_dyn[];          // [n_buf x buf_bytes][tpc x int4 meta][tpc x 64 feature words + 4][tpc x pre_stride]
   __shared__ __align__(8) uint64_t s_full[SS_NBUF_MAX], s_empty[SS_NBUF_MAX];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_cwarps = (blockDim.x >> 5) - 1;                 // consumer warps; the last warp is the TMA producer
-  const int level = db.L - 1;
   const int t_begin = blockIdx.x * plan.tpc;
   const int t_end = min(t_begin + plan.tpc, db.n_templates);
   const int n_phases = plan.n_phases, n_buf = plan.n_buf;
-  // CTAs walk the phases in rotated order so that, at any moment, different SMs pull different linear-memory rows out of
-  // L2 instead of all 148 hammering the same lines (the sums are order independent)
-  const int rot = (int)((blockIdx.x * 7u) % (unsigned)n_phases);
+  uint8_t* s_buf = s_dyn;
+  int4* s_meta = reinterpret_cast<int4*>(s_dyn + (size_t)n_buf * plan.buf_bytes);
+  uint32_t* s_feat = reinterpret_cast<uint32_t*>(s_meta + plan.tpc);
+  uint8_t* s_pre = reinterpret_cast<uint8_t*>(s_feat + plan.tpc * SS_MAXF + 4);
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+  // clusters walk the phases in rotated order so that, at any moment, different SMs pull different linear-memory rows
+  // out of L2 instead of all hammering the same lines (the sums are order independent)
+  const int rot = (int)(((blockIdx.x / CL) * 7u) % (unsigned)n_phases);
+  unsigned long long* trace = plan.trace ? plan.trace + (size_t)blockIdx.x * 8 : nullptr;
+  if (trace && tid == 0) { trace[0] = globaltimer(); unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); trace[5] = smid; }
 
   if (tid == 0) {
-    for (int b = 0; b < n_buf; ++b) { mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], n_cwarps); }
+    for (int b = 0; b < n_buf; ++b) { mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], n_cwarps * CL); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  if (CL > 1) cluster_sync_all();                             // every CTA's barriers are initialised before any peer touches them
+  if (warp != n_cwarps) {
+    // consumers: this CTA's per-template records, feature words and prefix counts -> shared memory while the producer
+    // already streams the first phases; slots past the end / of disabled classes get no features and no positions
+    for (int i = tid; i < plan.tpc; i += n_cwarps * 32) {
+      const int t = t_begin + i;
+      int4 m = make_int4(0, 0, 0, 0);
+      if (t < t_end) {
+        m = plan.gmeta[t];
+        m.w = db.L == 1 ? db.tid_of[t] : t;                   // the id candidates carry (see k_similarity_global)
+        if (!db.class_enabled[m.z]) m.x = 0;                  // no positions -> no candidates
+        // raw threshold int(2 nf + (threshold / 100) 2 nf + 0.5f) in fp32 (:1487); stored biased by 1, clamped to [-1, 255]
+        const int nf = m.y;
+        const int rt = (int)__fadd_rn(__fadd_rn((float)(2 * nf), __fmul_rn(__fdiv_rn(threshold, 100.f), (float)(2 * nf))), 0.5f);
+        m.y = nf | ((min(max(rt, -1), 255) + 1) << 8);
+      }
+      s_meta[i] = m;
+    }
+    for (int i = tid; i < plan.tpc * SS_MAXF; i += n_cwarps * 32) {
+      const int t = t_begin + i / SS_MAXF;
+      s_feat[i] = t < t_end ? plan.gfeat[(size_t)t * SS_MAXF + (i % SS_MAXF)] : 0u;
+    }
+    if (tid < 4) s_feat[plan.tpc * SS_MAXF + tid] = 0u;
+    for (int i = tid; i < plan.tpc * plan.pre_stride; i += n_cwarps * 32) {
+      const int t = t_begin + i / plan.pre_stride;
+      const bool on = t < t_end && db.class_enabled[db.class_of[t]];
+      s_pre[i] = on ? plan.gpre[(size_t)t * plan.pre_stride + (i % plan.pre_stride)] : (uint8_t)0;
+    }
+    asm volatile("bar.sync 1, %0;" ::"r"(n_cwarps * 32) : "memory");   // consumers only
+  }
+  if (trace && tid == 0) trace[1] = globaltimer();
 
   if (warp == n_cwarps) {
-    // ===== producer: one elected lane streams phase q into buffer q % n_buf as soon as every consumer warp released it =====
+    // ===== producer: one elected lane streams phase q into buffer q % n_buf as soon as every consumer warp of the cluster released it =====
     if (lane == 0) {
       for (int q = 0; q < n_phases; ++q) {
         const int b = q % n_buf;
-        if (q >= n_buf) mbar_wait(&s_empty[b], ((q / n_buf) - 1) & 1);
+        if (q >= n_buf) { if (CL > 1) mbar_wait_cluster(&s_empty[b], ((q / n_buf) - 1) & 1); else mbar_wait(&s_empty[b], ((q / n_buf) - 1) & 1); }
         int p = q + rot; if (p >= n_phases) p -= n_phases;
         const int ml = p / plan.n_rowblocks, rb = p - ml * plan.n_rowblocks;
         const int m = ml >> 3, lab = ml & 7;
         const uint8_t* src = lm_level + (size_t)m * g.mod_stride + (size_t)lab * g.label_stride + (size_t)rb * plan.phase_rows * g.cells;
         const int rows = min(plan.phase_rows, g.T * g.T - rb * plan.phase_rows);
         const uint32_t bytes = (uint32_t)(((size_t)rows * g.cells + plan.halo_bytes + 15) & ~(size_t)15);
-        mbar_expect_tx(&s_full[b], bytes);
-        bulk_g2s(s_buf + (size_t)b * plan.buf_bytes, src, bytes, &s_full[b]);
+        mbar_expect_tx(&s_full[b], bytes);                    // the whole phase lands here, whoever fetches it
+        if (CL == 1) {
+          bulk_g2s(s_buf + (size_t)b * plan.buf_bytes, src, bytes, &s_full[b]);
+        } else {
+          const uint32_t chunk = ((bytes / CL) + 15) & ~15u;
+          const uint32_t o = crank * chunk;
+          if (o < bytes) bulk_g2s_multicast(s_buf + (size_t)b * plan.buf_bytes + o, src + o, min(chunk, bytes - o), &s_full[b], (uint16_t)((1u << CL) - 1));
+        }
       }
+      if (trace) trace[7] = globaltimer();
     }
-    return;
-  }
-
-  // ===== consumers: this warp's templates.  Feature words (phase-sorted, phase id in the top byte) live in registers,
-  // one per lane (fa: features 0-31, fb: 32-63); kcur walks them in this CTA's rotated phase order =====
-  int tt[TPW], kcur[TPW], nfeat[TPW], nleft[TPW];
-  uint32_t fa[TPW], fb[TPW], fnext[TPW];
-  uint32_t acc[TPW][NW];
-#pragma unroll
-  for (int s = 0; s < TPW; ++s) {
-    const int t = t_begin + warp + s * n_cwarps;
-    tt[s] = (t < t_end && db.class_enabled[db.class_of[t]]) ? t : -1;
-    fa[s] = fb[s] = fnext[s] = SS_NOFEAT;
-    kcur[s] = nfeat[s] = nleft[s] = 0;
-    if (tt[s] >= 0) {
-      fa[s] = plan.gfeat[(size_t)t * SS_MAXF + lane];
-      fb[s] = plan.gfeat[(size_t)t * SS_MAXF + 32 + lane];
-      nfeat[s] = __popc(__ballot_sync(0xffffffffu, fa[s] != SS_NOFEAT)) + __popc(__ballot_sync(0xffffffffu, fb[s] != SS_NOFEAT));
-      // first feature at or after phase `rot` (padding words carry phase 255 and never count)
-      kcur[s] = __popc(__ballot_sync(0xffffffffu, (int)(fa[s] >> 24) < rot)) + __popc(__ballot_sync(0xffffffffu, (int)(fb[s] >> 24) < rot));
-      if (kcur[s] >= nfeat[s]) kcur[s] = 0;
-      nleft[s] = nfeat[s];
-      if (nleft[s] > 0) fnext[s] = __shfl_sync(0xffffffffu, kcur[s] < 32 ? fa[s] : fb[s], kcur[s] & 31);
-    }
-#pragma unroll
-    for (int i = 0; i < NW; ++i) acc[s][i] = 0;
-  }
-
-  int b = 0, p = rot;
-  uint32_t par = 0;
-  const uint8_t* lane_base0 = s_buf + lane * (NW * 4);
-  for (int q = 0; q < n_phases; ++q) {
-    mbar_wait(&s_full[b], par);
-    const uint8_t* lane_base = lane_base0 + b * plan.buf_bytes;
+  } else {
+    // ===== consumers =====
+    bool live[TPW];
+    const uint8_t* pre[TPW];
+    const uint32_t* fl[TPW];
+    uint32_t acc[TPW][NW];
 #pragma unroll
     for (int s = 0; s < TPW; ++s) {
-      while ((int)(fnext[s] >> 24) == p) {                    // warp-uniform
-        accumulate_feature<NW>(lane_base, fnext[s], acc[s]);
-        if (++kcur[s] == nfeat[s]) kcur[s] = 0;
-        fnext[s] = --nleft[s] > 0 ? __shfl_sync(0xffffffffu, kcur[s] < 32 ? fa[s] : fb[s], kcur[s] & 31) : SS_NOFEAT;
-      }
+      const int slot = warp + s * n_cwarps;
+      const int t = t_begin + slot;
+      const bool in = slot < plan.tpc && t < t_end;
+      live[s] = in;
+      pre[s] = s_pre + (in ? slot : 0) * plan.pre_stride;
+      fl[s] = s_feat + (in ? slot : 0) * SS_MAXF;
+      if (!in) pre[s] = nullptr;
+#pragma unroll
+      for (int i = 0; i < NW; ++i) acc[s][i] = 0;
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&s_empty[b]);                  // this warp is done with buffer b
-    if (++b == n_buf) { b = 0; par ^= 1; }
-    if (++p == n_phases) p = 0;
-  }
+    int b = 0, p = rot;
+    uint32_t par = 0;
+    const uint8_t* lane_base0 = s_buf + lane * (NW * 4);
+    for (int q = 0; q < n_phases; ++q) {
+      mbar_wait(&s_full[b], par);
+      if (trace && tid == 0 && q == 0) trace[2] = globaltimer();
+      const uint8_t* lane_base = lane_base0 + b * plan.buf_bytes;
+#pragma unroll
+      for (int s = 0; s < TPW; ++s) {
+        if (!pre[s]) continue;
+        int k = pre[s][p];
+        const int k1 = pre[s][p + 1];
+        if (k < k1) {                                         // warp-uniform
+          const uint32_t* fp = fl[s] + k;
+          const uint32_t* fe = fl[s] + k1;
+          uint32_t fw = *fp;
+          do {
+            const uint32_t nx = fp[1];                        // next feature word (one past the list is a valid pad word)
+            accumulate_feature<NW>(lane_base, fw, acc[s]);
+            fw = nx; ++fp;
+          } while (fp < fe);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {                                        // this warp is done with buffer b, in every CTA that writes into it
+        if (CL == 1) mbar_arrive(&s_empty[b]);
+        else {
+#pragma unroll
+          for (uint32_t c = 0; c < (uint32_t)CL; ++c) mbar_arrive_remote(&s_empty[b], c);
+        }
+      }
+      if (++b == n_buf) { b = 0; par ^= 1; }
+      if (++p == n_phases) p = 0;
+    }
+    if (trace && tid == 0) trace[3] = globaltimer();
+    if (trace && lane == 0) plan.trace[(size_t)plan.n_cta * 8 + 8 + ((size_t)blockIdx.x * 32 + warp) * 2] = globaltimer();       // per-warp loop end
 
-  // threshold + candidate emission (matchClass :1487-1506)
-  const int off = g.T / 2 + (g.T % 2 - 1);
+    // threshold + candidate emission (matchClass :1487-1506).  The raw threshold was computed in the prologue.  Slots are
+    // reserved with ONE atomic per template that has candidates (a returning atomic is a ~0.7 us round trip to L2, one
+    // per candidate would serialise), and the records are written ballot-compacted by all lanes in parallel.
+    const int off = g.T / 2 + (g.T % 2 - 1);
 #pragma unroll
-  for (int s = 0; s < TPW; ++s) {
-    const int t = tt[s];
-    if (t < 0) continue;
-    const fl_template_hdr_t* hdr = db.hdr + ((size_t)t * db.L + level) * db.M;
-    int nf = 0;
-    for (int m = 0; m < db.M; ++m) nf += hdr[m].feature_count;
-    const int raw_thr = (int)__fadd_rn(__fadd_rn((float)(2 * nf), __fmul_rn(__fdiv_rn(threshold, 100.f), (float)(2 * nf))), 0.5f);
-    if (raw_thr >= 255) continue;                             // a u8 total cannot exceed it
-    const int wf = (hdr[0].width - 1) / g.T + 1, hf = (hdr[0].height - 1) / g.T + 1;
-    const int tp = min((g.Hd - hf) * g.Wd + (g.Wd - wf) + 1, g.cells);               // template_positions :1155
-    const int cls = db.class_of[t];
-    const uint32_t thr4 = raw_thr < 0 ? 0u : (uint32_t)raw_thr * 0x01010101u;
+    for (int s = 0; s < TPW; ++s) {
+      if (!live[s]) continue;                                 // warp-uniform
+      const int4 meta = s_meta[warp + s * n_cwarps];
+      const int tp = meta.x, nf = meta.y & 0xFF, raw_thr = (meta.y >> 8) - 1;
+      if (tp <= 0 || raw_thr >= 255) continue;                // disabled class / a u8 total cannot exceed the threshold
+      const uint32_t thr4 = raw_thr < 0 ? 0u : (uint32_t)raw_thr * 0x01010101u;
+      int cnt = 0;
 #pragma unroll
-    for (int i = 0; i < NW; ++i) {
-      const int w = lane * NW + i;
-      if (4 * w >= tp) continue;
-      const uint32_t v = acc[s][i];
-      if (raw_thr >= 0 && !__vcmpgtu4(v, thr4)) continue;
+      for (int i = 0; i < NW; ++i) cnt += __popc(candidate_mask(acc[s][i], lane * NW + i, tp, raw_thr, thr4)) >> 3;
+      if (!__any_sync(0xffffffffu, cnt > 0)) continue;
+      const int total = __reduce_add_sync(0xffffffffu, cnt);
+      int base = 0;
+      if (lane == 0) base = atomicAdd(d_count, total);
+      base = __shfl_sync(0xffffffffu, base, 0);
 #pragma unroll
-      for (int bb = 0; bb < 4; ++bb) {
-        const int j = 4 * w + bb;
-        const int raw = (v >> (8 * bb)) & 0xFF;
-        if (j < tp && raw > raw_thr) {
-          const int r = j / g.Wd, c = j - r * g.Wd;
-          const int slot = atomicAdd(d_count, 1);
-          if (slot < cap) {
-            fl_match_t mt;
-            mt.x = c * g.T + off; mt.y = r * g.T + off;
-            mt.similarity = __fadd_rn(__fdiv_rn(__fmul_rn((float)raw, 100.f), (float)(4 * nf)), 0.5f);
-            mt.class_idx = cls; mt.template_id = db.L == 1 ? db.tid_of[t] : t;
-            cand[slot] = mt;
+      for (int i = 0; i < NW; ++i) {
+        const uint32_t v = acc[s][i];
+        const int w = lane * NW + i;
+        const uint32_t m = candidate_mask(v, w, tp, raw_thr, thr4);
+        if (!__any_sync(0xffffffffu, m != 0)) continue;
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb) {
+          const bool hit = (m >> (8 * bb)) & 1;
+          const uint32_t bal = __ballot_sync(0xffffffffu, hit);
+          if (hit) {
+            const int slot = base + __popc(bal & ((1u << lane) - 1));
+            if (slot < cap) {
+              const int j = 4 * w + bb, raw = (v >> (8 * bb)) & 0xFF;
+              const int r = j / g.Wd, c = j - r * g.Wd;
+              fl_match_t mt;
+              mt.x = c * g.T + off; mt.y = r * g.T + off;
+              mt.similarity = __fadd_rn(__fdiv_rn(__fmul_rn((float)raw, 100.f), (float)(4 * nf)), 0.5f);
+              mt.class_idx = meta.z; mt.template_id = meta.w;
+              cand[slot] = mt;
+            }
           }
+          base += __popc(bal);
         }
       }
     }
+    if (trace && lane == 0) { atomicMax(&trace[6], globaltimer()); plan.trace[(size_t)plan.n_cta * 8 + 8 + ((size_t)blockIdx.x * 32 + warp) * 2 + 1] = globaltimer(); }
   }
+  if (CL > 1) { __syncwarp(); cluster_sync_all(); }           // no CTA leaves while a peer may still write into it or signal it
+  if (trace && tid == 0) trace[4] = globaltimer();
+}
+
+__global__ void k_stamp(unsigned long long* p) { *p = globaltimer(); }
+
+template <int NW, int TPW, int CL>
+static int launch_staged_cl(fl_tdb db, fl_level_geom g, const uint8_t* lm_level, float threshold, fl_match_t* cand, int cap, int* d_count,
+                            fl_staged_plan plan, cudaStream_t s) {
+  auto kern = k_similarity_staged<NW, TPW, CL>;
+  static size_t configured = 0;
+  if ((size_t)plan.smem_bytes > configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes) != cudaSuccess) return -1;
+    configured = plan.smem_bytes;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(plan.n_cta); cfg.blockDim = dim3(plan.block_threads); cfg.dynamicSmemBytes = plan.smem_bytes; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  if (plan.trace) k_stamp<<<1, 1, 0, s>>>(plan.trace + (size_t)plan.n_cta * 8);
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, db, g, lm_level, threshold, cand, cap, d_count, plan);
+  if (plan.trace) k_stamp<<<1, 1, 0, s>>>(plan.trace + (size_t)plan.n_cta * 8 + 1);
+  return e == cudaSuccess ? 0 : -1;
 }
 
 template <int NW, int TPW>
 static int launch_staged(fl_tdb db, fl_level_geom g, const uint8_t* lm_level, float threshold, fl_match_t* cand, int cap, int* d_count,
                          fl_staged_plan plan, cudaStream_t s) {
-  auto kern = k_similarity_staged<NW, TPW>;
-  size_t smem = (size_t)plan.n_buf * plan.buf_bytes;
-  static size_t configured = 0;
-  if (smem > configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-    configured = smem;
+  switch (plan.cluster) {
+    case 1: return launch_staged_cl<NW, TPW, 1>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
+    case 2: return launch_staged_cl<NW, TPW, 2>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
+    case 4: return launch_staged_cl<NW, TPW, 4>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
   }
-  kern<<<plan.n_cta, plan.block_threads, smem, s>>>(db, g, lm_level, threshold, cand, cap, d_count, plan);
-  return 0;
+  return -1;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
 }
 
 // host planning: returns false if the geometry is not supported by the staged kernel.  max_positions = the largest
 // template_positions (linemod.cpp:1155) over the uploaded templates: only that many cells of a similarity map are ever
 // looked at, so the per-lane accumulator count NW is sized for it rather than for the whole grid.
+// Developer knobs (environment, read at planning time): FL_SS_CLUSTER = 1 | 2 | 4 CTAs per TMA-multicast cluster (default 1:
+// measured, multicast is slower here - the L2 -> SM stream is not the limiter and the cluster-wide buffer release costs more
+// than it saves), FL_SS_NBUF = 2..4 ring buffers (default 2).
 bool fl_plan_staged(const fl_level_geom& g, int M, int n_templates, int max_positions, int n_sm, fl_staged_plan* plan) {
   static const int kNW[] = {5, 7, 9, 11, 13, 15, 19, 23, 29, 37};
   fl_staged_plan p;
@@ -281,34 +424,44 @@ bool fl_plan_staged(const fl_level_geom& g, int M, int n_templates, int max_posi
   // unconditionally over 32 * NW + 1 words
   p.halo_bytes = 32 * p.nw_template * 4 + 16;
   if (p.halo_bytes + 16 > FL_LM_PAD) return false;
-  // rows per phase / number of buffers: 4 buffers of <= 48 KB when a (modality, label) splits evenly, else 2 of <= 100 KB;
-  // a row block must start 16-byte aligned in global memory
-  int pr = 0, nbuf = 0;
-  for (int attempt = 0; attempt < 2 && !pr; ++attempt) {
-    const size_t budget = attempt == 0 ? 48 * 1024 : 100 * 1024;
-    for (int cand_pr = T2; cand_pr >= 1; --cand_pr) {
-      if ((size_t)cand_pr * g.cells + p.halo_bytes > budget) continue;
-      if (cand_pr != T2 && ((size_t)cand_pr * g.cells) % 16 != 0) continue;
-      pr = cand_pr; nbuf = attempt == 0 ? 4 : 2;
-      break;
-    }
+  p.cluster = env_int("FL_SS_CLUSTER", 1);
+  if (p.cluster != 1 && p.cluster != 2 && p.cluster != 4) p.cluster = 1;
+  // CTAs: whole waves of the SM count, up to 31 consumer warps x TPW templates each (+ 1 producer warp)
+  const int per_cta_max = 31 * p.tpw;
+  int n_cta = (n_templates + per_cta_max - 1) / per_cta_max;
+  n_cta = ((n_cta + n_sm - 1) / n_sm) * n_sm;
+  p.tpc = (n_templates + n_cta - 1) / n_cta;
+  p.n_cta = (n_templates + p.tpc - 1) / p.tpc;
+  p.n_cta = ((p.n_cta + p.cluster - 1) / p.cluster) * p.cluster;   // whole clusters (trailing CTAs own no templates)
+  const int warps = (p.tpc + p.tpw - 1) / p.tpw;
+  p.block_threads = 32 * ((warps < 1 ? 1 : warps) + 1);
+  // rows per phase: the ring has n_buf (default 2) buffers that share the CTA's shared memory with the feature lists; a phase
+  // is the largest block of rows of one (modality, label) that fits a buffer; a row block must start 16-byte aligned in
+  // global memory.  (Measured at VGA, 8k templates: 2 x 78 KB / 16 phases beats 4 x 46 KB / 32 phases, 24.6 vs 29.9 us.)
+  int nbuf = env_int("FL_SS_NBUF", 2);
+  if (nbuf < 2 || nbuf > SS_NBUF_MAX) nbuf = 2;
+  const size_t lists = (size_t)p.tpc * 16 + ((size_t)p.tpc * SS_MAXF + 4) * 4 + (size_t)p.tpc * (SS_MAX_PHASES + 2);   // upper bound (n_phases <= SS_MAX_PHASES)
+  const size_t avail = 227 * 1024 - 1024;
+  if (lists + 4096 > avail) return false;
+  const size_t budget = ((avail - lists) / nbuf) & ~(size_t)127;
+  int pr = 0;
+  for (int cand_pr = T2; cand_pr >= 1; --cand_pr) {
+    if ((size_t)cand_pr * g.cells + p.halo_bytes + 128 > budget) continue;
+    if (cand_pr != T2 && ((size_t)cand_pr * g.cells) % 16 != 0) continue;
+    pr = cand_pr;
+    break;
   }
   if (!pr) return false;
   p.phase_rows = pr;
   p.n_rowblocks = (T2 + pr - 1) / pr;
   p.n_phases = M * 8 * p.n_rowblocks;
-  if (p.n_phases > SS_MAX_PHASES) return false;                // the phase id travels in one byte of the feature word
+  if (p.n_phases > SS_MAX_PHASES) return false;
   if ((size_t)pr * g.cells + p.halo_bytes >= (1u << 24)) return false;
   p.n_buf = p.n_phases < nbuf ? p.n_phases : nbuf;
   p.buf_bytes = (int)((((size_t)pr * g.cells + p.halo_bytes + 15) & ~(size_t)15) + 127) & ~127;
-  // CTAs: whole waves of the SM count, up to 31 consumer warps x TPW templates each (+ 1 producer warp)
-  int per_cta_max = 31 * p.tpw;
-  int n_cta = (n_templates + per_cta_max - 1) / per_cta_max;
-  n_cta = ((n_cta + n_sm - 1) / n_sm) * n_sm;
-  p.tpc = (n_templates + n_cta - 1) / n_cta;
-  p.n_cta = (n_templates + p.tpc - 1) / p.tpc;
-  int warps = (p.tpc + p.tpw - 1) / p.tpw;
-  p.block_threads = 32 * ((warps < 1 ? 1 : warps) + 1);
+  p.pre_stride = (p.n_phases + 1 + 3) & ~3;
+  p.smem_bytes = p.n_buf * p.buf_bytes + p.tpc * 16 + (p.tpc * SS_MAXF + 4) * 4 + p.tpc * p.pre_stride;
+  if (p.smem_bytes > 227 * 1024 - 512) return false;
   *plan = p;
   return true;
 }

@@ -172,7 +172,10 @@ enum {
   FL_DBG_QUANTIZED = 0,     /* (level, modality)         -> (W>>l)*(H>>l) u8 */
   FL_DBG_SPREAD = 1,        /* (level, modality)         -> same size u8 (only kept when fl_debug_keep_spread(h,1)) */
   FL_DBG_LINEAR_MEMORY = 2, /* (level, modality, label)  -> T*T*(W/T)*(H/T) u8 */
-  FL_DBG_SIMILARITY = 3     /* (template index)          -> (W/T)*(H/T) u16 total similarity at the coarsest level */
+  FL_DBG_SIMILARITY = 3,    /* (template index)          -> (W/T)*(H/T) u16 total similarity at the coarsest level */
+  FL_DBG_STAGED_TRACE = 4   /* ()                        -> 8 u64 per CTA of the staged similarity kernel {t_start, t_ready, t_first_data,
+                               t_loop_end, t_end (globaltimer ns), smid, 0, 0}; only when the process was started with FL_TRACE=1;
+                               returns the number of CTAs */
 };
 int fl_debug_keep_spread(fl_handle* h, int enable);
 /* kernel selection of the global similarity stage: the shared-memory-staged kernel is used when the template set is
