@@ -52,34 +52,57 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock and throttle reasons sampled DURING the timed region through NVML (same counters as the nvidia-smi line
+    of B200_PROFILING.md, but in-process so that a timed region of tens of milliseconds still gets dozens of samples)."""
 
-    def __init__(self, gpu_index: int):
+    def __init__(self, gpu_index: int, period_s: float = 0.002):
         super().__init__(daemon=True)
         self.gpu = gpu_index
-        self.samples = []
-        self.proc = None
+        self.period = period_s
+        self.sm, self.reasons, self.power = [], set(), []
+        self.sm_max = None
+        self._stop_evt = threading.Event()
+        self.err = None
 
     def run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                self.samples.append([x.strip() for x in line.split(",")])
-        except Exception:
-            pass
+            import pynvml as N
+            N.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may renumber the devices: map through the PCI bus id of the CUDA device
+            try:
+                import torch
+                bus = torch.cuda.get_device_properties(self.gpu).pci_bus_id
+                dom = torch.cuda.get_device_properties(self.gpu).pci_domain_id
+                dev = torch.cuda.get_device_properties(self.gpu).pci_device_id
+                hdl = N.nvmlDeviceGetHandleByPciBusId(("%08x:%02x:%02x.0" % (dom, bus, dev)).encode())
+            except Exception:
+                hdl = N.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.sm_max = float(N.nvmlDeviceGetMaxClockInfo(hdl, N.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": N.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": N.nvmlClocksEventReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": N.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": N.nvmlClocksEventReasonSwPowerCap}
+            get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self._stop_evt.is_set():
+                self.sm.append(float(N.nvmlDeviceGetClockInfo(hdl, N.NVML_CLOCK_SM)))
+                r = int(get_reasons(hdl))
+                for k, v in bits.items():
+                    if r & v:
+                        self.reasons.add(k)
+                try:
+                    self.power.append(N.nvmlDeviceGetPowerUsage(hdl) / 1e3)
+                except Exception:
+                    pass
+                time.sleep(self.period)
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
-        sm = [float(s[0]) for s in self.samples if len(s) >= 6 and s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if len(s) >= 6 and s[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for s in self.samples if len(s) >= 6 for i in range(4) if s[2 + i].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+        self._stop_evt.set()
+        self.join(timeout=2.0)
+        out = {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+               "samples": len(self.sm), "power_w_max": max(self.power) if self.power else None, "source": "NVML, sampled during the timed region"}
+        if self.err:
+            out["error"] = self.err
+        return out
 
 
 def make_inputs(n_templates: int, seed: int = 1):
@@ -174,7 +197,6 @@ def run_ours(args):
     d_frames = [(torch.from_numpy(b).to(dev), torch.from_numpy(d.view(np.int16)).to(dev)) for b, d in frames]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
     torch.cuda.synchronize()
-    h.profile(True)
 
     def step(i, timed):
         tb, td = d_frames[i % N_FRAMES]
@@ -201,11 +223,10 @@ def run_ours(args):
         sampler.start()
     torch.cuda.synchronize()
     launches0 = h.launch_count()
-    evs, stage = [], np.zeros(4)
+    evs = []
     wall0 = time.perf_counter()
     for i in range(args.steps):
         evs.append(step(args.warmup + i, True))
-        stage += h.last_stage_ms() if world == 1 else 0
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -219,6 +240,17 @@ def run_ours(args):
     dev_ms = float(t.item())
     n_matches = len(h.match_fetch()) if world == 1 else len(sm.fetch())
     evals_per_step = args.templates * world * CELLS
+    # per-stage device times: a second, shorter pass with the library's own CUDA events between the stages (on its stream);
+    # kept out of the headline loop because every event record costs the pipeline a few microseconds
+    stage, n_stage = np.zeros(4), min(args.steps, 100)
+    if world == 1:
+        h.profile(True)
+        for i in range(n_stage + 3):
+            step(i, False)
+            if i >= 3:
+                stage += h.last_stage_ms()
+        torch.cuda.synchronize()
+        h.profile(False)
     value = evals_per_step * args.steps / (dev_ms * 1e-3)
 
     # ---- e2e: host buffers through the C ABI (rank-local; N > 1 adds the host copies to the sharded path) ----
@@ -260,7 +292,7 @@ def run_ours(args):
     roofline = None
     extra = {}
     if world == 1:
-        st = stage / args.steps                                          # ms: front end, similarity, refine, sort
+        st = stage / n_stage                                             # ms: front end, similarity, refine, sort
         sm_clk = (clocks or {}).get("sm_mhz") or sm_max_mhz
         smem_peak = 148 * 128 * sm_clk * 1e6 / 1e9                       # GB/s: 148 SMs x 128 B/clk x achieved SM clock
         alg_bytes = args.templates * CELLS * FEATURES_COARSE             # 62 B per eval
@@ -268,11 +300,11 @@ def run_ours(args):
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                traffic = json.load(f).get("k_similarity_global")
+                traffic = json.load(f).get("k_similarity_staged")
         except Exception:
             pass
-        roofline = {"kernel": "similarity_global", "bound": "smem", "achieved": ach, "peak": smem_peak, "unit": "GB/s", "frac": ach / smem_peak,
-                    "traffic": traffic, "kernel_ms": float(st[1]), "peak_source": "148 SM x 128 B/clk x %.0f MHz (SM clock sampled under load); "
+        roofline = {"kernel": "k_similarity_staged (global similarity, all templates, coarsest level)", "bound": "smem", "achieved": ach, "peak": smem_peak, "unit": "GB/s", "frac": ach / smem_peak,
+                    "traffic": traffic, "kernel_ms": float(st[1]), "timer": "CUDA events on the library's stream around the stage (counter memset + launch + kernel), mean of %d steps" % n_stage, "peak_source": "148 SM x 128 B/clk x %.0f MHz (SM clock sampled under load); "
                     "MEASURED_PEAKS.json has no shared-memory figure" % sm_clk, "algorithmic_bytes_per_launch": alg_bytes}
         fe = FRONT_END_BYTES / (st[0] * 1e-3) / 1e9
         extra["roofline_front_end"] = {"kernels": "color_quantize, pyrdown, depth_quantize, resize_nn, spread_lm (x4)", "bound": "hbm",
@@ -292,7 +324,7 @@ def run_ours(args):
     # ---- ICP (BASELINE configs[2], C3): 256 hypotheses x ~10k points, reported beside the headline ----
     icp = None
     if world == 1 and not args.no_icp:
-        icp = bench_icp(h, synth)
+        icp = bench_icp(h, synth, cpu=not args.no_cpu)
 
     line = {"metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
@@ -310,16 +342,29 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def bench_icp(h, synth, n_hyp: int = 256):
-    """C3: n_hyp pose hypotheses, 100x100-pixel crops (~10k points each) against one 640x480 reference depth frame."""
-    import torch
-    base = [synth.make_icp_pair(W, H, seed=s, max_rot_deg=8, max_shift_mm=10, rect_wh=(100, 100)) for s in range(16)]
-    ref = base[0][1]
+def make_icp_workload(synth, n_hyp: int = 256, crop: int = 104):
+    """C3: one 640x480 reference depth frame tiled with 24 moved surfaces, n_hyp hypotheses whose 100x100-pixel model crops
+    (~10k points each) sit on those tiles (hypothesis i uses tile i % 24 with its own initial pose)."""
+    nx, ny = W // crop, H // crop
+    ref = np.zeros((H, W), np.uint16)
+    tiles = []
+    for k in range(nx * ny):
+        x0, y0 = (k % nx) * crop + 2, (k // nx) * crop + 2
+        md, rf, rm, rr, p = synth.make_icp_pair(W, H, seed=100 + k, max_rot_deg=6, max_shift_mm=8, rect_wh=(crop - 4, crop - 4), rect_xy=(x0, y0))
+        rr = (x0, y0, crop - 4, crop - 4)                              # pixel-aligned crops, like Recognition aligns a match
+        ref[y0:y0 + crop - 4, x0:x0 + crop - 4] = rf[y0:y0 + crop - 4, x0:x0 + crop - 4]
+        tiles.append((md, rm, rr, p))
     mds, rms, rrs, Rs, ts = [], [], [], [], []
     for i in range(n_hyp):
-        md, rf, rm, rr, p = base[i % 16]
+        md, rm, rr, p = tiles[i % len(tiles)]
         mds.append(md); rms.append(rm); rrs.append(rr)
         Rs.append(p[:12].reshape(3, 4)[:, :3]); ts.append(p[:12].reshape(3, 4)[:, 3])
+    return ref, mds, rms, rrs, Rs, ts
+
+
+def bench_icp(h, synth, n_hyp: int = 256, cpu: bool = True):
+    """C3 (BASELINE configs[2]): n_hyp pose hypotheses x ~10k model points against one 640x480 depth frame."""
+    ref, mds, rms, rrs, Rs, ts = make_icp_workload(synth, n_hyp)
     K = (608.0, 608.0, 320.0, 240.0)
     h.detection_batch(ref, K, mds, rms, rrs, Rs, ts)          # warm-up (allocates the workspace)
     times = []
@@ -329,16 +374,28 @@ def bench_icp(h, synth, n_hyp: int = 256):
         times.append(time.perf_counter() - t0)
     its = int(res["iterations"].sum())
     t = float(np.min(times))
-    return {"workload": "C3: %d hypotheses x 100x100 crops (~%d points) vs one 640x480 depth frame, <=10 iterations" % (n_hyp, int(res["n_points"].mean())),
-            "icp_iters_per_s": its / t, "hypotheses_per_s": n_hyp / t, "total_iterations": its, "batch_ms": 1e3 * t,
-            "timer": "host wall clock around fl_detection_batch (includes H2D of crops and D2H of poses)"}
+    out = {"workload": "C3: %d hypotheses x 10,000-pixel model crops (mean %d paired valid points) vs one 640x480 depth frame, <=10 iterations"
+                       % (n_hyp, int(res["n_points"].mean())),
+           "icp_iters_per_s": its / t, "hypotheses_per_s": n_hyp / t, "total_iterations": its, "batch_ms": 1e3 * t,
+           "timer": "host wall clock around fl_detection_batch (includes H2D of crops and D2H of poses)"}
+    if cpu:                                                    # CPU baseline leg: the C restatement of detection(), one thread, 8 hypotheses
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import fl_oracle_py as F
+        t0 = time.perf_counter()
+        cits = 0
+        for i in range(8):
+            cits += int(F.detection(mds[i], ref, K, rms[i], rrs[i], r_match=Rs[i], t_match=ts[i])["iterations"])
+        ct = time.perf_counter() - t0
+        out["cpu_baseline"] = {"icp_iters_per_s": cits / ct, "hypotheses_per_s": 8 / ct, "cores": 1, "kind": "port",
+                               "sample": "the first 8 hypotheses of the same batch (KD-tree build + ICP loop each)"}
+    return out
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--templates", type=int, default=8000, help="templates per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -32,7 +32,7 @@ struct fl_handle {
   fl_staged_plan plan;
   std::vector<int32_t> class_first_h, class_of_h;
   std::vector<float> pose13_h;
-  std::vector<uint8_t> class_enabled_h;
+  std::vector<uint8_t> class_enabled_h; bool class_enabled_valid;   // host mirror of d_class_enabled
   // geometry of the last frame
   int gW, gH; bool packed;
   fl_level_geom geom[FL_MAX_LEVELS]; fl_level_geom* d_geom;
@@ -109,7 +109,7 @@ extern "C" int fl_create(const fl_params_t* params, fl_handle** out) {
   FL_CUDA(cudaSetDevice(p.device));
   fl_handle* h = new (std::nothrow) fl_handle();
   if (!h) return FL_ERR_ARG;
-  h->p = p; h->launches = 0; h->gW = h->gH = 0; h->packed = false; h->have_result = false; h->profile = false; h->keep_spread = false;
+  h->p = p; h->class_enabled_valid = false; h->launches = 0; h->gW = h->gH = 0; h->packed = false; h->have_result = false; h->profile = false; h->keep_spread = false;
   h->n_templates = h->n_features = h->n_classes = 0;
   h->d_hdr = nullptr; h->d_feat = nullptr; h->d_class_of = nullptr; h->d_class_first = nullptr; h->d_class_enabled = nullptr; h->d_pfeat = nullptr;
   h->d_tid_of = nullptr;
@@ -262,7 +262,7 @@ extern "C" int fl_upload_templates(fl_handle* h, int32_t n_templates, const fl_t
   h->class_first_h = first; h->class_of_h.assign(class_of, class_of + n_templates);
   h->pose13_h.clear();
   if (pose13) h->pose13_h.assign(pose13, pose13 + (size_t)n_templates * 13);
-  h->class_enabled_h.assign((size_t)std::max(nc, 1), 1);
+  h->class_enabled_h.assign((size_t)std::max(nc, 1), 1); h->class_enabled_valid = false;
   h->packed = false;
   return FL_OK;
 }
@@ -360,11 +360,20 @@ static int run_match_stages(fl_handle* h, const uint8_t* d_bgr, const uint16_t* 
     if (p.modality_kind[m] == FL_MODALITY_COLOR_GRADIENT && !d_bgr) return FL_ERR_SIZE;
     if (p.modality_kind[m] == FL_MODALITY_DEPTH_NORMAL && !d_depth) return FL_ERR_SIZE;
   }
-  // class filter (Detector::match :1418-1434): unknown ids are ignored, empty = all
+  // class filter (Detector::match :1418-1434): unknown ids are ignored, empty = all.  Uploaded only when it changes.
   if (h->n_classes > 0) {
-    for (int c = 0; c < h->n_classes; ++c) h->h_class_enabled[c] = (n_filter > 0 && class_filter) ? 0 : 1;
-    if (n_filter > 0 && class_filter) for (int k = 0; k < n_filter; ++k) if (class_filter[k] >= 0 && class_filter[k] < h->n_classes) h->h_class_enabled[class_filter[k]] = 1;
-    FL_CUDA(cudaMemcpyAsync(h->d_class_enabled, h->h_class_enabled, (size_t)h->n_classes, cudaMemcpyHostToDevice, s));
+    bool changed = false;
+    for (int c = 0; c < h->n_classes; ++c) {
+      uint8_t on = (n_filter > 0 && class_filter) ? 0 : 1;
+      if (n_filter > 0 && class_filter) for (int k = 0; k < n_filter; ++k) if (class_filter[k] == c) on = 1;
+      if (h->class_enabled_h[c] != on) { h->class_enabled_h[c] = on; changed = true; }
+    }
+    if (changed || !h->class_enabled_valid) {
+      FL_CUDA(cudaStreamSynchronize(s));                                          // the pinned staging copy may still be in flight
+      memcpy(h->h_class_enabled, h->class_enabled_h.data(), (size_t)h->n_classes);
+      FL_CUDA(cudaMemcpyAsync(h->d_class_enabled, h->h_class_enabled, (size_t)h->n_classes, cudaMemcpyHostToDevice, s));
+      h->class_enabled_valid = true;
+    }
   }
   if (h->profile) cudaEventRecord(h->ev[0], s);
   const float thr_sq = p.weak_threshold * p.weak_threshold;

@@ -219,14 +219,19 @@ __global__ void __launch_bounds__(1024, 1) k_similarity_staged(fl_tdb db, fl_lev
       s_meta[i] = m;
     }
     for (int i = tid; i < plan.tpc * SS_MAXF; i += n_cwarps * 32) {
-      const int t = t_begin + i / SS_MAXF;
-      s_feat[i] = t < t_end ? plan.gfeat[(size_t)t * SS_MAXF + (i % SS_MAXF)] : 0u;
+      const int t = t_begin + (i >> 6);                       // SS_MAXF == 64
+      s_feat[i] = t < t_end ? plan.gfeat[(size_t)t * SS_MAXF + (i & (SS_MAXF - 1))] : 0u;
     }
     if (tid < 4) s_feat[plan.tpc * SS_MAXF + tid] = 0u;
-    for (int i = tid; i < plan.tpc * plan.pre_stride; i += n_cwarps * 32) {
-      const int t = t_begin + i / plan.pre_stride;
-      const bool on = t < t_end && db.class_enabled[db.class_of[t]];
-      s_pre[i] = on ? plan.gpre[(size_t)t * plan.pre_stride + (i % plan.pre_stride)] : (uint8_t)0;
+    {   // prefix counts, copied as 32-bit words (pre_stride is a multiple of 4): one warp per template row
+      const int wpr = plan.pre_stride >> 2;
+      uint32_t* s_pre32 = reinterpret_cast<uint32_t*>(s_pre);
+      const uint32_t* gpre32 = reinterpret_cast<const uint32_t*>(plan.gpre);
+      for (int row = warp; row < plan.tpc; row += n_cwarps) {
+        const int t = t_begin + row;
+        const bool on = t < t_end && db.class_enabled[db.class_of[t]];
+        for (int c = lane; c < wpr; c += 32) s_pre32[row * wpr + c] = on ? gpre32[(size_t)t * wpr + c] : 0u;
+      }
     }
     asm volatile("bar.sync 1, %0;" ::"r"(n_cwarps * 32) : "memory");   // consumers only
   }

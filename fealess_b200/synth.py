@@ -219,7 +219,7 @@ def make_templates(n_templates: int, W: int = 640, H: int = 480, T: Sequence[int
 # --------------------------------------------------------------------------------------------
 def make_icp_pair(W: int = 640, H: int = 480, seed: int = 0, rect_wh=(100, 100),
                   fx: float = 608.0, fy: float = 608.0, cx: float = 320.0, cy: float = 240.0,
-                  max_shift_mm: float = 6.0, max_rot_deg: float = 3.0):
+                  max_shift_mm: float = 6.0, max_rot_deg: float = 3.0, rect_xy=None):
     """A (model depth, ref depth, rect_model, rect_ref, pose13-ish) tuple for ``detection()``.
 
     The model depth image shows a smooth bumpy surface inside ``rect_model``; the reference depth is
@@ -232,6 +232,8 @@ def make_icp_pair(W: int = 640, H: int = 480, seed: int = 0, rect_wh=(100, 100),
     w, h = rect_wh
     mx = int(rng.integers(0, W - w))
     my = int(rng.integers(0, H - h))
+    if rect_xy is not None:                   # caller-chosen model rect (the random draws above keep the stream position)
+        mx, my = int(rect_xy[0]), int(rect_xy[1])
     # keep the two rects close: the crops are back-projected at their own pixel positions, so a large
     # offset would shear the clouds against each other (z * du / fx) beyond what ICP is meant to fix
     rx = int(np.clip(mx + rng.integers(-20, 21), 0, W - w - 1))
