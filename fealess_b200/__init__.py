@@ -43,7 +43,7 @@ EXPORTED_SYMBOLS = [
     "fl_default_params", "fl_create", "fl_destroy", "fl_last_error", "fl_version", "fl_sync", "fl_stream",
     "fl_upload_templates", "fl_set_template_ids", "fl_num_templates", "fl_get_pose_info", "fl_match", "fl_match_device", "fl_match_fetch",
     "fl_match_shard_device", "fl_sort_unique_device", "fl_depth_to_3d", "fl_icp_cloud_to_cloud_ex",
-    "fl_detection_batch", "fl_detection", "fl_nms", "fl_debug_keep_spread", "fl_debug_force_baseline", "fl_debug_uses_staged", "fl_debug_get", "fl_launch_count",
+    "fl_detection_batch", "fl_detection", "fl_nms", "fl_nms_ex", "fl_debug_keep_spread", "fl_debug_force_baseline", "fl_debug_uses_staged", "fl_debug_get", "fl_launch_count",
     "fl_profile", "fl_last_stage_ms",
 ]
 

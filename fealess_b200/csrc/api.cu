@@ -747,7 +747,8 @@ extern "C" int fl_detection(fl_handle* h, const uint16_t* model_depth, size_t mo
   return FL_OK;
 }
 
-extern "C" int fl_nms(fl_handle* h, const float* t3, const int32_t* n_model_pts, const float* icp_dist, int32_t n, float th, int32_t* out_idx) {
+extern "C" int fl_nms_ex(fl_handle* h, const float* t3, const int32_t* n_model_pts, const float* icp_dist, int32_t n, float th, int32_t* out_idx,
+                         uint8_t* absorbed) {
   if (!h || n < 0 || (n > 0 && (!t3 || !n_model_pts || !icp_dist || !out_idx))) return FL_ERR_ARG;
   if (n == 0) return 0;
   FL_CUDA(cudaSetDevice(h->p.device));
@@ -758,11 +759,16 @@ extern "C" int fl_nms(fl_handle* h, const float* t3, const int32_t* n_model_pts,
   FL_CUDA(cudaMemcpyAsync(d_n, n_model_pts, (size_t)n * 4, cudaMemcpyHostToDevice, s));
   FL_CUDA(cudaMemcpyAsync(d_d, icp_dist, (size_t)n * 4, cudaMemcpyHostToDevice, s));
   int32_t* d_cnt = d_o + 2 * n + 1;
-  fl_launch_nms(d_t, d_n, d_d, n, th, d_o, d_cnt, s); ++h->launches;
+  fl_launch_nms(d_t, d_n, d_d, n, th, d_o, d_cnt, s); ++h->launches;       // the absorbed flags live right after out_idx (n bytes)
   int32_t cnt = 0;
   FL_CUDA(cudaMemcpyAsync(out_idx, d_o, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+  if (absorbed) FL_CUDA(cudaMemcpyAsync(absorbed, d_o + n, (size_t)n, cudaMemcpyDeviceToHost, s));
   FL_CUDA(cudaMemcpyAsync(&cnt, d_cnt, 4, cudaMemcpyDeviceToHost, s));
   FL_CUDA(cudaStreamSynchronize(s));
   cudaFree(d_t); cudaFree(d_n); cudaFree(d_d); cudaFree(d_o);
   return cnt;
+}
+
+extern "C" int fl_nms(fl_handle* h, const float* t3, const int32_t* n_model_pts, const float* icp_dist, int32_t n, float th, int32_t* out_idx) {
+  return fl_nms_ex(h, t3, n_model_pts, icp_dist, n, th, out_idx, nullptr);
 }

@@ -166,6 +166,9 @@ int fl_detection(fl_handle* h, const uint16_t* model_depth, size_t model_stride,
  * out_idx receives, per emitted PoseResult, the index of the object it was taken from; returns the count (>= 0) or < 0. */
 int fl_nms(fl_handle* h, const float* t3, const int32_t* n_model_pts, const float* icp_dist, int32_t n,
            float th_obj_dist, int32_t* out_idx);
+/* same, and absorbed[i] (n bytes, nullable) = 1 for every object the reference would have marked check_done (NMS.cpp:27) */
+int fl_nms_ex(fl_handle* h, const float* t3, const int32_t* n_model_pts, const float* icp_dist, int32_t n,
+              float th_obj_dist, int32_t* out_idx, uint8_t* absorbed);
 
 /* ---- stage-level debug exports (host copies of device intermediates of the LAST match call) -------- */
 enum {

@@ -1,0 +1,103 @@
+"""The C++ host-side mirror of the reference interface (include/fealess_b200/linemod.hpp, icp.hpp).
+
+CPU: the mirror + its driver compile and link against the C-ABI library with -Wall -Wextra (no OpenCV in this image, so
+against the cv_min.hpp stand-in).  GPU (-m gpu): tests/cpp/shim_test.cpp runs Detector::match / detection / depthTo3d /
+nonMaximumSuppression the way CadReco's Recognition does and compares with expectations computed here by the CPU oracle."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import fealess_b200 as fb
+from fealess_b200 import build as fbuild
+from fealess_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "cpp", "shim_test.cpp")
+OUT_DIR = os.path.join(ROOT, "tests", "cpp", "_build")
+EXE = os.path.join(OUT_DIR, "shim_test")
+
+
+def _compile():
+    fbuild.build()
+    os.makedirs(OUT_DIR, exist_ok=True)
+    libdir = os.path.dirname(fb.library_path())
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [cxx, "-std=c++11", "-O1", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), SRC, "-o", EXE,
+           fb.library_path(), "-Wl,-rpath," + libdir]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return EXE
+
+
+def test_cpp_mirror_compiles_and_links():
+    exe = _compile()
+    r = subprocess.run([exe], capture_output=True, text=True)          # no case file: prints usage, touches no GPU
+    assert r.returncode == 2 and "usage" in r.stdout
+
+
+def test_cpp_headers_are_self_contained():
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    for hdr in ("fealess_b200/linemod.hpp", "fealess_b200/icp.hpp", "fealess_b200/cv_min.hpp", "fealess_b200.h"):
+        r = subprocess.run([cxx, "-std=c++11", "-fsyntax-only", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"), "-x", "c++", "-include", hdr, os.devnull],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, hdr + "\n" + r.stderr
+    r = subprocess.run(["gcc", "-std=c99", "-fsyntax-only", "-Wall", "-I", os.path.join(ROOT, "include"), "-x", "c", "-include", "fealess_b200.h", os.devnull],
+                       capture_output=True, text=True)                 # the C ABI header is plain C
+    assert r.returncode == 0, r.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_mirror_matches_oracle(tmp_path):
+    import fl_oracle_py as F
+    W, H, T = 640, 480, (5, 8)
+    b, d = synth.make_frame(W, H, 2)
+    det = F.Detector(T)
+    assert det.process(b, d) == 0
+    q = [det.quantized(l, m) for l in range(2) for m in range(2)]
+    ts = synth.make_templates(400, W, H, T, n_classes=3, seed=33, quantized=q, planted_fraction=0.05)
+    det.set_templates(ts)
+    thr = 70.0
+    exp = det.match(thr)
+    assert len(exp) > 0
+    md, rf, rm, rr, p = synth.make_icp_pair(W, H, seed=5, max_rot_deg=6, max_shift_mm=8)
+    R0 = p[:12].reshape(3, 4)[:, :3].astype(np.float32)
+    t0 = p[:12].reshape(3, 4)[:, 3].astype(np.float32)
+    o = F.detection(md, rf, (608.0, 608.0, 320.0, 240.0), rm, rr, r_match=R0, t_match=t0)
+    rng = np.random.default_rng(7)
+    n_obj = 40
+    t3 = (rng.uniform(0, 150, (n_obj, 3))).astype(np.float32)
+    npts = rng.integers(500, 1500, n_obj).astype(np.int32)
+    dist = rng.uniform(0.2, 3.0, n_obj).astype(np.float32)
+    keep = np.asarray(F.nms(t3, npts, dist, 30.0), np.int32)
+    blob = b"".join([
+        struct.pack("<ii", W, H), np.ascontiguousarray(b, np.uint8).tobytes(), np.ascontiguousarray(d, np.uint16).tobytes(),
+        struct.pack("<ii", 2, 2), np.asarray(T, np.int32).tobytes(),
+        struct.pack("<i", ts.n_templates), np.ascontiguousarray(ts.headers, np.int32).tobytes(),
+        struct.pack("<i", len(ts.features)), np.ascontiguousarray(ts.features, np.int32).tobytes(),
+        np.ascontiguousarray(ts.class_of, np.int32).tobytes(),
+        struct.pack("<fi", thr, len(exp)), np.ascontiguousarray(exp).tobytes(),
+        np.ascontiguousarray(md, np.uint16).tobytes(), np.ascontiguousarray(rf, np.uint16).tobytes(),
+        np.asarray(rm, np.int32).tobytes(), np.asarray(rr, np.int32).tobytes(), R0.tobytes(), t0.tobytes(),
+        np.asarray(o["T"], np.float32).tobytes(), np.asarray(o["R"], np.float32).tobytes(),
+        struct.pack("<i", n_obj), t3.tobytes(), npts.tobytes(), dist.tobytes(), struct.pack("<i", len(keep)), keep.tobytes(),
+    ])
+    case = tmp_path / "case.bin"
+    case.write_bytes(blob)
+    exe = _compile()
+    r = subprocess.run([exe, str(case)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "all checks passed" in r.stdout
+
+
+def test_compat_headers_forward_to_the_mirror():
+    """`#include "linemod_if.h"` / "detection.h" / "NMS.h" as CadReco writes them resolve to the mirror."""
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    src = '#include "linemod_if.h"\n#include "detection.h"\n#include "NMS.h"\n#include "ICP.h"\n#include "depth_to_3d.h"\n' \
+          'int main() { cv::Ptr<cup_linemod::Detector> d = cup_linemod::getDefaultLINEMOD(); std::vector<obj_data> o; std::vector<PoseResult> p; ' \
+          'return d->numClasses() + (int)o.size() + (int)p.size(); }\n'
+    r = subprocess.run([cxx, "-std=c++11", "-fsyntax-only", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include", "fealess_b200_compat"),
+                        "-I", os.path.join(ROOT, "include"), "-x", "c++", "-"], input=src, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
