@@ -381,7 +381,7 @@ static int run_match_stages(fl_handle* h, const uint8_t* d_bgr, const uint16_t* 
   for (int m = 0; m < p.n_modalities; ++m) { h->used_mask[m] = d_masks && d_masks[m]; any_mask |= h->used_mask[m]; }
   int first_color = -1;
   for (int m = 0; m < p.n_modalities; ++m) if (p.modality_kind[m] == FL_MODALITY_COLOR_GRADIENT && first_color < 0) first_color = m;
-  const bool zero_in_wave = !any_mask && getenv("FL_NO_MEMSET") != nullptr;
+  const bool zero_in_wave = !any_mask;                       // wave 0 resets the candidate counter: no memset node between the kernels
   if (!any_mask) {
     // wave schedule (frontend.cu): L + 1 launches for the whole front end
     for (int wv = 0; wv <= p.n_levels; ++wv) {
@@ -479,10 +479,10 @@ static int run_sort_unique(fl_handle* h, const fl_match_t* d_in, int n_lists, in
   cudaStream_t s = h->stream;
   if ((int64_t)n_lists * list_cap > h->key_cap) { fl_set_error("sort capacity %d < %lld", h->key_cap, (long long)n_lists * list_cap); return FL_ERR_CAPACITY; }
   int* d_hdr = reinterpret_cast<int*>(h->d_outblk);
-  h->launches += fl_launch_sort_unique(d_in, n_lists, list_cap, d_n_in, h->key_cap, d_out, out_cap, d_out_count, d_hdr, s);
   const bool own = fetch_first && d_out == h->d_out;
-  // one D2H copy: the summary and (own output block) the first matches right behind it
-  FL_CUDA(cudaMemcpyAsync(h->h_outblk, h->d_outblk, own ? 64 + sizeof(fl_match_t) * (size_t)std::min(FETCH_FIRST, out_cap) : 64, cudaMemcpyDeviceToHost, s));
+  // the kernel itself posts the summary and (own output block) the first matches into the mapped pinned block h_outblk
+  h->launches += fl_launch_sort_unique(d_in, n_lists, list_cap, d_n_in, h->key_cap, d_out, out_cap, d_out_count, d_hdr, h->h_small,
+                                       own ? h->h_first : nullptr, std::min(FETCH_FIRST, out_cap), s);
   if (h->profile) cudaEventRecord(h->ev[4], s);
   FL_CUDA(cudaStreamSynchronize(s));
   h->overflow = false;

@@ -98,8 +98,10 @@ void fl_launch_refine_level(fl_tdb db, fl_level_geom g, int level, const uint8_t
 // sort + unique: n_lists lists of list_cap records at d_in (counts in d_n_in); result in d_out/d_out_count, summary in
 // d_hdr[16] = {unique count, live records, flag_big, raw counts...}.  One launch; when flag_big comes back set the host
 // runs fl_launch_sort_unique_big (key workspace: next_pow2(n_upper) keys + 1 int).  Both return the number of launches.
+// h_hdr / h_first: mapped pinned host copies of the summary and of the first h_first_cap matches (nullable).
 int fl_launch_sort_unique(const fl_match_t* d_in, int n_lists, int list_cap, const int* d_n_in, int key_cap,
-                          fl_match_t* d_out, int out_cap, int* d_out_count, int* d_hdr, cudaStream_t s);
+                          fl_match_t* d_out, int out_cap, int* d_out_count, int* d_hdr, int* h_hdr, fl_match_t* h_first, int h_first_cap,
+                          cudaStream_t s);
 int fl_launch_sort_unique_big(const fl_match_t* d_in, int n_lists, int list_cap, const int* d_n_in, fl_sort_key* keys, int key_cap,
                               int n_upper, fl_match_t* d_out, int out_cap, int* d_out_count, cudaStream_t s);
 

@@ -236,7 +236,7 @@ void fl_launch_pyrdown_bgr(const uint8_t* src, int W, int H, uint8_t* dst, cudaS
 #define DQ_TH 16
 #define DQ_THREADS 256
 
-#define DQ_SMEM_BYTES ((DQ_TH + 14) * (DQ_TW + 14) * 2 + (DQ_TH + 4) * (DQ_TW + 4) + 16)
+#define DQ_SMEM_BYTES ((DQ_TH + 14) * (DQ_TW + 14) * 2 + 16 + (((DQ_TH + 4) * (DQ_TW + 4) + 15) & ~15) + DQ_TH * (DQ_TW + 4) * 8)
 
 __device__ __forceinline__ void dev_depth_quantize(const uint16_t* __restrict__ depth, int W, int H, int dist_thr, int diff_thr,
                                                    uint8_t* __restrict__ q, int bx, int by, uint8_t* smem) {
@@ -290,28 +290,30 @@ __device__ __forceinline__ void dev_depth_quantize(const uint16_t* __restrict__ 
     s_r[ry][rx] = v;
   }
   __syncthreads();
+  // 5x5 median (cv::medianBlur, :684).  The labels are one-hot bytes or 0 (NORMAL_LUT), i.e. 9 distinct values whose numeric
+  // order is the order of idx = 0 (for 0) or bit position + 1, so the median is read off a 9-bin histogram: bins of 5 bits
+  // packed in a u64, per-column histograms of 5 rows shared by the 5 pixels that overlap them.
+  unsigned long long(*s_ch)[RW] = reinterpret_cast<unsigned long long(*)[RW]>(smem + ((SH * SW * 2 + 15) & ~15) + ((RH * RW + 15) & ~15));
+  for (int i = tid; i < DQ_TH * RW; i += DQ_THREADS) {
+    const int oy = i / RW, rx = i - oy * RW;
+    unsigned long long hsum = 0;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) hsum += 1ull << (5 * (32 - __clz((unsigned)s_r[oy + j][rx])));
+    s_ch[oy][rx] = hsum;
+  }
+  __syncthreads();
   for (int i = tid; i < DQ_TH * DQ_TW; i += DQ_THREADS) {
-    int oy = i / DQ_TW, ox = i - oy * DQ_TW;
-    int x = x0 + ox, y = y0 + oy;
+    const int oy = i / DQ_TW, ox = i - oy * DQ_TW;
+    const int x = x0 + ox, y = y0 + oy;
     if (x >= W || y >= H) continue;
-    // exact median of 25 bytes by MSB-first radix selection of the 13th smallest
-    uint32_t vals[25];
+    const unsigned long long hist = s_ch[oy][ox] + s_ch[oy][ox + 1] + s_ch[oy][ox + 2] + s_ch[oy][ox + 3] + s_ch[oy][ox + 4];
+    int c = 0, med = 0;                                  // 13th smallest of 25
 #pragma unroll
-    for (int j = 0; j < 5; ++j)
-#pragma unroll
-      for (int k = 0; k < 5; ++k) vals[j * 5 + k] = s_r[oy + j][ox + k];
-    uint32_t prefix = 0, mask = 0;
-    int need = 13;
-#pragma unroll
-    for (int bit = 7; bit >= 0; --bit) {
-      uint32_t m2 = mask | (1u << bit);
-      int zeros = 0;
-#pragma unroll
-      for (int t = 0; t < 25; ++t) zeros += ((vals[t] & m2) == prefix) ? 1 : 0;   // matches prefix and has this bit clear
-      if (need > zeros) { need -= zeros; prefix |= 1u << bit; }
-      mask = m2;
+    for (int b = 0; b < 9; ++b) {
+      c += (int)((hist >> (5 * b)) & 31);
+      if (c < 13) med = b + 1;
     }
-    q[(size_t)y * W + x] = (uint8_t)prefix;
+    q[(size_t)y * W + x] = med == 0 ? (uint8_t)0 : (uint8_t)(1u << (med - 1));
   }
 }
 
@@ -370,12 +372,12 @@ __host__ __device__ inline size_t spread_smem_bytes(int T) {
 }
 
 __device__ __forceinline__ void dev_spread_lm(const uint8_t* __restrict__ q, const fl_level_geom& g, uint8_t* __restrict__ lm,
-                                              uint8_t* __restrict__ spread_out, int bx, int by, uint8_t* smem) {
+                                              uint8_t* __restrict__ spread_out, int bx, int by, uint8_t* smem, int cw) {
   uint2* s_resp = reinterpret_cast<uint2*>(smem);        // 256 x 8 B
   uint8_t* s_raw = smem + 2048;                          // [(2T-1)][tw] input (later reused for the final spread), then [(2T-1)][pw]
   const int T = g.T, W = g.W, H = g.H, Wd = g.Wd;
-  const int gy = by, cx0 = bx * SL_CW;
-  const int ncell = min(SL_CW, Wd - cx0);
+  const int gy = by, cx0 = bx * cw;                     // cw <= SL_CW cells per CTA (fewer on small levels: more CTAs in flight)
+  const int ncell = min(cw, Wd - cx0);
   const int pw = ncell * T;                             // pixels owned by this CTA per row
   const int tw = pw + T - 1, th = 2 * T - 1;
   const int px0 = cx0 * T, py0 = gy * T;
@@ -436,7 +438,7 @@ __device__ __forceinline__ void dev_spread_lm(const uint8_t* __restrict__ q, con
 __global__ void __launch_bounds__(SL_THREADS) k_spread_lm(const uint8_t* __restrict__ q, fl_level_geom g, uint8_t* __restrict__ lm,
                                                           uint8_t* __restrict__ spread_out) {
   extern __shared__ __align__(16) uint8_t smem_dyn[];
-  dev_spread_lm(q, g, lm, spread_out, blockIdx.x, blockIdx.y, smem_dyn);
+  dev_spread_lm(q, g, lm, spread_out, blockIdx.x, blockIdx.y, smem_dyn, SL_CW);
 }
 
 void fl_launch_spread_lm(const uint8_t* q, fl_level_geom g, uint8_t* lm_mod, uint8_t* spread_or_null, cudaStream_t s) {
@@ -466,7 +468,7 @@ __global__ void __launch_bounds__(256) k_front_end_wave(fl_fe_wave w) {
     case FL_JOB_DEPTH: dev_depth_quantize(reinterpret_cast<const uint16_t*>(jb.src), jb.W, jb.H, jb.p0, jb.p1, jb.dst, local % jb.gx, local / jb.gx, smem_dyn); break;
     case FL_JOB_PYRDOWN: dev_pyrdown_bgr(jb.src, jb.W, jb.H, jb.dst, local); break;
     case FL_JOB_RESIZE: dev_resize_nn_half(jb.src, jb.W, jb.H, jb.dst, local); break;
-    case FL_JOB_SPREAD: dev_spread_lm(jb.src, jb.g, jb.dst, jb.dst2, local % jb.gx, local / jb.gx, smem_dyn); break;
+    case FL_JOB_SPREAD: dev_spread_lm(jb.src, jb.g, jb.dst, jb.dst2, local % jb.gx, local / jb.gx, smem_dyn, jb.p0); break;
   }
 }
 
@@ -495,7 +497,10 @@ void fl_fe_add_resize(fl_fe_wave* w, const uint8_t* src, int W, int H, uint8_t* 
 void fl_fe_add_spread(fl_fe_wave* w, const uint8_t* q, fl_level_geom g, uint8_t* lm_mod, uint8_t* spread_or_null) {
   fl_fe_job& j = w->job[w->n_jobs++];
   j.kind = FL_JOB_SPREAD; j.src = q; j.dst = lm_mod; j.dst2 = spread_or_null; j.g = g; j.W = g.W; j.H = g.H;
-  j.gx = (g.Wd + SL_CW - 1) / SL_CW; j.cta_begin = w->n_ctas; w->n_ctas += j.gx * g.Hd;
+  int cw = SL_CW;                                       // small levels: narrower CTAs so that the job still fills the SMs
+  while (cw > 8 && ((g.Wd + cw - 1) / cw) * g.Hd < 148) cw >>= 1;
+  j.p0 = cw;
+  j.gx = (g.Wd + cw - 1) / cw; j.cta_begin = w->n_ctas; w->n_ctas += j.gx * g.Hd;
   size_t sm = spread_smem_bytes(g.T);
   w->smem = w->smem > sm ? w->smem : sm;
 }

@@ -126,6 +126,7 @@ void fl_launch_similarity_debug(fl_tdb db, fl_level_geom g, const uint8_t* lm_le
 // One CTA of 64 threads per candidate: thread = (patch row, 4-cell column group).
 // ------------------------------------------------------------------------------------------------
 #define RF_THREADS 256       // 4 feature groups x 64 (16 patch rows x 4 column groups of 4 cells)
+#define RF_MAXF (FL_MAX_MODALITIES * 63)
 
 __global__ void __launch_bounds__(RF_THREADS) k_refine_level(fl_tdb db, fl_level_geom g, int level, const uint8_t* __restrict__ lm_level,
                                                              float threshold, fl_match_t* __restrict__ cand, int cap,
@@ -133,52 +134,57 @@ __global__ void __launch_bounds__(RF_THREADS) k_refine_level(fl_tdb db, fl_level
   const int n = min(*d_count, cap);
   const int fgrp = threadIdx.x >> 6, cell = threadIdx.x & 63;
   const int row = cell >> 2, cg = cell & 3;
+  __shared__ uint32_t s_off[RF_MAXF];          // byte offset of every feature's window origin inside the level's linear memories, or FL_SKIP
+  __shared__ int s_mbeg[FL_MAX_MODALITIES + 1];
   __shared__ uint32_t s_part[3][64][2];
   __shared__ uint32_t s_best[2];
+  const int T = g.T, border = 8 * T;
   for (int ci = blockIdx.x; ci < n; ci += gridDim.x) {
     fl_match_t mt = cand[ci];
     if (mt.template_id < 0) continue;                              // dropped at a coarser level (:1570-1572)
     const int t = mt.template_id;                                  // handle-local template index (see k_similarity_global)
     const fl_template_hdr_t* hdr = db.hdr + ((size_t)t * db.L + level) * db.M;
-    const int T = g.T, border = 8 * T;
     int x = mt.x * 2 + 1, y = mt.y * 2 + 1;                        // :1525-1534
     x = max(x, border); y = max(y, border);
     x = min(x, g.W - hdr[0].width - border);
     y = min(y, g.H - hdr[0].height - border);
     const int ox = (x / T - 8) * T, oy = (y / T - 8) * T;          // :1240-1241 (C division truncates towards zero)
-    const int delta = (oy / T) * g.Wd + ox / T + row * g.Wd + cg * 4;
-    uint32_t tot_lo = 0, tot_hi = 0;
+    const int delta = (oy / T) * g.Wd + ox / T;
+    // stage 1: one thread per feature resolves the feature's window origin (all modalities), so that stage 2 issues
+    // nothing but independent linear-memory loads
     int nf = 0;
     for (int m = 0; m < db.M; ++m) {
       const fl_template_hdr_t h = hdr[m];
-      nf += h.feature_count;
-      const uint8_t* lm_mod = lm_level + (size_t)m * g.mod_stride;
-      const fl_pfeat* pf = db.pfeat + h.feature_begin;
-      uint32_t acc = 0;
-      // each of the 4 feature groups takes every 4th feature; 4 independent windows are in flight per thread
-      for (int k0 = fgrp; k0 < h.feature_count; k0 += 16) {
-        uint32_t v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int k = k0 + 4 * u;
-          v[u] = 0;
-          if (k < h.feature_count) {
-            const fl_pfeat p = pf[k];
-            const int fx = p.x + ox, fy = p.y + oy;
-            if (fx >= 0 && fy >= 0 && fx < g.W && fy < g.H) {      // :1257
-              // the packed offset was computed for (x, y); shifting by a multiple of T moves only the cell index
-              uint32_t o = p.lm_off;
-              if (o == FL_SKIP)                                    // outside the image unshifted, inside when shifted
-                o = (uint32_t)((size_t)db.feat[h.feature_begin + k].label * g.label_stride +
-                               (size_t)((p.y % T + T) % T * T + (p.x % T + T) % T) * g.cells + (size_t)(fy / T) * g.Wd + fx / T) +
-                    (uint32_t)(row * g.Wd + cg * 4);
-              else
-                o = (uint32_t)((int)o + delta);
-              v[u] = load_u8x4(lm_mod, o);
-            }
-          }
+      if (threadIdx.x == 0) s_mbeg[m] = nf;
+      for (int k = threadIdx.x; k < h.feature_count; k += RF_THREADS) {
+        const fl_pfeat p = db.pfeat[h.feature_begin + k];
+        const int fx = p.x + ox, fy = p.y + oy;
+        uint32_t o = FL_SKIP;
+        if (fx >= 0 && fy >= 0 && fx < g.W && fy < g.H) {          // :1257
+          // the packed offset was computed for (x, y); shifting by a multiple of T moves only the cell index
+          if (p.lm_off == FL_SKIP)                                 // outside the image unshifted, inside when shifted
+            o = (uint32_t)((size_t)db.feat[h.feature_begin + k].label * g.label_stride +
+                           (size_t)((p.y % T + T) % T * T + (p.x % T + T) % T) * g.cells + (size_t)(fy / T) * g.Wd + fx / T);
+          else
+            o = (uint32_t)((int)p.lm_off + delta);
+          o += (uint32_t)((size_t)m * g.mod_stride);
         }
-        acc += v[0] + v[1] + v[2] + v[3];                          // u8 lanes: <= 63 features x 4, no carry
+        s_off[nf + k] = o;
+      }
+      nf += h.feature_count;
+    }
+    if (threadIdx.x == 0) s_mbeg[db.M] = nf;
+    __syncthreads();
+    // stage 2: 16x16 patch, thread = (feature group, patch row, 4-cell column group); u8 lanes per modality (<= 63 x 4)
+    const uint32_t cell_off = (uint32_t)(row * g.Wd + cg * 4);
+    uint32_t tot_lo = 0, tot_hi = 0;
+    for (int m = 0; m < db.M; ++m) {
+      uint32_t acc = 0;
+      const int k1 = s_mbeg[m + 1];
+#pragma unroll 4
+      for (int k = s_mbeg[m] + fgrp; k < k1; k += 4) {
+        const uint32_t o = s_off[k];
+        if (o != FL_SKIP) acc += load_u8x4(lm_level, o + cell_off);
       }
       tot_lo += (acc & 0xFF) | ((acc & 0xFF00) << 8);
       tot_hi += ((acc >> 16) & 0xFF) | ((acc >> 24) << 16);
@@ -273,16 +279,22 @@ __global__ void __launch_bounds__(256) k_build_keys(const fl_match_t* __restrict
 // bitonic steps + k_unique_big).  d_scratch = {n_live, flag_big}.
 __global__ void __launch_bounds__(1024) k_sort_unique_small(const fl_match_t* __restrict__ in, int n_lists, int list_cap,
                                                             const int* __restrict__ n_in, int key_cap, fl_match_t* __restrict__ out,
-                                                            int out_cap, int* __restrict__ d_out_count, int* __restrict__ d_hdr) {
-  // d_hdr (16 ints, handle-owned) = {unique count, n_live, flag_big, raw n_in[0..11]}: one small D2H copy tells the host everything
+                                                            int out_cap, int* __restrict__ d_out_count, int* __restrict__ d_hdr,
+                                                            int* __restrict__ h_hdr, fl_match_t* __restrict__ h_first, int h_first_cap) {
+  // d_hdr (16 ints, handle-owned) = {unique count, n_live, flag_big, raw n_in[0..11]}.  h_hdr / h_first (nullable) are the
+  // same summary and the first matches in MAPPED PINNED HOST memory: the kernel posts them over PCIe itself, so the host
+  // needs no device-to-host copy (and none of its ~8 us of copy-engine hand-over) before it can read the result.
   __shared__ fl_sort_key s_k[SORT_SMEM_N];
   __shared__ int s_warp[32];
   __shared__ int s_n;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int total = 0;
   for (int l = 0; l < n_lists; ++l) total += min(max(n_in[l], 0), list_cap);
-  if (tid < 12) d_hdr[3 + tid] = tid < n_lists ? n_in[tid] : 0;
-  if (total > SORT_SMEM_N || total > key_cap) { if (tid == 0) { d_hdr[0] = 0; d_hdr[1] = total; d_hdr[2] = 1; } return; }
+  if (tid < 12) { const int c = tid < n_lists ? n_in[tid] : 0; d_hdr[3 + tid] = c; if (h_hdr) h_hdr[3 + tid] = c; }
+  if (total > SORT_SMEM_N || total > key_cap) {
+    if (tid == 0) { d_hdr[0] = 0; d_hdr[1] = total; d_hdr[2] = 1; if (h_hdr) { h_hdr[0] = 0; h_hdr[1] = total; h_hdr[2] = 1; } }
+    return;
+  }
   if (tid == 0) s_n = 0;
   __syncthreads();
   for (int i = tid; i < total; i += blockDim.x) {
@@ -328,8 +340,16 @@ __global__ void __launch_bounds__(1024) k_sort_unique_small(const fl_match_t* __
   __syncthreads();
   int pos = (warp > 0 ? s_warp[warp - 1] : 0) + inc - cnt;
   for (int i = b0; i < min(b0 + per, n); ++i)
-    if (i == 0 || !key_dup(s_k[i - 1], s_k[i])) { if (pos < out_cap) out[pos] = key_to_match(s_k[i]); ++pos; }
-  if (tid == 0) { *d_out_count = s_warp[31]; d_hdr[0] = s_warp[31]; d_hdr[1] = n; d_hdr[2] = 0; }
+    if (i == 0 || !key_dup(s_k[i - 1], s_k[i])) {
+      const fl_match_t m = key_to_match(s_k[i]);
+      if (pos < out_cap) out[pos] = m;
+      if (h_first && pos < h_first_cap) h_first[pos] = m;
+      ++pos;
+    }
+  if (tid == 0) {
+    *d_out_count = s_warp[31]; d_hdr[0] = s_warp[31]; d_hdr[1] = n; d_hdr[2] = 0;
+    if (h_hdr) { h_hdr[0] = s_warp[31]; h_hdr[1] = n; h_hdr[2] = 0; }
+  }
 }
 
 // large path: global bitonic steps + serial-chunk unique
@@ -382,8 +402,9 @@ __global__ void __launch_bounds__(1024) k_unique_big(const fl_sort_key* __restri
 
 // Host orchestration.  Scratch int (n_live of the big path) lives right after the key array.
 int fl_launch_sort_unique(const fl_match_t* d_in, int n_lists, int list_cap, const int* d_n_in, int key_cap,
-                          fl_match_t* d_out, int out_cap, int* d_out_count, int* d_hdr, cudaStream_t s) {
-  k_sort_unique_small<<<1, 1024, 0, s>>>(d_in, n_lists, list_cap, d_n_in, key_cap, d_out, out_cap, d_out_count, d_hdr);
+                          fl_match_t* d_out, int out_cap, int* d_out_count, int* d_hdr, int* h_hdr, fl_match_t* h_first, int h_first_cap,
+                          cudaStream_t s) {
+  k_sort_unique_small<<<1, 1024, 0, s>>>(d_in, n_lists, list_cap, d_n_in, key_cap, d_out, out_cap, d_out_count, d_hdr, h_hdr, h_first, h_first_cap);
   return 1;
 }
 
