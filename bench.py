@@ -367,16 +367,20 @@ def bench_icp(h, synth, n_hyp: int = 256, cpu: bool = True):
     ref, mds, rms, rrs, Rs, ts = make_icp_workload(synth, n_hyp)
     K = (608.0, 608.0, 320.0, 240.0)
     h.detection_batch(ref, K, mds, rms, rrs, Rs, ts)          # warm-up (allocates the workspace)
-    times = []
-    for _ in range(3):
+    times, dev = [], []
+    h.profile(True)
+    for _ in range(5):
         t0 = time.perf_counter()
         res = h.detection_batch(ref, K, mds, rms, rrs, Rs, ts)
         times.append(time.perf_counter() - t0)
+        dev.append(h.last_icp_ms())
+    h.profile(False)
     its = int(res["iterations"].sum())
     t = float(np.min(times))
     out = {"workload": "C3: %d hypotheses x 10,000-pixel model crops (mean %d paired valid points) vs one 640x480 depth frame, <=10 iterations"
                        % (n_hyp, int(res["n_points"].mean())),
            "icp_iters_per_s": its / t, "hypotheses_per_s": n_hyp / t, "total_iterations": its, "batch_ms": 1e3 * t,
+           "device_ms": float(np.min(dev)), "icp_iters_per_s_device": its / (float(np.min(dev)) * 1e-3),
            "timer": "host wall clock around fl_detection_batch (includes H2D of crops and D2H of poses)"}
     if cpu:                                                    # CPU baseline leg: the C restatement of detection(), one thread, 8 hypotheses
         sys.path.insert(0, os.path.join(ROOT, "oracle"))

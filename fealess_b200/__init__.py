@@ -44,7 +44,7 @@ EXPORTED_SYMBOLS = [
     "fl_upload_templates", "fl_set_template_ids", "fl_num_templates", "fl_get_pose_info", "fl_match", "fl_match_device", "fl_match_fetch",
     "fl_match_shard_device", "fl_sort_unique_device", "fl_depth_to_3d", "fl_icp_cloud_to_cloud_ex",
     "fl_detection_batch", "fl_detection", "fl_nms", "fl_nms_ex", "fl_debug_keep_spread", "fl_debug_force_baseline", "fl_debug_uses_staged", "fl_debug_get", "fl_launch_count",
-    "fl_profile", "fl_last_stage_ms",
+    "fl_profile", "fl_last_stage_ms", "fl_last_icp_ms",
 ]
 
 
@@ -242,6 +242,11 @@ class Handle:
         out = np.zeros(4, np.float32)
         _check(lib().fl_last_stage_ms(self._h, _p(out)), "fl_last_stage_ms")
         return out
+
+    def last_icp_ms(self) -> float:
+        v = C.c_float(0)
+        _check(lib().fl_last_icp_ms(self._h, C.byref(v)), "fl_last_icp_ms")
+        return float(v.value)
 
     # ---- debug exports ---------------------------------------------------------------------------
     def keep_spread(self, enable=True):

@@ -25,6 +25,30 @@ struct fl_sort_key { unsigned long long hi, lo; };
 
 void fl_set_error(const char* fmt, ...);
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------------
+// Every kernel of the per-frame pipeline can be launched with cudaLaunchAttributeProgrammaticStreamSerialization: its CTAs
+// may become resident while the previous kernel of the stream drains, run their prologue, and block in
+// fl_grid_dep_wait() until the previous kernel has completed and its writes are visible.  Rule: a kernel touches no
+// mutable global buffer before fl_grid_dep_wait(); fl_grid_dep_launch() tells the scheduler that the NEXT kernel may
+// start being placed.  Launched without the attribute both calls are no-ops.  The attribute is only set when the
+// process runs with FL_PDL=1 (measured: no gain for this pipeline, see fl_pdl_enabled in api.cu).
+#ifdef __CUDACC__
+__device__ __forceinline__ void fl_grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void fl_grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+bool fl_pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t fl_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = fl_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 #define FL_CUDA(call)                                                                  \
   do {                                                                                 \
     cudaError_t e__ = (call);                                                          \
@@ -51,9 +75,9 @@ struct fl_fe_job {
   const uint8_t* src; uint8_t* dst; uint8_t* dst2;
   fl_level_geom g;
 };
-#define FL_FE_MAX_JOBS 10
+#define FL_FE_MAX_JOBS 16
 struct fl_fe_wave { int n_jobs, n_ctas; size_t smem; int* zero_me; fl_fe_job job[FL_FE_MAX_JOBS]; };   // zero_me: int reset by CTA 0 (candidate counter), or NULL
-void fl_fe_add_color(fl_fe_wave* w, const uint8_t* bgr, int W, int H, float thr_sq, uint8_t* q);
+void fl_fe_add_color(fl_fe_wave* w, const uint8_t* bgr, int W, int H, float thr_sq, uint8_t* q, int part, int n_parts);
 void fl_fe_add_depth(fl_fe_wave* w, const uint16_t* depth, int W, int H, int dist_thr, int diff_thr, uint8_t* q);
 void fl_fe_add_pyrdown(fl_fe_wave* w, const uint8_t* src, int W, int H, uint8_t* dst);
 void fl_fe_add_resize(fl_fe_wave* w, const uint8_t* src, int W, int H, uint8_t* dst);

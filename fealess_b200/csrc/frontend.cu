@@ -367,67 +367,101 @@ void fl_launch_apply_mask(const uint8_t* q, const uint8_t* mask, int n, uint8_t*
 #define SL_CW 32
 #define SL_THREADS 256
 
+// shared memory: response table (2 KB) + input tile + horizontal-OR tile (rows padded to whole 32-bit words + slack)
+__host__ __device__ inline int spread_stride_in(int T) { return (SL_CW * T + T - 1 + 6) & ~3; }
+__host__ __device__ inline int spread_stride_pw(int T) { return (SL_CW * T + 3) & ~3; }
 __host__ __device__ inline size_t spread_smem_bytes(int T) {
-  return 2048 + (size_t)(2 * T - 1) * (SL_CW * T + T - 1) + (size_t)(2 * T - 1) * (SL_CW * T);   // response table + two tiles; <= 35 KB at T = 16
+  return 2048 + (size_t)(2 * T - 1) * spread_stride_in(T) + (size_t)(2 * T - 1) * spread_stride_pw(T);   // <= 35 KB at T = 16
 }
 
+// OR of the T bytes starting at every byte of a 32-bit word: words w[0..] hold the row from the word's own position on.
+// TT > 0: T known at compile time (the loop unrolls to T funnel shifts); TT == 0: runtime T, words read on the fly.
+template <int TT>
+__device__ __forceinline__ uint32_t or_window(const uint32_t* __restrict__ w, int T) {
+  uint32_t o = 0;
+  if (TT > 0) {
+    uint32_t v[(TT + 2) / 4 + 2];
+#pragma unroll
+    for (int i = 0; i < (TT + 2) / 4 + 2; ++i) v[i] = w[i];
+#pragma unroll
+    for (int k = 0; k < TT; ++k) o |= __funnelshift_r(v[k >> 2], v[(k >> 2) + 1], 8 * (k & 3));
+  } else {
+    for (int k = 0; k < T; ++k) o |= __funnelshift_r(w[k >> 2], w[(k >> 2) + 1], 8 * (k & 3));
+  }
+  return o;
+}
+
+template <int TT>
 __device__ __forceinline__ void dev_spread_lm(const uint8_t* __restrict__ q, const fl_level_geom& g, uint8_t* __restrict__ lm,
                                               uint8_t* __restrict__ spread_out, int bx, int by, uint8_t* smem, int cw) {
-  uint2* s_resp = reinterpret_cast<uint2*>(smem);        // 256 x 8 B
-  uint8_t* s_raw = smem + 2048;                          // [(2T-1)][tw] input (later reused for the final spread), then [(2T-1)][pw]
-  const int T = g.T, W = g.W, H = g.H, Wd = g.Wd;
+  const int T = TT > 0 ? TT : g.T;
+  const int W = g.W, H = g.H, Wd = g.Wd;
   const int gy = by, cx0 = bx * cw;                     // cw <= SL_CW cells per CTA (fewer on small levels: more CTAs in flight)
   const int ncell = min(cw, Wd - cx0);
   const int pw = ncell * T;                             // pixels owned by this CTA per row
   const int tw = pw + T - 1, th = 2 * T - 1;
   const int px0 = cx0 * T, py0 = gy * T;
-  const int tid = threadIdx.x;
-  uint8_t* s_in = s_raw;                                // th x tw
-  uint8_t* s_hor = s_raw + (size_t)(2 * T - 1) * (SL_CW * T + T - 1);   // th x pw horizontal OR
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NWARP = SL_THREADS / 32;
+  const int st_in = (tw + 6) & ~3;                      // row stride of the input tile: whole words, >= 3 bytes of zero slack
+  const int nw = (pw + 3) >> 2, st_pw = nw << 2;        // words per row of the OR tiles
+  uint2* s_resp = reinterpret_cast<uint2*>(smem);        // 256 x 8 B
+  uint8_t* s_in = smem + 2048;                          // [th][st_in]   input labels (later reused for the final spread)
+  uint8_t* s_hor = s_in + (size_t)(2 * T - 1) * spread_stride_in(T);   // [th][st_pw] horizontal OR
   for (int i = tid; i < 256; i += SL_THREADS) s_resp[i] = c_resp8[i];
-  for (int i = tid; i < th * tw; i += SL_THREADS) {
-    int r = i / tw, c = i - r * tw;
-    int y = py0 + r, x = px0 + c;
-    s_in[r * tw + c] = (x < W && y < H) ? q[(size_t)y * W + x] : (uint8_t)0;   // clipped window == OR with zeros
+  for (int r = warp; r < th; r += NWARP) {              // rows by warp, bytes by lane: coalesced, no index arithmetic
+    const int y = py0 + r;
+    const uint8_t* src = q + (size_t)y * W + px0;
+    for (int c = lane; c < st_in; c += 32) s_in[r * st_in + c] = (c < tw && px0 + c < W && y < H) ? src[c] : (uint8_t)0;   // clipped window == OR with zeros
   }
   __syncthreads();
-  for (int i = tid; i < th * pw; i += SL_THREADS) {
-    int r = i / pw, c = i - r * pw;
-    uint32_t v = 0;
-    for (int k = 0; k < T; ++k) v |= s_in[r * tw + c + k];
-    s_hor[r * pw + c] = (uint8_t)v;
+  for (int r = warp; r < th; r += NWARP) {              // horizontal OR, four pixels per thread
+    const uint32_t* row = reinterpret_cast<const uint32_t*>(s_in + r * st_in);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(s_hor + r * st_pw);
+    for (int wi = lane; wi < nw; wi += 32) dst[wi] = or_window<TT>(row + wi, T);
   }
   __syncthreads();
-  uint8_t* s_sp = s_in;                                 // T x pw final spread values (s_in is dead)
-  for (int i = tid; i < T * pw; i += SL_THREADS) {
-    int r = i / pw, c = i - r * pw;
-    uint32_t v = 0;
-    for (int k = 0; k < T; ++k) v |= s_hor[(r + k) * pw + c];
-    s_sp[r * pw + c] = (uint8_t)v;
-    if (spread_out) spread_out[(size_t)(py0 + r) * W + px0 + c] = (uint8_t)v;
+  uint8_t* s_sp = s_in;                                 // [T][st_pw] final spread values (s_in is dead)
+  for (int r = warp; r < T; r += NWARP) {               // vertical OR
+    uint32_t* dst = reinterpret_cast<uint32_t*>(s_sp + r * st_pw);
+    for (int wi = lane; wi < nw; wi += 32) {
+      uint32_t v = 0;
+      if (TT > 0) {
+#pragma unroll
+        for (int k = 0; k < TT; ++k) v |= reinterpret_cast<const uint32_t*>(s_hor + (r + k) * st_pw)[wi];
+      } else {
+        for (int k = 0; k < T; ++k) v |= reinterpret_cast<const uint32_t*>(s_hor + (r + k) * st_pw)[wi];
+      }
+      dst[wi] = v;
+      if (spread_out)
+        for (int k = 0; k < 4; ++k) if (4 * wi + k < pw) spread_out[(size_t)(py0 + r) * W + px0 + 4 * wi + k] = (uint8_t)(v >> (8 * k));
+    }
   }
   __syncthreads();
-  // scatter: item = (grid row ry, grid col rx, group of 4 cells); 8 labels -> 8 word stores per item
-  const int ngrp = (ncell + 3) / 4;
+  // scatter: item = (residue row ry, residue column rx, group of 4 cells); 8 labels -> 8 word stores per item
+  const int ngrp = (ncell + 3) >> 2;
   const int items = T * T * ngrp;
   const size_t cells = (size_t)g.cells;
+  const uint32_t inv_ngrp = (65536u + ngrp - 1) / ngrp, inv_T = (65536u + T - 1) / T;   // exact for the small ranges used here
   for (int i = tid; i < items; i += SL_THREADS) {
-    int rr = i / ngrp, c4 = i - rr * ngrp;
-    int ry = rr / T, rx = rr - ry * T;
+    const int rr = (int)(((uint32_t)i * inv_ngrp) >> 16), c4 = i - rr * ngrp;
+    const int ry = (int)(((uint32_t)rr * inv_T) >> 16), rx = rr - ry * T;
     uint32_t lo[4], hi[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      int c = c4 * 4 + k;
-      uint2 r8 = c < ncell ? s_resp[s_sp[ry * pw + c * T + rx]] : make_uint2(0, 0);
+      const int c = c4 * 4 + k;
+      const uint2 r8 = c < ncell ? s_resp[s_sp[ry * st_pw + c * T + rx]] : make_uint2(0, 0);
       lo[k] = r8.x; hi[k] = r8.y;
     }
-    size_t off = (size_t)rr * cells + (size_t)gy * Wd + cx0 + c4 * 4;
-    int nvalid = min(4, ncell - c4 * 4);
+    const size_t off = (size_t)rr * cells + (size_t)gy * Wd + cx0 + c4 * 4;
+    const int nvalid = min(4, ncell - c4 * 4);
 #pragma unroll
     for (int lab = 0; lab < 8; ++lab) {
       const uint32_t* src = lab < 4 ? lo : hi;
-      int sh = 8 * (lab & 3);
-      uint32_t w = ((src[0] >> sh) & 0xFF) | (((src[1] >> sh) & 0xFF) << 8) | (((src[2] >> sh) & 0xFF) << 16) | (((src[3] >> sh) & 0xFF) << 24);
+      // byte (lab & 3) of each of the four words -> one word
+      const uint32_t sel = 0x0040u + (lab & 3) * 0x0011u;          // PRMT selector: {byte b of x, byte b of y}
+      const uint32_t w01 = __byte_perm(src[0], src[1], sel), w23 = __byte_perm(src[2], src[3], sel);
+      const uint32_t w = __byte_perm(w01, w23, 0x5410);
       uint8_t* dst = lm + (size_t)lab * g.label_stride + off;
       if (nvalid == 4 && (((uintptr_t)dst) & 3) == 0) *reinterpret_cast<uint32_t*>(dst) = w;
       else for (int k = 0; k < nvalid; ++k) dst[k] = (uint8_t)(w >> (8 * k));
@@ -435,10 +469,20 @@ __device__ __forceinline__ void dev_spread_lm(const uint8_t* __restrict__ q, con
   }
 }
 
+__device__ __forceinline__ void dev_spread_lm_any(const uint8_t* __restrict__ q, const fl_level_geom& g, uint8_t* __restrict__ lm,
+                                                  uint8_t* __restrict__ spread_out, int bx, int by, uint8_t* smem, int cw) {
+  switch (g.T) {
+    case 5: dev_spread_lm<5>(q, g, lm, spread_out, bx, by, smem, cw); break;
+    case 8: dev_spread_lm<8>(q, g, lm, spread_out, bx, by, smem, cw); break;
+    case 4: dev_spread_lm<4>(q, g, lm, spread_out, bx, by, smem, cw); break;
+    default: dev_spread_lm<0>(q, g, lm, spread_out, bx, by, smem, cw); break;
+  }
+}
+
 __global__ void __launch_bounds__(SL_THREADS) k_spread_lm(const uint8_t* __restrict__ q, fl_level_geom g, uint8_t* __restrict__ lm,
                                                           uint8_t* __restrict__ spread_out) {
   extern __shared__ __align__(16) uint8_t smem_dyn[];
-  dev_spread_lm(q, g, lm, spread_out, blockIdx.x, blockIdx.y, smem_dyn, SL_CW);
+  dev_spread_lm_any(q, g, lm, spread_out, blockIdx.x, blockIdx.y, smem_dyn, SL_CW);
 }
 
 void fl_launch_spread_lm(const uint8_t* q, fl_level_geom g, uint8_t* lm_mod, uint8_t* spread_or_null, cudaStream_t s) {
@@ -457,6 +501,8 @@ void fl_launch_spread_lm(const uint8_t* q, fl_level_geom g, uint8_t* lm_mod, uin
 __global__ void __launch_bounds__(256) k_front_end_wave(fl_fe_wave w) {
   extern __shared__ __align__(16) uint8_t smem_dyn[];
   const int b = blockIdx.x;
+  fl_grid_dep_wait();                                   // the previous kernel of the stream wrote this wave's inputs
+  fl_grid_dep_launch();
   if (w.zero_me && b == 0 && threadIdx.x == 0) *w.zero_me = 0;
   int j = 0;
 #pragma unroll 1
@@ -464,18 +510,22 @@ __global__ void __launch_bounds__(256) k_front_end_wave(fl_fe_wave w) {
   const fl_fe_job& jb = w.job[j];
   const int local = b - jb.cta_begin;
   switch (jb.kind) {
-    case FL_JOB_COLOR: dev_color_quantize(jb.src, jb.W, jb.H, jb.thr_sq, jb.dst, local % jb.gx, local / jb.gx, smem_dyn); break;
+    case FL_JOB_COLOR: { const int tile = local + jb.p0; dev_color_quantize(jb.src, jb.W, jb.H, jb.thr_sq, jb.dst, tile % jb.gx, tile / jb.gx, smem_dyn); break; }
     case FL_JOB_DEPTH: dev_depth_quantize(reinterpret_cast<const uint16_t*>(jb.src), jb.W, jb.H, jb.p0, jb.p1, jb.dst, local % jb.gx, local / jb.gx, smem_dyn); break;
     case FL_JOB_PYRDOWN: dev_pyrdown_bgr(jb.src, jb.W, jb.H, jb.dst, local); break;
     case FL_JOB_RESIZE: dev_resize_nn_half(jb.src, jb.W, jb.H, jb.dst, local); break;
-    case FL_JOB_SPREAD: dev_spread_lm(jb.src, jb.g, jb.dst, jb.dst2, local % jb.gx, local / jb.gx, smem_dyn, jb.p0); break;
+    case FL_JOB_SPREAD: dev_spread_lm_any(jb.src, jb.g, jb.dst, jb.dst2, local % jb.gx, local / jb.gx, smem_dyn, jb.p0); break;
   }
 }
 
-void fl_fe_add_color(fl_fe_wave* w, const uint8_t* bgr, int W, int H, float thr_sq, uint8_t* q) {
+// part / n_parts: the tiles of one image may be spread over several waves (the job then covers tiles [first, first + count))
+void fl_fe_add_color(fl_fe_wave* w, const uint8_t* bgr, int W, int H, float thr_sq, uint8_t* q, int part, int n_parts) {
+  const int gx = (W + CQ_TW - 1) / CQ_TW, tiles = gx * ((H + CQ_TH - 1) / CQ_TH);
+  const int first = (int)((long long)tiles * part / n_parts), last = (int)((long long)tiles * (part + 1) / n_parts);
+  if (last <= first) return;
   fl_fe_job& j = w->job[w->n_jobs++];
   j.kind = FL_JOB_COLOR; j.src = bgr; j.dst = q; j.dst2 = nullptr; j.W = W; j.H = H; j.thr_sq = thr_sq;
-  j.gx = (W + CQ_TW - 1) / CQ_TW; j.cta_begin = w->n_ctas; w->n_ctas += j.gx * ((H + CQ_TH - 1) / CQ_TH);
+  j.gx = gx; j.p0 = first; j.p1 = last - first; j.cta_begin = w->n_ctas; w->n_ctas += last - first;
   w->smem = w->smem > (size_t)CQ_SMEM_BYTES ? w->smem : (size_t)CQ_SMEM_BYTES;
 }
 void fl_fe_add_depth(fl_fe_wave* w, const uint16_t* depth, int W, int H, int dist_thr, int diff_thr, uint8_t* q) {
@@ -505,7 +555,7 @@ void fl_fe_add_spread(fl_fe_wave* w, const uint8_t* q, fl_level_geom g, uint8_t*
   w->smem = w->smem > sm ? w->smem : sm;
 }
 void fl_launch_fe_wave(const fl_fe_wave& w, cudaStream_t s) {
-  if (w.n_ctas > 0) k_front_end_wave<<<w.n_ctas, 256, w.smem, s>>>(w);
+  if (w.n_ctas > 0) fl_launch_pdl(k_front_end_wave, dim3(w.n_ctas), dim3(256), w.smem, s, w);
 }
 
 // every hot kernel asks for the maximum shared-memory carveout so that the SMs never re-partition L1/shared memory between

@@ -67,26 +67,51 @@ __device__ __forceinline__ int block_excl_scan(int v, int* s_warp, int* total) {
   return base + inc - v;
 }
 
-// ordered fp32 chain: lanes 0..5 sum one component of a point list each (getMean, ICP.cpp:8-25); lanes 6..14 sum one
-// product m[a]*r[b] each (covariance += m * r^T, ICP.cpp:731-735).  Must be called by a full warp; returns lane's sum.
-__device__ __forceinline__ float chain15(const float* __restrict__ pm, int n_m, const float* __restrict__ pr, int n_r, int n_cov) {
-  const int lane = threadIdx.x & 31;
+// Ordered fp32 chains, staged through shared memory.  The reference sums centroids (getMean, ICP.cpp:8-25) and the
+// uncentred covariance (covariance += m * r^T, ICP.cpp:731-735) sequentially in fp32, and the result is order sensitive
+// (file header), so each of the 15 sums is one dependent chain walked by one lane of warp 0: lanes 0..2 / 3..5 sum one
+// component of the model / reference list, lanes 6..14 one product m[a] * r[b].  What made the chains slow was not the
+// adds but the global-memory latency in front of each batch of them, so the other warps stream the two point lists into
+// a double-buffered shared-memory stage (coalesced) one chunk ahead of the chain lanes.
+// Must be called by all ICP_THREADS threads; ends with a barrier; s_sum[0..14] holds the sums afterwards.
+#define ICP_CH 384                                     // points per stage buffer
+__device__ __forceinline__ void block_chain15(const float* __restrict__ pm, int n_m, const float* __restrict__ pr, int n_r, int n_cov,
+                                              float (*s_st)[2][ICP_CH * 3], float* s_sum) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nm_all = max(n_m, n_cov), nr_all = max(n_r, n_cov);      // the covariance reads both lists
+  const int n_chunks = (max(nm_all, nr_all) + ICP_CH - 1) / ICP_CH;
+  auto load_chunk = [&](int c, int t, int nt) {
+    const int base = c * ICP_CH, buf = c & 1;
+    const int cm = max(0, min(ICP_CH, nm_all - base)) * 3, cr = max(0, min(ICP_CH, nr_all - base)) * 3;
+    for (int i = t; i < cm; i += nt) s_st[buf][0][i] = pm[(size_t)base * 3 + i];
+    for (int i = t; i < cr; i += nt) s_st[buf][1][i] = pr[(size_t)base * 3 + i];
+  };
+  const int n_lane = lane < 3 ? n_m : (lane < 6 ? n_r : n_cov);
+  const int ia = lane < 3 ? lane : (lane < 6 ? lane - 3 : (lane - 6) / 3), ib = (lane - 6) % 3;
   float acc = 0.f;
-  if (lane < 3) {
-    const float* p = pm + lane;
+  if (n_chunks > 0) load_chunk(0, tid, ICP_THREADS);
+  __syncthreads();
+  for (int c = 0; c < n_chunks; ++c) {
+    if (warp == 0) {
+      if (lane < 15) {
+        const int cnt = max(0, min(ICP_CH, n_lane - c * ICP_CH));
+        const float* a = s_st[c & 1][lane >= 3 && lane < 6 ? 1 : 0] + ia;
+        if (lane < 6) {
 #pragma unroll 8
-    for (int i = 0; i < n_m; ++i) acc = __fadd_rn(acc, p[3 * i]);
-  } else if (lane < 6) {
-    const float* p = pr + (lane - 3);
+          for (int i = 0; i < cnt; ++i) acc = __fadd_rn(acc, a[3 * i]);
+        } else {
+          const float* b = s_st[c & 1][1] + ib;
 #pragma unroll 8
-    for (int i = 0; i < n_r; ++i) acc = __fadd_rn(acc, p[3 * i]);
-  } else if (lane < 15) {
-    const float* a = pm + (lane - 6) / 3;
-    const float* b = pr + (lane - 6) % 3;
-#pragma unroll 8
-    for (int i = 0; i < n_cov; ++i) acc = __fadd_rn(acc, __fmul_rn(a[3 * i], b[3 * i]));
+          for (int i = 0; i < cnt; ++i) acc = __fadd_rn(acc, __fmul_rn(a[3 * i], b[3 * i]));
+        }
+      }
+    } else if (c + 1 < n_chunks) {
+      load_chunk(c + 1, tid - 32, ICP_THREADS - 32);
+    }
+    __syncthreads();
   }
-  return acc;
+  if (warp == 0 && lane < 15) s_sum[lane] = acc;
+  __syncthreads();
 }
 
 __device__ __forceinline__ void matvec3(const float* R, const float* v, float* o) {   // Matx33f * Vec3f: s = 0; s += a*b
@@ -169,6 +194,8 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_prepare(const uint16_t* __r
                                                              const fl_icp_hyp* __restrict__ hyps, fl_icp_ws ws, float* __restrict__ t_init_out) {
   __shared__ int s_warp[ICP_WARPS];
   __shared__ float s_c[6];
+  __shared__ float s_st[2][2][ICP_CH * 3];
+  __shared__ float s_sum[16];
   const int h = blockIdx.x;
   const fl_icp_hyp hy = hyps[h];
   float* pr = ws.pts_ref + (size_t)h * ws.max_pts * 3;
@@ -199,10 +226,8 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_prepare(const uint16_t* __r
     n += tot;
   }
   __syncthreads();
-  if (threadIdx.x < 32) {                                          // getMean x2 (detection.cpp:165-166): ordered fp32 chains
-    float acc = chain15(pm, n, pr, n, 0);
-    if (threadIdx.x < 6) s_c[threadIdx.x] = n > 0 ? __fdiv_rn(acc, (float)n) : 0.f;
-  }
+  block_chain15(pm, n, pr, n, 0, s_st, s_sum);                    // getMean x2 (detection.cpp:165-166): ordered fp32 chains
+  if (threadIdx.x < 6) s_c[threadIdx.x] = n > 0 ? __fdiv_rn(s_sum[threadIdx.x], (float)n) : 0.f;
   __syncthreads();
   float tt[3];
 #pragma unroll
@@ -274,9 +299,11 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_run(fl_icp_ws ws, fl_icp_pa
   __shared__ int s_cnt[FL_ICP_CELLS];          // cell counters, then scatter cursors
   __shared__ float s_red[ICP_WARPS * 4];
   __shared__ float s_sum[16];                  // chain results
+  __shared__ float s_st[2][2][ICP_CH * 3];     // staging of the ordered chains (block_chain15); [.][0] doubles as the distance stage
+  __shared__ int s_cnt2[2];                    // paired-distance counters: {valid pairs, inliers}
   __shared__ float s_Ropt[9], s_Topt[3], s_R[9], s_T[3];
   __shared__ float s_dist_mean, s_dist_diff, s_ratio;
-  __shared__ int s_iter, s_go, s_ncor, s_finite;
+  __shared__ int s_iter, s_go, s_finite;
   __shared__ grid_info s_gi;
   const int h = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_ref = ws.n_ref[h], n_mod = ws.n_mod[h];
@@ -284,7 +311,6 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_run(fl_icp_ws ws, fl_icp_pa
   float* tmp = ws.pts_mod + (size_t)h * ws.max_pts * 3;           // pts_model_tmp
   float* cor_m = ws.cor_m + (size_t)h * ws.max_pts * 3;
   float* cor_r = ws.cor_r + (size_t)h * ws.max_pts * 3;
-  float* dist = ws.dist + (size_t)h * ws.max_pts;
   float4* gp = ws.grid_pts + (size_t)h * ws.max_pts;
   int* cs = ws.cell_start + (size_t)h * (FL_ICP_CELLS + 1);
   fl_icp_result_t* res = results + h;
@@ -357,34 +383,59 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_run(fl_icp_ws ws, fl_icp_pa
   __syncthreads();
   __threadfence_block();
 
-  // per-point paired distance of getL2distClouds (ICP.cpp:68-111); -1 marks a skipped pair (a real distance is >= 0 or NaN)
-  auto paired_distances = [&]() {
-    for (int i = tid; i < n_mod; i += ICP_THREADS) {
-      float d = -1.f;
-      const float rz = pref[3 * i + 2], mz = tmp[3 * i + 2];
-      if (pt_valid(rz) && pt_valid(mz)) {
-        float dx = __fsub_rn(tmp[3 * i], pref[3 * i]), dy = __fsub_rn(tmp[3 * i + 1], pref[3 * i + 1]), dz = __fsub_rn(mz, rz);
-        d = (float)sqrt((double)dx * dx + (double)dy * dy + (double)dz * dz);   // cv::norm(Vec3f) accumulates in double
-      }
-      dist[i] = d;
-    }
-  };
-  // ordered fp32 chain over the distances (one lane); updates dist_mean / ratio exactly like the reference
+  // getL2distClouds (ICP.cpp:68-111): paired distance of every index pair valid in both clouds, inliers = dist <= thr,
+  // dist_mean = (sequential fp32 sum of the inlier distances) / inliers, ratio = inliers / pairs.  The distances are
+  // computed by warps 1..7 one chunk ahead into shared memory while lane 0 of warp 0 walks the previous chunk in order;
+  // the two counters are order free (integer) and are reduced in parallel.  All threads call it; ends with a barrier.
   auto distance_chain = [&](float thr) {
-    if (tid == 0) {
-      float sum = 0.f; int nin = 0, counter = 0;
-#pragma unroll 8
-      for (int i = 0; i < n_mod; ++i) {
-        float d = dist[i];
-        if (!(d < 0.f)) { ++counter; if (d <= thr) { sum = __fadd_rn(sum, d); ++nin; } }
+    float* s_d0 = &s_st[0][0][0];
+    float* s_d1 = &s_st[1][0][0];
+    if (tid < 2) s_cnt2[tid] = 0;
+    const int n_chunks = (n_mod + ICP_CH - 1) / ICP_CH;
+    auto fill_chunk = [&](int c, int t, int nt) {
+      float* dst = (c & 1) ? s_d1 : s_d0;
+      int cnt = 0, nin = 0;
+      for (int k = t; k < ICP_CH; k += nt) {
+        const int i = c * ICP_CH + k;
+        float d = -1.f;                                              // -1 marks a skipped pair (a real distance is >= 0 or NaN)
+        if (i < n_mod) {
+          const float rz = pref[3 * i + 2], mz = tmp[3 * i + 2];
+          if (pt_valid(rz) && pt_valid(mz)) {
+            float dx = __fsub_rn(tmp[3 * i], pref[3 * i]), dy = __fsub_rn(tmp[3 * i + 1], pref[3 * i + 1]), dz = __fsub_rn(mz, rz);
+            d = (float)sqrt((double)dx * dx + (double)dy * dy + (double)dz * dz);   // cv::norm(Vec3f) accumulates in double
+            ++cnt; if (d <= thr) ++nin;
+          }
+        }
+        dst[k] = d;
       }
+      cnt = __reduce_add_sync(0xffffffffu, cnt); nin = __reduce_add_sync(0xffffffffu, nin);
+      if ((threadIdx.x & 31) == 0 && (cnt | nin)) { atomicAdd(&s_cnt2[0], cnt); atomicAdd(&s_cnt2[1], nin); }
+    };
+    __syncthreads();
+    if (n_chunks > 0) fill_chunk(0, tid, ICP_THREADS);
+    __syncthreads();
+    float sum = 0.f;
+    for (int c = 0; c < n_chunks; ++c) {
+      if (warp == 0) {
+        if (lane == 0) {
+          const float* src = (c & 1) ? s_d1 : s_d0;
+          const int cnt = min(ICP_CH, n_mod - c * ICP_CH);
+#pragma unroll 8
+          for (int k = 0; k < cnt; ++k) { const float d = src[k]; if (d >= 0.f && d <= thr) sum = __fadd_rn(sum, d); }
+        }
+      } else if (c + 1 < n_chunks) {
+        fill_chunk(c + 1, tid - 32, ICP_THREADS - 32);
+      }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      const int counter = s_cnt2[0], nin = s_cnt2[1];
       if (counter > 0) { s_dist_mean = __fdiv_rn(sum, (float)nin); s_ratio = __fdiv_rn((float)nin, (float)counter); }
       else { s_dist_mean = FLT_MAX; s_ratio = 0.f; }
     }
+    __syncthreads();
   };
 
-  paired_distances();
-  __syncthreads();
   distance_chain(FLT_MAX);                                          // ICP.cpp:670
   if (tid == 0) { s_dist_diff = FLT_MAX; s_iter = 0; }
   __syncthreads();
@@ -437,11 +488,7 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_run(fl_icp_ws ws, fl_icp_pa
       __syncthreads();
       continue;
     }
-    if (warp == 0) {                                                // centroids + covariance chains (:722-735)
-      float acc = chain15(cm, n_cm, cr, n_cr, n_cm);
-      if (lane < 15) s_sum[lane] = acc;
-    }
-    __syncthreads();
+    block_chain15(cm, n_cm, cr, n_cr, n_cm, s_st, s_sum);           // centroids + covariance chains (:722-735)
     if (tid == 0) {
       float mc[3], rc[3], cov[9], rm[3];
       for (int k = 0; k < 3; ++k) { mc[k] = __fdiv_rn(s_sum[k], (float)n_cm); rc[k] = __fdiv_rn(s_sum[3 + k], (float)n_cr); }
@@ -470,11 +517,8 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_run(fl_icp_ws ws, fl_icp_pa
       }
     }
     __syncthreads();
-    paired_distances();
-    __syncthreads();
     const float old_mean = s_dist_mean;
-    __syncthreads();
-    distance_chain(__fmul_rn(3.f, old_mean));                       // :778-780
+    distance_chain(__fmul_rn(3.f, old_mean));                       // :778-780 (starts with a barrier: every thread has read old_mean)
     if (tid == 0) {
       s_dist_diff = __fsub_rn(old_mean, s_dist_mean);
       float nT[3], nR[9];

@@ -57,6 +57,8 @@ template <bool kDebug>
 __global__ void __launch_bounds__(SG_THREADS) k_similarity_global(fl_tdb db, fl_level_geom g, const uint8_t* __restrict__ lm_level,
                                                                   float threshold, fl_match_t* __restrict__ cand, int cap,
                                                                   int* __restrict__ d_count, int t_debug, uint16_t* __restrict__ dbg) {
+  fl_grid_dep_wait();
+  fl_grid_dep_launch();
   const int t = kDebug ? t_debug : blockIdx.x;
   const int cls = db.class_of[t];
   if (!kDebug && !db.class_enabled[cls]) return;
@@ -115,7 +117,7 @@ __global__ void __launch_bounds__(SG_THREADS) k_similarity_global(fl_tdb db, fl_
 void fl_launch_similarity_global(fl_tdb db, fl_level_geom g, const uint8_t* lm_level, float threshold, fl_match_t* cand, int cap,
                                  int* d_count, cudaStream_t s) {
   if (db.n_templates > 0)
-    k_similarity_global<false><<<db.n_templates, SG_THREADS, 0, s>>>(db, g, lm_level, threshold, cand, cap, d_count, 0, nullptr);
+    fl_launch_pdl(k_similarity_global<false>, dim3(db.n_templates), dim3(SG_THREADS), 0, s, db, g, lm_level, threshold, cand, cap, d_count, 0, (uint16_t*)nullptr);
 }
 void fl_launch_similarity_debug(fl_tdb db, fl_level_geom g, const uint8_t* lm_level, int t, uint16_t* out, cudaStream_t s) {
   k_similarity_global<true><<<1, SG_THREADS, 0, s>>>(db, g, lm_level, 0.f, nullptr, 0, nullptr, t, out);
@@ -131,6 +133,8 @@ void fl_launch_similarity_debug(fl_tdb db, fl_level_geom g, const uint8_t* lm_le
 __global__ void __launch_bounds__(RF_THREADS) k_refine_level(fl_tdb db, fl_level_geom g, int level, const uint8_t* __restrict__ lm_level,
                                                              float threshold, fl_match_t* __restrict__ cand, int cap,
                                                              const int* __restrict__ d_count) {
+  fl_grid_dep_wait();
+  fl_grid_dep_launch();
   const int n = min(*d_count, cap);
   const int fgrp = threadIdx.x >> 6, cell = threadIdx.x & 63;
   const int row = cell >> 2, cg = cell & 3;
@@ -227,7 +231,7 @@ __global__ void __launch_bounds__(RF_THREADS) k_refine_level(fl_tdb db, fl_level
 void fl_launch_refine_level(fl_tdb db, fl_level_geom g, int level, const uint8_t* lm_level, float threshold, fl_match_t* cand,
                             int cap, const int* d_count, cudaStream_t s) {
   int grid = min(cap, 148 * 4);
-  if (grid > 0) k_refine_level<<<grid, RF_THREADS, 0, s>>>(db, g, level, lm_level, threshold, cand, cap, d_count);
+  if (grid > 0) fl_launch_pdl(k_refine_level, dim3(grid), dim3(RF_THREADS), 0, s, db, g, level, lm_level, threshold, cand, cap, d_count);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -288,6 +292,8 @@ __global__ void __launch_bounds__(1024) k_sort_unique_small(const fl_match_t* __
   __shared__ int s_warp[32];
   __shared__ int s_n;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  fl_grid_dep_wait();
+  fl_grid_dep_launch();
   int total = 0;
   for (int l = 0; l < n_lists; ++l) total += min(max(n_in[l], 0), list_cap);
   if (tid < 12) { const int c = tid < n_lists ? n_in[tid] : 0; d_hdr[3 + tid] = c; if (h_hdr) h_hdr[3 + tid] = c; }
@@ -332,7 +338,7 @@ __global__ void __launch_bounds__(1024) k_sort_unique_small(const fl_match_t* __
   if (lane == 31) s_warp[warp] = inc;
   __syncthreads();
   if (warp == 0) {
-    int w = s_warp[lane];
+    int w = lane < (int)(blockDim.x >> 5) ? s_warp[lane] : 0;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
     s_warp[lane] = w;
@@ -404,7 +410,9 @@ __global__ void __launch_bounds__(1024) k_unique_big(const fl_sort_key* __restri
 int fl_launch_sort_unique(const fl_match_t* d_in, int n_lists, int list_cap, const int* d_n_in, int key_cap,
                           fl_match_t* d_out, int out_cap, int* d_out_count, int* d_hdr, int* h_hdr, fl_match_t* h_first, int h_first_cap,
                           cudaStream_t s) {
-  k_sort_unique_small<<<1, 1024, 0, s>>>(d_in, n_lists, list_cap, d_n_in, key_cap, d_out, out_cap, d_out_count, d_hdr, h_hdr, h_first, h_first_cap);
+  // 256 threads: the common case is a few dozen records, where the cost is the ~30 block barriers of the bitonic network
+  fl_launch_pdl(k_sort_unique_small, dim3(1), dim3(256), 0, s, d_in, n_lists, list_cap, d_n_in, key_cap, d_out, out_cap, d_out_count, d_hdr, h_hdr, h_first,
+                h_first_cap);
   return 1;
 }
 

@@ -234,12 +234,15 @@ __global__ void __launch_bounds__(1024, 1) k_similarity_staged(fl_tdb db, fl_lev
       }
     }
     asm volatile("bar.sync 1, %0;" ::"r"(n_cwarps * 32) : "memory");   // consumers only
+    fl_grid_dep_wait();                                       // before the first write to the candidate list / counter
+    fl_grid_dep_launch();
   }
   if (trace && tid == 0) trace[1] = globaltimer();
 
   if (warp == n_cwarps) {
     // ===== producer: one elected lane streams phase q into buffer q % n_buf as soon as every consumer warp of the cluster released it =====
     if (lane == 0) {
+      fl_grid_dep_wait();                                     // the linear memories are written by the previous kernel of the stream
       for (int q = 0; q < n_phases; ++q) {
         const int b = q % n_buf;
         if (q >= n_buf) { if (CL > 1) mbar_wait_cluster(&s_empty[b], ((q / n_buf) - 1) & 1); else mbar_wait(&s_empty[b], ((q / n_buf) - 1) & 1); }
@@ -380,10 +383,12 @@ static int launch_staged_cl(fl_tdb db, fl_level_geom g, const uint8_t* lm_level,
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDim = dim3(plan.n_cta); cfg.blockDim = dim3(plan.block_threads); cfg.dynamicSmemBytes = plan.smem_bytes; cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // prologue (feature lists -> shared memory) overlaps the front end's tail
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = (fl_pdl_enabled() && !plan.trace) ? 2 : 1;
   if (plan.trace) k_stamp<<<1, 1, 0, s>>>(plan.trace + (size_t)plan.n_cta * 8);
   const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, db, g, lm_level, threshold, cand, cap, d_count, plan);
   if (plan.trace) k_stamp<<<1, 1, 0, s>>>(plan.trace + (size_t)plan.n_cta * 8 + 1);

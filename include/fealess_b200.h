@@ -176,6 +176,8 @@ enum {
   FL_DBG_SPREAD = 1,        /* (level, modality)         -> same size u8 (only kept when fl_debug_keep_spread(h,1)) */
   FL_DBG_LINEAR_MEMORY = 2, /* (level, modality, label)  -> T*T*(W/T)*(H/T) u8 */
   FL_DBG_SIMILARITY = 3,    /* (template index)          -> (W/T)*(H/T) u16 total similarity at the coarsest level */
+  FL_DBG_LAST_COUNTS = 5,   /* ()                        -> 16 ints of the last sort+unique: {matches, live candidates after refinement,
+                               multi-kernel-sort flag, raw candidates emitted by the global stage per list (up to 12)} */
   FL_DBG_STAGED_TRACE = 4   /* ()                        -> 8 u64 per CTA of the staged similarity kernel {t_start, t_ready, t_first_data,
                                t_loop_end, t_end (globaltimer ns), smid, 0, 0}; only when the process was started with FL_TRACE=1;
                                returns the number of CTAs */
@@ -192,6 +194,8 @@ int64_t fl_launch_count(fl_handle* h);
 /* per-stage device timing of the last fl_match*(): ms for front end, global similarity, refinement, sort (needs fl_profile(h,1)) */
 int fl_profile(fl_handle* h, int enable);
 int fl_last_stage_ms(fl_handle* h, float out4[4]);
+/* device time (ms) of the two ICP kernels of the last fl_detection_batch / fl_detection (needs fl_profile(h,1)) */
+int fl_last_icp_ms(fl_handle* h, float* ms);
 
 #ifdef __cplusplus
 }
