@@ -63,6 +63,12 @@ class ClockSampler(threading.Thread):
         self.sm_max = None
         self._stop_evt = threading.Event()
         self.err = None
+        self._ready = threading.Event()
+
+    def start_and_wait(self, timeout=5.0):
+        """Start sampling and return once NVML is initialised and the first sample is in (so short timed regions are covered)."""
+        self.start()
+        self._ready.wait(timeout)
 
     def run(self):
         try:
@@ -91,9 +97,11 @@ class ClockSampler(threading.Thread):
                     self.power.append(N.nvmlDeviceGetPowerUsage(hdl) / 1e3)
                 except Exception:
                     pass
+                self._ready.set()
                 time.sleep(self.period)
         except Exception as e:  # noqa: BLE001
             self.err = repr(e)
+            self._ready.set()
 
     def stop(self):
         self._stop_evt.set()
@@ -185,7 +193,7 @@ def run_ours(args):
 
     frames, synth = make_inputs(args.templates)
     n_total = args.templates * world                                   # weak scaling: per-GPU work fixed
-    cap = 1 << 14
+    cap = 2048                                                          # candidate records per rank in the all-gather block (41 KB)
     h = fb.Handle(T, (0, 1), W, H, max_candidates=max(1 << 16, world * (cap + 1) + 16), device=local)
     # quantised images for planting come from the product's own front end (empty template set)
     h.upload_templates(synth.make_templates(0))
@@ -220,7 +228,7 @@ def run_ours(args):
         dist.barrier()
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start_and_wait()
     torch.cuda.synchronize()
     launches0 = h.launch_count()
     evs = []
@@ -256,15 +264,26 @@ def run_ours(args):
     # ---- e2e: host buffers through the C ABI (rank-local; N > 1 adds the host copies to the sharded path) ----
     e2e = None
     if world == 1:
+        # the frames live in page-locked host memory (what a capture pipeline hands over); fl_match DMAs them from there
+        pinned = [(torch.from_numpy(b).pin_memory().numpy(), torch.from_numpy(d.view(np.int16)).pin_memory().numpy().view(np.uint16)) for b, d in frames]
         for i in range(3):
-            h.match(frames[i % N_FRAMES][0], frames[i % N_FRAMES][1], THRESHOLD, capacity=4096)
+            h.match(pinned[i % N_FRAMES][0], pinned[i % N_FRAMES][1], THRESHOLD, capacity=4096)
         t0 = time.perf_counter()
         for i in range(args.steps):
-            b, d = frames[i % N_FRAMES]
+            b, d = pinned[i % N_FRAMES]
             rc, m = h.match(b, d, THRESHOLD, capacity=4096)
         t1 = time.perf_counter()
+        for i in range(5):
+            h.match(frames[i % N_FRAMES][0], frames[i % N_FRAMES][1], THRESHOLD, capacity=4096)
+        tp0 = time.perf_counter()
+        for i in range(min(args.steps, 100)):
+            b, d = frames[i % N_FRAMES]
+            rc, m2 = h.match(b, d, THRESHOLD, capacity=4096)
+        tp1 = time.perf_counter()
         e2e = {"value": evals_per_step * args.steps / (t1 - t0), "unit": "evals/s", "h2d_bytes_per_step": W * H * 5,
-               "d2h_bytes_per_step": 12 + 1024 * 20, "frames_per_s": args.steps / (t1 - t0), "timer": "host wall clock around fl_match"}
+               "d2h_bytes_per_step": 64 + len(m) * 20, "frames_per_s": args.steps / (t1 - t0),
+               "timer": "host wall clock around fl_match (C ABI, host buffers in pinned memory; H2D and result read-back inside)",
+               "frames_per_s_pageable_input": min(args.steps, 100) / (tp1 - tp0)}
     else:
         pin = [(torch.from_numpy(b).pin_memory(), torch.from_numpy(d.view(np.int16)).pin_memory()) for b, d in frames]
         tb, td = d_frames[0]

@@ -42,7 +42,7 @@ ICP_RESULT_DTYPE = np.dtype([("R", "<f4", (9,)), ("T", "<f4", (3,)), ("dist_mean
 EXPORTED_SYMBOLS = [
     "fl_default_params", "fl_create", "fl_destroy", "fl_last_error", "fl_version", "fl_sync", "fl_stream",
     "fl_upload_templates", "fl_set_template_ids", "fl_num_templates", "fl_get_pose_info", "fl_match", "fl_match_device", "fl_match_fetch",
-    "fl_match_shard_device", "fl_sort_unique_device", "fl_depth_to_3d", "fl_icp_cloud_to_cloud_ex",
+    "fl_match_shard_device", "fl_sort_unique_device", "fl_sort_unique_blocks_device", "fl_depth_to_3d", "fl_icp_cloud_to_cloud_ex",
     "fl_detection_batch", "fl_detection", "fl_nms", "fl_nms_ex", "fl_debug_keep_spread", "fl_debug_force_baseline", "fl_debug_uses_staged", "fl_debug_get", "fl_launch_count",
     "fl_profile", "fl_last_stage_ms", "fl_last_icp_ms",
 ]
@@ -225,6 +225,9 @@ class Handle:
                            d_out_count: int) -> None:
         _check(lib().fl_sort_unique_device(self._h, C.c_void_p(d_in), n_lists, list_capacity, C.c_void_p(d_n_in), C.c_void_p(d_out),
                                            out_capacity, C.c_void_p(d_out_count)), "fl_sort_unique_device")
+
+    def sort_unique_blocks_device(self, d_blocks: int, n_blocks: int, capacity: int) -> None:
+        _check(lib().fl_sort_unique_blocks_device(self._h, C.c_void_p(d_blocks), n_blocks, capacity), "fl_sort_unique_blocks_device")
 
     def sync(self):
         _check(lib().fl_sync(self._h), "fl_sync")

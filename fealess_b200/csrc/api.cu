@@ -486,15 +486,14 @@ static int run_match_stages(fl_handle* h, const uint8_t* d_bgr, const uint16_t* 
 
 // sort + unique of candidate lists into (d_out, d_out_count); handles the rare > 2048 path; leaves
 // h_small = {count, n_live, flag, raw list counts...} and, for the handle's own output block, the first matches in h_first
-static int run_sort_unique(fl_handle* h, const fl_match_t* d_in, int n_lists, int list_cap, const int* d_n_in, fl_match_t* d_out, int out_cap,
-                           int* d_out_count, bool fetch_first) {
+static int run_sort_unique(fl_handle* h, fl_lists L, fl_match_t* d_out, int out_cap, int* d_out_count, bool fetch_first) {
   cudaStream_t s = h->stream;
+  const int n_lists = L.n_lists, list_cap = L.list_cap;
   if ((int64_t)n_lists * list_cap > h->key_cap) { fl_set_error("sort capacity %d < %lld", h->key_cap, (long long)n_lists * list_cap); return FL_ERR_CAPACITY; }
   int* d_hdr = reinterpret_cast<int*>(h->d_outblk);
   const bool own = fetch_first && d_out == h->d_out;
   // the kernel itself posts the summary and (own output block) the first matches into the mapped pinned block h_outblk
-  h->launches += fl_launch_sort_unique(d_in, n_lists, list_cap, d_n_in, h->key_cap, d_out, out_cap, d_out_count, d_hdr, h->h_small,
-                                       own ? h->h_first : nullptr, std::min(FETCH_FIRST, out_cap), s);
+  h->launches += fl_launch_sort_unique(L, h->key_cap, d_out, out_cap, d_out_count, d_hdr, h->h_small, own ? h->h_first : nullptr, std::min(FETCH_FIRST, out_cap), s);
   if (h->profile) cudaEventRecord(h->ev[4], s);
   FL_CUDA(cudaStreamSynchronize(s));
   h->overflow = false;
@@ -502,7 +501,7 @@ static int run_sort_unique(fl_handle* h, const fl_match_t* d_in, int n_lists, in
   for (int i = 0; i < std::min(n_lists, 12); ++i) { if (h->h_small[3 + i] > list_cap) h->overflow = true; n_upper += std::min(std::max(h->h_small[3 + i], 0), list_cap); }
   if (n_lists > 12) n_upper = n_lists * list_cap;
   if (h->h_small[2]) {                                                          // more than 2048 records: multi-kernel sort
-    int rc = fl_launch_sort_unique_big(d_in, n_lists, list_cap, d_n_in, h->d_keys, h->key_cap, n_upper, d_out, out_cap, d_out_count, s);
+    int rc = fl_launch_sort_unique_big(L, h->d_keys, h->key_cap, n_upper, d_out, out_cap, d_out_count, s);
     if (rc < 0) return FL_ERR_CAPACITY;
     h->launches += rc;
     FL_CUDA(cudaMemcpyAsync(h->h_small, d_out_count, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -521,7 +520,8 @@ extern "C" int fl_match_device(fl_handle* h, const void* d_bgr, const void* d_de
   h->have_result = false;
   TRY(run_match_stages(h, (const uint8_t*)d_bgr, (const uint16_t*)d_depth, W, H, d_masks, threshold, class_filter, n_filter, h->d_cand,
                        h->p.max_candidates, h->d_count));
-  TRY(run_sort_unique(h, h->d_cand, 1, h->p.max_candidates, h->d_count, h->d_out, h->p.max_candidates, h->d_out_count, true));
+  const fl_lists lists = {h->d_cand, 1, h->p.max_candidates, h->p.max_candidates, h->d_count, 1};
+  TRY(run_sort_unique(h, lists, h->d_out, h->p.max_candidates, h->d_out_count, true));
   h->have_result = true;
   return FL_OK;
 }
@@ -552,17 +552,37 @@ extern "C" int fl_match(fl_handle* h, const uint8_t* bgr, size_t bgr_stride, con
   FL_CUDA(cudaSetDevice(p.device));
   cudaStream_t s = h->stream;
   const uint8_t* d_bgr = nullptr; const uint16_t* d_depth = nullptr;
+  // Frame upload.  A caller buffer that is already page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory) is
+  // DMA'd directly, strided rows included; pageable memory goes through the handle's pinned staging buffer first.
+  auto is_pinned = [](const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+  };
+  if (depth) {                                                                     // depth first: it is the smaller image
+    if (depth_stride < (size_t)W * 2) return FL_ERR_SIZE;
+    if (is_pinned(depth)) {
+      FL_CUDA(cudaMemcpy2DAsync(h->d_in_depth, (size_t)W * 2, depth, depth_stride, (size_t)W * 2, H, cudaMemcpyHostToDevice, s));
+    } else {
+      for (int y = 0; y < H; ++y) memcpy(h->h_depth + (size_t)y * W, (const uint8_t*)depth + (size_t)y * depth_stride, (size_t)W * 2);
+      FL_CUDA(cudaMemcpyAsync(h->d_in_depth, h->h_depth, (size_t)W * H * 2, cudaMemcpyHostToDevice, s));
+    }
+    d_depth = h->d_in_depth;
+  }
   if (bgr) {
     if (bgr_stride < (size_t)W * 3) return FL_ERR_SIZE;
-    for (int y = 0; y < H; ++y) memcpy(h->h_bgr + (size_t)y * W * 3, bgr + (size_t)y * bgr_stride, (size_t)W * 3);
-    FL_CUDA(cudaMemcpyAsync(h->d_in_bgr, h->h_bgr, (size_t)W * H * 3, cudaMemcpyHostToDevice, s));
+    if (is_pinned(bgr)) {
+      FL_CUDA(cudaMemcpy2DAsync(h->d_in_bgr, (size_t)W * 3, bgr, bgr_stride, (size_t)W * 3, H, cudaMemcpyHostToDevice, s));
+    } else {
+      // pageable source: stage in two halves so the second half's host copy overlaps the first half's DMA
+      const int h0 = H / 2;
+      for (int part = 0; part < 2; ++part) {
+        const int y0 = part ? h0 : 0, y1 = part ? H : h0;
+        for (int y = y0; y < y1; ++y) memcpy(h->h_bgr + (size_t)y * W * 3, bgr + (size_t)y * bgr_stride, (size_t)W * 3);
+        if (y1 > y0) FL_CUDA(cudaMemcpyAsync(h->d_in_bgr + (size_t)y0 * W * 3, h->h_bgr + (size_t)y0 * W * 3, (size_t)(y1 - y0) * W * 3, cudaMemcpyHostToDevice, s));
+      }
+    }
     d_bgr = h->d_in_bgr;
-  }
-  if (depth) {
-    if (depth_stride < (size_t)W * 2) return FL_ERR_SIZE;
-    for (int y = 0; y < H; ++y) memcpy(h->h_depth + (size_t)y * W, (const uint8_t*)depth + (size_t)y * depth_stride, (size_t)W * 2);
-    FL_CUDA(cudaMemcpyAsync(h->d_in_depth, h->h_depth, (size_t)W * H * 2, cudaMemcpyHostToDevice, s));
-    d_depth = h->d_in_depth;
   }
   const void* d_masks[FL_MAX_MODALITIES] = {nullptr, nullptr, nullptr, nullptr};
   bool any_mask = false;
@@ -599,7 +619,19 @@ extern "C" int fl_sort_unique_device(fl_handle* h, const fl_match_t* d_in, int32
                                      fl_match_t* d_out, int32_t out_capacity, int32_t* d_out_count) {
   if (!h || !d_in || !d_n_in || !d_out || !d_out_count || n_lists < 1 || list_capacity < 1 || out_capacity < 1) return FL_ERR_ARG;
   FL_CUDA(cudaSetDevice(h->p.device));
-  return run_sort_unique(h, d_in, n_lists, list_capacity, d_n_in, d_out, out_capacity, d_out_count, false);
+  const fl_lists lists = {d_in, n_lists, list_capacity, list_capacity, d_n_in, 1};
+  return run_sort_unique(h, lists, d_out, out_capacity, d_out_count, false);
+}
+
+extern "C" int fl_sort_unique_blocks_device(fl_handle* h, const fl_match_t* d_blocks, int32_t n_blocks, int32_t capacity) {
+  if (!h || !d_blocks || n_blocks < 1 || capacity < 1) return FL_ERR_ARG;
+  FL_CUDA(cudaSetDevice(h->p.device));
+  h->have_result = false;
+  if (h->profile) for (int i = 0; i < 4; ++i) cudaEventRecord(h->ev[i], h->stream);   // stage times are not defined for this entry point
+  const fl_lists lists = {d_blocks + 1, n_blocks, capacity, capacity + 1, reinterpret_cast<const int*>(d_blocks), 5 * (capacity + 1)};
+  TRY(run_sort_unique(h, lists, h->d_out, h->p.max_candidates, h->d_out_count, true));
+  h->have_result = true;
+  return FL_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------

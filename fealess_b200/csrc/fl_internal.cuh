@@ -119,15 +119,17 @@ void fl_launch_similarity_global(fl_tdb db, fl_level_geom g, const uint8_t* lm_l
 void fl_launch_similarity_debug(fl_tdb db, fl_level_geom g, const uint8_t* lm_level, int t, uint16_t* out, cudaStream_t s);
 void fl_launch_refine_level(fl_tdb db, fl_level_geom g, int level, const uint8_t* lm_level, float threshold,
                             fl_match_t* cand, int cap, const int* d_count, cudaStream_t s);
-// sort + unique: n_lists lists of list_cap records at d_in (counts in d_n_in); result in d_out/d_out_count, summary in
-// d_hdr[16] = {unique count, live records, flag_big, raw counts...}.  One launch; when flag_big comes back set the host
-// runs fl_launch_sort_unique_big (key workspace: next_pow2(n_upper) keys + 1 int).  Both return the number of launches.
-// h_hdr / h_first: mapped pinned host copies of the summary and of the first h_first_cap matches (nullable).
-int fl_launch_sort_unique(const fl_match_t* d_in, int n_lists, int list_cap, const int* d_n_in, int key_cap,
-                          fl_match_t* d_out, int out_cap, int* d_out_count, int* d_hdr, int* h_hdr, fl_match_t* h_first, int h_first_cap,
-                          cudaStream_t s);
-int fl_launch_sort_unique_big(const fl_match_t* d_in, int n_lists, int list_cap, const int* d_n_in, fl_sort_key* keys, int key_cap,
-                              int n_upper, fl_match_t* d_out, int out_cap, int* d_out_count, cudaStream_t s);
+// candidate lists handed to sort + unique: list l holds min(n_in[l * n_in_stride], list_cap) records starting at
+// in + l * list_stride.  (list_stride = list_cap, n_in_stride = 1 for plain arrays; the all-gather block layout
+// [header record with the count in .x | list_cap records] has list_stride = list_cap + 1, n_in_stride = 5 * (list_cap + 1).)
+struct fl_lists { const fl_match_t* in; int n_lists, list_cap, list_stride; const int* n_in; int n_in_stride; };
+// sort + unique: result in d_out/d_out_count, summary in d_hdr[16] = {unique count, live records, flag_big, raw counts...}.
+// One launch; when flag_big comes back set the host runs fl_launch_sort_unique_big (key workspace: next_pow2(n_upper) keys
+// + 1 int).  Both return the number of launches.  h_hdr / h_first: mapped pinned host copies of the summary and of the
+// first h_first_cap matches (nullable).
+int fl_launch_sort_unique(fl_lists L, int key_cap, fl_match_t* d_out, int out_cap, int* d_out_count, int* d_hdr, int* h_hdr, fl_match_t* h_first,
+                          int h_first_cap, cudaStream_t s);
+int fl_launch_sort_unique_big(fl_lists L, fl_sort_key* keys, int key_cap, int n_upper, fl_match_t* d_out, int out_cap, int* d_out_count, cudaStream_t s);
 
 // ---- ICP (icp.cu) --------------------------------------------------------------------------------
 struct fl_icp_hyp {                 // one hypothesis of a batch, device-visible

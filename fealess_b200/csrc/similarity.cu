@@ -263,15 +263,13 @@ __device__ __forceinline__ bool key_dup(const fl_sort_key& a, const fl_sort_key&
 #define KEY_SENTINEL_HI 0xFFFFFFFFFFFFFFFFull
 
 // gather live candidates of all lists into the key array [0, n_pad), sentinel-padded; *d_n_live = number of live keys
-__global__ void __launch_bounds__(256) k_build_keys(const fl_match_t* __restrict__ in, int n_lists, int list_cap,
-                                                    const int* __restrict__ n_in, fl_sort_key* __restrict__ keys, int key_cap,
-                                                    int* __restrict__ d_n_live) {
+__global__ void __launch_bounds__(256) k_build_keys(fl_lists L, fl_sort_key* __restrict__ keys, int key_cap, int* __restrict__ d_n_live) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_lists * list_cap) return;
-  int l = i / list_cap, k = i - l * list_cap;
-  int n = min(n_in[l], list_cap);
+  if (i >= L.n_lists * L.list_cap) return;
+  int l = i / L.list_cap, k = i - l * L.list_cap;
+  int n = min(L.n_in[(size_t)l * L.n_in_stride], L.list_cap);
   if (k >= n) return;
-  fl_match_t m = in[i];
+  fl_match_t m = L.in[(size_t)l * L.list_stride + k];
   if (m.template_id < 0) return;
   int slot = atomicAdd(d_n_live, 1);
   if (slot < key_cap) keys[slot] = make_key(m);
@@ -281,8 +279,7 @@ __global__ void __launch_bounds__(256) k_build_keys(const fl_match_t* __restrict
 // Common case, ONE launch of one CTA: gather the live candidates of all lists, sort, prune duplicates.  When the lists hold
 // more than SORT_SMEM_N records it only sets *d_flag_big = 1 and the host runs the multi-kernel path (k_build_keys + global
 // bitonic steps + k_unique_big).  d_scratch = {n_live, flag_big}.
-__global__ void __launch_bounds__(1024) k_sort_unique_small(const fl_match_t* __restrict__ in, int n_lists, int list_cap,
-                                                            const int* __restrict__ n_in, int key_cap, fl_match_t* __restrict__ out,
+__global__ void __launch_bounds__(1024) k_sort_unique_small(fl_lists L, int key_cap, fl_match_t* __restrict__ out,
                                                             int out_cap, int* __restrict__ d_out_count, int* __restrict__ d_hdr,
                                                             int* __restrict__ h_hdr, fl_match_t* __restrict__ h_first, int h_first_cap) {
   // d_hdr (16 ints, handle-owned) = {unique count, n_live, flag_big, raw n_in[0..11]}.  h_hdr / h_first (nullable) are the
@@ -294,9 +291,10 @@ __global__ void __launch_bounds__(1024) k_sort_unique_small(const fl_match_t* __
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   fl_grid_dep_wait();
   fl_grid_dep_launch();
+  const int n_lists = L.n_lists, list_cap = L.list_cap;
   int total = 0;
-  for (int l = 0; l < n_lists; ++l) total += min(max(n_in[l], 0), list_cap);
-  if (tid < 12) { const int c = tid < n_lists ? n_in[tid] : 0; d_hdr[3 + tid] = c; if (h_hdr) h_hdr[3 + tid] = c; }
+  for (int l = 0; l < n_lists; ++l) total += min(max(L.n_in[(size_t)l * L.n_in_stride], 0), list_cap);
+  if (tid < 12) { const int c = tid < n_lists ? L.n_in[(size_t)tid * L.n_in_stride] : 0; d_hdr[3 + tid] = c; if (h_hdr) h_hdr[3 + tid] = c; }
   if (total > SORT_SMEM_N || total > key_cap) {
     if (tid == 0) { d_hdr[0] = 0; d_hdr[1] = total; d_hdr[2] = 1; if (h_hdr) { h_hdr[0] = 0; h_hdr[1] = total; h_hdr[2] = 1; } }
     return;
@@ -305,8 +303,8 @@ __global__ void __launch_bounds__(1024) k_sort_unique_small(const fl_match_t* __
   __syncthreads();
   for (int i = tid; i < total; i += blockDim.x) {
     int l = 0, k = i;
-    for (;;) { const int c = min(max(n_in[l], 0), list_cap); if (k < c) break; k -= c; ++l; }
-    const fl_match_t m = in[(size_t)l * list_cap + k];
+    for (;;) { const int c = min(max(L.n_in[(size_t)l * L.n_in_stride], 0), list_cap); if (k < c) break; k -= c; ++l; }
+    const fl_match_t m = L.in[(size_t)l * L.list_stride + k];
     if (m.template_id >= 0) s_k[atomicAdd(&s_n, 1)] = make_key(m);          // dropped candidates carry template_id -1
   }
   __syncthreads();
@@ -407,24 +405,21 @@ __global__ void __launch_bounds__(1024) k_unique_big(const fl_sort_key* __restri
 }
 
 // Host orchestration.  Scratch int (n_live of the big path) lives right after the key array.
-int fl_launch_sort_unique(const fl_match_t* d_in, int n_lists, int list_cap, const int* d_n_in, int key_cap,
-                          fl_match_t* d_out, int out_cap, int* d_out_count, int* d_hdr, int* h_hdr, fl_match_t* h_first, int h_first_cap,
-                          cudaStream_t s) {
+int fl_launch_sort_unique(fl_lists L, int key_cap, fl_match_t* d_out, int out_cap, int* d_out_count, int* d_hdr, int* h_hdr, fl_match_t* h_first,
+                          int h_first_cap, cudaStream_t s) {
   // 256 threads: the common case is a few dozen records, where the cost is the ~30 block barriers of the bitonic network
-  fl_launch_pdl(k_sort_unique_small, dim3(1), dim3(256), 0, s, d_in, n_lists, list_cap, d_n_in, key_cap, d_out, out_cap, d_out_count, d_hdr, h_hdr, h_first,
-                h_first_cap);
+  fl_launch_pdl(k_sort_unique_small, dim3(1), dim3(256), 0, s, L, key_cap, d_out, out_cap, d_out_count, d_hdr, h_hdr, h_first, h_first_cap);
   return 1;
 }
 
 // second stage, only when the small kernel reported more than SORT_SMEM_N records (the host has read the flag and the
 // record count n_upper)
-int fl_launch_sort_unique_big(const fl_match_t* d_in, int n_lists, int list_cap, const int* d_n_in, fl_sort_key* keys, int key_cap,
-                              int n_upper, fl_match_t* d_out, int out_cap, int* d_out_count, cudaStream_t s) {
+int fl_launch_sort_unique_big(fl_lists L, fl_sort_key* keys, int key_cap, int n_upper, fl_match_t* d_out, int out_cap, int* d_out_count, cudaStream_t s) {
   int launches = 0;
   int* d_scratch = reinterpret_cast<int*>(keys + key_cap);
   cudaMemsetAsync(d_scratch, 0, sizeof(int), s);
-  const int total = n_lists * list_cap;
-  k_build_keys<<<(total + 255) / 256, 256, 0, s>>>(d_in, n_lists, list_cap, d_n_in, keys, key_cap, d_scratch); ++launches;
+  const int total = L.n_lists * L.list_cap;
+  k_build_keys<<<(total + 255) / 256, 256, 0, s>>>(L, keys, key_cap, d_scratch); ++launches;
   int n_pad = 2;
   while (n_pad < n_upper) n_pad <<= 1;
   if (n_pad > key_cap) return -1;

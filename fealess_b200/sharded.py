@@ -82,9 +82,11 @@ def merge_on_host(gathered_np: np.ndarray) -> np.ndarray:
 
 class ShardedMatcher:
     """One rank of a template-sharded detector.  ``match_device`` = front end + matchClass on the local shard,
-    all-gather of candidate blocks over NCCL (NVLink / NVSwitch), sort + unique of the union on every rank."""
+    ONE all-gather of candidate blocks over NCCL (NVLink / NVSwitch), sort + unique of the union on every rank.  The
+    block layout ``[header | records]`` is consumed as it is by ``fl_sort_unique_blocks_device``: between the collective and
+    the sort there is no copy, no count extraction, no other kernel."""
 
-    def __init__(self, handle, tset, rank: int, world: int, capacity: int = 1 << 14, device=None):
+    def __init__(self, handle, tset, rank: int, world: int, capacity: int = 2048, device=None):
         import torch
         self.h, self.rank, self.world, self.cap = handle, rank, world, capacity
         shard, gids = shard_template_set(tset, rank, world)
@@ -93,31 +95,24 @@ class ShardedMatcher:
         self.n_local = shard.n_templates
         dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.block = torch.zeros(block_ints(capacity), dtype=torch.int32, device=dev)
-        self.out = torch.zeros(world * capacity * RECORD_INTS, dtype=torch.int32, device=dev)
-        self.out_count = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.gathered = torch.zeros(world * block_ints(capacity), dtype=torch.int32, device=dev)
         self.stream = torch.cuda.ExternalStream(handle.stream_ptr(), device=dev)
         self._torch = torch
 
-    def match_device(self, d_bgr: int, d_depth: int, W: int, H: int, threshold: float):
-        """Enqueue one frame.  Returns (out_records tensor [world*cap, 5] int32, out_count tensor) on the device."""
+    def match_device(self, d_bgr: int, d_depth: int, W: int, H: int, threshold: float) -> None:
+        """One frame: enqueue the local match, the all-gather and the merge on the handle's stream; returns when the merged
+        match list is ready (``fetch``)."""
         torch = self._torch
+        import torch.distributed as dist
         recs = records_view(self.block)
         # the count lives in the header record of the block, so the candidates + count travel in one collective
         self.h.match_shard_device(d_bgr, d_depth, W, H, threshold, recs.data_ptr(), self.cap, self.block.data_ptr())
         with torch.cuda.stream(self.stream):
-            gathered = gather_blocks(self.block, self.world)
-            counts, _ = split_blocks(gathered)
-            counts = counts.clamp(max=self.cap)          # a shard that overflowed reports more than it stored
-            self._keep = (gathered, counts)
-            # lists are `cap + 1` records apart inside `gathered`; pass the first record of list 0 and that stride
-            base = gathered.data_ptr() + RECORD_INTS * 4
-            self.h.sort_unique_device(base, self.world, self.cap + 1, counts.data_ptr(), self.out.data_ptr(),
-                                      self.world * self.cap, self.out_count.data_ptr())
-        return self.out.view(-1, RECORD_INTS), self.out_count
+            if self.world == 1 or not dist.is_initialized():
+                self.gathered.copy_(self.block)
+            else:
+                dist.all_gather_into_tensor(self.gathered, self.block)
+        self.h.sort_unique_blocks_device(self.gathered.data_ptr(), self.world, self.cap)
 
     def fetch(self) -> np.ndarray:
-        from . import MATCH_DTYPE
-        self.h.sync()
-        n = int(self.out_count[0].item())
-        a = self.out.view(-1, RECORD_INTS)[:n].cpu().numpy()
-        return np.ascontiguousarray(a).view(MATCH_DTYPE).reshape(-1)
+        return self.h.match_fetch()

@@ -143,6 +143,13 @@ int fl_match_shard_device(fl_handle* h, const void* d_bgr, const void* d_depth, 
 int fl_sort_unique_device(fl_handle* h, const fl_match_t* d_in, int32_t n_lists, int32_t list_capacity,
                           const int32_t* d_n_in, fl_match_t* d_out, int32_t out_capacity, int32_t* d_out_count);
 
+/* The all-gather layout of template-sharded matching: n_blocks blocks of (capacity + 1) records each, block b =
+ * [header record whose .x is the number of candidates of rank b | capacity candidate records] (what
+ * fl_match_shard_device produces when d_count points at the header of the caller's block and d_candidates at the record
+ * behind it).  Sorts + prunes the union into the handle's own result buffer and synchronises; read the matches with
+ * fl_match_fetch.  No intermediate copies or count extraction are needed between the collective and this call. */
+int fl_sort_unique_blocks_device(fl_handle* h, const fl_match_t* d_blocks, int32_t n_blocks, int32_t capacity);
+
 /* ---- ICP ------------------------------------------------------------------------------------------ */
 /* cup_d2pc::depthTo3d for 16UC1 input: out3 = H*W*3 floats in METRES, 0 depth -> NaN (depth_to_3d.cpp:99-137, 244-260) */
 int fl_depth_to_3d(fl_handle* h, const uint16_t* depth, size_t depth_stride, int32_t W, int32_t H,

@@ -316,3 +316,41 @@ def test_reference_facing_detector_mirror():
     rc, only = D.match([b, d], 75.0, class_ids=["obj01", "nope"])
     assert rc == 0 and all(m.class_id == "obj01" for m in only)
     assert len(only) == len(det.match(75.0, class_filter=[1]))
+
+
+def test_two_rank_gather_layout_on_one_gpu():
+    """The multi-GPU data path with the collective replaced by a concatenation: two handles hold the two template shards,
+    each writes its candidate block [header | records]; the blocks laid out as all_gather_into_tensor would lay them out
+    are merged by fl_sort_unique_blocks_device and must equal the single-handle result and the oracle."""
+    import torch
+    from fealess_b200 import sharded
+    W, H, T = 640, 480, (5, 8)
+    b, d = synth.make_frame(W, H, 3)
+    det = _oracle(b, d)
+    q = [det.quantized(l, m) for l in range(2) for m in range(2)]
+    ts = synth.make_templates(700, W, H, T, n_classes=3, seed=41, quantized=q, planted_fraction=0.05)
+    det.set_templates(ts)
+    want = det.match(65.0)
+    assert len(want) > 0
+    tb = torch.from_numpy(b).cuda()
+    td = torch.from_numpy(d.view(np.int16)).cuda()
+    cap = 512
+    blocks = torch.zeros(2 * sharded.block_ints(cap), dtype=torch.int32, device="cuda")
+    handles = []
+    for r in range(2):
+        sh, gids = sharded.shard_template_set(ts, r, 2)
+        hs = fb.Handle(T, (0, 1), W, H)
+        hs.upload_templates(sh)
+        hs.set_template_ids(gids)
+        blk = blocks[r * sharded.block_ints(cap):(r + 1) * sharded.block_ints(cap)]
+        torch.cuda.synchronize()
+        hs.match_shard_device(tb.data_ptr(), td.data_ptr(), W, H, 65.0, sharded.records_view(blk).data_ptr(), cap, blk.data_ptr())
+        hs.sync()
+        handles.append(hs)
+    counts = blocks.view(2, -1)[:, 0].cpu().numpy()
+    assert counts.sum() >= len(want) and counts.max() <= cap
+    handles[0].sort_unique_blocks_device(blocks.data_ptr(), 2, cap)
+    got = handles[0].match_fetch()
+    assert np.array_equal(got, want)
+    for hs in handles:
+        hs.close()
