@@ -200,7 +200,7 @@ def run_ours(args):
     rc, _, q = h.match(frames[0][0], frames[0][1], THRESHOLD, want_quantized=True)
     assert rc == 0
     tset = synth.make_templates(n_total, W, H, T, seed=1, quantized=q, planted_fraction=0.01)
-    sm = sharded.ShardedMatcher(h, tset, rank, world, capacity=cap, device=dev)
+    sm = sharded.ShardedMatcher(h, tset, rank, world, capacity=cap, device=dev, exchange=args.exchange)
     stream = sm.stream
     d_frames = [(torch.from_numpy(b).to(dev), torch.from_numpy(d.view(np.int16)).to(dev)) for b, d in frames]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
@@ -232,16 +232,24 @@ def run_ours(args):
     torch.cuda.synchronize()
     launches0 = h.launch_count()
     evs = []
+    import gc
+    gc.collect()
+    gc.disable()                                                        # no collector pauses inside the timed region
     wall0 = time.perf_counter()
     for i in range(args.steps):
         evs.append(step(args.warmup + i, True))
     torch.cuda.synchronize()
+    gc.enable()
     if world > 1:
         dist.barrier()
     wall1 = time.perf_counter()
     launches = h.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
-    dev_ms = float(sum(a.elapsed_time(b) for a, b in evs))
+    per_step = np.array([a.elapsed_time(b) for a, b in evs])
+    if args.per_step:
+        sys.stderr.write("rank %d per-step device ms: p10 %.4f p50 %.4f p90 %.4f max %.4f mean %.4f\n"
+                         % (rank, *np.percentile(per_step, [10, 50, 90]), per_step.max(), per_step.mean()))
+    dev_ms = float(per_step.sum())
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -350,7 +358,7 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": "C2: LINE-MOD match-only, 640x480, %d templates per GPU (%d total), L=2, T={5,8}, threshold 75" % (args.templates, n_total),
                        "l2": "flushed between steps (256 MB write)", "frames_per_s": args.steps / (dev_ms * 1e-3),
-                       "matches_last_frame": n_matches, "parallelism": "template-sharded x%d, 1 all-gather/frame" % world if world > 1 else "single GPU"},
+                       "matches_last_frame": n_matches, "parallelism": ("template-sharded x%d, candidate exchange: %s" % (world, "peer-memory push fused into the sort kernel (NVLink)" if sm.exchange == "p2p" else "1 NCCL all-gather/frame")) if world > 1 else "single GPU"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "wall_s_timed_region": wall1 - wall0}
     line.update(extra)
@@ -421,6 +429,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--templates", type=int, default=8000, help="templates per GPU")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"], help="candidate exchange of the template-sharded path (N > 1)")
+    ap.add_argument("--per-step", action="store_true", help="print the distribution of per-step device times of every rank to stderr")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-icp", action="store_true", help="skip the ICP side benchmark")
     args = ap.parse_args()

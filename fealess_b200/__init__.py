@@ -42,7 +42,7 @@ ICP_RESULT_DTYPE = np.dtype([("R", "<f4", (9,)), ("T", "<f4", (3,)), ("dist_mean
 EXPORTED_SYMBOLS = [
     "fl_default_params", "fl_create", "fl_destroy", "fl_last_error", "fl_version", "fl_sync", "fl_stream",
     "fl_upload_templates", "fl_set_template_ids", "fl_num_templates", "fl_get_pose_info", "fl_match", "fl_match_device", "fl_match_fetch",
-    "fl_match_shard_device", "fl_sort_unique_device", "fl_sort_unique_blocks_device", "fl_depth_to_3d", "fl_icp_cloud_to_cloud_ex",
+    "fl_match_shard_device", "fl_sort_unique_device", "fl_sort_unique_blocks_device", "fl_exchange_buffer_bytes", "fl_exchange_sort_unique_device", "fl_depth_to_3d", "fl_icp_cloud_to_cloud_ex",
     "fl_detection_batch", "fl_detection", "fl_nms", "fl_nms_ex", "fl_debug_keep_spread", "fl_debug_force_baseline", "fl_debug_uses_staged", "fl_debug_get", "fl_launch_count",
     "fl_profile", "fl_last_stage_ms", "fl_last_icp_ms",
 ]
@@ -93,6 +93,7 @@ def lib():
         L.fl_launch_count.restype = C.c_int64
         L.fl_stream.argtypes = [C.c_void_p]
         L.fl_launch_count.argtypes = [C.c_void_p]
+        L.fl_exchange_buffer_bytes.restype = C.c_size_t
         _lib = L
     return _lib
 
@@ -228,6 +229,11 @@ class Handle:
 
     def sort_unique_blocks_device(self, d_blocks: int, n_blocks: int, capacity: int) -> None:
         _check(lib().fl_sort_unique_blocks_device(self._h, C.c_void_p(d_blocks), n_blocks, capacity), "fl_sort_unique_blocks_device")
+
+    def exchange_sort_unique_device(self, rank: int, world: int, peer_buffers: Sequence[int], capacity: int, d_local_block: int, epoch: int) -> None:
+        arr = (C.c_void_p * world)(*[int(p) for p in peer_buffers])
+        _check(lib().fl_exchange_sort_unique_device(self._h, rank, world, arr, capacity, C.c_void_p(d_local_block), C.c_uint32(epoch)),
+               "fl_exchange_sort_unique_device")
 
     def sync(self):
         _check(lib().fl_sync(self._h), "fl_sync")

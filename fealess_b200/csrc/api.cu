@@ -486,14 +486,17 @@ static int run_match_stages(fl_handle* h, const uint8_t* d_bgr, const uint16_t* 
 
 // sort + unique of candidate lists into (d_out, d_out_count); handles the rare > 2048 path; leaves
 // h_small = {count, n_live, flag, raw list counts...} and, for the handle's own output block, the first matches in h_first
-static int run_sort_unique(fl_handle* h, fl_lists L, fl_match_t* d_out, int out_cap, int* d_out_count, bool fetch_first) {
+static int run_sort_unique(fl_handle* h, fl_lists L, fl_match_t* d_out, int out_cap, int* d_out_count, bool fetch_first, const fl_xchg* xchg = nullptr) {
   cudaStream_t s = h->stream;
   const int n_lists = L.n_lists, list_cap = L.list_cap;
   if ((int64_t)n_lists * list_cap > h->key_cap) { fl_set_error("sort capacity %d < %lld", h->key_cap, (long long)n_lists * list_cap); return FL_ERR_CAPACITY; }
   int* d_hdr = reinterpret_cast<int*>(h->d_outblk);
   const bool own = fetch_first && d_out == h->d_out;
   // the kernel itself posts the summary and (own output block) the first matches into the mapped pinned block h_outblk
-  h->launches += fl_launch_sort_unique(L, h->key_cap, d_out, out_cap, d_out_count, d_hdr, h->h_small, own ? h->h_first : nullptr, std::min(FETCH_FIRST, out_cap), s);
+  fl_xchg X;
+  memset(&X, 0, sizeof X);
+  if (xchg) X = *xchg;
+  h->launches += fl_launch_sort_unique(L, X, h->key_cap, d_out, out_cap, d_out_count, d_hdr, h->h_small, own ? h->h_first : nullptr, std::min(FETCH_FIRST, out_cap), s);
   if (h->profile) cudaEventRecord(h->ev[4], s);
   FL_CUDA(cudaStreamSynchronize(s));
   h->overflow = false;
@@ -621,6 +624,30 @@ extern "C" int fl_sort_unique_device(fl_handle* h, const fl_match_t* d_in, int32
   FL_CUDA(cudaSetDevice(h->p.device));
   const fl_lists lists = {d_in, n_lists, list_capacity, list_capacity, d_n_in, 1};
   return run_sort_unique(h, lists, d_out, out_capacity, d_out_count, false);
+}
+
+extern "C" size_t fl_exchange_buffer_bytes(int32_t world, int32_t capacity) {
+  if (world < 1 || capacity < 1) return 0;
+  return FL_XCHG_SIGNALS * sizeof(unsigned) + (size_t)2 * world * ((size_t)capacity + 1) * sizeof(fl_match_t);
+}
+
+extern "C" int fl_exchange_sort_unique_device(fl_handle* h, int32_t rank, int32_t world, void* const* peer_buffers, int32_t capacity,
+                                              const fl_match_t* d_local_block, uint32_t epoch) {
+  if (!h || !peer_buffers || !d_local_block || world < 1 || world > FL_XCHG_MAX_WORLD || rank < 0 || rank >= world || capacity < 1 || epoch == 0) return FL_ERR_ARG;
+  FL_CUDA(cudaSetDevice(h->p.device));
+  h->have_result = false;
+  if (h->profile) for (int i = 0; i < 4; ++i) cudaEventRecord(h->ev[i], h->stream);
+  fl_xchg X;
+  memset(&X, 0, sizeof X);
+  X.world = world; X.rank = rank; X.cap = capacity; X.epoch = epoch; X.local_block = d_local_block;
+  for (int p = 0; p < world; ++p) { if (!peer_buffers[p]) return FL_ERR_ARG; X.peer[p] = static_cast<uint8_t*>(peer_buffers[p]); }
+  // the lists the multi-kernel fallback would read: this rank's own buffer, parity of this epoch (filled by the kernel's exchange)
+  const uint8_t* own = X.peer[rank] + FL_XCHG_SIGNALS * sizeof(unsigned) + (size_t)(epoch & 1u) * world * ((size_t)capacity + 1) * sizeof(fl_match_t);
+  const fl_lists lists = {reinterpret_cast<const fl_match_t*>(own) + 1, world, capacity, capacity + 1, reinterpret_cast<const int*>(own), 5 * (capacity + 1)};
+  TRY(run_sort_unique(h, lists, h->d_out, h->p.max_candidates, h->d_out_count, true, &X));
+  if (h->h_small[15]) { fl_set_error("peer exchange timed out waiting for rank %d", h->h_small[15] - 1); return FL_ERR_STATE; }
+  h->have_result = true;
+  return FL_OK;
 }
 
 extern "C" int fl_sort_unique_blocks_device(fl_handle* h, const fl_match_t* d_blocks, int32_t n_blocks, int32_t capacity) {

@@ -123,12 +123,24 @@ void fl_launch_refine_level(fl_tdb db, fl_level_geom g, int level, const uint8_t
 // in + l * list_stride.  (list_stride = list_cap, n_in_stride = 1 for plain arrays; the all-gather block layout
 // [header record with the count in .x | list_cap records] has list_stride = list_cap + 1, n_in_stride = 5 * (list_cap + 1).)
 struct fl_lists { const fl_match_t* in; int n_lists, list_cap, list_stride; const int* n_in; int n_in_stride; };
+// Direct peer exchange fused into the head of the sort kernel (template-sharded matching, one process per GPU): every rank's
+// exchange buffer = [FL_XCHG_SIGNALS u32 signal words][2 parities x world blocks of (cap + 1) records] is mapped into every
+// process (peer[p] = base of rank p's buffer as seen from THIS process).  The kernel pushes this rank's block
+// [count | live records] into slot `rank` of every peer's buffer over NVLink, publishes `epoch` in the peer's signal word
+// `rank` (release, system scope), waits until all of its own signal words show `epoch` (acquire), and then sorts the
+// union straight out of its own buffer.  world == 0: no exchange.  The parity (epoch & 1) double-buffers the blocks: a rank
+// can be at most one frame ahead of a peer, because it cannot pass frame k + 1's wait before the peer has published
+// epoch k + 1, which the peer's stream does only after its frame-k sort kernel has finished.
+#define FL_XCHG_MAX_WORLD 8
+#define FL_XCHG_SIGNALS 64
+struct fl_xchg { int world, rank, cap; unsigned epoch; const fl_match_t* local_block; uint8_t* peer[FL_XCHG_MAX_WORLD]; };
+
 // sort + unique: result in d_out/d_out_count, summary in d_hdr[16] = {unique count, live records, flag_big, raw counts...}.
 // One launch; when flag_big comes back set the host runs fl_launch_sort_unique_big (key workspace: next_pow2(n_upper) keys
 // + 1 int).  Both return the number of launches.  h_hdr / h_first: mapped pinned host copies of the summary and of the
 // first h_first_cap matches (nullable).
-int fl_launch_sort_unique(fl_lists L, int key_cap, fl_match_t* d_out, int out_cap, int* d_out_count, int* d_hdr, int* h_hdr, fl_match_t* h_first,
-                          int h_first_cap, cudaStream_t s);
+int fl_launch_sort_unique(fl_lists L, fl_xchg X, int key_cap, fl_match_t* d_out, int out_cap, int* d_out_count, int* d_hdr, int* h_hdr,
+                          fl_match_t* h_first, int h_first_cap, cudaStream_t s);
 int fl_launch_sort_unique_big(fl_lists L, fl_sort_key* keys, int key_cap, int n_upper, fl_match_t* d_out, int out_cap, int* d_out_count, cudaStream_t s);
 
 // ---- ICP (icp.cu) --------------------------------------------------------------------------------

@@ -279,7 +279,10 @@ __global__ void __launch_bounds__(256) k_build_keys(fl_lists L, fl_sort_key* __r
 // Common case, ONE launch of one CTA: gather the live candidates of all lists, sort, prune duplicates.  When the lists hold
 // more than SORT_SMEM_N records it only sets *d_flag_big = 1 and the host runs the multi-kernel path (k_build_keys + global
 // bitonic steps + k_unique_big).  d_scratch = {n_live, flag_big}.
-__global__ void __launch_bounds__(1024) k_sort_unique_small(fl_lists L, int key_cap, fl_match_t* __restrict__ out,
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) { unsigned v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+
+__global__ void __launch_bounds__(1024) k_sort_unique_small(fl_lists L, fl_xchg X, int key_cap, fl_match_t* __restrict__ out,
                                                             int out_cap, int* __restrict__ d_out_count, int* __restrict__ d_hdr,
                                                             int* __restrict__ h_hdr, fl_match_t* __restrict__ h_first, int h_first_cap) {
   // d_hdr (16 ints, handle-owned) = {unique count, n_live, flag_big, raw n_in[0..11]}.  h_hdr / h_first (nullable) are the
@@ -291,12 +294,45 @@ __global__ void __launch_bounds__(1024) k_sort_unique_small(fl_lists L, int key_
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   fl_grid_dep_wait();
   fl_grid_dep_launch();
+  if (tid == 0) d_hdr[15] = 0;                                   // exchange time-out flag (1 + rank that never arrived)
+  __syncthreads();
+  unsigned long long t_dbg[4] = {0, 0, 0, 0};
+  if (X.world > 0) {
+    // ---- peer exchange (see fl_xchg): push, publish, wait ----
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_dbg[0]));
+    const size_t block_recs = (size_t)X.cap + 1;
+    const size_t parity_off = FL_XCHG_SIGNALS * sizeof(unsigned) + (size_t)(X.epoch & 1u) * X.world * block_recs * sizeof(fl_match_t);
+    const int* src = reinterpret_cast<const int*>(X.local_block);
+    const int n_local = min(max(src[0], 0), X.cap);
+    const int n_ints = 5 * (1 + n_local);                       // header record + live part of the list
+    for (int p = 0; p < X.world; ++p) {
+      int* dst = reinterpret_cast<int*>(X.peer[p] + parity_off + (size_t)X.rank * block_recs * sizeof(fl_match_t));
+      for (int i = tid; i < n_ints; i += blockDim.x) dst[i] = (i == 0) ? n_local : src[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_dbg[1]));
+    if (tid < X.world) st_release_sys(reinterpret_cast<unsigned*>(X.peer[tid]) + X.rank, X.epoch);
+    if (tid < X.world) {
+      const unsigned* sig = reinterpret_cast<const unsigned*>(X.peer[X.rank]) + tid;
+      const long long t0 = clock64();
+      while ((int)(ld_acquire_sys(sig) - X.epoch) < 0) {
+        if (clock64() - t0 > (1ll << 32)) { d_hdr[15] = 1 + tid; break; }   // ~2 s: a peer never arrived; report instead of hanging
+        __nanosleep(64);
+      }
+    }
+    __syncthreads();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_dbg[2]));
+    L.in = reinterpret_cast<const fl_match_t*>(X.peer[X.rank] + parity_off) + 1;
+    L.n_in = reinterpret_cast<const int*>(X.peer[X.rank] + parity_off);
+    L.n_lists = X.world; L.list_cap = X.cap; L.list_stride = X.cap + 1; L.n_in_stride = 5 * (X.cap + 1);
+  }
   const int n_lists = L.n_lists, list_cap = L.list_cap;
   int total = 0;
   for (int l = 0; l < n_lists; ++l) total += min(max(L.n_in[(size_t)l * L.n_in_stride], 0), list_cap);
   if (tid < 12) { const int c = tid < n_lists ? L.n_in[(size_t)tid * L.n_in_stride] : 0; d_hdr[3 + tid] = c; if (h_hdr) h_hdr[3 + tid] = c; }
   if (total > SORT_SMEM_N || total > key_cap) {
-    if (tid == 0) { d_hdr[0] = 0; d_hdr[1] = total; d_hdr[2] = 1; if (h_hdr) { h_hdr[0] = 0; h_hdr[1] = total; h_hdr[2] = 1; } }
+    if (tid == 0) { d_hdr[0] = 0; d_hdr[1] = total; d_hdr[2] = 1; if (h_hdr) { h_hdr[0] = 0; h_hdr[1] = total; h_hdr[2] = 1; h_hdr[15] = d_hdr[15]; } }
     return;
   }
   if (tid == 0) s_n = 0;
@@ -352,7 +388,11 @@ __global__ void __launch_bounds__(1024) k_sort_unique_small(fl_lists L, int key_
     }
   if (tid == 0) {
     *d_out_count = s_warp[31]; d_hdr[0] = s_warp[31]; d_hdr[1] = n; d_hdr[2] = 0;
-    if (h_hdr) { h_hdr[0] = s_warp[31]; h_hdr[1] = n; h_hdr[2] = 0; }
+    if (h_hdr) { h_hdr[0] = s_warp[31]; h_hdr[1] = n; h_hdr[2] = 0; h_hdr[15] = d_hdr[15]; }
+    if (h_hdr && X.world > 0 && X.world <= 4) {                  // developer timing of the exchange (ns): push, wait, sort
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_dbg[3]));
+      h_hdr[8] = (int)(t_dbg[1] - t_dbg[0]); h_hdr[9] = (int)(t_dbg[2] - t_dbg[1]); h_hdr[10] = (int)(t_dbg[3] - t_dbg[2]);
+    }
   }
 }
 
@@ -405,10 +445,10 @@ __global__ void __launch_bounds__(1024) k_unique_big(const fl_sort_key* __restri
 }
 
 // Host orchestration.  Scratch int (n_live of the big path) lives right after the key array.
-int fl_launch_sort_unique(fl_lists L, int key_cap, fl_match_t* d_out, int out_cap, int* d_out_count, int* d_hdr, int* h_hdr, fl_match_t* h_first,
-                          int h_first_cap, cudaStream_t s) {
+int fl_launch_sort_unique(fl_lists L, fl_xchg X, int key_cap, fl_match_t* d_out, int out_cap, int* d_out_count, int* d_hdr, int* h_hdr,
+                          fl_match_t* h_first, int h_first_cap, cudaStream_t s) {
   // 256 threads: the common case is a few dozen records, where the cost is the ~30 block barriers of the bitonic network
-  fl_launch_pdl(k_sort_unique_small, dim3(1), dim3(256), 0, s, L, key_cap, d_out, out_cap, d_out_count, d_hdr, h_hdr, h_first, h_first_cap);
+  fl_launch_pdl(k_sort_unique_small, dim3(1), dim3(256), 0, s, L, X, key_cap, d_out, out_cap, d_out_count, d_hdr, h_hdr, h_first, h_first_cap);
   return 1;
 }
 

@@ -81,13 +81,18 @@ def merge_on_host(gathered_np: np.ndarray) -> np.ndarray:
 
 
 class ShardedMatcher:
-    """One rank of a template-sharded detector.  ``match_device`` = front end + matchClass on the local shard,
-    ONE all-gather of candidate blocks over NCCL (NVLink / NVSwitch), sort + unique of the union on every rank.  The
-    block layout ``[header | records]`` is consumed as it is by ``fl_sort_unique_blocks_device``: between the collective and
-    the sort there is no copy, no count extraction, no other kernel."""
+    """One rank of a template-sharded detector.  ``match_device`` = front end + matchClass on the local shard, exchange of
+    the candidate blocks, sort + unique of the union on every rank.
 
-    def __init__(self, handle, tset, rank: int, world: int, capacity: int = 2048, device=None):
+    exchange = "p2p" (default on a multi-GPU job): every rank's exchange buffer is a torch symmetric-memory allocation
+    mapped into all processes; the library's own sort kernel pushes the local block into every peer over NVLink, signals,
+    waits for the peers and merges (``fl_exchange_sort_unique_device``) - ONE kernel, no collective-library call on the data
+    path.  exchange = "nccl": one ``all_gather_into_tensor`` of fixed-size blocks followed by
+    ``fl_sort_unique_blocks_device`` (the block layout ``[header | records]`` is consumed as it is)."""
+
+    def __init__(self, handle, tset, rank: int, world: int, capacity: int = 2048, device=None, exchange: str = "auto"):
         import torch
+        import torch.distributed as dist
         self.h, self.rank, self.world, self.cap = handle, rank, world, capacity
         shard, gids = shard_template_set(tset, rank, world)
         handle.upload_templates(shard)
@@ -98,15 +103,43 @@ class ShardedMatcher:
         self.gathered = torch.zeros(world * block_ints(capacity), dtype=torch.int32, device=dev)
         self.stream = torch.cuda.ExternalStream(handle.stream_ptr(), device=dev)
         self._torch = torch
+        self.epoch = 0
+        self.exchange = "nccl"
+        self.exchange_error = None
+        if exchange in ("auto", "p2p") and world > 1 and dist.is_initialized() and world <= 8:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                from . import lib
+                nbytes = int(lib().fl_exchange_buffer_bytes(world, capacity))
+                self._xbuf = symm_mem.empty(nbytes, dtype=torch.uint8, device=dev)
+                self._xhdl = symm_mem.rendezvous(self._xbuf, dist.group.WORLD)
+                self._xbuf.zero_()
+                torch.cuda.synchronize()
+                dist.barrier()
+                self._peers = [int(p) for p in self._xhdl.buffer_ptrs]
+                self.exchange = "p2p"
+            except Exception as e:  # noqa: BLE001  (no peer mapping available: fall back to the collective)
+                self.exchange_error = repr(e)
+                if exchange == "p2p":
+                    raise
+            # all ranks must agree on the mode
+            ok = torch.tensor([1 if self.exchange == "p2p" else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                self.exchange = "nccl"
 
     def match_device(self, d_bgr: int, d_depth: int, W: int, H: int, threshold: float) -> None:
-        """One frame: enqueue the local match, the all-gather and the merge on the handle's stream; returns when the merged
+        """One frame: enqueue the local match, the exchange and the merge on the handle's stream; returns when the merged
         match list is ready (``fetch``)."""
         torch = self._torch
         import torch.distributed as dist
         recs = records_view(self.block)
-        # the count lives in the header record of the block, so the candidates + count travel in one collective
+        # the count lives in the header record of the block, so the candidates + count travel together
         self.h.match_shard_device(d_bgr, d_depth, W, H, threshold, recs.data_ptr(), self.cap, self.block.data_ptr())
+        if self.exchange == "p2p":
+            self.epoch += 1
+            self.h.exchange_sort_unique_device(self.rank, self.world, self._peers, self.cap, self.block.data_ptr(), self.epoch)
+            return
         with torch.cuda.stream(self.stream):
             if self.world == 1 or not dist.is_initialized():
                 self.gathered.copy_(self.block)

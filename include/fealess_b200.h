@@ -150,6 +150,17 @@ int fl_sort_unique_device(fl_handle* h, const fl_match_t* d_in, int32_t n_lists,
  * fl_match_fetch.  No intermediate copies or count extraction are needed between the collective and this call. */
 int fl_sort_unique_blocks_device(fl_handle* h, const fl_match_t* d_blocks, int32_t n_blocks, int32_t capacity);
 
+/* The same merge with the exchange done by the library itself over peer memory (NVLink / NVSwitch), fused into the head
+ * of the sort kernel - no collective-library call on the data path.  Every rank owns an exchange buffer of
+ * fl_exchange_buffer_bytes(world, capacity) bytes (zero-initialised once) that is mapped into every process of the
+ * job (CUDA IPC, fabric handles, torch symmetric memory ...); peer_buffers[p] is the address of rank p's buffer in THIS
+ * process.  The kernel pushes this rank's block [count | records] into every peer's buffer, publishes `epoch` (> 0,
+ * incremented by all ranks for every frame) in the peer's signal word, waits for the epoch of all peers (bounded: a
+ * missing peer yields FL_ERR_STATE after ~2 s instead of a hang), and sorts + prunes the union.  world <= 8. */
+size_t fl_exchange_buffer_bytes(int32_t world, int32_t capacity);
+int fl_exchange_sort_unique_device(fl_handle* h, int32_t rank, int32_t world, void* const* peer_buffers, int32_t capacity,
+                                   const fl_match_t* d_local_block, uint32_t epoch);
+
 /* ---- ICP ------------------------------------------------------------------------------------------ */
 /* cup_d2pc::depthTo3d for 16UC1 input: out3 = H*W*3 floats in METRES, 0 depth -> NaN (depth_to_3d.cpp:99-137, 244-260) */
 int fl_depth_to_3d(fl_handle* h, const uint16_t* depth, size_t depth_stride, int32_t W, int32_t H,
