@@ -185,6 +185,16 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - fealess_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    if world > 1 and hasattr(os, "sched_setaffinity"):
+        # one rank = one GPU = its own slice of the host cores: the ranks busy-wait on their streams, and 8 of them sharing
+        # 16 cores with the NCCL / sampler threads otherwise delay each other by hundreds of microseconds in ~10 % of the steps
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            lw = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+            per = max(1, len(cores) // lw)
+            os.sched_setaffinity(0, set(cores[local * per:(local + 1) * per]) or set(cores))
+        except OSError:
+            pass
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -354,7 +364,7 @@ def run_ours(args):
         icp = bench_icp(h, synth, cpu=not args.no_cpu)
 
     line = {"metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "ms_per_step": dev_ms / args.steps, "ms_per_step_p50": float(np.median(per_step)), "ms_per_step_p90": float(np.percentile(per_step, 90)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
             "config": {"workload": "C2: LINE-MOD match-only, 640x480, %d templates per GPU (%d total), L=2, T={5,8}, threshold 75" % (args.templates, n_total),
                        "l2": "flushed between steps (256 MB write)", "frames_per_s": args.steps / (dev_ms * 1e-3),

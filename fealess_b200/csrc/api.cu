@@ -484,7 +484,7 @@ static int run_match_stages(fl_handle* h, const uint8_t* d_bgr, const uint16_t* 
   return FL_OK;
 }
 
-// sort + unique of candidate lists into (d_out, d_out_count); handles the rare > 2048 path; leaves
+// sort + unique of candidate lists into (d_out, d_out_count); handles the rare > 8,192-record path; leaves
 // h_small = {count, n_live, flag, raw list counts...} and, for the handle's own output block, the first matches in h_first
 static int run_sort_unique(fl_handle* h, fl_lists L, fl_match_t* d_out, int out_cap, int* d_out_count, bool fetch_first, const fl_xchg* xchg = nullptr) {
   cudaStream_t s = h->stream;
@@ -496,14 +496,15 @@ static int run_sort_unique(fl_handle* h, fl_lists L, fl_match_t* d_out, int out_
   fl_xchg X;
   memset(&X, 0, sizeof X);
   if (xchg) X = *xchg;
-  h->launches += fl_launch_sort_unique(L, X, h->key_cap, d_out, out_cap, d_out_count, d_hdr, h->h_small, own ? h->h_first : nullptr, std::min(FETCH_FIRST, out_cap), s);
+  h->launches += fl_launch_sort_unique(L, X, h->key_cap, d_out, out_cap, d_out_count, d_hdr, h->h_small, own ? h->h_first : nullptr,
+                                       std::min(FETCH_FIRST, out_cap), s);
   if (h->profile) cudaEventRecord(h->ev[4], s);
   FL_CUDA(cudaStreamSynchronize(s));
   h->overflow = false;
   int n_upper = 0;
   for (int i = 0; i < std::min(n_lists, 12); ++i) { if (h->h_small[3 + i] > list_cap) h->overflow = true; n_upper += std::min(std::max(h->h_small[3 + i], 0), list_cap); }
   if (n_lists > 12) n_upper = n_lists * list_cap;
-  if (h->h_small[2]) {                                                          // more than 2048 records: multi-kernel sort
+  if (h->h_small[2]) {                                                          // more records than the one-CTA sort holds: multi-kernel sort
     int rc = fl_launch_sort_unique_big(L, h->d_keys, h->key_cap, n_upper, d_out, out_cap, d_out_count, s);
     if (rc < 0) return FL_ERR_CAPACITY;
     h->launches += rc;

@@ -139,8 +139,8 @@ struct fl_xchg { int world, rank, cap; unsigned epoch; const fl_match_t* local_b
 // One launch; when flag_big comes back set the host runs fl_launch_sort_unique_big (key workspace: next_pow2(n_upper) keys
 // + 1 int).  Both return the number of launches.  h_hdr / h_first: mapped pinned host copies of the summary and of the
 // first h_first_cap matches (nullable).
-int fl_launch_sort_unique(fl_lists L, fl_xchg X, int key_cap, fl_match_t* d_out, int out_cap, int* d_out_count, int* d_hdr, int* h_hdr,
-                          fl_match_t* h_first, int h_first_cap, cudaStream_t s);
+int fl_launch_sort_unique(fl_lists L, fl_xchg X, int key_cap, fl_match_t* d_out, int out_cap, int* d_out_count, int* d_hdr,
+                          int* h_hdr, fl_match_t* h_first, int h_first_cap, cudaStream_t s);
 int fl_launch_sort_unique_big(fl_lists L, fl_sort_key* keys, int key_cap, int n_upper, fl_match_t* d_out, int out_cap, int* d_out_count, cudaStream_t s);
 
 // ---- ICP (icp.cu) --------------------------------------------------------------------------------

@@ -275,20 +275,20 @@ __global__ void __launch_bounds__(256) k_build_keys(fl_lists L, fl_sort_key* __r
   if (slot < key_cap) keys[slot] = make_key(m);
 }
 
-#define SORT_SMEM_N 2048
+#define SORT_SMEM_LARGE 8192     // keys the one-CTA sort holds in shared memory (128 KB); a power of two: the bitonic network pads to one
 // Common case, ONE launch of one CTA: gather the live candidates of all lists, sort, prune duplicates.  When the lists hold
-// more than SORT_SMEM_N records it only sets *d_flag_big = 1 and the host runs the multi-kernel path (k_build_keys + global
+// more records than fit its shared memory it only sets *d_flag_big = 1 and the host runs the multi-kernel path (k_build_keys + global
 // bitonic steps + k_unique_big).  d_scratch = {n_live, flag_big}.
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) { unsigned v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 
-__global__ void __launch_bounds__(1024) k_sort_unique_small(fl_lists L, fl_xchg X, int key_cap, fl_match_t* __restrict__ out,
+__global__ void __launch_bounds__(1024) k_sort_unique_small(fl_lists L, fl_xchg X, int key_cap, int smem_keys, fl_match_t* __restrict__ out,
                                                             int out_cap, int* __restrict__ d_out_count, int* __restrict__ d_hdr,
                                                             int* __restrict__ h_hdr, fl_match_t* __restrict__ h_first, int h_first_cap) {
   // d_hdr (16 ints, handle-owned) = {unique count, n_live, flag_big, raw n_in[0..11]}.  h_hdr / h_first (nullable) are the
   // same summary and the first matches in MAPPED PINNED HOST memory: the kernel posts them over PCIe itself, so the host
   // needs no device-to-host copy (and none of its ~8 us of copy-engine hand-over) before it can read the result.
-  __shared__ fl_sort_key s_k[SORT_SMEM_N];
+  extern __shared__ __align__(16) fl_sort_key s_k[];            // smem_keys keys
   __shared__ int s_warp[32];
   __shared__ int s_n;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -331,27 +331,32 @@ __global__ void __launch_bounds__(1024) k_sort_unique_small(fl_lists L, fl_xchg 
   int total = 0;
   for (int l = 0; l < n_lists; ++l) total += min(max(L.n_in[(size_t)l * L.n_in_stride], 0), list_cap);
   if (tid < 12) { const int c = tid < n_lists ? L.n_in[(size_t)tid * L.n_in_stride] : 0; d_hdr[3 + tid] = c; if (h_hdr) h_hdr[3 + tid] = c; }
-  if (total > SORT_SMEM_N || total > key_cap) {
+  if (total > smem_keys || total > key_cap) {
     if (tid == 0) { d_hdr[0] = 0; d_hdr[1] = total; d_hdr[2] = 1; if (h_hdr) { h_hdr[0] = 0; h_hdr[1] = total; h_hdr[2] = 1; h_hdr[15] = d_hdr[15]; } }
     return;
   }
+  // The launch always has 1,024 threads and room for SORT_SMEM_LARGE keys; a frame with few records (the common case)
+  // retires all but 256 of them here, so that the ~30 barriers of the bitonic network stay cheap.
+  const int nt = total > 1024 ? (int)blockDim.x : min(256, (int)blockDim.x);
+  if (tid >= nt) return;
+  auto sync_active = [&]() { asm volatile("bar.sync 1, %0;" ::"r"(nt) : "memory"); };
   if (tid == 0) s_n = 0;
-  __syncthreads();
-  for (int i = tid; i < total; i += blockDim.x) {
+  sync_active();
+  for (int i = tid; i < total; i += nt) {
     int l = 0, k = i;
     for (;;) { const int c = min(max(L.n_in[(size_t)l * L.n_in_stride], 0), list_cap); if (k < c) break; k -= c; ++l; }
     const fl_match_t m = L.in[(size_t)l * L.list_stride + k];
     if (m.template_id >= 0) s_k[atomicAdd(&s_n, 1)] = make_key(m);          // dropped candidates carry template_id -1
   }
-  __syncthreads();
+  sync_active();
   const int n = s_n;
   int n_pad = 2;
   while (n_pad < n) n_pad <<= 1;
-  for (int i = n + tid; i < n_pad; i += blockDim.x) { s_k[i].hi = KEY_SENTINEL_HI; s_k[i].lo = KEY_SENTINEL_HI; }
-  __syncthreads();
+  for (int i = n + tid; i < n_pad; i += nt) { s_k[i].hi = KEY_SENTINEL_HI; s_k[i].lo = KEY_SENTINEL_HI; }
+  sync_active();
   for (int k = 2; k <= n_pad; k <<= 1)
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = tid; i < n_pad; i += blockDim.x) {
+      for (int i = tid; i < n_pad; i += nt) {
         const int p = i ^ j;
         if (p > i) {
           const bool up = (i & k) == 0;
@@ -359,10 +364,10 @@ __global__ void __launch_bounds__(1024) k_sort_unique_small(fl_lists L, fl_xchg 
           if (key_less(b, a) == up) { s_k[i] = b; s_k[p] = a; }
         }
       }
-      __syncthreads();
+      sync_active();
     }
   // adjacent unique + ordered compaction: each thread owns a contiguous run of slots; block-wide exclusive scan of the kept counts
-  const int per = (n_pad + blockDim.x - 1) / blockDim.x;
+  const int per = (n_pad + nt - 1) / nt;
   const int b0 = tid * per;
   int cnt = 0;
   for (int i = b0; i < min(b0 + per, n); ++i) cnt += (i == 0 || !key_dup(s_k[i - 1], s_k[i])) ? 1 : 0;
@@ -370,14 +375,14 @@ __global__ void __launch_bounds__(1024) k_sort_unique_small(fl_lists L, fl_xchg 
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
   if (lane == 31) s_warp[warp] = inc;
-  __syncthreads();
+  sync_active();
   if (warp == 0) {
-    int w = lane < (int)(blockDim.x >> 5) ? s_warp[lane] : 0;
+    int w = lane < (nt >> 5) ? s_warp[lane] : 0;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
     s_warp[lane] = w;
   }
-  __syncthreads();
+  sync_active();
   int pos = (warp > 0 ? s_warp[warp - 1] : 0) + inc - cnt;
   for (int i = b0; i < min(b0 + per, n); ++i)
     if (i == 0 || !key_dup(s_k[i - 1], s_k[i])) {
@@ -445,14 +450,16 @@ __global__ void __launch_bounds__(1024) k_unique_big(const fl_sort_key* __restri
 }
 
 // Host orchestration.  Scratch int (n_live of the big path) lives right after the key array.
-int fl_launch_sort_unique(fl_lists L, fl_xchg X, int key_cap, fl_match_t* d_out, int out_cap, int* d_out_count, int* d_hdr, int* h_hdr,
-                          fl_match_t* h_first, int h_first_cap, cudaStream_t s) {
-  // 256 threads: the common case is a few dozen records, where the cost is the ~30 block barriers of the bitonic network
-  fl_launch_pdl(k_sort_unique_small, dim3(1), dim3(256), 0, s, L, X, key_cap, d_out, out_cap, d_out_count, d_hdr, h_hdr, h_first, h_first_cap);
+int fl_launch_sort_unique(fl_lists L, fl_xchg X, int key_cap, fl_match_t* d_out, int out_cap, int* d_out_count, int* d_hdr,
+                          int* h_hdr, fl_match_t* h_first, int h_first_cap, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) { cudaFuncSetAttribute(k_sort_unique_small, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM_LARGE * (int)sizeof(fl_sort_key)); configured = true; }
+  fl_launch_pdl(k_sort_unique_small, dim3(1), dim3(1024), (size_t)SORT_SMEM_LARGE * sizeof(fl_sort_key), s, L, X, key_cap, (int)SORT_SMEM_LARGE, d_out, out_cap,
+                d_out_count, d_hdr, h_hdr, h_first, h_first_cap);
   return 1;
 }
 
-// second stage, only when the small kernel reported more than SORT_SMEM_N records (the host has read the flag and the
+// second stage, only when the one-CTA kernel reported more records than its shared memory holds (the host has read the flag and the
 // record count n_upper)
 int fl_launch_sort_unique_big(fl_lists L, fl_sort_key* keys, int key_cap, int n_upper, fl_match_t* d_out, int out_cap, int* d_out_count, cudaStream_t s) {
   int launches = 0;

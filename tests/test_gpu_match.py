@@ -97,7 +97,8 @@ def test_match_list_identical(vga, thr):
 def test_large_candidate_count_takes_the_multi_kernel_sort(vga):
     W, H, b, d, det, ts, h = vga
     # low thresholds bring the raw threshold down to the chance level (2*nf): thousands of candidates (2.4k / 9.6k / 39k raw
-    # on this scene), which exercises the > 2048-key multi-kernel sort, the second D2H chunk and, at 0 %, the overflow path
+    # on this scene), which exercises the one-CTA sort with all 1,024 threads (<= 8,192 keys), the multi-kernel sort beyond
+    # that, the second D2H chunk and, at 0 %, the overflow path
     for thr in (30.0, 20.0, 10.0, 0.0):
         raw = det.match(thr, canonical=False)
         want = det.match(thr)
