@@ -234,12 +234,16 @@ def run_ours(args):
     for i in range(args.warmup):
         step(i, False)
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start_and_wait()
+        sampler.start_and_wait()                                        # NVML init takes ~10 ms: before the barrier, or every peer's first step waits for rank 0
+    if world > 1:
+        dist.barrier()
+        for i in range(2):                                              # re-align the ranks on the device after the host barrier
+            step(i, False)
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     launches0 = h.launch_count()
     evs = []
     import gc

@@ -148,6 +148,7 @@ extern "C" int fl_create(const fl_params_t* params, fl_handle** out) {
   h->key_cap = kc;
   TRY(dalloc(&h->d_keys, (size_t)kc + 1));      // + room for the two scratch ints behind the keys
   TRY(dalloc(&h->d_outblk, 64 + (size_t)p.max_candidates * sizeof(fl_match_t)));
+  FL_CUDA(cudaMemset(h->d_outblk, 0, 64));                                         // summary words, incl. the fused-tail overflow flag
   h->d_out_count = reinterpret_cast<int*>(h->d_outblk); h->d_out = reinterpret_cast<fl_match_t*>(h->d_outblk + 64);
   TRY(halloc(&h->h_bgr, npx * 3)); TRY(halloc(&h->h_depth, npx)); TRY(halloc(&h->h_mask, npx * p.n_modalities));
   TRY(halloc(&h->h_outblk, 64 + FETCH_FIRST * sizeof(fl_match_t))); TRY(halloc(&h->h_class_enabled, 4096));
@@ -394,8 +395,14 @@ static int run_match_stages(fl_handle* h, const uint8_t* d_bgr, const uint16_t* 
     // latency floor of one colour-tile CTA, about 8 us.)
     const int L = p.n_levels;
     fl_fe_wave w;
-    auto wave_begin = [&](bool zero) { w.n_jobs = 0; w.n_ctas = 0; w.smem = 0; w.zero_me = zero ? d_count : nullptr; };
-    auto wave_flush = [&]() { if (w.n_jobs > 0) { fl_launch_fe_wave(w, s); ++h->launches; } w.n_jobs = 0; w.n_ctas = 0; w.smem = 0; w.zero_me = nullptr; };
+    auto wave_begin = [&](bool zero) { w.n_jobs = 0; w.n_ctas = 0; w.smem = 0; w.n_pyr = 0; w.zero_me = zero ? d_count : nullptr; };
+    auto wave_flush = [&]() { if (w.n_jobs > 0) { fl_launch_fe_wave(w, s); ++h->launches; } w.n_jobs = 0; w.n_ctas = 0; w.smem = 0; w.n_pyr = 0; w.zero_me = nullptr; };
+    // word-parallel quantisers (frontend_v2.cuh); FL_FE_V1=1 selects the first, byte-granular versions (A/B timing).  The depth
+    // job also writes the NN-downsampled label pyramid when every level halves exactly (then dst_l(y,x) = src(2^l y, 2^l x)).
+    static const bool fe_v1 = getenv("FL_FE_V1") != nullptr;
+    bool depth_pyr_fused[FL_MAX_MODALITIES] = {false, false, false, false};
+    bool halves = true;
+    for (int l = 0; l + 1 < L; ++l) halves &= (h->geom[l].W % 2 == 0) && (h->geom[l].H % 2 == 0);
     auto wave_room = [&]() { if (w.n_jobs == FL_FE_MAX_JOBS) wave_flush(); };     // jobs of one wave are independent: splitting is always safe
     for (int wv = 0; wv <= L; ++wv) {
       wave_begin(wv == 0 && zero_in_wave);                                        // the candidate counter is reset by the first wave
@@ -403,9 +410,23 @@ static int run_match_stages(fl_handle* h, const uint8_t* d_bgr, const uint16_t* 
       if (l < L) {
         const fl_level_geom& g = h->geom[l];
         for (int m = 0; m < p.n_modalities; ++m)
-          if (p.modality_kind[m] == FL_MODALITY_COLOR_GRADIENT) { wave_room(); fl_fe_add_color(&w, l == 0 ? d_bgr : h->d_bgr[l], g.W, g.H, thr_sq, h->d_q[l][m], 0, 1); }
+          if (p.modality_kind[m] == FL_MODALITY_COLOR_GRADIENT) {
+            wave_room();
+            if (fe_v1) fl_fe_add_color(&w, l == 0 ? d_bgr : h->d_bgr[l], g.W, g.H, thr_sq, h->d_q[l][m], 0, 1);
+            else fl_fe_add_color_v2(&w, l == 0 ? d_bgr : h->d_bgr[l], g.W, g.H, thr_sq, h->d_q[l][m]);
+          }
         for (int m = 0; m < p.n_modalities; ++m)
-          if (p.modality_kind[m] == FL_MODALITY_DEPTH_NORMAL && l == 0) { wave_room(); fl_fe_add_depth(&w, d_depth, g.W, g.H, p.distance_threshold, p.difference_threshold, h->d_q[0][m]); }
+          if (p.modality_kind[m] == FL_MODALITY_DEPTH_NORMAL && l == 0) {
+            wave_room();
+            if (fe_v1) { fl_fe_add_depth(&w, d_depth, g.W, g.H, p.distance_threshold, p.difference_threshold, h->d_q[0][m]); continue; }
+            fl_depth_pyr pyr; memset(&pyr, 0, sizeof pyr);
+            if (halves && L > 1 && L - 1 <= FL_FE_MAX_PYR) {
+              pyr.n = L - 1;
+              for (int k = 1; k < L; ++k) { pyr.W[k - 1] = h->geom[k].W; pyr.H[k - 1] = h->geom[k].H; pyr.dst[k - 1] = h->d_q[k][m]; }
+            }
+            if (pyr.n > 0 && fl_fe_add_depth_v2(&w, d_depth, g.W, g.H, p.distance_threshold, p.difference_threshold, h->d_q[0][m], &pyr)) depth_pyr_fused[m] = true;
+            else fl_fe_add_depth_v2(&w, d_depth, g.W, g.H, p.distance_threshold, p.difference_threshold, h->d_q[0][m], nullptr);
+          }
       }
       if (l >= 1) {
         const fl_level_geom& g = h->geom[l - 1];
@@ -420,7 +441,7 @@ static int run_match_stages(fl_handle* h, const uint8_t* d_bgr, const uint16_t* 
         const fl_level_geom& g = h->geom[l];
         if (first_color >= 0 && l + 1 < L) { wave_room(); fl_fe_add_pyrdown(&w, l == 0 ? d_bgr : h->d_bgr[l], g.W, g.H, h->d_bgr[l + 1]); }   // shared by all colour modalities
         for (int m = 0; m < p.n_modalities; ++m)
-          if (p.modality_kind[m] == FL_MODALITY_DEPTH_NORMAL && l > 0) { wave_room(); fl_fe_add_resize(&w, h->d_q[l - 1][m], h->geom[l - 1].W, h->geom[l - 1].H, h->d_q[l][m]); }
+          if (p.modality_kind[m] == FL_MODALITY_DEPTH_NORMAL && l > 0 && !depth_pyr_fused[m]) { wave_room(); fl_fe_add_resize(&w, h->d_q[l - 1][m], h->geom[l - 1].W, h->geom[l - 1].H, h->d_q[l][m]); }
       }
       wave_flush();
     }
@@ -468,16 +489,26 @@ static int run_match_stages(fl_handle* h, const uint8_t* d_bgr, const uint16_t* 
   if (h->n_templates > 0) {
     fl_tdb db = make_tdb(h);
     const int lowest = p.n_levels - 1;
+    bool refined = false;
     if (h->use_staged) {
-      if (fl_launch_similarity_staged(db, h->geom[lowest], h->d_lm[lowest], threshold, cand, cap, d_count, h->plan, s) != 0) {
+      // the staged kernel refines its own candidates (fused tail, refine_warp.cuh) when FL_FUSE_TAIL=1 was set at planning time (developer variant, off by default)
+      fl_refine_args ra;
+      memset(&ra, 0, sizeof ra);
+      ra.n_levels = p.n_levels;
+      h->plan.fuse_ovf = reinterpret_cast<int*>(h->d_outblk) + 14;                 // posted to h_small[14] and cleared by the sort kernel
+      for (int l = 0; l < p.n_levels; ++l) { ra.g[l] = h->geom[l]; ra.lm[l] = h->d_lm[l]; }
+      if (fl_launch_similarity_staged(db, h->geom[lowest], h->d_lm[lowest], threshold, cand, cap, d_count, h->plan, ra, s) != 0) {
         fl_set_error("staged similarity kernel could not be configured"); return FL_ERR_CUDA;
       }
+      refined = h->plan.fuse_list_cap > 0;
+
     } else {
       fl_launch_similarity_global(db, h->geom[lowest], h->d_lm[lowest], threshold, cand, cap, d_count, s);
     }
     ++h->launches;
     if (h->profile) cudaEventRecord(h->ev[2], s);
-    for (int l = p.n_levels - 2; l >= 0; --l) { fl_launch_refine_level(db, h->geom[l], l, h->d_lm[l], threshold, cand, cap, d_count, s); ++h->launches; }
+    if (!refined)
+      for (int l = p.n_levels - 2; l >= 0; --l) { fl_launch_refine_level(db, h->geom[l], l, h->d_lm[l], threshold, cand, cap, d_count, s); ++h->launches; }
   } else if (h->profile) cudaEventRecord(h->ev[2], s);
   if (h->profile) cudaEventRecord(h->ev[3], s);
   FL_CUDA(cudaGetLastError());
@@ -502,8 +533,8 @@ static int run_sort_unique(fl_handle* h, fl_lists L, fl_match_t* d_out, int out_
   FL_CUDA(cudaStreamSynchronize(s));
   h->overflow = false;
   int n_upper = 0;
-  for (int i = 0; i < std::min(n_lists, 12); ++i) { if (h->h_small[3 + i] > list_cap) h->overflow = true; n_upper += std::min(std::max(h->h_small[3 + i], 0), list_cap); }
-  if (n_lists > 12) n_upper = n_lists * list_cap;
+  for (int i = 0; i < std::min(n_lists, 11); ++i) { if (h->h_small[3 + i] > list_cap) h->overflow = true; n_upper += std::min(std::max(h->h_small[3 + i], 0), list_cap); }
+  if (n_lists > 11) n_upper = n_lists * list_cap;
   if (h->h_small[2]) {                                                          // more records than the one-CTA sort holds: multi-kernel sort
     int rc = fl_launch_sort_unique_big(L, h->d_keys, h->key_cap, n_upper, d_out, out_cap, d_out_count, s);
     if (rc < 0) return FL_ERR_CAPACITY;
@@ -526,6 +557,17 @@ extern "C" int fl_match_device(fl_handle* h, const void* d_bgr, const void* d_de
                        h->p.max_candidates, h->d_count));
   const fl_lists lists = {h->d_cand, 1, h->p.max_candidates, h->p.max_candidates, h->d_count, 1};
   TRY(run_sort_unique(h, lists, h->d_out, h->p.max_candidates, h->d_out_count, true));
+  if (h->h_small[14]) {
+    // one CTA of the staged kernel found more coarse candidates than its shared-memory list holds (very low thresholds):
+    // run the frame again with the refinement as separate launches
+    const int keep = h->plan.fuse_list_cap;
+    h->plan.fuse_list_cap = 0;
+    int rc = run_match_stages(h, (const uint8_t*)d_bgr, (const uint16_t*)d_depth, W, H, d_masks, threshold, class_filter, n_filter, h->d_cand,
+                              h->p.max_candidates, h->d_count);
+    if (rc == FL_OK) rc = run_sort_unique(h, lists, h->d_out, h->p.max_candidates, h->d_out_count, true);
+    h->plan.fuse_list_cap = keep;
+    if (rc != FL_OK) return rc;
+  }
   h->have_result = true;
   return FL_OK;
 }
@@ -647,6 +689,7 @@ extern "C" int fl_exchange_sort_unique_device(fl_handle* h, int32_t rank, int32_
   const fl_lists lists = {reinterpret_cast<const fl_match_t*>(own) + 1, world, capacity, capacity + 1, reinterpret_cast<const int*>(own), 5 * (capacity + 1)};
   TRY(run_sort_unique(h, lists, h->d_out, h->p.max_candidates, h->d_out_count, true, &X));
   if (h->h_small[15]) { fl_set_error("peer exchange timed out waiting for rank %d", h->h_small[15] - 1); return FL_ERR_STATE; }
+  if (h->h_small[14]) { fl_set_error("more coarse candidates in one CTA than the fused refinement list holds; raise the threshold or unset FL_FUSE_TAIL"); return FL_ERR_CAPACITY; }
   h->have_result = true;
   return FL_OK;
 }
@@ -658,6 +701,7 @@ extern "C" int fl_sort_unique_blocks_device(fl_handle* h, const fl_match_t* d_bl
   if (h->profile) for (int i = 0; i < 4; ++i) cudaEventRecord(h->ev[i], h->stream);   // stage times are not defined for this entry point
   const fl_lists lists = {d_blocks + 1, n_blocks, capacity, capacity + 1, reinterpret_cast<const int*>(d_blocks), 5 * (capacity + 1)};
   TRY(run_sort_unique(h, lists, h->d_out, h->p.max_candidates, h->d_out_count, true));
+  if (h->h_small[14]) { fl_set_error("more coarse candidates in one CTA than the fused refinement list holds; raise the threshold or unset FL_FUSE_TAIL"); return FL_ERR_CAPACITY; }
   h->have_result = true;
   return FL_OK;
 }

@@ -68,17 +68,24 @@ void fl_launch_apply_mask(const uint8_t* q, const uint8_t* mask, int n, uint8_t*
 void fl_launch_spread_lm(const uint8_t* q, fl_level_geom g, uint8_t* lm_mod, uint8_t* spread_or_null, cudaStream_t s);
 
 // one launch = several independent front-end jobs (see k_front_end_wave)
-enum { FL_JOB_COLOR = 0, FL_JOB_DEPTH = 1, FL_JOB_PYRDOWN = 2, FL_JOB_RESIZE = 3, FL_JOB_SPREAD = 4 };
+enum { FL_JOB_COLOR = 0, FL_JOB_DEPTH = 1, FL_JOB_PYRDOWN = 2, FL_JOB_RESIZE = 3, FL_JOB_SPREAD = 4, FL_JOB_COLOR2 = 5, FL_JOB_DEPTH2 = 6 };
 struct fl_fe_job {
   int kind, cta_begin, gx, W, H, p0, p1;
   float thr_sq;
   const uint8_t* src; uint8_t* dst; uint8_t* dst2;
   fl_level_geom g;
 };
+// NN-downsampled copies of the level-0 depth labels written by the depth job itself: entry i = pyramid level i + 1
+#define FL_FE_MAX_PYR 7
+struct fl_depth_pyr { int n; int W[FL_FE_MAX_PYR], H[FL_FE_MAX_PYR]; uint8_t* dst[FL_FE_MAX_PYR]; };
 #define FL_FE_MAX_JOBS 16
-struct fl_fe_wave { int n_jobs, n_ctas; size_t smem; int* zero_me; fl_fe_job job[FL_FE_MAX_JOBS]; };   // zero_me: int reset by CTA 0 (candidate counter), or NULL
+#define FL_FE_MAX_DPYR 2
+struct fl_fe_wave { int n_jobs, n_ctas; size_t smem; int* zero_me; fl_fe_job job[FL_FE_MAX_JOBS]; int n_pyr; fl_depth_pyr pyr[FL_FE_MAX_DPYR]; };   // zero_me: int reset by CTA 0 (candidate counter), or NULL
 void fl_fe_add_color(fl_fe_wave* w, const uint8_t* bgr, int W, int H, float thr_sq, uint8_t* q, int part, int n_parts);
 void fl_fe_add_depth(fl_fe_wave* w, const uint16_t* depth, int W, int H, int dist_thr, int diff_thr, uint8_t* q);
+// word-parallel variants (frontend_v2.cuh); pyr (nullable, at most FL_FE_MAX_DPYR per wave): also write the NN pyramid of the labels
+void fl_fe_add_color_v2(fl_fe_wave* w, const uint8_t* bgr, int W, int H, float thr_sq, uint8_t* q);
+bool fl_fe_add_depth_v2(fl_fe_wave* w, const uint16_t* depth, int W, int H, int dist_thr, int diff_thr, uint8_t* q, const fl_depth_pyr* pyr);
 void fl_fe_add_pyrdown(fl_fe_wave* w, const uint8_t* src, int W, int H, uint8_t* dst);
 void fl_fe_add_resize(fl_fe_wave* w, const uint8_t* src, int W, int H, uint8_t* dst);
 void fl_fe_add_spread(fl_fe_wave* w, const uint8_t* q, fl_level_geom g, uint8_t* lm_mod, uint8_t* spread_or_null);
@@ -104,6 +111,8 @@ struct fl_staged_plan {
   int n_words, nw_template, tpw;           // 32-bit words per similarity map; template parameters of the instantiation used
   int tpc, n_cta, block_threads;           // templates per CTA, grid, block
   int cluster, smem_bytes, pre_stride;     // CTAs per cluster (TMA multicast group); dynamic shared memory; bytes per gpre row
+  int fuse_list_off, fuse_list_cap;        // fused refinement tail: per-CTA candidate list in shared memory (offset, records); cap 0 = not fused
+  int* fuse_ovf;                           // device int set to 1 when a CTA's list overflowed (the host then re-runs the frame unfused)
   uint32_t* gfeat;                         // [n_templates][64] feature words sorted by phase: word offset in the phase buffer << 5 | 8 * byte misalignment
   uint8_t* gpre;                           // [n_templates][pre_stride] prefix counts per phase
   int4* gmeta;                             // [n_templates] {template_positions, n_features, class, 0}
@@ -111,8 +120,14 @@ struct fl_staged_plan {
 };
 bool fl_plan_staged(const fl_level_geom& g, int M, int n_templates, int max_positions, int n_sm, fl_staged_plan* plan);
 void fl_launch_pack_staged(fl_tdb db, fl_level_geom g, fl_staged_plan plan, cudaStream_t s);
+// every level's geometry and linear memories, for the refinement fused into the staged kernel's tail (refine_warp.cuh)
+struct fl_refine_args {
+  int n_levels;
+  fl_level_geom g[FL_MAX_LEVELS];
+  const uint8_t* lm[FL_MAX_LEVELS];
+};
 int fl_launch_similarity_staged(fl_tdb db, fl_level_geom g, const uint8_t* lm_level, float threshold, fl_match_t* cand, int cap,
-                                int* d_count, fl_staged_plan plan, cudaStream_t s);
+                                int* d_count, fl_staged_plan plan, const fl_refine_args& ra, cudaStream_t s);
 void fl_launch_pack_features(fl_tdb db, const fl_level_geom* d_geom, int n_features_total, cudaStream_t s);
 void fl_launch_similarity_global(fl_tdb db, fl_level_geom g, const uint8_t* lm_level, float threshold,
                                  fl_match_t* cand, int cap, int* d_count, cudaStream_t s);

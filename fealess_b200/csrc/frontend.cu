@@ -65,16 +65,12 @@ __device__ __forceinline__ int angle_q16(float x, float y) {
   const float p1 = 0.9997878412794807f * scale, p3 = -0.3258083974640975f * scale;
   const float p5 = 0.1555786518463281f * scale, p7 = -0.04432655554792128f * scale;
   const float eps = 2.220446049250313e-16f;
-  float ax = fabsf(x), ay = fabsf(y), a, c, c2;
-  if (ax >= ay) {
-    c = __fdiv_rn(ay, __fadd_rn(ax, eps));
-    c2 = __fmul_rn(c, c);
-    a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
-  } else {
-    c = __fdiv_rn(ax, __fadd_rn(ay, eps));
-    c2 = __fmul_rn(c, c);
-    a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
-  }
+  // the two octant branches of fastAtan2 evaluate the same polynomial on min/max: one division instead of a divergent pair
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float c = __fdiv_rn(fminf(ax, ay), __fadd_rn(fmaxf(ax, ay), eps));
+  const float c2 = __fmul_rn(c, c);
+  float a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+  if (ax < ay) a = __fsub_rn(90.f, a);
   if (x < 0) a = __fsub_rn(180.f, a);
   if (y < 0) a = __fsub_rn(360.f, a);
   int r = __float2int_rn(__fmul_rn(a, (float)(16.0 / 360.0)));
@@ -189,6 +185,8 @@ void fl_launch_color_quantize(const uint8_t* bgr, int W, int H, float thr_sq, ui
   k_color_quantize<<<grid, CQ_THREADS, 0, s>>>(bgr, W, H, thr_sq, q);
 }
 
+#include "frontend_v2.cuh"
+
 // ------------------------------------------------------------------------------------------------
 // K2 cv::pyrDown of the BGR image: 5x5 [1 4 6 4 1]^2, BORDER_REFLECT_101, (sum + 128) >> 8
 // ------------------------------------------------------------------------------------------------
@@ -198,35 +196,52 @@ __device__ __forceinline__ int reflect101(int p, int n) {
   return p;
 }
 
+// one thread per output PIXEL (3 channels), CTA = 32 x 8 output pixels (the first version ran one thread per output byte
+// and spent ~540 instructions on index arithmetic for each of them)
+#define PD_TW 32
+#define PD_TH 8
+__device__ __forceinline__ int reflect101_near(int p, int n) {         // |overshoot| <= 2 and n >= 3: a single fold
+  return p < 0 ? -p : (p >= n ? 2 * n - 2 - p : p);
+}
 __device__ __forceinline__ void dev_pyrdown_bgr(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ dst, int bx) {
   const int dw = W / 2, dh = H / 2;
-  int i = bx * 256 + threadIdx.x;                  // one thread per output byte (pixel*3 + channel): coalesced stores
-  if (i >= dw * dh * 3) return;
-  int ch = i % 3, px = i / 3;
-  int x = px % dw, y = px / dw;
-  const int k[5] = {1, 4, 6, 4, 1};
-  int cx[5];
+  const int gx = (dw + PD_TW - 1) / PD_TW;
+  const int by = bx / gx; bx -= by * gx;
+  const int x = bx * PD_TW + (threadIdx.x & 31), y = by * PD_TH + (threadIdx.x >> 5);
+  if (x >= dw || y >= dh) return;
+  int cx[5], ry[5];
+  if (W >= 3 && H >= 3) {
 #pragma unroll
-  for (int t = 0; t < 5; ++t) cx[t] = reflect101(2 * x + t - 2, W) * 3 + ch;
-  int s = 0;
+    for (int t = 0; t < 5; ++t) { cx[t] = reflect101_near(2 * x + t - 2, W) * 3; ry[t] = reflect101_near(2 * y + t - 2, H); }
+  } else {
+#pragma unroll
+    for (int t = 0; t < 5; ++t) { cx[t] = reflect101(2 * x + t - 2, W) * 3; ry[t] = reflect101(2 * y + t - 2, H); }
+  }
+  int s0 = 0, s1 = 0, s2 = 0;
 #pragma unroll
   for (int j = 0; j < 5; ++j) {
-    const uint8_t* row = src + (size_t)reflect101(2 * y + j - 2, H) * W * 3;
-    int rs = 0;
+    const uint8_t* row = src + (size_t)ry[j] * W * 3;
+    const int kj = j == 0 || j == 4 ? 1 : (j == 2 ? 6 : 4);
+    int r0 = 0, r1 = 0, r2 = 0;
 #pragma unroll
-    for (int t = 0; t < 5; ++t) rs += k[t] * row[cx[t]];
-    s += k[j] * rs;
+    for (int t = 0; t < 5; ++t) {
+      const int kt = t == 0 || t == 4 ? 1 : (t == 2 ? 6 : 4);
+      const uint8_t* p = row + cx[t];
+      r0 += kt * p[0]; r1 += kt * p[1]; r2 += kt * p[2];
+    }
+    s0 += kj * r0; s1 += kj * r1; s2 += kj * r2;
   }
-  dst[i] = (uint8_t)((s + 128) >> 8);
+  uint8_t* o = dst + ((size_t)y * dw + x) * 3;
+  o[0] = (uint8_t)((s0 + 128) >> 8); o[1] = (uint8_t)((s1 + 128) >> 8); o[2] = (uint8_t)((s2 + 128) >> 8);
 }
 
 __global__ void __launch_bounds__(256) k_pyrdown_bgr(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ dst) {
   dev_pyrdown_bgr(src, W, H, dst, blockIdx.x);
 }
 
+static int pyrdown_ctas(int W, int H) { return ((W / 2 + PD_TW - 1) / PD_TW) * ((H / 2 + PD_TH - 1) / PD_TH); }
 void fl_launch_pyrdown_bgr(const uint8_t* src, int W, int H, uint8_t* dst, cudaStream_t s) {
-  int n = (W / 2) * (H / 2) * 3;
-  k_pyrdown_bgr<<<(n + 255) / 256, 256, 0, s>>>(src, W, H, dst);
+  if (pyrdown_ctas(W, H) > 0) k_pyrdown_bgr<<<pyrdown_ctas(W, H), 256, 0, s>>>(src, W, H, dst);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -498,7 +513,7 @@ void fl_launch_spread_lm(const uint8_t* q, fl_level_geom g, uint8_t* lm_mod, uin
 //   wave k >= 1 : colour quantise Lk | NN-downsample depth labels Lk | pyrDown Lk->Lk+1 | spread+LM of level k-1 (all modalities)
 //   last wave   : spread+LM of the coarsest level
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_front_end_wave(fl_fe_wave w) {
+__global__ void __launch_bounds__(256, 8) k_front_end_wave(fl_fe_wave w) {
   extern __shared__ __align__(16) uint8_t smem_dyn[];
   const int b = blockIdx.x;
   fl_grid_dep_wait();                                   // the previous kernel of the stream wrote this wave's inputs
@@ -515,6 +530,11 @@ __global__ void __launch_bounds__(256) k_front_end_wave(fl_fe_wave w) {
     case FL_JOB_PYRDOWN: dev_pyrdown_bgr(jb.src, jb.W, jb.H, jb.dst, local); break;
     case FL_JOB_RESIZE: dev_resize_nn_half(jb.src, jb.W, jb.H, jb.dst, local); break;
     case FL_JOB_SPREAD: dev_spread_lm_any(jb.src, jb.g, jb.dst, jb.dst2, local % jb.gx, local / jb.gx, smem_dyn, jb.p0); break;
+    case FL_JOB_COLOR2: dev_color_quantize_v2(jb.src, jb.W, jb.H, jb.thr_sq, jb.dst, local % jb.gx, local / jb.gx, smem_dyn); break;
+    case FL_JOB_DEPTH2:
+      dev_depth_quantize_v2(reinterpret_cast<const uint16_t*>(jb.src), jb.W, jb.H, jb.p0, jb.p1, jb.dst, w, jb.gx < 0 ? -1 : (jb.thr_sq > 0.5f ? 1 : 0),
+                            local % abs(jb.gx), local / abs(jb.gx), smem_dyn);
+      break;
   }
 }
 
@@ -534,10 +554,32 @@ void fl_fe_add_depth(fl_fe_wave* w, const uint16_t* depth, int W, int H, int dis
   j.gx = (W + DQ_TW - 1) / DQ_TW; j.cta_begin = w->n_ctas; w->n_ctas += j.gx * ((H + DQ_TH - 1) / DQ_TH);
   w->smem = w->smem > (size_t)DQ_SMEM_BYTES ? w->smem : (size_t)DQ_SMEM_BYTES;
 }
+void fl_fe_add_color_v2(fl_fe_wave* w, const uint8_t* bgr, int W, int H, float thr_sq, uint8_t* q) {
+  fl_fe_job& j = w->job[w->n_jobs++];
+  j.kind = FL_JOB_COLOR2; j.src = bgr; j.dst = q; j.dst2 = nullptr; j.W = W; j.H = H; j.thr_sq = thr_sq;
+  j.gx = (W + C2_TW - 1) / C2_TW; j.p0 = j.p1 = 0; j.cta_begin = w->n_ctas; w->n_ctas += j.gx * ((H + C2_TH - 1) / C2_TH);
+  w->smem = w->smem > (size_t)C2_SMEM_BYTES ? w->smem : (size_t)C2_SMEM_BYTES;
+}
+// returns false (nothing added) when a pyramid is requested but the wave has no free pyramid slot
+bool fl_fe_add_depth_v2(fl_fe_wave* w, const uint16_t* depth, int W, int H, int dist_thr, int diff_thr, uint8_t* q, const fl_depth_pyr* pyr) {
+  int slot = -1;
+  if (pyr && pyr->n > 0) {
+    if (w->n_pyr >= FL_FE_MAX_DPYR) return false;
+    slot = w->n_pyr++;
+    w->pyr[slot] = *pyr;
+  }
+  fl_fe_job& j = w->job[w->n_jobs++];
+  j.kind = FL_JOB_DEPTH2; j.src = reinterpret_cast<const uint8_t*>(depth); j.dst = q; j.dst2 = nullptr; j.W = W; j.H = H; j.p0 = dist_thr; j.p1 = diff_thr;
+  const int gx = (W + D2_TW - 1) / D2_TW;
+  j.gx = slot < 0 ? -gx : gx; j.thr_sq = (float)(slot < 0 ? 0 : slot);            // gx < 0: no pyramid; thr_sq carries the pyramid slot
+  j.cta_begin = w->n_ctas; w->n_ctas += gx * ((H + D2_TH - 1) / D2_TH);
+  w->smem = w->smem > (size_t)D2_SMEM_BYTES ? w->smem : (size_t)D2_SMEM_BYTES;
+  return true;
+}
 void fl_fe_add_pyrdown(fl_fe_wave* w, const uint8_t* src, int W, int H, uint8_t* dst) {
   fl_fe_job& j = w->job[w->n_jobs++];
   j.kind = FL_JOB_PYRDOWN; j.src = src; j.dst = dst; j.dst2 = nullptr; j.W = W; j.H = H; j.gx = 1;
-  j.cta_begin = w->n_ctas; w->n_ctas += ((W / 2) * (H / 2) * 3 + 255) / 256;
+  j.cta_begin = w->n_ctas; w->n_ctas += pyrdown_ctas(W, H);
 }
 void fl_fe_add_resize(fl_fe_wave* w, const uint8_t* src, int W, int H, uint8_t* dst) {
   fl_fe_job& j = w->job[w->n_jobs++];

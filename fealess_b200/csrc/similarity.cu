@@ -185,10 +185,24 @@ __global__ void __launch_bounds__(RF_THREADS) k_refine_level(fl_tdb db, fl_level
     for (int m = 0; m < db.M; ++m) {
       uint32_t acc = 0;
       const int k1 = s_mbeg[m + 1];
-#pragma unroll 4
-      for (int k = s_mbeg[m] + fgrp; k < k1; k += 4) {
-        const uint32_t o = s_off[k];
-        if (o != FL_SKIP) acc += load_u8x4(lm_level, o + cell_off);
+      // <= 63 features per modality (:1231) = <= 16 per feature group: all loads of a modality are issued before the first
+      // add (one L2 round trip instead of one per unroll step)
+      for (int k0 = s_mbeg[m] + fgrp; k0 < k1; k0 += 64) {
+        uint32_t lo[16], hi[16], sh[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const int k = k0 + 4 * u;
+          const uint32_t o = k < k1 ? s_off[k] : FL_SKIP;
+          const uint32_t a = o + cell_off;
+          sh[u] = (a & 3) * 8;
+          lo[u] = hi[u] = 0;
+          if (o != FL_SKIP) {
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(lm_level) + (a >> 2);
+            lo[u] = __ldg(w); hi[u] = __ldg(w + 1);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) acc += __funnelshift_r(lo[u], hi[u], sh[u]);
       }
       tot_lo += (acc & 0xFF) | ((acc & 0xFF00) << 8);
       tot_hi += ((acc >> 16) & 0xFF) | ((acc >> 24) << 16);
@@ -285,7 +299,7 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) { unsigned
 __global__ void __launch_bounds__(1024) k_sort_unique_small(fl_lists L, fl_xchg X, int key_cap, int smem_keys, fl_match_t* __restrict__ out,
                                                             int out_cap, int* __restrict__ d_out_count, int* __restrict__ d_hdr,
                                                             int* __restrict__ h_hdr, fl_match_t* __restrict__ h_first, int h_first_cap) {
-  // d_hdr (16 ints, handle-owned) = {unique count, n_live, flag_big, raw n_in[0..11]}.  h_hdr / h_first (nullable) are the
+  // d_hdr (16 ints, handle-owned) = {unique count, n_live, flag_big, raw n_in[0..10], fused-tail overflow flag, exchange time-out}.  h_hdr / h_first (nullable) are the
   // same summary and the first matches in MAPPED PINNED HOST memory: the kernel posts them over PCIe itself, so the host
   // needs no device-to-host copy (and none of its ~8 us of copy-engine hand-over) before it can read the result.
   extern __shared__ __align__(16) fl_sort_key s_k[];            // smem_keys keys
@@ -330,7 +344,8 @@ __global__ void __launch_bounds__(1024) k_sort_unique_small(fl_lists L, fl_xchg 
   const int n_lists = L.n_lists, list_cap = L.list_cap;
   int total = 0;
   for (int l = 0; l < n_lists; ++l) total += min(max(L.n_in[(size_t)l * L.n_in_stride], 0), list_cap);
-  if (tid < 12) { const int c = tid < n_lists ? L.n_in[(size_t)tid * L.n_in_stride] : 0; d_hdr[3 + tid] = c; if (h_hdr) h_hdr[3 + tid] = c; }
+  if (tid < 11) { const int c = tid < n_lists ? L.n_in[(size_t)tid * L.n_in_stride] : 0; d_hdr[3 + tid] = c; if (h_hdr) h_hdr[3 + tid] = c; }
+  if (tid == 0) { if (h_hdr) h_hdr[14] = d_hdr[14]; d_hdr[14] = 0; }   // overflow flag of the fused refinement tail (set by the staged kernel): post and clear
   if (total > smem_keys || total > key_cap) {
     if (tid == 0) { d_hdr[0] = 0; d_hdr[1] = total; d_hdr[2] = 1; if (h_hdr) { h_hdr[0] = 0; h_hdr[1] = total; h_hdr[2] = 1; h_hdr[15] = d_hdr[15]; } }
     return;
@@ -340,6 +355,58 @@ __global__ void __launch_bounds__(1024) k_sort_unique_small(fl_lists L, fl_xchg 
   const int nt = total > 1024 ? (int)blockDim.x : min(256, (int)blockDim.x);
   if (tid >= nt) return;
   auto sync_active = [&]() { asm volatile("bar.sync 1, %0;" ::"r"(nt) : "memory"); };
+  if (total <= 256) {
+    // Few records (the common case): rank sort.  Thread i owns record i; its rank among the live records is the number of
+    // keys that precede it (ties - fully identical records - broken by index), so the sort is one pass over shared memory
+    // and three barriers instead of the ~30 of the bitonic network.
+    fl_sort_key key; key.hi = KEY_SENTINEL_HI; key.lo = KEY_SENTINEL_HI;
+    bool live = false;
+    if (tid < total) {
+      int l = 0, k = tid;
+      for (;;) { const int c = min(max(L.n_in[(size_t)l * L.n_in_stride], 0), list_cap); if (k < c) break; k -= c; ++l; }
+      const fl_match_t m = L.in[(size_t)l * L.list_stride + k];
+      if (m.template_id >= 0) { key = make_key(m); live = true; }
+    }
+    s_k[tid] = key;
+    sync_active();
+    fl_sort_key* s_sorted = s_k + 256;
+    if (live) {
+      int rank = 0;
+      for (int j = 0; j < total; ++j) {
+        const fl_sort_key o = s_k[j];
+        rank += (key_less(o, key) || (o.hi == key.hi && o.lo == key.lo && j < tid)) ? 1 : 0;
+      }
+      s_sorted[rank] = key;
+    }
+    const unsigned live_mask = __ballot_sync(0xffffffffu, live);
+    if (lane == 0) s_warp[warp] = __popc(live_mask);
+    sync_active();
+    int n = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) n += s_warp[w];
+    const bool keep = tid < n && (tid == 0 || !key_dup(s_sorted[tid - 1], s_sorted[tid]));
+    const unsigned keep_mask = __ballot_sync(0xffffffffu, keep);
+    sync_active();                                                 // every warp has read the live counts
+    if (lane == 0) s_warp[warp] = __popc(keep_mask);
+    sync_active();
+    int pos = __popc(keep_mask & ((1u << lane) - 1)), n_unique = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { if (w < warp) pos += s_warp[w]; n_unique += s_warp[w]; }
+    if (keep) {
+      const fl_match_t m = key_to_match(s_sorted[tid]);
+      if (pos < out_cap) out[pos] = m;
+      if (h_first && pos < h_first_cap) h_first[pos] = m;
+    }
+    if (tid == 0) {
+      *d_out_count = n_unique; d_hdr[0] = n_unique; d_hdr[1] = n; d_hdr[2] = 0;
+      if (h_hdr) { h_hdr[0] = n_unique; h_hdr[1] = n; h_hdr[2] = 0; h_hdr[15] = d_hdr[15]; }
+      if (h_hdr && X.world > 0 && X.world <= 4) {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_dbg[3]));
+        h_hdr[8] = (int)(t_dbg[1] - t_dbg[0]); h_hdr[9] = (int)(t_dbg[2] - t_dbg[1]); h_hdr[10] = (int)(t_dbg[3] - t_dbg[2]);
+      }
+    }
+    return;
+  }
   if (tid == 0) s_n = 0;
   sync_active();
   for (int i = tid; i < total; i += nt) {

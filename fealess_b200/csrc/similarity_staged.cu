@@ -25,6 +25,7 @@
 // template has <= 63 coarsest-level features over all modalities (so one u8 lane holds the total, 63*4 = 252) and the same
 // width/height for all modalities at that level (what cropTemplates :52-96 produces); otherwise the baseline kernel runs.
 #include "fl_internal.cuh"
+#include "refine_warp.cuh"
 #include <stdlib.h>
 
 #define SS_MAXF 64                      // feature words per template (<= 63 used)
@@ -173,12 +174,17 @@ __device__ __forceinline__ uint32_t candidate_mask(uint32_t v, int w, int tp, in
   return m;
 }
 
+// FUSE: the kernel also refines its candidates up the pyramid (fl_refine_candidate_warp) and appends FINAL matches to the
+// list: coarsest-level candidates go to a per-CTA list in shared memory, then every warp of the CTA takes candidates off
+// that list.  Candidates beyond the list's capacity are refined on the spot by the warp that found them.
 template <int NW, int TPW, int CL>
-__global__ void __launch_bounds__(1024, 1) k_similarity_staged(fl_tdb db, fl_level_geom g, const uint8_t* __restrict__ lm_level, float threshold,
+__global__ void __launch_bounds__(1024, 1) k_similarity_staged(const __grid_constant__ fl_tdb db, fl_level_geom g, const uint8_t* __restrict__ lm_level, float threshold,
                                                                fl_match_t* __restrict__ cand, int cap, int* __restrict__ d_count,
-                                                               fl_staged_plan plan) {
-  extern __shared__ __align__(128) uint8_t s_dyn[];          // [n_buf x buf_bytes][tpc x int4 meta][tpc x 64 feature words + 4][tpc x pre_stride]
+                                                               fl_staged_plan plan, const __grid_constant__ fl_refine_args ra) {
+  extern __shared__ __align__(128) uint8_t s_dyn[];          // [n_buf x buf_bytes][tpc x int4 meta][tpc x 64 feature words + 4][tpc x pre_stride][fuse_list_cap x int4]
   __shared__ __align__(8) uint64_t s_full[SS_NBUF_MAX], s_empty[SS_NBUF_MAX];
+  __shared__ int s_ncand;
+  const bool fuse = plan.fuse_list_cap > 0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_cwarps = (blockDim.x >> 5) - 1;                 // consumer warps; the last warp is the TMA producer
   const int t_begin = blockIdx.x * plan.tpc;
@@ -195,7 +201,9 @@ __global__ void __launch_bounds__(1024, 1) k_similarity_staged(fl_tdb db, fl_lev
   unsigned long long* trace = plan.trace ? plan.trace + (size_t)blockIdx.x * 8 : nullptr;
   if (trace && tid == 0) { trace[0] = globaltimer(); unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); trace[5] = smid; }
 
+  int4* s_list = reinterpret_cast<int4*>(s_dyn + plan.fuse_list_off);      // {template, x | y << 16, similarity bits, class}
   if (tid == 0) {
+    s_ncand = 0;
     for (int b = 0; b < n_buf; ++b) { mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], n_cwarps * CL); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -209,7 +217,7 @@ __global__ void __launch_bounds__(1024, 1) k_similarity_staged(fl_tdb db, fl_lev
       int4 m = make_int4(0, 0, 0, 0);
       if (t < t_end) {
         m = plan.gmeta[t];
-        m.w = db.L == 1 ? db.tid_of[t] : t;                   // the id candidates carry (see k_similarity_global)
+        m.w = (db.L == 1 && !fuse) ? db.tid_of[t] : t;        // the id candidates carry (see k_similarity_global); fused: always local
         if (!db.class_enabled[m.z]) m.x = 0;                  // no positions -> no candidates
         // raw threshold int(2 nf + (threshold / 100) 2 nf + 0.5f) in fp32 (:1487); stored biased by 1, clamped to [-1, 255]
         const int nf = m.y;
@@ -335,8 +343,11 @@ __global__ void __launch_bounds__(1024, 1) k_similarity_staged(fl_tdb db, fl_lev
       if (!__any_sync(0xffffffffu, cnt > 0)) continue;
       const int total = __reduce_add_sync(0xffffffffu, cnt);
       int base = 0;
-      if (lane == 0) base = atomicAdd(d_count, total);
+      if (lane == 0) base = fuse ? atomicAdd(&s_ncand, total) : atomicAdd(d_count, total);
       base = __shfl_sync(0xffffffffu, base, 0);
+      const int lim = fuse ? plan.fuse_list_cap : cap;
+      // list full (> fuse_list_cap coarse candidates from this CTA's templates): flag it; the host re-runs the frame unfused
+      if (fuse && base + total > lim && lane == 0 && plan.fuse_ovf) *plan.fuse_ovf = 1;
 #pragma unroll
       for (int i = 0; i < NW; ++i) {
         const uint32_t v = acc[s][i];
@@ -347,15 +358,16 @@ __global__ void __launch_bounds__(1024, 1) k_similarity_staged(fl_tdb db, fl_lev
         for (int bb = 0; bb < 4; ++bb) {
           const bool hit = (m >> (8 * bb)) & 1;
           const uint32_t bal = __ballot_sync(0xffffffffu, hit);
-          if (hit) {
-            const int slot = base + __popc(bal & ((1u << lane) - 1));
-            if (slot < cap) {
-              const int j = 4 * w + bb, raw = (v >> (8 * bb)) & 0xFF;
-              const int r = j / g.Wd, c = j - r * g.Wd;
+          const int slot = base + __popc(bal & ((1u << lane) - 1));
+          const int j = 4 * w + bb, raw = (v >> (8 * bb)) & 0xFF;
+          const int r = j / g.Wd, c = j - r * g.Wd;
+          const int mx = c * g.T + off, my = r * g.T + off;
+          const float msim = __fadd_rn(__fdiv_rn(__fmul_rn((float)raw, 100.f), (float)(4 * nf)), 0.5f);
+          if (hit && slot < lim) {
+            if (fuse) s_list[slot] = make_int4(meta.w, (mx & 0xFFFF) | (my << 16), __float_as_int(msim), meta.z);
+            else {
               fl_match_t mt;
-              mt.x = c * g.T + off; mt.y = r * g.T + off;
-              mt.similarity = __fadd_rn(__fdiv_rn(__fmul_rn((float)raw, 100.f), (float)(4 * nf)), 0.5f);
-              mt.class_idx = meta.z; mt.template_id = meta.w;
+              mt.x = mx; mt.y = my; mt.similarity = msim; mt.class_idx = meta.z; mt.template_id = meta.w;
               cand[slot] = mt;
             }
           }
@@ -365,6 +377,17 @@ __global__ void __launch_bounds__(1024, 1) k_similarity_staged(fl_tdb db, fl_lev
     }
     if (trace && lane == 0) { atomicMax(&trace[6], globaltimer()); plan.trace[(size_t)plan.n_cta * 8 + 8 + ((size_t)blockIdx.x * 32 + warp) * 2 + 1] = globaltimer(); }
   }
+  if (fuse) {
+    // ===== fused tail: every warp of the CTA (the producer warp too) refines candidates off the CTA's list =====
+    __syncwarp();                                             // the producer warp's lanes arrive separately
+    __syncthreads();
+    const int n_list = min(s_ncand, plan.fuse_list_cap);
+    const int n_warps = blockDim.x >> 5;
+    for (int i = warp; i < n_list; i += n_warps) {
+      const int4 c = s_list[i];
+      fl_refine_and_emit_warp(db, ra, threshold, c.x, c.w, (int)(short)(c.y & 0xFFFF), c.y >> 16, __int_as_float(c.z), cand, cap, d_count);
+    }
+  }
   if (CL > 1) { __syncwarp(); cluster_sync_all(); }           // no CTA leaves while a peer may still write into it or signal it
   if (trace && tid == 0) trace[4] = globaltimer();
 }
@@ -373,7 +396,7 @@ __global__ void k_stamp(unsigned long long* p) { *p = globaltimer(); }
 
 template <int NW, int TPW, int CL>
 static int launch_staged_cl(fl_tdb db, fl_level_geom g, const uint8_t* lm_level, float threshold, fl_match_t* cand, int cap, int* d_count,
-                            fl_staged_plan plan, cudaStream_t s) {
+                            fl_staged_plan plan, const fl_refine_args& ra, cudaStream_t s) {
   auto kern = k_similarity_staged<NW, TPW, CL>;
   static size_t configured = 0;
   if ((size_t)plan.smem_bytes > configured) {
@@ -390,18 +413,18 @@ static int launch_staged_cl(fl_tdb db, fl_level_geom g, const uint8_t* lm_level,
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = (fl_pdl_enabled() && !plan.trace) ? 2 : 1;
   if (plan.trace) k_stamp<<<1, 1, 0, s>>>(plan.trace + (size_t)plan.n_cta * 8);
-  const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, db, g, lm_level, threshold, cand, cap, d_count, plan);
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, db, g, lm_level, threshold, cand, cap, d_count, plan, ra);
   if (plan.trace) k_stamp<<<1, 1, 0, s>>>(plan.trace + (size_t)plan.n_cta * 8 + 1);
   return e == cudaSuccess ? 0 : -1;
 }
 
 template <int NW, int TPW>
 static int launch_staged(fl_tdb db, fl_level_geom g, const uint8_t* lm_level, float threshold, fl_match_t* cand, int cap, int* d_count,
-                         fl_staged_plan plan, cudaStream_t s) {
+                         fl_staged_plan plan, const fl_refine_args& ra, cudaStream_t s) {
   switch (plan.cluster) {
-    case 1: return launch_staged_cl<NW, TPW, 1>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
-    case 2: return launch_staged_cl<NW, TPW, 2>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
-    case 4: return launch_staged_cl<NW, TPW, 4>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
+    case 1: return launch_staged_cl<NW, TPW, 1>(db, g, lm_level, threshold, cand, cap, d_count, plan, ra, s);
+    case 2: return launch_staged_cl<NW, TPW, 2>(db, g, lm_level, threshold, cand, cap, d_count, plan, ra, s);
+    case 4: return launch_staged_cl<NW, TPW, 4>(db, g, lm_level, threshold, cand, cap, d_count, plan, ra, s);
   }
   return -1;
 }
@@ -450,7 +473,11 @@ bool fl_plan_staged(const fl_level_geom& g, int M, int n_templates, int max_posi
   // global memory.  (Measured at VGA, 8k templates: 2 x 78 KB / 16 phases beats 4 x 46 KB / 32 phases, 24.6 vs 29.9 us.)
   int nbuf = env_int("FL_SS_NBUF", 2);
   if (nbuf < 2 || nbuf > SS_NBUF_MAX) nbuf = 2;
-  const size_t lists = (size_t)p.tpc * 16 + ((size_t)p.tpc * SS_MAXF + 4) * 4 + (size_t)p.tpc * (SS_MAX_PHASES + 2);   // upper bound (n_phases <= SS_MAX_PHASES)
+  // Fused refinement tail (developer knob FL_FUSE_TAIL=1, OFF by default): measured on B200 at 8k templates it is SLOWER than the
+  // separate refinement launch (stage 143 us vs 43 + 11 us): candidates cluster in the few CTAs that own a matching template,
+  // one warp per candidate leaves ~2 features' loads in flight under the 64-register cap, and the other 140 CTAs idle.
+  const int fuse_cap = env_int("FL_FUSE_TAIL", 0) ? 2048 : 0;                    // candidates per CTA list (16 B each)
+  const size_t lists = (size_t)p.tpc * 16 + ((size_t)p.tpc * SS_MAXF + 4) * 4 + (size_t)p.tpc * (SS_MAX_PHASES + 2) + 16 + (size_t)fuse_cap * 16;   // upper bound (n_phases <= SS_MAX_PHASES)
   const size_t avail = 227 * 1024 - 1024;
   if (lists + 4096 > avail) return false;
   const size_t budget = ((avail - lists) / nbuf) & ~(size_t)127;
@@ -471,24 +498,27 @@ bool fl_plan_staged(const fl_level_geom& g, int M, int n_templates, int max_posi
   p.buf_bytes = (int)((((size_t)pr * g.cells + p.halo_bytes + 15) & ~(size_t)15) + 127) & ~127;
   p.pre_stride = (p.n_phases + 1 + 3) & ~3;
   p.smem_bytes = p.n_buf * p.buf_bytes + p.tpc * 16 + (p.tpc * SS_MAXF + 4) * 4 + p.tpc * p.pre_stride;
+  p.fuse_list_off = (p.smem_bytes + 15) & ~15;
+  p.fuse_list_cap = fuse_cap;
+  p.smem_bytes = p.fuse_list_off + fuse_cap * 16;
   if (p.smem_bytes > 227 * 1024 - 512) return false;
   *plan = p;
   return true;
 }
 
 int fl_launch_similarity_staged(fl_tdb db, fl_level_geom g, const uint8_t* lm_level, float threshold, fl_match_t* cand, int cap,
-                                int* d_count, fl_staged_plan plan, cudaStream_t s) {
+                                int* d_count, fl_staged_plan plan, const fl_refine_args& ra, cudaStream_t s) {
   switch (plan.nw_template) {
-    case 5: return launch_staged<5, 2>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
-    case 7: return launch_staged<7, 2>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
-    case 9: return launch_staged<9, 2>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
-    case 11: return launch_staged<11, 2>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
-    case 13: return launch_staged<13, 1>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
-    case 15: return launch_staged<15, 1>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
-    case 19: return launch_staged<19, 1>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
-    case 23: return launch_staged<23, 1>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
-    case 29: return launch_staged<29, 1>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
-    case 37: return launch_staged<37, 1>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
+    case 5: return launch_staged<5, 2>(db, g, lm_level, threshold, cand, cap, d_count, plan, ra, s);
+    case 7: return launch_staged<7, 2>(db, g, lm_level, threshold, cand, cap, d_count, plan, ra, s);
+    case 9: return launch_staged<9, 2>(db, g, lm_level, threshold, cand, cap, d_count, plan, ra, s);
+    case 11: return launch_staged<11, 2>(db, g, lm_level, threshold, cand, cap, d_count, plan, ra, s);
+    case 13: return launch_staged<13, 1>(db, g, lm_level, threshold, cand, cap, d_count, plan, ra, s);
+    case 15: return launch_staged<15, 1>(db, g, lm_level, threshold, cand, cap, d_count, plan, ra, s);
+    case 19: return launch_staged<19, 1>(db, g, lm_level, threshold, cand, cap, d_count, plan, ra, s);
+    case 23: return launch_staged<23, 1>(db, g, lm_level, threshold, cand, cap, d_count, plan, ra, s);
+    case 29: return launch_staged<29, 1>(db, g, lm_level, threshold, cand, cap, d_count, plan, ra, s);
+    case 37: return launch_staged<37, 1>(db, g, lm_level, threshold, cand, cap, d_count, plan, ra, s);
   }
   return -1;
 }

@@ -125,6 +125,26 @@ def test_staged_and_baseline_similarity_kernels_agree(vga):
     assert np.array_equal(staged, want) and np.array_equal(base, want)
 
 
+def test_fused_refinement_tail_equals_separate_refinement_launches(vga):
+    """FL_FUSE_TAIL=1 at planning time makes the staged kernel refine its own candidates (fused tail, a developer variant); the
+    default keeps the refinement outside.  Both must give the oracle's list, also when one CTA's shared-memory candidate list
+    overflows (low threshold -> the frame is re-run unfused)."""
+    W, H, b, d, det, ts, h = vga
+    os.environ["FL_FUSE_TAIL"] = "1"
+    try:
+        h2 = fb.Handle((5, 8), (0, 1), W, H, max_candidates=1 << 17)   # fused variant
+        h2.upload_templates(ts)
+        for thr in (75.0, 50.0, 25.0):
+            want = det.match(thr)
+            rc_a, plain = h.match(b, d, thr, capacity=1 << 16)
+            rc_b, fused = h2.match(b, d, thr, capacity=1 << 16)
+            assert rc_a == 0 and rc_b == 0
+            assert np.array_equal(fused, want) and np.array_equal(plain, want), thr
+        h2.close()
+    finally:
+        del os.environ["FL_FUSE_TAIL"]
+
+
 def test_templates_with_features_on_the_box_border_and_ragged_sets(vga):
     """Features at x == width / y == height make similarity() read past the end of a linear-memory row (flat addressing);
     a template larger than the frame has no valid position at all; a set that is not eligible for the staged kernel (64+
@@ -224,6 +244,22 @@ def test_three_levels_720p():
     _check_front_end(h, det, W, H, L=3)
     want = det.match(70.0)
     assert len(want) > 0 and np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("W,H,T", [(240, 160, (5, 8)), (250, 160, (5, 5)), (480, 270, (5, 5)), (80, 60, (5, 5))])
+def test_front_end_ragged_sizes(W, H, T):
+    """Partial tiles, widths that are not multiples of 4 (unaligned load / store paths), odd level-1 sizes, tiny frames."""
+    b, d = synth.make_frame(W, H, 11)
+    det = _oracle(b, d, T)
+    h = fb.Handle(T, (0, 1), W, H)
+    h.upload_templates(synth.make_templates(0))
+    h.keep_spread(True)
+    rc, got, q = h.match(b, d, 80.0, want_quantized=True)
+    assert rc == 0 and len(got) == 0
+    for i in range(4):
+        assert np.array_equal(q[i], det.quantized(i // 2, i % 2)), "quantized %d" % i
+    _check_front_end(h, det, W, H)
+    h.close()
 
 
 def test_single_modality_colour_only():

@@ -1,0 +1,27 @@
+"""Developer experiment (GPU box): front-end stage time (CUDA events of the library) for the word-parallel quantisers vs the
+first byte-granular versions (FL_FE_V1=1 in the environment selects the latter; one process per variant)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import fealess_b200 as fb
+from fealess_b200 import synth
+
+W, H, T = 640, 480, (5, 8)
+NT = int(sys.argv[1]) if len(sys.argv) > 1 else 8000
+frames = [synth.make_frame(W, H, i) for i in range(4)]
+h = fb.Handle(T, (0, 1), W, H)
+h.upload_templates(synth.make_templates(0))
+rc, _, q = h.match(frames[0][0], frames[0][1], 75.0, want_quantized=True)
+ts = synth.make_templates(NT, W, H, T, seed=1, quantized=q, planted_fraction=0.01)
+h.upload_templates(ts)
+h.profile(True)
+st = np.zeros(4); n = 0
+for it in range(104):
+    b, d = frames[it % 4]
+    rc, m = h.match(b, d, 75.0)
+    if it >= 4:
+        st += h.last_stage_ms(); n += 1
+st /= n
+print("FL_FE_V1=%s | matches %d | stage us: fe %.1f sim %.1f refine %.1f sort %.1f total %.1f"
+      % (os.environ.get("FL_FE_V1"), len(m), *(1e3 * st), 1e3 * st.sum()), flush=True)
