@@ -48,6 +48,7 @@ struct fl_handle {
   uint8_t* d_spread[FL_MAX_LEVELS][FL_MAX_MODALITIES];     // debug only
   uint8_t* d_lm[FL_MAX_LEVELS]; size_t lm_bytes[FL_MAX_LEVELS];
   bool used_mask[FL_MAX_MODALITIES]; bool keep_spread;
+  unsigned* d_fe_counters; unsigned fe_counter_base[FL_FE_MAX_JOBS];   // in-grid dependency counters of the single-launch front end (+ 1 error word)
   // candidates / matches
   fl_match_t* d_cand; int* d_count; fl_sort_key* d_keys; int key_cap; uint8_t* d_outblk; fl_match_t* d_out; int* d_out_count;   // d_outblk = [16-int summary][matches]
   // pinned host staging
@@ -144,6 +145,9 @@ extern "C" int fl_create(const fl_params_t* params, fl_handle** out) {
     TRY(dalloc(&h->d_lm[l], h->lm_bytes[l]));
   }
   TRY(dalloc(&h->d_cand, (size_t)p.max_candidates)); TRY(dalloc(&h->d_count, 4));
+  FL_CUDA(cudaMemset(h->d_count, 0, 4 * sizeof(int)));
+  TRY(dalloc(&h->d_fe_counters, FL_FE_MAX_JOBS + 1)); FL_CUDA(cudaMemset(h->d_fe_counters, 0, (FL_FE_MAX_JOBS + 1) * sizeof(unsigned)));
+  memset(h->fe_counter_base, 0, sizeof h->fe_counter_base);                             // [0] candidate count, [1] CTA ticket counter of k_refine_sort
   int kc = 2; while (kc < p.max_candidates) kc <<= 1;
   h->key_cap = kc;
   TRY(dalloc(&h->d_keys, (size_t)kc + 1));      // + room for the two scratch ints behind the keys
@@ -188,6 +192,7 @@ extern "C" int fl_destroy(fl_handle* h) {
     cudaFree(h->d_bgr[l]); cudaFree(h->d_lm[l]);
     for (int m = 0; m < FL_MAX_MODALITIES; ++m) { cudaFree(h->d_q[l][m]); cudaFree(h->d_qm[l][m]); cudaFree(h->d_mask[l][m]); cudaFree(h->d_spread[l][m]); }
   }
+  cudaFree(h->d_fe_counters);
   cudaFree(h->d_cand); cudaFree(h->d_count); cudaFree(h->d_keys); cudaFree(h->d_outblk);
   cudaFreeHost(h->h_bgr); cudaFreeHost(h->h_depth); cudaFreeHost(h->h_mask); cudaFreeHost(h->h_outblk); cudaFreeHost(h->h_class_enabled);
   for (int i = 0; i < 5; ++i) cudaEventDestroy(h->ev[i]);
@@ -355,8 +360,10 @@ static int ensure_geometry(fl_handle* h, int W, int H) {
 }
 
 // front end + matchClass on the handle's templates; candidates land in (cand, count)
+// defer_refine: leave the candidates at the coarsest level; the caller refines them in the same launch that sorts (k_refine_sort)
 static int run_match_stages(fl_handle* h, const uint8_t* d_bgr, const uint16_t* d_depth, int W, int H, const void* const* d_masks,
-                            float threshold, const int32_t* class_filter, int n_filter, fl_match_t* cand, int cap, int* d_count) {
+                            float threshold, const int32_t* class_filter, int n_filter, fl_match_t* cand, int cap, int* d_count,
+                            bool defer_refine = false) {
   const fl_params_t& p = h->p;
   FL_CUDA(cudaSetDevice(p.device));
   TRY(ensure_geometry(h, W, H));
@@ -395,7 +402,7 @@ static int run_match_stages(fl_handle* h, const uint8_t* d_bgr, const uint16_t* 
     // latency floor of one colour-tile CTA, about 8 us.)
     const int L = p.n_levels;
     fl_fe_wave w;
-    auto wave_begin = [&](bool zero) { w.n_jobs = 0; w.n_ctas = 0; w.smem = 0; w.n_pyr = 0; w.zero_me = zero ? d_count : nullptr; };
+    auto wave_begin = [&](bool zero) { w.n_jobs = 0; w.n_ctas = 0; w.smem = 0; w.n_pyr = 0; w.zero_me = zero ? d_count : nullptr; w.counters = nullptr; w.dep_error = nullptr; };
     auto wave_flush = [&]() { if (w.n_jobs > 0) { fl_launch_fe_wave(w, s); ++h->launches; } w.n_jobs = 0; w.n_ctas = 0; w.smem = 0; w.n_pyr = 0; w.zero_me = nullptr; };
     // word-parallel quantisers (frontend_v2.cuh); FL_FE_V1=1 selects the first, byte-granular versions (A/B timing).  The depth
     // job also writes the NN-downsampled label pyramid when every level halves exactly (then dst_l(y,x) = src(2^l y, 2^l x)).
@@ -404,6 +411,57 @@ static int run_match_stages(fl_handle* h, const uint8_t* d_bgr, const uint16_t* 
     bool halves = true;
     for (int l = 0; l + 1 < L; ++l) halves &= (h->geom[l].W % 2 == 0) && (h->geom[l].H % 2 == 0);
     auto wave_room = [&]() { if (w.n_jobs == FL_FE_MAX_JOBS) wave_flush(); };     // jobs of one wave are independent: splitting is always safe
+    // ---- single-launch front end: every job of the frame in ONE grid, producers before consumers, dependencies resolved by
+    // per-job CTA counters inside the kernel (k_front_end_wave).  Removes L launches + their dependency gaps and lets the
+    // level-0 work fill the machine while the short critical chain pyrDown -> colour L(top) -> spread L(top) runs.
+    static const bool fe_waves = getenv("FL_FE_WAVES") != nullptr;               // developer A/B: one launch per wave, as before
+    int n_color = 0, n_depth = 0;
+    for (int m = 0; m < p.n_modalities; ++m) { n_color += p.modality_kind[m] == FL_MODALITY_COLOR_GRADIENT; n_depth += p.modality_kind[m] == FL_MODALITY_DEPTH_NORMAL; }
+    const int n_jobs_single = (n_color ? L - 1 : 0) + n_color * L + n_depth + p.n_modalities * L;
+    const bool single = !fe_v1 && !fe_waves && n_jobs_single <= FL_FE_MAX_JOBS && n_depth <= FL_FE_MAX_DPYR && (L == 1 || (halves && L - 1 <= FL_FE_MAX_PYR));
+    if (single) {
+      wave_begin(zero_in_wave);
+      w.counters = h->d_fe_counters; w.dep_error = reinterpret_cast<int*>(h->d_fe_counters + FL_FE_MAX_JOBS);
+      int slot_pyr[FL_MAX_LEVELS], slot_color[FL_MAX_LEVELS][FL_MAX_MODALITIES], slot_depth[FL_MAX_MODALITIES];
+      auto last_job = [&]() -> fl_fe_job& { return w.job[w.n_jobs - 1]; };
+      auto job_ctas = [&](int idx) { return (idx + 1 < w.n_jobs ? w.job[idx + 1].cta_begin : w.n_ctas) - w.job[idx].cta_begin; };
+      auto produce = [&]() { last_job().signal_slot = w.n_jobs - 1; return w.n_jobs - 1; };
+      auto consume = [&](int slot) { last_job().wait_slot = slot; last_job().wait_target = h->fe_counter_base[slot] + (unsigned)job_ctas(slot); };
+      // 1. colour pyramid chain (short jobs, on the critical path of the coarsest level)
+      if (first_color >= 0)
+        for (int l = 0; l + 1 < L; ++l) {
+          fl_fe_add_pyrdown(&w, l == 0 ? d_bgr : h->d_bgr[l], h->geom[l].W, h->geom[l].H, h->d_bgr[l + 1]);
+          slot_pyr[l + 1] = produce();
+          if (l > 0) consume(slot_pyr[l]);
+        }
+      // 2. depth labels of every level (one job per depth modality)
+      for (int m = 0; m < p.n_modalities; ++m)
+        if (p.modality_kind[m] == FL_MODALITY_DEPTH_NORMAL) {
+          fl_depth_pyr pyr; memset(&pyr, 0, sizeof pyr);
+          pyr.n = L - 1;
+          for (int k = 1; k < L; ++k) { pyr.W[k - 1] = h->geom[k].W; pyr.H[k - 1] = h->geom[k].H; pyr.dst[k - 1] = h->d_q[k][m]; }
+          fl_fe_add_depth_v2(&w, d_depth, h->geom[0].W, h->geom[0].H, p.distance_threshold, p.difference_threshold, h->d_q[0][m], pyr.n > 0 ? &pyr : nullptr);
+          slot_depth[m] = produce();
+        }
+      // 3. colour labels, coarsest level first
+      for (int l = L - 1; l >= 0; --l)
+        for (int m = 0; m < p.n_modalities; ++m)
+          if (p.modality_kind[m] == FL_MODALITY_COLOR_GRADIENT) {
+            fl_fe_add_color_v2(&w, l == 0 ? d_bgr : h->d_bgr[l], h->geom[l].W, h->geom[l].H, thr_sq, h->d_q[l][m]);
+            slot_color[l][m] = produce();
+            if (l > 0) consume(slot_pyr[l]);
+          }
+      // 4. spread + response maps + linear memories, coarsest level first (the similarity kernel needs only that one)
+      for (int l = L - 1; l >= 0; --l)
+        for (int m = 0; m < p.n_modalities; ++m) {
+          uint8_t* spread = nullptr;
+          if (h->keep_spread) { if (!h->d_spread[l][m]) TRY(dalloc(&h->d_spread[l][m], (size_t)(p.max_width >> l) * (p.max_height >> l))); spread = h->d_spread[l][m]; }
+          fl_fe_add_spread(&w, h->d_q[l][m], h->geom[l], h->d_lm[l] + (size_t)m * h->geom[l].mod_stride, spread);
+          consume(p.modality_kind[m] == FL_MODALITY_COLOR_GRADIENT ? slot_color[l][m] : slot_depth[m]);
+        }
+      for (int i = 0; i < w.n_jobs; ++i) if (w.job[i].signal_slot >= 0) h->fe_counter_base[i] += (unsigned)job_ctas(i);
+      wave_flush();
+    } else
     for (int wv = 0; wv <= L; ++wv) {
       wave_begin(wv == 0 && zero_in_wave);                                        // the candidate counter is reset by the first wave
       const int l = wv;                                                             // level whose labels this wave produces
@@ -507,7 +565,7 @@ static int run_match_stages(fl_handle* h, const uint8_t* d_bgr, const uint16_t* 
     }
     ++h->launches;
     if (h->profile) cudaEventRecord(h->ev[2], s);
-    if (!refined)
+    if (!refined && !defer_refine)
       for (int l = p.n_levels - 2; l >= 0; --l) { fl_launch_refine_level(db, h->geom[l], l, h->d_lm[l], threshold, cand, cap, d_count, s); ++h->launches; }
   } else if (h->profile) cudaEventRecord(h->ev[2], s);
   if (h->profile) cudaEventRecord(h->ev[3], s);
@@ -517,7 +575,9 @@ static int run_match_stages(fl_handle* h, const uint8_t* d_bgr, const uint16_t* 
 
 // sort + unique of candidate lists into (d_out, d_out_count); handles the rare > 8,192-record path; leaves
 // h_small = {count, n_live, flag, raw list counts...} and, for the handle's own output block, the first matches in h_first
-static int run_sort_unique(fl_handle* h, fl_lists L, fl_match_t* d_out, int out_cap, int* d_out_count, bool fetch_first, const fl_xchg* xchg = nullptr) {
+struct fl_refine_req { float threshold; fl_match_t* cand; int cap; const int* d_count; };   // refine these candidates in the sort launch (k_refine_sort)
+static int run_sort_unique(fl_handle* h, fl_lists L, fl_match_t* d_out, int out_cap, int* d_out_count, bool fetch_first, const fl_xchg* xchg = nullptr,
+                           const fl_refine_req* refine = nullptr) {
   cudaStream_t s = h->stream;
   const int n_lists = L.n_lists, list_cap = L.list_cap;
   if ((int64_t)n_lists * list_cap > h->key_cap) { fl_set_error("sort capacity %d < %lld", h->key_cap, (long long)n_lists * list_cap); return FL_ERR_CAPACITY; }
@@ -527,8 +587,17 @@ static int run_sort_unique(fl_handle* h, fl_lists L, fl_match_t* d_out, int out_
   fl_xchg X;
   memset(&X, 0, sizeof X);
   if (xchg) X = *xchg;
-  h->launches += fl_launch_sort_unique(L, X, h->key_cap, d_out, out_cap, d_out_count, d_hdr, h->h_small, own ? h->h_first : nullptr,
-                                       std::min(FETCH_FIRST, out_cap), s);
+  if (refine) {
+    fl_refine_args ra;
+    memset(&ra, 0, sizeof ra);
+    ra.n_levels = h->p.n_levels;
+    for (int l = 0; l < h->p.n_levels; ++l) { ra.g[l] = h->geom[l]; ra.lm[l] = h->d_lm[l]; }
+    h->launches += fl_launch_refine_sort(make_tdb(h), ra, refine->threshold, refine->cand, refine->cap, refine->d_count, h->d_count + 1, h->n_sm, L, X, h->key_cap,
+                                         d_out, out_cap, d_out_count, d_hdr, h->h_small, own ? h->h_first : nullptr, std::min(FETCH_FIRST, out_cap), s);
+  } else {
+    h->launches += fl_launch_sort_unique(L, X, h->key_cap, d_out, out_cap, d_out_count, d_hdr, h->h_small, own ? h->h_first : nullptr,
+                                         std::min(FETCH_FIRST, out_cap), s);
+  }
   if (h->profile) cudaEventRecord(h->ev[4], s);
   FL_CUDA(cudaStreamSynchronize(s));
   h->overflow = false;
@@ -553,10 +622,16 @@ extern "C" int fl_match_device(fl_handle* h, const void* d_bgr, const void* d_de
                                float threshold, const int32_t* class_filter, int32_t n_filter) {
   if (!h) return FL_ERR_ARG;
   h->have_result = false;
+  // refinement and sort + unique share one launch (k_refine_sort) unless FL_SPLIT_REFINE=1 (developer A/B) or the staged kernel
+  // already refined (FL_FUSE_TAIL)
+  static const bool split_refine = getenv("FL_SPLIT_REFINE") != nullptr;
+  const bool defer = !split_refine && h->n_templates > 0 && h->p.n_levels > 1;
   TRY(run_match_stages(h, (const uint8_t*)d_bgr, (const uint16_t*)d_depth, W, H, d_masks, threshold, class_filter, n_filter, h->d_cand,
-                       h->p.max_candidates, h->d_count));
+                       h->p.max_candidates, h->d_count, defer));
   const fl_lists lists = {h->d_cand, 1, h->p.max_candidates, h->p.max_candidates, h->d_count, 1};
-  TRY(run_sort_unique(h, lists, h->d_out, h->p.max_candidates, h->d_out_count, true));
+  const bool in_sort = defer && !(h->use_staged && h->plan.fuse_list_cap > 0);
+  const fl_refine_req req = {threshold, h->d_cand, h->p.max_candidates, h->d_count};
+  TRY(run_sort_unique(h, lists, h->d_out, h->p.max_candidates, h->d_out_count, true, nullptr, in_sort ? &req : nullptr));
   if (h->h_small[14]) {
     // one CTA of the staged kernel found more coarse candidates than its shared-memory list holds (very low thresholds):
     // run the frame again with the refinement as separate launches

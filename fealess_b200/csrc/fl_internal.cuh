@@ -74,13 +74,18 @@ struct fl_fe_job {
   float thr_sq;
   const uint8_t* src; uint8_t* dst; uint8_t* dst2;
   fl_level_geom g;
+  // in-grid dependencies (single-launch front end): a CTA of this job first waits until counters[wait_slot] has reached
+  // wait_target (all CTAs of the producing job have finished), and bumps counters[signal_slot] when it is done; -1 = none
+  int wait_slot, signal_slot;
+  unsigned wait_target;
 };
 // NN-downsampled copies of the level-0 depth labels written by the depth job itself: entry i = pyramid level i + 1
 #define FL_FE_MAX_PYR 7
 struct fl_depth_pyr { int n; int W[FL_FE_MAX_PYR], H[FL_FE_MAX_PYR]; uint8_t* dst[FL_FE_MAX_PYR]; };
 #define FL_FE_MAX_JOBS 16
 #define FL_FE_MAX_DPYR 2
-struct fl_fe_wave { int n_jobs, n_ctas; size_t smem; int* zero_me; fl_fe_job job[FL_FE_MAX_JOBS]; int n_pyr; fl_depth_pyr pyr[FL_FE_MAX_DPYR]; };   // zero_me: int reset by CTA 0 (candidate counter), or NULL
+struct fl_fe_wave { int n_jobs, n_ctas; size_t smem; int* zero_me; fl_fe_job job[FL_FE_MAX_JOBS]; int n_pyr; fl_depth_pyr pyr[FL_FE_MAX_DPYR];
+                    unsigned* counters; int* dep_error; };   // zero_me: int reset by CTA 0 (candidate counter), or NULL; counters: FL_FE_MAX_JOBS monotonic CTA counters
 void fl_fe_add_color(fl_fe_wave* w, const uint8_t* bgr, int W, int H, float thr_sq, uint8_t* q, int part, int n_parts);
 void fl_fe_add_depth(fl_fe_wave* w, const uint16_t* depth, int W, int H, int dist_thr, int diff_thr, uint8_t* q);
 // word-parallel variants (frontend_v2.cuh); pyr (nullable, at most FL_FE_MAX_DPYR per wave): also write the NN pyramid of the labels
@@ -155,6 +160,10 @@ struct fl_xchg { int world, rank, cap; unsigned epoch; const fl_match_t* local_b
 // + 1 int).  Both return the number of launches.  h_hdr / h_first: mapped pinned host copies of the summary and of the
 // first h_first_cap matches (nullable).
 int fl_launch_sort_unique(fl_lists L, fl_xchg X, int key_cap, fl_match_t* d_out, int out_cap, int* d_out_count, int* d_hdr,
+                          int* h_hdr, fl_match_t* h_first, int h_first_cap, cudaStream_t s);
+// refinement of every level + sort + unique in one launch (the last CTA to finish sorts); done_ctr: zero-initialised device int
+int fl_launch_refine_sort(fl_tdb db, const fl_refine_args& ra, float threshold, fl_match_t* cand, int cap, const int* d_count, int* done_ctr, int n_sm,
+                          fl_lists L, fl_xchg X, int key_cap, fl_match_t* d_out, int out_cap, int* d_out_count, int* d_hdr,
                           int* h_hdr, fl_match_t* h_first, int h_first_cap, cudaStream_t s);
 int fl_launch_sort_unique_big(fl_lists L, fl_sort_key* keys, int key_cap, int n_upper, fl_match_t* d_out, int out_cap, int* d_out_count, cudaStream_t s);
 

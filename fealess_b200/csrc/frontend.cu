@@ -227,7 +227,7 @@ __device__ __forceinline__ void dev_pyrdown_bgr(const uint8_t* __restrict__ src,
     for (int t = 0; t < 5; ++t) {
       const int kt = t == 0 || t == 4 ? 1 : (t == 2 ? 6 : 4);
       const uint8_t* p = row + cx[t];
-      r0 += kt * p[0]; r1 += kt * p[1]; r2 += kt * p[2];
+      r0 += kt * __ldcg(p); r1 += kt * __ldcg(p + 1); r2 += kt * __ldcg(p + 2);   // L2 loads: the source may come from an earlier job of this launch
     }
     s0 += kj * r0; s1 += kj * r1; s2 += kj * r2;
   }
@@ -427,7 +427,7 @@ __device__ __forceinline__ void dev_spread_lm(const uint8_t* __restrict__ q, con
   for (int r = warp; r < th; r += NWARP) {              // rows by warp, bytes by lane: coalesced, no index arithmetic
     const int y = py0 + r;
     const uint8_t* src = q + (size_t)y * W + px0;
-    for (int c = lane; c < st_in; c += 32) s_in[r * st_in + c] = (c < tw && px0 + c < W && y < H) ? src[c] : (uint8_t)0;   // clipped window == OR with zeros
+    for (int c = lane; c < st_in; c += 32) s_in[r * st_in + c] = (c < tw && px0 + c < W && y < H) ? __ldcg(src + c) : (uint8_t)0;   // clipped window == OR with zeros
   }
   __syncthreads();
   for (int r = warp; r < th; r += NWARP) {              // horizontal OR, four pixels per thread
@@ -513,7 +513,7 @@ void fl_launch_spread_lm(const uint8_t* q, fl_level_geom g, uint8_t* lm_mod, uin
 //   wave k >= 1 : colour quantise Lk | NN-downsample depth labels Lk | pyrDown Lk->Lk+1 | spread+LM of level k-1 (all modalities)
 //   last wave   : spread+LM of the coarsest level
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 8) k_front_end_wave(fl_fe_wave w) {
+__global__ void __launch_bounds__(256, 6) k_front_end_wave(fl_fe_wave w) {
   extern __shared__ __align__(16) uint8_t smem_dyn[];
   const int b = blockIdx.x;
   fl_grid_dep_wait();                                   // the previous kernel of the stream wrote this wave's inputs
@@ -524,6 +524,23 @@ __global__ void __launch_bounds__(256, 8) k_front_end_wave(fl_fe_wave w) {
   while (j + 1 < w.n_jobs && b >= w.job[j + 1].cta_begin) ++j;
   const fl_fe_job& jb = w.job[j];
   const int local = b - jb.cta_begin;
+  if (jb.wait_slot >= 0) {
+    // In-grid dependency: CTAs are dispatched in blockIdx order and a producing job always precedes its consumers in the grid,
+    // so every producer CTA is resident (or done) before a consumer starts to wait here.  The wait is bounded: after ~1 s it gives
+    // up and raises dep_error instead of hanging the device.
+    if (threadIdx.x == 0) {
+      const unsigned* c = w.counters + jb.wait_slot;
+      const long long t0 = clock64();
+      unsigned v;
+      for (;;) {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(c) : "memory");
+        if ((int)(v - jb.wait_target) >= 0) break;
+        if (clock64() - t0 > (1ll << 31)) { if (w.dep_error) *w.dep_error = 1; break; }
+        __nanosleep(64);
+      }
+    }
+    __syncthreads();
+  }
   switch (jb.kind) {
     case FL_JOB_COLOR: { const int tile = local + jb.p0; dev_color_quantize(jb.src, jb.W, jb.H, jb.thr_sq, jb.dst, tile % jb.gx, tile / jb.gx, smem_dyn); break; }
     case FL_JOB_DEPTH: dev_depth_quantize(reinterpret_cast<const uint16_t*>(jb.src), jb.W, jb.H, jb.p0, jb.p1, jb.dst, local % jb.gx, local / jb.gx, smem_dyn); break;
@@ -536,6 +553,10 @@ __global__ void __launch_bounds__(256, 8) k_front_end_wave(fl_fe_wave w) {
                             local % abs(jb.gx), local / abs(jb.gx), smem_dyn);
       break;
   }
+  if (jb.signal_slot >= 0) {
+    __syncthreads();                                    // every thread's stores of this CTA ...
+    if (threadIdx.x == 0) { __threadfence(); atomicAdd(w.counters + jb.signal_slot, 1u); }   // ... are visible before the count
+  }
 }
 
 // part / n_parts: the tiles of one image may be spread over several waves (the job then covers tiles [first, first + count))
@@ -544,18 +565,21 @@ void fl_fe_add_color(fl_fe_wave* w, const uint8_t* bgr, int W, int H, float thr_
   const int first = (int)((long long)tiles * part / n_parts), last = (int)((long long)tiles * (part + 1) / n_parts);
   if (last <= first) return;
   fl_fe_job& j = w->job[w->n_jobs++];
+  j.wait_slot = -1; j.signal_slot = -1; j.wait_target = 0;
   j.kind = FL_JOB_COLOR; j.src = bgr; j.dst = q; j.dst2 = nullptr; j.W = W; j.H = H; j.thr_sq = thr_sq;
   j.gx = gx; j.p0 = first; j.p1 = last - first; j.cta_begin = w->n_ctas; w->n_ctas += last - first;
   w->smem = w->smem > (size_t)CQ_SMEM_BYTES ? w->smem : (size_t)CQ_SMEM_BYTES;
 }
 void fl_fe_add_depth(fl_fe_wave* w, const uint16_t* depth, int W, int H, int dist_thr, int diff_thr, uint8_t* q) {
   fl_fe_job& j = w->job[w->n_jobs++];
+  j.wait_slot = -1; j.signal_slot = -1; j.wait_target = 0;
   j.kind = FL_JOB_DEPTH; j.src = reinterpret_cast<const uint8_t*>(depth); j.dst = q; j.dst2 = nullptr; j.W = W; j.H = H; j.p0 = dist_thr; j.p1 = diff_thr;
   j.gx = (W + DQ_TW - 1) / DQ_TW; j.cta_begin = w->n_ctas; w->n_ctas += j.gx * ((H + DQ_TH - 1) / DQ_TH);
   w->smem = w->smem > (size_t)DQ_SMEM_BYTES ? w->smem : (size_t)DQ_SMEM_BYTES;
 }
 void fl_fe_add_color_v2(fl_fe_wave* w, const uint8_t* bgr, int W, int H, float thr_sq, uint8_t* q) {
   fl_fe_job& j = w->job[w->n_jobs++];
+  j.wait_slot = -1; j.signal_slot = -1; j.wait_target = 0;
   j.kind = FL_JOB_COLOR2; j.src = bgr; j.dst = q; j.dst2 = nullptr; j.W = W; j.H = H; j.thr_sq = thr_sq;
   j.gx = (W + C2_TW - 1) / C2_TW; j.p0 = j.p1 = 0; j.cta_begin = w->n_ctas; w->n_ctas += j.gx * ((H + C2_TH - 1) / C2_TH);
   w->smem = w->smem > (size_t)C2_SMEM_BYTES ? w->smem : (size_t)C2_SMEM_BYTES;
@@ -569,6 +593,7 @@ bool fl_fe_add_depth_v2(fl_fe_wave* w, const uint16_t* depth, int W, int H, int 
     w->pyr[slot] = *pyr;
   }
   fl_fe_job& j = w->job[w->n_jobs++];
+  j.wait_slot = -1; j.signal_slot = -1; j.wait_target = 0;
   j.kind = FL_JOB_DEPTH2; j.src = reinterpret_cast<const uint8_t*>(depth); j.dst = q; j.dst2 = nullptr; j.W = W; j.H = H; j.p0 = dist_thr; j.p1 = diff_thr;
   const int gx = (W + D2_TW - 1) / D2_TW;
   j.gx = slot < 0 ? -gx : gx; j.thr_sq = (float)(slot < 0 ? 0 : slot);            // gx < 0: no pyramid; thr_sq carries the pyramid slot
@@ -578,16 +603,19 @@ bool fl_fe_add_depth_v2(fl_fe_wave* w, const uint16_t* depth, int W, int H, int 
 }
 void fl_fe_add_pyrdown(fl_fe_wave* w, const uint8_t* src, int W, int H, uint8_t* dst) {
   fl_fe_job& j = w->job[w->n_jobs++];
+  j.wait_slot = -1; j.signal_slot = -1; j.wait_target = 0;
   j.kind = FL_JOB_PYRDOWN; j.src = src; j.dst = dst; j.dst2 = nullptr; j.W = W; j.H = H; j.gx = 1;
   j.cta_begin = w->n_ctas; w->n_ctas += pyrdown_ctas(W, H);
 }
 void fl_fe_add_resize(fl_fe_wave* w, const uint8_t* src, int W, int H, uint8_t* dst) {
   fl_fe_job& j = w->job[w->n_jobs++];
+  j.wait_slot = -1; j.signal_slot = -1; j.wait_target = 0;
   j.kind = FL_JOB_RESIZE; j.src = src; j.dst = dst; j.dst2 = nullptr; j.W = W; j.H = H; j.gx = 1;
   j.cta_begin = w->n_ctas; w->n_ctas += ((W / 2) * (H / 2) + 255) / 256;
 }
 void fl_fe_add_spread(fl_fe_wave* w, const uint8_t* q, fl_level_geom g, uint8_t* lm_mod, uint8_t* spread_or_null) {
   fl_fe_job& j = w->job[w->n_jobs++];
+  j.wait_slot = -1; j.signal_slot = -1; j.wait_target = 0;
   j.kind = FL_JOB_SPREAD; j.src = q; j.dst = lm_mod; j.dst2 = spread_or_null; j.g = g; j.W = g.W; j.H = g.H;
   int cw = SL_CW;                                       // small levels: narrower CTAs so that the job still fills the SMs
   while (cw > 8 && ((g.Wd + cw - 1) / cw) * g.Hd < 148) cw >>= 1;

@@ -68,13 +68,13 @@ __device__ __forceinline__ void dev_color_quantize_v2(const uint8_t* __restrict_
     uint32_t w0, w1, w2;
     if (aligned && sx >= 0 && sx + 3 < W) {
       const uint32_t* p = reinterpret_cast<const uint32_t*>(bgr + ((size_t)sy * W + sx) * 3);
-      w0 = __ldg(p); w1 = __ldg(p + 1); w2 = __ldg(p + 2);
+      w0 = __ldcg(p); w1 = __ldcg(p + 1); w2 = __ldcg(p + 2);           // L2 loads: a pyramid level may come from an earlier job of this launch
     } else {
       uint32_t b[12];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const uint8_t* p = bgr + ((size_t)sy * W + clampi(sx + j, 0, W - 1)) * 3;
-        b[3 * j] = p[0]; b[3 * j + 1] = p[1]; b[3 * j + 2] = p[2];
+        b[3 * j] = __ldcg(p); b[3 * j + 1] = __ldcg(p + 1); b[3 * j + 2] = __ldcg(p + 2);
       }
       w0 = b[0] | b[1] << 8 | b[2] << 16 | b[3] << 24;
       w1 = b[4] | b[5] << 8 | b[6] << 16 | b[7] << 24;

@@ -130,115 +130,137 @@ void fl_launch_similarity_debug(fl_tdb db, fl_level_geom g, const uint8_t* lm_le
 #define RF_THREADS 256       // 4 feature groups x 64 (16 patch rows x 4 column groups of 4 cells)
 #define RF_MAXF (FL_MAX_MODALITIES * 63)
 
+struct fl_refine_smem {                        // per group of RF_THREADS threads
+  uint32_t off[RF_MAXF];                       // byte offset of every feature's window origin inside the level's linear memories, or FL_SKIP
+  int mbeg[FL_MAX_MODALITIES + 1];
+  uint32_t part[3][64][2];
+  uint32_t best[2];
+  fl_match_t mt;
+};
+
+__device__ __forceinline__ void group_sync(int bar_id) { asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(RF_THREADS) : "memory"); }
+
+// One level of local refinement of one candidate by a group of RF_THREADS threads (gt = thread index inside the group,
+// bar_id = the group's named barrier).  mt is the candidate at level + 1 on entry (template_id = handle-local template index) and
+// at `level` on return; template_id = -1 marks it dropped (:1570-1572).  Group-uniform control flow.
+__device__ __forceinline__ void refine_level_group(const fl_tdb& db, const fl_level_geom& g, int level, const uint8_t* __restrict__ lm_level,
+                                                   float threshold, fl_match_t& mt, fl_refine_smem& sm, int gt, int bar_id) {
+  const int fgrp = gt >> 6, cell = gt & 63;
+  const int row = cell >> 2, cg = cell & 3;
+  const int T = g.T, border = 8 * T;
+  const int t = mt.template_id;                                    // handle-local template index (see k_similarity_global)
+  const fl_template_hdr_t* hdr = db.hdr + ((size_t)t * db.L + level) * db.M;
+  int x = mt.x * 2 + 1, y = mt.y * 2 + 1;                          // :1525-1534
+  x = max(x, border); y = max(y, border);
+  x = min(x, g.W - hdr[0].width - border);
+  y = min(y, g.H - hdr[0].height - border);
+  const int ox = (x / T - 8) * T, oy = (y / T - 8) * T;            // :1240-1241 (C division truncates towards zero)
+  const int delta = (oy / T) * g.Wd + ox / T;
+  // stage 1: one thread per feature resolves the feature's window origin (all modalities), so that stage 2 issues
+  // nothing but independent linear-memory loads
+  int nf = 0;
+  for (int m = 0; m < db.M; ++m) {
+    const fl_template_hdr_t h = hdr[m];
+    if (gt == 0) sm.mbeg[m] = nf;
+    for (int k = gt; k < h.feature_count; k += RF_THREADS) {
+      const fl_pfeat p = db.pfeat[h.feature_begin + k];
+      const int fx = p.x + ox, fy = p.y + oy;
+      uint32_t o = FL_SKIP;
+      if (fx >= 0 && fy >= 0 && fx < g.W && fy < g.H) {            // :1257
+        // the packed offset was computed for (x, y); shifting by a multiple of T moves only the cell index
+        if (p.lm_off == FL_SKIP)                                   // outside the image unshifted, inside when shifted
+          o = (uint32_t)((size_t)db.feat[h.feature_begin + k].label * g.label_stride +
+                         (size_t)((p.y % T + T) % T * T + (p.x % T + T) % T) * g.cells + (size_t)(fy / T) * g.Wd + fx / T);
+        else
+          o = (uint32_t)((int)p.lm_off + delta);
+        o += (uint32_t)((size_t)m * g.mod_stride);
+      }
+      sm.off[nf + k] = o;
+    }
+    nf += h.feature_count;
+  }
+  if (gt == 0) sm.mbeg[db.M] = nf;
+  group_sync(bar_id);
+  // stage 2: 16x16 patch, thread = (feature group, patch row, 4-cell column group); u8 lanes per modality (<= 63 x 4)
+  const uint32_t cell_off = (uint32_t)(row * g.Wd + cg * 4);
+  uint32_t tot_lo = 0, tot_hi = 0;
+  for (int m = 0; m < db.M; ++m) {
+    uint32_t acc = 0;
+    const int k1 = sm.mbeg[m + 1];
+    // <= 63 features per modality (:1231) = <= 16 per feature group: all loads of a modality are issued before the first
+    // add (one L2 round trip instead of one per unroll step)
+    for (int k0 = sm.mbeg[m] + fgrp; k0 < k1; k0 += 64) {
+      uint32_t lo[16], hi[16], sh[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int k = k0 + 4 * u;
+        const uint32_t o = k < k1 ? sm.off[k] : FL_SKIP;
+        const uint32_t a = o + cell_off;
+        sh[u] = (a & 3) * 8;
+        lo[u] = hi[u] = 0;
+        if (o != FL_SKIP) {
+          const uint32_t* w = reinterpret_cast<const uint32_t*>(lm_level) + (a >> 2);
+          lo[u] = __ldg(w); hi[u] = __ldg(w + 1);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 16; ++u) acc += __funnelshift_r(lo[u], hi[u], sh[u]);
+    }
+    tot_lo += (acc & 0xFF) | ((acc & 0xFF00) << 8);
+    tot_hi += ((acc >> 16) & 0xFF) | ((acc >> 24) << 16);
+  }
+  if (fgrp > 0) { sm.part[fgrp - 1][cell][0] = tot_lo; sm.part[fgrp - 1][cell][1] = tot_hi; }
+  group_sync(bar_id);
+  if (fgrp == 0) {
+#pragma unroll
+    for (int gq = 0; gq < 3; ++gq) { tot_lo += sm.part[gq][cell][0]; tot_hi += sm.part[gq][cell][1]; }   // u16 lanes
+    // first maximum in row-major order: key = score << 8 | (255 - index); all-zero patch -> best 0 at (-1,-1) (:1547-1562)
+    uint32_t key = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint32_t sc = (k < 2 ? tot_lo >> (16 * k) : tot_hi >> (16 * (k - 2))) & 0xFFFF;
+      uint32_t idx = row * 16 + cg * 4 + k;
+      uint32_t kk = (sc << 8) | (255 - idx);
+      if (sc > 0 && kk > key) key = kk;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) key = max(key, __shfl_xor_sync(0xffffffffu, key, o));
+    if ((gt & 31) == 0) sm.best[gt >> 5] = key;
+  }
+  group_sync(bar_id);
+  if (gt == 0) {
+    uint32_t kb = max(sm.best[0], sm.best[1]);
+    int best = (int)(kb >> 8), br = -1, bc = -1;
+    if (best > 0) { int idx = 255 - (int)(kb & 255); br = idx >> 4; bc = idx & 15; }
+    const int off = T / 2 + (T % 2 - 1);
+    fl_match_t r = mt;
+    r.x = (x / T - 8 + bc) * T + off;                              // :1564-1566
+    r.y = (y / T - 8 + br) * T + off;
+    r.similarity = __fdiv_rn(__fmul_rn((float)best, 100.f), (float)(4 * nf));
+    if (r.similarity < threshold) r.template_id = -1;              // mark dropped (remove_if :1570)
+    sm.mt = r;
+  }
+  group_sync(bar_id);
+  mt = sm.mt;
+  group_sync(bar_id);                                              // sm is free for the next level / candidate
+}
+
 __global__ void __launch_bounds__(RF_THREADS) k_refine_level(fl_tdb db, fl_level_geom g, int level, const uint8_t* __restrict__ lm_level,
                                                              float threshold, fl_match_t* __restrict__ cand, int cap,
                                                              const int* __restrict__ d_count) {
   fl_grid_dep_wait();
   fl_grid_dep_launch();
+  __shared__ fl_refine_smem sm;
   const int n = min(*d_count, cap);
-  const int fgrp = threadIdx.x >> 6, cell = threadIdx.x & 63;
-  const int row = cell >> 2, cg = cell & 3;
-  __shared__ uint32_t s_off[RF_MAXF];          // byte offset of every feature's window origin inside the level's linear memories, or FL_SKIP
-  __shared__ int s_mbeg[FL_MAX_MODALITIES + 1];
-  __shared__ uint32_t s_part[3][64][2];
-  __shared__ uint32_t s_best[2];
-  const int T = g.T, border = 8 * T;
   for (int ci = blockIdx.x; ci < n; ci += gridDim.x) {
     fl_match_t mt = cand[ci];
     if (mt.template_id < 0) continue;                              // dropped at a coarser level (:1570-1572)
-    const int t = mt.template_id;                                  // handle-local template index (see k_similarity_global)
-    const fl_template_hdr_t* hdr = db.hdr + ((size_t)t * db.L + level) * db.M;
-    int x = mt.x * 2 + 1, y = mt.y * 2 + 1;                        // :1525-1534
-    x = max(x, border); y = max(y, border);
-    x = min(x, g.W - hdr[0].width - border);
-    y = min(y, g.H - hdr[0].height - border);
-    const int ox = (x / T - 8) * T, oy = (y / T - 8) * T;          // :1240-1241 (C division truncates towards zero)
-    const int delta = (oy / T) * g.Wd + ox / T;
-    // stage 1: one thread per feature resolves the feature's window origin (all modalities), so that stage 2 issues
-    // nothing but independent linear-memory loads
-    int nf = 0;
-    for (int m = 0; m < db.M; ++m) {
-      const fl_template_hdr_t h = hdr[m];
-      if (threadIdx.x == 0) s_mbeg[m] = nf;
-      for (int k = threadIdx.x; k < h.feature_count; k += RF_THREADS) {
-        const fl_pfeat p = db.pfeat[h.feature_begin + k];
-        const int fx = p.x + ox, fy = p.y + oy;
-        uint32_t o = FL_SKIP;
-        if (fx >= 0 && fy >= 0 && fx < g.W && fy < g.H) {          // :1257
-          // the packed offset was computed for (x, y); shifting by a multiple of T moves only the cell index
-          if (p.lm_off == FL_SKIP)                                 // outside the image unshifted, inside when shifted
-            o = (uint32_t)((size_t)db.feat[h.feature_begin + k].label * g.label_stride +
-                           (size_t)((p.y % T + T) % T * T + (p.x % T + T) % T) * g.cells + (size_t)(fy / T) * g.Wd + fx / T);
-          else
-            o = (uint32_t)((int)p.lm_off + delta);
-          o += (uint32_t)((size_t)m * g.mod_stride);
-        }
-        s_off[nf + k] = o;
-      }
-      nf += h.feature_count;
-    }
-    if (threadIdx.x == 0) s_mbeg[db.M] = nf;
-    __syncthreads();
-    // stage 2: 16x16 patch, thread = (feature group, patch row, 4-cell column group); u8 lanes per modality (<= 63 x 4)
-    const uint32_t cell_off = (uint32_t)(row * g.Wd + cg * 4);
-    uint32_t tot_lo = 0, tot_hi = 0;
-    for (int m = 0; m < db.M; ++m) {
-      uint32_t acc = 0;
-      const int k1 = s_mbeg[m + 1];
-      // <= 63 features per modality (:1231) = <= 16 per feature group: all loads of a modality are issued before the first
-      // add (one L2 round trip instead of one per unroll step)
-      for (int k0 = s_mbeg[m] + fgrp; k0 < k1; k0 += 64) {
-        uint32_t lo[16], hi[16], sh[16];
-#pragma unroll
-        for (int u = 0; u < 16; ++u) {
-          const int k = k0 + 4 * u;
-          const uint32_t o = k < k1 ? s_off[k] : FL_SKIP;
-          const uint32_t a = o + cell_off;
-          sh[u] = (a & 3) * 8;
-          lo[u] = hi[u] = 0;
-          if (o != FL_SKIP) {
-            const uint32_t* w = reinterpret_cast<const uint32_t*>(lm_level) + (a >> 2);
-            lo[u] = __ldg(w); hi[u] = __ldg(w + 1);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 16; ++u) acc += __funnelshift_r(lo[u], hi[u], sh[u]);
-      }
-      tot_lo += (acc & 0xFF) | ((acc & 0xFF00) << 8);
-      tot_hi += ((acc >> 16) & 0xFF) | ((acc >> 24) << 16);
-    }
-    if (fgrp > 0) { s_part[fgrp - 1][cell][0] = tot_lo; s_part[fgrp - 1][cell][1] = tot_hi; }
-    __syncthreads();
-    if (fgrp == 0) {
-#pragma unroll
-      for (int gq = 0; gq < 3; ++gq) { tot_lo += s_part[gq][cell][0]; tot_hi += s_part[gq][cell][1]; }   // u16 lanes
-      // first maximum in row-major order: key = score << 8 | (255 - index); all-zero patch -> best 0 at (-1,-1) (:1547-1562)
-      uint32_t key = 0;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        uint32_t sc = (k < 2 ? tot_lo >> (16 * k) : tot_hi >> (16 * (k - 2))) & 0xFFFF;
-        uint32_t idx = row * 16 + cg * 4 + k;
-        uint32_t kk = (sc << 8) | (255 - idx);
-        if (sc > 0 && kk > key) key = kk;
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) key = max(key, __shfl_xor_sync(0xffffffffu, key, o));
-      if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = key;
-    }
-    __syncthreads();
+    const int t = mt.template_id;
+    refine_level_group(db, g, level, lm_level, threshold, mt, sm, threadIdx.x, 0);
     if (threadIdx.x == 0) {
-      uint32_t kb = max(s_best[0], s_best[1]);
-      int best = (int)(kb >> 8), br = -1, bc = -1;
-      if (best > 0) { int idx = 255 - (int)(kb & 255); br = idx >> 4; bc = idx & 15; }
-      const int off = T / 2 + (T % 2 - 1);
-      mt.x = (x / T - 8 + bc) * T + off;                           // :1564-1566
-      mt.y = (y / T - 8 + br) * T + off;
-      mt.similarity = __fdiv_rn(__fmul_rn((float)best, 100.f), (float)(4 * nf));
-      if (mt.similarity < threshold) mt.template_id = -1;         // mark dropped (remove_if :1570)
-      else if (level == 0) mt.template_id = db.tid_of[t];         // final per-class template_id
+      if (mt.template_id >= 0 && level == 0) mt.template_id = db.tid_of[t];   // final per-class template_id
       cand[ci] = mt;
     }
-    __syncthreads();
   }
 }
 
@@ -296,20 +318,39 @@ __global__ void __launch_bounds__(256) k_build_keys(fl_lists L, fl_sort_key* __r
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) { unsigned v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 
-__global__ void __launch_bounds__(1024) k_sort_unique_small(fl_lists L, fl_xchg X, int key_cap, int smem_keys, fl_match_t* __restrict__ out,
-                                                            int out_cap, int* __restrict__ d_out_count, int* __restrict__ d_hdr,
-                                                            int* __restrict__ h_hdr, fl_match_t* __restrict__ h_first, int h_first_cap) {
+// loads that must see what other CTAs of the SAME launch wrote (fused refine + sort): L2, not this SM's L1
+__device__ __forceinline__ int ld_count(const fl_lists& L, int l) { return __ldcg(L.n_in + (size_t)l * L.n_in_stride); }
+__device__ __forceinline__ fl_match_t ld_match(const fl_match_t* p) {
+  const int* q = reinterpret_cast<const int*>(p);
+  fl_match_t m;
+  m.x = __ldcg(q); m.y = __ldcg(q + 1); m.similarity = __int_as_float(__ldcg(q + 2)); m.class_idx = __ldcg(q + 3); m.template_id = __ldcg(q + 4);
+  return m;
+}
+
+__device__ __forceinline__ void sort_unique_body(fl_lists L, fl_xchg X, int key_cap, int smem_keys, fl_sort_key* s_k, fl_match_t* __restrict__ out,
+                                                 int out_cap, int* __restrict__ d_out_count, int* __restrict__ d_hdr,
+                                                 int* __restrict__ h_hdr, fl_match_t* __restrict__ h_first, int h_first_cap,
+                                                 int dbg_a = 0, int dbg_b = 0, int dbg_n = 0) {   // dbg_*: caller's timeline (ns) for h_hdr[8], [9], [11]
   // d_hdr (16 ints, handle-owned) = {unique count, n_live, flag_big, raw n_in[0..10], fused-tail overflow flag, exchange time-out}.  h_hdr / h_first (nullable) are the
   // same summary and the first matches in MAPPED PINNED HOST memory: the kernel posts them over PCIe itself, so the host
   // needs no device-to-host copy (and none of its ~8 us of copy-engine hand-over) before it can read the result.
-  extern __shared__ __align__(16) fl_sort_key s_k[];            // smem_keys keys
+  // Stores to mapped host memory cost ~0.7 us EACH when one thread issues them one after the other (measured: 6 us for the dozen
+  // header words), so the summary is staged in shared memory and leaves as ONE coalesced 64-byte store, the records as
+  // contiguous 128-byte warp stores.
   __shared__ int s_warp[32];
   __shared__ int s_n;
+  __shared__ int s_hdr[16];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  fl_grid_dep_wait();
-  fl_grid_dep_launch();
-  if (tid == 0) d_hdr[15] = 0;                                   // exchange time-out flag (1 + rank that never arrived)
+  unsigned long long t_body0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_body0));
+  if (tid < 16 && tid != 14) s_hdr[tid] = 0;                    // [15]: exchange time-out flag (1 + rank that never arrived)
+  if (tid == 32) s_hdr[14] = __ldcg(d_hdr + 14);                 // overflow flag of the fused refinement tail (set by the staged kernel): posted below, then cleared
   __syncthreads();
+  // one warp posts the staged summary: device copy (flag word cleared) and mapped host copy
+  auto post_header = [&]() {
+    if (tid < 16) { const int v = s_hdr[tid]; d_hdr[tid] = tid == 14 ? 0 : v; if (h_hdr) h_hdr[tid] = v; }
+    if (tid == 16 && d_out_count != d_hdr) *d_out_count = s_hdr[0];
+  };
   unsigned long long t_dbg[4] = {0, 0, 0, 0};
   if (X.world > 0) {
     // ---- peer exchange (see fl_xchg): push, publish, wait ----
@@ -331,7 +372,7 @@ __global__ void __launch_bounds__(1024) k_sort_unique_small(fl_lists L, fl_xchg 
       const unsigned* sig = reinterpret_cast<const unsigned*>(X.peer[X.rank]) + tid;
       const long long t0 = clock64();
       while ((int)(ld_acquire_sys(sig) - X.epoch) < 0) {
-        if (clock64() - t0 > (1ll << 32)) { d_hdr[15] = 1 + tid; break; }   // ~2 s: a peer never arrived; report instead of hanging
+        if (clock64() - t0 > (1ll << 32)) { s_hdr[15] = 1 + tid; break; }   // ~2 s: a peer never arrived; report instead of hanging
         __nanosleep(64);
       }
     }
@@ -343,18 +384,22 @@ __global__ void __launch_bounds__(1024) k_sort_unique_small(fl_lists L, fl_xchg 
   }
   const int n_lists = L.n_lists, list_cap = L.list_cap;
   int total = 0;
-  for (int l = 0; l < n_lists; ++l) total += min(max(L.n_in[(size_t)l * L.n_in_stride], 0), list_cap);
-  if (tid < 11) { const int c = tid < n_lists ? L.n_in[(size_t)tid * L.n_in_stride] : 0; d_hdr[3 + tid] = c; if (h_hdr) h_hdr[3 + tid] = c; }
-  if (tid == 0) { if (h_hdr) h_hdr[14] = d_hdr[14]; d_hdr[14] = 0; }   // overflow flag of the fused refinement tail (set by the staged kernel): post and clear
+  for (int l = 0; l < n_lists; ++l) total += min(max(ld_count(L, l), 0), list_cap);
+  if (tid < 11) s_hdr[3 + tid] = tid < n_lists ? ld_count(L, tid) : 0;
   if (total > smem_keys || total > key_cap) {
-    if (tid == 0) { d_hdr[0] = 0; d_hdr[1] = total; d_hdr[2] = 1; if (h_hdr) { h_hdr[0] = 0; h_hdr[1] = total; h_hdr[2] = 1; h_hdr[15] = d_hdr[15]; } }
+    if (tid == 0) { s_hdr[0] = 0; s_hdr[1] = total; s_hdr[2] = 1; }
+    __syncthreads();
+    post_header();
     return;
   }
+  __syncthreads();                                               // s_hdr[3..13] complete before threads retire
   // The launch always has 1,024 threads and room for SORT_SMEM_LARGE keys; a frame with few records (the common case)
   // retires all but 256 of them here, so that the ~30 barriers of the bitonic network stay cheap.
   const int nt = total > 1024 ? (int)blockDim.x : min(256, (int)blockDim.x);
   if (tid >= nt) return;
   auto sync_active = [&]() { asm volatile("bar.sync 1, %0;" ::"r"(nt) : "memory"); };
+  unsigned long long ts[5] = {0, 0, 0, 0, 0};
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts[0]));
   if (total <= 256) {
     // Few records (the common case): rank sort.  Thread i owns record i; its rank among the live records is the number of
     // keys that precede it (ties - fully identical records - broken by index), so the sort is one pass over shared memory
@@ -363,12 +408,13 @@ __global__ void __launch_bounds__(1024) k_sort_unique_small(fl_lists L, fl_xchg 
     bool live = false;
     if (tid < total) {
       int l = 0, k = tid;
-      for (;;) { const int c = min(max(L.n_in[(size_t)l * L.n_in_stride], 0), list_cap); if (k < c) break; k -= c; ++l; }
-      const fl_match_t m = L.in[(size_t)l * L.list_stride + k];
+      for (;;) { const int c = min(max(ld_count(L, l), 0), list_cap); if (k < c) break; k -= c; ++l; }
+      const fl_match_t m = ld_match(L.in + (size_t)l * L.list_stride + k);
       if (m.template_id >= 0) { key = make_key(m); live = true; }
     }
     s_k[tid] = key;
     sync_active();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts[1]));
     fl_sort_key* s_sorted = s_k + 256;
     if (live) {
       int rank = 0;
@@ -389,30 +435,46 @@ __global__ void __launch_bounds__(1024) k_sort_unique_small(fl_lists L, fl_xchg 
     sync_active();                                                 // every warp has read the live counts
     if (lane == 0) s_warp[warp] = __popc(keep_mask);
     sync_active();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts[2]));
     int pos = __popc(keep_mask & ((1u << lane) - 1)), n_unique = 0;
 #pragma unroll
     for (int w = 0; w < 8; ++w) { if (w < warp) pos += s_warp[w]; n_unique += s_warp[w]; }
+    int* s_out = reinterpret_cast<int*>(s_k + 512);               // staged records, 5 ints each (<= 256 records)
     if (keep) {
       const fl_match_t m = key_to_match(s_sorted[tid]);
-      if (pos < out_cap) out[pos] = m;
-      if (h_first && pos < h_first_cap) h_first[pos] = m;
+      int* o = s_out + 5 * pos;
+      o[0] = m.x; o[1] = m.y; o[2] = __float_as_int(m.similarity); o[3] = m.class_idx; o[4] = m.template_id;
     }
     if (tid == 0) {
-      *d_out_count = n_unique; d_hdr[0] = n_unique; d_hdr[1] = n; d_hdr[2] = 0;
-      if (h_hdr) { h_hdr[0] = n_unique; h_hdr[1] = n; h_hdr[2] = 0; h_hdr[15] = d_hdr[15]; }
-      if (h_hdr && X.world > 0 && X.world <= 4) {
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts[3]));
+      s_hdr[0] = n_unique; s_hdr[1] = n; s_hdr[2] = 0;
+      if (n_lists == 1) { s_hdr[4] = (int)(ts[0] - t_body0); s_hdr[5] = (int)(ts[1] - ts[0]); s_hdr[6] = (int)(ts[2] - ts[1]); s_hdr[7] = (int)(ts[3] - ts[2]); }   // developer timeline (ns)
+      if (X.world == 0) { s_hdr[8] = dbg_a; s_hdr[9] = dbg_b; s_hdr[10] = (int)(ts[3] - t_body0); s_hdr[11] = dbg_n; }
+      if (X.world > 0 && X.world <= 4) {
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_dbg[3]));
-        h_hdr[8] = (int)(t_dbg[1] - t_dbg[0]); h_hdr[9] = (int)(t_dbg[2] - t_dbg[1]); h_hdr[10] = (int)(t_dbg[3] - t_dbg[2]);
+        s_hdr[8] = (int)(t_dbg[1] - t_dbg[0]); s_hdr[9] = (int)(t_dbg[2] - t_dbg[1]); s_hdr[10] = (int)(t_dbg[3] - t_dbg[2]);
       }
     }
+    sync_active();
+    {
+      int* out_i = reinterpret_cast<int*>(out);
+      int* hf_i = reinterpret_cast<int*>(h_first);
+      const int n_out = 5 * min(n_unique, out_cap), n_hf = h_first ? 5 * min(n_unique, h_first_cap) : 0;
+      for (int i = tid; i < 5 * n_unique; i += nt) {
+        const int v = s_out[i];
+        if (i < n_out) out_i[i] = v;
+        if (i < n_hf) hf_i[i] = v;
+      }
+    }
+    post_header();
     return;
   }
   if (tid == 0) s_n = 0;
   sync_active();
   for (int i = tid; i < total; i += nt) {
     int l = 0, k = i;
-    for (;;) { const int c = min(max(L.n_in[(size_t)l * L.n_in_stride], 0), list_cap); if (k < c) break; k -= c; ++l; }
-    const fl_match_t m = L.in[(size_t)l * L.list_stride + k];
+    for (;;) { const int c = min(max(ld_count(L, l), 0), list_cap); if (k < c) break; k -= c; ++l; }
+    const fl_match_t m = ld_match(L.in + (size_t)l * L.list_stride + k);
     if (m.template_id >= 0) s_k[atomicAdd(&s_n, 1)] = make_key(m);          // dropped candidates carry template_id -1
   }
   sync_active();
@@ -459,13 +521,69 @@ __global__ void __launch_bounds__(1024) k_sort_unique_small(fl_lists L, fl_xchg 
       ++pos;
     }
   if (tid == 0) {
-    *d_out_count = s_warp[31]; d_hdr[0] = s_warp[31]; d_hdr[1] = n; d_hdr[2] = 0;
-    if (h_hdr) { h_hdr[0] = s_warp[31]; h_hdr[1] = n; h_hdr[2] = 0; h_hdr[15] = d_hdr[15]; }
-    if (h_hdr && X.world > 0 && X.world <= 4) {                  // developer timing of the exchange (ns): push, wait, sort
+    s_hdr[0] = s_warp[31]; s_hdr[1] = n; s_hdr[2] = 0;
+    if (X.world > 0 && X.world <= 4) {                           // developer timing of the exchange (ns): push, wait, sort
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_dbg[3]));
-      h_hdr[8] = (int)(t_dbg[1] - t_dbg[0]); h_hdr[9] = (int)(t_dbg[2] - t_dbg[1]); h_hdr[10] = (int)(t_dbg[3] - t_dbg[2]);
+      s_hdr[8] = (int)(t_dbg[1] - t_dbg[0]); s_hdr[9] = (int)(t_dbg[2] - t_dbg[1]); s_hdr[10] = (int)(t_dbg[3] - t_dbg[2]);
     }
   }
+  sync_active();
+  post_header();
+}
+
+__global__ void __launch_bounds__(1024) k_sort_unique_small(fl_lists L, fl_xchg X, int key_cap, int smem_keys, fl_match_t* __restrict__ out,
+                                                            int out_cap, int* __restrict__ d_out_count, int* __restrict__ d_hdr,
+                                                            int* __restrict__ h_hdr, fl_match_t* __restrict__ h_first, int h_first_cap) {
+  extern __shared__ __align__(16) fl_sort_key s_k[];            // smem_keys keys
+  fl_grid_dep_wait();
+  fl_grid_dep_launch();
+  sort_unique_body(L, X, key_cap, smem_keys, s_k, out, out_cap, d_out_count, d_hdr, h_hdr, h_first, h_first_cap);
+}
+
+// Refinement up the whole pyramid + sort + unique in ONE launch (the single-handle match path): RS_GROUPS groups of RF_THREADS
+// threads per CTA refine candidates (a candidate stays with its group for all levels, so no grid-wide step is needed between
+// levels); the CTA that finishes last (ticket on *done_ctr) then sorts the list, prunes duplicates and posts the result to
+// the host.  Saves the launch + dependency gap of every refinement level and of the sort kernel.
+#define RS_GROUPS 4
+__global__ void __launch_bounds__(RS_GROUPS * RF_THREADS, 1) k_refine_sort(const __grid_constant__ fl_tdb db, const __grid_constant__ fl_refine_args ra,
+                                                                          float threshold, fl_match_t* cand, int cap, const int* __restrict__ d_count,
+                                                                          int* done_ctr, fl_lists L, fl_xchg X, int key_cap, int smem_keys, fl_match_t* __restrict__ out,
+                                                                          int out_cap, int* __restrict__ d_out_count, int* __restrict__ d_hdr,
+                                                                          int* __restrict__ h_hdr, fl_match_t* __restrict__ h_first, int h_first_cap) {
+  extern __shared__ __align__(16) fl_sort_key s_k[];
+  __shared__ fl_refine_smem sm[RS_GROUPS];
+  __shared__ int s_last;
+  unsigned long long tq[4] = {0, 0, 0, 0};                          // developer timeline (ns), posted in h_hdr[8..11] when no exchange runs
+  fl_grid_dep_wait();
+  fl_grid_dep_launch();
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tq[0]));
+  const int grp = threadIdx.x / RF_THREADS, gt = threadIdx.x - grp * RF_THREADS;
+  const int n = min(*d_count, cap);
+  if (ra.n_levels > 1) {
+    for (int ci = blockIdx.x * RS_GROUPS + grp; ci < n; ci += gridDim.x * RS_GROUPS) {
+      fl_match_t mt = cand[ci];
+      if (mt.template_id < 0) continue;
+      const int t = mt.template_id;
+      for (int l = ra.n_levels - 2; l >= 0 && mt.template_id >= 0; --l) refine_level_group(db, ra.g[l], l, ra.lm[l], threshold, mt, sm[grp], gt, 1 + grp);
+      if (gt == 0) {
+        if (mt.template_id >= 0) mt.template_id = db.tid_of[t];    // final per-class template_id
+        cand[ci] = mt;
+      }
+    }
+  }
+  __syncthreads();
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tq[1]));
+  if (threadIdx.x == 0) {
+    __threadfence();                                               // this CTA's records before its ticket
+    const int ticket = atomicAdd(done_ctr, 1);
+    s_last = ticket == (int)gridDim.x - 1;
+    if (s_last) *done_ctr = 0;                                     // ready for the next launch
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tq[2]));
+  sort_unique_body(L, X, key_cap, smem_keys, s_k, out, out_cap, d_out_count, d_hdr, h_hdr, h_first, h_first_cap, (int)(tq[1] - tq[0]), (int)(tq[2] - tq[1]), n);
 }
 
 // large path: global bitonic steps + serial-chunk unique
@@ -523,6 +641,16 @@ int fl_launch_sort_unique(fl_lists L, fl_xchg X, int key_cap, fl_match_t* d_out,
   if (!configured) { cudaFuncSetAttribute(k_sort_unique_small, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM_LARGE * (int)sizeof(fl_sort_key)); configured = true; }
   fl_launch_pdl(k_sort_unique_small, dim3(1), dim3(1024), (size_t)SORT_SMEM_LARGE * sizeof(fl_sort_key), s, L, X, key_cap, (int)SORT_SMEM_LARGE, d_out, out_cap,
                 d_out_count, d_hdr, h_hdr, h_first, h_first_cap);
+  return 1;
+}
+
+int fl_launch_refine_sort(fl_tdb db, const fl_refine_args& ra, float threshold, fl_match_t* cand, int cap, const int* d_count, int* done_ctr, int n_sm,
+                          fl_lists L, fl_xchg X, int key_cap, fl_match_t* d_out, int out_cap, int* d_out_count, int* d_hdr,
+                          int* h_hdr, fl_match_t* h_first, int h_first_cap, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) { cudaFuncSetAttribute(k_refine_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM_LARGE * (int)sizeof(fl_sort_key)); configured = true; }
+  fl_launch_pdl(k_refine_sort, dim3(n_sm > 0 ? n_sm : 148), dim3(RS_GROUPS * RF_THREADS), (size_t)SORT_SMEM_LARGE * sizeof(fl_sort_key), s, db, ra, threshold, cand, cap,
+                d_count, done_ctr, L, X, key_cap, (int)SORT_SMEM_LARGE, d_out, out_cap, d_out_count, d_hdr, h_hdr, h_first, h_first_cap);
   return 1;
 }
 

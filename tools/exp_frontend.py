@@ -16,12 +16,23 @@ rc, _, q = h.match(frames[0][0], frames[0][1], 75.0, want_quantized=True)
 ts = synth.make_templates(NT, W, H, T, seed=1, quantized=q, planted_fraction=0.01)
 h.upload_templates(ts)
 h.profile(True)
+import ctypes as C
 st = np.zeros(4); n = 0
+tl = np.zeros(4)
+tl2 = np.zeros(4)
+cnt = np.zeros(16, np.int32)
 for it in range(104):
     b, d = frames[it % 4]
     rc, m = h.match(b, d, 75.0)
     if it >= 4:
         st += h.last_stage_ms(); n += 1
+        fb.lib().fl_debug_get(h._h, 5, 0, 0, 0, C.c_void_p(cnt.ctypes.data), C.c_size_t(cnt.nbytes))
+        tl += cnt[8:12]
+        tl2 += cnt[4:8]
 st /= n
-print("FL_FE_V1=%s | matches %d | stage us: fe %.1f sim %.1f refine %.1f sort %.1f total %.1f"
-      % (os.environ.get("FL_FE_V1"), len(m), *(1e3 * st), 1e3 * st.sum()), flush=True)
+tl /= n
+tl2 /= n
+print("sort body (rank path) timeline, mean us: counts %.2f, gather %.2f, rank+scan %.2f, output %.2f" % tuple(tl2 / 1e3))
+print("refine+sort kernel timeline (last CTA), mean: refine %.2f us, ticket %.2f us, sort %.2f us, candidates %.1f" % (tl[0] / 1e3, tl[1] / 1e3, tl[2] / 1e3, tl[3]))
+print("env %s | matches %d | stage us: fe %.1f sim %.1f refine %.1f sort %.1f total %.1f"
+      % ({k: v for k, v in os.environ.items() if k.startswith("FL_")}, len(m), *(1e3 * st), 1e3 * st.sum()), flush=True)
