@@ -223,12 +223,19 @@ def run_ours(args):
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
             e0.record(stream)
+        # enqueue the frame, record the end event right behind its last kernel, THEN let the host wait: the events bracket the
+        # device work only (the synchronous call would put the host's wake-up + event-enqueue latency, ~20 us, inside them)
         if world == 1:
-            h.match_device(tb.data_ptr(), td.data_ptr(), W, H, THRESHOLD)
-        else:
-            sm.match_device(tb.data_ptr(), td.data_ptr(), W, H, THRESHOLD)
-        with torch.cuda.stream(stream):
+            h.match_device_async(tb.data_ptr(), td.data_ptr(), W, H, THRESHOLD)
             e1.record(stream)
+            h.match_wait()
+        else:
+            whole = sm.match_device_async(tb.data_ptr(), td.data_ptr(), W, H, THRESHOLD)
+            if whole:
+                e1.record(stream)
+            sm.match_wait()
+            if not whole:                                              # NCCL exchange: the collective + merge are issued by match_wait
+                e1.record(stream)
         return e0, e1
 
     for i in range(args.warmup):

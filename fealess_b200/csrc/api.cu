@@ -28,7 +28,7 @@ struct fl_handle {
   // template database
   int n_templates, n_features, n_classes;
   fl_template_hdr_t* d_hdr; fl_feature_t* d_feat; int32_t* d_class_of; int32_t* d_class_first; uint8_t* d_class_enabled;
-  fl_pfeat* d_pfeat; int32_t* d_tid_of;
+  fl_pfeat* d_pfeat; int32_t* d_tid_of; uint8_t* d_rrec;
   std::vector<int32_t> tid_of_h;
   std::vector<int32_t> coarse_wh;                          // (width, height) of every template at the coarsest level
   bool staged_eligible, use_staged; int n_sm; int force_baseline;   // staged global-similarity kernel (similarity_staged.cu)
@@ -48,6 +48,9 @@ struct fl_handle {
   uint8_t* d_spread[FL_MAX_LEVELS][FL_MAX_MODALITIES];     // debug only
   uint8_t* d_lm[FL_MAX_LEVELS]; size_t lm_bytes[FL_MAX_LEVELS];
   bool used_mask[FL_MAX_MODALITIES]; bool keep_spread;
+  // state between the enqueue half (fl_match_device_async, ..._async) and fl_match_wait
+  bool pend_sort, pend_match, pend_own, pend_masks_valid; fl_lists pend_lists; fl_match_t* pend_out; int pend_out_cap; int* pend_out_count;
+  const void* pend_bgr; const void* pend_depth; int pend_W, pend_H; float pend_threshold; const void* pend_masks[FL_MAX_MODALITIES]; std::vector<int32_t> pend_filter;
   unsigned* d_fe_counters; unsigned fe_counter_base[FL_FE_MAX_JOBS];   // in-grid dependency counters of the single-launch front end (+ 1 error word)
   // candidates / matches
   fl_match_t* d_cand; int* d_count; fl_sort_key* d_keys; int key_cap; uint8_t* d_outblk; fl_match_t* d_out; int* d_out_count;   // d_outblk = [16-int summary][matches]
@@ -115,7 +118,7 @@ extern "C" int fl_create(const fl_params_t* params, fl_handle** out) {
   if (!h) return FL_ERR_ARG;
   h->p = p; h->class_enabled_valid = false; h->launches = 0; h->gW = h->gH = 0; h->packed = false; h->have_result = false; h->profile = false; h->keep_spread = false;
   h->n_templates = h->n_features = h->n_classes = 0;
-  h->d_hdr = nullptr; h->d_feat = nullptr; h->d_class_of = nullptr; h->d_class_first = nullptr; h->d_class_enabled = nullptr; h->d_pfeat = nullptr;
+  h->d_hdr = nullptr; h->d_feat = nullptr; h->d_class_of = nullptr; h->d_class_first = nullptr; h->d_class_enabled = nullptr; h->d_pfeat = nullptr; h->d_rrec = nullptr;
   h->d_tid_of = nullptr;
   h->staged_eligible = false; h->use_staged = false; h->force_baseline = 0; memset(&h->plan, 0, sizeof h->plan);
   { cudaDeviceProp prop; FL_CUDA(cudaGetDeviceProperties(&prop, p.device)); h->n_sm = prop.multiProcessorCount; }
@@ -147,7 +150,8 @@ extern "C" int fl_create(const fl_params_t* params, fl_handle** out) {
   TRY(dalloc(&h->d_cand, (size_t)p.max_candidates)); TRY(dalloc(&h->d_count, 4));
   FL_CUDA(cudaMemset(h->d_count, 0, 4 * sizeof(int)));
   TRY(dalloc(&h->d_fe_counters, FL_FE_MAX_JOBS + 1)); FL_CUDA(cudaMemset(h->d_fe_counters, 0, (FL_FE_MAX_JOBS + 1) * sizeof(unsigned)));
-  memset(h->fe_counter_base, 0, sizeof h->fe_counter_base);                             // [0] candidate count, [1] CTA ticket counter of k_refine_sort
+  memset(h->fe_counter_base, 0, sizeof h->fe_counter_base);
+  h->pend_sort = h->pend_match = false;                             // [0] candidate count, [1] CTA ticket counter of k_refine_sort
   int kc = 2; while (kc < p.max_candidates) kc <<= 1;
   h->key_cap = kc;
   TRY(dalloc(&h->d_keys, (size_t)kc + 1));      // + room for the two scratch ints behind the keys
@@ -172,11 +176,11 @@ static void icp_free(fl_handle* h) {
 }
 
 static void free_templates(fl_handle* h) {
-  cudaFree(h->d_hdr); cudaFree(h->d_feat); cudaFree(h->d_class_of); cudaFree(h->d_class_first); cudaFree(h->d_class_enabled); cudaFree(h->d_pfeat);
+  cudaFree(h->d_hdr); cudaFree(h->d_feat); cudaFree(h->d_class_of); cudaFree(h->d_class_first); cudaFree(h->d_class_enabled); cudaFree(h->d_pfeat); cudaFree(h->d_rrec);
   cudaFree(h->d_tid_of); cudaFree(h->plan.gfeat); cudaFree(h->plan.gpre); cudaFree(h->plan.gmeta); cudaFree(h->plan.trace);
   h->plan.gfeat = nullptr; h->plan.gpre = nullptr; h->plan.gmeta = nullptr; h->plan.trace = nullptr;
   h->use_staged = false; h->staged_eligible = false;
-  h->d_hdr = nullptr; h->d_feat = nullptr; h->d_class_of = nullptr; h->d_class_first = nullptr; h->d_class_enabled = nullptr; h->d_pfeat = nullptr;
+  h->d_hdr = nullptr; h->d_feat = nullptr; h->d_class_of = nullptr; h->d_class_first = nullptr; h->d_class_enabled = nullptr; h->d_pfeat = nullptr; h->d_rrec = nullptr;
   h->d_tid_of = nullptr;
   h->n_templates = h->n_features = h->n_classes = 0; h->packed = false;
 }
@@ -305,6 +309,7 @@ static fl_tdb make_tdb(fl_handle* h) {
   db.n_templates = h->n_templates; db.L = h->p.n_levels; db.M = h->p.n_modalities; db.n_classes = h->n_classes;
   db.hdr = h->d_hdr; db.feat = h->d_feat; db.class_of = h->d_class_of; db.class_first = h->d_class_first;
   db.class_enabled = h->d_class_enabled; db.pfeat = h->d_pfeat; db.tid_of = h->d_tid_of;
+  db.rrec = h->d_rrec; db.rrec_bytes = fl_rrec_bytes(h->p.n_modalities);
   return db;
 }
 
@@ -338,6 +343,10 @@ static int ensure_geometry(fl_handle* h, int W, int H) {
   }
   if (!h->packed && h->n_templates > 0) {
     fl_launch_pack_features(make_tdb(h), h->d_geom, h->n_features, h->stream); ++h->launches;
+    if (p.n_levels > 1) {
+      if (!h->d_rrec) TRY(dalloc(&h->d_rrec, (size_t)h->n_templates * (p.n_levels - 1) * fl_rrec_bytes(p.n_modalities)));
+      fl_launch_pack_refine_records(make_tdb(h), h->d_geom, h->stream); ++h->launches;
+    }
     h->use_staged = false;
     fl_staged_plan plan;
     if (h->staged_eligible && !h->force_baseline && h->n_templates >= 256 &&
@@ -427,6 +436,12 @@ static int run_match_stages(fl_handle* h, const uint8_t* d_bgr, const uint16_t* 
       auto job_ctas = [&](int idx) { return (idx + 1 < w.n_jobs ? w.job[idx + 1].cta_begin : w.n_ctas) - w.job[idx].cta_begin; };
       auto produce = [&]() { last_job().signal_slot = w.n_jobs - 1; return w.n_jobs - 1; };
       auto consume = [&](int slot) { last_job().wait_slot = slot; last_job().wait_target = h->fe_counter_base[slot] + (unsigned)job_ctas(slot); };
+      // 0. the staged similarity kernel's per-template feature lists -> L2 (they would otherwise cost its prologue DRAM round trips)
+      if (h->use_staged && h->n_templates > 0 && n_jobs_single + 3 <= FL_FE_MAX_JOBS) {
+        fl_fe_add_prefetch(&w, h->plan.gfeat, (size_t)h->n_templates * 64 * sizeof(uint32_t));
+        fl_fe_add_prefetch(&w, h->plan.gpre, (size_t)h->n_templates * h->plan.pre_stride);
+        fl_fe_add_prefetch(&w, h->plan.gmeta, (size_t)h->n_templates * sizeof(int4));
+      }
       // 1. colour pyramid chain (short jobs, on the critical path of the coarsest level)
       if (first_color >= 0)
         for (int l = 0; l + 1 < L; ++l) {
@@ -576,8 +591,9 @@ static int run_match_stages(fl_handle* h, const uint8_t* d_bgr, const uint16_t* 
 // sort + unique of candidate lists into (d_out, d_out_count); handles the rare > 8,192-record path; leaves
 // h_small = {count, n_live, flag, raw list counts...} and, for the handle's own output block, the first matches in h_first
 struct fl_refine_req { float threshold; fl_match_t* cand; int cap; const int* d_count; };   // refine these candidates in the sort launch (k_refine_sort)
-static int run_sort_unique(fl_handle* h, fl_lists L, fl_match_t* d_out, int out_cap, int* d_out_count, bool fetch_first, const fl_xchg* xchg = nullptr,
-                           const fl_refine_req* refine = nullptr) {
+// first half of sort + unique (optionally with the refinement in the same launch): enqueue only
+static int sort_launch(fl_handle* h, fl_lists L, fl_match_t* d_out, int out_cap, int* d_out_count, bool fetch_first, const fl_xchg* xchg = nullptr,
+                       const fl_refine_req* refine = nullptr) {
   cudaStream_t s = h->stream;
   const int n_lists = L.n_lists, list_cap = L.list_cap;
   if ((int64_t)n_lists * list_cap > h->key_cap) { fl_set_error("sort capacity %d < %lld", h->key_cap, (long long)n_lists * list_cap); return FL_ERR_CAPACITY; }
@@ -599,6 +615,20 @@ static int run_sort_unique(fl_handle* h, fl_lists L, fl_match_t* d_out, int out_
                                          std::min(FETCH_FIRST, out_cap), s);
   }
   if (h->profile) cudaEventRecord(h->ev[4], s);
+  // what the second half (sort_finish) needs: it runs after the host has waited for the stream
+  h->pend_lists = L; h->pend_out = d_out; h->pend_out_cap = out_cap; h->pend_out_count = d_out_count; h->pend_own = own; h->pend_sort = true;
+  return FL_OK;
+}
+
+// second half of sort + unique: wait for the stream, read the posted summary, run the multi-kernel path if the one-CTA sort
+// reported more records than it holds
+static int sort_finish(fl_handle* h) {
+  cudaStream_t s = h->stream;
+  if (!h->pend_sort) return FL_ERR_STATE;
+  h->pend_sort = false;
+  const fl_lists L = h->pend_lists;
+  fl_match_t* d_out = h->pend_out; const int out_cap = h->pend_out_cap; int* d_out_count = h->pend_out_count; const bool own = h->pend_own;
+  const int n_lists = L.n_lists, list_cap = L.list_cap;
   FL_CUDA(cudaStreamSynchronize(s));
   h->overflow = false;
   int n_upper = 0;
@@ -618,26 +648,50 @@ static int run_sort_unique(fl_handle* h, fl_lists L, fl_match_t* d_out, int out_
   return FL_OK;
 }
 
-extern "C" int fl_match_device(fl_handle* h, const void* d_bgr, const void* d_depth, int32_t W, int32_t H, const void* const* d_masks,
-                               float threshold, const int32_t* class_filter, int32_t n_filter) {
+static int run_sort_unique(fl_handle* h, fl_lists L, fl_match_t* d_out, int out_cap, int* d_out_count, bool fetch_first, const fl_xchg* xchg = nullptr,
+                           const fl_refine_req* refine = nullptr) {
+  TRY(sort_launch(h, L, d_out, out_cap, d_out_count, fetch_first, xchg, refine));
+  return sort_finish(h);
+}
+
+extern "C" int fl_match_device_async(fl_handle* h, const void* d_bgr, const void* d_depth, int32_t W, int32_t H, const void* const* d_masks,
+                                     float threshold, const int32_t* class_filter, int32_t n_filter) {
   if (!h) return FL_ERR_ARG;
-  h->have_result = false;
-  // refinement and sort + unique share one launch (k_refine_sort) unless FL_SPLIT_REFINE=1 (developer A/B) or the staged kernel
-  // already refined (FL_FUSE_TAIL)
-  static const bool split_refine = getenv("FL_SPLIT_REFINE") != nullptr;
-  const bool defer = !split_refine && h->n_templates > 0 && h->p.n_levels > 1;
+  h->have_result = false; h->pend_match = false;
+  // refinement and sort + unique share one launch (k_refine_sort) when FL_FUSE_REFINE_SORT=1 (developer A/B; measured slower:
+  // the 1,024-thread CTAs it needs cost more to launch than the separate refinement launch they save)
+  static const bool fuse_refine_sort = getenv("FL_FUSE_REFINE_SORT") != nullptr;
+  const bool defer = fuse_refine_sort && h->n_templates > 0 && h->p.n_levels > 1;
   TRY(run_match_stages(h, (const uint8_t*)d_bgr, (const uint16_t*)d_depth, W, H, d_masks, threshold, class_filter, n_filter, h->d_cand,
                        h->p.max_candidates, h->d_count, defer));
   const fl_lists lists = {h->d_cand, 1, h->p.max_candidates, h->p.max_candidates, h->d_count, 1};
   const bool in_sort = defer && !(h->use_staged && h->plan.fuse_list_cap > 0);
   const fl_refine_req req = {threshold, h->d_cand, h->p.max_candidates, h->d_count};
-  TRY(run_sort_unique(h, lists, h->d_out, h->p.max_candidates, h->d_out_count, true, nullptr, in_sort ? &req : nullptr));
+  TRY(sort_launch(h, lists, h->d_out, h->p.max_candidates, h->d_out_count, true, nullptr, in_sort ? &req : nullptr));
+  // kept for fl_match_wait: the fused-tail overflow case re-runs the frame
+  h->pend_match = true; h->pend_bgr = d_bgr; h->pend_depth = d_depth; h->pend_W = W; h->pend_H = H; h->pend_threshold = threshold;
+  h->pend_masks_valid = d_masks != nullptr;
+  for (int m = 0; m < FL_MAX_MODALITIES; ++m) h->pend_masks[m] = d_masks ? d_masks[m] : nullptr;
+  h->pend_filter.assign(class_filter && n_filter > 0 ? class_filter : nullptr, class_filter && n_filter > 0 ? class_filter + n_filter : nullptr);
+  return FL_OK;
+}
+
+extern "C" int fl_match_wait(fl_handle* h) {
+  if (!h) return FL_ERR_ARG;
+  if (!h->pend_sort) return FL_ERR_STATE;
+  const bool was_match = h->pend_match;
+  h->pend_match = false;
+  TRY(sort_finish(h));
+  if (h->h_small[15]) { fl_set_error("peer exchange timed out waiting for rank %d", h->h_small[15] - 1); return FL_ERR_STATE; }
   if (h->h_small[14]) {
-    // one CTA of the staged kernel found more coarse candidates than its shared-memory list holds (very low thresholds):
-    // run the frame again with the refinement as separate launches
+    if (!was_match) { fl_set_error("more coarse candidates in one CTA than the fused refinement list holds; raise the threshold or unset FL_FUSE_TAIL"); return FL_ERR_CAPACITY; }
+    // one CTA of the staged kernel found more coarse candidates than its shared-memory list holds (very low thresholds,
+    // FL_FUSE_TAIL only): run the frame again with the refinement as separate launches
     const int keep = h->plan.fuse_list_cap;
     h->plan.fuse_list_cap = 0;
-    int rc = run_match_stages(h, (const uint8_t*)d_bgr, (const uint16_t*)d_depth, W, H, d_masks, threshold, class_filter, n_filter, h->d_cand,
+    const fl_lists lists = {h->d_cand, 1, h->p.max_candidates, h->p.max_candidates, h->d_count, 1};
+    int rc = run_match_stages(h, (const uint8_t*)h->pend_bgr, (const uint16_t*)h->pend_depth, h->pend_W, h->pend_H, h->pend_masks_valid ? h->pend_masks : nullptr,
+                              h->pend_threshold, h->pend_filter.empty() ? nullptr : h->pend_filter.data(), (int)h->pend_filter.size(), h->d_cand,
                               h->p.max_candidates, h->d_count);
     if (rc == FL_OK) rc = run_sort_unique(h, lists, h->d_out, h->p.max_candidates, h->d_out_count, true);
     h->plan.fuse_list_cap = keep;
@@ -645,6 +699,13 @@ extern "C" int fl_match_device(fl_handle* h, const void* d_bgr, const void* d_de
   }
   h->have_result = true;
   return FL_OK;
+}
+
+extern "C" int fl_match_device(fl_handle* h, const void* d_bgr, const void* d_depth, int32_t W, int32_t H, const void* const* d_masks,
+                               float threshold, const int32_t* class_filter, int32_t n_filter) {
+  int rc = fl_match_device_async(h, d_bgr, d_depth, W, H, d_masks, threshold, class_filter, n_filter);
+  if (rc != FL_OK) return rc;
+  return fl_match_wait(h);
 }
 
 extern "C" int fl_match_fetch(fl_handle* h, fl_match_t* out, int32_t capacity, int32_t* count) {
@@ -749,11 +810,11 @@ extern "C" size_t fl_exchange_buffer_bytes(int32_t world, int32_t capacity) {
   return FL_XCHG_SIGNALS * sizeof(unsigned) + (size_t)2 * world * ((size_t)capacity + 1) * sizeof(fl_match_t);
 }
 
-extern "C" int fl_exchange_sort_unique_device(fl_handle* h, int32_t rank, int32_t world, void* const* peer_buffers, int32_t capacity,
-                                              const fl_match_t* d_local_block, uint32_t epoch) {
+extern "C" int fl_exchange_sort_unique_device_async(fl_handle* h, int32_t rank, int32_t world, void* const* peer_buffers, int32_t capacity,
+                                                    const fl_match_t* d_local_block, uint32_t epoch) {
   if (!h || !peer_buffers || !d_local_block || world < 1 || world > FL_XCHG_MAX_WORLD || rank < 0 || rank >= world || capacity < 1 || epoch == 0) return FL_ERR_ARG;
   FL_CUDA(cudaSetDevice(h->p.device));
-  h->have_result = false;
+  h->have_result = false; h->pend_match = false;
   if (h->profile) for (int i = 0; i < 4; ++i) cudaEventRecord(h->ev[i], h->stream);
   fl_xchg X;
   memset(&X, 0, sizeof X);
@@ -762,11 +823,14 @@ extern "C" int fl_exchange_sort_unique_device(fl_handle* h, int32_t rank, int32_
   // the lists the multi-kernel fallback would read: this rank's own buffer, parity of this epoch (filled by the kernel's exchange)
   const uint8_t* own = X.peer[rank] + FL_XCHG_SIGNALS * sizeof(unsigned) + (size_t)(epoch & 1u) * world * ((size_t)capacity + 1) * sizeof(fl_match_t);
   const fl_lists lists = {reinterpret_cast<const fl_match_t*>(own) + 1, world, capacity, capacity + 1, reinterpret_cast<const int*>(own), 5 * (capacity + 1)};
-  TRY(run_sort_unique(h, lists, h->d_out, h->p.max_candidates, h->d_out_count, true, &X));
-  if (h->h_small[15]) { fl_set_error("peer exchange timed out waiting for rank %d", h->h_small[15] - 1); return FL_ERR_STATE; }
-  if (h->h_small[14]) { fl_set_error("more coarse candidates in one CTA than the fused refinement list holds; raise the threshold or unset FL_FUSE_TAIL"); return FL_ERR_CAPACITY; }
-  h->have_result = true;
-  return FL_OK;
+  return sort_launch(h, lists, h->d_out, h->p.max_candidates, h->d_out_count, true, &X);
+}
+
+extern "C" int fl_exchange_sort_unique_device(fl_handle* h, int32_t rank, int32_t world, void* const* peer_buffers, int32_t capacity,
+                                              const fl_match_t* d_local_block, uint32_t epoch) {
+  int rc = fl_exchange_sort_unique_device_async(h, rank, world, peer_buffers, capacity, d_local_block, epoch);
+  if (rc != FL_OK) return rc;
+  return fl_match_wait(h);
 }
 
 extern "C" int fl_sort_unique_blocks_device(fl_handle* h, const fl_match_t* d_blocks, int32_t n_blocks, int32_t capacity) {

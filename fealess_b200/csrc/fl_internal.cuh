@@ -68,7 +68,7 @@ void fl_launch_apply_mask(const uint8_t* q, const uint8_t* mask, int n, uint8_t*
 void fl_launch_spread_lm(const uint8_t* q, fl_level_geom g, uint8_t* lm_mod, uint8_t* spread_or_null, cudaStream_t s);
 
 // one launch = several independent front-end jobs (see k_front_end_wave)
-enum { FL_JOB_COLOR = 0, FL_JOB_DEPTH = 1, FL_JOB_PYRDOWN = 2, FL_JOB_RESIZE = 3, FL_JOB_SPREAD = 4, FL_JOB_COLOR2 = 5, FL_JOB_DEPTH2 = 6 };
+enum { FL_JOB_COLOR = 0, FL_JOB_DEPTH = 1, FL_JOB_PYRDOWN = 2, FL_JOB_RESIZE = 3, FL_JOB_SPREAD = 4, FL_JOB_COLOR2 = 5, FL_JOB_DEPTH2 = 6, FL_JOB_PREFETCH = 7 };
 struct fl_fe_job {
   int kind, cta_begin, gx, W, H, p0, p1;
   float thr_sq;
@@ -92,6 +92,9 @@ void fl_fe_add_depth(fl_fe_wave* w, const uint16_t* depth, int W, int H, int dis
 void fl_fe_add_color_v2(fl_fe_wave* w, const uint8_t* bgr, int W, int H, float thr_sq, uint8_t* q);
 bool fl_fe_add_depth_v2(fl_fe_wave* w, const uint16_t* depth, int W, int H, int dist_thr, int diff_thr, uint8_t* q, const fl_depth_pyr* pyr);
 void fl_fe_add_pyrdown(fl_fe_wave* w, const uint8_t* src, int W, int H, uint8_t* dst);
+// pull `bytes` at src towards L2 (one 128-byte line per thread): the similarity kernel's per-template feature lists, touched
+// in the shadow of the front end so that its prologue does not start with DRAM round trips
+void fl_fe_add_prefetch(fl_fe_wave* w, const void* src, size_t bytes);
 void fl_fe_add_resize(fl_fe_wave* w, const uint8_t* src, int W, int H, uint8_t* dst);
 void fl_fe_add_spread(fl_fe_wave* w, const uint8_t* q, fl_level_geom g, uint8_t* lm_mod, uint8_t* spread_or_null);
 void fl_launch_fe_wave(const fl_fe_wave& w, cudaStream_t s);
@@ -108,7 +111,15 @@ struct fl_tdb {                     // device template database
   const int32_t* tid_of;            // [n_templates] per-class template_id reported in matches (global id for shards)
   const uint8_t* class_enabled;     // [n_classes] (class filter of the current call)
   fl_pfeat* pfeat;                  // [n_features] packed for the current geometry
+  // refinement records (levels 0 .. L-2), one fixed-size block per (template, level): {width, height, n_features, 0, fc[0..3]}
+  // (32 B) + M x 64 feature slots of 8 B.  A candidate's template index alone gives the address of everything its refinement
+  // reads, so header and features load concurrently (no dependent pointer chase) and can be prefetched into L2 by the kernel
+  // that emits the candidate.  Slot = fl_pfeat; a feature outside the image at offset 0 carries lm_off = FL_RSKIP | label.
+  uint8_t* rrec; int rrec_bytes;
 };
+#define FL_RSKIP 0xFFFFFFF0u
+__host__ __device__ inline int fl_rrec_bytes(int M) { return (32 + M * 64 * 8 + 127) & ~127; }
+void fl_launch_pack_refine_records(fl_tdb db, const fl_level_geom* d_geom, cudaStream_t s);
 // plan of the shared-memory-staged global similarity kernel (similarity_staged.cu) for one frame geometry
 struct fl_staged_plan {
   int phase_rows, n_rowblocks, n_phases;   // a phase = phase_rows linear-memory rows of one (modality, label)

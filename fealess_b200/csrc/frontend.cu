@@ -547,6 +547,11 @@ __global__ void __launch_bounds__(256, 6) k_front_end_wave(fl_fe_wave w) {
     case FL_JOB_PYRDOWN: dev_pyrdown_bgr(jb.src, jb.W, jb.H, jb.dst, local); break;
     case FL_JOB_RESIZE: dev_resize_nn_half(jb.src, jb.W, jb.H, jb.dst, local); break;
     case FL_JOB_SPREAD: dev_spread_lm_any(jb.src, jb.g, jb.dst, jb.dst2, local % jb.gx, local / jb.gx, smem_dyn, jb.p0); break;
+    case FL_JOB_PREFETCH: {
+      const size_t line = (size_t)local * 256 + threadIdx.x;
+      if (line * 128 < (size_t)jb.W * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(jb.src + line * 128));
+      break;
+    }
     case FL_JOB_COLOR2: dev_color_quantize_v2(jb.src, jb.W, jb.H, jb.thr_sq, jb.dst, local % jb.gx, local / jb.gx, smem_dyn); break;
     case FL_JOB_DEPTH2:
       dev_depth_quantize_v2(reinterpret_cast<const uint16_t*>(jb.src), jb.W, jb.H, jb.p0, jb.p1, jb.dst, w, jb.gx < 0 ? -1 : (jb.thr_sq > 0.5f ? 1 : 0),
@@ -606,6 +611,14 @@ void fl_fe_add_pyrdown(fl_fe_wave* w, const uint8_t* src, int W, int H, uint8_t*
   j.wait_slot = -1; j.signal_slot = -1; j.wait_target = 0;
   j.kind = FL_JOB_PYRDOWN; j.src = src; j.dst = dst; j.dst2 = nullptr; j.W = W; j.H = H; j.gx = 1;
   j.cta_begin = w->n_ctas; w->n_ctas += pyrdown_ctas(W, H);
+}
+void fl_fe_add_prefetch(fl_fe_wave* w, const void* src, size_t bytes) {
+  const int lines = (int)((bytes + 127) / 128);
+  if (lines <= 0 || w->n_jobs >= FL_FE_MAX_JOBS) return;
+  fl_fe_job& j = w->job[w->n_jobs++];
+  j.wait_slot = -1; j.signal_slot = -1; j.wait_target = 0;
+  j.kind = FL_JOB_PREFETCH; j.src = static_cast<const uint8_t*>(src); j.dst = nullptr; j.dst2 = nullptr; j.W = lines; j.H = 0; j.gx = 1;
+  j.cta_begin = w->n_ctas; w->n_ctas += (lines + 255) / 256;
 }
 void fl_fe_add_resize(fl_fe_wave* w, const uint8_t* src, int W, int H, uint8_t* dst) {
   fl_fe_job& j = w->job[w->n_jobs++];

@@ -36,6 +36,40 @@ void fl_launch_pack_features(fl_tdb db, const fl_level_geom* d_geom, int n_featu
   if (n > 0) k_pack_features<<<(n + 255) / 256, 256, 0, s>>>(db, d_geom, n);
 }
 
+// refinement records (fl_tdb::rrec): one thread per (template, level < L-1, modality slot)
+__global__ void __launch_bounds__(256) k_pack_refine_records(fl_tdb db, const fl_level_geom* __restrict__ geom) {
+  const int rec = blockIdx.x;                            // (t, level)
+  const int t = rec / (db.L - 1), level = rec - t * (db.L - 1);
+  const fl_level_geom g = geom[level];
+  const fl_template_hdr_t* hdr = db.hdr + ((size_t)t * db.L + level) * db.M;
+  uint8_t* out = db.rrec + (size_t)rec * db.rrec_bytes;
+  const int gt = threadIdx.x, m = gt >> 6, k = gt & 63;
+  if (gt == 0) {
+    int nf = 0;
+    int fc[4] = {0, 0, 0, 0};
+    for (int mm = 0; mm < db.M; ++mm) { fc[mm] = hdr[mm].feature_count; nf += fc[mm]; }
+    int* o = reinterpret_cast<int*>(out);
+    o[0] = hdr[0].width; o[1] = hdr[0].height; o[2] = nf; o[3] = 0; o[4] = fc[0]; o[5] = fc[1]; o[6] = fc[2]; o[7] = fc[3];
+  }
+  if (m < db.M) {
+    fl_pfeat p;
+    p.lm_off = 0xFFFFFFFFu; p.x = -32768; p.y = -32768;  // empty slot: never inside the image
+    if (k < hdr[m].feature_count) {
+      const fl_feature_t f = db.feat[hdr[m].feature_begin + k];
+      p.x = (int16_t)max(min(f.x, 32767), -32768);
+      p.y = (int16_t)max(min(f.y, 32767), -32768);
+      if (f.x < 0 || f.y < 0 || f.x >= g.W || f.y >= g.H) p.lm_off = FL_RSKIP | (uint32_t)f.label;
+      else p.lm_off = (uint32_t)((size_t)f.label * g.label_stride + (size_t)((f.y % g.T) * g.T + (f.x % g.T)) * g.cells +
+                                 (size_t)(f.y / g.T) * g.Wd + f.x / g.T);
+    }
+    reinterpret_cast<fl_pfeat*>(out + 32)[gt] = p;
+  }
+}
+void fl_launch_pack_refine_records(fl_tdb db, const fl_level_geom* d_geom, cudaStream_t s) {
+  const int n = db.n_templates * (db.L - 1);
+  if (n > 0 && db.rrec) k_pack_refine_records<<<n, 256, 0, s>>>(db, d_geom);
+}
+
 // unaligned 4-byte window at byte offset a of a 4-byte-aligned buffer
 __device__ __forceinline__ uint32_t load_u8x4(const uint8_t* __restrict__ base, uint32_t a) {
   const uint32_t* w = reinterpret_cast<const uint32_t*>(base) + (a >> 2);
@@ -131,8 +165,8 @@ void fl_launch_similarity_debug(fl_tdb db, fl_level_geom g, const uint8_t* lm_le
 #define RF_MAXF (FL_MAX_MODALITIES * 63)
 
 struct fl_refine_smem {                        // per group of RF_THREADS threads
-  uint32_t off[RF_MAXF];                       // byte offset of every feature's window origin inside the level's linear memories, or FL_SKIP
-  int mbeg[FL_MAX_MODALITIES + 1];
+  uint32_t off[FL_MAX_MODALITIES * 64];        // byte offset of every feature slot's window origin inside the level's linear memories, or FL_SKIP
+  int mbeg[FL_MAX_MODALITIES + 1], cnt[FL_MAX_MODALITIES];
   uint32_t part[3][64][2];
   uint32_t best[2];
   fl_match_t mt;
@@ -149,44 +183,45 @@ __device__ __forceinline__ void refine_level_group(const fl_tdb& db, const fl_le
   const int row = cell >> 2, cg = cell & 3;
   const int T = g.T, border = 8 * T;
   const int t = mt.template_id;                                    // handle-local template index (see k_similarity_global)
-  const fl_template_hdr_t* hdr = db.hdr + ((size_t)t * db.L + level) * db.M;
+  // the candidate's refinement record: header and this thread's feature slot are independent loads (one round trip)
+  const uint8_t* rec = db.rrec + ((size_t)t * (db.L - 1) + level) * db.rrec_bytes;
+  const int4 h0 = __ldg(reinterpret_cast<const int4*>(rec));       // width, height, n_features
+  const int4 h1 = __ldg(reinterpret_cast<const int4*>(rec) + 1);   // features per modality
+  fl_pfeat p; p.lm_off = 0xFFFFFFFFu; p.x = -32768; p.y = -32768;
+  if (gt < db.M * 64) p = reinterpret_cast<const fl_pfeat*>(rec + 32)[gt];
   int x = mt.x * 2 + 1, y = mt.y * 2 + 1;                          // :1525-1534
   x = max(x, border); y = max(y, border);
-  x = min(x, g.W - hdr[0].width - border);
-  y = min(y, g.H - hdr[0].height - border);
+  x = min(x, g.W - h0.x - border);
+  y = min(y, g.H - h0.y - border);
   const int ox = (x / T - 8) * T, oy = (y / T - 8) * T;            // :1240-1241 (C division truncates towards zero)
   const int delta = (oy / T) * g.Wd + ox / T;
-  // stage 1: one thread per feature resolves the feature's window origin (all modalities), so that stage 2 issues
-  // nothing but independent linear-memory loads
-  int nf = 0;
-  for (int m = 0; m < db.M; ++m) {
-    const fl_template_hdr_t h = hdr[m];
-    if (gt == 0) sm.mbeg[m] = nf;
-    for (int k = gt; k < h.feature_count; k += RF_THREADS) {
-      const fl_pfeat p = db.pfeat[h.feature_begin + k];
-      const int fx = p.x + ox, fy = p.y + oy;
-      uint32_t o = FL_SKIP;
-      if (fx >= 0 && fy >= 0 && fx < g.W && fy < g.H) {            // :1257
-        // the packed offset was computed for (x, y); shifting by a multiple of T moves only the cell index
-        if (p.lm_off == FL_SKIP)                                   // outside the image unshifted, inside when shifted
-          o = (uint32_t)((size_t)db.feat[h.feature_begin + k].label * g.label_stride +
-                         (size_t)((p.y % T + T) % T * T + (p.x % T + T) % T) * g.cells + (size_t)(fy / T) * g.Wd + fx / T);
-        else
-          o = (uint32_t)((int)p.lm_off + delta);
-        o += (uint32_t)((size_t)m * g.mod_stride);
-      }
-      sm.off[nf + k] = o;
+  // stage 1: one thread per feature slot resolves the feature's window origin, so that stage 2 issues nothing but
+  // independent linear-memory loads
+  const int nf = h0.z;
+  {
+    const int m = gt >> 6;
+    const int fx = p.x + ox, fy = p.y + oy;
+    uint32_t o = FL_SKIP;
+    if (fx >= 0 && fy >= 0 && fx < g.W && fy < g.H) {              // :1257
+      // the packed offset was computed for (x, y); shifting by a multiple of T moves only the cell index
+      if ((p.lm_off & FL_RSKIP) == FL_RSKIP)                       // outside the image unshifted, inside when shifted
+        o = (uint32_t)((size_t)(p.lm_off & 15u) * g.label_stride +
+                       (size_t)((p.y % T + T) % T * T + (p.x % T + T) % T) * g.cells + (size_t)(fy / T) * g.Wd + fx / T);
+      else
+        o = (uint32_t)((int)p.lm_off + delta);
+      o += (uint32_t)((size_t)m * g.mod_stride);
     }
-    nf += h.feature_count;
+    sm.off[gt] = o;
+    if (gt <= db.M) sm.mbeg[gt] = gt * 64;                         // fixed 64 slots per modality
+    if (gt < 4) sm.cnt[gt] = gt == 0 ? h1.x : (gt == 1 ? h1.y : (gt == 2 ? h1.z : h1.w));
   }
-  if (gt == 0) sm.mbeg[db.M] = nf;
   group_sync(bar_id);
   // stage 2: 16x16 patch, thread = (feature group, patch row, 4-cell column group); u8 lanes per modality (<= 63 x 4)
   const uint32_t cell_off = (uint32_t)(row * g.Wd + cg * 4);
   uint32_t tot_lo = 0, tot_hi = 0;
   for (int m = 0; m < db.M; ++m) {
     uint32_t acc = 0;
-    const int k1 = sm.mbeg[m + 1];
+    const int k1 = sm.mbeg[m] + sm.cnt[m];
     // <= 63 features per modality (:1231) = <= 16 per feature group: all loads of a modality are issued before the first
     // add (one L2 round trip instead of one per unroll step)
     for (int k0 = sm.mbeg[m] + fgrp; k0 < k1; k0 += 64) {
@@ -256,9 +291,10 @@ __global__ void __launch_bounds__(RF_THREADS) k_refine_level(fl_tdb db, fl_level
     fl_match_t mt = cand[ci];
     if (mt.template_id < 0) continue;                              // dropped at a coarser level (:1570-1572)
     const int t = mt.template_id;
+    const int final_id = (threadIdx.x == 0 && level == 0) ? db.tid_of[t] : 0;   // issued now, needed after the refinement
     refine_level_group(db, g, level, lm_level, threshold, mt, sm, threadIdx.x, 0);
     if (threadIdx.x == 0) {
-      if (mt.template_id >= 0 && level == 0) mt.template_id = db.tid_of[t];   // final per-class template_id
+      if (mt.template_id >= 0 && level == 0) mt.template_id = final_id;       // final per-class template_id
       cand[ci] = mt;
     }
   }
@@ -291,7 +327,9 @@ __device__ __forceinline__ fl_match_t key_to_match(const fl_sort_key& k) {
   m.x = (int)(k.lo & 0xFFFF) - 32768;
   return m;
 }
-__device__ __forceinline__ bool key_less(const fl_sort_key& a, const fl_sort_key& b) { return a.hi < b.hi || (a.hi == b.hi && a.lo < b.lo); }
+// branch-free on purpose (| and &, not || and &&): in the sorting networks every lane compares different keys, and
+// short-circuit branches would diverge on every comparison
+__device__ __forceinline__ bool key_less(const fl_sort_key& a, const fl_sort_key& b) { return (a.hi < b.hi) | ((a.hi == b.hi) & (a.lo < b.lo)); }
 __device__ __forceinline__ bool key_dup(const fl_sort_key& a, const fl_sort_key& b) {
   // equal x, y, similarity, class; template_id ignored (linemod.hpp:271-274)
   return (a.hi >> 32) == (b.hi >> 32) && a.lo == b.lo;
@@ -393,108 +431,135 @@ __device__ __forceinline__ void sort_unique_body(fl_lists L, fl_xchg X, int key_
     return;
   }
   __syncthreads();                                               // s_hdr[3..13] complete before threads retire
-  // The launch always has 1,024 threads and room for SORT_SMEM_LARGE keys; a frame with few records (the common case)
-  // retires all but 256 of them here, so that the ~30 barriers of the bitonic network stay cheap.
+  // The launch always has 1,024 threads and room for SORT_SMEM_LARGE keys; frames with <= 1,024 records (the common case)
+  // retire all but 256 threads here, so that the barriers stay cheap.
   const int nt = total > 1024 ? (int)blockDim.x : min(256, (int)blockDim.x);
   if (tid >= nt) return;
   auto sync_active = [&]() { asm volatile("bar.sync 1, %0;" ::"r"(nt) : "memory"); };
-  unsigned long long ts[5] = {0, 0, 0, 0, 0};
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts[0]));
-  if (total <= 256) {
-    // Few records (the common case): rank sort.  Thread i owns record i; its rank among the live records is the number of
-    // keys that precede it (ties - fully identical records - broken by index), so the sort is one pass over shared memory
-    // and three barriers instead of the ~30 of the bitonic network.
+  auto load_key = [&](int e) {                                     // record e of the concatenated lists -> key (sentinel if dropped / past the end)
     fl_sort_key key; key.hi = KEY_SENTINEL_HI; key.lo = KEY_SENTINEL_HI;
-    bool live = false;
-    if (tid < total) {
-      int l = 0, k = tid;
+    if (e < total) {
+      int l = 0, k = e;
       for (;;) { const int c = min(max(ld_count(L, l), 0), list_cap); if (k < c) break; k -= c; ++l; }
       const fl_match_t m = ld_match(L.in + (size_t)l * L.list_stride + k);
-      if (m.template_id >= 0) { key = make_key(m); live = true; }
+      if (m.template_id >= 0) key = make_key(m);                   // dropped candidates carry template_id -1
     }
-    s_k[tid] = key;
-    sync_active();
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts[1]));
-    fl_sort_key* s_sorted = s_k + 256;
-    if (live) {
-      int rank = 0;
-      for (int j = 0; j < total; ++j) {
-        const fl_sort_key o = s_k[j];
-        rank += (key_less(o, key) || (o.hi == key.hi && o.lo == key.lo && j < tid)) ? 1 : 0;
-      }
-      s_sorted[rank] = key;
-    }
+    return key;
+  };
+  unsigned long long ts[5] = {0, 0, 0, 0, 0};
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts[0]));
+  int n = 0, n_pad = 2;                                            // live keys, sorted slots (after this block s_k[0, n) is sorted)
+  if (total <= 256 && nt == 256) {
+    // rank sort: the rank of a record among the live ones is the number of keys that precede it (ties - fully identical
+    // records - broken by index): one pass over shared memory and three barriers
+    const fl_sort_key key = load_key(tid);
+    const bool live = !(key.hi == KEY_SENTINEL_HI && key.lo == KEY_SENTINEL_HI);
+    fl_sort_key* s_in = s_k + 256;
+    s_in[tid] = key;
     const unsigned live_mask = __ballot_sync(0xffffffffu, live);
     if (lane == 0) s_warp[warp] = __popc(live_mask);
     sync_active();
-    int n = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts[1]));
+    if (live) {
+      int rank = 0;
+      for (int j0 = 0; j0 < total; j0 += 8) {                      // 8 broadcast loads in flight per pass
+        fl_sort_key o[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) o[u] = s_in[j0 + u];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          rank += (int)((j0 + u < total) & (key_less(o[u], key) | ((o[u].hi == key.hi) & (o[u].lo == key.lo) & (j0 + u < tid))));
+      }
+      s_k[rank] = key;
+    }
 #pragma unroll
     for (int w = 0; w < 8; ++w) n += s_warp[w];
-    const bool keep = tid < n && (tid == 0 || !key_dup(s_sorted[tid - 1], s_sorted[tid]));
-    const unsigned keep_mask = __ballot_sync(0xffffffffu, keep);
-    sync_active();                                                 // every warp has read the live counts
-    if (lane == 0) s_warp[warp] = __popc(keep_mask);
+    n_pad = 256;
     sync_active();
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts[2]));
-    int pos = __popc(keep_mask & ((1u << lane) - 1)), n_unique = 0;
+  } else if (total <= 1024 && nt == 256) {
+    // bitonic network on keys held in REGISTERS, four consecutive slots per thread: strides 1 and 2 stay inside a thread,
+    // strides 4..64 are warp shuffles, only strides >= 128 go through shared memory (3 exchanges for 512 slots, 6 for 1,024,
+    // instead of 45 / 55 barrier-separated passes), and the 4 independent keys per thread hide the compare latency.
+    const int N2 = total <= 512 ? 512 : 1024;
+    const bool active = tid < N2 / 4;
+    fl_sort_key key[4];
+    int nlive = 0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) { if (w < warp) pos += s_warp[w]; n_unique += s_warp[w]; }
-    int* s_out = reinterpret_cast<int*>(s_k + 512);               // staged records, 5 ints each (<= 256 records)
-    if (keep) {
-      const fl_match_t m = key_to_match(s_sorted[tid]);
-      int* o = s_out + 5 * pos;
-      o[0] = m.x; o[1] = m.y; o[2] = __float_as_int(m.similarity); o[3] = m.class_idx; o[4] = m.template_id;
+    for (int r = 0; r < 4; ++r) {
+      key[r].hi = KEY_SENTINEL_HI; key[r].lo = KEY_SENTINEL_HI;
+      if (active) key[r] = load_key(4 * tid + r);
+      nlive += !(key[r].hi == KEY_SENTINEL_HI && key[r].lo == KEY_SENTINEL_HI);
     }
-    if (tid == 0) {
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts[3]));
-      s_hdr[0] = n_unique; s_hdr[1] = n; s_hdr[2] = 0;
-      if (n_lists == 1) { s_hdr[4] = (int)(ts[0] - t_body0); s_hdr[5] = (int)(ts[1] - ts[0]); s_hdr[6] = (int)(ts[2] - ts[1]); s_hdr[7] = (int)(ts[3] - ts[2]); }   // developer timeline (ns)
-      if (X.world == 0) { s_hdr[8] = dbg_a; s_hdr[9] = dbg_b; s_hdr[10] = (int)(ts[3] - t_body0); s_hdr[11] = dbg_n; }
-      if (X.world > 0 && X.world <= 4) {
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_dbg[3]));
-        s_hdr[8] = (int)(t_dbg[1] - t_dbg[0]); s_hdr[9] = (int)(t_dbg[2] - t_dbg[1]); s_hdr[10] = (int)(t_dbg[3] - t_dbg[2]);
-      }
-    }
-    sync_active();
-    {
-      int* out_i = reinterpret_cast<int*>(out);
-      int* hf_i = reinterpret_cast<int*>(h_first);
-      const int n_out = 5 * min(n_unique, out_cap), n_hf = h_first ? 5 * min(n_unique, h_first_cap) : 0;
-      for (int i = tid; i < 5 * n_unique; i += nt) {
-        const int v = s_out[i];
-        if (i < n_out) out_i[i] = v;
-        if (i < n_hf) hf_i[i] = v;
-      }
-    }
-    post_header();
-    return;
-  }
-  if (tid == 0) s_n = 0;
-  sync_active();
-  for (int i = tid; i < total; i += nt) {
-    int l = 0, k = i;
-    for (;;) { const int c = min(max(ld_count(L, l), 0), list_cap); if (k < c) break; k -= c; ++l; }
-    const fl_match_t m = ld_match(L.in + (size_t)l * L.list_stride + k);
-    if (m.template_id >= 0) s_k[atomicAdd(&s_n, 1)] = make_key(m);          // dropped candidates carry template_id -1
-  }
-  sync_active();
-  const int n = s_n;
-  int n_pad = 2;
-  while (n_pad < n) n_pad <<= 1;
-  for (int i = n + tid; i < n_pad; i += nt) { s_k[i].hi = KEY_SENTINEL_HI; s_k[i].lo = KEY_SENTINEL_HI; }
-  sync_active();
-  for (int k = 2; k <= n_pad; k <<= 1)
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = tid; i < n_pad; i += nt) {
-        const int p = i ^ j;
-        if (p > i) {
-          const bool up = (i & k) == 0;
-          const fl_sort_key a = s_k[i], b = s_k[p];
-          if (key_less(b, a) == up) { s_k[i] = b; s_k[p] = a; }
+    nlive = __reduce_add_sync(0xffffffffu, nlive);
+    if (lane == 0) s_warp[warp] = nlive;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts[1]));
+    for (int k = 2; k <= N2; k <<= 1)
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        fl_sort_key o[4];
+        if (j >= 128) {
+          if (active) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) s_k[4 * tid + r] = key[r];
+          }
+          sync_active();
+          if (active) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) o[r] = s_k[(4 * tid + r) ^ j];
+          }
+          sync_active();
+        } else if (j >= 4) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) { o[r].hi = __shfl_xor_sync(0xffffffffu, key[r].hi, j >> 2); o[r].lo = __shfl_xor_sync(0xffffffffu, key[r].lo, j >> 2); }
+        } else {
+          if (j == 1) { o[0] = key[1]; o[1] = key[0]; o[2] = key[3]; o[3] = key[2]; }
+          else { o[0] = key[2]; o[1] = key[3]; o[2] = key[0]; o[3] = key[1]; }
+        }
+        if (active) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const int e = 4 * tid + r;
+            const bool take_min = ((e & k) == 0) == ((e & j) == 0);
+            const bool lt = key_less(o[r], key[r]), gt = key_less(key[r], o[r]);
+            const bool take = take_min ? lt : gt;                  // selects, no branches
+            key[r].hi = take ? o[r].hi : key[r].hi;
+            key[r].lo = take ? o[r].lo : key[r].lo;
+          }
         }
       }
-      sync_active();
+    if (active) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) s_k[4 * tid + r] = key[r];
     }
+    sync_active();
+#pragma unroll
+    for (int w = 0; w < 8; ++w) n += s_warp[w];
+    n_pad = N2;
+  } else {
+    if (tid == 0) s_n = 0;
+    sync_active();
+    for (int i = tid; i < total; i += nt) {
+      const fl_sort_key key = load_key(i);
+      if (!(key.hi == KEY_SENTINEL_HI && key.lo == KEY_SENTINEL_HI)) s_k[atomicAdd(&s_n, 1)] = key;
+    }
+    sync_active();
+    n = s_n;
+    while (n_pad < n) n_pad <<= 1;
+    for (int i = n + tid; i < n_pad; i += nt) { s_k[i].hi = KEY_SENTINEL_HI; s_k[i].lo = KEY_SENTINEL_HI; }
+    sync_active();
+    for (int k = 2; k <= n_pad; k <<= 1)
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = tid; i < n_pad; i += nt) {
+          const int p = i ^ j;
+          if (p > i) {
+            const bool up = (i & k) == 0;
+            const fl_sort_key a = s_k[i], b = s_k[p];
+            if (key_less(b, a) == up) { s_k[i] = b; s_k[p] = a; }
+          }
+        }
+        sync_active();
+      }
+  }
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts[2]));
   // adjacent unique + ordered compaction: each thread owns a contiguous run of slots; block-wide exclusive scan of the kept counts
   const int per = (n_pad + nt - 1) / nt;
   const int b0 = tid * per;
@@ -503,6 +568,7 @@ __device__ __forceinline__ void sort_unique_body(fl_lists L, fl_xchg X, int key_
   int inc = cnt;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+  sync_active();                                                   // every thread has read the live counts in s_warp
   if (lane == 31) s_warp[warp] = inc;
   sync_active();
   if (warp == 0) {
@@ -513,21 +579,42 @@ __device__ __forceinline__ void sort_unique_body(fl_lists L, fl_xchg X, int key_
   }
   sync_active();
   int pos = (warp > 0 ? s_warp[warp - 1] : 0) + inc - cnt;
+  const int n_unique = s_warp[31];
+  // records leave through a staging area in shared memory when they fit (<= 1,024 sorted slots: the keys use at most 1,024 of
+  // the 8,192 slots), so that device and mapped-host copies are contiguous 128-byte warp stores
+  const bool staged = n_pad <= 1024;
+  int* s_out = reinterpret_cast<int*>(s_k + 1024);
   for (int i = b0; i < min(b0 + per, n); ++i)
     if (i == 0 || !key_dup(s_k[i - 1], s_k[i])) {
       const fl_match_t m = key_to_match(s_k[i]);
-      if (pos < out_cap) out[pos] = m;
-      if (h_first && pos < h_first_cap) h_first[pos] = m;
+      if (staged) { int* o = s_out + 5 * pos; o[0] = m.x; o[1] = m.y; o[2] = __float_as_int(m.similarity); o[3] = m.class_idx; o[4] = m.template_id; }
+      else {
+        if (pos < out_cap) out[pos] = m;
+        if (h_first && pos < h_first_cap) h_first[pos] = m;
+      }
       ++pos;
     }
   if (tid == 0) {
-    s_hdr[0] = s_warp[31]; s_hdr[1] = n; s_hdr[2] = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts[3]));
+    s_hdr[0] = n_unique; s_hdr[1] = n; s_hdr[2] = 0;
+    if (n_lists == 1) { s_hdr[4] = (int)(ts[0] - t_body0); s_hdr[5] = (int)(ts[1] - ts[0]); s_hdr[6] = (int)(ts[2] - ts[1]); s_hdr[7] = (int)(ts[3] - ts[2]); }   // developer timeline (ns)
+    if (X.world == 0) { s_hdr[8] = dbg_a; s_hdr[9] = dbg_b; s_hdr[10] = (int)(ts[3] - t_body0); s_hdr[11] = dbg_n; }
     if (X.world > 0 && X.world <= 4) {                           // developer timing of the exchange (ns): push, wait, sort
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_dbg[3]));
       s_hdr[8] = (int)(t_dbg[1] - t_dbg[0]); s_hdr[9] = (int)(t_dbg[2] - t_dbg[1]); s_hdr[10] = (int)(t_dbg[3] - t_dbg[2]);
     }
   }
   sync_active();
+  if (staged) {
+    int* out_i = reinterpret_cast<int*>(out);
+    int* hf_i = reinterpret_cast<int*>(h_first);
+    const int n_out = 5 * min(n_unique, out_cap), n_hf = h_first ? 5 * min(n_unique, h_first_cap) : 0;
+    for (int q = tid; q < 5 * n_unique; q += nt) {
+      const int v = s_out[q];
+      if (q < n_out) out_i[q] = v;
+      if (q < n_hf) hf_i[q] = v;
+    }
+  }
   post_header();
 }
 

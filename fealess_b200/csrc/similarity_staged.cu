@@ -342,6 +342,13 @@ __global__ void __launch_bounds__(1024, 1) k_similarity_staged(const __grid_cons
       for (int i = 0; i < NW; ++i) cnt += __popc(candidate_mask(acc[s][i], lane * NW + i, tp, raw_thr, thr4)) >> 3;
       if (!__any_sync(0xffffffffu, cnt > 0)) continue;
       const int total = __reduce_add_sync(0xffffffffu, cnt);
+      // this template has candidates: pull its refinement records (and its id) towards L2 now, so that the refinement
+      // kernel finds them there instead of paying two DRAM round trips per candidate
+      if (db.rrec && db.L > 1) {
+        const uint8_t* rec = db.rrec + (size_t)meta.w * (db.L - 1) * db.rrec_bytes;
+        for (int o = lane * 128; o < (db.L - 1) * db.rrec_bytes; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + o));
+        if (lane == 31) asm volatile("prefetch.global.L2 [%0];" ::"l"(db.tid_of + meta.w));
+      }
       int base = 0;
       if (lane == 0) base = fuse ? atomicAdd(&s_ncand, total) : atomicAdd(d_count, total);
       base = __shfl_sync(0xffffffffu, base, 0);

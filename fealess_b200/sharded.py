@@ -128,17 +128,24 @@ class ShardedMatcher:
             if int(ok.item()) == 0:
                 self.exchange = "nccl"
 
-    def match_device(self, d_bgr: int, d_depth: int, W: int, H: int, threshold: float) -> None:
-        """One frame: enqueue the local match, the exchange and the merge on the handle's stream; returns when the merged
-        match list is ready (``fetch``)."""
-        torch = self._torch
-        import torch.distributed as dist
+    def match_device_async(self, d_bgr: int, d_depth: int, W: int, H: int, threshold: float) -> bool:
+        """One frame, enqueue only: the local match and (p2p exchange) the exchange + merge kernel go onto the handle's stream.
+        Returns True when ``match_wait`` is all that is left (p2p); with the NCCL exchange the collective and the merge are
+        issued by ``match_wait``."""
         recs = records_view(self.block)
         # the count lives in the header record of the block, so the candidates + count travel together
         self.h.match_shard_device(d_bgr, d_depth, W, H, threshold, recs.data_ptr(), self.cap, self.block.data_ptr())
         if self.exchange == "p2p":
             self.epoch += 1
-            self.h.exchange_sort_unique_device(self.rank, self.world, self._peers, self.cap, self.block.data_ptr(), self.epoch)
+            self.h.exchange_sort_unique_device_async(self.rank, self.world, self._peers, self.cap, self.block.data_ptr(), self.epoch)
+            return True
+        return False
+
+    def match_wait(self) -> None:
+        torch = self._torch
+        import torch.distributed as dist
+        if self.exchange == "p2p":
+            self.h.match_wait()
             return
         with torch.cuda.stream(self.stream):
             if self.world == 1 or not dist.is_initialized():
@@ -146,6 +153,11 @@ class ShardedMatcher:
             else:
                 dist.all_gather_into_tensor(self.gathered, self.block)
         self.h.sort_unique_blocks_device(self.gathered.data_ptr(), self.world, self.cap)
+
+    def match_device(self, d_bgr: int, d_depth: int, W: int, H: int, threshold: float) -> None:
+        """One frame: the local match, the exchange and the merge; returns when the merged match list is ready (``fetch``)."""
+        self.match_device_async(d_bgr, d_depth, W, H, threshold)
+        self.match_wait()
 
     def fetch(self) -> np.ndarray:
         return self.h.match_fetch()

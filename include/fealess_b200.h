@@ -130,6 +130,13 @@ int fl_match(fl_handle* h, const uint8_t* bgr, size_t bgr_stride, const uint16_t
 int fl_match_device(fl_handle* h, const void* d_bgr, const void* d_depth, int32_t W, int32_t H,
                     const void* const* d_masks, float threshold, const int32_t* class_filter, int32_t n_filter);
 int fl_match_fetch(fl_handle* h, fl_match_t* out, int32_t capacity, int32_t* count);
+/* The two halves of fl_match_device: ..._async only enqueues the frame's kernels on the handle's stream (fl_stream) and
+ * returns; fl_match_wait waits for them and finishes the call (status as fl_match_device).  A caller can overlap its own host
+ * work with the device, or bracket exactly the device work with CUDA events recorded on fl_stream (what bench.py does).
+ * One frame in flight per handle: fl_match_wait must be called before the next ..._async call. */
+int fl_match_device_async(fl_handle* h, const void* d_bgr, const void* d_depth, int32_t W, int32_t H,
+                          const void* const* d_masks, float threshold, const int32_t* class_filter, int32_t n_filter);
+int fl_match_wait(fl_handle* h);
 
 /* Template-sharded matching (one handle per GPU holds a shard of the templates):
  * fl_match_shard_device runs the front end + matchClass over this handle's templates and writes the UNSORTED
@@ -160,6 +167,9 @@ int fl_sort_unique_blocks_device(fl_handle* h, const fl_match_t* d_blocks, int32
 size_t fl_exchange_buffer_bytes(int32_t world, int32_t capacity);
 int fl_exchange_sort_unique_device(fl_handle* h, int32_t rank, int32_t world, void* const* peer_buffers, int32_t capacity,
                                    const fl_match_t* d_local_block, uint32_t epoch);
+/* enqueue-only half; finish with fl_match_wait */
+int fl_exchange_sort_unique_device_async(fl_handle* h, int32_t rank, int32_t world, void* const* peer_buffers, int32_t capacity,
+                                         const fl_match_t* d_local_block, uint32_t epoch);
 
 /* ---- ICP ------------------------------------------------------------------------------------------ */
 /* cup_d2pc::depthTo3d for 16UC1 input: out3 = H*W*3 floats in METRES, 0 depth -> NaN (depth_to_3d.cpp:99-137, 244-260) */

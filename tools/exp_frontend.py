@@ -29,6 +29,8 @@ for it in range(104):
         fb.lib().fl_debug_get(h._h, 5, 0, 0, 0, C.c_void_p(cnt.ctypes.data), C.c_size_t(cnt.nbytes))
         tl += cnt[8:12]
         tl2 += cnt[4:8]
+        if it < 8:
+            print("frame %d: unique %d live %d raw %d | sort body ns: counts %d gather %d sort %d output %d" % (it % 4, cnt[0], cnt[1], cnt[3], cnt[4], cnt[5], cnt[6], cnt[7]))
 st /= n
 tl /= n
 tl2 /= n
