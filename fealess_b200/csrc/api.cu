@@ -51,6 +51,7 @@ struct fl_handle {
   // state between the enqueue half (fl_match_device_async, ..._async) and fl_match_wait
   bool pend_sort, pend_match, pend_own, pend_masks_valid; fl_lists pend_lists; fl_match_t* pend_out; int pend_out_cap; int* pend_out_count;
   const void* pend_bgr; const void* pend_depth; int pend_W, pend_H; float pend_threshold; const void* pend_masks[FL_MAX_MODALITIES]; std::vector<int32_t> pend_filter;
+  unsigned long long* d_fe_trace; int fe_trace_jobs, fe_trace_kind[FL_FE_MAX_JOBS], fe_trace_ctas[FL_FE_MAX_JOBS];
   unsigned* d_fe_counters; unsigned fe_counter_base[FL_FE_MAX_JOBS];   // in-grid dependency counters of the single-launch front end (+ 1 error word)
   // candidates / matches
   fl_match_t* d_cand; int* d_count; fl_sort_key* d_keys; int key_cap; uint8_t* d_outblk; fl_match_t* d_out; int* d_out_count;   // d_outblk = [16-int summary][matches]
@@ -151,7 +152,7 @@ extern "C" int fl_create(const fl_params_t* params, fl_handle** out) {
   FL_CUDA(cudaMemset(h->d_count, 0, 4 * sizeof(int)));
   TRY(dalloc(&h->d_fe_counters, FL_FE_MAX_JOBS + 1)); FL_CUDA(cudaMemset(h->d_fe_counters, 0, (FL_FE_MAX_JOBS + 1) * sizeof(unsigned)));
   memset(h->fe_counter_base, 0, sizeof h->fe_counter_base);
-  h->pend_sort = h->pend_match = false;                             // [0] candidate count, [1] CTA ticket counter of k_refine_sort
+  h->pend_sort = h->pend_match = false; h->d_fe_trace = nullptr; h->fe_trace_jobs = 0;                             // [0] candidate count, [1] CTA ticket counter of k_refine_sort
   int kc = 2; while (kc < p.max_candidates) kc <<= 1;
   h->key_cap = kc;
   TRY(dalloc(&h->d_keys, (size_t)kc + 1));      // + room for the two scratch ints behind the keys
@@ -196,7 +197,7 @@ extern "C" int fl_destroy(fl_handle* h) {
     cudaFree(h->d_bgr[l]); cudaFree(h->d_lm[l]);
     for (int m = 0; m < FL_MAX_MODALITIES; ++m) { cudaFree(h->d_q[l][m]); cudaFree(h->d_qm[l][m]); cudaFree(h->d_mask[l][m]); cudaFree(h->d_spread[l][m]); }
   }
-  cudaFree(h->d_fe_counters);
+  cudaFree(h->d_fe_counters); cudaFree(h->d_fe_trace);
   cudaFree(h->d_cand); cudaFree(h->d_count); cudaFree(h->d_keys); cudaFree(h->d_outblk);
   cudaFreeHost(h->h_bgr); cudaFreeHost(h->h_depth); cudaFreeHost(h->h_mask); cudaFreeHost(h->h_outblk); cudaFreeHost(h->h_class_enabled);
   for (int i = 0; i < 5; ++i) cudaEventDestroy(h->ev[i]);
@@ -411,7 +412,7 @@ static int run_match_stages(fl_handle* h, const uint8_t* d_bgr, const uint16_t* 
     // latency floor of one colour-tile CTA, about 8 us.)
     const int L = p.n_levels;
     fl_fe_wave w;
-    auto wave_begin = [&](bool zero) { w.n_jobs = 0; w.n_ctas = 0; w.smem = 0; w.n_pyr = 0; w.zero_me = zero ? d_count : nullptr; w.counters = nullptr; w.dep_error = nullptr; };
+    auto wave_begin = [&](bool zero) { w.n_jobs = 0; w.n_ctas = 0; w.smem = 0; w.n_pyr = 0; w.zero_me = zero ? d_count : nullptr; w.counters = nullptr; w.dep_error = nullptr; w.trace = nullptr; };
     auto wave_flush = [&]() { if (w.n_jobs > 0) { fl_launch_fe_wave(w, s); ++h->launches; } w.n_jobs = 0; w.n_ctas = 0; w.smem = 0; w.n_pyr = 0; w.zero_me = nullptr; };
     // word-parallel quantisers (frontend_v2.cuh); FL_FE_V1=1 selects the first, byte-granular versions (A/B timing).  The depth
     // job also writes the NN-downsampled label pyramid when every level halves exactly (then dst_l(y,x) = src(2^l y, 2^l x)).
@@ -441,11 +442,16 @@ static int run_match_stages(fl_handle* h, const uint8_t* d_bgr, const uint16_t* 
         fl_fe_add_prefetch(&w, h->plan.gfeat, (size_t)h->n_templates * 64 * sizeof(uint32_t));
         fl_fe_add_prefetch(&w, h->plan.gpre, (size_t)h->n_templates * h->plan.pre_stride);
         fl_fe_add_prefetch(&w, h->plan.gmeta, (size_t)h->n_templates * sizeof(int4));
+        if (n_jobs_single + 6 <= FL_FE_MAX_JOBS) {                               // the prologue's dependent lookups: template -> class -> enabled
+          fl_fe_add_prefetch(&w, h->d_class_of, (size_t)h->n_templates * sizeof(int32_t));
+          fl_fe_add_prefetch(&w, h->d_class_enabled, (size_t)std::max(h->n_classes, 1));
+          fl_fe_add_prefetch(&w, h->d_tid_of, (size_t)h->n_templates * sizeof(int32_t));
+        }
       }
       // 1. colour pyramid chain (short jobs, on the critical path of the coarsest level)
       if (first_color >= 0)
         for (int l = 0; l + 1 < L; ++l) {
-          fl_fe_add_pyrdown(&w, l == 0 ? d_bgr : h->d_bgr[l], h->geom[l].W, h->geom[l].H, h->d_bgr[l + 1]);
+          fl_fe_add_pyrdown(&w, l == 0 ? d_bgr : h->d_bgr[l], h->geom[l].W, h->geom[l].H, h->d_bgr[l + 1], l == 0);
           slot_pyr[l + 1] = produce();
           if (l > 0) consume(slot_pyr[l]);
         }
@@ -475,6 +481,17 @@ static int run_match_stages(fl_handle* h, const uint8_t* d_bgr, const uint16_t* 
           consume(p.modality_kind[m] == FL_MODALITY_COLOR_GRADIENT ? slot_color[l][m] : slot_depth[m]);
         }
       for (int i = 0; i < w.n_jobs; ++i) if (w.job[i].signal_slot >= 0) h->fe_counter_base[i] += (unsigned)job_ctas(i);
+      static const bool fe_trace = getenv("FL_TRACE") != nullptr;                // developer timeline: per job first start / last end
+      if (fe_trace) {
+        if (!h->d_fe_trace) TRY(dalloc(&h->d_fe_trace, 2 * FL_FE_MAX_JOBS + 2 * FL_FE_MAX_JOBS));
+        unsigned long long init[2 * FL_FE_MAX_JOBS];
+        for (int i = 0; i < FL_FE_MAX_JOBS; ++i) { init[2 * i] = ~0ull; init[2 * i + 1] = 0; }
+        FL_CUDA(cudaMemcpyAsync(h->d_fe_trace, init, sizeof init, cudaMemcpyHostToDevice, s));
+        FL_CUDA(cudaStreamSynchronize(s));
+        w.trace = h->d_fe_trace;
+        h->fe_trace_jobs = w.n_jobs;
+        for (int i = 0; i < w.n_jobs; ++i) { h->fe_trace_kind[i] = w.job[i].kind; h->fe_trace_ctas[i] = job_ctas(i); }
+      }
       wave_flush();
     } else
     for (int wv = 0; wv <= L; ++wv) {
@@ -512,7 +529,7 @@ static int run_match_stages(fl_handle* h, const uint8_t* d_bgr, const uint16_t* 
       }
       if (l < L) {
         const fl_level_geom& g = h->geom[l];
-        if (first_color >= 0 && l + 1 < L) { wave_room(); fl_fe_add_pyrdown(&w, l == 0 ? d_bgr : h->d_bgr[l], g.W, g.H, h->d_bgr[l + 1]); }   // shared by all colour modalities
+        if (first_color >= 0 && l + 1 < L) { wave_room(); fl_fe_add_pyrdown(&w, l == 0 ? d_bgr : h->d_bgr[l], g.W, g.H, h->d_bgr[l + 1], true); }   // shared by all colour modalities
         for (int m = 0; m < p.n_modalities; ++m)
           if (p.modality_kind[m] == FL_MODALITY_DEPTH_NORMAL && l > 0 && !depth_pyr_fused[m]) { wave_room(); fl_fe_add_resize(&w, h->d_q[l - 1][m], h->geom[l - 1].W, h->geom[l - 1].H, h->d_q[l][m]); }
       }
@@ -884,6 +901,15 @@ extern "C" int fl_debug_get(fl_handle* h, int what, int32_t a, int32_t b, int32_
     if (bytes < 16 * sizeof(int)) return FL_ERR_CAPACITY;
     memcpy(host_out, h->h_small, 16 * sizeof(int));
     return FL_OK;
+  }
+  if (what == 6) {                                                               // developer: front-end job timeline {kind, ctas, start, end} x jobs (FL_TRACE=1)
+    if (!h->d_fe_trace || h->fe_trace_jobs <= 0) return FL_ERR_STATE;
+    if (bytes < (size_t)h->fe_trace_jobs * 4 * sizeof(unsigned long long)) return FL_ERR_CAPACITY;
+    unsigned long long raw[2 * FL_FE_MAX_JOBS];
+    FL_CUDA(cudaMemcpy(raw, h->d_fe_trace, sizeof raw, cudaMemcpyDeviceToHost));
+    unsigned long long* o = static_cast<unsigned long long*>(host_out);
+    for (int i = 0; i < h->fe_trace_jobs; ++i) { o[4 * i] = (unsigned long long)h->fe_trace_kind[i]; o[4 * i + 1] = (unsigned long long)h->fe_trace_ctas[i]; o[4 * i + 2] = raw[2 * i]; o[4 * i + 3] = raw[2 * i + 1]; }
+    return h->fe_trace_jobs;
   }
   if (what == FL_DBG_STAGED_TRACE) {
     if (!h->use_staged || !h->plan.trace) return FL_ERR_STATE;

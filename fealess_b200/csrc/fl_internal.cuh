@@ -85,13 +85,14 @@ struct fl_depth_pyr { int n; int W[FL_FE_MAX_PYR], H[FL_FE_MAX_PYR]; uint8_t* ds
 #define FL_FE_MAX_JOBS 16
 #define FL_FE_MAX_DPYR 2
 struct fl_fe_wave { int n_jobs, n_ctas; size_t smem; int* zero_me; fl_fe_job job[FL_FE_MAX_JOBS]; int n_pyr; fl_depth_pyr pyr[FL_FE_MAX_DPYR];
-                    unsigned* counters; int* dep_error; };   // zero_me: int reset by CTA 0 (candidate counter), or NULL; counters: FL_FE_MAX_JOBS monotonic CTA counters
+                    unsigned* counters; int* dep_error;
+                    unsigned long long* trace; };   // trace (FL_TRACE=1): per job {first CTA start, last CTA end} in globaltimer ns   // zero_me: int reset by CTA 0 (candidate counter), or NULL; counters: FL_FE_MAX_JOBS monotonic CTA counters
 void fl_fe_add_color(fl_fe_wave* w, const uint8_t* bgr, int W, int H, float thr_sq, uint8_t* q, int part, int n_parts);
 void fl_fe_add_depth(fl_fe_wave* w, const uint16_t* depth, int W, int H, int dist_thr, int diff_thr, uint8_t* q);
 // word-parallel variants (frontend_v2.cuh); pyr (nullable, at most FL_FE_MAX_DPYR per wave): also write the NN pyramid of the labels
 void fl_fe_add_color_v2(fl_fe_wave* w, const uint8_t* bgr, int W, int H, float thr_sq, uint8_t* q);
 bool fl_fe_add_depth_v2(fl_fe_wave* w, const uint16_t* depth, int W, int H, int dist_thr, int diff_thr, uint8_t* q, const fl_depth_pyr* pyr);
-void fl_fe_add_pyrdown(fl_fe_wave* w, const uint8_t* src, int W, int H, uint8_t* dst);
+void fl_fe_add_pyrdown(fl_fe_wave* w, const uint8_t* src, int W, int H, uint8_t* dst, bool src_static);
 // pull `bytes` at src towards L2 (one 128-byte line per thread): the similarity kernel's per-template feature lists, touched
 // in the shadow of the front end so that its prologue does not start with DRAM round trips
 void fl_fe_add_prefetch(fl_fe_wave* w, const void* src, size_t bytes);

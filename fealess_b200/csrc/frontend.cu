@@ -18,6 +18,8 @@
 // ------------------------------------------------------------------------------------------------
 __constant__ uint8_t c_normal_plane[400];
 __constant__ uint2 c_resp8[256];
+__device__ uint2 g_resp8[256];          // same table in global memory: 256 threads copy it to shared memory with ONE coalesced load each
+                                        // (the constant cache serialises a warp's 32 distinct addresses)
 
 int fl_launch_tables_init() {
   uint8_t plane[400];
@@ -46,6 +48,7 @@ int fl_launch_tables_init() {
   }
   FL_CUDA(cudaMemcpyToSymbol(c_normal_plane, plane, sizeof plane));
   FL_CUDA(cudaMemcpyToSymbol(c_resp8, resp, sizeof resp));
+  FL_CUDA(cudaMemcpyToSymbol(g_resp8, resp, sizeof resp));
   return FL_OK;
 }
 
@@ -203,7 +206,9 @@ __device__ __forceinline__ int reflect101(int p, int n) {
 __device__ __forceinline__ int reflect101_near(int p, int n) {         // |overshoot| <= 2 and n >= 3: a single fold
   return p < 0 ? -p : (p >= n ? 2 * n - 2 - p : p);
 }
-__device__ __forceinline__ void dev_pyrdown_bgr(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ dst, int bx) {
+// src_static: the source was complete before this launch (the caller's frame), so it may go through L1 (neighbouring threads
+// share every line); a level produced by an earlier job of the same launch must be read from L2.
+__device__ __forceinline__ void dev_pyrdown_bgr(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ dst, int bx, bool src_static) {
   const int dw = W / 2, dh = H / 2;
   const int gx = (dw + PD_TW - 1) / PD_TW;
   const int by = bx / gx; bx -= by * gx;
@@ -227,7 +232,8 @@ __device__ __forceinline__ void dev_pyrdown_bgr(const uint8_t* __restrict__ src,
     for (int t = 0; t < 5; ++t) {
       const int kt = t == 0 || t == 4 ? 1 : (t == 2 ? 6 : 4);
       const uint8_t* p = row + cx[t];
-      r0 += kt * __ldcg(p); r1 += kt * __ldcg(p + 1); r2 += kt * __ldcg(p + 2);   // L2 loads: the source may come from an earlier job of this launch
+      if (src_static) { r0 += kt * __ldg(p); r1 += kt * __ldg(p + 1); r2 += kt * __ldg(p + 2); }
+      else { r0 += kt * __ldcg(p); r1 += kt * __ldcg(p + 1); r2 += kt * __ldcg(p + 2); }
     }
     s0 += kj * r0; s1 += kj * r1; s2 += kj * r2;
   }
@@ -236,7 +242,7 @@ __device__ __forceinline__ void dev_pyrdown_bgr(const uint8_t* __restrict__ src,
 }
 
 __global__ void __launch_bounds__(256) k_pyrdown_bgr(const uint8_t* __restrict__ src, int W, int H, uint8_t* __restrict__ dst) {
-  dev_pyrdown_bgr(src, W, H, dst, blockIdx.x);
+  dev_pyrdown_bgr(src, W, H, dst, blockIdx.x, false);
 }
 
 static int pyrdown_ctas(int W, int H) { return ((W / 2 + PD_TW - 1) / PD_TW) * ((H / 2 + PD_TH - 1) / PD_TH); }
@@ -423,11 +429,32 @@ __device__ __forceinline__ void dev_spread_lm(const uint8_t* __restrict__ q, con
   uint2* s_resp = reinterpret_cast<uint2*>(smem);        // 256 x 8 B
   uint8_t* s_in = smem + 2048;                          // [th][st_in]   input labels (later reused for the final spread)
   uint8_t* s_hor = s_in + (size_t)(2 * T - 1) * spread_stride_in(T);   // [th][st_pw] horizontal OR
-  for (int i = tid; i < 256; i += SL_THREADS) s_resp[i] = c_resp8[i];
-  for (int r = warp; r < th; r += NWARP) {              // rows by warp, bytes by lane: coalesced, no index arithmetic
-    const int y = py0 + r;
-    const uint8_t* src = q + (size_t)y * W + px0;
-    for (int c = lane; c < st_in; c += 32) s_in[r * st_in + c] = (c < tw && px0 + c < W && y < H) ? __ldcg(src + c) : (uint8_t)0;   // clipped window == OR with zeros
+  for (int i = tid; i < 256; i += SL_THREADS) s_resp[i] = g_resp8[i];
+  if (((reinterpret_cast<uintptr_t>(q) | (uintptr_t)W | (uintptr_t)px0) & 3) == 0) {
+    // word-aligned tile: whole 32-bit words, every load of the tile in flight at once (fixed trip count, unrolled).  A word is
+    // either entirely inside the image or entirely outside (W % 4 == 0); bytes past the CTA's own window are real pixels of
+    // the neighbour and are never read by the OR passes below.
+    const int nwi = st_in >> 2;
+    const int n_items = th * nwi;
+    uint32_t* s_in32 = reinterpret_cast<uint32_t*>(s_in);
+    for (int i0 = 0; i0 < n_items; i0 += 4 * SL_THREADS) {
+      uint32_t v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {                     // 4 loads in flight per thread (the whole tile for T <= 8)
+        const int i = i0 + tid + u * SL_THREADS;
+        const int r = i / nwi, wi = i - r * nwi;
+        const int y = py0 + r, x = px0 + 4 * wi;
+        v[u] = (i < n_items && y < H && x < W) ? __ldcg(reinterpret_cast<const uint32_t*>(q + (size_t)y * W + x)) : 0u;   // clipped window == OR with zeros
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const int i = i0 + tid + u * SL_THREADS; if (i < n_items) s_in32[i] = v[u]; }
+    }
+  } else {
+    for (int r = warp; r < th; r += NWARP) {            // rows by warp, bytes by lane: coalesced, no index arithmetic
+      const int y = py0 + r;
+      const uint8_t* src = q + (size_t)y * W + px0;
+      for (int c = lane; c < st_in; c += 32) s_in[r * st_in + c] = (c < tw && px0 + c < W && y < H) ? __ldcg(src + c) : (uint8_t)0;   // clipped window == OR with zeros
+    }
   }
   __syncthreads();
   for (int r = warp; r < th; r += NWARP) {              // horizontal OR, four pixels per thread
@@ -524,6 +551,7 @@ __global__ void __launch_bounds__(256, 6) k_front_end_wave(fl_fe_wave w) {
   while (j + 1 < w.n_jobs && b >= w.job[j + 1].cta_begin) ++j;
   const fl_fe_job& jb = w.job[j];
   const int local = b - jb.cta_begin;
+  if (w.trace && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); atomicMin(w.trace + 2 * j, t); }
   if (jb.wait_slot >= 0) {
     // In-grid dependency: CTAs are dispatched in blockIdx order and a producing job always precedes its consumers in the grid,
     // so every producer CTA is resident (or done) before a consumer starts to wait here.  The wait is bounded: after ~1 s it gives
@@ -544,7 +572,7 @@ __global__ void __launch_bounds__(256, 6) k_front_end_wave(fl_fe_wave w) {
   switch (jb.kind) {
     case FL_JOB_COLOR: { const int tile = local + jb.p0; dev_color_quantize(jb.src, jb.W, jb.H, jb.thr_sq, jb.dst, tile % jb.gx, tile / jb.gx, smem_dyn); break; }
     case FL_JOB_DEPTH: dev_depth_quantize(reinterpret_cast<const uint16_t*>(jb.src), jb.W, jb.H, jb.p0, jb.p1, jb.dst, local % jb.gx, local / jb.gx, smem_dyn); break;
-    case FL_JOB_PYRDOWN: dev_pyrdown_bgr(jb.src, jb.W, jb.H, jb.dst, local); break;
+    case FL_JOB_PYRDOWN: dev_pyrdown_bgr(jb.src, jb.W, jb.H, jb.dst, local, jb.p0 != 0); break;
     case FL_JOB_RESIZE: dev_resize_nn_half(jb.src, jb.W, jb.H, jb.dst, local); break;
     case FL_JOB_SPREAD: dev_spread_lm_any(jb.src, jb.g, jb.dst, jb.dst2, local % jb.gx, local / jb.gx, smem_dyn, jb.p0); break;
     case FL_JOB_PREFETCH: {
@@ -558,6 +586,7 @@ __global__ void __launch_bounds__(256, 6) k_front_end_wave(fl_fe_wave w) {
                             local % abs(jb.gx), local / abs(jb.gx), smem_dyn);
       break;
   }
+  if (w.trace) { __syncthreads(); if (threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); atomicMax(w.trace + 2 * j + 1, t); } }
   if (jb.signal_slot >= 0) {
     __syncthreads();                                    // every thread's stores of this CTA ...
     if (threadIdx.x == 0) { __threadfence(); atomicAdd(w.counters + jb.signal_slot, 1u); }   // ... are visible before the count
@@ -606,10 +635,10 @@ bool fl_fe_add_depth_v2(fl_fe_wave* w, const uint16_t* depth, int W, int H, int 
   w->smem = w->smem > (size_t)D2_SMEM_BYTES ? w->smem : (size_t)D2_SMEM_BYTES;
   return true;
 }
-void fl_fe_add_pyrdown(fl_fe_wave* w, const uint8_t* src, int W, int H, uint8_t* dst) {
+void fl_fe_add_pyrdown(fl_fe_wave* w, const uint8_t* src, int W, int H, uint8_t* dst, bool src_static) {
   fl_fe_job& j = w->job[w->n_jobs++];
   j.wait_slot = -1; j.signal_slot = -1; j.wait_target = 0;
-  j.kind = FL_JOB_PYRDOWN; j.src = src; j.dst = dst; j.dst2 = nullptr; j.W = W; j.H = H; j.gx = 1;
+  j.kind = FL_JOB_PYRDOWN; j.src = src; j.dst = dst; j.dst2 = nullptr; j.W = W; j.H = H; j.gx = 1; j.p0 = src_static ? 1 : 0;
   j.cta_begin = w->n_ctas; w->n_ctas += pyrdown_ctas(W, H);
 }
 void fl_fe_add_prefetch(fl_fe_wave* w, const void* src, size_t bytes) {

@@ -184,6 +184,7 @@ __global__ void __launch_bounds__(1024, 1) k_similarity_staged(const __grid_cons
   extern __shared__ __align__(128) uint8_t s_dyn[];          // [n_buf x buf_bytes][tpc x int4 meta][tpc x 64 feature words + 4][tpc x pre_stride][fuse_list_cap x int4]
   __shared__ __align__(8) uint64_t s_full[SS_NBUF_MAX], s_empty[SS_NBUF_MAX];
   __shared__ int s_ncand;
+  __shared__ __align__(8) uint64_t s_aux;                     // completion of the bulk copy of this CTA's feature lists
   const bool fuse = plan.fuse_list_cap > 0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_cwarps = (blockDim.x >> 5) - 1;                 // consumer warps; the last warp is the TMA producer
@@ -205,6 +206,7 @@ __global__ void __launch_bounds__(1024, 1) k_similarity_staged(const __grid_cons
   if (tid == 0) {
     s_ncand = 0;
     for (int b = 0; b < n_buf; ++b) { mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], n_cwarps * CL); }
+    mbar_init(&s_aux, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -226,10 +228,8 @@ __global__ void __launch_bounds__(1024, 1) k_similarity_staged(const __grid_cons
       }
       s_meta[i] = m;
     }
-    for (int i = tid; i < plan.tpc * SS_MAXF; i += n_cwarps * 32) {
-      const int t = t_begin + (i >> 6);                       // SS_MAXF == 64
-      s_feat[i] = t < t_end ? plan.gfeat[(size_t)t * SS_MAXF + (i & (SS_MAXF - 1))] : 0u;
-    }
+    // (the feature words of this CTA's templates are one contiguous block of plan.gfeat: the producer thread fetches it with a
+    // single bulk copy, see below; slots past the end are never read because their prefix counts are zero)
     if (tid < 4) s_feat[plan.tpc * SS_MAXF + tid] = 0u;
     {   // prefix counts, copied as 32-bit words (pre_stride is a multiple of 4): one warp per template row
       const int wpr = plan.pre_stride >> 2;
@@ -242,6 +242,7 @@ __global__ void __launch_bounds__(1024, 1) k_similarity_staged(const __grid_cons
       }
     }
     asm volatile("bar.sync 1, %0;" ::"r"(n_cwarps * 32) : "memory");   // consumers only
+    if (t_end > t_begin) mbar_wait(&s_aux, 0);                // feature words have landed
     fl_grid_dep_wait();                                       // before the first write to the candidate list / counter
     fl_grid_dep_launch();
   }
@@ -250,6 +251,11 @@ __global__ void __launch_bounds__(1024, 1) k_similarity_staged(const __grid_cons
   if (warp == n_cwarps) {
     // ===== producer: one elected lane streams phase q into buffer q % n_buf as soon as every consumer warp of the cluster released it =====
     if (lane == 0) {
+      if (t_end > t_begin) {                                  // static data: may be fetched before the previous kernel has finished
+        const uint32_t fbytes = (uint32_t)(t_end - t_begin) * SS_MAXF * 4u;
+        mbar_expect_tx(&s_aux, fbytes);
+        bulk_g2s(s_feat, plan.gfeat + (size_t)t_begin * SS_MAXF, fbytes, &s_aux);
+      }
       fl_grid_dep_wait();                                     // the linear memories are written by the previous kernel of the stream
       for (int q = 0; q < n_phases; ++q) {
         const int b = q % n_buf;

@@ -14,7 +14,7 @@ NT = int(sys.argv[1]) if len(sys.argv) > 1 else 8000
 
 
 def trace(h):
-    buf = np.zeros(1024 * 8, np.uint64)
+    buf = np.zeros(4096 * 8, np.uint64)
     n = fb.lib().fl_debug_get(h._h, 4, 0, 0, 0, C.c_void_p(buf.ctypes.data), C.c_size_t(buf.nbytes))
     if n <= 0:
         return None
@@ -31,7 +31,7 @@ def main():
     h0.force_baseline(True)
     ref = [h0.match(b, d, 75.0)[1] for b, d in frames]
     print("baseline matches per frame", [len(r) for r in ref])
-    for cl, kb in [(1, 2), (1, 3), (1, 4)]:
+    for cl, kb in [(1, 2)]:
         os.environ["FL_SS_CLUSTER"] = str(cl)
         os.environ["FL_SS_NBUF"] = str(kb)
         h = fb.Handle(T, (0, 1), W, H)
