@@ -355,10 +355,10 @@ def run_ours(args):
                     "traffic": traffic, "kernel_ms": float(st[1]), "timer": "CUDA events on the library's stream around the stage (counter memset + launch + kernel), mean of %d steps" % n_stage, "peak_source": "148 SM x 128 B/clk x %.0f MHz (SM clock sampled under load); "
                     "MEASURED_PEAKS.json has no shared-memory figure" % sm_clk, "algorithmic_bytes_per_launch": alg_bytes}
         fe = FRONT_END_BYTES / (st[0] * 1e-3) / 1e9
-        extra["roofline_front_end"] = {"kernels": "color_quantize, pyrdown, depth_quantize, resize_nn, spread_lm (x4)", "bound": "hbm",
+        extra["roofline_front_end"] = {"kernels": "k_front_end_wave: ONE launch (colour + depth quantisers, pyrDown, spread + response maps + linear memories of both levels, in-grid dependencies)", "bound": "hbm",
                                        "achieved": fe, "peak": hbm_gbs, "unit": "GB/s", "frac": fe / hbm_gbs, "stage_ms": float(st[0]),
                                        "algorithmic_bytes": FRONT_END_BYTES, "peak_source": peak_src + " MEASURED_PEAKS.json hbm_gbs",
-                                       "note": "7.7 MB per VGA frame = 1.2 us at peak: this stage is launch-latency bound, not bandwidth bound"}
+                                       "note": "7.7 MB per VGA frame = 1.2 us at peak: at VGA this stage is bound by instruction issue and dependency latency (13 M warp instructions), not by bandwidth"}
         extra["stage_ms"] = {"front_end": float(st[0]), "similarity_global": float(st[1]), "refine": float(st[2]), "sort_unique_and_fetch": float(st[3])}
 
     # ---- CPU baseline (rank 0, N = 1 only): the C restatement, single thread = the reference's execution model ----

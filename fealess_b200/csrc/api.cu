@@ -358,8 +358,8 @@ static int ensure_geometry(fl_handle* h, int W, int H) {
       TRY(dalloc(&h->plan.gpre, (size_t)h->n_templates * plan.pre_stride));
       TRY(dalloc(&h->plan.gmeta, (size_t)h->n_templates));
       if (getenv("FL_TRACE")) {                                                  // developer timeline of the staged kernel (FL_DBG_STAGED_TRACE)
-        TRY(dalloc(&h->plan.trace, (size_t)plan.n_cta * 72 + 8));                 // + stamps of a 1-thread kernel before / after the launch
-        FL_CUDA(cudaMemsetAsync(h->plan.trace, 0, ((size_t)plan.n_cta * 72 + 8) * sizeof(unsigned long long), h->stream));
+        TRY(dalloc(&h->plan.trace, (size_t)plan.n_cta * 136 + 8));                 // + stamps of a 1-thread kernel before / after the launch
+        FL_CUDA(cudaMemsetAsync(h->plan.trace, 0, ((size_t)plan.n_cta * 136 + 8) * sizeof(unsigned long long), h->stream));
       }
       fl_launch_pack_staged(make_tdb(h), h->geom[p.n_levels - 1], h->plan, h->stream); ++h->launches;
       h->use_staged = true;
@@ -761,7 +761,9 @@ extern "C" int fl_match(fl_handle* h, const uint8_t* bgr, size_t bgr_stride, con
   if (depth) {                                                                     // depth first: it is the smaller image
     if (depth_stride < (size_t)W * 2) return FL_ERR_SIZE;
     if (is_pinned(depth)) {
-      FL_CUDA(cudaMemcpy2DAsync(h->d_in_depth, (size_t)W * 2, depth, depth_stride, (size_t)W * 2, H, cudaMemcpyHostToDevice, s));
+      // dense rows go as ONE linear DMA (a 2-D copy of the same bytes is split into row descriptors and runs at about half the rate)
+      if (depth_stride == (size_t)W * 2) FL_CUDA(cudaMemcpyAsync(h->d_in_depth, depth, (size_t)W * H * 2, cudaMemcpyHostToDevice, s));
+      else FL_CUDA(cudaMemcpy2DAsync(h->d_in_depth, (size_t)W * 2, depth, depth_stride, (size_t)W * 2, H, cudaMemcpyHostToDevice, s));
     } else {
       for (int y = 0; y < H; ++y) memcpy(h->h_depth + (size_t)y * W, (const uint8_t*)depth + (size_t)y * depth_stride, (size_t)W * 2);
       FL_CUDA(cudaMemcpyAsync(h->d_in_depth, h->h_depth, (size_t)W * H * 2, cudaMemcpyHostToDevice, s));
@@ -771,7 +773,8 @@ extern "C" int fl_match(fl_handle* h, const uint8_t* bgr, size_t bgr_stride, con
   if (bgr) {
     if (bgr_stride < (size_t)W * 3) return FL_ERR_SIZE;
     if (is_pinned(bgr)) {
-      FL_CUDA(cudaMemcpy2DAsync(h->d_in_bgr, (size_t)W * 3, bgr, bgr_stride, (size_t)W * 3, H, cudaMemcpyHostToDevice, s));
+      if (bgr_stride == (size_t)W * 3) FL_CUDA(cudaMemcpyAsync(h->d_in_bgr, bgr, (size_t)W * H * 3, cudaMemcpyHostToDevice, s));
+      else FL_CUDA(cudaMemcpy2DAsync(h->d_in_bgr, (size_t)W * 3, bgr, bgr_stride, (size_t)W * 3, H, cudaMemcpyHostToDevice, s));
     } else {
       // pageable source: stage in two halves so the second half's host copy overlaps the first half's DMA
       const int h0 = H / 2;
@@ -913,7 +916,7 @@ extern "C" int fl_debug_get(fl_handle* h, int what, int32_t a, int32_t b, int32_
   }
   if (what == FL_DBG_STAGED_TRACE) {
     if (!h->use_staged || !h->plan.trace) return FL_ERR_STATE;
-    size_t n = ((size_t)h->plan.n_cta * 72 + 8) * sizeof(unsigned long long);
+    size_t n = ((size_t)h->plan.n_cta * 136 + 8) * sizeof(unsigned long long);
     if (bytes < n) return FL_ERR_CAPACITY;
     FL_CUDA(cudaMemcpy(host_out, h->plan.trace, n, cudaMemcpyDeviceToHost));
     return h->plan.n_cta;

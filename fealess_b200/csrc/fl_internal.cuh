@@ -128,6 +128,7 @@ struct fl_staged_plan {
   int n_words, nw_template, tpw;           // 32-bit words per similarity map; template parameters of the instantiation used
   int tpc, n_cta, block_threads;           // templates per CTA, grid, block
   int cluster, smem_bytes, pre_stride;     // CTAs per cluster (TMA multicast group); dynamic shared memory; bytes per gpre row
+  int stage_off;                           // emission staging area (one similarity map, nw_template x 32 words)
   int fuse_list_off, fuse_list_cap;        // fused refinement tail: per-CTA candidate list in shared memory (offset, records); cap 0 = not fused
   int* fuse_ovf;                           // device int set to 1 when a CTA's list overflowed (the host then re-runs the frame unfused)
   uint32_t* gfeat;                         // [n_templates][64] feature words sorted by phase: word offset in the phase buffer << 5 | 8 * byte misalignment

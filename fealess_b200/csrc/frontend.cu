@@ -540,7 +540,7 @@ void fl_launch_spread_lm(const uint8_t* q, fl_level_geom g, uint8_t* lm_mod, uin
 //   wave k >= 1 : colour quantise Lk | NN-downsample depth labels Lk | pyrDown Lk->Lk+1 | spread+LM of level k-1 (all modalities)
 //   last wave   : spread+LM of the coarsest level
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 6) k_front_end_wave(fl_fe_wave w) {
+__global__ void __launch_bounds__(256, 8) k_front_end_wave(fl_fe_wave w) {
   extern __shared__ __align__(16) uint8_t smem_dyn[];
   const int b = blockIdx.x;
   fl_grid_dep_wait();                                   // the previous kernel of the stream wrote this wave's inputs

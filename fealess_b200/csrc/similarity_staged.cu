@@ -184,6 +184,7 @@ __global__ void __launch_bounds__(1024, 1) k_similarity_staged(const __grid_cons
   extern __shared__ __align__(128) uint8_t s_dyn[];          // [n_buf x buf_bytes][tpc x int4 meta][tpc x 64 feature words + 4][tpc x pre_stride][fuse_list_cap x int4]
   __shared__ __align__(8) uint64_t s_full[SS_NBUF_MAX], s_empty[SS_NBUF_MAX];
   __shared__ int s_ncand;
+  __shared__ int s_emit_lock;                                 // the CTA's emission staging area is taken by one warp at a time
   __shared__ __align__(8) uint64_t s_aux;                     // completion of the bulk copy of this CTA's feature lists
   const bool fuse = plan.fuse_list_cap > 0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(1024, 1) k_similarity_staged(const __grid_cons
 
   int4* s_list = reinterpret_cast<int4*>(s_dyn + plan.fuse_list_off);      // {template, x | y << 16, similarity bits, class}
   if (tid == 0) {
-    s_ncand = 0;
+    s_ncand = 0; s_emit_lock = 0;
     for (int b = 0; b < n_buf; ++b) { mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], n_cwarps * CL); }
     mbar_init(&s_aux, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -330,65 +331,95 @@ __global__ void __launch_bounds__(1024, 1) k_similarity_staged(const __grid_cons
       if (++p == n_phases) p = 0;
     }
     if (trace && tid == 0) trace[3] = globaltimer();
-    if (trace && lane == 0) plan.trace[(size_t)plan.n_cta * 8 + 8 + ((size_t)blockIdx.x * 32 + warp) * 2] = globaltimer();       // per-warp loop end
+    if (trace && lane == 0) plan.trace[(size_t)plan.n_cta * 8 + 8 + ((size_t)blockIdx.x * 32 + warp) * 4] = globaltimer();       // per-warp loop end
 
-    // threshold + candidate emission (matchClass :1487-1506).  The raw threshold was computed in the prologue.  Slots are
-    // reserved with ONE atomic per template that has candidates (a returning atomic is a ~0.7 us round trip to L2, one
-    // per candidate would serialise), and the records are written ballot-compacted by all lanes in parallel.
+    // threshold + candidate emission (matchClass :1487-1506).  The raw threshold was computed in the prologue.
+    // Every warp first asks "any byte above the threshold?" with a few SWAR operations per accumulator word.  The rare warp that
+    // has candidates copies its accumulators to a staging area in shared memory (one per CTA, taken with a lock), where the byte
+    // index IS the cell index, and walks it with a COMPACT loop: the first version unrolled the per-candidate code over
+    // NW x 4 x TPW register positions, ~100 KB of cold instructions whose instruction-cache misses cost a candidate-bearing
+    // warp 5-10 us (measured) - and the whole kernel waits for its slowest warp.  Slots are reserved with ONE returning atomic
+    // per template; the records are written ballot-compacted by all lanes in parallel.
     const int off = g.T / 2 + (g.T % 2 - 1);
+    uint32_t* s_stage = reinterpret_cast<uint32_t*>(s_dyn + plan.stage_off);
 #pragma unroll
     for (int s = 0; s < TPW; ++s) {
       if (!live[s]) continue;                                 // warp-uniform
       const int4 meta = s_meta[warp + s * n_cwarps];
       const int tp = meta.x, nf = meta.y & 0xFF, raw_thr = (meta.y >> 8) - 1;
       if (tp <= 0 || raw_thr >= 255) continue;                // disabled class / a u8 total cannot exceed the threshold
-      const uint32_t thr4 = raw_thr < 0 ? 0u : (uint32_t)raw_thr * 0x01010101u;
-      int cnt = 0;
+      // bytes >= raw_thr + 1, two 16-bit lanes at a time: e + (256 - t) carries into bit 8 exactly when e >= t
+      uint32_t anyw = raw_thr < 0 ? 1u : 0u;
+      if (raw_thr >= 0) {
+        const uint32_t k = (uint32_t)(255 - raw_thr) * 0x00010001u;
 #pragma unroll
-      for (int i = 0; i < NW; ++i) cnt += __popc(candidate_mask(acc[s][i], lane * NW + i, tp, raw_thr, thr4)) >> 3;
-      if (!__any_sync(0xffffffffu, cnt > 0)) continue;
-      const int total = __reduce_add_sync(0xffffffffu, cnt);
-      // this template has candidates: pull its refinement records (and its id) towards L2 now, so that the refinement
-      // kernel finds them there instead of paying two DRAM round trips per candidate
-      if (db.rrec && db.L > 1) {
-        const uint8_t* rec = db.rrec + (size_t)meta.w * (db.L - 1) * db.rrec_bytes;
-        for (int o = lane * 128; o < (db.L - 1) * db.rrec_bytes; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + o));
-        if (lane == 31) asm volatile("prefetch.global.L2 [%0];" ::"l"(db.tid_of + meta.w));
+        for (int i = 0; i < NW; ++i) {
+          const uint32_t v = acc[s][i];
+          anyw |= (((v & 0x00FF00FFu) + k) | (((v >> 8) & 0x00FF00FFu) + k)) & 0x01000100u;
+        }
       }
-      int base = 0;
-      if (lane == 0) base = fuse ? atomicAdd(&s_ncand, total) : atomicAdd(d_count, total);
-      base = __shfl_sync(0xffffffffu, base, 0);
-      const int lim = fuse ? plan.fuse_list_cap : cap;
-      // list full (> fuse_list_cap coarse candidates from this CTA's templates): flag it; the host re-runs the frame unfused
-      if (fuse && base + total > lim && lane == 0 && plan.fuse_ovf) *plan.fuse_ovf = 1;
+      if (!__any_sync(0xffffffffu, anyw != 0)) continue;      // (cells past template_positions are filtered below)
+      if (lane == 0) { while (atomicCAS(&s_emit_lock, 0, 1) != 0) __nanosleep(100); }
+      __syncwarp();
 #pragma unroll
-      for (int i = 0; i < NW; ++i) {
-        const uint32_t v = acc[s][i];
-        const int w = lane * NW + i;
-        const uint32_t m = candidate_mask(v, w, tp, raw_thr, thr4);
-        if (!__any_sync(0xffffffffu, m != 0)) continue;
+      for (int i = 0; i < NW; ++i) s_stage[lane * NW + i] = acc[s][i];
+      __syncwarp();
+      // pass 1 (cheap, ~20 instructions per 128 cells): compact the (cell, raw) pairs above the threshold into a list.  A lone
+      // warp runs dependent code at ~5 cycles per instruction, so the expensive per-candidate work (division, IEEE divide,
+      // record stores) is done ONCE for up to 32 candidates in pass 2 instead of once per group of 32 cells.
+      uint32_t* s_hits = s_stage + NW * 32;
+      const int n_words_tp = (tp + 3) >> 2;
+      int total = 0;
+      for (int w0 = 0; w0 < n_words_tp; w0 += 32) {
+        const int w = w0 + lane;
+        const uint32_t v = w < n_words_tp ? s_stage[w] : 0u;
 #pragma unroll
-        for (int bb = 0; bb < 4; ++bb) {
-          const bool hit = (m >> (8 * bb)) & 1;
+        for (int b = 0; b < 4; ++b) {
+          const int raw = (int)((v >> (8 * b)) & 0xFFu), j = 4 * w + b;
+          const bool hit = w < n_words_tp && j < tp && raw > raw_thr;
           const uint32_t bal = __ballot_sync(0xffffffffu, hit);
-          const int slot = base + __popc(bal & ((1u << lane) - 1));
-          const int j = 4 * w + bb, raw = (v >> (8 * bb)) & 0xFF;
+          if (hit) s_hits[total + __popc(bal & ((1u << lane) - 1))] = (uint32_t)j | ((uint32_t)raw << 16);
+          total += __popc(bal);
+        }
+      }
+      __syncwarp();
+      if (total > 0) {
+        // this template has candidates: pull its refinement records (and its id) towards L2 now, so that the refinement
+        // kernel finds them there instead of paying two DRAM round trips per candidate
+        if (db.rrec && db.L > 1) {
+          const uint8_t* rec = db.rrec + (size_t)meta.w * (db.L - 1) * db.rrec_bytes;
+          for (int o = lane * 128; o < (db.L - 1) * db.rrec_bytes; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + o));
+          if (lane == 31) asm volatile("prefetch.global.L2 [%0];" ::"l"(db.tid_of + meta.w));
+        }
+        if (trace && lane == 0) plan.trace[(size_t)plan.n_cta * 8 + 8 + ((size_t)blockIdx.x * 32 + warp) * 4 + 2] = globaltimer();   // before the atomic
+        int base = 0;
+        if (lane == 0) base = fuse ? atomicAdd(&s_ncand, total) : atomicAdd(d_count, total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (trace && lane == 0) plan.trace[(size_t)plan.n_cta * 8 + 8 + ((size_t)blockIdx.x * 32 + warp) * 4 + 3] = globaltimer();   // after the atomic
+        const int lim = fuse ? plan.fuse_list_cap : cap;
+        // list full (> fuse_list_cap coarse candidates from this CTA's templates): flag it; the host re-runs the frame unfused
+        if (fuse && base + total > lim && lane == 0 && plan.fuse_ovf) *plan.fuse_ovf = 1;
+        // pass 2: one lane per candidate
+        for (int k = lane; k < total; k += 32) {
+          const int slot = base + k;
+          if (slot >= lim) break;
+          const uint32_t hv = s_hits[k];
+          const int j = (int)(hv & 0xFFFFu), raw = (int)(hv >> 16);
           const int r = j / g.Wd, c = j - r * g.Wd;
           const int mx = c * g.T + off, my = r * g.T + off;
           const float msim = __fadd_rn(__fdiv_rn(__fmul_rn((float)raw, 100.f), (float)(4 * nf)), 0.5f);
-          if (hit && slot < lim) {
-            if (fuse) s_list[slot] = make_int4(meta.w, (mx & 0xFFFF) | (my << 16), __float_as_int(msim), meta.z);
-            else {
-              fl_match_t mt;
-              mt.x = mx; mt.y = my; mt.similarity = msim; mt.class_idx = meta.z; mt.template_id = meta.w;
-              cand[slot] = mt;
-            }
+          if (fuse) s_list[slot] = make_int4(meta.w, (mx & 0xFFFF) | (my << 16), __float_as_int(msim), meta.z);
+          else {
+            fl_match_t mt;
+            mt.x = mx; mt.y = my; mt.similarity = msim; mt.class_idx = meta.z; mt.template_id = meta.w;
+            cand[slot] = mt;
           }
-          base += __popc(bal);
         }
       }
+      __syncwarp();
+      if (lane == 0) { __threadfence_block(); atomicExch(&s_emit_lock, 0); }
     }
-    if (trace && lane == 0) { atomicMax(&trace[6], globaltimer()); plan.trace[(size_t)plan.n_cta * 8 + 8 + ((size_t)blockIdx.x * 32 + warp) * 2 + 1] = globaltimer(); }
+    if (trace && lane == 0) { atomicMax(&trace[6], globaltimer()); plan.trace[(size_t)plan.n_cta * 8 + 8 + ((size_t)blockIdx.x * 32 + warp) * 4 + 1] = globaltimer(); }
   }
   if (fuse) {
     // ===== fused tail: every warp of the CTA (the producer warp too) refines candidates off the CTA's list =====
@@ -424,7 +455,11 @@ static int launch_staged_cl(fl_tdb db, fl_level_geom g, const uint8_t* lm_level,
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // prologue (feature lists -> shared memory) overlaps the front end's tail
   attr[1].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = (fl_pdl_enabled() && !plan.trace) ? 2 : 1;
+  // no cluster attribute for CL == 1: a plain launch (the attribute alone selects the cluster launch path)
+  const bool pdl = fl_pdl_enabled() && !plan.trace;
+  if (CL == 1) { attr[0] = attr[1]; cfg.numAttrs = pdl ? 1 : 0; }
+  else cfg.numAttrs = pdl ? 2 : 1;
+  cfg.attrs = attr;
   if (plan.trace) k_stamp<<<1, 1, 0, s>>>(plan.trace + (size_t)plan.n_cta * 8);
   const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, db, g, lm_level, threshold, cand, cap, d_count, plan, ra);
   if (plan.trace) k_stamp<<<1, 1, 0, s>>>(plan.trace + (size_t)plan.n_cta * 8 + 1);
@@ -490,7 +525,7 @@ bool fl_plan_staged(const fl_level_geom& g, int M, int n_templates, int max_posi
   // separate refinement launch (stage 143 us vs 43 + 11 us): candidates cluster in the few CTAs that own a matching template,
   // one warp per candidate leaves ~2 features' loads in flight under the 64-register cap, and the other 140 CTAs idle.
   const int fuse_cap = env_int("FL_FUSE_TAIL", 0) ? 2048 : 0;                    // candidates per CTA list (16 B each)
-  const size_t lists = (size_t)p.tpc * 16 + ((size_t)p.tpc * SS_MAXF + 4) * 4 + (size_t)p.tpc * (SS_MAX_PHASES + 2) + 16 + (size_t)fuse_cap * 16;   // upper bound (n_phases <= SS_MAX_PHASES)
+  const size_t lists = (size_t)p.tpc * 16 + ((size_t)p.tpc * SS_MAXF + 4) * 4 + (size_t)p.tpc * (SS_MAX_PHASES + 2) + 32 + (size_t)fuse_cap * 16 + (size_t)p.nw_template * 128 * 5;   // upper bound (n_phases <= SS_MAX_PHASES)
   const size_t avail = 227 * 1024 - 1024;
   if (lists + 4096 > avail) return false;
   const size_t budget = ((avail - lists) / nbuf) & ~(size_t)127;
@@ -513,7 +548,8 @@ bool fl_plan_staged(const fl_level_geom& g, int M, int n_templates, int max_posi
   p.smem_bytes = p.n_buf * p.buf_bytes + p.tpc * 16 + (p.tpc * SS_MAXF + 4) * 4 + p.tpc * p.pre_stride;
   p.fuse_list_off = (p.smem_bytes + 15) & ~15;
   p.fuse_list_cap = fuse_cap;
-  p.smem_bytes = p.fuse_list_off + fuse_cap * 16;
+  p.stage_off = (p.fuse_list_off + fuse_cap * 16 + 15) & ~15;              // emission staging: one similarity map (NW x 32 words)
+  p.smem_bytes = p.stage_off + p.nw_template * 128 * 5;                     // the map (NW x 32 words) + one list word per cell
   if (p.smem_bytes > 227 * 1024 - 512) return false;
   *plan = p;
   return true;

@@ -336,6 +336,33 @@ def test_device_resident_and_sharded_api_single_gpu():
     assert h.launch_count() > 0
 
 
+def test_read_linemod_file_then_match(tmp_path):
+    """readLinemod (linemod_if.cpp:36-47): a template file in the reference's layout -> device database -> the oracle's matches;
+    and the async halves of match_device give the same list as the synchronous call."""
+    from fealess_b200 import linemod_io
+    b, d = synth.make_frame(640, 480, 0)
+    det = _oracle(b, d)
+    q = [det.quantized(l, m) for l in range(2) for m in range(2)]
+    ts = synth.make_templates(40, n_classes=2, seed=16, quantized=q, planted_fraction=0.25)
+    det.set_templates(ts)
+    want = det.match(75.0)
+    D0 = fb.Detector()
+    D0.add_template_set(ts)
+    path = str(tmp_path / "linemod_templates.yml")
+    linemod_io.write_linemod(D0, path)
+    D = linemod_io.read_linemod(path)
+    rc, matches = D.match([b, d], 75.0)
+    assert rc == 0 and len(matches) == len(want) > 0
+    for m, w in zip(matches, want):
+        assert (m.x, m.y, np.float32(m.similarity), m.class_id, m.template_id) == (w["x"], w["y"], w["similarity"], "obj%02d" % w["class_idx"], w["template_id"])
+    import torch
+    h = D._handle
+    tb, td = torch.from_numpy(b).cuda(), torch.from_numpy(d.view(np.int16)).cuda()
+    h.match_device_async(tb.data_ptr(), td.data_ptr(), 640, 480, 75.0)
+    h.match_wait()
+    assert np.array_equal(h.match_fetch(), want)
+
+
 def test_reference_facing_detector_mirror():
     b, d = synth.make_frame(640, 480, 0)
     det = _oracle(b, d)

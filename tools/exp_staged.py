@@ -14,10 +14,13 @@ NT = int(sys.argv[1]) if len(sys.argv) > 1 else 8000
 
 
 def trace(h):
-    buf = np.zeros(4096 * 8, np.uint64)
+    buf = np.zeros(8192 * 8, np.uint64)
     n = fb.lib().fl_debug_get(h._h, 4, 0, 0, 0, C.c_void_p(buf.ctypes.data), C.c_size_t(buf.nbytes))
     if n <= 0:
         return None
+    per_warp = buf[n * 8 + 8:n * 8 + 8 + n * 128].reshape(n, 32, 4).astype(np.int64)      # [cta][warp]{loop end, warp end}
+    global PER_WARP
+    PER_WARP = per_warp
     return buf[:n * 8].reshape(n, 8).astype(np.int64), buf[n * 8:n * 8 + 2].astype(np.int64)
 
 
@@ -62,6 +65,21 @@ def main():
                 (tr[:, 3] - tr[:, 2]).min() / 1e3, (tr[:, 3] - tr[:, 2]).mean() / 1e3, (tr[:, 3] - tr[:, 2]).max() / 1e3,
                 (tr[:, 4] - tr[:, 3]).mean() / 1e3)
         print(msg, flush=True)
+        if tr is not None:
+            pw = PER_WARP
+            live = pw[:, :, 0] > 0
+            emis = (pw[:, :, 1] - pw[:, :, 0])[live] / 1e3
+            t0 = tr[:, 0].min()
+            loop_end = (pw[:, :, 0][live] - t0) / 1e3
+            warp_end = (pw[:, :, 1][live] - t0) / 1e3
+            d = np.where(live, pw[:, :, 1] - pw[:, :, 0], 0)
+            for idx in np.argsort(d.ravel())[::-1][:6]:
+                c, w = divmod(int(idx), 32)
+                print("  slow warp: cta %d warp %d loop end %.1f us emission %.2f us | loop end -> before atomic %.2f, atomic %.2f, after atomic -> end %.2f"
+                      % (c, w, (pw[c, w, 0] - t0) / 1e3, d[c, w] / 1e3, (pw[c, w, 2] - pw[c, w, 0]) / 1e3, (pw[c, w, 3] - pw[c, w, 2]) / 1e3, (pw[c, w, 1] - pw[c, w, 3]) / 1e3))
+            print("per-warp: loop end us p50 %.1f p99 %.1f max %.1f | warp end us p50 %.1f p99 %.1f max %.1f | emission us p50 %.2f p90 %.2f p99 %.2f max %.2f, warps > 2 us: %d of %d"
+                  % (np.percentile(loop_end, 50), np.percentile(loop_end, 99), loop_end.max(), np.percentile(warp_end, 50), np.percentile(warp_end, 99), warp_end.max(),
+                     np.percentile(emis, 50), np.percentile(emis, 90), np.percentile(emis, 99), emis.max(), int((emis > 2).sum()), emis.size))
         h.close()
 
 
