@@ -49,7 +49,7 @@ struct fl_handle {
   uint8_t* d_lm[FL_MAX_LEVELS]; size_t lm_bytes[FL_MAX_LEVELS];
   bool used_mask[FL_MAX_MODALITIES]; bool keep_spread;
   // state between the enqueue half (fl_match_device_async, ..._async) and fl_match_wait
-  bool pend_sort, pend_match, pend_own, pend_masks_valid; fl_lists pend_lists; fl_match_t* pend_out; int pend_out_cap; int* pend_out_count;
+  bool pend_sort, pend_match, pend_own, pend_masks_valid, pend_small_fused; fl_lists pend_lists; fl_match_t* pend_out; int pend_out_cap; int* pend_out_count;
   const void* pend_bgr; const void* pend_depth; int pend_W, pend_H; float pend_threshold; const void* pend_masks[FL_MAX_MODALITIES]; std::vector<int32_t> pend_filter;
   unsigned long long* d_fe_trace; int fe_trace_jobs, fe_trace_kind[FL_FE_MAX_JOBS], fe_trace_ctas[FL_FE_MAX_JOBS];
   unsigned* d_fe_counters; unsigned fe_counter_base[FL_FE_MAX_JOBS];   // in-grid dependency counters of the single-launch front end (+ 1 error word)
@@ -152,7 +152,7 @@ extern "C" int fl_create(const fl_params_t* params, fl_handle** out) {
   FL_CUDA(cudaMemset(h->d_count, 0, 4 * sizeof(int)));
   TRY(dalloc(&h->d_fe_counters, FL_FE_MAX_JOBS + 1)); FL_CUDA(cudaMemset(h->d_fe_counters, 0, (FL_FE_MAX_JOBS + 1) * sizeof(unsigned)));
   memset(h->fe_counter_base, 0, sizeof h->fe_counter_base);
-  h->pend_sort = h->pend_match = false; h->d_fe_trace = nullptr; h->fe_trace_jobs = 0;                             // [0] candidate count, [1] CTA ticket counter of k_refine_sort
+  h->pend_sort = h->pend_match = false; h->pend_small_fused = false; h->d_fe_trace = nullptr; h->fe_trace_jobs = 0;                             // [0] candidate count, [1] CTA ticket counter of k_refine_sort
   int kc = 2; while (kc < p.max_candidates) kc <<= 1;
   h->key_cap = kc;
   TRY(dalloc(&h->d_keys, (size_t)kc + 1));      // + room for the two scratch ints behind the keys
@@ -607,7 +607,7 @@ static int run_match_stages(fl_handle* h, const uint8_t* d_bgr, const uint16_t* 
 
 // sort + unique of candidate lists into (d_out, d_out_count); handles the rare > 8,192-record path; leaves
 // h_small = {count, n_live, flag, raw list counts...} and, for the handle's own output block, the first matches in h_first
-struct fl_refine_req { float threshold; fl_match_t* cand; int cap; const int* d_count; };   // refine these candidates in the sort launch (k_refine_sort)
+struct fl_refine_req { float threshold; fl_match_t* cand; int cap; const int* d_count; bool small; };   // refine these candidates in the sort launch (k_refine_sort)
 // first half of sort + unique (optionally with the refinement in the same launch): enqueue only
 static int sort_launch(fl_handle* h, fl_lists L, fl_match_t* d_out, int out_cap, int* d_out_count, bool fetch_first, const fl_xchg* xchg = nullptr,
                        const fl_refine_req* refine = nullptr) {
@@ -626,7 +626,8 @@ static int sort_launch(fl_handle* h, fl_lists L, fl_match_t* d_out, int out_cap,
     ra.n_levels = h->p.n_levels;
     for (int l = 0; l < h->p.n_levels; ++l) { ra.g[l] = h->geom[l]; ra.lm[l] = h->d_lm[l]; }
     h->launches += fl_launch_refine_sort(make_tdb(h), ra, refine->threshold, refine->cand, refine->cap, refine->d_count, h->d_count + 1, h->n_sm, L, X, h->key_cap,
-                                         d_out, out_cap, d_out_count, d_hdr, h->h_small, own ? h->h_first : nullptr, std::min(FETCH_FIRST, out_cap), s);
+                                         d_out, out_cap, d_out_count, d_hdr, h->h_small, own ? h->h_first : nullptr, std::min(FETCH_FIRST, out_cap), refine->small, s);
+    h->pend_small_fused = refine->small;
   } else {
     h->launches += fl_launch_sort_unique(L, X, h->key_cap, d_out, out_cap, d_out_count, d_hdr, h->h_small, own ? h->h_first : nullptr,
                                          std::min(FETCH_FIRST, out_cap), s);
@@ -651,6 +652,14 @@ static int sort_finish(fl_handle* h) {
   int n_upper = 0;
   for (int i = 0; i < std::min(n_lists, 11); ++i) { if (h->h_small[3 + i] > list_cap) h->overflow = true; n_upper += std::min(std::max(h->h_small[3 + i], 0), list_cap); }
   if (n_lists > 11) n_upper = n_lists * list_cap;
+  if (h->h_small[2] && h->pend_small_fused && n_upper <= 8192) {
+    // the fused refinement + sort launch sorts up to 1,024 records in its last CTA; this frame has more (already refined in
+    // place): run the stand-alone one-CTA sort (8,192 keys) on them
+    h->pend_small_fused = false;
+    TRY(sort_launch(h, L, d_out, out_cap, d_out_count, own));
+    return sort_finish(h);
+  }
+  h->pend_small_fused = false;
   if (h->h_small[2]) {                                                          // more records than the one-CTA sort holds: multi-kernel sort
     int rc = fl_launch_sort_unique_big(L, h->d_keys, h->key_cap, n_upper, d_out, out_cap, d_out_count, s);
     if (rc < 0) return FL_ERR_CAPACITY;
@@ -675,15 +684,16 @@ extern "C" int fl_match_device_async(fl_handle* h, const void* d_bgr, const void
                                      float threshold, const int32_t* class_filter, int32_t n_filter) {
   if (!h) return FL_ERR_ARG;
   h->have_result = false; h->pend_match = false;
-  // refinement and sort + unique share one launch (k_refine_sort) when FL_FUSE_REFINE_SORT=1 (developer A/B; measured slower:
-  // the 1,024-thread CTAs it needs cost more to launch than the separate refinement launch they save)
-  static const bool fuse_refine_sort = getenv("FL_FUSE_REFINE_SORT") != nullptr;
-  const bool defer = fuse_refine_sort && h->n_templates > 0 && h->p.n_levels > 1;
+  // refinement and sort + unique share one launch (k_refine_sort<1>: 256-thread CTAs, the last one to finish sorts up to 1,024
+  // records).  FL_SPLIT_REFINE=1: separate launches (developer A/B).  FL_FUSE_REFINE_SORT=1: the variant with 1,024-thread CTAs
+  // and the 8,192-key sort inside (measured slower: those CTAs cost more to launch than the launch they save).
+  static const bool fuse_big = getenv("FL_FUSE_REFINE_SORT") != nullptr, split_refine = getenv("FL_SPLIT_REFINE") != nullptr;
+  const bool defer = !split_refine && h->n_templates > 0 && h->p.n_levels > 1;
   TRY(run_match_stages(h, (const uint8_t*)d_bgr, (const uint16_t*)d_depth, W, H, d_masks, threshold, class_filter, n_filter, h->d_cand,
                        h->p.max_candidates, h->d_count, defer));
   const fl_lists lists = {h->d_cand, 1, h->p.max_candidates, h->p.max_candidates, h->d_count, 1};
   const bool in_sort = defer && !(h->use_staged && h->plan.fuse_list_cap > 0);
-  const fl_refine_req req = {threshold, h->d_cand, h->p.max_candidates, h->d_count};
+  const fl_refine_req req = {threshold, h->d_cand, h->p.max_candidates, h->d_count, !fuse_big};
   TRY(sort_launch(h, lists, h->d_out, h->p.max_candidates, h->d_out_count, true, nullptr, in_sort ? &req : nullptr));
   // kept for fl_match_wait: the fused-tail overflow case re-runs the frame
   h->pend_match = true; h->pend_bgr = d_bgr; h->pend_depth = d_depth; h->pend_W = W; h->pend_H = H; h->pend_threshold = threshold;

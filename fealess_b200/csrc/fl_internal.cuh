@@ -177,7 +177,7 @@ int fl_launch_sort_unique(fl_lists L, fl_xchg X, int key_cap, fl_match_t* d_out,
 // refinement of every level + sort + unique in one launch (the last CTA to finish sorts); done_ctr: zero-initialised device int
 int fl_launch_refine_sort(fl_tdb db, const fl_refine_args& ra, float threshold, fl_match_t* cand, int cap, const int* d_count, int* done_ctr, int n_sm,
                           fl_lists L, fl_xchg X, int key_cap, fl_match_t* d_out, int out_cap, int* d_out_count, int* d_hdr,
-                          int* h_hdr, fl_match_t* h_first, int h_first_cap, cudaStream_t s);
+                          int* h_hdr, fl_match_t* h_first, int h_first_cap, bool small, cudaStream_t s);
 int fl_launch_sort_unique_big(fl_lists L, fl_sort_key* keys, int key_cap, int n_upper, fl_match_t* d_out, int out_cap, int* d_out_count, cudaStream_t s);
 
 // ---- ICP (icp.cu) --------------------------------------------------------------------------------

@@ -631,8 +631,8 @@ __global__ void __launch_bounds__(1024) k_sort_unique_small(fl_lists L, fl_xchg 
 // threads per CTA refine candidates (a candidate stays with its group for all levels, so no grid-wide step is needed between
 // levels); the CTA that finishes last (ticket on *done_ctr) then sorts the list, prunes duplicates and posts the result to
 // the host.  Saves the launch + dependency gap of every refinement level and of the sort kernel.
-#define RS_GROUPS 4
-__global__ void __launch_bounds__(RS_GROUPS * RF_THREADS, 1) k_refine_sort(const __grid_constant__ fl_tdb db, const __grid_constant__ fl_refine_args ra,
+template <int RS_GROUPS>
+__global__ void __launch_bounds__(RS_GROUPS * RF_THREADS) k_refine_sort(const __grid_constant__ fl_tdb db, const __grid_constant__ fl_refine_args ra,
                                                                           float threshold, fl_match_t* cand, int cap, const int* __restrict__ d_count,
                                                                           int* done_ctr, fl_lists L, fl_xchg X, int key_cap, int smem_keys, fl_match_t* __restrict__ out,
                                                                           int out_cap, int* __restrict__ d_out_count, int* __restrict__ d_hdr,
@@ -731,12 +731,21 @@ int fl_launch_sort_unique(fl_lists L, fl_xchg X, int key_cap, fl_match_t* d_out,
   return 1;
 }
 
+// small = true: one 256-thread group per CTA, 592 CTAs, shared memory for 1,024 keys + staging (no opt-in needed): as cheap
+// to launch as k_refine_level; lists with more than 1,024 records come back flagged and the host runs the stand-alone sort.
+// small = false: four groups per CTA and the full 8,192-key sort (developer A/B, slower to launch).
 int fl_launch_refine_sort(fl_tdb db, const fl_refine_args& ra, float threshold, fl_match_t* cand, int cap, const int* d_count, int* done_ctr, int n_sm,
                           fl_lists L, fl_xchg X, int key_cap, fl_match_t* d_out, int out_cap, int* d_out_count, int* d_hdr,
-                          int* h_hdr, fl_match_t* h_first, int h_first_cap, cudaStream_t s) {
+                          int* h_hdr, fl_match_t* h_first, int h_first_cap, bool small, cudaStream_t s) {
+  if (small) {
+    const int keys = 1024;
+    fl_launch_pdl(k_refine_sort<1>, dim3(4 * (n_sm > 0 ? n_sm : 148)), dim3(RF_THREADS), (size_t)(keys + 1280) * sizeof(fl_sort_key), s, db, ra, threshold, cand, cap,
+                  d_count, done_ctr, L, X, key_cap, keys, d_out, out_cap, d_out_count, d_hdr, h_hdr, h_first, h_first_cap);
+    return 1;
+  }
   static bool configured = false;
-  if (!configured) { cudaFuncSetAttribute(k_refine_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM_LARGE * (int)sizeof(fl_sort_key)); configured = true; }
-  fl_launch_pdl(k_refine_sort, dim3(n_sm > 0 ? n_sm : 148), dim3(RS_GROUPS * RF_THREADS), (size_t)SORT_SMEM_LARGE * sizeof(fl_sort_key), s, db, ra, threshold, cand, cap,
+  if (!configured) { cudaFuncSetAttribute(k_refine_sort<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM_LARGE * (int)sizeof(fl_sort_key)); configured = true; }
+  fl_launch_pdl(k_refine_sort<4>, dim3(n_sm > 0 ? n_sm : 148), dim3(4 * RF_THREADS), (size_t)SORT_SMEM_LARGE * sizeof(fl_sort_key), s, db, ra, threshold, cand, cap,
                 d_count, done_ctr, L, X, key_cap, (int)SORT_SMEM_LARGE, d_out, out_cap, d_out_count, d_hdr, h_hdr, h_first, h_first_cap);
   return 1;
 }
