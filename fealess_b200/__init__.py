@@ -42,7 +42,7 @@ ICP_RESULT_DTYPE = np.dtype([("R", "<f4", (9,)), ("T", "<f4", (3,)), ("dist_mean
 EXPORTED_SYMBOLS = [
     "fl_default_params", "fl_create", "fl_destroy", "fl_last_error", "fl_version", "fl_sync", "fl_stream",
     "fl_upload_templates", "fl_set_template_ids", "fl_num_templates", "fl_get_pose_info", "fl_match", "fl_match_device", "fl_match_device_async", "fl_match_wait", "fl_match_fetch",
-    "fl_match_shard_device", "fl_sort_unique_device", "fl_sort_unique_blocks_device", "fl_exchange_buffer_bytes", "fl_exchange_sort_unique_device", "fl_exchange_sort_unique_device_async", "fl_depth_to_3d", "fl_icp_cloud_to_cloud_ex",
+    "fl_match_shard_device", "fl_sort_unique_device", "fl_sort_unique_blocks_device", "fl_exchange_buffer_bytes", "fl_exchange_sort_unique_device", "fl_exchange_sort_unique_device_async", "fl_match_shard_exchange_device_async", "fl_depth_to_3d", "fl_icp_cloud_to_cloud_ex",
     "fl_detection_batch", "fl_detection", "fl_nms", "fl_nms_ex", "fl_debug_keep_spread", "fl_debug_force_baseline", "fl_debug_uses_staged", "fl_debug_get", "fl_launch_count",
     "fl_profile", "fl_last_stage_ms", "fl_last_icp_ms",
 ]
@@ -248,6 +248,14 @@ class Handle:
         arr = (C.c_void_p * world)(*[int(p) for p in peer_buffers])
         _check(lib().fl_exchange_sort_unique_device_async(self._h, rank, world, arr, capacity, C.c_void_p(d_local_block), C.c_uint32(epoch)),
                "fl_exchange_sort_unique_device_async")
+
+    def match_shard_exchange_device_async(self, d_bgr: int, d_depth: int, W: int, H: int, threshold: float, rank: int, world: int,
+                                          peer_buffers: Sequence[int], capacity: int, d_local_block: int, epoch: int, class_filter=None) -> None:
+        cf = None if not class_filter else np.ascontiguousarray(class_filter, np.int32)
+        arr = (C.c_void_p * world)(*[int(p) for p in peer_buffers])
+        _check(lib().fl_match_shard_exchange_device_async(self._h, C.c_void_p(d_bgr), C.c_void_p(d_depth), W, H, C.c_float(threshold), _p(cf),
+                                                          0 if cf is None else int(cf.size), rank, world, arr, capacity, C.c_void_p(d_local_block),
+                                                          C.c_uint32(epoch)), "fl_match_shard_exchange_device_async")
 
     def sync(self):
         _check(lib().fl_sync(self._h), "fl_sync")

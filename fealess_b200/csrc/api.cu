@@ -856,6 +856,30 @@ extern "C" int fl_exchange_sort_unique_device_async(fl_handle* h, int32_t rank, 
   return sort_launch(h, lists, h->d_out, h->p.max_candidates, h->d_out_count, true, &X);
 }
 
+// Template-sharded frame in one go (enqueue only): front end + matchClass on this handle's shard with the candidates written
+// straight into the caller's block [count | records], then ONE launch that refines them, pushes the block to every peer,
+// waits for the peers' blocks and sorts the union (k_refine_sort<1> with the exchange in its last CTA).
+extern "C" int fl_match_shard_exchange_device_async(fl_handle* h, const void* d_bgr, const void* d_depth, int32_t W, int32_t H, float threshold,
+                                                    const int32_t* class_filter, int32_t n_filter, int32_t rank, int32_t world,
+                                                    void* const* peer_buffers, int32_t capacity, fl_match_t* d_local_block, uint32_t epoch) {
+  if (!h || !peer_buffers || !d_local_block || world < 1 || world > FL_XCHG_MAX_WORLD || rank < 0 || rank >= world || capacity < 1 || epoch == 0) return FL_ERR_ARG;
+  FL_CUDA(cudaSetDevice(h->p.device));
+  h->have_result = false; h->pend_match = false;
+  static const bool split_refine = getenv("FL_SPLIT_REFINE") != nullptr;
+  const bool defer = !split_refine && h->n_templates > 0 && h->p.n_levels > 1 && !(h->use_staged && h->plan.fuse_list_cap > 0);
+  fl_match_t* recs = d_local_block + 1;
+  int* d_cnt = reinterpret_cast<int*>(d_local_block);
+  TRY(run_match_stages(h, (const uint8_t*)d_bgr, (const uint16_t*)d_depth, W, H, nullptr, threshold, class_filter, n_filter, recs, capacity, d_cnt, defer));
+  fl_xchg X;
+  memset(&X, 0, sizeof X);
+  X.world = world; X.rank = rank; X.cap = capacity; X.epoch = epoch; X.local_block = d_local_block;
+  for (int p = 0; p < world; ++p) { if (!peer_buffers[p]) return FL_ERR_ARG; X.peer[p] = static_cast<uint8_t*>(peer_buffers[p]); }
+  const uint8_t* own = X.peer[rank] + FL_XCHG_SIGNALS * sizeof(unsigned) + (size_t)(epoch & 1u) * world * ((size_t)capacity + 1) * sizeof(fl_match_t);
+  const fl_lists lists = {reinterpret_cast<const fl_match_t*>(own) + 1, world, capacity, capacity + 1, reinterpret_cast<const int*>(own), 5 * (capacity + 1)};
+  const fl_refine_req req = {threshold, recs, capacity, d_cnt, true};
+  return sort_launch(h, lists, h->d_out, h->p.max_candidates, h->d_out_count, true, &X, defer ? &req : nullptr);
+}
+
 extern "C" int fl_exchange_sort_unique_device(fl_handle* h, int32_t rank, int32_t world, void* const* peer_buffers, int32_t capacity,
                                               const fl_match_t* d_local_block, uint32_t epoch) {
   int rc = fl_exchange_sort_unique_device_async(h, rank, world, peer_buffers, capacity, d_local_block, epoch);

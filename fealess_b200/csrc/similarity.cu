@@ -396,11 +396,11 @@ __device__ __forceinline__ void sort_unique_body(fl_lists L, fl_xchg X, int key_
     const size_t block_recs = (size_t)X.cap + 1;
     const size_t parity_off = FL_XCHG_SIGNALS * sizeof(unsigned) + (size_t)(X.epoch & 1u) * X.world * block_recs * sizeof(fl_match_t);
     const int* src = reinterpret_cast<const int*>(X.local_block);
-    const int n_local = min(max(src[0], 0), X.cap);
+    const int n_local = min(max(__ldcg(src), 0), X.cap);        // L2 loads: in the fused launch other CTAs have just refined these records
     const int n_ints = 5 * (1 + n_local);                       // header record + live part of the list
     for (int p = 0; p < X.world; ++p) {
       int* dst = reinterpret_cast<int*>(X.peer[p] + parity_off + (size_t)X.rank * block_recs * sizeof(fl_match_t));
-      for (int i = tid; i < n_ints; i += blockDim.x) dst[i] = (i == 0) ? n_local : src[i];
+      for (int i = tid; i < n_ints; i += blockDim.x) dst[i] = (i == 0) ? n_local : __ldcg(src + i);
     }
     __threadfence_system();
     __syncthreads();

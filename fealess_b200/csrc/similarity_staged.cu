@@ -236,10 +236,11 @@ __global__ void __launch_bounds__(1024, 1) k_similarity_staged(const __grid_cons
       const int wpr = plan.pre_stride >> 2;
       uint32_t* s_pre32 = reinterpret_cast<uint32_t*>(s_pre);
       const uint32_t* gpre32 = reinterpret_cast<const uint32_t*>(plan.gpre);
+      // (no class lookup here: a disabled class shows up as zero positions in s_meta, which the consumers test after the
+      // barrier - the template -> class -> enabled chain would otherwise sit in front of these loads)
       for (int row = warp; row < plan.tpc; row += n_cwarps) {
         const int t = t_begin + row;
-        const bool on = t < t_end && db.class_enabled[db.class_of[t]];
-        for (int c = lane; c < wpr; c += 32) s_pre32[row * wpr + c] = on ? gpre32[(size_t)t * wpr + c] : 0u;
+        for (int c = lane; c < wpr; c += 32) s_pre32[row * wpr + c] = t < t_end ? gpre32[(size_t)t * wpr + c] : 0u;
       }
     }
     asm volatile("bar.sync 1, %0;" ::"r"(n_cwarps * 32) : "memory");   // consumers only
@@ -288,7 +289,7 @@ __global__ void __launch_bounds__(1024, 1) k_similarity_staged(const __grid_cons
     for (int s = 0; s < TPW; ++s) {
       const int slot = warp + s * n_cwarps;
       const int t = t_begin + slot;
-      const bool in = slot < plan.tpc && t < t_end;
+      const bool in = slot < plan.tpc && t < t_end && s_meta[slot < plan.tpc ? slot : 0].x > 0;   // no positions (or disabled class): no work at all
       live[s] = in;
       pre[s] = s_pre + (in ? slot : 0) * plan.pre_stride;
       fl[s] = s_feat + (in ? slot : 0) * SS_MAXF;
@@ -373,6 +374,11 @@ __global__ void __launch_bounds__(1024, 1) k_similarity_staged(const __grid_cons
       for (int w0 = 0; w0 < n_words_tp; w0 += 32) {
         const int w = w0 + lane;
         const uint32_t v = w < n_words_tp ? s_stage[w] : 0u;
+        {   // most groups of 128 cells hold no candidate: one SWAR test + one ballot rejects them
+          const uint32_t k = (uint32_t)(255 - max(raw_thr, 0)) * 0x00010001u;
+          const uint32_t any = raw_thr < 0 ? 1u : ((((v & 0x00FF00FFu) + k) | (((v >> 8) & 0x00FF00FFu) + k)) & 0x01000100u);
+          if (!__any_sync(0xffffffffu, w < n_words_tp && any != 0)) continue;
+        }
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
           const int raw = (int)((v >> (8 * b)) & 0xFFu), j = 4 * w + b;

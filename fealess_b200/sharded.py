@@ -132,13 +132,15 @@ class ShardedMatcher:
         """One frame, enqueue only: the local match and (p2p exchange) the exchange + merge kernel go onto the handle's stream.
         Returns True when ``match_wait`` is all that is left (p2p); with the NCCL exchange the collective and the merge are
         issued by ``match_wait``."""
+        if self.exchange == "p2p":
+            # front end + matchClass, then ONE launch: refinement, push to the peers, wait, sort of the union
+            self.epoch += 1
+            self.h.match_shard_exchange_device_async(d_bgr, d_depth, W, H, threshold, self.rank, self.world, self._peers, self.cap,
+                                                     self.block.data_ptr(), self.epoch)
+            return True
         recs = records_view(self.block)
         # the count lives in the header record of the block, so the candidates + count travel together
         self.h.match_shard_device(d_bgr, d_depth, W, H, threshold, recs.data_ptr(), self.cap, self.block.data_ptr())
-        if self.exchange == "p2p":
-            self.epoch += 1
-            self.h.exchange_sort_unique_device_async(self.rank, self.world, self._peers, self.cap, self.block.data_ptr(), self.epoch)
-            return True
         return False
 
     def match_wait(self) -> None:

@@ -167,6 +167,12 @@ int fl_sort_unique_blocks_device(fl_handle* h, const fl_match_t* d_blocks, int32
 size_t fl_exchange_buffer_bytes(int32_t world, int32_t capacity);
 int fl_exchange_sort_unique_device(fl_handle* h, int32_t rank, int32_t world, void* const* peer_buffers, int32_t capacity,
                                    const fl_match_t* d_local_block, uint32_t epoch);
+/* fl_match_shard_device + the exchange in one call (enqueue only; finish with fl_match_wait): the candidates go straight into the
+ * caller's block d_local_block = [count | capacity records] (device memory), and ONE launch refines them, pushes the block to
+ * every peer, waits for the peers and sorts the union. */
+int fl_match_shard_exchange_device_async(fl_handle* h, const void* d_bgr, const void* d_depth, int32_t W, int32_t H, float threshold,
+                                         const int32_t* class_filter, int32_t n_filter, int32_t rank, int32_t world,
+                                         void* const* peer_buffers, int32_t capacity, fl_match_t* d_local_block, uint32_t epoch);
 /* enqueue-only half; finish with fl_match_wait */
 int fl_exchange_sort_unique_device_async(fl_handle* h, int32_t rank, int32_t world, void* const* peer_buffers, int32_t capacity,
                                          const fl_match_t* d_local_block, uint32_t epoch);

@@ -382,6 +382,29 @@ def test_reference_facing_detector_mirror():
     assert len(only) == len(det.match(75.0, class_filter=[1]))
 
 
+def test_fused_shard_exchange_in_one_launch_world1():
+    """fl_match_shard_exchange_device_async with a world of one: the rank pushes its block into its own exchange buffer, signals and
+    waits on itself, and the same launch refines + sorts - the whole peer-memory path on a single GPU, twice (both parities)."""
+    import torch
+    W, H, T = 640, 480, (5, 8)
+    b, d = synth.make_frame(W, H, 0)
+    det = _oracle(b, d, T)
+    q = [det.quantized(l, m) for l in range(2) for m in range(2)]
+    ts = synth.make_templates(500, W, H, T, n_classes=3, seed=51, quantized=q, planted_fraction=0.05)
+    det.set_templates(ts)
+    h = fb.Handle(T, (0, 1), W, H)
+    h.upload_templates(ts)
+    cap = 2048
+    xbuf = torch.zeros(int(fb.lib().fl_exchange_buffer_bytes(1, cap)), dtype=torch.uint8, device="cuda")
+    block = torch.zeros((cap + 1) * 5, dtype=torch.int32, device="cuda")
+    tb, td = torch.from_numpy(b).cuda(), torch.from_numpy(d.view(np.int16)).cuda()
+    for epoch, thr in ((1, 70.0), (2, 60.0), (3, 70.0)):
+        h.match_shard_exchange_device_async(tb.data_ptr(), td.data_ptr(), W, H, thr, 0, 1, [xbuf.data_ptr()], cap, block.data_ptr(), epoch)
+        h.match_wait()
+        want = det.match(thr)
+        assert len(want) > 0 and np.array_equal(h.match_fetch(), want), thr
+
+
 def test_two_rank_gather_layout_on_one_gpu():
     """The multi-GPU data path with the collective replaced by a concatenation: two handles hold the two template shards,
     each writes its candidate block [header | records]; the blocks laid out as all_gather_into_tensor would lay them out
