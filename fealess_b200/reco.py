@@ -1,0 +1,137 @@
+"""Host-side mirror of ``CObjRecoLmICP`` - the immediate caller of the hot path (reference CadReco/obj_reco_lmicp.cpp:47-259,
+``SURVEY.md`` section 8f ranks 1 and 3).  Same entry points, argument meaning and status codes:
+
+* ``AddObj(feature_path)``   :67-74   reads ``<path>/linemod_templates.yml`` (``readLinemod``) - and, unlike the reference, ALSO loads
+                                       every rendered template depth image ``<path>/depth/<template_id>.png`` once, converted to
+                                       millimetres (``convertTo(CV_16UC1, 0.1)``, :187).  The reference decodes that PNG from disk
+                                       inside every ``Recognition`` call (:156-157), which would dominate once LINE-MOD + ICP take
+                                       tens of microseconds.
+* ``Recognition(rgb, depth, K)`` :86-204  ``PrepareInputData`` (:216-259: size checks, INTER_LINEAR rescale to 640 columns, intrinsics
+                                       zoom), ``Detector::match`` at 75 %, then ``detection()`` (ICP, <= 10 iterations, 0.5 / 0.01 mm
+                                       thresholds :52-55) on ``matches[0]`` with the template's box as model rect and the box moved to
+                                       the match position as reference rect (:127-132), pose packed as a 4x4 world-to-camera matrix
+                                       (``Convert`` :20-30).
+
+``top_k`` / ``th_obj_dist`` wire what the reference left unwired (section 8f rank 3): the K best matches are refined in ONE batched ICP
+launch (``fl_detection_batch``) and filtered by the reference's ``nonMaximumSuppression`` (ICP/NMS.cpp:6-39).  The defaults
+(``top_k=1``, no NMS) are exactly the reference's behaviour.
+
+Kept from the reference on purpose (``SURVEY.md`` A.6 v): ``detection`` receives the CALLER's intrinsics, not the zoomed ones.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+ERROR_INVALID_PARAM = 0x80000001        # CadReco/lotus_common.h:5-10
+ERROR_OPEN_FILE_FAILED = 0x80000002
+PROC_IMG_WIDTH = 640                    # obj_reco_lmicp.cpp:16
+
+
+def model_depth_to_mm(depth_png: np.ndarray) -> np.ndarray:
+    """``depImg_model_raw.convertTo(depImg_model_raw_1, CV_16UC1, 0.1)`` (:187): fp32 scale, round half to even, saturate."""
+    v = np.rint(depth_png.astype(np.float32) * np.float32(0.1))
+    return np.clip(v, 0, 65535).astype(np.uint16)
+
+
+class ObjRecoLmICP:
+    def __init__(self, device: int = 0, max_width: int = 640, max_height: int = 480):
+        self.m_matching_threshold = 75.0                             # :52-55
+        self.m_icp_it_thr, self.m_dist_mean_thr, self.m_dist_diff_thr = 10, 0.5, 0.01
+        self._args = (device, max_width, max_height)
+        self.m_lm_detector = None
+        self._model_depth: Dict[Tuple[Optional[str], int], np.ndarray] = {}
+        self.m_cam = None
+
+    # ---- AddObj ----
+    def AddObj(self, str_feature_path: str) -> int:
+        from . import linemod_io
+        import cv2
+        try:
+            det = linemod_io.read_linemod(os.path.join(str_feature_path, "linemod_templates.yml"), max_width=self._args[1],
+                                          max_height=self._args[2], device=self._args[0])
+        except (IOError, ValueError):
+            return ERROR_OPEN_FILE_FAILED
+        if det.numClasses() == 0:
+            return ERROR_OPEN_FILE_FAILED
+        depths = {}
+        for cid in det.classIds():
+            for tid in range(det.numTemplates(cid)):
+                if (None, tid) in depths:
+                    continue
+                img = cv2.imread(os.path.join(str_feature_path, "depth", "%d.png" % tid), cv2.IMREAD_UNCHANGED)
+                if img is not None:
+                    depths[(None, tid)] = model_depth_to_mm(img)     # the reference keys the file by template_id alone (:156)
+        self.m_lm_detector, self._model_depth = det, depths
+        return 0
+
+    def add_detector(self, detector, model_depths_mm: Dict[Tuple[Optional[str], int], np.ndarray]) -> None:
+        """Programmatic alternative to ``AddObj``: a ready detector + model depth images in mm keyed by (class_id or None, template_id)."""
+        self.m_lm_detector, self._model_depth = detector, dict(model_depths_mm)
+
+    # ---- PrepareInputData ----
+    def _prepare(self, rgb, depth, K) -> Optional[Tuple[np.ndarray, np.ndarray]]:
+        import cv2
+        if rgb is None or depth is None or rgb.ndim != 3 or depth.ndim != 2 or rgb.shape[0] <= 0 or rgb.shape[1] <= 0:
+            return None
+        if rgb.shape[:2] != depth.shape[:2] or int(K["width"]) != rgb.shape[1] or int(K["height"]) != rgb.shape[0]:
+            return None                                              # :223-227
+        zoom = np.float32(PROC_IMG_WIDTH * 1.0 / rgb.shape[1])
+        w, h = PROC_IMG_WIDTH, rgb.shape[0] * PROC_IMG_WIDTH // rgb.shape[1]
+        self.m_cam = dict(fx=K["fx"] * zoom, fy=K["fy"] * zoom, cx=K["cx"] * zoom, cy=K["cy"] * zoom, width=w, height=h)   # :238-246
+        if rgb.shape[1] != w:                                        # TImage2Mat(..., true): interpolation flag 1 = INTER_LINEAR (:42)
+            rgb = cv2.resize(rgb, (w, h), interpolation=cv2.INTER_LINEAR)
+            depth = cv2.resize(depth, (w, h), interpolation=cv2.INTER_LINEAR)
+        return np.ascontiguousarray(rgb, np.uint8), np.ascontiguousarray(depth, np.uint16)
+
+    # ---- Recognition ----
+    def Recognition(self, rgb: np.ndarray, depth: np.ndarray, K: dict, top_k: int = 1, th_obj_dist: Optional[float] = None):
+        """Returns (status, results); results = list of dicts {strObjTag, tWorld2Cam (4x4 fp32), similarity, template_id, icp}."""
+        from . import nonMaximumSuppression
+        if self.m_lm_detector is None:
+            return ERROR_INVALID_PARAM, []
+        prep = self._prepare(rgb, depth, K)
+        if prep is None:
+            return ERROR_INVALID_PARAM, []
+        m_rgb, m_depth = prep
+        det = self.m_lm_detector
+        rc, matches = det.match([m_rgb, m_depth], self.m_matching_threshold)
+        if rc != 0:
+            return ERROR_INVALID_PARAM, []
+        if not matches:
+            return 0, []
+        hyps = []
+        for m in matches[:max(1, top_k)]:
+            tmpl = det.getTemplates(m.class_id, m.template_id)[0]            # current_template[0] (:111, :127-132)
+            w, h, ox, oy = int(tmpl[0]), int(tmpl[1]), int(tmpl[2]), int(tmpl[3])
+            md = self._model_depth.get((m.class_id, m.template_id))
+            if md is None:
+                md = self._model_depth.get((None, m.template_id))
+            if md is None:
+                continue
+            pose = np.asarray(det.getPoseInfo(m.template_id, m.class_id), np.float32).reshape(-1)
+            P = pose[:12].reshape(3, 4)
+            hyps.append(dict(match=m, model_depth=md, rect_model=(ox, oy, w, h), rect_ref=(ox + (m.x - ox), oy + (m.y - oy), w, h),
+                             r_match=P[:, :3].copy(), t_match=P[:, 3].copy(), d_match=float(pose[12])))
+        if not hyps:
+            return 0, []
+        Kc = (float(K["fx"]), float(K["fy"]), float(K["cx"]), float(K["cy"]))   # the caller's intrinsics, as the reference passes them (:188)
+        res = det._handle.detection_batch(m_depth, Kc, [h["model_depth"] for h in hyps], [h["rect_model"] for h in hyps],
+                                          [h["rect_ref"] for h in hyps], [h["r_match"] for h in hyps], [h["t_match"] for h in hyps],
+                                          self.m_icp_it_thr, self.m_dist_mean_thr, self.m_dist_diff_thr)
+        out = []
+        for hyp, r in zip(hyps, res):
+            if int(r["status"]) != 0:                                 # rect outside the frame: the reference throws (detection.cpp:43-44)
+                continue
+            pose4 = np.zeros((4, 4), np.float32)                      # Convert (:20-30)
+            pose4[:3, :3] = r["R"].reshape(3, 3); pose4[:3, 3] = r["T"]; pose4[3, 3] = 1.0
+            out.append(dict(strObjTag=hyp["match"].class_id, tWorld2Cam=pose4, similarity=float(hyp["match"].similarity),
+                            template_id=int(hyp["match"].template_id), icp=r.copy()))
+        if th_obj_dist is not None and len(out) > 1:                  # nonMaximumSuppression over the refined objects (NMS.cpp:6-39)
+            objs = [dict(match_class=o["strObjTag"], match_sim=o["similarity"], r=o["tWorld2Cam"][:3, :3], t=o["tWorld2Cam"][:3, 3],
+                         pts_model=int(o["icp"]["n_points"]), icp_dist=float(o["icp"]["dist_mean"])) for o in out]
+            keep = nonMaximumSuppression(objs, th_obj_dist, det._handle)
+            out = [out[k["index"]] for k in keep]
+        return 0, out

@@ -138,3 +138,47 @@ def test_nms_matches_oracle_and_golden(h, golden_dir):
     objs = [dict(match_class=i % 3, match_sim=90.0 - i, r=np.eye(3), t=z["nms_t3"][i], pts_model=int(z["nms_n"][i]), icp_dist=float(z["nms_dist"][i])) for i in range(24)]
     res = fb.nonMaximumSuppression(objs, 25.0, handle=h)
     assert [r["index"] for r in res] == list(z["nms_out_th25"])
+
+
+def test_recognition_mirror_end_to_end(tmp_path):
+    """CObjRecoLmICP mirror (obj_reco_lmicp.cpp:67-204): AddObj reads linemod_templates.yml + every depth/<id>.png once, Recognition =
+    match at 75 % -> ICP on matches[0] with the template box as model rect and the box at the match position as reference rect ->
+    4x4 pose.  Checked against the oracle's match list and the oracle's detection() on the same rects; top_k + NMS wire the batch path."""
+    import cv2
+    from fealess_b200 import linemod_io, reco
+    W, H, T = 640, 480, (5, 8)
+    b, d = synth.make_frame(W, H, 0)
+    det = F.Detector(T)
+    assert det.process(b, d) == 0
+    q = [det.quantized(l, m) for l in range(2) for m in range(2)]
+    ts = synth.make_templates(24, W, H, T, n_classes=1, seed=61, quantized=q, planted_fraction=0.5)
+    det.set_templates(ts)
+    want = det.match(75.0)
+    assert len(want) > 0
+    D0 = fb.Detector()
+    D0.add_template_set(ts)
+    linemod_io.write_linemod(D0, str(tmp_path / "linemod_templates.yml"))
+    (tmp_path / "depth").mkdir()
+    for tid in range(ts.n_templates):                                   # rendered model depth in 0.1 mm units, as the reference stores it
+        cv2.imwrite(str(tmp_path / "depth" / ("%d.png" % tid)), (d.astype(np.uint32) * 10).clip(0, 65535).astype(np.uint16))
+    r = reco.ObjRecoLmICP()
+    assert r.AddObj(str(tmp_path)) == 0
+    K = dict(fx=608.0, fy=608.0, cx=320.0, cy=240.0, width=W, height=H)
+    rc, res = r.Recognition(b, d, K)
+    assert rc == 0 and len(res) == 1
+    top = want[0]
+    assert res[0]["strObjTag"] == "obj%02d" % top["class_idx"] and res[0]["template_id"] == top["template_id"]
+    hdr, _ = ts.template(int(top["template_id"]), 0, 0)
+    rect_model = (int(hdr[2]), int(hdr[3]), int(hdr[0]), int(hdr[1]))
+    rect_ref = (int(top["x"]), int(top["y"]), int(hdr[0]), int(hdr[1]))
+    P = ts.pose13[int(top["template_id"])][:12].reshape(3, 4)
+    md = reco.model_depth_to_mm((d.astype(np.uint32) * 10).clip(0, 65535).astype(np.uint16))
+    o = F.detection(md, d, (608.0, 608.0, 320.0, 240.0), rect_model, rect_ref, r_match=P[:, :3], t_match=P[:, 3], d_match=float(ts.pose13[int(top["template_id"])][12]))
+    if o["rc"] == 0:
+        pose = res[0]["tWorld2Cam"]
+        assert rot_err(o["R"], pose[:3, :3]) < 1e-4 and float(np.abs(o["T"] - pose[:3, 3]).max()) < 0.1
+        assert pose[3].tolist() == [0.0, 0.0, 0.0, 1.0]
+    rc, many = r.Recognition(b, d, K, top_k=5, th_obj_dist=1e9)           # everything within th of the first -> one object survives NMS
+    assert rc == 0 and len(many) == 1
+    rc, many = r.Recognition(b, d, K, top_k=5)
+    assert rc == 0 and 1 <= len(many) <= 5
