@@ -462,7 +462,10 @@ static int launch_staged_cl(fl_tdb db, fl_level_geom g, const uint8_t* lm_level,
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // prologue (feature lists -> shared memory) overlaps the front end's tail
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   // no cluster attribute for CL == 1: a plain launch (the attribute alone selects the cluster launch path)
-  const bool pdl = fl_pdl_enabled() && !plan.trace;
+  // FL_PDL_SIM=1 (developer A/B): programmatic dependent launch for THIS kernel only - its CTAs may become resident and run their
+  // prologue while the front-end launch drains
+  static const bool pdl_sim = getenv("FL_PDL_SIM") != nullptr;
+  const bool pdl = (fl_pdl_enabled() || pdl_sim) && !plan.trace;
   if (CL == 1) { attr[0] = attr[1]; cfg.numAttrs = pdl ? 1 : 0; }
   else cfg.numAttrs = pdl ? 2 : 1;
   cfg.attrs = attr;
