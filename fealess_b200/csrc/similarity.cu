@@ -739,8 +739,16 @@ int fl_launch_refine_sort(fl_tdb db, const fl_refine_args& ra, float threshold, 
                           int* h_hdr, fl_match_t* h_first, int h_first_cap, bool small, cudaStream_t s) {
   if (small) {
     const int keys = 1024;
-    fl_launch_pdl(k_refine_sort<1>, dim3(4 * (n_sm > 0 ? n_sm : 148)), dim3(RF_THREADS), (size_t)(keys + 1280) * sizeof(fl_sort_key), s, db, ra, threshold, cand, cap,
-                  d_count, done_ctr, L, X, key_cap, keys, d_out, out_cap, d_out_count, d_hdr, h_hdr, h_first, h_first_cap);
+    static const bool pdl_refine = getenv("FL_PDL_REFINE") != nullptr;       // developer A/B: pre-launch behind the similarity kernel
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(4 * (n_sm > 0 ? n_sm : 148)); cfg.blockDim = dim3(RF_THREADS); cfg.dynamicSmemBytes = (size_t)(keys + 1280) * sizeof(fl_sort_key); cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = (fl_pdl_enabled() || pdl_refine) ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, k_refine_sort<1>, db, ra, threshold, cand, cap, d_count, done_ctr, L, X, key_cap, keys, d_out, out_cap, d_out_count, d_hdr, h_hdr, h_first,
+                       h_first_cap);
     return 1;
   }
   static bool configured = false;
