@@ -268,8 +268,10 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     per_step = np.array([a.elapsed_time(b) for a, b in evs])
     if args.per_step:
-        sys.stderr.write("rank %d per-step device ms: p10 %.4f p50 %.4f p90 %.4f max %.4f mean %.4f\n"
-                         % (rank, *np.percentile(per_step, [10, 50, 90]), per_step.max(), per_step.mean()))
+        slow = np.nonzero(per_step > 3 * np.median(per_step))[0]
+        sys.stderr.write("rank %d per-step device ms: p10 %.4f p50 %.4f p90 %.4f max %.4f mean %.4f | steps > 3x median: %s\n"
+                         % (rank, *np.percentile(per_step, [10, 50, 90]), per_step.max(), per_step.mean(),
+                            ", ".join("%d (%.2f ms)" % (i, per_step[i]) for i in slow[:8]) or "none"))
     dev_ms = float(per_step.sum())
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:

@@ -149,8 +149,13 @@ void fl_launch_pack_staged(fl_tdb db, fl_level_geom g, fl_staged_plan plan, cuda
 // One feature of one template: lane g owns the NW consecutive 32-bit words [g*NW, (g+1)*NW) of the similarity map, so
 // its window is the NW + 1 consecutive words starting at its base + the feature's word offset: NW + 1 loads (instead of
 // two per word), one funnel shift and one add per word.  NW is odd, so the 32 lanes of one load hit 32 different banks.
+#ifndef FL_SS_IMAD
+#define FL_SS_IMAD 0      // 1: every other add goes to the FMA pipe as IMAD (x * one + acc, `one` a run-time 1) to take load off the ALU pipe the
+                          // funnel shifts use.  Measured on B200: SLOWER (loop 27.3 vs 25.9 us) - two-operand IADD3s fold two adds into one
+                          // issue slot, IMADs do not, and issue slots matter more here than the ALU pipe.
+#endif
 template <int NW>
-__device__ __forceinline__ void accumulate_feature(const uint8_t* __restrict__ lane_base, uint32_t fw, uint32_t (&acc)[NW]) {
+__device__ __forceinline__ void accumulate_feature(const uint8_t* __restrict__ lane_base, uint32_t fw, uint32_t (&acc)[NW], uint32_t one) {
   const uint32_t* w = reinterpret_cast<const uint32_t*>(lane_base + (fw >> 5));
   constexpr int CH = 12;                                      // loads in flight per chunk (register budget)
   uint32_t carry = w[0];
@@ -161,7 +166,12 @@ __device__ __forceinline__ void accumulate_feature(const uint8_t* __restrict__ l
 #pragma unroll
     for (int i = 0; i < CH; ++i) if (c + i < NW) v[i + 1] = w[c + i + 1];
 #pragma unroll
-    for (int i = 0; i < CH; ++i) if (c + i < NW) acc[c + i] += __funnelshift_r(v[i], v[i + 1], fw);   // shift = low 5 bits; four u8 lanes, no carry (sums <= 252)
+    for (int i = 0; i < CH; ++i)
+      if (c + i < NW) {
+        const uint32_t x = __funnelshift_r(v[i], v[i + 1], fw);   // shift = low 5 bits; four u8 lanes, no carry (sums <= 252)
+        if (FL_SS_IMAD && ((c + i) & 1)) asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc[c + i]) : "r"(x), "r"(one));
+        else acc[c + i] += x;
+      }
     carry = v[(NW - c) < CH ? (NW - c) : CH];
   }
 }
@@ -299,6 +309,7 @@ __global__ void __launch_bounds__(1024, 1) k_similarity_staged(const __grid_cons
     }
     int b = 0, p = rot;
     uint32_t par = 0;
+    const uint32_t one = (uint32_t)(plan.cluster > 0);        // 1, but not provably so: keeps the IMADs of accumulate_feature
     const uint8_t* lane_base0 = s_buf + lane * (NW * 4);
     for (int q = 0; q < n_phases; ++q) {
       mbar_wait(&s_full[b], par);
@@ -315,7 +326,7 @@ __global__ void __launch_bounds__(1024, 1) k_similarity_staged(const __grid_cons
           uint32_t fw = *fp;
           do {
             const uint32_t nx = fp[1];                        // next feature word (one past the list is a valid pad word)
-            accumulate_feature<NW>(lane_base, fw, acc[s]);
+            accumulate_feature<NW>(lane_base, fw, acc[s], one);
             fw = nx; ++fp;
           } while (fp < fe);
         }
