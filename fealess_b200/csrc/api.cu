@@ -683,6 +683,7 @@ static int run_sort_unique(fl_handle* h, fl_lists L, fl_match_t* d_out, int out_
 extern "C" int fl_match_device_async(fl_handle* h, const void* d_bgr, const void* d_depth, int32_t W, int32_t H, const void* const* d_masks,
                                      float threshold, const int32_t* class_filter, int32_t n_filter) {
   if (!h) return FL_ERR_ARG;
+  if (h->pend_sort) { fl_set_error("fl_match_wait has not been called for the previous frame"); return FL_ERR_STATE; }
   h->have_result = false; h->pend_match = false;
   // refinement and sort + unique share one launch (k_refine_sort<1>: 256-thread CTAs, the last one to finish sorts up to 1,024
   // records).  FL_SPLIT_REFINE=1: separate launches (developer A/B).  FL_FUSE_REFINE_SORT=1: the variant with 1,024-thread CTAs
@@ -864,6 +865,7 @@ extern "C" int fl_match_shard_exchange_device_async(fl_handle* h, const void* d_
                                                     void* const* peer_buffers, int32_t capacity, fl_match_t* d_local_block, uint32_t epoch) {
   if (!h || !peer_buffers || !d_local_block || world < 1 || world > FL_XCHG_MAX_WORLD || rank < 0 || rank >= world || capacity < 1 || epoch == 0) return FL_ERR_ARG;
   FL_CUDA(cudaSetDevice(h->p.device));
+  if (h->pend_sort) { fl_set_error("fl_match_wait has not been called for the previous frame"); return FL_ERR_STATE; }
   h->have_result = false; h->pend_match = false;
   static const bool split_refine = getenv("FL_SPLIT_REFINE") != nullptr;
   const bool defer = !split_refine && h->n_templates > 0 && h->p.n_levels > 1 && !(h->use_staged && h->plan.fuse_list_cap > 0);

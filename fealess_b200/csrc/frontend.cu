@@ -555,7 +555,7 @@ __global__ void __launch_bounds__(256, 8) k_front_end_wave(fl_fe_wave w) {
   if (jb.wait_slot >= 0) {
     // In-grid dependency: CTAs are dispatched in blockIdx order and a producing job always precedes its consumers in the grid,
     // so every producer CTA is resident (or done) before a consumer starts to wait here.  The wait is bounded: after ~1 s it gives
-    // up and raises dep_error instead of hanging the device.
+    // up, records the job in dep_error and traps (the host's next CUDA call fails with FL_ERR_CUDA) instead of hanging the device.
     if (threadIdx.x == 0) {
       const unsigned* c = w.counters + jb.wait_slot;
       const long long t0 = clock64();
@@ -563,7 +563,11 @@ __global__ void __launch_bounds__(256, 8) k_front_end_wave(fl_fe_wave w) {
       for (;;) {
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(c) : "memory");
         if ((int)(v - jb.wait_target) >= 0) break;
-        if (clock64() - t0 > (1ll << 31)) { if (w.dep_error) *w.dep_error = 1; break; }
+        if (clock64() - t0 > (1ll << 31)) {           // never observed; fail loudly (the next CUDA call of the host reports it) instead of computing on stale data
+          if (w.dep_error) *w.dep_error = 1 + j;
+          __threadfence_system();
+          __trap();
+        }
         __nanosleep(64);
       }
     }

@@ -359,6 +359,9 @@ def test_read_linemod_file_then_match(tmp_path):
     h = D._handle
     tb, td = torch.from_numpy(b).cuda(), torch.from_numpy(d.view(np.int16)).cuda()
     h.match_device_async(tb.data_ptr(), td.data_ptr(), 640, 480, 75.0)
+    with pytest.raises(fb.FealessError) as e:                  # one frame in flight per handle
+        h.match_device_async(tb.data_ptr(), td.data_ptr(), 640, 480, 75.0)
+    assert e.value.rc == fb.FL_ERR_STATE
     h.match_wait()
     assert np.array_equal(h.match_fetch(), want)
 
