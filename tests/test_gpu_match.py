@@ -246,6 +246,27 @@ def test_three_levels_720p():
     assert len(want) > 0 and np.array_equal(got, want)
 
 
+def test_four_levels_1080p():
+    """BASELINE config C5's geometry: 1920x1080, four pyramid levels, T = {5,5,5,5} (the only T that divides every level,
+    SURVEY.md 8d): 16 front-end jobs in one launch with a three-deep pyrDown chain, the depth job writing three pyramid levels,
+    partial tiles at 240x135, three refinement levels inside the fused refinement + sort launch."""
+    W, H, T = 1920, 1080, (5, 5, 5, 5)
+    b, d = synth.make_frame(W, H, 3)
+    det = _oracle(b, d, T)
+    q = [det.quantized(l, m) for l in range(4) for m in range(2)]
+    ts = synth.make_templates(300, W, H, T, n_classes=5, seed=15, quantized=q, planted_fraction=0.1, max_size=160)
+    det.set_templates(ts)
+    h = fb.Handle(T, (0, 1), W, H)
+    h.upload_templates(ts)
+    h.keep_spread(True)
+    rc, got = h.match(b, d, 70.0)
+    assert rc == 0
+    _check_front_end(h, det, W, H, L=4)
+    want = det.match(70.0)
+    assert len(want) > 0 and np.array_equal(got, want)
+    h.close()
+
+
 @pytest.mark.parametrize("W,H,T", [(240, 160, (5, 8)), (250, 160, (5, 5)), (480, 270, (5, 5)), (80, 60, (5, 5))])
 def test_front_end_ragged_sizes(W, H, T):
     """Partial tiles, widths that are not multiples of 4 (unaligned load / store paths), odd level-1 sizes, tiny frames."""
