@@ -129,6 +129,7 @@ class Handle:
         self.params = p
         self.T = tuple(int(t) for t in T)
         self.L = len(T)
+        self._match_out = {}                                      # capacity -> reusable result buffer of match()
         self.M = len(modality_kind)
         self._h = C.c_void_p()
         rc = L.fl_create(C.byref(p), C.byref(self._h))
@@ -181,7 +182,9 @@ class Handle:
         H, W = ref.shape[:2]
         bgr_c = None if bgr is None else np.ascontiguousarray(bgr, np.uint8)
         dep_c = None if depth is None else np.ascontiguousarray(depth, np.uint16)
-        out = np.zeros(capacity, MATCH_DTYPE)
+        out = self._match_out.get(capacity)                     # result buffer reused across calls (the returned list is a copy)
+        if out is None:
+            out = self._match_out[capacity] = np.zeros(capacity, MATCH_DTYPE)
         cnt = C.c_int32(0)
         cf = None if not class_filter else np.ascontiguousarray(class_filter, np.int32)
         marr = None
@@ -219,7 +222,9 @@ class Handle:
         _check(lib().fl_match_wait(self._h), "fl_match_wait")
 
     def match_fetch(self, capacity: int = 1 << 16) -> np.ndarray:
-        out = np.zeros(capacity, MATCH_DTYPE)
+        out = self._match_out.get(capacity)                     # reused across calls (a fresh 1.3 MB buffer per frame costs more than the fetch)
+        if out is None:
+            out = self._match_out[capacity] = np.zeros(capacity, MATCH_DTYPE)
         cnt = C.c_int32(0)
         _check(lib().fl_match_fetch(self._h, _p(out), capacity, C.byref(cnt)), "fl_match_fetch", ok=(FL_OK, FL_ERR_CAPACITY))
         return out[:min(cnt.value, capacity)].copy()
