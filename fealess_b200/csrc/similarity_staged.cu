@@ -176,14 +176,6 @@ __device__ __forceinline__ void accumulate_feature(const uint8_t* __restrict__ l
   }
 }
 
-// per-byte mask (0xFF where the cell is a candidate) of accumulator word w of a template: raw > raw_thr and cell < tp
-__device__ __forceinline__ uint32_t candidate_mask(uint32_t v, int w, int tp, int raw_thr, uint32_t thr4) {
-  if (4 * w >= tp) return 0u;
-  uint32_t m = raw_thr < 0 ? 0xFFFFFFFFu : __vcmpgtu4(v, thr4);
-  if (4 * w + 4 > tp) m &= 0xFFFFFFFFu >> (8 * (4 * w + 4 - tp));
-  return m;
-}
-
 // FUSE: the kernel also refines its candidates up the pyramid (fl_refine_candidate_warp) and appends FINAL matches to the
 // list: coarsest-level candidates go to a per-CTA list in shared memory, then every warp of the CTA takes candidates off
 // that list.  Candidates beyond the list's capacity are refined on the spot by the warp that found them.
