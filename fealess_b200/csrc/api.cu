@@ -52,7 +52,7 @@ struct fl_handle {
   bool pend_sort, pend_match, pend_own, pend_masks_valid, pend_small_fused; fl_lists pend_lists; fl_match_t* pend_out; int pend_out_cap; int* pend_out_count;
   const void* pend_bgr; const void* pend_depth; int pend_W, pend_H; float pend_threshold; const void* pend_masks[FL_MAX_MODALITIES]; std::vector<int32_t> pend_filter;
   unsigned long long* d_fe_trace; int fe_trace_jobs, fe_trace_kind[FL_FE_MAX_JOBS], fe_trace_ctas[FL_FE_MAX_JOBS];
-  unsigned* d_fe_counters; unsigned fe_counter_base[FL_FE_MAX_JOBS];   // in-grid dependency counters of the single-launch front end (+ 1 error word)
+  unsigned* d_fe_counters; unsigned fe_counter_base[FL_FE_MAX_JOBS]; unsigned fe_row_base[FL_FE_MAX_JOBS];   // in-grid dependency counters of the single-launch front end (+ 1 error word)
   // candidates / matches
   fl_match_t* d_cand; int* d_count; fl_sort_key* d_keys; int key_cap; uint8_t* d_outblk; fl_match_t* d_out; int* d_out_count;   // d_outblk = [16-int summary][matches]
   // pinned host staging
@@ -150,8 +150,10 @@ extern "C" int fl_create(const fl_params_t* params, fl_handle** out) {
   }
   TRY(dalloc(&h->d_cand, (size_t)p.max_candidates)); TRY(dalloc(&h->d_count, 4));
   FL_CUDA(cudaMemset(h->d_count, 0, 4 * sizeof(int)));
-  TRY(dalloc(&h->d_fe_counters, FL_FE_MAX_JOBS + 1)); FL_CUDA(cudaMemset(h->d_fe_counters, 0, (FL_FE_MAX_JOBS + 1) * sizeof(unsigned)));
-  memset(h->fe_counter_base, 0, sizeof h->fe_counter_base);
+  // [FL_FE_MAX_JOBS job counters][1 error word][FL_FE_MAX_JOBS x FL_FE_MAX_TILE_ROWS tile-row counters]
+  TRY(dalloc(&h->d_fe_counters, FL_FE_MAX_JOBS + 1 + FL_FE_MAX_JOBS * FL_FE_MAX_TILE_ROWS));
+  FL_CUDA(cudaMemset(h->d_fe_counters, 0, (FL_FE_MAX_JOBS + 1 + FL_FE_MAX_JOBS * FL_FE_MAX_TILE_ROWS) * sizeof(unsigned)));
+  memset(h->fe_counter_base, 0, sizeof h->fe_counter_base); memset(h->fe_row_base, 0, sizeof h->fe_row_base);
   h->pend_sort = h->pend_match = false; h->pend_small_fused = false; h->d_fe_trace = nullptr; h->fe_trace_jobs = 0;                             // [0] candidate count, [1] CTA ticket counter of k_refine_sort
   int kc = 2; while (kc < p.max_candidates) kc <<= 1;
   h->key_cap = kc;
@@ -342,6 +344,13 @@ static int ensure_geometry(fl_handle* h, int W, int H) {
     FL_CUDA(cudaStreamSynchronize(h->stream));                                  // h->geom is pageable
     h->gW = W; h->gH = H; h->packed = false;
   }
+  if (!h->packed) {
+    // the front end's tile-row counters are per job SLOT and advance by "tiles per row" every frame; a new geometry or template
+    // set can change the job layout, so they restart from zero (stream-ordered with the launches that follow)
+    FL_CUDA(cudaMemsetAsync(h->d_fe_counters + FL_FE_MAX_JOBS + 1, 0, (size_t)FL_FE_MAX_JOBS * FL_FE_MAX_TILE_ROWS * sizeof(unsigned), h->stream));
+    memset(h->fe_row_base, 0, sizeof h->fe_row_base);
+    if (h->n_templates == 0) h->packed = true;
+  }
   if (!h->packed && h->n_templates > 0) {
     fl_launch_pack_features(make_tdb(h), h->d_geom, h->n_features, h->stream); ++h->launches;
     if (p.n_levels > 1) {
@@ -436,6 +445,21 @@ static int run_match_stages(fl_handle* h, const uint8_t* d_bgr, const uint16_t* 
       auto last_job = [&]() -> fl_fe_job& { return w.job[w.n_jobs - 1]; };
       auto job_ctas = [&](int idx) { return (idx + 1 < w.n_jobs ? w.job[idx + 1].cta_begin : w.n_ctas) - w.job[idx].cta_begin; };
       auto produce = [&]() { last_job().signal_slot = w.n_jobs - 1; return w.n_jobs - 1; };
+      static const bool row_deps = getenv("FL_FE_JOB_DEPS") == nullptr;          // FL_FE_JOB_DEPS=1: whole-job waits only (developer A/B)
+      // tile jobs (32 x 16 tiles) also count per tile row; returns false when the image has more tile rows than counters
+      auto produce_rows = [&](int slot) {
+        fl_fe_job& jb = w.job[slot];
+        const int rows = (jb.H + 15) / 16;
+        if (!row_deps || rows > FL_FE_MAX_TILE_ROWS) return;
+        jb.row_base = FL_FE_MAX_JOBS + 1 + slot * FL_FE_MAX_TILE_ROWS;
+      };
+      auto consume_rows = [&](int slot, int shift) {      // spread job: wait per tile row of producer `slot` (level shift for the depth pyramid)
+        const fl_fe_job& pj = w.job[slot];
+        if (pj.row_base < 0) return;
+        fl_fe_job& jb = last_job();
+        jb.wait_row_base = pj.row_base; jb.wait_row_shift = shift; jb.wait_row_count = (pj.H + 15) / 16;
+        jb.wait_row_target = h->fe_row_base[slot] + (unsigned)abs(pj.gx);
+      };
       auto consume = [&](int slot) { last_job().wait_slot = slot; last_job().wait_target = h->fe_counter_base[slot] + (unsigned)job_ctas(slot); };
       // 0. the staged similarity kernel's per-template feature lists -> L2 (they would otherwise cost its prologue DRAM round trips)
       if (h->use_staged && h->n_templates > 0 && n_jobs_single + 3 <= FL_FE_MAX_JOBS) {
@@ -463,6 +487,7 @@ static int run_match_stages(fl_handle* h, const uint8_t* d_bgr, const uint16_t* 
           for (int k = 1; k < L; ++k) { pyr.W[k - 1] = h->geom[k].W; pyr.H[k - 1] = h->geom[k].H; pyr.dst[k - 1] = h->d_q[k][m]; }
           fl_fe_add_depth_v2(&w, d_depth, h->geom[0].W, h->geom[0].H, p.distance_threshold, p.difference_threshold, h->d_q[0][m], pyr.n > 0 ? &pyr : nullptr);
           slot_depth[m] = produce();
+          produce_rows(slot_depth[m]);
         }
       // 3. colour labels, coarsest level first
       for (int l = L - 1; l >= 0; --l)
@@ -470,6 +495,7 @@ static int run_match_stages(fl_handle* h, const uint8_t* d_bgr, const uint16_t* 
           if (p.modality_kind[m] == FL_MODALITY_COLOR_GRADIENT) {
             fl_fe_add_color_v2(&w, l == 0 ? d_bgr : h->d_bgr[l], h->geom[l].W, h->geom[l].H, thr_sq, h->d_q[l][m]);
             slot_color[l][m] = produce();
+            produce_rows(slot_color[l][m]);
             if (l > 0) consume(slot_pyr[l]);
           }
       // 4. spread + response maps + linear memories, coarsest level first (the similarity kernel needs only that one)
@@ -478,9 +504,12 @@ static int run_match_stages(fl_handle* h, const uint8_t* d_bgr, const uint16_t* 
           uint8_t* spread = nullptr;
           if (h->keep_spread) { if (!h->d_spread[l][m]) TRY(dalloc(&h->d_spread[l][m], (size_t)(p.max_width >> l) * (p.max_height >> l))); spread = h->d_spread[l][m]; }
           fl_fe_add_spread(&w, h->d_q[l][m], h->geom[l], h->d_lm[l] + (size_t)m * h->geom[l].mod_stride, spread);
-          consume(p.modality_kind[m] == FL_MODALITY_COLOR_GRADIENT ? slot_color[l][m] : slot_depth[m]);
+          const bool is_color = p.modality_kind[m] == FL_MODALITY_COLOR_GRADIENT;
+          consume(is_color ? slot_color[l][m] : slot_depth[m]);
+          consume_rows(is_color ? slot_color[l][m] : slot_depth[m], is_color ? 0 : l);
         }
       for (int i = 0; i < w.n_jobs; ++i) if (w.job[i].signal_slot >= 0) h->fe_counter_base[i] += (unsigned)job_ctas(i);
+      for (int i = 0; i < w.n_jobs; ++i) if (w.job[i].row_base >= 0) h->fe_row_base[i] += (unsigned)abs(w.job[i].gx);
       static const bool fe_trace = getenv("FL_TRACE") != nullptr;                // developer timeline: per job first start / last end
       if (fe_trace) {
         if (!h->d_fe_trace) TRY(dalloc(&h->d_fe_trace, 2 * FL_FE_MAX_JOBS + 2 * FL_FE_MAX_JOBS));

@@ -78,7 +78,13 @@ struct fl_fe_job {
   // wait_target (all CTAs of the producing job have finished), and bumps counters[signal_slot] when it is done; -1 = none
   int wait_slot, signal_slot;
   unsigned wait_target;
+  // finer grain for the spread jobs: a producing tile job also counts its finished tiles PER TILE ROW (counters[row_base + by]);
+  // a spread CTA that owns grid row gy waits only for the tile rows that hold its label rows [gy T, gy T + 2T - 2] (row y of
+  // its level lives in producer row (y << wait_row_shift) / 16), so it starts while later rows are still being quantised
+  int row_base, wait_row_base, wait_row_shift, wait_row_count;
+  unsigned wait_row_target;
 };
+#define FL_FE_MAX_TILE_ROWS 128
 // NN-downsampled copies of the level-0 depth labels written by the depth job itself: entry i = pyramid level i + 1
 #define FL_FE_MAX_PYR 7
 struct fl_depth_pyr { int n; int W[FL_FE_MAX_PYR], H[FL_FE_MAX_PYR]; uint8_t* dst[FL_FE_MAX_PYR]; };

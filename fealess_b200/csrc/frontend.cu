@@ -552,7 +552,26 @@ __global__ void __launch_bounds__(256, 8) k_front_end_wave(fl_fe_wave w) {
   const fl_fe_job& jb = w.job[j];
   const int local = b - jb.cta_begin;
   if (w.trace && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); atomicMin(w.trace + 2 * j, t); }
-  if (jb.wait_slot >= 0) {
+  if (jb.wait_row_base >= 0) {
+    // row-grained wait of a spread CTA (see fl_fe_job): the producer's tile rows that hold this grid row's label rows
+    if (threadIdx.x == 0) {
+      const int gy = local / jb.gx, T = jb.g.T;
+      const int y0 = gy * T, y1 = min(gy * T + 2 * T - 2, jb.g.H - 1);
+      const int by0 = (y0 << jb.wait_row_shift) >> 4, by1 = min((y1 << jb.wait_row_shift) >> 4, jb.wait_row_count - 1);
+      const long long t0 = clock64();
+      for (int by = by0; by <= by1; ++by) {
+        const unsigned* c = w.counters + jb.wait_row_base + by;
+        unsigned v;
+        for (;;) {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(c) : "memory");
+          if ((int)(v - jb.wait_row_target) >= 0) break;
+          if (clock64() - t0 > (1ll << 31)) { if (w.dep_error) *w.dep_error = 1 + j; __threadfence_system(); __trap(); }
+          __nanosleep(64);
+        }
+      }
+    }
+    __syncthreads();
+  } else if (jb.wait_slot >= 0) {
     // In-grid dependency: CTAs are dispatched in blockIdx order and a producing job always precedes its consumers in the grid,
     // so every producer CTA is resident (or done) before a consumer starts to wait here.  The wait is bounded: after ~1 s it gives
     // up, records the job in dep_error and traps (the host's next CUDA call fails with FL_ERR_CUDA) instead of hanging the device.
@@ -593,7 +612,11 @@ __global__ void __launch_bounds__(256, 8) k_front_end_wave(fl_fe_wave w) {
   if (w.trace) { __syncthreads(); if (threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); atomicMax(w.trace + 2 * j + 1, t); } }
   if (jb.signal_slot >= 0) {
     __syncthreads();                                    // every thread's stores of this CTA ...
-    if (threadIdx.x == 0) { __threadfence(); atomicAdd(w.counters + jb.signal_slot, 1u); }   // ... are visible before the count
+    if (threadIdx.x == 0) {                             // ... are visible before the counts
+      __threadfence();
+      if (jb.row_base >= 0) atomicAdd(w.counters + jb.row_base + local / abs(jb.gx), 1u);
+      atomicAdd(w.counters + jb.signal_slot, 1u);
+    }
   }
 }
 
@@ -603,21 +626,21 @@ void fl_fe_add_color(fl_fe_wave* w, const uint8_t* bgr, int W, int H, float thr_
   const int first = (int)((long long)tiles * part / n_parts), last = (int)((long long)tiles * (part + 1) / n_parts);
   if (last <= first) return;
   fl_fe_job& j = w->job[w->n_jobs++];
-  j.wait_slot = -1; j.signal_slot = -1; j.wait_target = 0;
+  j.wait_slot = -1; j.signal_slot = -1; j.wait_target = 0; j.row_base = -1; j.wait_row_base = -1; j.wait_row_shift = 0; j.wait_row_count = 0; j.wait_row_target = 0;
   j.kind = FL_JOB_COLOR; j.src = bgr; j.dst = q; j.dst2 = nullptr; j.W = W; j.H = H; j.thr_sq = thr_sq;
   j.gx = gx; j.p0 = first; j.p1 = last - first; j.cta_begin = w->n_ctas; w->n_ctas += last - first;
   w->smem = w->smem > (size_t)CQ_SMEM_BYTES ? w->smem : (size_t)CQ_SMEM_BYTES;
 }
 void fl_fe_add_depth(fl_fe_wave* w, const uint16_t* depth, int W, int H, int dist_thr, int diff_thr, uint8_t* q) {
   fl_fe_job& j = w->job[w->n_jobs++];
-  j.wait_slot = -1; j.signal_slot = -1; j.wait_target = 0;
+  j.wait_slot = -1; j.signal_slot = -1; j.wait_target = 0; j.row_base = -1; j.wait_row_base = -1; j.wait_row_shift = 0; j.wait_row_count = 0; j.wait_row_target = 0;
   j.kind = FL_JOB_DEPTH; j.src = reinterpret_cast<const uint8_t*>(depth); j.dst = q; j.dst2 = nullptr; j.W = W; j.H = H; j.p0 = dist_thr; j.p1 = diff_thr;
   j.gx = (W + DQ_TW - 1) / DQ_TW; j.cta_begin = w->n_ctas; w->n_ctas += j.gx * ((H + DQ_TH - 1) / DQ_TH);
   w->smem = w->smem > (size_t)DQ_SMEM_BYTES ? w->smem : (size_t)DQ_SMEM_BYTES;
 }
 void fl_fe_add_color_v2(fl_fe_wave* w, const uint8_t* bgr, int W, int H, float thr_sq, uint8_t* q) {
   fl_fe_job& j = w->job[w->n_jobs++];
-  j.wait_slot = -1; j.signal_slot = -1; j.wait_target = 0;
+  j.wait_slot = -1; j.signal_slot = -1; j.wait_target = 0; j.row_base = -1; j.wait_row_base = -1; j.wait_row_shift = 0; j.wait_row_count = 0; j.wait_row_target = 0;
   j.kind = FL_JOB_COLOR2; j.src = bgr; j.dst = q; j.dst2 = nullptr; j.W = W; j.H = H; j.thr_sq = thr_sq;
   j.gx = (W + C2_TW - 1) / C2_TW; j.p0 = j.p1 = 0; j.cta_begin = w->n_ctas; w->n_ctas += j.gx * ((H + C2_TH - 1) / C2_TH);
   w->smem = w->smem > (size_t)C2_SMEM_BYTES ? w->smem : (size_t)C2_SMEM_BYTES;
@@ -631,7 +654,7 @@ bool fl_fe_add_depth_v2(fl_fe_wave* w, const uint16_t* depth, int W, int H, int 
     w->pyr[slot] = *pyr;
   }
   fl_fe_job& j = w->job[w->n_jobs++];
-  j.wait_slot = -1; j.signal_slot = -1; j.wait_target = 0;
+  j.wait_slot = -1; j.signal_slot = -1; j.wait_target = 0; j.row_base = -1; j.wait_row_base = -1; j.wait_row_shift = 0; j.wait_row_count = 0; j.wait_row_target = 0;
   j.kind = FL_JOB_DEPTH2; j.src = reinterpret_cast<const uint8_t*>(depth); j.dst = q; j.dst2 = nullptr; j.W = W; j.H = H; j.p0 = dist_thr; j.p1 = diff_thr;
   const int gx = (W + D2_TW - 1) / D2_TW;
   j.gx = slot < 0 ? -gx : gx; j.thr_sq = (float)(slot < 0 ? 0 : slot);            // gx < 0: no pyramid; thr_sq carries the pyramid slot
@@ -641,7 +664,7 @@ bool fl_fe_add_depth_v2(fl_fe_wave* w, const uint16_t* depth, int W, int H, int 
 }
 void fl_fe_add_pyrdown(fl_fe_wave* w, const uint8_t* src, int W, int H, uint8_t* dst, bool src_static) {
   fl_fe_job& j = w->job[w->n_jobs++];
-  j.wait_slot = -1; j.signal_slot = -1; j.wait_target = 0;
+  j.wait_slot = -1; j.signal_slot = -1; j.wait_target = 0; j.row_base = -1; j.wait_row_base = -1; j.wait_row_shift = 0; j.wait_row_count = 0; j.wait_row_target = 0;
   j.kind = FL_JOB_PYRDOWN; j.src = src; j.dst = dst; j.dst2 = nullptr; j.W = W; j.H = H; j.gx = 1; j.p0 = src_static ? 1 : 0;
   j.cta_begin = w->n_ctas; w->n_ctas += pyrdown_ctas(W, H);
 }
@@ -649,19 +672,19 @@ void fl_fe_add_prefetch(fl_fe_wave* w, const void* src, size_t bytes) {
   const int lines = (int)((bytes + 127) / 128);
   if (lines <= 0 || w->n_jobs >= FL_FE_MAX_JOBS) return;
   fl_fe_job& j = w->job[w->n_jobs++];
-  j.wait_slot = -1; j.signal_slot = -1; j.wait_target = 0;
+  j.wait_slot = -1; j.signal_slot = -1; j.wait_target = 0; j.row_base = -1; j.wait_row_base = -1; j.wait_row_shift = 0; j.wait_row_count = 0; j.wait_row_target = 0;
   j.kind = FL_JOB_PREFETCH; j.src = static_cast<const uint8_t*>(src); j.dst = nullptr; j.dst2 = nullptr; j.W = lines; j.H = 0; j.gx = 1;
   j.cta_begin = w->n_ctas; w->n_ctas += (lines + 255) / 256;
 }
 void fl_fe_add_resize(fl_fe_wave* w, const uint8_t* src, int W, int H, uint8_t* dst) {
   fl_fe_job& j = w->job[w->n_jobs++];
-  j.wait_slot = -1; j.signal_slot = -1; j.wait_target = 0;
+  j.wait_slot = -1; j.signal_slot = -1; j.wait_target = 0; j.row_base = -1; j.wait_row_base = -1; j.wait_row_shift = 0; j.wait_row_count = 0; j.wait_row_target = 0;
   j.kind = FL_JOB_RESIZE; j.src = src; j.dst = dst; j.dst2 = nullptr; j.W = W; j.H = H; j.gx = 1;
   j.cta_begin = w->n_ctas; w->n_ctas += ((W / 2) * (H / 2) + 255) / 256;
 }
 void fl_fe_add_spread(fl_fe_wave* w, const uint8_t* q, fl_level_geom g, uint8_t* lm_mod, uint8_t* spread_or_null) {
   fl_fe_job& j = w->job[w->n_jobs++];
-  j.wait_slot = -1; j.signal_slot = -1; j.wait_target = 0;
+  j.wait_slot = -1; j.signal_slot = -1; j.wait_target = 0; j.row_base = -1; j.wait_row_base = -1; j.wait_row_shift = 0; j.wait_row_count = 0; j.wait_row_target = 0;
   j.kind = FL_JOB_SPREAD; j.src = q; j.dst = lm_mod; j.dst2 = spread_or_null; j.g = g; j.W = g.W; j.H = g.H;
   int cw = SL_CW;                                       // small levels: narrower CTAs so that the job still fills the SMs
   while (cw > 8 && ((g.Wd + cw - 1) / cw) * g.Hd < 148) cw >>= 1;
