@@ -11,7 +11,8 @@
 //                                                     addPoseInfo / getPoseInfo, getTemplates, getT, pyramidLevels,
 //                                                     numTemplates, numClasses, classIds, getModalities
 //   getDefaultLINE / getDefaultLINEMOD .............. linemod.cpp:1822-1835
-// Not provided (out of scope): addTemplate (training), read/write* (YAML), colormap/drawResponse.
+//   readLinemod / writeLinemod ...................... linemod_if.cpp:36-66: in linemod_io.hpp (own FileStorage-YAML reader / writer)
+// Not provided (out of scope): addTemplate (training), colormap/drawResponse.
 #ifndef FEALESS_B200_LINEMOD_HPP
 #define FEALESS_B200_LINEMOD_HPP
 
@@ -185,6 +186,7 @@ class Detector {
   // for a single class, which is how CadReco uses it (SURVEY.md A.6 iv)
   int addPoseInfo(const float* const pose_info) { TemplatePoseInfo.push_back(std::vector<float>(pose_info, pose_info + 13)); return (int)TemplatePoseInfo.size(); }
   std::vector<float> getPoseInfo(int template_id) { return TemplatePoseInfo.at((size_t)template_id); }
+  int numPoseInfos() const { return (int)TemplatePoseInfo.size(); }   // mirror-only: lets writeLinemod stay inside the list
 
   const std::vector<Ptr<Modality> >& getModalities() const { return modalities; }
   int getT(int pyramid_level) const { return T_at_level[pyramid_level]; }
