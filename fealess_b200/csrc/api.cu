@@ -65,6 +65,10 @@ struct fl_handle {
   fl_icp_ws icp; fl_icp_hyp* d_hyps; float* d_t_init; fl_icp_result_t* d_results; uint16_t* d_model_crops; uint16_t* d_ref_depth;
   size_t ref_depth_cap;
   uint16_t* h_model_crops; fl_icp_hyp* h_hyps; fl_icp_result_t* h_results; size_t h_crop_cap;
+  // rendered template depth crops kept on the device (fl_upload_model_depths) and the geometry of the depth frame that the
+  // last host-input fl_match left in d_in_depth (0 x 0 = none)
+  uint16_t* d_resident; std::vector<size_t> res_off; std::vector<fl_rect_t> res_rect; int res_W, res_H;
+  int in_depth_W, in_depth_H;
 };
 
 template <typename T> static int dalloc(T** p, size_t n) {
@@ -126,6 +130,7 @@ extern "C" int fl_create(const fl_params_t* params, fl_handle** out) {
   h->icp_hyp_cap = h->icp_pts_cap = 0; memset(&h->icp, 0, sizeof h->icp);
   h->d_hyps = nullptr; h->d_t_init = nullptr; h->d_results = nullptr; h->d_model_crops = nullptr; h->d_ref_depth = nullptr; h->ref_depth_cap = 0;
   h->h_model_crops = nullptr; h->h_hyps = nullptr; h->h_results = nullptr; h->h_crop_cap = 0;
+  h->d_resident = nullptr; h->res_W = h->res_H = 0; h->in_depth_W = h->in_depth_H = 0;
   memset(h->d_bgr, 0, sizeof h->d_bgr); memset(h->d_q, 0, sizeof h->d_q); memset(h->d_qm, 0, sizeof h->d_qm);
   memset(h->d_mask, 0, sizeof h->d_mask); memset(h->d_spread, 0, sizeof h->d_spread); memset(h->d_lm, 0, sizeof h->d_lm);
   memset(h->used_mask, 0, sizeof h->used_mask); memset(h->stage_ms, 0, sizeof h->stage_ms); h->icp_ms = 0.f;
@@ -193,7 +198,7 @@ extern "C" int fl_destroy(fl_handle* h) {
   cudaSetDevice(h->p.device);
   cudaStreamSynchronize(h->stream);
   free_templates(h); icp_free(h);
-  cudaFree(h->d_ref_depth);
+  cudaFree(h->d_ref_depth); cudaFree(h->d_resident);
   cudaFree(h->d_in_bgr); cudaFree(h->d_in_depth); cudaFree(h->d_geom);
   for (int l = 0; l < FL_MAX_LEVELS; ++l) {
     cudaFree(h->d_bgr[l]); cudaFree(h->d_lm[l]);
@@ -809,6 +814,7 @@ extern "C" int fl_match(fl_handle* h, const uint8_t* bgr, size_t bgr_stride, con
       FL_CUDA(cudaMemcpyAsync(h->d_in_depth, h->h_depth, (size_t)W * H * 2, cudaMemcpyHostToDevice, s));
     }
     d_depth = h->d_in_depth;
+    h->in_depth_W = W; h->in_depth_H = H;
   }
   if (bgr) {
     if (bgr_stride < (size_t)W * 3) return FL_ERR_SIZE;
@@ -1041,6 +1047,44 @@ extern "C" int fl_icp_cloud_to_cloud_ex(fl_handle* h, const float* pts_ref, int3
   return FL_OK;
 }
 
+// rects inside the W x H frame?  (cv::Mat ROI throw, detection.cpp:43-44)
+static bool rect_inside(const fl_rect_t& a, int W, int H) {
+  return a.x >= 0 && a.y >= 0 && a.width >= 0 && a.height >= 0 && a.x + a.width <= W && a.y + a.height <= H;
+}
+// the reference depth frame on the device: a host frame is uploaded into d_ref_depth; NULL selects the frame the last
+// host-input fl_match left in d_in_depth (Recognition hands the same image to match and to detection, obj_reco_lmicp.cpp:101, 188)
+static int icp_ref_frame(fl_handle* h, const uint16_t* ref_depth, size_t ref_stride, int W, int H, const uint16_t** d_ref) {
+  if (!ref_depth) {
+    if (h->in_depth_W != W || h->in_depth_H != H) { fl_set_error("ref_depth == NULL needs a preceding fl_match of a %d x %d depth frame on this handle (have %d x %d)", W, H, h->in_depth_W, h->in_depth_H); return FL_ERR_STATE; }
+    *d_ref = h->d_in_depth;
+    return FL_OK;
+  }
+  if (ref_stride < (size_t)W * 2) return FL_ERR_ARG;
+  if ((size_t)W * H > h->ref_depth_cap) { cudaFree(h->d_ref_depth); TRY(dalloc(&h->d_ref_depth, (size_t)W * H)); h->ref_depth_cap = (size_t)W * H; }
+  FL_CUDA(cudaMemcpy2DAsync(h->d_ref_depth, (size_t)W * 2, ref_depth, ref_stride, (size_t)W * 2, H, cudaMemcpyHostToDevice, h->stream));
+  *d_ref = h->d_ref_depth;
+  return FL_OK;
+}
+// h_hyps[0..n) are filled: upload them, run prepare + the ICP loop, fetch the results
+static int icp_run_batch(fl_handle* h, const uint16_t* d_ref, int W, int H, fl_intrinsics_t K_ref, int n, fl_icp_params_t prm, fl_icp_result_t* out) {
+  cudaStream_t s = h->stream;
+  FL_CUDA(cudaMemcpyAsync(h->d_hyps, h->h_hyps, sizeof(fl_icp_hyp) * (size_t)n, cudaMemcpyHostToDevice, s));
+  if (h->profile) cudaEventRecord(h->ev[0], s);
+  fl_launch_icp_prepare(d_ref, W, H, K_ref, h->d_hyps, h->icp, h->d_t_init, s); ++h->launches;
+  fl_launch_icp_run(h->icp, prm, h->d_hyps, h->d_t_init, h->d_results, s); ++h->launches;
+  if (h->profile) cudaEventRecord(h->ev[1], s);
+  FL_CUDA(cudaMemcpyAsync(h->h_results, h->d_results, sizeof(fl_icp_result_t) * (size_t)n, cudaMemcpyDeviceToHost, s));
+  FL_CUDA(cudaStreamSynchronize(s));
+  if (h->profile) cudaEventElapsedTime(&h->icp_ms, h->ev[0], h->ev[1]);
+  FL_CUDA(cudaGetLastError());
+  memcpy(out, h->h_results, sizeof(fl_icp_result_t) * (size_t)n);
+  return FL_OK;
+}
+static void icp_fill_pose(fl_icp_hyp& hy, const float* r_match9, const float* t_match3, int i) {
+  for (int k = 0; k < 9; ++k) hy.r_match[k] = r_match9 ? r_match9[9 * i + k] : (k % 4 == 0 ? 1.f : 0.f);
+  for (int k = 0; k < 3; ++k) hy.t_match[k] = t_match3 ? t_match3[3 * i + k] : 0.f;
+}
+
 extern "C" int fl_detection_batch(fl_handle* h, const uint16_t* ref_depth, size_t ref_stride, int32_t W, int32_t H, fl_intrinsics_t K_ref,
                                   const uint16_t* const* model_depth, const size_t* model_stride, const fl_rect_t* rect_model,
                                   const fl_rect_t* rect_ref, const float* r_match9, const float* t_match3, const float* d_match, int32_t n,
@@ -1054,21 +1098,18 @@ extern "C" int fl_detection_batch(fl_handle* h, const uint16_t* ref_depth, size_
   std::vector<int> st(n, FL_OK);
   for (int i = 0; i < n; ++i) {
     const fl_rect_t& a = rect_model[i]; const fl_rect_t& b = rect_ref[i];
-    bool ok = a.x >= 0 && a.y >= 0 && a.width >= 0 && a.height >= 0 && a.x + a.width <= W && a.y + a.height <= H &&
-              b.x >= 0 && b.y >= 0 && b.width >= 0 && b.height >= 0 && b.x + b.width <= W && b.y + b.height <= H && model_depth[i];
-    if (!ok) { st[i] = FL_ERR_ROI; continue; }                                  // cv::Mat ROI throw (detection.cpp:43-44)
+    if (!(rect_inside(a, W, H) && rect_inside(b, W, H) && model_depth[i])) { st[i] = FL_ERR_ROI; continue; }
     max_pts = std::max(max_pts, std::max(a.width * a.height, b.width * b.height));
   }
   TRY(icp_reserve(h, n, max_pts));
   const int mp = h->icp.max_pts;
-  if ((size_t)W * H > h->ref_depth_cap) { cudaFree(h->d_ref_depth); TRY(dalloc(&h->d_ref_depth, (size_t)W * H)); h->ref_depth_cap = (size_t)W * H; }
-  FL_CUDA(cudaMemcpy2DAsync(h->d_ref_depth, (size_t)W * 2, ref_depth, ref_stride, (size_t)W * 2, H, cudaMemcpyHostToDevice, s));
+  const uint16_t* d_ref = nullptr;
+  TRY(icp_ref_frame(h, ref_depth, ref_stride, W, H, &d_ref));
   for (int i = 0; i < n; ++i) {
     fl_icp_hyp& hy = h->h_hyps[i];
     hy.model_depth = h->d_model_crops + (size_t)i * mp;
     hy.rect_model = rect_model[i]; hy.rect_ref = rect_ref[i]; hy.status = st[i];
-    for (int k = 0; k < 9; ++k) hy.r_match[k] = r_match9 ? r_match9[9 * i + k] : (k % 4 == 0 ? 1.f : 0.f);
-    for (int k = 0; k < 3; ++k) hy.t_match[k] = t_match3 ? t_match3[3 * i + k] : 0.f;
+    icp_fill_pose(hy, r_match9, t_match3, i);
     if (st[i] != FL_OK) continue;
     const fl_rect_t& a = rect_model[i];
     uint16_t* dst = h->h_model_crops + (size_t)i * mp;
@@ -1077,17 +1118,61 @@ extern "C" int fl_detection_batch(fl_handle* h, const uint16_t* ref_depth, size_
   }
   // one copy for all crops (the staging block is contiguous): 256 separate copies cost more than the ICP itself
   FL_CUDA(cudaMemcpyAsync(h->d_model_crops, h->h_model_crops, (size_t)n * mp * 2, cudaMemcpyHostToDevice, s));
-  FL_CUDA(cudaMemcpyAsync(h->d_hyps, h->h_hyps, sizeof(fl_icp_hyp) * (size_t)n, cudaMemcpyHostToDevice, s));
-  if (h->profile) cudaEventRecord(h->ev[0], s);
-  fl_launch_icp_prepare(h->d_ref_depth, W, H, K_ref, h->d_hyps, h->icp, h->d_t_init, s); ++h->launches;
-  fl_launch_icp_run(h->icp, prm, h->d_hyps, h->d_t_init, h->d_results, s); ++h->launches;
-  if (h->profile) cudaEventRecord(h->ev[1], s);
-  FL_CUDA(cudaMemcpyAsync(h->h_results, h->d_results, sizeof(fl_icp_result_t) * (size_t)n, cudaMemcpyDeviceToHost, s));
-  FL_CUDA(cudaStreamSynchronize(s));
-  if (h->profile) cudaEventElapsedTime(&h->icp_ms, h->ev[0], h->ev[1]);
-  FL_CUDA(cudaGetLastError());
-  memcpy(out, h->h_results, sizeof(fl_icp_result_t) * (size_t)n);
+  return icp_run_batch(h, d_ref, W, H, K_ref, n, prm, out);
+}
+
+// The rendered template depth crops of the detector's templates, uploaded ONCE (AddObj time) and packed back to back.
+extern "C" int fl_upload_model_depths(fl_handle* h, int32_t n_models, const uint16_t* const* model_depth, const size_t* model_stride,
+                                      const fl_rect_t* rect_model, int32_t W, int32_t H) {
+  if (!h || n_models < 0 || W <= 0 || H <= 0 || (n_models > 0 && (!model_depth || !model_stride || !rect_model))) return FL_ERR_ARG;
+  FL_CUDA(cudaSetDevice(h->p.device));
+  std::vector<size_t> off((size_t)n_models + 1, 0);
+  for (int i = 0; i < n_models; ++i) {
+    if (!model_depth[i] || model_stride[i] < (size_t)W * 2) return FL_ERR_ARG;
+    if (!rect_inside(rect_model[i], W, H)) { fl_set_error("model rect %d lies outside the %d x %d image", i, W, H); return FL_ERR_ROI; }
+    off[i + 1] = off[i] + (size_t)rect_model[i].width * rect_model[i].height;
+  }
+  std::vector<uint16_t> packed(std::max<size_t>(off[n_models], 1));
+  for (int i = 0; i < n_models; ++i) {
+    const fl_rect_t& a = rect_model[i];
+    for (int y = 0; y < a.height; ++y)
+      memcpy(&packed[off[i] + (size_t)y * a.width], (const uint8_t*)model_depth[i] + (size_t)(a.y + y) * model_stride[i] + (size_t)a.x * 2, (size_t)a.width * 2);
+  }
+  FL_CUDA(cudaStreamSynchronize(h->stream));                                    // an ICP batch that still reads the old set
+  cudaFree(h->d_resident); h->d_resident = nullptr;
+  TRY(dalloc(&h->d_resident, packed.size()));
+  FL_CUDA(cudaMemcpy(h->d_resident, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice));
+  h->res_off.assign(off.begin(), off.end() - 1);
+  h->res_rect.assign(rect_model, rect_model + n_models);
+  h->res_W = W; h->res_H = H;
   return FL_OK;
+}
+
+extern "C" int fl_detection_batch_resident(fl_handle* h, const uint16_t* ref_depth, size_t ref_stride, int32_t W, int32_t H, fl_intrinsics_t K_ref,
+                                           const int32_t* model_index, const fl_rect_t* rect_ref, const float* r_match9, const float* t_match3,
+                                           int32_t n, fl_icp_params_t prm, fl_icp_result_t* out) {
+  if (!h || !model_index || !rect_ref || !out || n < 0 || W <= 0 || H <= 0) return FL_ERR_ARG;
+  if (n == 0) return FL_OK;
+  if (!h->d_resident || h->res_W != W || h->res_H != H) { fl_set_error("no model depth crops uploaded for %d x %d frames (fl_upload_model_depths)", W, H); return FL_ERR_STATE; }
+  FL_CUDA(cudaSetDevice(h->p.device));
+  int max_pts = 16;
+  std::vector<int> st(n, FL_OK);
+  for (int i = 0; i < n; ++i) {
+    if (model_index[i] < 0 || (size_t)model_index[i] >= h->res_rect.size()) return FL_ERR_ARG;
+    const fl_rect_t& a = h->res_rect[model_index[i]]; const fl_rect_t& b = rect_ref[i];
+    if (!rect_inside(b, W, H)) { st[i] = FL_ERR_ROI; continue; }
+    max_pts = std::max(max_pts, std::max(a.width * a.height, b.width * b.height));
+  }
+  TRY(icp_reserve(h, n, max_pts));
+  const uint16_t* d_ref = nullptr;
+  TRY(icp_ref_frame(h, ref_depth, ref_stride, W, H, &d_ref));
+  for (int i = 0; i < n; ++i) {
+    fl_icp_hyp& hy = h->h_hyps[i];
+    hy.model_depth = h->d_resident + h->res_off[model_index[i]];
+    hy.rect_model = h->res_rect[model_index[i]]; hy.rect_ref = rect_ref[i]; hy.status = st[i];
+    icp_fill_pose(hy, r_match9, t_match3, i);
+  }
+  return icp_run_batch(h, d_ref, W, H, K_ref, n, prm, out);
 }
 
 extern "C" int fl_detection(fl_handle* h, const uint16_t* model_depth, size_t model_stride, const uint16_t* ref_depth, size_t ref_stride,

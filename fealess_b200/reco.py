@@ -5,7 +5,10 @@
                                        every rendered template depth image ``<path>/depth/<template_id>.png`` once, converted to
                                        millimetres (``convertTo(CV_16UC1, 0.1)``, :187).  The reference decodes that PNG from disk
                                        inside every ``Recognition`` call (:156-157), which would dominate once LINE-MOD + ICP take
-                                       tens of microseconds.
+                                       tens of microseconds.  On the first ``Recognition`` the images, cropped to their template
+                                       boxes, move to the device for good (``fl_upload_model_depths``); from then on a frame's ICP
+                                       sends only the hypothesis records and reads the depth frame ``match`` already uploaded
+                                       (``fl_detection_batch_resident`` with ``ref_depth == NULL``).
 * ``Recognition(rgb, depth, K)`` :86-204  ``PrepareInputData`` (:216-259: size checks, INTER_LINEAR rescale to 640 columns, intrinsics
                                        zoom), ``Detector::match`` at 75 %, then ``detection()`` (ICP, <= 10 iterations, 0.5 / 0.01 mm
                                        thresholds :52-55) on ``matches[0]`` with the template's box as model rect and the box moved to
@@ -43,6 +46,7 @@ class ObjRecoLmICP:
         self._args = (device, max_width, max_height)
         self.m_lm_detector = None
         self._model_depth: Dict[Tuple[Optional[str], int], np.ndarray] = {}
+        self._resident: Optional[Tuple[tuple, Dict[Tuple[str, int], int]]] = None     # (frame shape, crop index) once uploaded
         self.m_cam = None
 
     # ---- AddObj ----
@@ -64,12 +68,29 @@ class ObjRecoLmICP:
                 img = cv2.imread(os.path.join(str_feature_path, "depth", "%d.png" % tid), cv2.IMREAD_UNCHANGED)
                 if img is not None:
                     depths[(None, tid)] = model_depth_to_mm(img)     # the reference keys the file by template_id alone (:156)
-        self.m_lm_detector, self._model_depth = det, depths
+        self.m_lm_detector, self._model_depth, self._resident = det, depths, None
         return 0
 
     def add_detector(self, detector, model_depths_mm: Dict[Tuple[Optional[str], int], np.ndarray]) -> None:
         """Programmatic alternative to ``AddObj``: a ready detector + model depth images in mm keyed by (class_id or None, template_id)."""
-        self.m_lm_detector, self._model_depth = detector, dict(model_depths_mm)
+        self.m_lm_detector, self._model_depth, self._resident = detector, dict(model_depths_mm), None
+
+    def _upload_model_crops(self, frame_shape) -> Dict[Tuple[str, int], int]:
+        """(class_id, template_id) -> index of the template's depth crop on the device; uploaded once per detector."""
+        det, index, images, rects = self.m_lm_detector, {}, [], []
+        for cid in det.classIds():
+            for tid in range(det.numTemplates(cid)):
+                md = self._model_depth.get((cid, tid))
+                if md is None:
+                    md = self._model_depth.get((None, tid))
+                w, h, ox, oy = [int(v) for v in det.getTemplates(cid, tid)[0][:4]]
+                if md is None or md.shape != tuple(frame_shape) or ox < 0 or oy < 0 or ox + w > md.shape[1] or oy + h > md.shape[0]:
+                    continue                                          # such a hypothesis takes the per-call path (and its ROI error)
+                index[(cid, tid)] = len(images)
+                images.append(md); rects.append((ox, oy, w, h))
+        if images:
+            det._handle.upload_model_depths(images, rects)
+        return index
 
     # ---- PrepareInputData ----
     def _prepare(self, rgb, depth, K) -> Optional[Tuple[np.ndarray, np.ndarray]]:
@@ -118,9 +139,18 @@ class ObjRecoLmICP:
         if not hyps:
             return 0, []
         Kc = (float(K["fx"]), float(K["fy"]), float(K["cx"]), float(K["cy"]))   # the caller's intrinsics, as the reference passes them (:188)
-        res = det._handle.detection_batch(m_depth, Kc, [h["model_depth"] for h in hyps], [h["rect_model"] for h in hyps],
-                                          [h["rect_ref"] for h in hyps], [h["r_match"] for h in hyps], [h["t_match"] for h in hyps],
-                                          self.m_icp_it_thr, self.m_dist_mean_thr, self.m_dist_diff_thr)
+        if self._resident is None or self._resident[0] != m_depth.shape:
+            self._resident = (m_depth.shape, self._upload_model_crops(m_depth.shape))
+        crop = [self._resident[1].get((h["match"].class_id, h["match"].template_id)) for h in hyps]
+        if all(c is not None for c in crop):                          # crops resident, depth frame already on the device from match()
+            ref = None if "DepthNormal" in det.getModalities() else m_depth      # a colour-only detector never uploaded the depth frame
+            res = det._handle.detection_batch_resident(ref, Kc, crop, [h["rect_ref"] for h in hyps], [h["r_match"] for h in hyps],
+                                                       [h["t_match"] for h in hyps], self.m_icp_it_thr, self.m_dist_mean_thr,
+                                                       self.m_dist_diff_thr, frame_size=(m_depth.shape[1], m_depth.shape[0]))
+        else:
+            res = det._handle.detection_batch(m_depth, Kc, [h["model_depth"] for h in hyps], [h["rect_model"] for h in hyps],
+                                              [h["rect_ref"] for h in hyps], [h["r_match"] for h in hyps], [h["t_match"] for h in hyps],
+                                              self.m_icp_it_thr, self.m_dist_mean_thr, self.m_dist_diff_thr)
         out = []
         for hyp, r in zip(hyps, res):
             if int(r["status"]) != 0:                                 # rect outside the frame: the reference throws (detection.cpp:43-44)

@@ -191,6 +191,20 @@ int fl_detection_batch(fl_handle* h, const uint16_t* ref_depth, size_t ref_strid
                        const fl_rect_t* rect_model, const fl_rect_t* rect_ref,
                        const float* r_match9, const float* t_match3, const float* d_match, int32_t n,
                        fl_icp_params_t p, fl_icp_result_t* out);
+/* The rendered template depth images of the detector's templates, cropped to their template boxes and kept on the device.
+ * The reference decodes <path>/depth/<template_id>.png from disk inside EVERY Recognition call and converts it to mm
+ * (CadReco/obj_reco_lmicp.cpp:156-157, 187); a caller of this library decodes them once (AddObj) and hands them over here.
+ * model_depth[i] points at pixel (0,0) of the i-th W x H image (u16 mm, rows of model_stride[i] bytes); only rect_model[i]
+ * is read and stored.  Replaces any set uploaded before. */
+int fl_upload_model_depths(fl_handle* h, int32_t n_models, const uint16_t* const* model_depth, const size_t* model_stride,
+                           const fl_rect_t* rect_model, int32_t W, int32_t H);
+/* fl_detection_batch over uploaded crops: hypothesis i uses crop model_index[i] and the rect_model it was uploaded with.
+ * ref_depth == NULL takes the depth frame that the last fl_match call on this handle copied to the device (Recognition
+ * passes the same image to match and to detection, obj_reco_lmicp.cpp:101, 188): only the hypothesis records (100 B each)
+ * cross PCIe.  FL_ERR_STATE without uploaded crops / without such a frame of the same W x H. */
+int fl_detection_batch_resident(fl_handle* h, const uint16_t* ref_depth, size_t ref_stride, int32_t W, int32_t H, fl_intrinsics_t K_ref,
+                                const int32_t* model_index, const fl_rect_t* rect_ref, const float* r_match9, const float* t_match3,
+                                int32_t n, fl_icp_params_t p, fl_icp_result_t* out);
 /* single-hypothesis convenience with the reference's argument order (ICP/detection.h:9-11) */
 int fl_detection(fl_handle* h, const uint16_t* model_depth, size_t model_stride, const uint16_t* ref_depth, size_t ref_stride,
                  int32_t W, int32_t H, fl_intrinsics_t K_ref, fl_rect_t rect_model, fl_rect_t rect_ref,

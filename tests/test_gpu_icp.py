@@ -112,6 +112,42 @@ def test_cloud_api_edge_cases(h):
     assert r["iterations"] == 0 and np.array_equal(r["R"].reshape(3, 3), np.eye(3, dtype=np.float32)) and r["dist_mean"] == 0
 
 
+def test_resident_model_crops_equal_per_call_upload(h):
+    """fl_upload_model_depths + fl_detection_batch_resident (template depth crops kept on the device) must give
+    byte-identical results to fl_detection_batch, with a host reference frame and with the frame the last match left on the device."""
+    cases = [synth.make_icp_pair(seed=20 + s, max_rot_deg=r, max_shift_mm=sh, rect_wh=wh)
+             for s, (r, sh, wh) in enumerate([(3, 6, (100, 100)), (8, 10, (80, 120)), (12, 15, (64, 64)), (5, 3, (120, 90)), (2, 2, (50, 70))])]
+    ref = cases[0][1]
+    mds = [c[0] for c in cases]; rms = [c[2] for c in cases]; rrs = [c[3] for c in cases]
+    Rs = [_rt(c[4])[0] for c in cases]; ts = [_rt(c[4])[1] for c in cases]
+    want = h.detection_batch(ref, K, mds, rms, rrs, Rs, ts)
+    o = F.detection(mds[1], ref, K, rms[1], rrs[1], r_match=Rs[1], t_match=ts[1])
+    assert want[1]["iterations"] == o["iterations"] and rot_err(want[1]["R"], o["R"]) < 1e-6
+    with pytest.raises(fb.FealessError):                                                 # nothing uploaded yet
+        fb.Handle().detection_batch_resident(ref, K, [0], [rrs[0]])
+    h.upload_model_depths(mds, rms)
+    order = [3, 0, 4, 1, 2, 1]                                                           # any subset, any order, repeats
+    got = h.detection_batch_resident(ref, K, order, [rrs[i] for i in order], [Rs[i] for i in order], [ts[i] for i in order])
+    assert got.tobytes() == want[order].tobytes()
+    # the reference frame of the last host-input match is still on the device: ref_depth = NULL reads it
+    b, _ = synth.make_frame(640, 480, 0)
+    hm = fb.Handle()
+    hm.upload_templates(synth.make_templates(8, 640, 480, (5, 8), seed=1))
+    with pytest.raises(fb.FealessError):                                                 # no frame yet on this handle
+        hm.upload_model_depths(mds, rms); hm.detection_batch_resident(None, K, [0], [rrs[0]], frame_size=(640, 480))
+    rc, _ = hm.match(b, ref, 90.0)
+    assert rc == 0
+    got = hm.detection_batch_resident(None, K, order, [rrs[i] for i in order], [Rs[i] for i in order], [ts[i] for i in order], frame_size=(640, 480))
+    assert got.tobytes() == want[order].tobytes()
+    # a reference rect outside the frame is a per-hypothesis ROI error, like the per-call path (detection.cpp:43-44)
+    bad = h.detection_batch_resident(ref, K, [0, 1], [(600, 400, 100, 100), rrs[1]], [Rs[0], Rs[1]], [ts[0], ts[1]])
+    assert bad[0]["status"] == fb.FL_ERR_ROI and bad[1].tobytes() == want[1].tobytes()
+    with pytest.raises(fb.FealessError):                                                 # crop index out of range
+        h.detection_batch_resident(ref, K, [len(mds)], [rrs[0]])
+    with pytest.raises(fb.FealessError):                                                 # a model rect outside its image is refused at upload
+        h.upload_model_depths(mds[:1], [(600, 400, 100, 100)])
+
+
 def test_depth_to_3d_bit_exact(h):
     _, d = synth.make_frame(640, 480, 2)
     for Kc in (K, (525.3, 531.7, 311.2, 247.9)):
