@@ -42,7 +42,7 @@ ICP_RESULT_DTYPE = np.dtype([("R", "<f4", (9,)), ("T", "<f4", (3,)), ("dist_mean
 EXPORTED_SYMBOLS = [
     "fl_default_params", "fl_create", "fl_destroy", "fl_last_error", "fl_version", "fl_sync", "fl_stream",
     "fl_upload_templates", "fl_set_template_ids", "fl_num_templates", "fl_get_pose_info", "fl_match", "fl_match_device", "fl_match_device_async", "fl_match_wait", "fl_match_fetch",
-    "fl_match_shard_device", "fl_sort_unique_device", "fl_sort_unique_blocks_device", "fl_exchange_buffer_bytes", "fl_exchange_sort_unique_device", "fl_exchange_sort_unique_device_async", "fl_match_shard_exchange_device_async", "fl_depth_to_3d", "fl_icp_cloud_to_cloud_ex",
+    "fl_resize_linear", "fl_match_rescaled", "fl_match_shard_device", "fl_sort_unique_device", "fl_sort_unique_blocks_device", "fl_exchange_buffer_bytes", "fl_exchange_sort_unique_device", "fl_exchange_sort_unique_device_async", "fl_match_shard_exchange_device_async", "fl_depth_to_3d", "fl_icp_cloud_to_cloud_ex",
     "fl_detection_batch", "fl_upload_model_depths", "fl_detection_batch_resident", "fl_detection", "fl_nms", "fl_nms_ex", "fl_debug_keep_spread", "fl_debug_force_baseline", "fl_debug_uses_staged", "fl_debug_get", "fl_launch_count",
     "fl_profile", "fl_last_stage_ms", "fl_last_icp_ms",
 ]
@@ -205,6 +205,39 @@ class Handle:
             _check(rc, "fl_match")
         res = out[:min(cnt.value, capacity)].copy()
         return (rc, res, qbufs) if want_quantized else (rc, res)
+
+    def resize_linear(self, img: np.ndarray, W: int, H: int) -> np.ndarray:
+        """fl_resize_linear: ``cv::resize(img, Size(W, H), INTER_LINEAR)`` on the device for an 8UC3 or 16UC1 image."""
+        if img.ndim == 3 and img.shape[2] == 3:
+            src, kind, out = np.ascontiguousarray(img, np.uint8), 0, np.zeros((H, W, 3), np.uint8)
+        elif img.ndim == 2:
+            src, kind, out = np.ascontiguousarray(img, np.uint16), 1, np.zeros((H, W), np.uint16)
+        else:
+            raise ValueError("resize_linear takes H x W x 3 uint8 or H x W uint16 images")
+        _check(lib().fl_resize_linear(self._h, _p(src), C.c_size_t(src.strides[0]), src.shape[1], src.shape[0], kind, _p(out), W, H), "fl_resize_linear")
+        return out
+
+    def match_rescaled(self, bgr: Optional[np.ndarray], depth: Optional[np.ndarray], W: int, H: int, threshold: float,
+                       class_filter: Optional[Sequence[int]] = None, want_depth: bool = False, capacity: int = 1 << 16):
+        """fl_match_rescaled: upload the frame at its own size, rescale it to W x H on the device (INTER_LINEAR), match.
+        Returns (rc, matches[, rescaled depth])."""
+        ref = depth if depth is not None else bgr
+        sH, sW = ref.shape[:2]
+        bgr_c = None if bgr is None else np.ascontiguousarray(bgr, np.uint8)
+        dep_c = None if depth is None else np.ascontiguousarray(depth, np.uint16)
+        out = self._match_out.get(capacity)
+        if out is None:
+            out = self._match_out[capacity] = np.zeros(capacity, MATCH_DTYPE)
+        cnt = C.c_int32(0)
+        cf = None if not class_filter else np.ascontiguousarray(class_filter, np.int32)
+        dout = np.zeros((H, W), np.uint16) if (want_depth and dep_c is not None) else None
+        rc = lib().fl_match_rescaled(self._h, _p(bgr_c), C.c_size_t(0 if bgr_c is None else sW * 3), _p(dep_c),
+                                     C.c_size_t(0 if dep_c is None else sW * 2), sW, sH, W, H, C.c_float(threshold), _p(cf),
+                                     0 if cf is None else int(cf.size), _p(out), capacity, C.byref(cnt), _p(dout))
+        if rc not in (FL_OK, FL_ERR_SIZE, FL_ERR_GEOMETRY, FL_ERR_CAPACITY):
+            _check(rc, "fl_match_rescaled")
+        res = out[:min(cnt.value, capacity)].copy()
+        return (rc, res, dout) if want_depth else (rc, res)
 
     def match_device(self, d_bgr: int, d_depth: int, W: int, H: int, threshold: float, class_filter=None) -> None:
         """Frame already in device memory (raw device pointers, dense rows); results stay on the device."""
@@ -526,6 +559,30 @@ class Detector:
             quantized_images[:] = r[2]
         return 0, [Match(m["x"], m["y"], m["similarity"], self._class_order[m["class_idx"]], m["template_id"]) for m in recs]
 
+
+def _detector_match_rescaled(self, sources: Sequence[np.ndarray], W: int, H: int, threshold: float, want_depth: bool = False):
+    """``PrepareInputData`` + ``Detector::match`` (obj_reco_lmicp.cpp:216-259, :101): the sources keep their own size on the host and
+    are rescaled to W x H on the device.  Returns (status, matches[, rescaled depth])."""
+    if len(sources) != len(self.modalities):
+        return (-1, [], None) if want_depth else (-1, [])
+    if self._dirty:
+        self._upload()
+    bgr = depth = None
+    for m, s in zip(self.modalities, sources):
+        if m == "ColorGradient":
+            bgr = s
+        else:
+            depth = s
+    r = self._handle.match_rescaled(bgr, depth, W, H, threshold, want_depth=want_depth)
+    rc, recs = r[0], r[1]
+    if rc in (FL_ERR_GEOMETRY, FL_ERR_CAPACITY):
+        raise FealessError(rc, "Detector.match_rescaled", "geometry (W%T, H%T, W*H%16) or capacity")
+    ms = [] if rc != FL_OK else [Match(m["x"], m["y"], m["similarity"], self._class_order[m["class_idx"]], m["template_id"]) for m in recs]
+    st = 0 if rc == FL_OK else -1
+    return (st, ms, r[2]) if want_depth else (st, ms)
+
+
+Detector.match_rescaled = _detector_match_rescaled
 
 _default_handle = None
 

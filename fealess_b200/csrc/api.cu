@@ -1,10 +1,12 @@
 // C ABI of fealess_b200 (include/fealess_b200.h): handle lifecycle, device workspaces, and the orchestration of the
 // kernels in frontend.cu / similarity.cu / icp.cu on the handle's stream.  CUDA only - there is no CPU path here.
 #include "fl_internal.cuh"
+#include "resize_tables.h"
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <cmath>
 #include <new>
 #include <vector>
 
@@ -69,6 +71,9 @@ struct fl_handle {
   // last host-input fl_match left in d_in_depth (0 x 0 = none)
   uint16_t* d_resident; std::vector<size_t> res_off; std::vector<fl_rect_t> res_rect; int res_W, res_H;
   int in_depth_W, in_depth_H;
+  // input rescale: device tables of the current (source -> destination) geometry, source-frame staging
+  fl_resize_tables rz; int rz_sW, rz_sH, rz_dW, rz_dH;
+  uint8_t* d_src_bgr; uint16_t* d_src_depth; size_t src_cap;
 };
 
 template <typename T> static int dalloc(T** p, size_t n) {
@@ -131,6 +136,8 @@ extern "C" int fl_create(const fl_params_t* params, fl_handle** out) {
   h->d_hyps = nullptr; h->d_t_init = nullptr; h->d_results = nullptr; h->d_model_crops = nullptr; h->d_ref_depth = nullptr; h->ref_depth_cap = 0;
   h->h_model_crops = nullptr; h->h_hyps = nullptr; h->h_results = nullptr; h->h_crop_cap = 0;
   h->d_resident = nullptr; h->res_W = h->res_H = 0; h->in_depth_W = h->in_depth_H = 0;
+  memset(&h->rz, 0, sizeof h->rz); h->rz_sW = h->rz_sH = h->rz_dW = h->rz_dH = 0;
+  h->d_src_bgr = nullptr; h->d_src_depth = nullptr; h->src_cap = 0;
   memset(h->d_bgr, 0, sizeof h->d_bgr); memset(h->d_q, 0, sizeof h->d_q); memset(h->d_qm, 0, sizeof h->d_qm);
   memset(h->d_mask, 0, sizeof h->d_mask); memset(h->d_spread, 0, sizeof h->d_spread); memset(h->d_lm, 0, sizeof h->d_lm);
   memset(h->used_mask, 0, sizeof h->used_mask); memset(h->stage_ms, 0, sizeof h->stage_ms); h->icp_ms = 0.f;
@@ -199,6 +206,8 @@ extern "C" int fl_destroy(fl_handle* h) {
   cudaStreamSynchronize(h->stream);
   free_templates(h); icp_free(h);
   cudaFree(h->d_ref_depth); cudaFree(h->d_resident);
+  cudaFree(h->rz.xofs); cudaFree(h->rz.yofs); cudaFree(h->rz.ialpha); cudaFree(h->rz.ibeta); cudaFree(h->rz.alpha); cudaFree(h->rz.beta);
+  cudaFree(h->d_src_bgr); cudaFree(h->d_src_depth);
   cudaFree(h->d_in_bgr); cudaFree(h->d_in_depth); cudaFree(h->d_geom);
   for (int l = 0; l < FL_MAX_LEVELS; ++l) {
     cudaFree(h->d_bgr[l]); cudaFree(h->d_lm[l]);
@@ -993,6 +1002,89 @@ extern "C" int fl_debug_get(fl_handle* h, int what, int32_t a, int32_t b, int32_
     return h->plan.n_cta;
   }
   return FL_ERR_ARG;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// input rescale: cv::resize INTER_LINEAR tables (OpenCV imgproc/src/resize.cpp, the loops that fill xofs / alpha / yofs / beta)
+// ---------------------------------------------------------------------------------------------------
+static int resize_tables(fl_handle* h, int sW, int sH, int dW, int dH) {
+  if (h->rz.xofs && h->rz_sW == sW && h->rz_sH == sH && h->rz_dW == dW && h->rz_dH == dH) return FL_OK;
+  FL_CUDA(cudaStreamSynchronize(h->stream));
+  cudaFree(h->rz.xofs); cudaFree(h->rz.yofs); cudaFree(h->rz.ialpha); cudaFree(h->rz.ibeta); cudaFree(h->rz.alpha); cudaFree(h->rz.beta);
+  memset(&h->rz, 0, sizeof h->rz);
+  std::vector<int> xo, yo; std::vector<float> xa, yb;
+  std::vector<short> ia, ib;
+  fl_resize_axis(sW, dW, true, xo, xa, ia); fl_resize_axis(sH, dH, false, yo, yb, ib);
+  TRY(dalloc(&h->rz.xofs, (size_t)dW)); TRY(dalloc(&h->rz.yofs, (size_t)dH));
+  TRY(dalloc(&h->rz.ialpha, (size_t)dW)); TRY(dalloc(&h->rz.ibeta, (size_t)dH)); TRY(dalloc(&h->rz.alpha, (size_t)dW)); TRY(dalloc(&h->rz.beta, (size_t)dH));
+  FL_CUDA(cudaMemcpy(h->rz.xofs, xo.data(), (size_t)dW * 4, cudaMemcpyHostToDevice)); FL_CUDA(cudaMemcpy(h->rz.yofs, yo.data(), (size_t)dH * 4, cudaMemcpyHostToDevice));
+  FL_CUDA(cudaMemcpy(h->rz.ialpha, ia.data(), (size_t)dW * 4, cudaMemcpyHostToDevice)); FL_CUDA(cudaMemcpy(h->rz.ibeta, ib.data(), (size_t)dH * 4, cudaMemcpyHostToDevice));
+  FL_CUDA(cudaMemcpy(h->rz.alpha, xa.data(), (size_t)dW * 8, cudaMemcpyHostToDevice)); FL_CUDA(cudaMemcpy(h->rz.beta, yb.data(), (size_t)dH * 8, cudaMemcpyHostToDevice));
+  h->rz_sW = sW; h->rz_sH = sH; h->rz_dW = dW; h->rz_dH = dH;
+  return FL_OK;
+}
+static int resize_staging(fl_handle* h, size_t npx) {
+  if (npx <= h->src_cap) return FL_OK;
+  FL_CUDA(cudaStreamSynchronize(h->stream));
+  cudaFree(h->d_src_bgr); cudaFree(h->d_src_depth); h->d_src_bgr = nullptr; h->d_src_depth = nullptr; h->src_cap = 0;
+  TRY(dalloc(&h->d_src_bgr, npx * 3)); TRY(dalloc(&h->d_src_depth, npx));
+  h->src_cap = npx;
+  return FL_OK;
+}
+
+extern "C" int fl_resize_linear(fl_handle* h, const void* src, size_t src_stride, int32_t sW, int32_t sH, int32_t type, void* dst, int32_t W, int32_t H) {
+  if (!h || !src || !dst || sW <= 0 || sH <= 0 || W <= 0 || H <= 0 || (type != FL_IMG_8UC3 && type != FL_IMG_16UC1)) return FL_ERR_ARG;
+  const size_t px = type == FL_IMG_8UC3 ? 3 : 2;
+  if (src_stride < (size_t)sW * px) return FL_ERR_ARG;
+  FL_CUDA(cudaSetDevice(h->p.device));
+  cudaStream_t s = h->stream;
+  TRY(resize_tables(h, sW, sH, W, H));
+  TRY(resize_staging(h, (size_t)sW * sH));
+  void* d_src = type == FL_IMG_8UC3 ? (void*)h->d_src_bgr : (void*)h->d_src_depth;
+  void* d_dst = nullptr;
+  FL_CUDA(cudaMalloc(&d_dst, (size_t)W * H * px));
+  FL_CUDA(cudaMemcpy2DAsync(d_src, (size_t)sW * px, src, src_stride, (size_t)sW * px, sH, cudaMemcpyHostToDevice, s));
+  fl_launch_resize_linear(d_src, sW, sH, type, d_dst, W, H, h->rz, s); ++h->launches;
+  cudaError_t e = cudaMemcpyAsync(dst, d_dst, (size_t)W * H * px, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFree(d_dst);
+  FL_CUDA(e);
+  FL_CUDA(cudaGetLastError());
+  return FL_OK;
+}
+
+extern "C" int fl_match_rescaled(fl_handle* h, const uint8_t* bgr, size_t bgr_stride, const uint16_t* depth, size_t depth_stride, int32_t sW, int32_t sH,
+                                 int32_t W, int32_t H, float threshold, const int32_t* class_filter, int32_t n_filter, fl_match_t* out, int32_t capacity,
+                                 int32_t* count, uint16_t* rescaled_depth_out) {
+  if (!h || !count || sW <= 0 || sH <= 0) return FL_ERR_ARG;
+  *count = 0;
+  const fl_params_t& p = h->p;
+  if (W <= 0 || H <= 0 || W > p.max_width || H > p.max_height) return FL_ERR_SIZE;
+  if (sW == W && sH == H) {                                                      // TImage2Mat resizes only when the width differs (:42)
+    int rc = fl_match(h, bgr, bgr_stride, depth, depth_stride, W, H, nullptr, threshold, class_filter, n_filter, out, capacity, count, nullptr);
+    if (rescaled_depth_out && depth) for (int y = 0; y < H; ++y) memcpy(rescaled_depth_out + (size_t)y * W, (const uint8_t*)depth + (size_t)y * depth_stride, (size_t)W * 2);
+    return rc;
+  }
+  if ((bgr && bgr_stride < (size_t)sW * 3) || (depth && depth_stride < (size_t)sW * 2)) return FL_ERR_SIZE;
+  FL_CUDA(cudaSetDevice(p.device));
+  cudaStream_t s = h->stream;
+  TRY(resize_tables(h, sW, sH, W, H));
+  TRY(resize_staging(h, (size_t)sW * sH));
+  const uint8_t* d_bgr = nullptr; const uint16_t* d_depth = nullptr;
+  if (depth) {
+    FL_CUDA(cudaMemcpy2DAsync(h->d_src_depth, (size_t)sW * 2, depth, depth_stride, (size_t)sW * 2, sH, cudaMemcpyHostToDevice, s));
+    fl_launch_resize_linear(h->d_src_depth, sW, sH, FL_IMG_16UC1, h->d_in_depth, W, H, h->rz, s); ++h->launches;
+    d_depth = h->d_in_depth; h->in_depth_W = W; h->in_depth_H = H;
+    if (rescaled_depth_out) FL_CUDA(cudaMemcpyAsync(rescaled_depth_out, h->d_in_depth, (size_t)W * H * 2, cudaMemcpyDeviceToHost, s));
+  }
+  if (bgr) {
+    FL_CUDA(cudaMemcpy2DAsync(h->d_src_bgr, (size_t)sW * 3, bgr, bgr_stride, (size_t)sW * 3, sH, cudaMemcpyHostToDevice, s));
+    fl_launch_resize_linear(h->d_src_bgr, sW, sH, FL_IMG_8UC3, h->d_in_bgr, W, H, h->rz, s); ++h->launches;
+    d_bgr = h->d_in_bgr;
+  }
+  int rc = fl_match_device(h, d_bgr, d_depth, W, H, nullptr, threshold, class_filter, n_filter);
+  if (rc != FL_OK) return rc;
+  return fl_match_fetch(h, out, capacity, count);
 }
 
 // ---------------------------------------------------------------------------------------------------

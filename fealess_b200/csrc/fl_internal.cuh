@@ -205,6 +205,13 @@ struct fl_icp_ws {                  // per-batch workspace, all device pointers
 };
 #define FL_ICP_GRID 64
 #define FL_ICP_CELLS (FL_ICP_GRID * FL_ICP_GRID)
+// cv::resize INTER_LINEAR (resize.cu): device tables built by the host for one (source size -> destination size) pair
+struct fl_resize_tables {
+  int* xofs; int* yofs;             // [dW], [dH] source index of the left / upper tap (rows unclipped: the kernel clips)
+  short2* ialpha; short2* ibeta;    // 8U: 11-bit fixed-point weight pairs
+  float2* alpha; float2* beta;      // 16U: float weight pairs
+};
+void fl_launch_resize_linear(const void* src, int sW, int sH, int type, void* dst, int dW, int dH, const fl_resize_tables& t, cudaStream_t s);
 void fl_launch_depth_to_3d(const uint16_t* depth, int W, int H, fl_intrinsics_t K, float* out3, cudaStream_t s);
 void fl_launch_icp_prepare(const uint16_t* ref_depth, int W, int H, fl_intrinsics_t K_ref, const fl_icp_hyp* hyps,
                            fl_icp_ws ws, float* t_init_out, cudaStream_t s);

@@ -48,6 +48,7 @@ class ObjRecoLmICP:
         self._model_depth: Dict[Tuple[Optional[str], int], np.ndarray] = {}
         self._resident: Optional[Tuple[tuple, Dict[Tuple[str, int], int]]] = None     # (frame shape, crop index) once uploaded
         self.m_cam = None
+        self.last_icp_path = None                                    # "resident" / "per-call": which ICP entry the last Recognition took
 
     # ---- AddObj ----
     def AddObj(self, str_feature_path: str) -> int:
@@ -94,7 +95,6 @@ class ObjRecoLmICP:
 
     # ---- PrepareInputData ----
     def _prepare(self, rgb, depth, K) -> Optional[Tuple[np.ndarray, np.ndarray]]:
-        import cv2
         if rgb is None or depth is None or rgb.ndim != 3 or depth.ndim != 2 or rgb.shape[0] <= 0 or rgb.shape[1] <= 0:
             return None
         if rgb.shape[:2] != depth.shape[:2] or int(K["width"]) != rgb.shape[1] or int(K["height"]) != rgb.shape[0]:
@@ -102,9 +102,8 @@ class ObjRecoLmICP:
         zoom = np.float32(PROC_IMG_WIDTH * 1.0 / rgb.shape[1])
         w, h = PROC_IMG_WIDTH, rgb.shape[0] * PROC_IMG_WIDTH // rgb.shape[1]
         self.m_cam = dict(fx=K["fx"] * zoom, fy=K["fy"] * zoom, cx=K["cx"] * zoom, cy=K["cy"] * zoom, width=w, height=h)   # :238-246
-        if rgb.shape[1] != w:                                        # TImage2Mat(..., true): interpolation flag 1 = INTER_LINEAR (:42)
-            rgb = cv2.resize(rgb, (w, h), interpolation=cv2.INTER_LINEAR)
-            depth = cv2.resize(depth, (w, h), interpolation=cv2.INTER_LINEAR)
+        # TImage2Mat(..., true) rescales with INTER_LINEAR when the width differs (:42); that happens on the DEVICE inside
+        # Detector.match_rescaled (fl_match_rescaled), so the frame crosses PCIe once at its own size and is never resized on the host
         return np.ascontiguousarray(rgb, np.uint8), np.ascontiguousarray(depth, np.uint16)
 
     # ---- Recognition ----
@@ -118,7 +117,13 @@ class ObjRecoLmICP:
             return ERROR_INVALID_PARAM, []
         m_rgb, m_depth = prep
         det = self.m_lm_detector
-        rc, matches = det.match([m_rgb, m_depth], self.m_matching_threshold)
+        fw, fh = self.m_cam["width"], self.m_cam["height"]          # processing size (640 columns)
+        rescaled = m_rgb.shape[1] != fw
+        if rescaled:
+            by_name = {"ColorGradient": m_rgb, "DepthNormal": m_depth}
+            rc, matches = det.match_rescaled([by_name[m] for m in det.getModalities()], fw, fh, self.m_matching_threshold)
+        else:
+            rc, matches = det.match([m_rgb, m_depth], self.m_matching_threshold)
         if rc != 0:
             return ERROR_INVALID_PARAM, []
         if not matches:
@@ -139,17 +144,23 @@ class ObjRecoLmICP:
         if not hyps:
             return 0, []
         Kc = (float(K["fx"]), float(K["fy"]), float(K["cx"]), float(K["cy"]))   # the caller's intrinsics, as the reference passes them (:188)
-        if self._resident is None or self._resident[0] != m_depth.shape:
-            self._resident = (m_depth.shape, self._upload_model_crops(m_depth.shape))
-        crop = [self._resident[1].get((h["match"].class_id, h["match"].template_id)) for h in hyps]
+        if self._resident is None or self._resident[0] != (fh, fw):
+            self._resident = ((fh, fw), self._upload_model_crops((fh, fw)))
+        crop = [self._resident[1].get((hy["match"].class_id, hy["match"].template_id)) for hy in hyps]
         if all(c is not None for c in crop):                          # crops resident, depth frame already on the device from match()
-            ref = None if "DepthNormal" in det.getModalities() else m_depth      # a colour-only detector never uploaded the depth frame
-            res = det._handle.detection_batch_resident(ref, Kc, crop, [h["rect_ref"] for h in hyps], [h["r_match"] for h in hyps],
-                                                       [h["t_match"] for h in hyps], self.m_icp_it_thr, self.m_dist_mean_thr,
-                                                       self.m_dist_diff_thr, frame_size=(m_depth.shape[1], m_depth.shape[0]))
+            ref = None                                                # the (rescaled) depth frame match() left on the device
+            if "DepthNormal" not in det.getModalities():              # a colour-only detector never uploaded the depth frame
+                ref = det._handle.resize_linear(m_depth, fw, fh) if rescaled else m_depth
+            self.last_icp_path = "resident"
+            res = det._handle.detection_batch_resident(ref, Kc, crop, [hy["rect_ref"] for hy in hyps], [hy["r_match"] for hy in hyps],
+                                                       [hy["t_match"] for hy in hyps], self.m_icp_it_thr, self.m_dist_mean_thr,
+                                                       self.m_dist_diff_thr, frame_size=(fw, fh))
         else:
-            res = det._handle.detection_batch(m_depth, Kc, [h["model_depth"] for h in hyps], [h["rect_model"] for h in hyps],
-                                              [h["rect_ref"] for h in hyps], [h["r_match"] for h in hyps], [h["t_match"] for h in hyps],
+            if rescaled:
+                m_depth = det._handle.resize_linear(m_depth, fw, fh)
+            self.last_icp_path = "per-call"
+            res = det._handle.detection_batch(m_depth, Kc, [hy["model_depth"] for hy in hyps], [hy["rect_model"] for hy in hyps],
+                                              [hy["rect_ref"] for hy in hyps], [hy["r_match"] for hy in hyps], [hy["t_match"] for hy in hyps],
                                               self.m_icp_it_thr, self.m_dist_mean_thr, self.m_dist_diff_thr)
         out = []
         for hyp, r in zip(hyps, res):

@@ -177,6 +177,21 @@ int fl_match_shard_exchange_device_async(fl_handle* h, const void* d_bgr, const 
 int fl_exchange_sort_unique_device_async(fl_handle* h, int32_t rank, int32_t world, void* const* peer_buffers, int32_t capacity,
                                          const fl_match_t* d_local_block, uint32_t epoch);
 
+/* ---- input rescale (the caller's PrepareInputData) ------------------------------------------------- */
+enum { FL_IMG_8UC3 = 0, FL_IMG_16UC1 = 1 };
+/* cv::resize(src, dst, Size(W, H), 0, 0, INTER_LINEAR) on the device for the two image formats of
+ * CObjRecoLmICP::PrepareInputData (CadReco/obj_reco_lmicp.cpp:38-45, 255-256: TImage2Mat(..., INTER_LINEAR)); host in,
+ * host out (dst dense, W*H pixels).  OpenCV's own arithmetic (imgproc/src/resize.cpp; 8U fixed point, 16U float, 2x = area). */
+int fl_resize_linear(fl_handle* h, const void* src, size_t src_stride, int32_t src_W, int32_t src_H, int32_t type,
+                     void* dst, int32_t W, int32_t H);
+/* PrepareInputData + Detector::match in one call: the src_W x src_H frame is uploaded, rescaled ON THE DEVICE to W x H
+ * (W, H within fl_params_t.max_*) and matched; the rescaled depth frame stays on the device for
+ * fl_detection_batch_resident(ref_depth = NULL).  Equal sizes: plain fl_match.  rescaled_depth_out (nullable): W*H u16, the
+ * frame detection() would receive (m_depth). */
+int fl_match_rescaled(fl_handle* h, const uint8_t* bgr, size_t bgr_stride, const uint16_t* depth, size_t depth_stride,
+                      int32_t src_W, int32_t src_H, int32_t W, int32_t H, float threshold, const int32_t* class_filter, int32_t n_filter,
+                      fl_match_t* out, int32_t capacity, int32_t* count, uint16_t* rescaled_depth_out);
+
 /* ---- ICP ------------------------------------------------------------------------------------------ */
 /* cup_d2pc::depthTo3d for 16UC1 input: out3 = H*W*3 floats in METRES, 0 depth -> NaN (depth_to_3d.cpp:99-137, 244-260) */
 int fl_depth_to_3d(fl_handle* h, const uint16_t* depth, size_t depth_stride, int32_t W, int32_t H,

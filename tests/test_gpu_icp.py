@@ -201,7 +201,7 @@ def test_recognition_mirror_end_to_end(tmp_path):
     assert r.AddObj(str(tmp_path)) == 0
     K = dict(fx=608.0, fy=608.0, cx=320.0, cy=240.0, width=W, height=H)
     rc, res = r.Recognition(b, d, K)
-    assert rc == 0 and len(res) == 1
+    assert rc == 0 and len(res) == 1 and r.last_icp_path == "resident"      # template depth crops on the device, frame from match()
     top = want[0]
     assert res[0]["strObjTag"] == "obj%02d" % top["class_idx"] and res[0]["template_id"] == top["template_id"]
     hdr, _ = ts.template(int(top["template_id"]), 0, 0)
