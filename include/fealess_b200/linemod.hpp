@@ -174,6 +174,28 @@ class Detector {
     return 0;
   }
 
+  // Mirror-only: PrepareInputData's INTER_LINEAR rescale (CadReco/obj_reco_lmicp.cpp:38-45, 255-256) + match() in one device pass
+  // (fl_match_rescaled): the src_W x src_H frame is uploaded as it is, rescaled to W x H on the GPU and matched; the rescaled depth
+  // frame stays on the device for fl_detection_batch_resident.  Same return values as match(); colour + depth modalities only.
+  int matchRescaled(const uint8_t* bgr, size_t bgr_step, const uint16_t* depth, size_t depth_step, int src_W, int src_H, int W, int H,
+                    float threshold, std::vector<Match>& matches) const {
+    matches.clear();
+    bool has_color = false, has_depth = false;
+    for (size_t m = 0; m < modalities.size(); ++m) (modalities[m]->kind() == FL_MODALITY_COLOR_GRADIENT ? has_color : has_depth) = true;
+    if ((has_color && !bgr) || (has_depth && !depth)) return -1;
+    ensure_uploaded(W, H);
+    std::vector<fl_match_t> out(4096);
+    int32_t count = 0;
+    int rc = fl_match_rescaled(handle_, has_color ? bgr : nullptr, bgr_step, has_depth ? depth : nullptr, depth_step, src_W, src_H, W, H, threshold,
+                               nullptr, 0, out.data(), (int32_t)out.size(), &count, nullptr);
+    if (rc == FL_ERR_CAPACITY && count > (int32_t)out.size()) { out.resize((size_t)count); rc = fl_match_fetch(handle_, out.data(), (int32_t)out.size(), &count); }
+    if (rc == FL_ERR_SIZE) return -1;
+    fealess_b200::check_status(rc, "Detector::matchRescaled");
+    matches.reserve((size_t)count);
+    for (int i = 0; i < count; ++i) matches.push_back(Match(out[i].x, out[i].y, out[i].similarity, class_names_[out[i].class_idx], out[i].template_id));
+    return 0;
+  }
+
   // Detector::addSyntheticTemplate (linemod.cpp:1636-1642): templates = one TemplatePyramid, (L0 M0, L0 M1, L1 M0, ...)
   int addSyntheticTemplate(const std::vector<Template>& templates, const String& class_id) {
     std::vector<TemplatePyramid>& tp = class_templates[class_id];

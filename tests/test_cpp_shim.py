@@ -40,7 +40,7 @@ def test_cpp_mirror_compiles_and_links():
 
 def test_cpp_headers_are_self_contained():
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    for hdr in ("fealess_b200/linemod.hpp", "fealess_b200/linemod_io.hpp", "fealess_b200_compat/linemod_if.h", "fealess_b200/icp.hpp", "fealess_b200/cv_min.hpp", "fealess_b200.h"):
+    for hdr in ("fealess_b200/linemod.hpp", "fealess_b200/linemod_io.hpp", "fealess_b200/obj_reco.hpp", "fealess_b200/png16.hpp", "fealess_b200_compat/linemod_if.h", "fealess_b200/icp.hpp", "fealess_b200/cv_min.hpp", "fealess_b200.h"):
         r = subprocess.run([cxx, "-std=c++11", "-fsyntax-only", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"), "-x", "c++", "-include", hdr, os.devnull],
                            capture_output=True, text=True)
         assert r.returncode == 0, hdr + "\n" + r.stderr
