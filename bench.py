@@ -392,9 +392,67 @@ def run_ours(args):
     line.update(extra)
     if icp:
         line["icp"] = icp
+    if world == 1 and not args.no_icp:
+        try:                                                    # a side measurement: it must never cost the headline line
+            line["recognition"] = bench_recognition(synth, frames, q, cpu=not args.no_cpu)
+        except Exception as e:  # noqa: BLE001
+            line["recognition"] = {"error": "%s: %s" % (type(e).__name__, e)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_recognition(synth, frames, q, cpu: bool = True, n_templates: int = 2000, top_k: int = 5, n_timed: int = 100):
+    """C1 (BASELINE configs[0]): the reference's whole ``Recognition`` call - PrepareInputData, match at 75 %, ICP of the top-5
+    hypotheses - on a 640x480 frame with 1 object x 2,000 templates, through the product API mirror (fealess_b200.reco), host
+    buffers in, poses out.  The templates are planted on frame 0, so frame 0 is the frame every timed call processes (each call
+    runs match + 5 ICPs); the 1280x960 variant sends the pixel-doubled frame and rescales it on the device."""
+    import fealess_b200 as fb
+    from fealess_b200 import reco
+    b, d = frames[0]
+    tset = synth.make_templates(n_templates, W, H, T, n_classes=1, seed=7, quantized=q, planted_fraction=0.01)
+    det = fb.Detector()
+    det.add_template_set(tset)
+    r = reco.ObjRecoLmICP()
+    r.add_detector(det, {(None, tid): d for tid in range(n_templates)})       # synthetic rendered depth: the frame's own depth for every template
+    K = dict(fx=608.0, fy=608.0, cx=320.0, cy=240.0, width=W, height=H)
+    big_b, big_d = np.repeat(np.repeat(b, 2, 0), 2, 1), np.repeat(np.repeat(d, 2, 0), 2, 1)
+    Kbig = dict(K, width=2 * W, height=2 * H)
+    out = {}
+    for tag, (fb_, fd_, Kd) in (("", (b, d, K)), ("_1280x960_input", (big_b, big_d, Kbig))):
+        for _ in range(5):
+            rc, res = r.Recognition(fb_, fd_, Kd, top_k=top_k)
+        if rc != 0 or not res:
+            raise RuntimeError("Recognition benchmark frame produced no pose (rc %d)" % rc)
+        t0 = time.perf_counter()
+        for _ in range(n_timed):
+            rc, res = r.Recognition(fb_, fd_, Kd, top_k=top_k)
+        dt = (time.perf_counter() - t0) / n_timed
+        out["frames_per_s" + tag] = 1.0 / dt
+        out["ms_per_frame" + tag] = 1e3 * dt
+        out["poses_per_frame" + tag] = len(res)
+    out.update({"workload": "C1: Recognition (match at 75 %% + ICP of the top-%d matches) on one 640x480 RGB-D frame, 1 object x %d templates, L=2, T={5,8}" % (top_k, n_templates),
+                "icp_path": r.last_icp_path,
+                "timer": "host wall clock around ObjRecoLmICP.Recognition (H2D of the frame, 3 match launches, 2 ICP launches, poses back), mean of %d calls" % n_timed})
+    if cpu:                                                    # the C restatement of the same call, one thread, 3 frames
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import fl_oracle_py as F
+        odet = F.Detector(T)
+        odet.set_templates(tset)
+        Kc = (608.0, 608.0, 320.0, 240.0)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            odet.process(b, d)
+            ms = odet.match(THRESHOLD)
+            for m in ms[:top_k]:
+                hdr, _f = tset.template(int(m["template_id"]), 0, 0)
+                P = tset.pose13[int(m["template_id"])][:12].reshape(3, 4)
+                F.detection(d, d, Kc, (int(hdr[2]), int(hdr[3]), int(hdr[0]), int(hdr[1])), (int(m["x"]), int(m["y"]), int(hdr[0]), int(hdr[1])),
+                            r_match=P[:, :3], t_match=P[:, 3])
+        ct = (time.perf_counter() - t0) / 3
+        out["cpu_baseline"] = {"frames_per_s": 1.0 / ct, "cores": 1, "kind": "port",
+                               "sample": "3 whole frames: front end + matchClass over %d templates + %d ICPs each" % (n_templates, min(top_k, len(ms)))}
+    return out
 
 
 def make_icp_workload(synth, n_hyp: int = 256, crop: int = 104):
