@@ -31,6 +31,15 @@ def test_device_resize_bit_exact(sw, sh, dw, dh):
     assert np.array_equal(h.resize_linear(wide[:, :sw], dw, dh), R.resize_linear(a, dw, dh))
 
 
+def test_device_resize_equals_committed_golden(golden_dir):
+    """The fixtures cv2.resize (IPP off) produced when oracle/make_golden.py ran (tests/golden/resize_small.npz)."""
+    z = np.load(os.path.join(golden_dir, "resize_small.npz"))
+    h = fb.Handle()
+    for i, (sw, sh, dw, dh) in enumerate(z["sizes"]):
+        assert np.array_equal(h.resize_linear(z["bgr_%d" % i], int(dw), int(dh)), z["bgr_out_%d" % i])
+        assert np.array_equal(h.resize_linear(z["depth_%d" % i], int(dw), int(dh)), z["depth_out_%d" % i])
+
+
 @pytest.mark.parametrize("sw,sh", [(1024, 768), (1280, 960), (320, 240)])
 def test_match_rescaled_equals_match_of_rescaled_frame(sw, sh):
     """fl_match_rescaled(frame at its own size) == fl_match(oracle-rescaled frame) == the CPU oracle's match list; the rescaled depth

@@ -41,3 +41,12 @@ def test_depth_like_input_and_identity():
         assert np.array_equal(R.resize_linear(d, 640, 480), d)
     finally:
         cv2.ipp.setUseIPP(True)
+
+
+def test_oracle_equals_committed_golden(golden_dir):
+    """tests/golden/resize_small.npz (written by oracle/make_golden.py from cv2.resize with IPP off) - no cv2 needed to check."""
+    z = np.load(os.path.join(golden_dir, "resize_small.npz"))
+    for i, (sw, sh, dw, dh) in enumerate(z["sizes"]):
+        assert z["bgr_%d" % i].shape == (sh, sw, 3)
+        assert np.array_equal(R.resize_linear(z["bgr_%d" % i], int(dw), int(dh)), z["bgr_out_%d" % i])
+        assert np.array_equal(R.resize_linear(z["depth_%d" % i], int(dw), int(dh)), z["depth_out_%d" % i])
