@@ -163,3 +163,47 @@ class ShardedMatcher:
 
     def fetch(self) -> np.ndarray:
         return self.h.match_fetch()
+
+
+# ---------------------------------------------------------------------------------------------------
+# Hypothesis-sharded pose refinement ("ICP hypotheses are dealt across GPUs; small all-gather of the refined
+# poses before NMS").  After the candidate exchange every rank holds the SAME sorted match list, so hypothesis k of the top-K
+# goes to rank k % world without any negotiation; each rank refines its share in one batched ICP launch
+# (Handle.detection_batch_resident / detection_batch), one all-gather of fixed-size result blocks brings all poses to every
+# rank, and every rank runs the reference's nonMaximumSuppression (ICP/NMS.cpp:6-39) redundantly on the complete list - in
+# the ORIGINAL hypothesis order, which is what makes the greedy result independent of the number of GPUs.
+# ---------------------------------------------------------------------------------------------------
+def hypothesis_share(n_hyp: int, rank: int, world: int) -> np.ndarray:
+    """Indices (into the sorted hypothesis list) refined by ``rank``: k with k % world == rank."""
+    return np.arange(rank, n_hyp, world, dtype=np.int64)
+
+
+def refine_sharded(n_hyp: int, refine_fn, rank: int, world: int, group=None, device=None) -> np.ndarray:
+    """Refines ``n_hyp`` hypotheses across ``world`` ranks.  ``refine_fn(indices) -> ICP_RESULT_DTYPE[len(indices)]`` runs this rank's
+    batched ICP for the given hypothesis indices (it is not called with an empty share).  Returns all ``n_hyp`` records in
+    hypothesis order on every rank.  One collective (all-gather of ``ceil(n_hyp / world)`` records per rank)."""
+    import torch
+    import torch.distributed as dist
+    from . import ICP_RESULT_DTYPE
+    mine = hypothesis_share(n_hyp, rank, world)
+    res = refine_fn(mine) if len(mine) else np.zeros(0, ICP_RESULT_DTYPE)
+    res = np.ascontiguousarray(res, dtype=ICP_RESULT_DTYPE)
+    if len(res) != len(mine):
+        raise ValueError("refine_fn returned %d records for %d hypotheses" % (len(res), len(mine)))
+    if world == 1 or not dist.is_initialized():
+        return res
+    per_rank = (n_hyp + world - 1) // world
+    nbytes = per_rank * ICP_RESULT_DTYPE.itemsize
+    if device is None:
+        device = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    block = torch.zeros(nbytes, dtype=torch.uint8)
+    block[: res.nbytes] = torch.from_numpy(res.view(np.uint8).reshape(-1).copy())
+    block = block.to(device)
+    out = torch.empty(world * nbytes, dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(out, block, group=group)
+    blocks = out.cpu().numpy().reshape(world, nbytes)
+    merged = np.zeros(n_hyp, ICP_RESULT_DTYPE)
+    for r in range(world):
+        idx = hypothesis_share(n_hyp, r, world)
+        merged[idx] = blocks[r, : len(idx) * ICP_RESULT_DTYPE.itemsize].copy().view(ICP_RESULT_DTYPE)
+    return merged

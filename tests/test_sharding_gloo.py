@@ -91,3 +91,53 @@ def test_shard_assignment_is_a_partition():
     h, f = sh.template(2, 1, 0)
     h0, f0 = ts.template(7, 1, 0)
     assert np.array_equal(f, f0) and list(h[:5]) == list(h0[:5])
+
+
+def _fake_refine(indices):
+    """A stand-in for the batched ICP launch: a record that depends only on the hypothesis index."""
+    from fealess_b200 import ICP_RESULT_DTYPE
+    out = np.zeros(len(indices), ICP_RESULT_DTYPE)
+    for j, k in enumerate(indices):
+        out["R"][j] = np.arange(9, dtype=np.float32) + 10 * k
+        out["T"][j] = (k, 2 * k, (k * 37) % 11)
+        out["dist_mean"][j] = 0.25 + (k * 7) % 5
+        out["iterations"][j] = k % 10
+        out["n_points"][j] = 1000 + (k * 131) % 400
+    return out
+
+
+def _refine_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        for n_hyp in (0, 1, 2, 5, 16):
+            calls = []
+
+            def fn(idx):
+                calls.append(list(idx))
+                return _fake_refine(idx)
+            merged = sharded.refine_sharded(n_hyp, fn, rank, world)
+            assert calls == ([list(range(rank, n_hyp, world))] if len(range(rank, n_hyp, world)) else [])   # empty shares launch nothing
+            np.save(os.path.join(out_dir, "refined_%d_%d.npy" % (n_hyp, rank)), merged)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_hypothesis_sharded_refinement_equals_single_process(tmp_path):
+    """Top-K hypotheses dealt k % world, ONE all-gather of the pose records, every rank ends with the complete list in hypothesis
+    order (the order nonMaximumSuppression depends on)."""
+    import fl_oracle_py as Fo
+    world = 2
+    mp.spawn(_refine_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for n_hyp in (0, 1, 2, 5, 16):
+        want = sharded.refine_sharded(n_hyp, _fake_refine, 0, 1)                          # world of one: no collective
+        assert len(want) == n_hyp
+        for rank in range(world):
+            got = np.load(tmp_path / ("refined_%d_%d.npy" % (n_hyp, rank)))
+            assert got.tobytes() == want.tobytes()
+    # the greedy NMS over the gathered list (hypothesis order) is therefore the same on every rank and for every world size
+    full = _fake_refine(np.arange(16))
+    a = Fo.nms(full["T"], full["n_points"].astype(np.int32), full["dist_mean"], 12.0)
+    b = Fo.nms(np.load(tmp_path / "refined_16_1.npy")["T"], full["n_points"].astype(np.int32), full["dist_mean"], 12.0)
+    assert np.array_equal(a, b) and 0 < len(a) < 16
+    assert [list(sharded.hypothesis_share(5, r, 2)) for r in range(2)] == [[0, 2, 4], [1, 3]]
