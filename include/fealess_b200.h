@@ -187,7 +187,8 @@ int fl_resize_linear(fl_handle* h, const void* src, size_t src_stride, int32_t s
 /* PrepareInputData + Detector::match in one call: the src_W x src_H frame is uploaded, rescaled ON THE DEVICE to W x H
  * (W, H within fl_params_t.max_*) and matched; the rescaled depth frame stays on the device for
  * fl_detection_batch_resident(ref_depth = NULL).  Equal sizes: plain fl_match.  rescaled_depth_out (nullable): W*H u16, the
- * frame detection() would receive (m_depth). */
+ * frame detection() would receive (m_depth).  No masks: the caller never sets one (SetROI is a stub, obj_reco_lmicp.cpp:81-84);
+ * a masked frame goes through fl_resize_linear + fl_match. */
 int fl_match_rescaled(fl_handle* h, const uint8_t* bgr, size_t bgr_stride, const uint16_t* depth, size_t depth_stride,
                       int32_t src_W, int32_t src_H, int32_t W, int32_t H, float threshold, const int32_t* class_filter, int32_t n_filter,
                       fl_match_t* out, int32_t capacity, int32_t* count, uint16_t* rescaled_depth_out);
