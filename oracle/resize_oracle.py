@@ -6,7 +6,8 @@ the reference does not pin (CMakeLists.txt:13-16); this file restates OpenCV's o
 the xofs / alpha / yofs / beta table loops, ``HResizeLinear``, ``VResizeLinear`` with ``FixedPtCast<int, uchar, 22>`` for 8U and
 ``Cast<float, ushort>`` for 16U, and the ``INTER_LINEAR -> INTER_AREA`` switch for an exact 2x decimation) in numpy.
 
-Pinned by tests/test_resize_oracle.py against ``cv2.resize`` 4.13 of this image with IPP switched off (``cv2.ipp.setUseIPP(False)``):
+PARITY STATUS: parity unpinned by the reference itself (it holds no tests or vectors for this step); the anchor is
+OpenCV.  Pinned by tests/test_resize_oracle.py against ``cv2.resize`` 4.13 of this image with IPP switched off (``cv2.ipp.setUseIPP(False)``):
 bit-exact for both types over down-scales, up-scales, odd sizes and the 2x case.  With IPP on, OpenCV hands 16U linear resizing to
 Intel's closed routine, whose results differ from OpenCV's own code by up to 3 counts on ~25 % of the pixels; the oracle (and the
 CUDA kernel) follow OpenCV's code.  Only tests/, smoke() and bench.py's CPU legs may import this module.
