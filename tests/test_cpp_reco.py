@@ -96,6 +96,19 @@ def _write_frame(path, bgr, depth, K):
         f.write(np.ascontiguousarray(depth, np.uint16).tobytes())
 
 
+def test_recognition_fails_loudly_without_a_gpu(exe, tmp_path):
+    """There is no CPU path behind the product API: on a machine without a CUDA device Recognition raises (fl_create -> FL_ERR_CUDA)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    b, d = synth.make_frame(640, 480, 0)
+    ts = synth.make_templates(4, 640, 480, (5, 8), n_classes=1, seed=61)
+    _feature_dir(tmp_path, ts, d)
+    _write_frame(str(tmp_path / "frame.bin"), b, d, (608.0, 608.0, 320.0, 240.0))
+    r = subprocess.run([exe, "run", str(tmp_path), str(tmp_path / "frame.bin")], capture_output=True, text=True)
+    assert r.returncode == 4 and "addobj 00000000" in r.stdout and "no usable CUDA device" in r.stdout
+
+
 @pytest.mark.gpu
 def test_cpp_recognition_equals_python_mirror(exe, tmp_path):
     import cv2
