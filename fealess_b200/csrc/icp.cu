@@ -179,10 +179,11 @@ __device__ void svd3_rot(const float* cov, float* R) {
     float s = (float)(sd > DBL_MIN ? 1 / sd : 0.);
     for (int k = 0; k < 3; ++k) U[i][k] = __fmul_rn(At[i][k], s);
   }
+  // Mat(vt.t() * u.t()) (ICP.cpp:744) is a cv::gemm; for CV_32F its kernel accumulates the products in double and rounds once
   for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) {
-    float s = 0.f;
-    for (int i = 0; i < 3; ++i) s = __fadd_rn(s, __fmul_rn(Vt[i][r], U[i][c]));
-    R[3 * r + c] = s;
+    double s = 0.;
+    for (int i = 0; i < 3; ++i) s += (double)Vt[i][r] * (double)U[i][c];   // fp32 x fp32 is exact in fp64, so contraction cannot change it
+    R[3 * r + c] = (float)s;
   }
 }
 
@@ -566,7 +567,7 @@ __global__ void k_nms(const float* __restrict__ t3, const int32_t* __restrict__ 
     for (int j = i + 1; j < n; ++j) {
       if (done[j]) continue;
       double s = 0;
-      for (int k = 0; k < 3; ++k) { double d = (double)t3[3 * win + k] - (double)t3[3 * j + k]; s += d * d; }   // cv::norm(Mat, Mat)
+      for (int k = 0; k < 3; ++k) { double d = (double)__fsub_rn(t3[3 * win + k], t3[3 * j + k]); s += d * d; }   // cv::norm(Mat, Mat): fp32 difference, fp64 squares
       if (sqrt(s) < (double)th) {
         done[j] = 1;
         if (n_model[j] > size_th && icp_dist[j] < icp_dist[win]) win = j;

@@ -813,10 +813,12 @@ void flo_svd3_rot(const float cov[9], float R[9]) {
     float s = (float)(sd > DBL_MIN ? 1 / sd : 0.);
     for (int k = 0; k < 3; ++k) U[i][k] = At[i][k] * s;
   }
+  /* Mat(vt.t() * u.t()) is a cv::gemm with both operands transposed: its kernel for CV_32F (GEMMSingleMul<float,double>)
+   * accumulates the three products in double and rounds once (checked against oracle/_ref and cv2.gemm). */
   for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) {
-    float s = 0.f;
-    for (int i = 0; i < 3; ++i) s += Vt[i][r] * U[i][c];
-    R[3 * r + c] = s;
+    double s = 0.;
+    for (int i = 0; i < 3; ++i) s += (double)Vt[i][r] * (double)U[i][c];
+    R[3 * r + c] = (float)s;
   }
 }
 
@@ -935,7 +937,7 @@ int flo_nms(const float* t3, const int32_t* n_model_pts, const float* icp_dist, 
     for (int j = i + 1; j < n; ++j) {
       if (done[j]) continue;
       double s = 0;
-      for (int k = 0; k < 3; ++k) { double dd = (double)t3[3 * win + k] - (double)t3[3 * j + k]; s += dd * dd; }   /* cv::norm(Mat,Mat) */
+      for (int k = 0; k < 3; ++k) { double dd = (double)(t3[3 * win + k] - t3[3 * j + k]); s += dd * dd; }   /* cv::norm(Mat,Mat): normL2Sqr<float,double>, v = double(a - b) with the difference taken in fp32 */
       if (sqrt(s) < th) {
         done[j] = 1;
         if (n_model_pts[j] > size_th && icp_dist[j] < icp_dist[win]) win = j;   /* :27-28 */

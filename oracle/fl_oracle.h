@@ -5,11 +5,12 @@
  * compare the CUDA path with, and the "port" CPU baseline bench.py times.  Nothing under
  * fealess_b200/ may include, link or call it.
  *
- * PARITY STATUS: the reference has no tests / golden vectors and cannot be built in this image
- * (needs the OpenCV 3.x C++ SDK), so this oracle is pinned against (a) the sha256 of the reference's
- * two embedded tables and (b) fixtures in tests/golden/ produced by oracle/oracle_cv2.py, which runs
- * the same cited lines on the REAL OpenCV primitives (cv2 4.13).  "Parity unpinned by the reference's
- * own tests" - see DESIGN.md.
+ * PARITY STATUS: pinned on the reference itself.  oracle/_ref/libfl_ref.so is the reference's own linemod.cpp and ICP
+ * sources compiled unmodified (oracle/build_ref.py; OpenCV replaced by the stand-in oracle/ref_shim, whose primitives are
+ * pinned on the real cv2 4.13 and can be swapped for it at run time); tests/test_oracle_ref.py shows this file equal to it
+ * bit for bit on every integer stage, on the pre-sort match lists, on depthTo3d / matToVec / NMS and on the ICP poses.
+ * Older anchors kept: the sha256 of the reference's two embedded tables and the fixtures in tests/golden/ written by
+ * oracle/oracle_cv2.py (the cited lines evaluated on cv2).  The reference holds no tests or golden vectors of its own.
  *
  * All file:line citations are relative to /root/reference.
  */

@@ -298,30 +298,37 @@ def test_single_modality_colour_only():
     assert h.match(None, d, 70.0)[0] == fb.FL_ERR_SIZE    # the colour modality has no source
 
 
-def test_properties_at_full_size_8k_templates():
-    """BASELINE config C2 (8k templates): size-independent properties instead of the (slow) oracle over all templates."""
-    W, H, T = 640, 480, (5, 8)
+def _full_size_case(W, H, T, n_templates, n_classes, thresholds, seed=1, planted=0.01, max_candidates=1 << 16):
+    """Whole-list parity at a BASELINE.json configuration's real size: the C oracle over EVERY template (OpenMP over templates,
+    result-identical to one thread - tests/test_oracle_golden.py), so a missed match among the non-matching templates would show."""
     b, d = synth.make_frame(W, H, 0)
-    det = _oracle(b, d)
-    q = [det.quantized(l, m) for l in range(2) for m in range(2)]
-    ts = synth.make_templates(8000, W, H, T, seed=1, quantized=q, planted_fraction=0.01)
-    h = fb.Handle(T, (0, 1), W, H)
+    det = _oracle(b, d, T)
+    L = len(T)
+    q = [det.quantized(l, m) for l in range(L) for m in range(2)]
+    ts = synth.make_templates(n_templates, W, H, T, n_classes=n_classes, seed=seed, quantized=q, planted_fraction=planted)
+    det.set_templates(ts)
+    h = fb.Handle(T, (0, 1), W, H, max_candidates=max_candidates)
     h.upload_templates(ts)
-    rc, got = h.match(b, d, 75.0)
-    assert rc == 0 and len(got) > 0
-    # (1) sorted by the canonical order and free of adjacent duplicates; idempotent under re-canonicalisation
-    assert np.array_equal(canonical(got), got)
-    # (2) every reported match is reproduced by the oracle restricted to that template (spot check: all planted hits)
-    tids = np.unique(got["template_id"])
-    sub = ts.subset(tids.tolist())
-    det.set_templates(sub)
-    want = det.match(75.0)
-    remap = {i: int(t) for i, t in enumerate(tids)}
-    want["template_id"] = [remap[int(t)] for t in want["template_id"]]
-    assert np.array_equal(canonical(want), got)
-    # (3) determinism across calls, and shard invariance: two half-shards reproduce the full result
-    rc, again = h.match(b, d, 75.0)
-    assert np.array_equal(again, got)
+    h.keep_spread(True)
+    out = []
+    for thr in thresholds:
+        want = det.match(thr, n_threads=os.cpu_count() or 1)
+        rc, got = h.match(b, d, thr, capacity=max_candidates)
+        assert rc == 0 and len(got) == len(want) > 0, (thr, rc, len(got), len(want))
+        assert np.array_equal(got, want), thr
+        out.append(got)
+    assert h.uses_staged()
+    _check_front_end(h, det, W, H, L=L)
+    return b, d, ts, det, h, out
+
+
+def test_c2_full_oracle_8k_templates():
+    """BASELINE config C2 (640x480, 8,000 templates, match only): full lists at thresholds 75 and 60."""
+    W, H, T = 640, 480, (5, 8)
+    b, d, ts, det, h, (got75, got60) = _full_size_case(W, H, T, 8000, 1, (75.0, 60.0))
+    assert len(got60) > len(got75)
+    # determinism across calls, and shard invariance: two half-shards reproduce the full result
+    assert np.array_equal(h.match(b, d, 75.0)[1], got75)
     from fealess_b200 import sharded
     parts = []
     for r in range(2):
@@ -331,7 +338,25 @@ def test_properties_at_full_size_8k_templates():
         hs.set_template_ids(gids)
         parts.append(hs.match(b, d, 75.0)[1])
         hs.close()
-    assert np.array_equal(canonical(np.concatenate(parts)), got)
+    assert np.array_equal(canonical(np.concatenate(parts)), got75)
+    h.close()
+
+
+def test_c4_full_oracle_720p_15_classes_x_2000():
+    """BASELINE config C4 geometry and size: 1280x720, 15 classes x 2,000 templates, T = {5, 8} (1280 % 5 == 720 % 5 == 0,
+    640 % 8 == 360 % 8 == 0)."""
+    b, d, ts, det, h, (got,) = _full_size_case(1280, 720, (5, 8), 30000, 15, (75.0,), planted=0.004)
+    assert len(np.unique(got["class_idx"])) >= 8
+    rc, only = h.match(b, d, 75.0, class_filter=[3, 11])
+    assert rc == 0 and np.array_equal(only, det.match(75.0, class_filter=[3, 11], n_threads=os.cpu_count() or 1))
+    h.close()
+
+
+def test_c5_full_oracle_1080p_four_levels_32k():
+    """BASELINE config C5 geometry and size: 1920x1080, 4 pyramid levels, 32,000 templates, T = {5, 5, 5, 5} (T_l must
+    divide both dimensions of level l; {5, 8, ..} is invalid at 960x540)."""
+    b, d, ts, det, h, (got,) = _full_size_case(1920, 1080, (5, 5, 5, 5), 32000, 16, (75.0,), planted=0.004)
+    h.close()
 
 
 def test_device_resident_and_sharded_api_single_gpu():
