@@ -64,7 +64,7 @@ struct fl_handle {
   bool profile; cudaEvent_t ev[5]; float stage_ms[4]; float icp_ms;
   // ICP workspace (grown on demand)
   int icp_hyp_cap, icp_pts_cap;
-  fl_icp_ws icp; fl_icp_hyp* d_hyps; float* d_t_init; fl_icp_result_t* d_results; uint16_t* d_model_crops; uint16_t* d_ref_depth;
+  fl_icp_ws icp; fl_icp_hyp* d_hyps; fl_icp_result_t* d_results; uint16_t* d_model_crops; uint16_t* d_ref_depth; int* d_icp_ticket;
   size_t ref_depth_cap;
   uint16_t* h_model_crops; fl_icp_hyp* h_hyps; fl_icp_result_t* h_results; size_t h_crop_cap;
   // rendered template depth crops kept on the device (fl_upload_model_depths) and the geometry of the depth frame that the
@@ -133,7 +133,7 @@ extern "C" int fl_create(const fl_params_t* params, fl_handle** out) {
   h->staged_eligible = false; h->use_staged = false; h->force_baseline = 0; memset(&h->plan, 0, sizeof h->plan);
   { cudaDeviceProp prop; FL_CUDA(cudaGetDeviceProperties(&prop, p.device)); h->n_sm = prop.multiProcessorCount; }
   h->icp_hyp_cap = h->icp_pts_cap = 0; memset(&h->icp, 0, sizeof h->icp);
-  h->d_hyps = nullptr; h->d_t_init = nullptr; h->d_results = nullptr; h->d_model_crops = nullptr; h->d_ref_depth = nullptr; h->ref_depth_cap = 0;
+  h->d_hyps = nullptr; h->d_results = nullptr; h->d_model_crops = nullptr; h->d_ref_depth = nullptr; h->ref_depth_cap = 0; h->d_icp_ticket = nullptr;
   h->h_model_crops = nullptr; h->h_hyps = nullptr; h->h_results = nullptr; h->h_crop_cap = 0;
   h->d_resident = nullptr; h->res_W = h->res_H = 0; h->in_depth_W = h->in_depth_H = 0;
   memset(&h->rz, 0, sizeof h->rz); h->rz_sW = h->rz_sH = h->rz_dW = h->rz_dH = 0;
@@ -181,11 +181,11 @@ extern "C" int fl_create(const fl_params_t* params, fl_handle** out) {
 
 static void icp_free(fl_handle* h) {
   cudaFree(h->icp.pts_ref); cudaFree(h->icp.pts_mod); cudaFree(h->icp.cor_m); cudaFree(h->icp.cor_r); cudaFree(h->icp.dist);
-  cudaFree(h->icp.grid_pts); cudaFree(h->icp.cell_start); cudaFree(h->icp.n_ref); cudaFree(h->icp.n_mod);
-  cudaFree(h->d_hyps); cudaFree(h->d_t_init); cudaFree(h->d_results); cudaFree(h->d_model_crops);
+  cudaFree(h->icp.grid_pts); cudaFree(h->icp.nn_d2); cudaFree(h->icp.nn_slot); cudaFree(h->icp.n_ref); cudaFree(h->icp.n_mod);
+  cudaFree(h->d_hyps); cudaFree(h->d_results); cudaFree(h->d_model_crops); cudaFree(h->d_icp_ticket);
   cudaFreeHost(h->h_model_crops); cudaFreeHost(h->h_hyps); cudaFreeHost(h->h_results);
   memset(&h->icp, 0, sizeof h->icp);
-  h->d_hyps = nullptr; h->d_t_init = nullptr; h->d_results = nullptr; h->d_model_crops = nullptr;
+  h->d_hyps = nullptr; h->d_results = nullptr; h->d_model_crops = nullptr; h->d_icp_ticket = nullptr;
   h->h_model_crops = nullptr; h->h_hyps = nullptr; h->h_results = nullptr; h->h_crop_cap = 0;
   h->icp_hyp_cap = h->icp_pts_cap = 0;
 }
@@ -1092,14 +1092,15 @@ extern "C" int fl_match_rescaled(fl_handle* h, const uint8_t* bgr, size_t bgr_st
 // ---------------------------------------------------------------------------------------------------
 static int icp_reserve(fl_handle* h, int n_hyp, int max_pts) {
   if (n_hyp <= h->icp_hyp_cap && max_pts <= h->icp_pts_cap) { h->icp.n_hyp = n_hyp; return FL_OK; }
-  int nh = std::max(n_hyp, h->icp_hyp_cap), np = std::max(max_pts, h->icp_pts_cap);
+  int nh = std::max(n_hyp, h->icp_hyp_cap), np = (std::max(max_pts, h->icp_pts_cap) + 3) & ~3;
   FL_CUDA(cudaStreamSynchronize(h->stream));
   icp_free(h);
   size_t tot = (size_t)nh * np;
   TRY(dalloc(&h->icp.pts_ref, tot * 3)); TRY(dalloc(&h->icp.pts_mod, tot * 3)); TRY(dalloc(&h->icp.cor_m, tot * 3)); TRY(dalloc(&h->icp.cor_r, tot * 3));
-  TRY(dalloc(&h->icp.dist, tot)); TRY(dalloc(&h->icp.grid_pts, tot)); TRY(dalloc(&h->icp.cell_start, (size_t)nh * (FL_ICP_CELLS + 1)));
+  TRY(dalloc(&h->icp.dist, tot)); TRY(dalloc(&h->icp.grid_pts, tot)); TRY(dalloc(&h->icp.nn_d2, tot)); TRY(dalloc(&h->icp.nn_slot, tot));
+  TRY(dalloc(&h->d_icp_ticket, (size_t)1));
   TRY(dalloc(&h->icp.n_ref, (size_t)nh)); TRY(dalloc(&h->icp.n_mod, (size_t)nh));
-  TRY(dalloc(&h->d_hyps, (size_t)nh)); TRY(dalloc(&h->d_t_init, (size_t)nh * 3)); TRY(dalloc(&h->d_results, (size_t)nh)); TRY(dalloc(&h->d_model_crops, tot));
+  TRY(dalloc(&h->d_hyps, (size_t)nh)); TRY(dalloc(&h->d_results, (size_t)nh)); TRY(dalloc(&h->d_model_crops, tot));
   TRY(halloc(&h->h_model_crops, tot)); TRY(halloc(&h->h_hyps, (size_t)nh)); TRY(halloc(&h->h_results, (size_t)nh));
   h->icp_hyp_cap = nh; h->icp_pts_cap = np; h->icp.max_pts = np; h->icp.n_hyp = n_hyp;
   return FL_OK;
@@ -1131,7 +1132,10 @@ extern "C" int fl_icp_cloud_to_cloud_ex(fl_handle* h, const float* pts_ref, int3
   FL_CUDA(cudaMemcpyAsync(h->icp.n_ref, &n_ref, 4, cudaMemcpyHostToDevice, s));
   FL_CUDA(cudaMemcpyAsync(h->icp.n_mod, &n_model, 4, cudaMemcpyHostToDevice, s));
   FL_CUDA(cudaStreamSynchronize(s));                                            // &n_ref / &n_model are stack addresses
-  fl_launch_icp_run(h->icp, prm, nullptr, nullptr, h->d_results, s); ++h->launches;
+  { const fl_intrinsics_t none = {0.f, 0.f, 0.f, 0.f};
+    const int nl = fl_launch_icp(h->icp, prm, nullptr, nullptr, 0, 0, none, h->d_results, h->d_icp_ticket, h->n_sm, s);
+    if (nl < 0) { fl_set_error("ICP kernel launch failed: %s", cudaGetErrorString(cudaGetLastError())); return FL_ERR_CUDA; }
+    h->launches += nl; }
   FL_CUDA(cudaMemcpyAsync(h->h_results, h->d_results, sizeof(fl_icp_result_t), cudaMemcpyDeviceToHost, s));
   FL_CUDA(cudaStreamSynchronize(s));
   FL_CUDA(cudaGetLastError());
@@ -1162,8 +1166,9 @@ static int icp_run_batch(fl_handle* h, const uint16_t* d_ref, int W, int H, fl_i
   cudaStream_t s = h->stream;
   FL_CUDA(cudaMemcpyAsync(h->d_hyps, h->h_hyps, sizeof(fl_icp_hyp) * (size_t)n, cudaMemcpyHostToDevice, s));
   if (h->profile) cudaEventRecord(h->ev[0], s);
-  fl_launch_icp_prepare(d_ref, W, H, K_ref, h->d_hyps, h->icp, h->d_t_init, s); ++h->launches;
-  fl_launch_icp_run(h->icp, prm, h->d_hyps, h->d_t_init, h->d_results, s); ++h->launches;
+  { const int nl = fl_launch_icp(h->icp, prm, h->d_hyps, d_ref, W, H, K_ref, h->d_results, h->d_icp_ticket, h->n_sm, s);
+    if (nl < 0) { fl_set_error("ICP kernel launch failed: %s", cudaGetErrorString(cudaGetLastError())); return FL_ERR_CUDA; }
+    h->launches += nl; }
   if (h->profile) cudaEventRecord(h->ev[1], s);
   FL_CUDA(cudaMemcpyAsync(h->h_results, h->d_results, sizeof(fl_icp_result_t) * (size_t)n, cudaMemcpyDeviceToHost, s));
   FL_CUDA(cudaStreamSynchronize(s));

@@ -193,15 +193,15 @@ struct fl_icp_hyp {                 // one hypothesis of a batch, device-visible
   float r_match[9], t_match[3];
   int status;
 };
-struct fl_icp_ws {                  // per-batch workspace, all device pointers
+struct fl_icp_ws {                  // per-batch workspace, all device pointers; max_pts is a multiple of 4
   int n_hyp, max_pts;
   float* pts_ref;                   // [n_hyp][max_pts][3]
   float* pts_mod;                   // [n_hyp][max_pts][3]  (pts_model_tmp)
   float* cor_m; float* cor_r;       // [n_hyp][max_pts][3]  ordered correspondences
-  float* dist;                      // [n_hyp][max_pts]     per-point paired distance (NaN-coded skips)
-  float4* grid_pts;                 // [n_hyp][max_pts]     ref points sorted by cell (x,y,z,index)
-  int* cell_start;                  // [n_hyp][FL_ICP_CELLS+1]
-  int* n_ref; int* n_mod;           // [n_hyp]
+  float* dist;                      // [n_hyp][max_pts]     inlier distances of the index pairs (0 for the others)
+  float* nn_d2; int* nn_slot;       // [n_hyp][max_pts]     nearest reference point of every model point: squared distance, slot in the grid
+  float4* grid_pts;                 // [n_hyp][max_pts]     ref points sorted by cell (x,y,z,index) - only for clouds that do not fit shared memory
+  int* n_ref; int* n_mod;           // [n_hyp]              cloud mode only
 };
 #define FL_ICP_GRID 64
 #define FL_ICP_CELLS (FL_ICP_GRID * FL_ICP_GRID)
@@ -213,9 +213,9 @@ struct fl_resize_tables {
 };
 void fl_launch_resize_linear(const void* src, int sW, int sH, int type, void* dst, int dW, int dH, const fl_resize_tables& t, cudaStream_t s);
 void fl_launch_depth_to_3d(const uint16_t* depth, int W, int H, fl_intrinsics_t K, float* out3, cudaStream_t s);
-void fl_launch_icp_prepare(const uint16_t* ref_depth, int W, int H, fl_intrinsics_t K_ref, const fl_icp_hyp* hyps,
-                           fl_icp_ws ws, float* t_init_out, cudaStream_t s);
-void fl_launch_icp_run(fl_icp_ws ws, fl_icp_params_t p, const fl_icp_hyp* hyps_or_null, const float* t_init_or_null,
-                       fl_icp_result_t* results, cudaStream_t s);
+// the whole of detection() / icpCloudToCloud_Ex for a batch in ONE persistent launch (icp.cu); hyps == NULL: cloud mode.
+// ticket: device int (reset by the call).  Returns the number of launches, -1 on a launch error.
+int fl_launch_icp(fl_icp_ws ws, fl_icp_params_t p, const fl_icp_hyp* hyps_or_null, const uint16_t* ref_depth, int W, int H, fl_intrinsics_t K_ref,
+                  fl_icp_result_t* results, int* ticket, int n_sm, cudaStream_t s);
 void fl_launch_nms(const float* t3, const int32_t* n_model, const float* icp_dist, int n, float th, int32_t* out_idx,
                    int32_t* out_count, cudaStream_t s);
