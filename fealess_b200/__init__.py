@@ -43,7 +43,7 @@ EXPORTED_SYMBOLS = [
     "fl_default_params", "fl_create", "fl_destroy", "fl_last_error", "fl_version", "fl_sync", "fl_stream",
     "fl_upload_templates", "fl_set_template_ids", "fl_num_templates", "fl_get_pose_info", "fl_match", "fl_match_device", "fl_match_device_async", "fl_match_wait", "fl_match_fetch",
     "fl_resize_linear", "fl_match_rescaled", "fl_match_shard_device", "fl_sort_unique_device", "fl_sort_unique_blocks_device", "fl_exchange_buffer_bytes", "fl_exchange_sort_unique_device", "fl_exchange_sort_unique_device_async", "fl_match_shard_exchange_device_async", "fl_depth_to_3d", "fl_icp_cloud_to_cloud_ex",
-    "fl_detection_batch", "fl_upload_model_depths", "fl_detection_batch_resident", "fl_detection", "fl_nms", "fl_nms_ex", "fl_debug_keep_spread", "fl_debug_force_baseline", "fl_debug_uses_staged", "fl_debug_get", "fl_launch_count",
+    "fl_detection_batch", "fl_upload_model_depths", "fl_detection_batch_resident", "fl_detection", "fl_nms", "fl_nms_ex", "fl_debug_keep_spread", "fl_debug_force_baseline", "fl_debug_uses_staged", "fl_debug_get", "fl_debug_icp_trace", "fl_launch_count",
     "fl_profile", "fl_last_stage_ms", "fl_last_icp_ms",
 ]
 
@@ -254,12 +254,16 @@ class Handle:
     def match_wait(self) -> None:
         _check(lib().fl_match_wait(self._h), "fl_match_wait")
 
-    def match_fetch(self, capacity: int = 1 << 16) -> np.ndarray:
+    def match_fetch(self, capacity: int = 1 << 16, allow_truncated: bool = False) -> np.ndarray:
+        """The merged match list of the last frame.  An overflow (a candidate buffer, an exchange block or ``capacity`` too small)
+        raises ``FealessError(FL_ERR_CAPACITY)`` unless ``allow_truncated``; ``last_fetch_rc`` keeps the status either way."""
         out = self._match_out.get(capacity)                     # reused across calls (a fresh 1.3 MB buffer per frame costs more than the fetch)
         if out is None:
             out = self._match_out[capacity] = np.zeros(capacity, MATCH_DTYPE)
         cnt = C.c_int32(0)
-        _check(lib().fl_match_fetch(self._h, _p(out), capacity, C.byref(cnt)), "fl_match_fetch", ok=(FL_OK, FL_ERR_CAPACITY))
+        ok = (FL_OK, FL_ERR_CAPACITY) if allow_truncated else (FL_OK,)      # FL_ERR_CAPACITY: more candidates than a buffer holds, list incomplete
+        self.last_fetch_rc = lib().fl_match_fetch(self._h, _p(out), capacity, C.byref(cnt))
+        _check(self.last_fetch_rc, "fl_match_fetch", ok=ok)
         return out[:min(cnt.value, capacity)].copy()
 
     def match_shard_device(self, d_bgr: int, d_depth: int, W: int, H: int, threshold: float, d_candidates: int, capacity: int,
@@ -318,6 +322,12 @@ class Handle:
         return float(v.value)
 
     # ---- debug exports ---------------------------------------------------------------------------
+    def icp_trace(self, n_hyp: int) -> np.ndarray:
+        """fl_debug_icp_trace: [n_hyp, 20] uint64 phase clock of the last ICP batch (after ``profile(True)``)."""
+        out = np.zeros((n_hyp, 20), np.uint64)
+        _check(lib().fl_debug_icp_trace(self._h, _p(out), n_hyp), "fl_debug_icp_trace")
+        return out
+
     def keep_spread(self, enable=True):
         _check(lib().fl_debug_keep_spread(self._h, int(enable)), "fl_debug_keep_spread")
 

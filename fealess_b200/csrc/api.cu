@@ -64,7 +64,7 @@ struct fl_handle {
   bool profile; cudaEvent_t ev[5]; float stage_ms[4]; float icp_ms;
   // ICP workspace (grown on demand)
   int icp_hyp_cap, icp_pts_cap;
-  fl_icp_ws icp; fl_icp_hyp* d_hyps; fl_icp_result_t* d_results; uint16_t* d_model_crops; uint16_t* d_ref_depth; int* d_icp_ticket;
+  fl_icp_ws icp; fl_icp_hyp* d_hyps; fl_icp_result_t* d_results; uint16_t* d_model_crops; uint16_t* d_ref_depth; int* d_icp_ticket; unsigned long long* d_icp_trace; int icp_trace_cap, icp_trace_n;
   size_t ref_depth_cap;
   uint16_t* h_model_crops; fl_icp_hyp* h_hyps; fl_icp_result_t* h_results; size_t h_crop_cap;
   // rendered template depth crops kept on the device (fl_upload_model_depths) and the geometry of the depth frame that the
@@ -133,7 +133,7 @@ extern "C" int fl_create(const fl_params_t* params, fl_handle** out) {
   h->staged_eligible = false; h->use_staged = false; h->force_baseline = 0; memset(&h->plan, 0, sizeof h->plan);
   { cudaDeviceProp prop; FL_CUDA(cudaGetDeviceProperties(&prop, p.device)); h->n_sm = prop.multiProcessorCount; }
   h->icp_hyp_cap = h->icp_pts_cap = 0; memset(&h->icp, 0, sizeof h->icp);
-  h->d_hyps = nullptr; h->d_results = nullptr; h->d_model_crops = nullptr; h->d_ref_depth = nullptr; h->ref_depth_cap = 0; h->d_icp_ticket = nullptr;
+  h->d_hyps = nullptr; h->d_results = nullptr; h->d_model_crops = nullptr; h->d_ref_depth = nullptr; h->ref_depth_cap = 0; h->d_icp_ticket = nullptr; h->d_icp_trace = nullptr; h->icp_trace_cap = h->icp_trace_n = 0;
   h->h_model_crops = nullptr; h->h_hyps = nullptr; h->h_results = nullptr; h->h_crop_cap = 0;
   h->d_resident = nullptr; h->res_W = h->res_H = 0; h->in_depth_W = h->in_depth_H = 0;
   memset(&h->rz, 0, sizeof h->rz); h->rz_sW = h->rz_sH = h->rz_dW = h->rz_dH = 0;
@@ -180,6 +180,7 @@ extern "C" int fl_create(const fl_params_t* params, fl_handle** out) {
 }
 
 static void icp_free(fl_handle* h) {
+  cudaFree(h->d_icp_trace); h->d_icp_trace = nullptr; h->icp_trace_cap = h->icp_trace_n = 0;
   cudaFree(h->icp.pts_ref); cudaFree(h->icp.pts_mod); cudaFree(h->icp.cor_m); cudaFree(h->icp.cor_r); cudaFree(h->icp.dist);
   cudaFree(h->icp.grid_pts); cudaFree(h->icp.nn_d2); cudaFree(h->icp.nn_slot); cudaFree(h->icp.n_ref); cudaFree(h->icp.n_mod);
   cudaFree(h->d_hyps); cudaFree(h->d_results); cudaFree(h->d_model_crops); cudaFree(h->d_icp_ticket);
@@ -227,6 +228,13 @@ extern "C" void* fl_stream(fl_handle* h) { return h ? (void*)h->stream : nullptr
 extern "C" int64_t fl_launch_count(fl_handle* h) { return h ? h->launches : 0; }
 extern "C" int fl_profile(fl_handle* h, int enable) { if (!h) return FL_ERR_ARG; h->profile = enable != 0; return FL_OK; }
 extern "C" int fl_last_icp_ms(fl_handle* h, float* ms) { if (!h || !ms) return FL_ERR_ARG; *ms = h->icp_ms; return FL_OK; }
+extern "C" int fl_debug_icp_trace(fl_handle* h, uint64_t* out, int32_t n_hyp) {
+  if (!h || !out || n_hyp < 0) return FL_ERR_ARG;
+  if (!h->d_icp_trace || n_hyp > h->icp_trace_n) { fl_set_error("no ICP phase clock: call fl_profile(h, 1) before the batch"); return FL_ERR_STATE; }
+  FL_CUDA(cudaSetDevice(h->p.device));
+  FL_CUDA(cudaMemcpy(out, h->d_icp_trace, (size_t)n_hyp * FL_ICP_TRACE_WORDS * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  return FL_OK;
+}
 extern "C" int fl_last_stage_ms(fl_handle* h, float out4[4]) { if (!h || !out4) return FL_ERR_ARG; memcpy(out4, h->stage_ms, sizeof h->stage_ms); return FL_OK; }
 // 1 = always use the baseline (L1/L2-fed) global similarity kernel; 0 = use the shared-memory-staged kernel when eligible
 extern "C" int fl_debug_force_baseline(fl_handle* h, int enable) { if (!h) return FL_ERR_ARG; h->force_baseline = enable != 0; h->packed = false; return FL_OK; }
@@ -668,12 +676,16 @@ static int sort_launch(fl_handle* h, fl_lists L, fl_match_t* d_out, int out_cap,
     memset(&ra, 0, sizeof ra);
     ra.n_levels = h->p.n_levels;
     for (int l = 0; l < h->p.n_levels; ++l) { ra.g[l] = h->geom[l]; ra.lm[l] = h->d_lm[l]; }
-    h->launches += fl_launch_refine_sort(make_tdb(h), ra, refine->threshold, refine->cand, refine->cap, refine->d_count, h->d_count + 1, h->n_sm, L, X, h->key_cap,
+    const int nl = fl_launch_refine_sort(make_tdb(h), ra, refine->threshold, refine->cand, refine->cap, refine->d_count, h->d_count + 1, h->n_sm, L, X, h->key_cap,
                                          d_out, out_cap, d_out_count, d_hdr, h->h_small, own ? h->h_first : nullptr, std::min(FETCH_FIRST, out_cap), refine->small, s);
+    if (nl < 0) { fl_set_error("refinement + sort launch failed: %s", cudaGetErrorString(cudaGetLastError())); return FL_ERR_CUDA; }
+    h->launches += nl;
     h->pend_small_fused = refine->small;
   } else {
-    h->launches += fl_launch_sort_unique(L, X, h->key_cap, d_out, out_cap, d_out_count, d_hdr, h->h_small, own ? h->h_first : nullptr,
+    const int nl = fl_launch_sort_unique(L, X, h->key_cap, d_out, out_cap, d_out_count, d_hdr, h->h_small, own ? h->h_first : nullptr,
                                          std::min(FETCH_FIRST, out_cap), s);
+    if (nl < 0) { fl_set_error("sort launch failed: %s", cudaGetErrorString(cudaGetLastError())); return FL_ERR_CUDA; }
+    h->launches += nl;
   }
   if (h->profile) cudaEventRecord(h->ev[4], s);
   // what the second half (sort_finish) needs: it runs after the host has waited for the stream
@@ -697,10 +709,16 @@ static int sort_finish(fl_handle* h) {
   if (n_lists > 11) n_upper = n_lists * list_cap;
   if (h->h_small[2] && h->pend_small_fused && n_upper <= 8192) {
     // the fused refinement + sort launch sorts up to 1,024 records in its last CTA; this frame has more (already refined in
-    // place): run the stand-alone one-CTA sort (8,192 keys) on them
+    // place): run the stand-alone one-CTA sort (8,192 keys) on them.  What the first launch reported about the exchange
+    // (a peer that never arrived) and the fused tail survives the second launch, which knows about neither.
+    const int keep14 = h->h_small[14], keep15 = h->h_small[15];
+    const bool keep_overflow = h->overflow;
     h->pend_small_fused = false;
     TRY(sort_launch(h, L, d_out, out_cap, d_out_count, own));
-    return sort_finish(h);
+    const int rc = sort_finish(h);
+    h->h_small[14] |= keep14; if (keep15) h->h_small[15] = keep15;
+    h->overflow |= keep_overflow;
+    return rc;
   }
   h->pend_small_fused = false;
   if (h->h_small[2]) {                                                          // more records than the one-CTA sort holds: multi-kernel sort
@@ -801,6 +819,9 @@ extern "C" int fl_match(fl_handle* h, const uint8_t* bgr, size_t bgr_stride, con
   if (!h || !count) return FL_ERR_ARG;
   *count = 0;
   const fl_params_t& p = h->p;
+  // an asynchronous frame still in flight may be reading the staging buffers this call is about to overwrite
+  if (h->pend_sort) { fl_set_error("fl_match_wait has not been called for the previous frame"); return FL_ERR_STATE; }
+  h->in_depth_W = h->in_depth_H = 0;                                               // d_in_depth counts as "the matched frame" only once this call has succeeded
   if (W <= 0 || H <= 0 || W > p.max_width || H > p.max_height) return FL_ERR_SIZE;
   FL_CUDA(cudaSetDevice(p.device));
   cudaStream_t s = h->stream;
@@ -823,7 +844,6 @@ extern "C" int fl_match(fl_handle* h, const uint8_t* bgr, size_t bgr_stride, con
       FL_CUDA(cudaMemcpyAsync(h->d_in_depth, h->h_depth, (size_t)W * H * 2, cudaMemcpyHostToDevice, s));
     }
     d_depth = h->d_in_depth;
-    h->in_depth_W = W; h->in_depth_H = H;
   }
   if (bgr) {
     if (bgr_stride < (size_t)W * 3) return FL_ERR_SIZE;
@@ -851,6 +871,7 @@ extern "C" int fl_match(fl_handle* h, const uint8_t* bgr, size_t bgr_stride, con
   }
   int rc = fl_match_device(h, d_bgr, d_depth, W, H, any_mask ? d_masks : nullptr, threshold, class_filter, n_filter);
   if (rc != FL_OK) return rc;
+  if (d_depth) { h->in_depth_W = W; h->in_depth_H = H; }
   rc = fl_match_fetch(h, out, capacity, count);
   if (quantized_out) {
     for (int l = 0; l < p.n_levels; ++l) for (int m = 0; m < p.n_modalities; ++m) {
@@ -889,6 +910,7 @@ extern "C" int fl_exchange_sort_unique_device_async(fl_handle* h, int32_t rank, 
                                                     const fl_match_t* d_local_block, uint32_t epoch) {
   if (!h || !peer_buffers || !d_local_block || world < 1 || world > FL_XCHG_MAX_WORLD || rank < 0 || rank >= world || capacity < 1 || epoch == 0) return FL_ERR_ARG;
   FL_CUDA(cudaSetDevice(h->p.device));
+  if (h->pend_sort) { fl_set_error("fl_match_wait has not been called for the previous frame"); return FL_ERR_STATE; }
   h->have_result = false; h->pend_match = false;
   if (h->profile) for (int i = 0; i < 4; ++i) cudaEventRecord(h->ev[i], h->stream);
   fl_xchg X;
@@ -1059,6 +1081,8 @@ extern "C" int fl_match_rescaled(fl_handle* h, const uint8_t* bgr, size_t bgr_st
   if (!h || !count || sW <= 0 || sH <= 0) return FL_ERR_ARG;
   *count = 0;
   const fl_params_t& p = h->p;
+  if (h->pend_sort) { fl_set_error("fl_match_wait has not been called for the previous frame"); return FL_ERR_STATE; }
+  h->in_depth_W = h->in_depth_H = 0;
   if (W <= 0 || H <= 0 || W > p.max_width || H > p.max_height) return FL_ERR_SIZE;
   if (sW == W && sH == H) {                                                      // TImage2Mat resizes only when the width differs (:42)
     int rc = fl_match(h, bgr, bgr_stride, depth, depth_stride, W, H, nullptr, threshold, class_filter, n_filter, out, capacity, count, nullptr);
@@ -1074,7 +1098,7 @@ extern "C" int fl_match_rescaled(fl_handle* h, const uint8_t* bgr, size_t bgr_st
   if (depth) {
     FL_CUDA(cudaMemcpy2DAsync(h->d_src_depth, (size_t)sW * 2, depth, depth_stride, (size_t)sW * 2, sH, cudaMemcpyHostToDevice, s));
     fl_launch_resize_linear(h->d_src_depth, sW, sH, FL_IMG_16UC1, h->d_in_depth, W, H, h->rz, s); ++h->launches;
-    d_depth = h->d_in_depth; h->in_depth_W = W; h->in_depth_H = H;
+    d_depth = h->d_in_depth;
     if (rescaled_depth_out) FL_CUDA(cudaMemcpyAsync(rescaled_depth_out, h->d_in_depth, (size_t)W * H * 2, cudaMemcpyDeviceToHost, s));
   }
   if (bgr) {
@@ -1084,6 +1108,7 @@ extern "C" int fl_match_rescaled(fl_handle* h, const uint8_t* bgr, size_t bgr_st
   }
   int rc = fl_match_device(h, d_bgr, d_depth, W, H, nullptr, threshold, class_filter, n_filter);
   if (rc != FL_OK) return rc;
+  if (d_depth) { h->in_depth_W = W; h->in_depth_H = H; }
   return fl_match_fetch(h, out, capacity, count);
 }
 
@@ -1133,7 +1158,7 @@ extern "C" int fl_icp_cloud_to_cloud_ex(fl_handle* h, const float* pts_ref, int3
   FL_CUDA(cudaMemcpyAsync(h->icp.n_mod, &n_model, 4, cudaMemcpyHostToDevice, s));
   FL_CUDA(cudaStreamSynchronize(s));                                            // &n_ref / &n_model are stack addresses
   { const fl_intrinsics_t none = {0.f, 0.f, 0.f, 0.f};
-    const int nl = fl_launch_icp(h->icp, prm, nullptr, nullptr, 0, 0, none, h->d_results, h->d_icp_ticket, h->n_sm, s);
+    const int nl = fl_launch_icp(h->icp, prm, nullptr, nullptr, 0, 0, none, h->d_results, h->d_icp_ticket, nullptr, h->n_sm, s);
     if (nl < 0) { fl_set_error("ICP kernel launch failed: %s", cudaGetErrorString(cudaGetLastError())); return FL_ERR_CUDA; }
     h->launches += nl; }
   FL_CUDA(cudaMemcpyAsync(h->h_results, h->d_results, sizeof(fl_icp_result_t), cudaMemcpyDeviceToHost, s));
@@ -1166,7 +1191,12 @@ static int icp_run_batch(fl_handle* h, const uint16_t* d_ref, int W, int H, fl_i
   cudaStream_t s = h->stream;
   FL_CUDA(cudaMemcpyAsync(h->d_hyps, h->h_hyps, sizeof(fl_icp_hyp) * (size_t)n, cudaMemcpyHostToDevice, s));
   if (h->profile) cudaEventRecord(h->ev[0], s);
-  { const int nl = fl_launch_icp(h->icp, prm, h->d_hyps, d_ref, W, H, K_ref, h->d_results, h->d_icp_ticket, h->n_sm, s);
+  unsigned long long* trace = nullptr;
+  if (h->profile) {                                                             // per-hypothesis phase clock of the fused kernel (fl_debug_icp_trace)
+    if (h->icp_trace_cap < n) { cudaFree(h->d_icp_trace); h->d_icp_trace = nullptr; TRY(dalloc(&h->d_icp_trace, (size_t)n * FL_ICP_TRACE_WORDS)); h->icp_trace_cap = n; }
+    trace = h->d_icp_trace; h->icp_trace_n = n;
+  }
+  { const int nl = fl_launch_icp(h->icp, prm, h->d_hyps, d_ref, W, H, K_ref, h->d_results, h->d_icp_ticket, trace, h->n_sm, s);
     if (nl < 0) { fl_set_error("ICP kernel launch failed: %s", cudaGetErrorString(cudaGetLastError())); return FL_ERR_CUDA; }
     h->launches += nl; }
   if (h->profile) cudaEventRecord(h->ev[1], s);

@@ -6,6 +6,7 @@
 #include <string.h>
 #include "../../include/fealess_b200.h"
 
+#define FL_MAX_DEVICES 64        // devices of one process (per-device kernel attribute tables)
 #define FL_LM_PAD 4096          // zero bytes after each label's linear memory (flat-addressing over-read)
 #define FL_MAX_T 16
 #define FL_SKIP 0xFFFFFFFFu     // packed-feature offset of a feature that falls outside the image
@@ -203,6 +204,7 @@ struct fl_icp_ws {                  // per-batch workspace, all device pointers;
   float4* grid_pts;                 // [n_hyp][max_pts]     ref points sorted by cell (x,y,z,index) - only for clouds that do not fit shared memory
   int* n_ref; int* n_mod;           // [n_hyp]              cloud mode only
 };
+#define FL_ICP_TRACE_WORDS 20      // developer timeline of the fused ICP launch: words per hypothesis (fl_debug_icp_trace)
 #define FL_ICP_GRID 64
 #define FL_ICP_CELLS (FL_ICP_GRID * FL_ICP_GRID)
 // cv::resize INTER_LINEAR (resize.cu): device tables built by the host for one (source size -> destination size) pair
@@ -214,8 +216,8 @@ struct fl_resize_tables {
 void fl_launch_resize_linear(const void* src, int sW, int sH, int type, void* dst, int dW, int dH, const fl_resize_tables& t, cudaStream_t s);
 void fl_launch_depth_to_3d(const uint16_t* depth, int W, int H, fl_intrinsics_t K, float* out3, cudaStream_t s);
 // the whole of detection() / icpCloudToCloud_Ex for a batch in ONE persistent launch (icp.cu); hyps == NULL: cloud mode.
-// ticket: device int (reset by the call).  Returns the number of launches, -1 on a launch error.
+// ticket: device int (reset by the call); trace: NULL or FL_ICP_TRACE_WORDS words per hypothesis (SM cycles per phase).  Returns the number of launches, -1 on a launch error.
 int fl_launch_icp(fl_icp_ws ws, fl_icp_params_t p, const fl_icp_hyp* hyps_or_null, const uint16_t* ref_depth, int W, int H, fl_intrinsics_t K_ref,
-                  fl_icp_result_t* results, int* ticket, int n_sm, cudaStream_t s);
+                  fl_icp_result_t* results, int* ticket, unsigned long long* trace, int n_sm, cudaStream_t s);
 void fl_launch_nms(const float* t3, const int32_t* n_model, const float* icp_dist, int n, float th, int32_t* out_idx,
                    int32_t* out_count, cudaStream_t s);

@@ -16,6 +16,7 @@
 #include "fl_internal.cuh"
 #include <float.h>
 #include <math.h>
+#include <mutex>
 
 
 __device__ __forceinline__ bool pt_valid(float z) { return z <= 900.0f; }   // is_vec3f_valid (NaN fails), common.cpp:261-266
@@ -72,7 +73,9 @@ void fl_launch_depth_to_3d(const uint16_t* depth, int W, int H, fl_intrinsics_t 
 #define ICP_NWARPS (ICP_NT / 32)
 #define ICP_REC 15                               // floats per record: m.xyz, r.xyz, m[a] * r[b]
 #define ICP_CH 256                               // records per ring buffer (record mode, 2 buffers)
-#define ICP_STAGE_FLOATS (2 * ICP_CH * ICP_REC)  // 7,680 floats = 30,720 B
+#define ICP_CHS (ICP_CH + 4)                     // column stride inside a buffer (records are staged COLUMN-major; + 4: bank spread)
+#define ICP_RBUF (ICP_REC * ICP_CHS)             // floats per record-mode buffer
+#define ICP_STAGE_FLOATS (2 * ICP_RBUF + 32)     // 7,832 floats = 31,328 B, incl. slack for the consumer's look-ahead loads
 #define ICP_DCH 1024                             // floats per ring buffer in distance mode
 #define ICP_DNB 7                                // ... and buffers (7 x 1,024 <= 7,680)
 #define ICP_NSTAGE 8                             // stager warps in record mode (one record per thread and chunk)
@@ -103,22 +106,47 @@ __device__ __forceinline__ int block_excl_scan(int v, int* s_warp, int* total) {
   return base + inc - v;
 }
 
-// The consumer half of an ordered chain: warp 0 sums NCOL columns of `n_steps` records, record i of chunk c at
-// stage[(c % NB) * CHUNK * NCOL + i * NCOL + column]; lane j owns column j.  Called by the 32 lanes of warp 0.
-template <int NCOL, int CHUNK, int NB>
-__device__ __forceinline__ void chain_consume(int n_steps, const float* s_stage, float* s_sum, int bar_threads) {
+// The consumer half of an ordered chain: warp 0 sums NCOL columns of `n_steps` values; chunk c lives in ring buffer c % NB
+// (BUF floats each) COLUMN-major: value i of column j at buf[j * STRIDE + i]; lane j owns column j and fetches four steps per
+// LDS.128 one group of 16 steps ahead of the adds.  Measured (tools/micro/chain_bench.cu): 4.46 cycles per step = the FADD
+// dependent-issue floor; record-major scalar loads ran at 5.3-7.4.  Called by the 32 lanes of warp 0.
+template <int NCOL, int CHUNK, int NB, int BUF, int STRIDE>
+__device__ __forceinline__ void chain_consume(int n_steps, const float* s_stage, float* s_sum, int bar_threads, unsigned long long* wait_cycles, unsigned long long* add_cycles) {
   const int lane = threadIdx.x & 31;
   const int n_chunks = (n_steps + CHUNK - 1) / CHUNK;
   float acc = 0.f;
   for (int c = 0; c < n_chunks; ++c) {
     const int b = c % NB;
+    const long long tw = wait_cycles ? clock64() : 0;
     nb_sync(ICP_BAR_FULL(b), bar_threads);
+    if (wait_cycles && lane == 0) *wait_cycles += (unsigned long long)(clock64() - tw);   // time the sum stood still waiting for data
     const int m = min(CHUNK, n_steps - c * CHUNK);
+    const long long ta = wait_cycles ? clock64() : 0;
     if (lane < NCOL) {
-      const float* s = s_stage + (size_t)b * CHUNK * NCOL + lane;
-#pragma unroll 16
-      for (int i = 0; i < m; ++i) acc = __fadd_rn(acc, s[i * NCOL]);
+      const float4* p = reinterpret_cast<const float4*>(s_stage + (size_t)b * BUF + lane * STRIDE);
+      float4 v[4], w[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = p[u];                   // (reads past m stay inside the ring and are never added)
+      const int full = m >> 2;
+      int i = 0;
+      for (; i + 4 <= full; i += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) w[u] = p[i + 4 + u];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { acc = __fadd_rn(acc, v[u].x); acc = __fadd_rn(acc, v[u].y); acc = __fadd_rn(acc, v[u].z); acc = __fadd_rn(acc, v[u].w); }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = w[u];
+      }
+      const int left = m - 4 * i;                                 // < 16 values, already in v[]
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (4 * u + 0 < left) acc = __fadd_rn(acc, v[u].x);
+        if (4 * u + 1 < left) acc = __fadd_rn(acc, v[u].y);
+        if (4 * u + 2 < left) acc = __fadd_rn(acc, v[u].z);
+        if (4 * u + 3 < left) acc = __fadd_rn(acc, v[u].w);
+      }
     }
+    if (wait_cycles && lane == 0) *add_cycles += (unsigned long long)(clock64() - ta);
     __syncwarp();
     if (c + NB < n_chunks) nb_arrive(ICP_BAR_EMPTY(b), bar_threads);
   }
@@ -199,7 +227,7 @@ __device__ void svd3_rot(const float* cov, float* R) {
 }
 
 
-struct grid_info { float minx, miny, inv_cell, cell; };
+struct grid_info { float minx, miny, inv_cell, cell, z0, zstep; };   // z0 / zstep: quantisation of the per-cell z ranges
 
 __device__ __forceinline__ int cell_of(float v, float mn, float inv_cell) {
   int c = (int)floorf(__fmul_rn(__fsub_rn(v, mn), inv_cell));
@@ -208,8 +236,8 @@ __device__ __forceinline__ int cell_of(float v, float mn, float inv_cell) {
 
 // exact nearest neighbour of q among the grid points, as far as it can matter: a neighbour whose squared distance exceeds
 // bound2 may be missed (the caller drops such pairs).  Returns the SLOT in gp (or -1) and the squared distance.
-__device__ __forceinline__ void nn_query(const float4* __restrict__ gp, const int* __restrict__ cs, const grid_info gi, const float qx,
-                                         const float qy, const float qz, const float bound2, float* best_out, int* slot_out) {
+__device__ __forceinline__ void nn_query(const float4* __restrict__ gp, const int* __restrict__ cs, const unsigned* __restrict__ zr, const grid_info gi,
+                                         const float qx, const float qy, const float qz, const float bound2, float* best_out, int* slot_out) {
   float best = FLT_MAX; int bslot = -1, bidx = 0x7fffffff;
   const int cx = cell_of(qx, gi.minx, gi.inv_cell), cy = cell_of(qy, gi.miny, gi.inv_cell);
   auto scan_run = [&](int p0, int p1) {
@@ -228,31 +256,65 @@ __device__ __forceinline__ void nn_query(const float4* __restrict__ gp, const in
     const int x0 = max(cx - 1, 0), x1 = min(cx + 1, FL_ICP_GRID - 1);
     for (int yy = max(cy - 1, 0); yy <= min(cy + 1, FL_ICP_GRID - 1); ++yy) scan_run(cs[yy * FL_ICP_GRID + x0], cs[yy * FL_ICP_GRID + x1 + 1]);
   }
-  // every point outside the (2k+1)^2 block is farther than k * cell in x or y; 0.9999 absorbs the rounding of cell_of
+  // every point outside the 3 x 3 block is farther than one cell in x or y (0.9999 absorbs the rounding of cell_of)
   const float c1 = gi.cell * 0.9999f;
   float r2 = fminf(best, bound2);
   if (!(c1 * c1 >= r2)) {
-    const float inv_c1 = 1.0f / c1;
-    int k = (int)ceilf(sqrtf(r2) * inv_c1);
-    k = max(k, 2);
-    while (k < FL_ICP_GRID && (float)k * c1 * (float)k * c1 < r2) ++k;
-    k = min(k, FL_ICP_GRID);
-    for (int j = 0; j <= k; ++j) {
-      r2 = fminf(best, bound2);
-      if (j >= 2) { const float dyb = (float)(j - 1) * c1; if (dyb * dyb >= r2) break; }   // rows at offset j lie beyond (j-1) * cell in y
-      int kx = (int)ceilf(sqrtf(r2) * inv_c1);
-      while (kx < k && (float)kx * c1 * (float)kx * c1 < r2) ++kx;
-      kx = min(max(kx, 1), k);
-      const int x0 = max(cx - kx, 0), x1 = min(cx + kx, FL_ICP_GRID - 1);
+    // The disc of radius sqrt(r2) around q, row by row from the query's row outwards, per row only the cells the disc reaches
+    // (the chord), re-evaluated with the best distance found so far.  The clouds are surfaces, so while they are still apart the
+    // nearest neighbour is as far as the GAP between them and the disc covers many cells whose points are all about that far
+    // away: every cell therefore carries its z range, and a cell is opened only if its box can hold a closer point at all.
+    // eps / the one-step slack of the z ranges cover the rounding of cell_of and of the quantisation.
+    const float eps = gi.cell * 1e-3f;
+    const float r = sqrtf(r2);
+    const int y_lo = cell_of(qy - r - eps, gi.miny, gi.inv_cell), y_hi = cell_of(qy + r + eps, gi.miny, gi.inv_cell);
+    for (int j = 0; j < FL_ICP_GRID; ++j) {
+      bool any = false;
       for (int sgn = 0; sgn < (j ? 2 : 1); ++sgn) {
         const int yy = sgn ? cy - j : cy + j;
-        if (yy < 0 || yy >= FL_ICP_GRID) continue;
-        if (j <= 1 && kx == 1) continue;                           // already scanned in the 3 x 3 pass
-        scan_run(cs[yy * FL_ICP_GRID + x0], cs[yy * FL_ICP_GRID + x1 + 1]);
+        if (yy < y_lo || yy > y_hi) continue;
+        any = true;
+        const float lo = gi.miny + (float)yy * gi.cell, hi = lo + gi.cell;
+        const float dy = fmaxf(fmaxf(lo - qy, qy - hi) - eps, 0.f);      // distance from q to the row's band
+        r2 = fminf(best, bound2);
+        const float h2 = r2 - dy * dy;
+        if (!(h2 > 0.f)) continue;
+        const float hx = sqrtf(h2) + eps;
+        const int x0 = cell_of(qx - hx, gi.minx, gi.inv_cell), x1 = cell_of(qx + hx, gi.minx, gi.inv_cell);
+        for (int xx = x0; xx <= x1; ++xx) {
+          if (j <= 1 && xx >= cx - 1 && xx <= cx + 1) continue;          // inside the 3 x 3 block scanned above
+          const int c = yy * FL_ICP_GRID + xx;
+          const int p0 = cs[c], p1 = cs[c + 1];
+          if (p0 == p1) continue;
+          const float lox = gi.minx + (float)xx * gi.cell;
+          const float dx = fmaxf(fmaxf(lox - qx, qx - (lox + gi.cell)) - eps, 0.f);
+          const unsigned zq = zr[c];
+          const float zlo = gi.z0 + (float)(zq & 0xFFFFu) * gi.zstep, zhi = gi.z0 + (float)(zq >> 16) * gi.zstep;
+          const float dz = fmaxf(fmaxf(zlo - qz, qz - zhi), 0.f);
+          if (dx * dx + dy * dy + dz * dz >= fminf(best, bound2)) continue;   // (a lower bound with slack: a skipped cell holds nothing <= best)
+          scan_run(p0, p1);
+        }
       }
+      if (!any && j > 0) break;
     }
   }
   *best_out = best; *slot_out = bslot;
+}
+
+// four consecutive points per thread as three 16-byte accesses: a warp moves 1.5 KB of contiguous memory per step instead of
+// three stride-12 word accesses (the per-hypothesis arrays start 16-byte aligned: max_pts is a multiple of 4)
+struct pts4 { float x[4], y[4], z[4]; };
+__device__ __forceinline__ pts4 load_pts4(const float* p) {
+  const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1], c = reinterpret_cast<const float4*>(p)[2];
+  pts4 r;
+  r.x[0] = a.x; r.y[0] = a.y; r.z[0] = a.z; r.x[1] = a.w; r.y[1] = b.x; r.z[1] = b.y;
+  r.x[2] = b.z; r.y[2] = b.w; r.z[2] = c.x; r.x[3] = c.y; r.y[3] = c.z; r.z[3] = c.w;
+  return r;
+}
+__device__ __forceinline__ void store_pts4(float* p, const pts4& r) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(r.x[0], r.y[0], r.z[0], r.x[1]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(r.y[1], r.z[1], r.x[2], r.y[2]);
+  reinterpret_cast<float4*>(p)[2] = make_float4(r.z[2], r.x[3], r.y[3], r.z[3]);
 }
 
 struct fl_icp_args {
@@ -263,14 +325,16 @@ struct fl_icp_args {
   fl_icp_result_t* results;
   int* ticket;                       // zero before the launch
   int smem_pts;                      // grid points that fit the shared-memory copy (0: the grid stays in global memory)
+  unsigned long long* trace;         // NULL, or FL_ICP_TRACE_WORDS words per hypothesis: SM cycles per phase (fl_profile)
 };
 
 __global__ void __launch_bounds__(ICP_NT, 1) k_icp_fused(const __grid_constant__ fl_icp_args A) {
-  extern __shared__ __align__(16) uint8_t s_dyn[];              // [smem_pts float4][4097 int cell starts][ICP_STAGE_FLOATS float]
+  extern __shared__ __align__(16) uint8_t s_dyn[];              // [smem_pts float4][4097 int cell starts][4096 z ranges][ICP_STAGE_FLOATS float]
   __shared__ int s_warp[ICP_NWARPS];
   __shared__ float s_red[ICP_NWARPS * 4];
   __shared__ float s_sum[16];
   __shared__ int s_cnt2[2];
+  __shared__ float s_apx;                    // unordered sum of the inlier distances: only sizes the speculative neighbour search
   __shared__ float s_Ropt[9], s_Topt[3], s_R[9], s_T[3], s_tinit[3], s_tt[3];
   __shared__ float s_dist_mean, s_dist_diff, s_ratio;
   __shared__ int s_iter, s_go, s_finite, s_h;
@@ -279,7 +343,8 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp_fused(const __grid_constant__
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float4* s_gp = reinterpret_cast<float4*>(s_dyn);
   int* s_cs = reinterpret_cast<int*>(s_dyn + (size_t)A.smem_pts * 16);
-  float* s_stage = reinterpret_cast<float*>(s_cs + FL_ICP_CELLS + 4);
+  unsigned* s_zr = reinterpret_cast<unsigned*>(s_cs + FL_ICP_CELLS + 4);   // per cell: quantised {z min (low half), z max (high half)}
+  float* s_stage = reinterpret_cast<float*>(s_zr + FL_ICP_CELLS);
   int* s_cur = reinterpret_cast<int*>(s_stage);                 // scatter cursors of the grid build (the ring is idle then)
 
   for (;;) {
@@ -297,34 +362,39 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp_fused(const __grid_constant__
     fl_icp_result_t* res = A.results + h;
     const int status = A.hyps ? A.hyps[h].status : FL_OK;
     int n_ref = 0, n_mod = 0;
+    // phase clock (developer timeline, fl_profile): thread 0 charges the cycles since the last stamp to phase p
+    unsigned long long* trc = A.trace ? A.trace + (size_t)h * FL_ICP_TRACE_WORDS : nullptr;
+    long long t_last = trc ? clock64() : 0;
+    const long long t_begin = t_last;
+    auto TR = [&](int p) { if (trc && tid == 0) { const long long t = clock64(); trc[p] += (unsigned long long)(t - t_last); t_last = t; } };
+    if (trc && tid < FL_ICP_TRACE_WORDS) trc[tid] = 0;
 
     // ---- record-mode chain (centroids, covariance): warp 0 consumes, warps 1..ICP_NSTAGE stage, the rest wait at the barrier ----
     auto chain_records = [&](const float* pm, int n_m, const float* pr, int n_r, int n_cov) {
       const int n_steps = max(max(n_m, n_r), n_cov);
       const int bar_threads = 32 * (1 + ICP_NSTAGE);
       if (warp == 0) {
-        if (n_cov > 0) chain_consume<ICP_REC, ICP_CH, 2>(n_steps, s_stage, s_sum, bar_threads);
-        else chain_consume<6, ICP_CH, 2>(n_steps, s_stage, s_sum, bar_threads);
+        if (n_cov > 0) chain_consume<ICP_REC, ICP_CH, 2, ICP_RBUF, ICP_CHS>(n_steps, s_stage, s_sum, bar_threads, trc ? trc + 12 : nullptr, trc ? trc + 15 : nullptr);
+        else chain_consume<6, ICP_CH, 2, ICP_RBUF, ICP_CHS>(n_steps, s_stage, s_sum, bar_threads, trc ? trc + 12 : nullptr, trc ? trc + 15 : nullptr);
       } else if (warp <= ICP_NSTAGE) {
         const int k = tid - 32;                                     // record of the chunk this thread builds
         const int n_chunks = (n_steps + ICP_CH - 1) / ICP_CH;
-        const int ncol = n_cov > 0 ? ICP_REC : 6;
         for (int c = 0; c < n_chunks; ++c) {
           const int b = c & 1, i = c * ICP_CH + k;
           float m0 = 0.f, m1 = 0.f, m2 = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f;
           if (i < n_m || i < n_cov) { m0 = pm[3 * (size_t)i]; m1 = pm[3 * (size_t)i + 1]; m2 = pm[3 * (size_t)i + 2]; }
           if (i < n_r || i < n_cov) { r0 = pr[3 * (size_t)i]; r1 = pr[3 * (size_t)i + 1]; r2 = pr[3 * (size_t)i + 2]; }
           if (c >= 2) nb_sync(ICP_BAR_EMPTY(b), bar_threads);       // (the loads above are already in flight)
-          float* o = s_stage + (size_t)b * ICP_CH * ncol + k * ncol;
+          float* o = s_stage + (size_t)b * ICP_RBUF + k;            // column-major: column j of this record at o[j * ICP_CHS]
           const bool im = i < n_m, ir = i < n_r, ic = i < n_cov;
-          o[0] = im ? m0 : 0.f; o[1] = im ? m1 : 0.f; o[2] = im ? m2 : 0.f;
-          o[3] = ir ? r0 : 0.f; o[4] = ir ? r1 : 0.f; o[5] = ir ? r2 : 0.f;
+          o[0 * ICP_CHS] = im ? m0 : 0.f; o[1 * ICP_CHS] = im ? m1 : 0.f; o[2 * ICP_CHS] = im ? m2 : 0.f;
+          o[3 * ICP_CHS] = ir ? r0 : 0.f; o[4 * ICP_CHS] = ir ? r1 : 0.f; o[5 * ICP_CHS] = ir ? r2 : 0.f;
           if (n_cov > 0) {                                          // covariance += m * r^T (ICP.cpp:731-735): Matx product, s = 0 + a * b
             const float mm[3] = {m0, m1, m2}, rr[3] = {r0, r1, r2};
 #pragma unroll
             for (int a = 0; a < 3; ++a)
 #pragma unroll
-              for (int bb = 0; bb < 3; ++bb) o[6 + 3 * a + bb] = ic ? __fmul_rn(mm[a], rr[bb]) : 0.f;
+              for (int bb = 0; bb < 3; ++bb) o[(6 + 3 * a + bb) * ICP_CHS] = ic ? __fmul_rn(mm[a], rr[bb]) : 0.f;
           }
           nb_arrive(ICP_BAR_FULL(b), bar_threads);
         }
@@ -335,26 +405,54 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp_fused(const __grid_constant__
     // ---- distance pass (getL2distClouds, ICP.cpp:68-111), first half: every index pair valid in both clouds, its distance
     // (cv::norm(Vec3f): squares accumulate in double), inlier = dist <= thr.  The inlier distances go to dist[] (0 for everything
     // else: adding +0 leaves the running sum unchanged), the two integer counters are order free.  All threads. ----
-    auto distance_fill = [&](float thr) {
+    auto distance_fill = [&](float thr, bool xf) {                // xf: first move the model points by (s_Ropt, s_Topt): transformPoints in place (:756)
       if (tid < 2) s_cnt2[tid] = 0;
+      if (tid == 2) s_apx = 0.f;
       __syncthreads();
       int cnt = 0, nin = 0;
-      for (int i0 = 0; i0 < n_mod; i0 += ICP_NT) {
-        const int i = i0 + tid;
-        if (i < n_mod) {
-          float d_eff = 0.f;
-          const float rz = pref[3 * (size_t)i + 2], mz = tmp[3 * (size_t)i + 2];
-          if (pt_valid(rz) && pt_valid(mz)) {
-            const float dx = __fsub_rn(tmp[3 * (size_t)i], pref[3 * (size_t)i]), dy = __fsub_rn(tmp[3 * (size_t)i + 1], pref[3 * (size_t)i + 1]), dz = __fsub_rn(mz, rz);
-            const float d = (float)sqrt((double)dx * dx + (double)dy * dy + (double)dz * dz);
-            ++cnt;
-            if (d <= thr) { ++nin; d_eff = d; }
-          }
-          dist[i] = d_eff;
+      float part = 0.f;
+      auto one = [&](float rx, float ry, float rz, float mx, float my, float mz) {
+        float d_eff = 0.f;
+        if (pt_valid(rz) && pt_valid(mz)) {
+          const float dx = __fsub_rn(mx, rx), dy = __fsub_rn(my, ry), dz = __fsub_rn(mz, rz);
+          const float d = (float)sqrt((double)dx * dx + (double)dy * dy + (double)dz * dz);
+          ++cnt;
+          if (d <= thr) { ++nin; d_eff = d; part += d; }
         }
+        return d_eff;
+      };
+      float Ro[9], To[3];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) Ro[k] = xf ? s_Ropt[k] : 0.f;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) To[k] = xf ? s_Topt[k] : 0.f;
+      auto xform = [&](float& x, float& y, float& z) {
+        if (!pt_valid(z)) return;
+        const float p[3] = {x, y, z};
+        float o[3]; matvec3(Ro, p, o);
+        x = __fadd_rn(o[0], To[0]); y = __fadd_rn(o[1], To[1]); z = __fadd_rn(o[2], To[2]);
+      };
+      for (int i4 = 4 * tid; i4 + 4 <= n_mod; i4 += 4 * ICP_NT) {
+        const pts4 r = load_pts4(pref + 3 * (size_t)i4);
+        pts4 m = load_pts4(tmp + 3 * (size_t)i4);
+        if (xf) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) xform(m.x[k], m.y[k], m.z[k]);
+          store_pts4(tmp + 3 * (size_t)i4, m);
+        }
+        float4 d;
+        d.x = one(r.x[0], r.y[0], r.z[0], m.x[0], m.y[0], m.z[0]); d.y = one(r.x[1], r.y[1], r.z[1], m.x[1], m.y[1], m.z[1]);
+        d.z = one(r.x[2], r.y[2], r.z[2], m.x[2], m.y[2], m.z[2]); d.w = one(r.x[3], r.y[3], r.z[3], m.x[3], m.y[3], m.z[3]);
+        *reinterpret_cast<float4*>(dist + i4) = d;
+      }
+      for (int i = (n_mod & ~3) + tid; i < n_mod; i += ICP_NT) {
+        if (xf) xform(tmp[3 * (size_t)i], tmp[3 * (size_t)i + 1], tmp[3 * (size_t)i + 2]);
+        dist[i] = one(pref[3 * (size_t)i], pref[3 * (size_t)i + 1], pref[3 * (size_t)i + 2], tmp[3 * (size_t)i], tmp[3 * (size_t)i + 1], tmp[3 * (size_t)i + 2]);
       }
       cnt = __reduce_add_sync(0xffffffffu, cnt); nin = __reduce_add_sync(0xffffffffu, nin);
-      if (lane == 0 && (cnt | nin)) { atomicAdd(&s_cnt2[0], cnt); atomicAdd(&s_cnt2[1], nin); }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      if (lane == 0 && (cnt | nin)) { atomicAdd(&s_cnt2[0], cnt); atomicAdd(&s_cnt2[1], nin); atomicAdd(&s_apx, part); }
       __syncthreads();
     };
     // second half: warp 0 sums dist[] in order, warp 1 stages it through the ring; with `search`, the warps 2.. look up the
@@ -362,7 +460,9 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp_fused(const __grid_constant__
     auto distance_chain = [&](bool search, float bound2, const float4* gp, const grid_info gi) {
       const int bar_threads = 64;
       if (warp == 0) {
-        chain_consume<1, ICP_DCH, ICP_DNB>(n_mod, s_stage, s_sum, bar_threads);
+        const long long tc = trc ? clock64() : 0;
+        chain_consume<1, ICP_DCH, ICP_DNB, ICP_DCH, 0>(n_mod, s_stage, s_sum, bar_threads, trc ? trc + 13 : nullptr, trc ? trc + 16 : nullptr);
+        if (trc && tid == 0) trc[14] += (unsigned long long)(clock64() - tc);
       } else if (warp == 1) {
         const int n_chunks = (n_mod + ICP_DCH - 1) / ICP_DCH;
         for (int c = 0; c < n_chunks; ++c) {
@@ -381,7 +481,7 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp_fused(const __grid_constant__
       } else if (search) {
         for (int i = tid - 64; i < n_mod; i += ICP_NT - 64) {
           float best; int slot;
-          nn_query(gp, s_cs, gi, tmp[3 * (size_t)i], tmp[3 * (size_t)i + 1], tmp[3 * (size_t)i + 2], bound2, &best, &slot);
+          nn_query(gp, s_cs, s_zr, gi, tmp[3 * (size_t)i], tmp[3 * (size_t)i + 1], tmp[3 * (size_t)i + 2], bound2, &best, &slot);
           nn_d2[i] = best; nn_slot[i] = slot;
         }
       }
@@ -394,37 +494,76 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp_fused(const __grid_constant__
       __syncthreads();
     };
 
+    float mnx = FLT_MAX, mny = FLT_MAX, mxx = -FLT_MAX, mxy = -FLT_MAX;   // x/y bounding box of the reference cloud (this thread's share)
     // ---- prepare: back-project the two crops, keep pixel pairs valid in both (order preserved), centroid shift ----
     if (A.hyps) {
       if (status == FL_OK) {
         const fl_icp_hyp& hy = A.hyps[h];
         const fl_rect_t rr = hy.rect_ref, rm = hy.rect_model;
+        const uint16_t* __restrict__ mdepth = hy.model_depth;
         const int total = min(min(rr.width * rr.height, rm.width * rm.height), ws.max_pts);
         const float inv_fxr = __fdiv_rn(1.0f, A.Kr.fx), inv_fyr = __fdiv_rn(1.0f, A.Kr.fy);
         const float inv_fm = __fdiv_rn(1.0f, 608.0f);                // initInternalMat: fx = fy = 608, c = (320, 240) (common.cpp:358)
+        // Order-preserving compaction with ONE block scan per 32k pixels: every WARP owns a block of consecutive pixels and walks it
+        // 32 at a time (lane = pixel, so the depth loads and the point stores of a step are contiguous); pass 1 keeps one ballot per
+        // step (lane j holds the ballot of step j), the warp totals are scanned across the CTA, pass 2 back-projects the kept pairs
+        // and writes each at (warp base + kept pairs of the earlier steps + kept lanes below).  Validity depends on z alone.
+        auto z_valid = [](uint16_t dv) { return dv != 0 && pt_valid(__fmul_rn(__fmul_rn((float)dv, (float)(1 / 1000.0)), 1000.0f)); };
         int n = 0;
-        for (int c0 = 0; c0 < total; c0 += ICP_NT) {
-          const int i = c0 + tid;
-          float3 a = make_float3(0, 0, 0), b = make_float3(0, 0, 0);
-          int keep = 0;
-          if (i < total) {
-            const int ur = rr.x + i % rr.width, vr = rr.y + i / rr.width;
-            const int um = rm.x + i % rm.width, vm = rm.y + i / rm.width;
-            a = backproject_mm(A.ref_depth[(size_t)vr * A.W + ur], ur, vr, inv_fxr, inv_fyr, A.Kr.cx, A.Kr.cy);
-            b = backproject_mm(hy.model_depth[i], um, vm, inv_fm, inv_fm, 320.0f, 240.0f);
-            keep = (pt_valid(a.z) && pt_valid(b.z)) ? 1 : 0;         // paired matToVec, common.cpp:382-405
+        for (int base = 0; base < total; base += ICP_NT * 32) {
+          const int rem = min(total - base, ICP_NT * 32);
+          const int steps = ((rem + ICP_NWARPS - 1) / ICP_NWARPS + 31) >> 5;   // steps of 32 pixels per warp (<= 32)
+          const int w0 = base + warp * steps * 32, w1 = min(w0 + steps * 32, base + rem);
+          unsigned myb = 0;
+          int wcount = 0;
+          {
+            int i = w0 + lane, ur = i % rr.width, vr = i / rr.width;
+            for (int j0 = 0; j0 < steps; j0 += 8) {                   // eight steps at a time: their 16 loads are in flight together
+              uint16_t dr[8], dm[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const bool in = j0 + u < steps && i < w1;
+                dr[u] = in ? A.ref_depth[(size_t)(rr.y + vr) * A.W + rr.x + ur] : (uint16_t)0;
+                dm[u] = in ? mdepth[i] : (uint16_t)0;
+                i += 32; ur += 32;
+                while (ur >= rr.width) { ur -= rr.width; ++vr; }
+              }
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const unsigned bal = __ballot_sync(0xffffffffu, z_valid(dr[u]) && z_valid(dm[u]));
+                if (lane == j0 + u) myb = bal;
+                wcount += __popc(bal);
+              }
+            }
           }
           int tot;
-          const int pos = n + block_excl_scan(keep, s_warp, &tot);
-          if (keep) {
-            pref[3 * (size_t)pos] = a.x; pref[3 * (size_t)pos + 1] = a.y; pref[3 * (size_t)pos + 2] = a.z;
-            tmp[3 * (size_t)pos] = b.x; tmp[3 * (size_t)pos + 1] = b.y; tmp[3 * (size_t)pos + 2] = b.z;
+          int run = n + block_excl_scan(lane == 0 ? wcount : 0, s_warp, &tot);   // lane 0 of each warp carries the warp's total
+          run = __shfl_sync(0xffffffffu, run, 0);
+          {
+            int i = w0 + lane, ur = i % rr.width, vr = i / rr.width, um = i % rm.width, vm = i / rm.width;
+            for (int j = 0; j < steps; ++j) {
+              const unsigned bal = __shfl_sync(0xffffffffu, myb, j);
+              if ((bal >> lane) & 1u) {
+                const int pos = run + __popc(bal & ((1u << lane) - 1u));
+                const float3 a = backproject_mm(A.ref_depth[(size_t)(rr.y + vr) * A.W + rr.x + ur], rr.x + ur, rr.y + vr, inv_fxr, inv_fyr, A.Kr.cx, A.Kr.cy);
+                const float3 b = backproject_mm(mdepth[i], rm.x + um, rm.y + vm, inv_fm, inv_fm, 320.0f, 240.0f);   // paired matToVec, common.cpp:382-405
+                pref[3 * (size_t)pos] = a.x; pref[3 * (size_t)pos + 1] = a.y; pref[3 * (size_t)pos + 2] = a.z;
+                tmp[3 * (size_t)pos] = b.x; tmp[3 * (size_t)pos + 1] = b.y; tmp[3 * (size_t)pos + 2] = b.z;
+                mnx = fminf(mnx, a.x); mxx = fmaxf(mxx, a.x); mny = fminf(mny, a.y); mxy = fmaxf(mxy, a.y);
+              }
+              run += __popc(bal);
+              i += 32; ur += 32; um += 32;
+              while (ur >= rr.width) { ur -= rr.width; ++vr; }
+              while (um >= rm.width) { um -= rm.width; ++vm; }
+            }
           }
           n += tot;
         }
         n_ref = n_mod = n;
         __syncthreads();
+        TR(0);
         chain_records(tmp, n, pref, n, 0);                          // getMean x2 (detection.cpp:165-166)
+        TR(1);
         if (tid < 3) {
           const float mc = n > 0 ? __fdiv_rn(s_sum[tid], (float)n) : 0.f, rc = n > 0 ? __fdiv_rn(s_sum[3 + tid], (float)n) : 0.f;
           const float tt = __fsub_rn(rc, mc);                        // t_match_tmp = r_centroid - m_centroid (:177)
@@ -433,11 +572,17 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp_fused(const __grid_constant__
         }
         __syncthreads();
         const float t0 = s_tt[0], t1 = s_tt[1], t2 = s_tt[2];
-        for (int i = tid; i < n; i += ICP_NT) {                       // transformPoints(pts_mod, I, t_tmp) (:206)
-          if (!pt_valid(tmp[3 * (size_t)i + 2])) continue;
-          tmp[3 * (size_t)i] = __fadd_rn(tmp[3 * (size_t)i], t0); tmp[3 * (size_t)i + 1] = __fadd_rn(tmp[3 * (size_t)i + 1], t1);
-          tmp[3 * (size_t)i + 2] = __fadd_rn(tmp[3 * (size_t)i + 2], t2);
+        auto shift = [&](float& x, float& y, float& z) {             // transformPoints(pts_mod, I, t_tmp) (:206), then copyPoints (ICP.cpp:667)
+          if (pt_valid(z)) { x = __fadd_rn(x, t0); y = __fadd_rn(y, t1); z = __fadd_rn(z, t2); }
+          if (!pt_valid(z)) { x = 0.f; y = 0.f; z = 0.f; }            // a point pushed beyond the validity range is dropped by the copy
+        };
+        for (int i4 = 4 * tid; i4 + 4 <= n; i4 += 4 * ICP_NT) {
+          pts4 q = load_pts4(tmp + 3 * (size_t)i4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) shift(q.x[k], q.y[k], q.z[k]);
+          store_pts4(tmp + 3 * (size_t)i4, q);
         }
+        for (int i = (n & ~3) + tid; i < n; i += ICP_NT) shift(tmp[3 * (size_t)i], tmp[3 * (size_t)i + 1], tmp[3 * (size_t)i + 2]);
       }
     } else {
       n_ref = ws.n_ref[h]; n_mod = ws.n_mod[h];
@@ -458,10 +603,11 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp_fused(const __grid_constant__
     // ---- grid over the reference cloud (replaces the KD-tree build, ICP.cpp:650-659) ----
     const bool grid_in_smem = n_ref <= A.smem_pts;
     float4* gp = grid_in_smem ? s_gp : ws.grid_pts + (size_t)h * ws.max_pts;
-    float mnx = FLT_MAX, mny = FLT_MAX, mxx = -FLT_MAX, mxy = -FLT_MAX;
-    for (int i = tid; i < n_ref; i += ICP_NT) {
-      const float x = pref[3 * (size_t)i], y = pref[3 * (size_t)i + 1], z = pref[3 * (size_t)i + 2];
-      if (isfinite(x) && isfinite(y) && isfinite(z)) { mnx = fminf(mnx, x); mxx = fmaxf(mxx, x); mny = fminf(mny, y); mxy = fmaxf(mxy, y); }
+    if (!A.hyps) {                                                  // cloud mode: the bounding box was not collected while pairing
+      for (int i = tid; i < n_ref; i += ICP_NT) {
+        const float x = pref[3 * (size_t)i], y = pref[3 * (size_t)i + 1], z = pref[3 * (size_t)i + 2];
+        if (isfinite(x) && isfinite(y) && isfinite(z)) { mnx = fminf(mnx, x); mxx = fmaxf(mxx, x); mny = fminf(mny, y); mxy = fmaxf(mxy, y); }
+      }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -482,7 +628,7 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp_fused(const __grid_constant__
       for (int k = 0; k < 3; ++k) s_T[k] = 0.f;
     }
     __syncthreads();
-    const grid_info gi = s_gi;
+    grid_info gi = s_gi;
     for (int i = tid; i < n_ref; i += ICP_NT) {
       const float x = pref[3 * (size_t)i], y = pref[3 * (size_t)i + 1], z = pref[3 * (size_t)i + 2];
       if (isfinite(x) && isfinite(y) && isfinite(z)) atomicAdd(&s_cur[cell_of(y, gi.miny, gi.inv_cell) * FL_ICP_GRID + cell_of(x, gi.minx, gi.inv_cell)], 1);
@@ -507,13 +653,46 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp_fused(const __grid_constant__
         gp[slot] = make_float4(x, y, z, __int_as_float(i));
       }
     }
-    // ---- copyPoints(pts_model, pts_model_tmp) (ICP.cpp:667): invalid points become (0,0,0) ----
-    for (int i = tid; i < n_mod; i += ICP_NT)
-      if (!pt_valid(tmp[3 * (size_t)i + 2])) { tmp[3 * (size_t)i] = 0.f; tmp[3 * (size_t)i + 1] = 0.f; tmp[3 * (size_t)i + 2] = 0.f; }
+    // ---- copyPoints(pts_model, pts_model_tmp) (ICP.cpp:667): invalid points become (0,0,0) (detection mode: done with the shift) ----
+    if (!A.hyps)
+      for (int i = tid; i < n_mod; i += ICP_NT)
+        if (!pt_valid(tmp[3 * (size_t)i + 2])) { tmp[3 * (size_t)i] = 0.f; tmp[3 * (size_t)i + 1] = 0.f; tmp[3 * (size_t)i + 2] = 0.f; }
     __syncthreads();
+    {   // per-cell z range, quantised to 16 bits over the cloud's z extent with one step of slack on either side (4 cells per thread)
+      constexpr int PER = FL_ICP_CELLS / ICP_NT;
+      float zl[PER], zh[PER], gl = FLT_MAX, gh = -FLT_MAX;
+#pragma unroll
+      for (int k = 0; k < PER; ++k) {
+        zl[k] = FLT_MAX; zh[k] = -FLT_MAX;
+        for (int p = s_cs[tid * PER + k]; p < s_cs[tid * PER + k + 1]; ++p) { const float z = gp[p].z; zl[k] = fminf(zl[k], z); zh[k] = fmaxf(zh[k], z); }
+        gl = fminf(gl, zl[k]); gh = fmaxf(gh, zh[k]);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { gl = fminf(gl, __shfl_xor_sync(0xffffffffu, gl, o)); gh = fmaxf(gh, __shfl_xor_sync(0xffffffffu, gh, o)); }
+      if (lane == 0) { s_red[warp * 4] = gl; s_red[warp * 4 + 1] = gh; }
+      __syncthreads();
+      gl = s_red[0]; gh = s_red[1];
+      for (int w = 1; w < ICP_NWARPS; ++w) { gl = fminf(gl, s_red[w * 4]); gh = fmaxf(gh, s_red[w * 4 + 1]); }
+      const float zstep = fmaxf((gh - gl) / 65000.f, 1e-6f), inv_step = 1.0f / zstep;
+      if (tid == 0) { s_gi.z0 = gl; s_gi.zstep = zstep; }
+#pragma unroll
+      for (int k = 0; k < PER; ++k) {
+        unsigned q = 0xFFFFu;                                          // empty cell (never opened: its run is empty)
+        if (zl[k] <= zh[k]) {
+          const int lo = max((int)floorf((zl[k] - gl) * inv_step) - 1, 0), hi = min((int)ceilf((zh[k] - gl) * inv_step) + 1, 65535);
+          q = (unsigned)lo | ((unsigned)hi << 16);
+        }
+        s_zr[tid * PER + k] = q;
+      }
+    }
+    __syncthreads();
+    gi = s_gi;                                                      // now with the z quantisation
+    TR(2);
 
-    distance_fill(FLT_MAX);                                         // ICP.cpp:670
+    distance_fill(FLT_MAX, false);                                  // ICP.cpp:670
+    TR(3);
     distance_chain(false, 0.f, gp, gi);
+    TR(4);
     if (tid == 0) { s_dist_diff = FLT_MAX; s_iter = 0; }
     __syncthreads();
     bool have_nn = false;                                           // nn_slot / nn_d2 hold the neighbours of the current tmp[]
@@ -526,49 +705,80 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp_fused(const __grid_constant__
       __syncthreads();
       const int iter = s_iter;
       int n_cm, n_cr;
-      if (iter == 1) {                                              // :700-704 copies with invalid -> 0
-        for (int i = tid; i < n_ref; i += ICP_NT) {
-          const bool v = pt_valid(pref[3 * (size_t)i + 2]);
-          cor_r[3 * (size_t)i] = v ? pref[3 * (size_t)i] : 0.f; cor_r[3 * (size_t)i + 1] = v ? pref[3 * (size_t)i + 1] : 0.f; cor_r[3 * (size_t)i + 2] = v ? pref[3 * (size_t)i + 2] : 0.f;
-        }
-        for (int i = tid; i < n_mod; i += ICP_NT) {
-          const bool v = pt_valid(tmp[3 * (size_t)i + 2]);
-          cor_m[3 * (size_t)i] = v ? tmp[3 * (size_t)i] : 0.f; cor_m[3 * (size_t)i + 1] = v ? tmp[3 * (size_t)i + 1] : 0.f; cor_m[3 * (size_t)i + 2] = v ? tmp[3 * (size_t)i + 2] : 0.f;
+      const float* cm = cor_m; const float* cr = cor_r;
+      if (iter == 1) {                                              // :700-704: copies with invalid -> 0
+        // pts_model_tmp holds no invalid point any more (copyPoints zeroed them), so its copy IS tmp[]; the reference cloud of a
+        // detection() call holds only valid points too; a caller-supplied cloud may not, so cloud mode makes the copy
+        cm = tmp; cr = pref;
+        if (!A.hyps) {
+          for (int i = tid; i < n_ref; i += ICP_NT) {
+            const bool v = pt_valid(pref[3 * (size_t)i + 2]);
+            cor_r[3 * (size_t)i] = v ? pref[3 * (size_t)i] : 0.f; cor_r[3 * (size_t)i + 1] = v ? pref[3 * (size_t)i + 1] : 0.f; cor_r[3 * (size_t)i + 2] = v ? pref[3 * (size_t)i + 2] : 0.f;
+          }
+          cr = cor_r;
         }
         n_cm = n_mod; n_cr = n_ref;
       } else {                                                      // :708 -> PointsCorresponding :193-279
         const float thr = __fmul_rn(3.f, s_dist_mean);
         if (!have_nn) {                                             // (only when the overlapped search could not be used)
+          if (trc && tid == 0) trc[17] += 1;
           for (int i = tid; i < n_mod; i += ICP_NT) {
             float best; int slot;
-            nn_query(gp, s_cs, gi, tmp[3 * (size_t)i], tmp[3 * (size_t)i + 1], tmp[3 * (size_t)i + 2], thr, &best, &slot);
+            nn_query(gp, s_cs, s_zr, gi, tmp[3 * (size_t)i], tmp[3 * (size_t)i + 1], tmp[3 * (size_t)i + 2], thr, &best, &slot);
             nn_d2[i] = best; nn_slot[i] = slot;
           }
           __syncthreads();
         }
+        // order-preserving compaction of the accepted pairs, warp-aggregated like the pairing above (coalesced loads and stores)
         int n = 0;
-        for (int c0 = 0; c0 < n_mod; c0 += ICP_NT) {
-          const int i = c0 + tid;
-          int keep = 0, slot = -1;
-          if (i < n_mod) { slot = nn_slot[i]; keep = (slot >= 0 && nn_d2[i] <= thr) ? 1 : 0; }   // squared distance against un-squared 3*dist_mean (:268)
+        for (int base = 0; base < n_mod; base += ICP_NT * 32) {
+          const int rem = min(n_mod - base, ICP_NT * 32);
+          const int steps = ((rem + ICP_NWARPS - 1) / ICP_NWARPS + 31) >> 5;
+          const int w0 = base + warp * steps * 32, w1 = min(w0 + steps * 32, base + rem);
+          unsigned myb = 0;
+          int wcount = 0;
+          for (int j0 = 0; j0 < steps; j0 += 8) {
+            int sl[8]; float dd[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int i = w0 + (j0 + u) * 32 + lane;
+              const bool in = j0 + u < steps && i < w1;
+              sl[u] = in ? nn_slot[i] : -1; dd[u] = in ? nn_d2[i] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const unsigned bal = __ballot_sync(0xffffffffu, sl[u] >= 0 && dd[u] <= thr);   // squared distance against un-squared 3*dist_mean (:268)
+              if (lane == j0 + u) myb = bal;
+              wcount += __popc(bal);
+            }
+          }
           int tot;
-          const int pos = n + block_excl_scan(keep, s_warp, &tot);
-          if (keep) {
-            const float4 r = gp[slot];
-            cor_m[3 * (size_t)pos] = tmp[3 * (size_t)i]; cor_m[3 * (size_t)pos + 1] = tmp[3 * (size_t)i + 1]; cor_m[3 * (size_t)pos + 2] = tmp[3 * (size_t)i + 2];
-            cor_r[3 * (size_t)pos] = r.x; cor_r[3 * (size_t)pos + 1] = r.y; cor_r[3 * (size_t)pos + 2] = r.z;
+          int run = n + block_excl_scan(lane == 0 ? wcount : 0, s_warp, &tot);
+          run = __shfl_sync(0xffffffffu, run, 0);
+          for (int j = 0; j < steps; ++j) {
+            const unsigned bal = __shfl_sync(0xffffffffu, myb, j);
+            const int i = w0 + j * 32 + lane;
+            if ((bal >> lane) & 1u) {
+              const int pos = run + __popc(bal & ((1u << lane) - 1u));
+              const float4 r = gp[nn_slot[i]];
+              cor_m[3 * (size_t)pos] = tmp[3 * (size_t)i]; cor_m[3 * (size_t)pos + 1] = tmp[3 * (size_t)i + 1]; cor_m[3 * (size_t)pos + 2] = tmp[3 * (size_t)i + 2];
+              cor_r[3 * (size_t)pos] = r.x; cor_r[3 * (size_t)pos + 1] = r.y; cor_r[3 * (size_t)pos + 2] = r.z;
+            }
+            run += __popc(bal);
           }
           n += tot;
         }
         n_cm = n_cr = n;
       }
       __syncthreads();
+      TR(5);
       if (n_cr < 3 || n_cm < 3) {                                   // :711-715
         if (tid == 0) s_iter = A.prm.icp_it_thr;
         __syncthreads();
         continue;
       }
-      chain_records(cor_m, n_cm, cor_r, n_cr, n_cm);                // centroids + covariance chains (:722-735)
+      chain_records(cm, n_cm, cr, n_cr, n_cm);                      // centroids + covariance chains (:722-735)
+      TR(6);
       if (tid == 0) {
         float mc[3], rc[3], cov[9], rm[3];
         for (int k = 0; k < 3; ++k) { mc[k] = __fdiv_rn(s_sum[k], (float)n_cm); rc[k] = __fdiv_rn(s_sum[3 + k], (float)n_cr); }
@@ -581,29 +791,24 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp_fused(const __grid_constant__
         s_finite = fin;                                             // :748-749
       }
       __syncthreads();
+      TR(7);
       if (!s_finite) continue;                                      // (tmp[] unchanged: the neighbours found for it stay valid)
-      {
-        float Ro[9], To[3];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) Ro[k] = s_Ropt[k];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) To[k] = s_Topt[k];
-        for (int i = tid; i < n_mod; i += ICP_NT) {                 // transformPoints in place (:756)
-          float p[3] = {tmp[3 * (size_t)i], tmp[3 * (size_t)i + 1], tmp[3 * (size_t)i + 2]};
-          if (!pt_valid(p[2])) continue;
-          float o[3]; matvec3(Ro, p, o);
-#pragma unroll
-          for (int k = 0; k < 3; ++k) tmp[3 * (size_t)i + k] = __fadd_rn(o[k], To[k]);
-        }
-      }
+      TR(8);
       const float old_mean = s_dist_mean;
-      distance_fill(__fmul_rn(3.f, old_mean));                      // :778-780 (its first barrier also orders the transform before the search)
-      // The loop goes on only if dist_mean dropped by more than dist_diff_thr; with a non-negative threshold the next accept
-      // radius 3 * dist_mean is therefore below 3 * old_mean, which bounds the search that runs under the distance sum.
-      const bool more = iter < A.prm.icp_it_thr;
-      const float bound2 = A.prm.dist_diff_thr >= 0.f ? __fmul_rn(3.f, old_mean) : FLT_MAX;
+      distance_fill(__fmul_rn(3.f, old_mean), true);                // transformPoints (:756) fused with the distances (:778-780): one pass over the clouds
+      // The neighbour search of the next iteration runs under the distance sum, so its radius cannot use the exact new
+      // dist_mean yet: it uses an unordered (parallel) sum of the same distances, padded by 0.1 %; if the exact accept radius
+      // 3 * dist_mean turns out larger after all (it cannot, short of pathological rounding), the search is simply redone.
+      // The same estimate predicts whether the loop will go on at all (:684); a hypothesis that is about to stop is not searched
+      // for (if the exact sums disagree with the prediction, the search is done afterwards instead).
+      const float apx_mean = __fdiv_rn(s_apx, (float)max(s_cnt2[1], 1));
+      const bool more = iter < A.prm.icp_it_thr && apx_mean > A.prm.dist_mean_thr * 0.999f &&
+                        (old_mean - apx_mean) > A.prm.dist_diff_thr - 1e-3f * fabsf(old_mean);
+      const float bound2 = __fmul_rn(__fmul_rn(3.f, apx_mean), 1.001f);
+      TR(3);
       distance_chain(more, bound2, gp, gi);
-      have_nn = more;
+      TR(4);
+      have_nn = more && (__fmul_rn(3.f, s_dist_mean) <= bound2);
       if (tid == 0) {
         s_dist_diff = __fsub_rn(old_mean, s_dist_mean);
         float nT[3], nR[9];
@@ -628,6 +833,7 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp_fused(const __grid_constant__
       }
       r.dist_mean = s_dist_mean; r.inlier_ratio = s_ratio; r.iterations = s_iter; r.n_points = n_mod; r.status = FL_OK;
       *res = r;
+      if (trc) { trc[9] = (unsigned long long)(clock64() - t_begin); trc[10] = (unsigned long long)s_iter; trc[11] = (unsigned long long)n_mod; }
     }
     __syncthreads();
   }
@@ -635,25 +841,29 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp_fused(const __grid_constant__
 
 // dynamic shared memory of k_icp_fused for a batch whose largest cloud has max_pts points (0 grid points if they do not fit)
 static int icp_smem_plan(int max_pts, int* smem_pts) {
-  const int fixed = (FL_ICP_CELLS + 4) * 4 + ICP_STAGE_FLOATS * 4;
+  const int fixed = (FL_ICP_CELLS + 4) * 4 + FL_ICP_CELLS * 4 + ICP_STAGE_FLOATS * 4;
   const int avail = 227 * 1024 - 2048 - fixed;                      // 2 KB: the kernel's static shared memory
   *smem_pts = (max_pts * 16 <= avail) ? ((max_pts + 3) & ~3) : 0;
   return fixed + *smem_pts * 16;
 }
 
 int fl_launch_icp(fl_icp_ws ws, fl_icp_params_t p, const fl_icp_hyp* hyps_or_null, const uint16_t* ref_depth, int W, int H, fl_intrinsics_t K_ref,
-                  fl_icp_result_t* results, int* ticket, int n_sm, cudaStream_t s) {
+                  fl_icp_result_t* results, int* ticket, unsigned long long* trace, int n_sm, cudaStream_t s) {
   if (ws.n_hyp <= 0) return 0;
   fl_icp_args A;
-  A.ws = ws; A.prm = p; A.hyps = hyps_or_null; A.ref_depth = ref_depth; A.W = W; A.H = H; A.Kr = K_ref; A.results = results; A.ticket = ticket;
+  A.ws = ws; A.prm = p; A.hyps = hyps_or_null; A.ref_depth = ref_depth; A.W = W; A.H = H; A.Kr = K_ref; A.results = results; A.ticket = ticket; A.trace = trace;
   const int smem = icp_smem_plan(ws.max_pts, &A.smem_pts);
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return -1;
-  static int configured[64];                                        // per device: the attribute belongs to the (device, function) pair
-  if (dev < 0 || dev >= 64) return -1;
-  if (smem > configured[dev]) {
-    if (cudaFuncSetAttribute(k_icp_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
-    configured[dev] = smem;
+  if (dev < 0 || dev >= FL_MAX_DEVICES) return -1;
+  {   // the opt-in belongs to the (device, function) pair
+    static std::mutex mu;
+    static int configured[FL_MAX_DEVICES];
+    std::lock_guard<std::mutex> lk(mu);
+    if (smem > configured[dev]) {
+      if (cudaFuncSetAttribute(k_icp_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
+      configured[dev] = smem;
+    }
   }
   if (cudaMemsetAsync(ticket, 0, sizeof(int), s) != cudaSuccess) return -1;
   k_icp_fused<<<min(ws.n_hyp, n_sm), ICP_NT, smem, s>>>(A);

@@ -8,6 +8,7 @@
 // Byte-lane arithmetic: a template has <= 63 features per modality (CV_Assert :1137) and a response is <= 4, so four
 // packed u8 sums in one 32-bit register never carry across lanes (63*4 = 252): one IADD adds four cells.
 #include "fl_internal.cuh"
+#include <mutex>
 
 // ------------------------------------------------------------------------------------------------
 // per-geometry feature packing (runs once per frame size, not per frame)
@@ -396,11 +397,12 @@ __device__ __forceinline__ void sort_unique_body(fl_lists L, fl_xchg X, int key_
     const size_t block_recs = (size_t)X.cap + 1;
     const size_t parity_off = FL_XCHG_SIGNALS * sizeof(unsigned) + (size_t)(X.epoch & 1u) * X.world * block_recs * sizeof(fl_match_t);
     const int* src = reinterpret_cast<const int*>(X.local_block);
-    const int n_local = min(max(__ldcg(src), 0), X.cap);        // L2 loads: in the fused launch other CTAs have just refined these records
-    const int n_ints = 5 * (1 + n_local);                       // header record + live part of the list
+    const int n_raw = __ldcg(src);                              // L2 loads: in the fused launch other CTAs have just refined these records
+    const int n_local = min(max(n_raw, 0), X.cap);              // records that exist; the header keeps the RAW count so that every
+    const int n_ints = 5 * (1 + n_local);                       // rank (and the host) sees an overflow; readers clamp it to the capacity
     for (int p = 0; p < X.world; ++p) {
       int* dst = reinterpret_cast<int*>(X.peer[p] + parity_off + (size_t)X.rank * block_recs * sizeof(fl_match_t));
-      for (int i = tid; i < n_ints; i += blockDim.x) dst[i] = (i == 0) ? n_local : __ldcg(src + i);
+      for (int i = tid; i < n_ints; i += blockDim.x) dst[i] = (i == 0) ? n_raw : __ldcg(src + i);
     }
     __threadfence_system();
     __syncthreads();
@@ -721,14 +723,30 @@ __global__ void __launch_bounds__(1024) k_unique_big(const fl_sort_key* __restri
   if (tid == 0) *d_out_count = s_base;
 }
 
-// Host orchestration.  Scratch int (n_live of the big path) lives right after the key array.
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the (device, function) pair: it is set once per device this process
+// launches on (a process-wide flag would leave every device but the first without the opt-in), under a lock because handles
+// on different devices may be driven by different host threads.
+static bool fl_once_per_device(int which) {
+  static std::mutex mu;
+  static bool done[2][FL_MAX_DEVICES];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= FL_MAX_DEVICES) return false;
+  std::lock_guard<std::mutex> lk(mu);
+  if (done[which][dev]) return true;
+  const int bytes = SORT_SMEM_LARGE * (int)sizeof(fl_sort_key);
+  const cudaError_t e = which == 0 ? cudaFuncSetAttribute(k_sort_unique_small, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)
+                                   : cudaFuncSetAttribute(k_refine_sort<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return false;
+  done[which][dev] = true;
+  return true;
+}
+
+// Host orchestration.  Scratch int (n_live of the big path) lives right after the key array.  Return: launches made, -1 = launch error.
 int fl_launch_sort_unique(fl_lists L, fl_xchg X, int key_cap, fl_match_t* d_out, int out_cap, int* d_out_count, int* d_hdr,
                           int* h_hdr, fl_match_t* h_first, int h_first_cap, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) { cudaFuncSetAttribute(k_sort_unique_small, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM_LARGE * (int)sizeof(fl_sort_key)); configured = true; }
-  fl_launch_pdl(k_sort_unique_small, dim3(1), dim3(1024), (size_t)SORT_SMEM_LARGE * sizeof(fl_sort_key), s, L, X, key_cap, (int)SORT_SMEM_LARGE, d_out, out_cap,
-                d_out_count, d_hdr, h_hdr, h_first, h_first_cap);
-  return 1;
+  if (!fl_once_per_device(0)) return -1;
+  return fl_launch_pdl(k_sort_unique_small, dim3(1), dim3(1024), (size_t)SORT_SMEM_LARGE * sizeof(fl_sort_key), s, L, X, key_cap, (int)SORT_SMEM_LARGE, d_out,
+                       out_cap, d_out_count, d_hdr, h_hdr, h_first, h_first_cap) == cudaSuccess ? 1 : -1;
 }
 
 // small = true: one 256-thread group per CTA, 592 CTAs, shared memory for 1,024 keys + staging (no opt-in needed): as cheap
@@ -747,15 +765,12 @@ int fl_launch_refine_sort(fl_tdb db, const fl_refine_args& ra, float threshold, 
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = (fl_pdl_enabled() || pdl_refine) ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, k_refine_sort<1>, db, ra, threshold, cand, cap, d_count, done_ctr, L, X, key_cap, keys, d_out, out_cap, d_out_count, d_hdr, h_hdr, h_first,
-                       h_first_cap);
-    return 1;
+    return cudaLaunchKernelEx(&cfg, k_refine_sort<1>, db, ra, threshold, cand, cap, d_count, done_ctr, L, X, key_cap, keys, d_out, out_cap, d_out_count, d_hdr, h_hdr,
+                              h_first, h_first_cap) == cudaSuccess ? 1 : -1;
   }
-  static bool configured = false;
-  if (!configured) { cudaFuncSetAttribute(k_refine_sort<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM_LARGE * (int)sizeof(fl_sort_key)); configured = true; }
-  fl_launch_pdl(k_refine_sort<4>, dim3(n_sm > 0 ? n_sm : 148), dim3(4 * RF_THREADS), (size_t)SORT_SMEM_LARGE * sizeof(fl_sort_key), s, db, ra, threshold, cand, cap,
-                d_count, done_ctr, L, X, key_cap, (int)SORT_SMEM_LARGE, d_out, out_cap, d_out_count, d_hdr, h_hdr, h_first, h_first_cap);
-  return 1;
+  if (!fl_once_per_device(1)) return -1;
+  return fl_launch_pdl(k_refine_sort<4>, dim3(n_sm > 0 ? n_sm : 148), dim3(4 * RF_THREADS), (size_t)SORT_SMEM_LARGE * sizeof(fl_sort_key), s, db, ra, threshold, cand,
+                       cap, d_count, done_ctr, L, X, key_cap, (int)SORT_SMEM_LARGE, d_out, out_cap, d_out_count, d_hdr, h_hdr, h_first, h_first_cap) == cudaSuccess ? 1 : -1;
 }
 
 // second stage, only when the one-CTA kernel reported more records than its shared memory holds (the host has read the flag and the

@@ -27,6 +27,7 @@
 #include "fl_internal.cuh"
 #include "refine_warp.cuh"
 #include <stdlib.h>
+#include <mutex>
 
 #define SS_MAXF 64                      // feature words per template (<= 63 used)
 #define SS_MAX_PHASES 254
@@ -451,10 +452,16 @@ template <int NW, int TPW, int CL>
 static int launch_staged_cl(fl_tdb db, fl_level_geom g, const uint8_t* lm_level, float threshold, fl_match_t* cand, int cap, int* d_count,
                             fl_staged_plan plan, const fl_refine_args& ra, cudaStream_t s) {
   auto kern = k_similarity_staged<NW, TPW, CL>;
-  static size_t configured = 0;
-  if ((size_t)plan.smem_bytes > configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes) != cudaSuccess) return -1;
-    configured = plan.smem_bytes;
+  {   // the opt-in belongs to the (device, function) pair; per-device table, locked (handles on several devices / host threads)
+    static std::mutex mu;
+    static size_t configured[FL_MAX_DEVICES];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= FL_MAX_DEVICES) return -1;
+    std::lock_guard<std::mutex> lk(mu);
+    if ((size_t)plan.smem_bytes > configured[dev]) {
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes) != cudaSuccess) return -1;
+      configured[dev] = plan.smem_bytes;
+    }
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);

@@ -258,8 +258,14 @@ int64_t fl_launch_count(fl_handle* h);
 /* per-stage device timing of the last fl_match*(): ms for front end, global similarity, refinement, sort (needs fl_profile(h,1)) */
 int fl_profile(fl_handle* h, int enable);
 int fl_last_stage_ms(fl_handle* h, float out4[4]);
-/* device time (ms) of the two ICP kernels of the last fl_detection_batch / fl_detection (needs fl_profile(h,1)) */
+/* device time (ms) of the ICP launch of the last fl_detection_batch / fl_detection (needs fl_profile(h,1)) */
 int fl_last_icp_ms(fl_handle* h, float* ms);
+/* developer timeline of that launch (needs fl_profile(h,1)): 20 words per hypothesis, SM clock cycles spent in
+ * {0 pairing, 1 centroid sums, 2 shift + grid build, 3 distances, 4 distance sum (+ neighbour search), 5 correspondences,
+ *  6 centroid + covariance sums, 7 SVD, 8 transform, 9 whole hypothesis}, then {10 iterations, 11 points}, then cycles the ordered
+ *  sums waited for their stagers {12 record sums, 13 distance sums}, {14 distance sums without the overlapped search} and the cycles
+ *  inside the additions proper {15 record sums, 16 distance sums} */
+int fl_debug_icp_trace(fl_handle* h, uint64_t* out, int32_t n_hyp);
 
 #ifdef __cplusplus
 }

@@ -454,6 +454,32 @@ def test_fused_shard_exchange_in_one_launch_world1():
         assert len(want) > 0 and np.array_equal(h.match_fetch(), want), thr
 
 
+def test_exchange_block_overflow_is_reported():
+    """A rank that emits more candidates than its exchange block holds publishes the RAW count, so that the merged list is reported
+    as incomplete (FL_ERR_CAPACITY) instead of silently truncated (peer-memory path, world of one)."""
+    import torch
+    W, H, T = 640, 480, (5, 8)
+    b, d = synth.make_frame(W, H, 0)
+    det = _oracle(b, d, T)
+    q = [det.quantized(l, m) for l in range(2) for m in range(2)]
+    ts = synth.make_templates(500, W, H, T, n_classes=3, seed=51, quantized=q, planted_fraction=0.05)
+    det.set_templates(ts)
+    assert len(det.match(60.0, canonical=False)) > 8
+    h = fb.Handle(T, (0, 1), W, H)
+    h.upload_templates(ts)
+    cap = 8
+    xbuf = torch.zeros(int(fb.lib().fl_exchange_buffer_bytes(1, cap)), dtype=torch.uint8, device="cuda")
+    block = torch.zeros((cap + 1) * 5, dtype=torch.int32, device="cuda")
+    tb, td = torch.from_numpy(b).cuda(), torch.from_numpy(d.view(np.int16)).cuda()
+    h.match_shard_exchange_device_async(tb.data_ptr(), td.data_ptr(), W, H, 60.0, 0, 1, [xbuf.data_ptr()], cap, block.data_ptr(), 1)
+    h.match_wait()
+    with pytest.raises(fb.FealessError) as e:
+        h.match_fetch()
+    assert e.value.rc == fb.FL_ERR_CAPACITY
+    assert len(h.match_fetch(allow_truncated=True)) <= cap
+    h.close()
+
+
 def test_two_rank_gather_layout_on_one_gpu():
     """The multi-GPU data path with the collective replaced by a concatenation: two handles hold the two template shards,
     each writes its candidate block [header | records]; the blocks laid out as all_gather_into_tensor would lay them out
