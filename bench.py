@@ -15,8 +15,13 @@ similarity of every template at the coarsest level, local refinement of the cand
                copy of the frame and device->host read of the match list inside the timed region).
 * N > 1      : weak scaling, templates sharded (every rank holds 8,000 templates of an N x 8,000 set and sees the
                same frame), one NCCL all-gather of candidate blocks per frame, sort + unique on every rank.
-* ``--impl reference``: the reference's CPU path (the C restatement under oracle/, since the reference itself cannot be
-               built here) on the host cores, OpenMP over templates, same metric and workload.
+* ``--impl reference``: the reference's OWN CPU implementation: oracle/_ref/libfl_ref.so = /root/reference/linemod/linemod.cpp
+               compiled unmodified (oracle/build_ref.py), its real ``Detector::match`` on one host thread (the reference is
+               single-threaded), OpenCV's primitives supplied by the real cv2 of the image where importable.  Without the
+               prebuilt library: the C restatement under oracle/ with OpenMP over templates (``kind: port``).
+* every run of our arm checks, outside the timed region, that the match list of frame 0 equals the CPU arm's list.
+* ``--config C4|C5``: the strong-scaling pipeline benchmark (fixed template set sharded over the GPUs, match + exchange + ICP of
+               the top-5 hypotheses + NMS, frames/s); see run_pipeline.
 """
 from __future__ import annotations
 
@@ -40,6 +45,7 @@ CELLS = (W // 2 // T[1]) * (H // 2 // T[1])     # 40 x 30 = 1,200
 FRONT_END_BYTES = 5 * W * H + 2 * 8 * (W * H + (W // 2) * (H // 2))   # 7,680,000 B
 N_FRAMES = 8                    # distinct synthetic frames cycled through the steps
 METRIC = "template.px evals/s (LINE-MOD match, 640x480, 8k templates/GPU)"
+WORKLOAD = "C2: LINE-MOD match-only, 640x480, %d templates per GPU, L=2, T={5,8}, threshold 75"   # same string in both arms
 
 
 def load_peaks():
@@ -143,30 +149,77 @@ def cpu_time_frames(frames, tset, n_threads: int, steps: int, warmup: int):
     return times, n_matches
 
 
+def ref_time_frames(frames, tset, steps: int, warmup: int):
+    """The reference's own Detector::match (oracle/_ref) on one thread; returns (times, matches of the last frame, description)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import fl_ref_py as R
+    prims = "oracle/ref_shim's restated primitives"
+    try:
+        import cv2  # noqa: F401
+        R.install_cv2_hooks()
+        prims = "the image's real cv2 %s primitives (GaussianBlur, Sobel, phase, medianBlur, pyrDown, resize) through callbacks" % cv2.__version__
+    except Exception:  # noqa: BLE001
+        pass
+    det = R.Detector(T)
+    det.set_templates(tset)
+    times, last = [], None
+    for i in range(warmup + steps):
+        b, d = frames[i % len(frames)]
+        t0 = time.perf_counter()
+        rc, m = det.match_full(b, d, THRESHOLD)
+        t1 = time.perf_counter()
+        if rc != 0:
+            raise RuntimeError("reference Detector::match returned %d" % rc)
+        if i >= warmup:
+            times.append(t1 - t0)
+            last = m
+    R.remove_hooks()
+    return times, last, prims
+
+
+def match_list_sha(m) -> str:
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(m).tobytes()).hexdigest()[:16]
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import fl_oracle_py as F
+    import fl_ref_py as R
     frames, synth = make_inputs(args.templates)
     det = F.Detector(T)
     det.process(*frames[0])
     q = [det.quantized(l, m) for l in range(2) for m in range(2)]
     tset = synth.make_templates(args.templates, W, H, T, seed=1, quantized=q, planted_fraction=0.01)
-    cores = os.cpu_count() or 1
-    times, n_matches = cpu_time_frames(frames, tset, cores, args.steps, args.warmup)
+    cores_all = os.cpu_count() or 1
+    steps = args.steps
+    if R.available():
+        steps = min(args.steps, 60)                                      # ~0.12 s per step on one thread: bounded so the run ends within a minute
+        times, last, prims = ref_time_frames(frames, tset, steps, min(args.warmup, 3))
+        kind, cores, n_matches = "reference", 1, len(last)
+        sample = ("the reference's own Detector::match (linemod.cpp compiled unmodified, oracle/_ref) on ONE thread - its real execution "
+                  "model - over %d whole frames x all %d templates; OpenCV supplied by %s" % (steps, args.templates, prims))
+    else:
+        times, n_matches = cpu_time_frames(frames, tset, cores_all, steps, args.warmup)
+        kind, cores = "port", cores_all
+        sample = ("oracle/_ref not in this checkout: the C restatement, %d whole frames x all %d templates; front end single-threaded, "
+                  "matchClass OpenMP over templates" % (steps, args.templates))
     tot = float(np.sum(times))
-    evals = args.templates * CELLS * args.steps
-    v = evals / tot
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak",
+    v = args.templates * CELLS * steps / tot
+    # for context: the OpenMP restatement on every host core (NOT the reference's execution model)
+    pt, _ = cpu_time_frames(frames, tset, cores_all, 6, 2)
+    port_all = args.templates * CELLS * len(pt) / float(np.sum(pt))
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "evals/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * tot / steps, "ms_per_step_p50": 1e3 * float(np.median(times)),
+            "ms_per_step_p95": 1e3 * float(np.percentile(times, 95)), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "C2: LINE-MOD match-only, 640x480, %d templates, L=2, T={5,8}, threshold 75" % args.templates,
-                       "frames_per_s": args.steps / tot, "matches_last_frame": n_matches},
-            "cpu_baseline": {"value": v, "unit": "evals/s", "cores": cores, "kind": "port",
-                             "sample": "full workload, every step = one whole frame over all %d templates; front end single-threaded, "
-                                       "matchClass OpenMP over templates (the reference itself is single-threaded)" % args.templates},
+            "config": {"workload": WORKLOAD % args.templates, "frames_per_s": steps / tot, "matches_last_frame": n_matches},
+            "cpu_baseline": {"value": v, "unit": "evals/s", "cores": cores, "kind": kind, "sample": sample,
+                             "port_all_cores": {"value": port_all, "unit": "evals/s", "cores": cores_all,
+                                                "note": "C restatement with OpenMP over templates on every host core - not the reference's execution model"}},
             "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -283,6 +336,25 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms = float(t.item())
     n_matches = len(h.match_fetch()) if world == 1 else len(sm.fetch())
+    # ---- correctness, outside the timed region: the match list of frame 0 must equal the CPU arm's list (every rank holds the
+    # merged list; the CPU side is the C restatement over ALL n_total templates, OpenMP over templates, pinned bit for bit on
+    # the reference's own code by tests/test_oracle_ref.py) ----
+    step(0, False)
+    torch.cuda.synchronize()
+    got0 = h.match_fetch() if world == 1 else sm.fetch()
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import fl_oracle_py as F
+    odet = F.Detector(T)
+    odet.set_templates(tset)
+    odet.process(*frames[0])
+    want0 = odet.match(THRESHOLD, n_threads=os.cpu_count() or 1)
+    list_ok = len(got0) == len(want0) and bool(np.array_equal(got0, want0))
+    ok_t = torch.tensor([1 if list_ok else 0], device=dev)
+    if world > 1:
+        dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
+    if int(ok_t.item()) != 1:
+        raise SystemExit("bench.py: rank %d: the match list of frame 0 (%d records) differs from the CPU arm's (%d records)" % (rank, len(got0), len(want0)))
+    list_sha = match_list_sha(want0)
     evals_per_step = args.templates * world * CELLS
     # per-stage device times: a second, shorter pass with the library's own CUDA events between the stages (on its stream);
     # kept out of the headline loop because every event record costs the pipeline a few microseconds
@@ -371,10 +443,18 @@ def run_ours(args):
     # ---- CPU baseline (rank 0, N = 1 only): the C restatement, single thread = the reference's execution model ----
     cpu = None
     if world == 1 and not args.no_cpu:
-        ct, _ = cpu_time_frames(frames, tset, 1, 8, 2)
+        import fl_ref_py as R
+        if R.available():                                       # the reference's own Detector::match on one thread (its execution model)
+            ct, last, prims = ref_time_frames(frames, tset, 8, 2)
+            fi = (2 + 8 - 1) % len(frames)                       # the frame of the reference's last timed step
+            if set(map(tuple, last.tolist())) != set(map(tuple, h.match(frames[fi][0], frames[fi][1], THRESHOLD)[1].tolist())):   # (its std::unique may keep non-adjacent duplicates: compare as sets)
+                raise SystemExit("bench.py: the reference's own match list of frame %d differs from the GPU's" % fi)
+            kind, sample = "reference", "8 whole frames (after 2 warm-up), all %d templates, the reference's own Detector::match (oracle/_ref) on one thread; OpenCV = %s" % (args.templates, prims)
+        else:
+            ct, _ = cpu_time_frames(frames, tset, 1, 8, 2)
+            kind, sample = "port", "8 whole frames (after 2 warm-up) of the same workload, all %d templates, single thread (oracle/_ref not in this checkout)" % args.templates
         cv = args.templates * CELLS * len(ct) / float(np.sum(ct))
-        cpu = {"value": cv, "unit": "evals/s", "cores": 1, "kind": "port", "frames_per_s": len(ct) / float(np.sum(ct)),
-               "sample": "8 whole frames (after 2 warm-up) of the same workload, all %d templates, single thread" % args.templates}
+        cpu = {"value": cv, "unit": "evals/s", "cores": 1, "kind": kind, "frames_per_s": len(ct) / float(np.sum(ct)), "sample": sample}
 
     # ---- ICP (BASELINE configs[2], C3): 256 hypotheses x ~10k points, reported beside the headline ----
     icp = None
@@ -382,11 +462,13 @@ def run_ours(args):
         icp = bench_icp(h, synth, cpu=not args.no_cpu)
 
     line = {"metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms / args.steps, "ms_per_step_p50": float(np.median(per_step)), "ms_per_step_p90": float(np.percentile(per_step, 90)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "ms_per_step": dev_ms / args.steps, "ms_per_step_p50": float(np.median(per_step)), "ms_per_step_p90": float(np.percentile(per_step, 90)),
+            "ms_per_step_p95": float(np.percentile(per_step, 95)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
-            "config": {"workload": "C2: LINE-MOD match-only, 640x480, %d templates per GPU (%d total), L=2, T={5,8}, threshold 75" % (args.templates, n_total),
+            "config": {"workload": WORKLOAD % args.templates, "templates_total": n_total,
                        "l2": "flushed between steps (256 MB write)", "frames_per_s": args.steps / (dev_ms * 1e-3),
-                       "matches_last_frame": n_matches, "parallelism": ("template-sharded x%d, candidate exchange: %s" % (world, "peer-memory push fused into the sort kernel (NVLink)" if sm.exchange == "p2p" else "1 NCCL all-gather/frame")) if world > 1 else "single GPU"},
+                       "matches_last_frame": n_matches, "match_list_frame0": {"records": int(len(want0)), "sha256_16": list_sha,
+                                                                              "equals_cpu_arm": True}, "parallelism": ("template-sharded x%d, candidate exchange: %s" % (world, "peer-memory push fused into the sort kernel (NVLink)" if sm.exchange == "p2p" else "1 NCCL all-gather/frame")) if world > 1 else "single GPU"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "wall_s_timed_region": wall1 - wall0}
     line.update(extra)
@@ -395,8 +477,211 @@ def run_ours(args):
     if world == 1 and not args.no_icp:
         try:                                                    # a side measurement: it must never cost the headline line
             line["recognition"] = bench_recognition(synth, frames, q, cpu=not args.no_cpu)
+            # BASELINE.json's first metric, "frames/s (LINE-MOD match+ICP, 640x480)", on configs[0] (C1), host buffers in, poses out
+            line["frames_per_s_match_icp_640x480"] = {"value": line["recognition"]["frames_per_s"], "unit": "frames/s",
+                                                      "cpu_baseline": (line["recognition"].get("cpu_baseline") or {}).get("frames_per_s"),
+                                                      "workload": line["recognition"]["workload"]}
         except Exception as e:  # noqa: BLE001
             line["recognition"] = {"error": "%s: %s" % (type(e).__name__, e)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# strong-scaling pipeline benchmark: BASELINE.json configs[3] (C4) and configs[4] (C5)
+# ------------------------------------------------------------------------------------------------------------------
+PIPELINES = {
+    "C4": dict(W=1280, H=720, T=(5, 8), classes=15, per_class=2000,
+               desc="C4: full obj_reco_lmicp pipeline at 1280x720, 15 objects x 2,000 templates (fixed set, sharded over the GPUs), L=2, T={5,8}: "
+                    "match + candidate exchange + ICP of the top-5 hypotheses + NMS"),
+    "C5": dict(W=1920, H=1080, T=(5, 5, 5, 5), classes=16, per_class=2000,
+               desc="C5: stress, 1920x1080, 32,000 templates x 4 pyramid levels (fixed set, sharded over the GPUs), T={5,5,5,5}: "
+                    "match + candidate exchange + ICP of the top-5 hypotheses + NMS"),
+}
+TOP_K = 5
+
+
+def run_pipeline(args):
+    """Strong scaling: ONE fixed template set dealt over the ranks (gid % world), every rank sees the frame.  A step = one frame
+    through front end + matchClass on the local shard, the candidate exchange + merge (peer-memory push fused into the sort
+    kernel, or one NCCL all-gather), ICP of the top-5 matches dealt over the ranks (k % world) with one all-gather of the pose
+    records, and nonMaximumSuppression on every rank.  Timed on the device (CUDA events on the handle's stream bracket the whole
+    frame, host decisions included), max over ranks; frame resident in HBM, template depth crops resident (AddObj time)."""
+    import torch
+    import torch.distributed as dist
+    import fealess_b200 as fb
+    from fealess_b200 import sharded, synth
+
+    cfg = PIPELINES[args.config]
+    Wp, Hp, Tp = cfg["W"], cfg["H"], cfg["T"]
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - fealess_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_total = cfg["classes"] * cfg["per_class"]
+    L = len(Tp)
+    frames = [synth.make_frame(Wp, Hp, i) for i in range(2)]
+    cap = 4096
+    h = fb.Handle(Tp, (0, 1), Wp, Hp, max_candidates=max(1 << 16, world * (cap + 1) + 16), device=local)
+    h.upload_templates(synth.make_templates(0, Wp, Hp, Tp))
+    rc, _, q = h.match(frames[0][0], frames[0][1], THRESHOLD, want_quantized=True)
+    assert rc == 0
+    tset = synth.make_templates(n_total, Wp, Hp, Tp, n_classes=cfg["classes"], seed=1, quantized=q, planted_fraction=0.004)
+    sm = sharded.ShardedMatcher(h, tset, rank, world, capacity=cap, device=dev, exchange=args.exchange)
+    stream = sm.stream
+    # the templates' rendered depth crops stay on the device (AddObj time); the synthetic stand-in for a rendered view is frame 0's depth
+    hdr0 = tset.headers.reshape(n_total, L * 2, 7)[:, 0, :]
+    rects_model = np.stack([hdr0[:, 2], hdr0[:, 3], hdr0[:, 0], hdr0[:, 1]], axis=1).astype(np.int32)
+    h.upload_model_depths([frames[0][1]] * n_total, rects_model)
+    class_first = np.zeros(cfg["classes"], np.int64)
+    for c in range(cfg["classes"]):
+        class_first[c] = int(np.argmax(tset.class_of == c))
+    d_frames = [(torch.from_numpy(b).to(dev), torch.from_numpy(d.view(np.int16)).to(dev)) for b, d in frames]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    K = (608.0 * Wp / 640, 608.0 * Wp / 640, Wp / 2.0, Hp / 2.0)
+    torch.cuda.synchronize()
+    stamps = np.zeros(4)
+
+    def refine_top(matches, d_depth_ptr):
+        top = matches[:TOP_K]
+        n = len(top)
+        if n == 0:
+            return np.zeros(0, fb.ICP_RESULT_DTYPE), np.zeros(0, np.int32)
+        gidx = (class_first[top["class_idx"]] + top["template_id"]).astype(np.int64)
+        rr = np.stack([top["x"], top["y"], rects_model[gidx, 2], rects_model[gidx, 3]], axis=1).astype(np.int32)
+        P = tset.pose13[gidx][:, :12].reshape(n, 3, 4)
+        Rm, tm = np.ascontiguousarray(P[:, :, :3]), np.ascontiguousarray(P[:, :, 3])
+
+        def mine(idx):
+            return h.detection_batch_resident_device(d_depth_ptr, Wp, Hp, K, gidx[idx].astype(np.int32), rr[idx], Rm[idx], tm[idx])
+        res = sharded.refine_sharded(n, mine, rank, world, device=dev)
+        ok = np.nonzero(res["status"] == 0)[0]
+        keep = h.nms(res["T"][ok], res["n_points"][ok], res["dist_mean"][ok], 30.0) if len(ok) else np.zeros(0, np.int32)
+        return res, ok[keep] if len(ok) else keep
+
+    def step(i, timed):
+        tb, td = d_frames[i % len(d_frames)]
+        with torch.cuda.stream(stream):
+            flush.zero_()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+        t0 = time.perf_counter()
+        sm.match_device(tb.data_ptr(), td.data_ptr(), Wp, Hp, THRESHOLD)
+        m = sm.fetch()
+        t1 = time.perf_counter()
+        res, keep = refine_top(m, td.data_ptr())
+        t2 = time.perf_counter()
+        with torch.cuda.stream(stream):
+            e1.record(stream)
+        if timed:
+            stamps[0] += t1 - t0; stamps[1] += t2 - t1; stamps[2] += 1
+        return e0, e1, m, res, keep
+
+    for i in range(max(args.warmup, 3)):
+        step(i, False)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start_and_wait()
+    if world > 1:
+        dist.barrier()
+    launches0 = h.launch_count()
+    evs = []
+    for i in range(args.steps):
+        evs.append(step(i, True))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = h.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    per_step = np.array([a.elapsed_time(b) for a, b, *_ in evs])
+    t = torch.tensor([float(per_step.sum())], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    # ---- correctness outside the timed region: merged list of frame 0 == the CPU arm's list over ALL templates ----
+    _, _, got0, res0, keep0 = step(0, False)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import fl_oracle_py as F
+    odet = F.Detector(Tp)
+    odet.set_templates(tset)
+    odet.process(*frames[0])
+    want0 = odet.match(THRESHOLD, n_threads=os.cpu_count() or 1)
+    ok_t = torch.tensor([1 if (len(got0) == len(want0) and np.array_equal(got0, want0)) else 0], device=dev)
+    if world > 1:
+        dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
+    if int(ok_t.item()) != 1:
+        raise SystemExit("bench.py: rank %d: merged match list of frame 0 (%d) differs from the CPU arm's (%d)" % (rank, len(got0), len(want0)))
+    # ---- e2e: the frame starts in pinned host memory, the poses end on the host ----
+    pin = [(torch.from_numpy(b).pin_memory(), torch.from_numpy(d.view(np.int16)).pin_memory()) for b, d in frames]
+    tb, td = d_frames[0]
+    n_e2e = min(args.steps, 50)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    w0 = time.perf_counter()
+    for i in range(n_e2e):
+        pb, pd = pin[i % len(pin)]
+        with torch.cuda.stream(stream):
+            tb.copy_(pb, non_blocking=True); td.copy_(pd, non_blocking=True)
+        sm.match_device(tb.data_ptr(), td.data_ptr(), Wp, Hp, THRESHOLD)
+        m = sm.fetch()
+        res, keep = refine_top(m, td.data_ptr())
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    tt = torch.tensor([time.perf_counter() - w0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    fps = args.steps / (dev_ms * 1e-3)
+    cpu = None
+    if world == 1 and not args.no_cpu:                                   # one whole frame on one thread: the reference's own code when oracle/_ref is there
+        import fl_ref_py as R
+        use_ref = R.available()
+        t0 = time.perf_counter()
+        if use_ref:
+            try:
+                import cv2  # noqa: F401
+                R.install_cv2_hooks()
+            except Exception:  # noqa: BLE001
+                pass
+            rd = R.Detector(Tp)
+            rd.set_templates(tset)
+            t0 = time.perf_counter()
+            rc, ms = rd.match_full(frames[0][0], frames[0][1], THRESHOLD)
+        else:
+            odet.process(*frames[0]); ms = odet.match(THRESHOLD)
+        for mm in ms[:TOP_K]:
+            g = int(class_first[int(mm["class_idx"])] + int(mm["template_id"]))
+            P = tset.pose13[g][:12].reshape(3, 4)
+            (R if use_ref else F).detection(frames[0][1], frames[0][1], K, tuple(int(v) for v in rects_model[g]),
+                                            (int(mm["x"]), int(mm["y"]), int(rects_model[g][2]), int(rects_model[g][3])), r_match=P[:, :3], t_match=P[:, 3])
+        ct = time.perf_counter() - t0
+        if use_ref:
+            R.remove_hooks()
+        cpu = {"value": 1.0 / ct, "unit": "frames/s", "cores": 1, "kind": "reference" if use_ref else "port",
+               "sample": "ONE whole frame on one thread: %s over all %d templates + %d x detection()" % ("the reference's own Detector::match (oracle/_ref)" if use_ref else "the C restatement", n_total, min(TOP_K, len(ms)))}
+    line = {"metric": "frames/s (LINE-MOD match + top-%d ICP + NMS, %dx%d, %d templates sharded over the GPUs)" % (TOP_K, Wp, Hp, n_total),
+            "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
+            "ms_per_step_p50": float(np.median(per_step)), "ms_per_step_p95": float(np.percentile(per_step, 95)), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u8 (match) / f32 (ICP)", "data": "synthetic",
+            "config": {"workload": cfg["desc"], "templates_total": n_total, "templates_per_gpu": sm.n_local, "l2": "flushed between steps (256 MB write)",
+                       "evals_per_s": n_total * (Wp >> (L - 1)) // Tp[-1] * ((Hp >> (L - 1)) // Tp[-1]) * fps,
+                       "matches_frame0": int(len(got0)), "poses_frame0": int(len(keep0)), "match_list_frame0_equals_cpu_arm": True,
+                       "parallelism": ("template-sharded x%d (gid %% world), exchange: %s; ICP hypotheses k %% world, one all-gather of pose records" % (world, sm.exchange)) if world > 1 else "single GPU",
+                       "host_wall_ms_per_step_rank0": {"match_exchange_fetch": 1e3 * stamps[0] / max(stamps[2], 1), "icp_gather_nms": 1e3 * stamps[1] / max(stamps[2], 1)}},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": n_e2e / float(tt.item()), "unit": "frames/s", "h2d_bytes_per_step": Wp * Hp * 5, "d2h_bytes_per_step": 64 + 20 * int(len(m)) + 68 * TOP_K,
+                    "timer": "host wall clock, max over ranks; frame from pinned host memory, poses to the host"},
+            "roofline": None, "cpu_baseline": cpu}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -434,24 +719,40 @@ def bench_recognition(synth, frames, q, cpu: bool = True, n_templates: int = 200
     out.update({"workload": "C1: Recognition (match at 75 %% + ICP of the top-%d matches) on one 640x480 RGB-D frame, 1 object x %d templates, L=2, T={5,8}" % (top_k, n_templates),
                 "icp_path": r.last_icp_path,
                 "timer": "host wall clock around ObjRecoLmICP.Recognition (H2D of the frame, 3 match launches, 2 ICP launches, poses back), mean of %d calls" % n_timed})
-    if cpu:                                                    # the C restatement of the same call, one thread, 3 frames
+    if cpu:                                                    # the same call on one CPU thread, 3 frames: the reference's own code when oracle/_ref is there
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import fl_oracle_py as F
-        odet = F.Detector(T)
-        odet.set_templates(tset)
+        import fl_ref_py as R
+        use_ref = R.available()
         Kc = (608.0, 608.0, 320.0, 240.0)
+        if use_ref:
+            try:
+                import cv2  # noqa: F401
+                R.install_cv2_hooks()
+            except Exception:  # noqa: BLE001
+                pass
+            odet = R.Detector(T)
+        else:
+            odet = F.Detector(T)
+        odet.set_templates(tset)
         t0 = time.perf_counter()
         for _ in range(3):
-            odet.process(b, d)
-            ms = odet.match(THRESHOLD)
+            if use_ref:
+                rc, ms = odet.match_full(b, d, THRESHOLD)          # Detector::match (linemod.cpp:1356-1441)
+            else:
+                odet.process(b, d)
+                ms = odet.match(THRESHOLD)
             for m in ms[:top_k]:
                 hdr, _f = tset.template(int(m["template_id"]), 0, 0)
                 P = tset.pose13[int(m["template_id"])][:12].reshape(3, 4)
-                F.detection(d, d, Kc, (int(hdr[2]), int(hdr[3]), int(hdr[0]), int(hdr[1])), (int(m["x"]), int(m["y"]), int(hdr[0]), int(hdr[1])),
-                            r_match=P[:, :3], t_match=P[:, 3])
+                (R if use_ref else F).detection(d, d, Kc, (int(hdr[2]), int(hdr[3]), int(hdr[0]), int(hdr[1])), (int(m["x"]), int(m["y"]), int(hdr[0]), int(hdr[1])),
+                                                r_match=P[:, :3], t_match=P[:, 3])
         ct = (time.perf_counter() - t0) / 3
-        out["cpu_baseline"] = {"frames_per_s": 1.0 / ct, "cores": 1, "kind": "port",
-                               "sample": "3 whole frames: front end + matchClass over %d templates + %d ICPs each" % (n_templates, min(top_k, len(ms)))}
+        if use_ref:
+            R.remove_hooks()
+        out["cpu_baseline"] = {"frames_per_s": 1.0 / ct, "cores": 1, "kind": "reference" if use_ref else "port",
+                               "sample": "3 whole frames on one thread: %s over %d templates + %d x detection() each"
+                                         % ("the reference's own Detector::match (oracle/_ref, cv2 primitives)" if use_ref else "the C restatement's front end + matchClass", n_templates, min(top_k, len(ms)))}
     return out
 
 
@@ -487,6 +788,7 @@ def bench_icp(h, synth, n_hyp: int = 256, cpu: bool = True):
         res = h.detection_batch(ref, K, mds, rms, rrs, Rs, ts)
         times.append(time.perf_counter() - t0)
         dev.append(h.last_icp_ms())
+    trace = h.icp_trace(n_hyp).astype(np.float64)              # per-hypothesis phase clock of the fused launch (SM cycles)
     h.profile(False)
     # the same batch with the model crops resident on the device (uploaded once, as AddObj would): only the reference frame
     # and the hypothesis records are copied per call
@@ -509,16 +811,41 @@ def bench_icp(h, synth, n_hyp: int = 256, cpu: bool = True):
            "timer": "host wall clock around fl_detection_batch (includes H2D of crops and D2H of poses)",
            "batch_ms_resident_crops": 1e3 * float(np.min(times_res)),
            "icp_iters_per_s_resident_crops": its / float(np.min(times_res))}
+    # roofline of the ICP launch: 36 algorithmic bytes per model point and iteration (12 model + 12 matched
+    # reference + 12 index-paired reference).  The launch is NOT bandwidth bound - three serial fp32 sums per iteration that must
+    # round like the reference's loops set its floor - so the fraction is reported for completeness, next to the share of the
+    # hypothesis time spent inside those sums and in the neighbour search.
+    hbm_gbs, sm_mhz, peak_src = load_peaks()
+    alg = 36.0 * float((res["n_points"].astype(np.float64) * res["iterations"]).sum())
+    ach = alg / (float(np.min(dev)) * 1e-3) / 1e9
+    tot = max(float(trace[:, 9].sum()), 1.0)
+    out["roofline"] = {"kernel": "k_icp_fused (pairing + the whole icpCloudToCloud_Ex loop, one persistent launch)", "bound": "latency (ordered fp32 sums)",
+                       "achieved": ach, "peak": hbm_gbs, "unit": "GB/s", "frac": ach / hbm_gbs, "peak_source": peak_src + " MEASURED_PEAKS.json hbm_gbs (no L2 figure there)",
+                       "algorithmic_bytes_per_launch": alg, "traffic": None,
+                       "time_shares": {"ordered_sums": float((trace[:, 1] + trace[:, 6] + trace[:, 14]).sum() / tot),
+                                       "neighbour_search_beyond_the_distance_sum": float((trace[:, 4] - trace[:, 14]).sum() / tot),
+                                       "distances": float(trace[:, 3].sum() / tot), "pairing_and_grid": float((trace[:, 0] + trace[:, 2]).sum() / tot),
+                                       "correspondences_svd_rest": float((trace[:, 5] + trace[:, 7] + trace[:, 8]).sum() / tot)},
+                       "sm_time_us_per_hypothesis_mean": float(trace[:, 9].mean() / sm_mhz), "sm_time_us_per_iteration_mean": float((trace[:, 9] / np.maximum(trace[:, 10], 1)).mean() / sm_mhz),
+                       "ordered_sum_cycles_per_step": float(trace[:, 15].sum() / max(float(((1 + trace[:, 10]) * trace[:, 11]).sum()), 1.0))}
     if cpu:                                                    # CPU baseline leg: the C restatement of detection(), one thread, 8 hypotheses
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import fl_oracle_py as F
+        import fl_ref_py as R
+        use_ref = R.available()
+        cits = int(sum(res["iterations"][:8]))                 # (the reference's detection() does not report its iteration count; the poses are identical)
         t0 = time.perf_counter()
-        cits = 0
         for i in range(8):
-            cits += int(F.detection(mds[i], ref, K, rms[i], rrs[i], r_match=Rs[i], t_match=ts[i])["iterations"])
+            if use_ref:
+                rr_ = R.detection(mds[i], ref, K, rms[i], rrs[i], r_match=Rs[i], t_match=ts[i])
+                if not (np.array_equal(rr_["R"], res["R"][i].reshape(3, 3)) and np.array_equal(rr_["T"], res["T"][i])):
+                    raise RuntimeError("ICP pose %d differs from the reference's own detection()" % i)
+            else:
+                F.detection(mds[i], ref, K, rms[i], rrs[i], r_match=Rs[i], t_match=ts[i])
         ct = time.perf_counter() - t0
-        out["cpu_baseline"] = {"icp_iters_per_s": cits / ct, "hypotheses_per_s": 8 / ct, "cores": 1, "kind": "port",
-                               "sample": "the first 8 hypotheses of the same batch (KD-tree build + ICP loop each)"}
+        out["cpu_baseline"] = {"icp_iters_per_s": cits / ct, "hypotheses_per_s": 8 / ct, "cores": 1, "kind": "reference" if use_ref else "port",
+                               "sample": "the first 8 hypotheses of the same batch through %s (back-projection of both frames + KD-tree build + ICP loop each); poses compared bit for bit"
+                                         % ("the reference's own detection() (oracle/_ref)" if use_ref else "the C restatement")}
     return out
 
 
@@ -533,9 +860,15 @@ def main():
     ap.add_argument("--per-step", action="store_true", help="print the distribution of per-step device times of every rank to stderr")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-icp", action="store_true", help="skip the ICP side benchmark")
+    ap.add_argument("--config", default="C2", choices=["C2", "C4", "C5"], help="C2: the headline match-only benchmark (weak scaling); C4 / C5: the "
+                    "strong-scaling pipeline benchmark (fixed template set sharded over the GPUs, match + top-5 ICP + NMS, frames/s)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    if args.impl == "reference":
+    if args.config != "C2" and args.impl == "ours":
+        if args.steps == 500:
+            args.steps = 100
+        run_pipeline(args)
+    elif args.impl == "reference":
         run_reference(args)            # ~0.1 s per step on 8 host threads: the default run ends within seconds
     else:
         run_ours(args)

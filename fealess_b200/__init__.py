@@ -43,7 +43,7 @@ EXPORTED_SYMBOLS = [
     "fl_default_params", "fl_create", "fl_destroy", "fl_last_error", "fl_version", "fl_sync", "fl_stream",
     "fl_upload_templates", "fl_set_template_ids", "fl_num_templates", "fl_get_pose_info", "fl_match", "fl_match_device", "fl_match_device_async", "fl_match_wait", "fl_match_fetch",
     "fl_resize_linear", "fl_match_rescaled", "fl_match_shard_device", "fl_sort_unique_device", "fl_sort_unique_blocks_device", "fl_exchange_buffer_bytes", "fl_exchange_sort_unique_device", "fl_exchange_sort_unique_device_async", "fl_match_shard_exchange_device_async", "fl_depth_to_3d", "fl_icp_cloud_to_cloud_ex",
-    "fl_detection_batch", "fl_upload_model_depths", "fl_detection_batch_resident", "fl_detection", "fl_nms", "fl_nms_ex", "fl_debug_keep_spread", "fl_debug_force_baseline", "fl_debug_uses_staged", "fl_debug_get", "fl_debug_icp_trace", "fl_launch_count",
+    "fl_detection_batch", "fl_upload_model_depths", "fl_detection_batch_resident", "fl_detection_batch_resident_device", "fl_detection", "fl_nms", "fl_nms_ex", "fl_debug_keep_spread", "fl_debug_force_baseline", "fl_debug_uses_staged", "fl_debug_get", "fl_debug_icp_trace", "fl_launch_count",
     "fl_profile", "fl_last_stage_ms", "fl_last_icp_ms",
 ]
 
@@ -419,6 +419,20 @@ class Handle:
         _check(lib().fl_detection_batch_resident(self._h, _p(ref), C.c_size_t(stride), W, H, Intrinsics(*[float(v) for v in K_ref]), _p(idx),
                                                  _p(rr), _p(rmat), _p(tvec), n, IcpParams(icp_it_thr, dist_mean_thr, dist_diff_thr), _p(out)),
                "fl_detection_batch_resident")
+        return out[:n]
+
+    def detection_batch_resident_device(self, d_ref_depth: int, W: int, H: int, K_ref, model_index, rects_ref, r_match=None, t_match=None,
+                                        icp_it_thr=10, dist_mean_thr=0.5, dist_diff_thr=0.01) -> np.ndarray:
+        """fl_detection_batch_resident_device: the reference depth frame is a device pointer (dense W x H u16)."""
+        idx = np.ascontiguousarray(model_index, np.int32).reshape(-1)
+        n = len(idx)
+        rr = np.ascontiguousarray(rects_ref, np.int32).reshape(-1, 4)
+        rmat = None if r_match is None else np.ascontiguousarray(r_match, np.float32).reshape(-1, 9)
+        tvec = None if t_match is None else np.ascontiguousarray(t_match, np.float32).reshape(-1, 3)
+        out = np.zeros(max(n, 1), ICP_RESULT_DTYPE)
+        _check(lib().fl_detection_batch_resident_device(self._h, C.c_void_p(d_ref_depth), W, H, Intrinsics(*[float(v) for v in K_ref]), _p(idx),
+                                                        _p(rr), _p(rmat), _p(tvec), n, IcpParams(icp_it_thr, dist_mean_thr, dist_diff_thr), _p(out)),
+               "fl_detection_batch_resident_device")
         return out[:n]
 
     def nms(self, t3, n_model_pts, icp_dist, th_obj_dist) -> np.ndarray:

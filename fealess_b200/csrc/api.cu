@@ -1275,9 +1275,9 @@ extern "C" int fl_upload_model_depths(fl_handle* h, int32_t n_models, const uint
   return FL_OK;
 }
 
-extern "C" int fl_detection_batch_resident(fl_handle* h, const uint16_t* ref_depth, size_t ref_stride, int32_t W, int32_t H, fl_intrinsics_t K_ref,
-                                           const int32_t* model_index, const fl_rect_t* rect_ref, const float* r_match9, const float* t_match3,
-                                           int32_t n, fl_icp_params_t prm, fl_icp_result_t* out) {
+static int detection_batch_resident(fl_handle* h, const uint16_t* ref_depth, size_t ref_stride, const uint16_t* d_ref_given, int32_t W, int32_t H,
+                                    fl_intrinsics_t K_ref, const int32_t* model_index, const fl_rect_t* rect_ref, const float* r_match9,
+                                    const float* t_match3, int32_t n, fl_icp_params_t prm, fl_icp_result_t* out) {
   if (!h || !model_index || !rect_ref || !out || n < 0 || W <= 0 || H <= 0) return FL_ERR_ARG;
   if (n == 0) return FL_OK;
   if (!h->d_resident || h->res_W != W || h->res_H != H) { fl_set_error("no model depth crops uploaded for %d x %d frames (fl_upload_model_depths)", W, H); return FL_ERR_STATE; }
@@ -1291,8 +1291,8 @@ extern "C" int fl_detection_batch_resident(fl_handle* h, const uint16_t* ref_dep
     max_pts = std::max(max_pts, std::max(a.width * a.height, b.width * b.height));
   }
   TRY(icp_reserve(h, n, max_pts));
-  const uint16_t* d_ref = nullptr;
-  TRY(icp_ref_frame(h, ref_depth, ref_stride, W, H, &d_ref));
+  const uint16_t* d_ref = d_ref_given;
+  if (!d_ref) TRY(icp_ref_frame(h, ref_depth, ref_stride, W, H, &d_ref));
   for (int i = 0; i < n; ++i) {
     fl_icp_hyp& hy = h->h_hyps[i];
     hy.model_depth = h->d_resident + h->res_off[model_index[i]];
@@ -1300,6 +1300,19 @@ extern "C" int fl_detection_batch_resident(fl_handle* h, const uint16_t* ref_dep
     icp_fill_pose(hy, r_match9, t_match3, i);
   }
   return icp_run_batch(h, d_ref, W, H, K_ref, n, prm, out);
+}
+
+extern "C" int fl_detection_batch_resident(fl_handle* h, const uint16_t* ref_depth, size_t ref_stride, int32_t W, int32_t H, fl_intrinsics_t K_ref,
+                                           const int32_t* model_index, const fl_rect_t* rect_ref, const float* r_match9, const float* t_match3,
+                                           int32_t n, fl_icp_params_t prm, fl_icp_result_t* out) {
+  return detection_batch_resident(h, ref_depth, ref_stride, nullptr, W, H, K_ref, model_index, rect_ref, r_match9, t_match3, n, prm, out);
+}
+// the same with the reference depth frame ALREADY ON THE DEVICE (dense rows of W u16), e.g. the frame fl_match_device* was given
+extern "C" int fl_detection_batch_resident_device(fl_handle* h, const void* d_ref_depth, int32_t W, int32_t H, fl_intrinsics_t K_ref,
+                                                  const int32_t* model_index, const fl_rect_t* rect_ref, const float* r_match9,
+                                                  const float* t_match3, int32_t n, fl_icp_params_t prm, fl_icp_result_t* out) {
+  if (!d_ref_depth) return FL_ERR_ARG;
+  return detection_batch_resident(h, nullptr, 0, static_cast<const uint16_t*>(d_ref_depth), W, H, K_ref, model_index, rect_ref, r_match9, t_match3, n, prm, out);
 }
 
 extern "C" int fl_detection(fl_handle* h, const uint16_t* model_depth, size_t model_stride, const uint16_t* ref_depth, size_t ref_stride,

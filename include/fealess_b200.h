@@ -221,6 +221,11 @@ int fl_upload_model_depths(fl_handle* h, int32_t n_models, const uint16_t* const
 int fl_detection_batch_resident(fl_handle* h, const uint16_t* ref_depth, size_t ref_stride, int32_t W, int32_t H, fl_intrinsics_t K_ref,
                                 const int32_t* model_index, const fl_rect_t* rect_ref, const float* r_match9, const float* t_match3,
                                 int32_t n, fl_icp_params_t p, fl_icp_result_t* out);
+/* the same with the reference depth frame already on the device (dense rows of W u16; e.g. the frame given to fl_match_device*):
+ * nothing but the hypothesis records crosses PCIe (detection() of CadReco/obj_reco_lmicp.cpp:187-199 in a device-resident pipeline) */
+int fl_detection_batch_resident_device(fl_handle* h, const void* d_ref_depth, int32_t W, int32_t H, fl_intrinsics_t K_ref,
+                                       const int32_t* model_index, const fl_rect_t* rect_ref, const float* r_match9, const float* t_match3,
+                                       int32_t n, fl_icp_params_t p, fl_icp_result_t* out);
 /* single-hypothesis convenience with the reference's argument order (ICP/detection.h:9-11) */
 int fl_detection(fl_handle* h, const uint16_t* model_depth, size_t model_stride, const uint16_t* ref_depth, size_t ref_stride,
                  int32_t W, int32_t H, fl_intrinsics_t K_ref, fl_rect_t rect_model, fl_rect_t rect_ref,
