@@ -567,10 +567,12 @@ def run_pipeline(args):
         tb, td = d_frames[i % len(d_frames)]
         with torch.cuda.stream(stream):
             flush.zero_()
-            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); em = torch.cuda.Event(enable_timing=True)
             e0.record(stream)
         t0 = time.perf_counter()
         sm.match_device(tb.data_ptr(), td.data_ptr(), Wp, Hp, THRESHOLD)
+        with torch.cuda.stream(stream):
+            em.record(stream)                                         # the merged match list is complete on this rank
         m = sm.fetch()
         t1 = time.perf_counter()
         res, keep = refine_top(m, td.data_ptr())
@@ -579,7 +581,7 @@ def run_pipeline(args):
             e1.record(stream)
         if timed:
             stamps[0] += t1 - t0; stamps[1] += t2 - t1; stamps[2] += 1
-        return e0, e1, m, res, keep
+        return e0, e1, m, res, keep, em
 
     for i in range(max(args.warmup, 3)):
         step(i, False)
@@ -599,12 +601,13 @@ def run_pipeline(args):
     launches = h.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     per_step = np.array([a.elapsed_time(b) for a, b, *_ in evs])
-    t = torch.tensor([float(per_step.sum())], dtype=torch.float64, device=dev)
+    match_ms = float(np.sum([ev[0].elapsed_time(ev[5]) for ev in evs]))
+    t = torch.tensor([float(per_step.sum()), match_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms = float(t.item())
+    dev_ms, match_ms = float(t[0].item()), float(t[1].item())
     # ---- correctness outside the timed region: merged list of frame 0 == the CPU arm's list over ALL templates ----
-    _, _, got0, res0, keep0 = step(0, False)
+    _, _, got0, res0, keep0, _ = step(0, False)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import fl_oracle_py as F
     odet = F.Detector(Tp)
@@ -677,6 +680,9 @@ def run_pipeline(args):
                        "evals_per_s": n_total * (Wp >> (L - 1)) // Tp[-1] * ((Hp >> (L - 1)) // Tp[-1]) * fps,
                        "matches_frame0": int(len(got0)), "poses_frame0": int(len(keep0)), "match_list_frame0_equals_cpu_arm": True,
                        "parallelism": ("template-sharded x%d (gid %% world), exchange: %s; ICP hypotheses k %% world, one all-gather of pose records" % (world, sm.exchange)) if world > 1 else "single GPU",
+                       "match_exchange_ms_per_step": match_ms / args.steps, "match_exchange_frames_per_s": args.steps / (match_ms * 1e-3),
+                       "limiter": "ICP of the top-%d hypotheses: a hypothesis is three serial fp32 sums per iteration over its %s paired points (exactness), i.e. milliseconds for 100..200-pixel templates; "
+                                  "it does not shrink with more GPUs once every hypothesis has its own (%.2f of %.2f ms per frame here)" % (TOP_K, "15k..40k", (dev_ms - match_ms) / args.steps, dev_ms / args.steps),
                        "host_wall_ms_per_step_rank0": {"match_exchange_fetch": 1e3 * stamps[0] / max(stamps[2], 1), "icp_gather_nms": 1e3 * stamps[1] / max(stamps[2], 1)}},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": n_e2e / float(tt.item()), "unit": "frames/s", "h2d_bytes_per_step": Wp * Hp * 5, "d2h_bytes_per_step": 64 + 20 * int(len(m)) + 68 * TOP_K,
