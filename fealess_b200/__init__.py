@@ -45,6 +45,7 @@ EXPORTED_SYMBOLS = [
     "fl_resize_linear", "fl_match_rescaled", "fl_match_shard_device", "fl_sort_unique_device", "fl_sort_unique_blocks_device", "fl_exchange_buffer_bytes", "fl_exchange_sort_unique_device", "fl_exchange_sort_unique_device_async", "fl_match_shard_exchange_device_async", "fl_depth_to_3d", "fl_icp_cloud_to_cloud_ex",
     "fl_detection_batch", "fl_upload_model_depths", "fl_detection_batch_resident", "fl_detection_batch_resident_device", "fl_detection", "fl_nms", "fl_nms_ex", "fl_debug_keep_spread", "fl_debug_force_baseline", "fl_debug_uses_staged", "fl_debug_get", "fl_debug_icp_trace", "fl_launch_count",
     "fl_profile", "fl_last_stage_ms", "fl_last_icp_ms",
+    "fl_group_create", "fl_group_destroy", "fl_group_size", "fl_group_handle", "fl_group_upload_templates", "fl_group_match",
 ]
 
 
@@ -444,6 +445,60 @@ class Handle:
         if n < 0:
             _check(n, "fl_nms")
         return out[:n].copy()
+
+
+class Group:
+    """fl_group: Detector::match over N handles of this process (``devices`` may repeat a device), templates sharded gid % N."""
+
+    def __init__(self, devices: Sequence[int], T: Sequence[int] = (5, 8), modality_kind: Sequence[int] = (0, 1), max_width=640, max_height=480,
+                 exchange_capacity: int = 2048):
+        L = lib()
+        p = Params()
+        L.fl_default_params(C.byref(p))
+        p.n_levels = len(T)
+        for i, t in enumerate(T):
+            p.T[i] = int(t)
+        p.n_modalities = len(modality_kind)
+        for i, k in enumerate(modality_kind):
+            p.modality_kind[i] = int(k)
+        p.max_width, p.max_height = max_width, max_height
+        self._g = C.c_void_p()
+        dv = np.ascontiguousarray(devices, np.int32)
+        rc = L.fl_group_create(C.byref(p), _p(dv), len(dv), exchange_capacity, C.byref(self._g))
+        if rc != FL_OK:
+            self._g = None
+            raise FealessError(rc, "fl_group_create", L.fl_last_error().decode(errors="replace"))
+
+    def close(self):
+        if getattr(self, "_g", None):
+            lib().fl_group_destroy(self._g)
+            self._g = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def upload_templates(self, tset) -> None:
+        hdr = np.ascontiguousarray(tset.headers, np.int32)
+        ft = np.ascontiguousarray(tset.features, np.int32)
+        co = np.ascontiguousarray(tset.class_of, np.int32)
+        pose = np.ascontiguousarray(tset.pose13, np.float32)
+        _check(lib().fl_group_upload_templates(self._g, tset.n_templates, _p(hdr), _p(ft), ft.shape[0], _p(co), _p(pose)), "fl_group_upload_templates")
+
+    def match(self, bgr, depth, threshold: float, class_filter=None, capacity: int = 1 << 16):
+        H, W = depth.shape[:2]
+        b = np.ascontiguousarray(bgr, np.uint8)
+        d = np.ascontiguousarray(depth, np.uint16)
+        out = np.zeros(capacity, MATCH_DTYPE)
+        cnt = C.c_int32(0)
+        cf = None if not class_filter else np.ascontiguousarray(class_filter, np.int32)
+        rc = lib().fl_group_match(self._g, _p(b), C.c_size_t(W * 3), _p(d), C.c_size_t(W * 2), W, H, C.c_float(threshold), _p(cf),
+                                  0 if cf is None else int(cf.size), _p(out), capacity, C.byref(cnt))
+        if rc not in (FL_OK, FL_ERR_CAPACITY):
+            _check(rc, "fl_group_match")
+        return rc, out[:min(cnt.value, capacity)].copy()
 
 
 # --------------------------------------------------------------------------------------------------

@@ -226,6 +226,7 @@ extern "C" int fl_destroy(fl_handle* h) {
 extern "C" int fl_sync(fl_handle* h) { if (!h) return FL_ERR_ARG; FL_CUDA(cudaStreamSynchronize(h->stream)); return FL_OK; }
 extern "C" void* fl_stream(fl_handle* h) { return h ? (void*)h->stream : nullptr; }
 extern "C" int64_t fl_launch_count(fl_handle* h) { return h ? h->launches : 0; }
+int fl_entries_per_template(const fl_handle* h) { return h ? h->p.n_levels * h->p.n_modalities : 0; }
 extern "C" int fl_profile(fl_handle* h, int enable) { if (!h) return FL_ERR_ARG; h->profile = enable != 0; return FL_OK; }
 extern "C" int fl_last_icp_ms(fl_handle* h, float* ms) { if (!h || !ms) return FL_ERR_ARG; *ms = h->icp_ms; return FL_OK; }
 extern "C" int fl_debug_icp_trace(fl_handle* h, uint64_t* out, int32_t n_hyp) {

@@ -25,6 +25,7 @@ struct fl_level_geom {
 struct fl_sort_key { unsigned long long hi, lo; };
 
 void fl_set_error(const char* fmt, ...);
+int fl_entries_per_template(const fl_handle* h);   // n_levels * n_modalities of the handle (api.cu)
 
 // ---- programmatic dependent launch (PDL) -------------------------------------------------------------------------
 // Every kernel of the per-frame pipeline can be launched with cudaLaunchAttributeProgrammaticStreamSerialization: its CTAs

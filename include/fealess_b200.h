@@ -16,6 +16,7 @@
  *   fl_icp_cloud_to_cloud_ex ............. icpCloudToCloud_Ex ICP/ICP.h:165-172, ICP/ICP.cpp:617-809
  *   fl_detection / fl_detection_batch .... detection() ICP/detection.h:9-11, ICP/detection.cpp:11-254
  *   fl_nms ............................... nonMaximumSuppression ICP/NMS.h:14-16, ICP/NMS.cpp:6-39
+ *   fl_group_* ........................... the same Detector::match over N GPUs of one process (templates sharded)
  *   fl_debug_get ......................... stage-level exports for bit-exact parity checks (no reference equivalent)
  *
  * The library is CUDA-only (sm_100a): there is no CPU fallback; every call fails with FL_ERR_CUDA if no
@@ -176,6 +177,22 @@ int fl_match_shard_exchange_device_async(fl_handle* h, const void* d_bgr, const 
 /* enqueue-only half; finish with fl_match_wait */
 int fl_exchange_sort_unique_device_async(fl_handle* h, int32_t rank, int32_t world, void* const* peer_buffers, int32_t capacity,
                                          const fl_match_t* d_local_block, uint32_t epoch);
+
+/* ---- template-sharded matching over N handles of ONE process (no torch, no NCCL, no Python) ---------
+ * For a C++ host such as CObjRecoLmICP (CadReco/obj_reco_lmicp.cpp:86-204) that wants Detector::match spread over several GPUs:
+ * the group creates one handle per entry of `devices` (the same device may appear more than once), enables peer access between
+ * the devices, allocates every handle's exchange buffer and candidate block, deals the templates gid % n with their global
+ * per-class ids, and runs fl_match_shard_exchange_device_async on every handle per frame.  The merged list equals a single
+ * handle's list.  exchange_capacity = candidate records one handle may emit per frame (more -> FL_ERR_CAPACITY). */
+typedef struct fl_group fl_group;
+int fl_group_create(const fl_params_t* params, const int32_t* devices, int32_t n, int32_t exchange_capacity, fl_group** out);
+int fl_group_destroy(fl_group* g);
+int32_t fl_group_size(const fl_group* g);
+fl_handle* fl_group_handle(fl_group* g, int32_t i);          /* handle i (e.g. for fl_get_pose_info, fl_detection_batch*) */
+int fl_group_upload_templates(fl_group* g, int32_t n_templates, const fl_template_hdr_t* headers, const fl_feature_t* features,
+                              int32_t n_features, const int32_t* class_of, const float* pose13);   /* layout of fl_upload_templates */
+int fl_group_match(fl_group* g, const uint8_t* bgr, size_t bgr_stride, const uint16_t* depth, size_t depth_stride, int32_t W, int32_t H,
+                   float threshold, const int32_t* class_filter, int32_t n_filter, fl_match_t* out, int32_t capacity, int32_t* count);
 
 /* ---- input rescale (the caller's PrepareInputData) ------------------------------------------------- */
 enum { FL_IMG_8UC3 = 0, FL_IMG_16UC1 = 1 };

@@ -96,10 +96,18 @@ struct Match {
 
 class Detector {
  public:
-  Detector() : pyramid_levels(0), handle_(nullptr), dirty_(true), cap_w_(0), cap_h_(0) {}
+  Detector() : pyramid_levels(0), handle_(nullptr), group_(nullptr), xcap_(2048), dirty_(true), cap_w_(0), cap_h_(0) {}
   Detector(const std::vector<Ptr<Modality> >& modalities_, const std::vector<int>& T_pyramid)
-      : modalities(modalities_), pyramid_levels((int)T_pyramid.size()), T_at_level(T_pyramid), handle_(nullptr), dirty_(true), cap_w_(0), cap_h_(0) {}
-  ~Detector() { if (handle_) fl_destroy(handle_); }
+      : modalities(modalities_), pyramid_levels((int)T_pyramid.size()), T_at_level(T_pyramid), handle_(nullptr), group_(nullptr), xcap_(2048), dirty_(true), cap_w_(0), cap_h_(0) {}
+  ~Detector() { release_device(); }
+
+  // NOT in the reference: spread match() over several GPUs of this process.  The templates are dealt round-robin over one handle per
+  // entry of `devices` (fl_group_*: peer-memory candidate exchange inside the sort kernel, no NCCL / Python involved); match() returns
+  // the same list as on one GPU.  exchange_capacity = candidates one GPU may emit per frame.  Masks are not supported in this mode.
+  void useDevices(const std::vector<int>& devices, int exchange_capacity = 2048) {
+    release_device();
+    devices_ = devices; xcap_ = exchange_capacity; dirty_ = true; cap_w_ = cap_h_ = 0;
+  }
   Detector(const Detector&) = delete;
   Detector& operator=(const Detector&) = delete;
 
@@ -140,6 +148,7 @@ class Detector {
       for (int y = 0; y < H; ++y) std::memcpy(&mask_store[m][(size_t)y * W], k.ptr<uint8_t>(y), (size_t)W);
       mask_ptr[m] = mask_store[m].data(); any_mask = true;
     }
+    if (any_mask && devices_.size() > 1) throw cv::Exception("Detector::match: masks are not supported together with useDevices()");
     ensure_uploaded(W, H);
     // class filter: ids the detector does not know are ignored (:1425-1433)
     std::vector<int32_t> filter;
@@ -159,9 +168,18 @@ class Detector {
     }
     std::vector<fl_match_t> out(4096);
     int32_t count = 0;
-    int rc = fl_match(handle_, bgr, bgr_step, depth, depth_step, W, H, any_mask ? mask_ptr.data() : nullptr, threshold,
-                      filter.empty() ? nullptr : filter.data(), (int32_t)filter.size(), out.data(), (int32_t)out.size(), &count,
-                      qptr.empty() ? nullptr : qptr.data());
+    int rc;
+    if (group_) {                                                            // template-sharded over the GPUs of useDevices()
+      rc = fl_group_match(group_, bgr, bgr_step, depth, depth_step, W, H, threshold, filter.empty() ? nullptr : filter.data(), (int32_t)filter.size(),
+                          out.data(), (int32_t)out.size(), &count);
+      if (quantized_images.needed() && (rc == FL_OK || rc == FL_ERR_CAPACITY)) {   // the front end alone, on the first GPU
+        const int32_t none = -1; fl_match_t dummy; int32_t c2 = 0;
+        fealess_b200::check_status(fl_match(handle_, bgr, bgr_step, depth, depth_step, W, H, nullptr, 100.0f, &none, 1, &dummy, 1, &c2, qptr.data()), "Detector::match");
+      }
+    } else
+    rc = fl_match(handle_, bgr, bgr_step, depth, depth_step, W, H, any_mask ? mask_ptr.data() : nullptr, threshold,
+                  filter.empty() ? nullptr : filter.data(), (int32_t)filter.size(), out.data(), (int32_t)out.size(), &count,
+                  qptr.empty() ? nullptr : qptr.data());
     if (rc == FL_ERR_CAPACITY && count > (int32_t)out.size()) {             // more matches than the first buffer: fetch them all
       out.resize((size_t)count);
       rc = fl_match_fetch(handle_, out.data(), (int32_t)out.size(), &count);
@@ -183,6 +201,7 @@ class Detector {
     bool has_color = false, has_depth = false;
     for (size_t m = 0; m < modalities.size(); ++m) (modalities[m]->kind() == FL_MODALITY_COLOR_GRADIENT ? has_color : has_depth) = true;
     if ((has_color && !bgr) || (has_depth && !depth)) return -1;
+    if (devices_.size() > 1) throw cv::Exception("Detector::match_rescaled is not available together with useDevices()");
     ensure_uploaded(W, H);
     std::vector<fl_match_t> out(4096);
     int32_t count = 0;
@@ -239,7 +258,7 @@ class Detector {
   // create / grow the handle for this frame size and (re-)upload the flattened template database when it changed
   void ensure_uploaded(int W, int H) const {
     if (!handle_ || W > cap_w_ || H > cap_h_) {
-      if (handle_) { fl_destroy(handle_); handle_ = nullptr; }
+      release_device();
       fl_params_t p;
       fl_default_params(&p);
       p.n_levels = pyramid_levels;
@@ -253,7 +272,14 @@ class Detector {
       }
       p.max_width = std::max(W, cap_w_); p.max_height = std::max(H, cap_h_);
       p.device = fealess_b200::device_ordinal();
-      fealess_b200::check_status(fl_create(&p, &handle_), "fl_create");
+      if (devices_.size() > 1) {
+        std::vector<int32_t> dv(devices_.begin(), devices_.end());
+        fealess_b200::check_status(fl_group_create(&p, dv.data(), (int32_t)dv.size(), xcap_, &group_), "fl_group_create");
+        handle_ = fl_group_handle(group_, 0);                     // (owned by the group)
+      } else {
+        if (devices_.size() == 1) p.device = devices_[0];
+        fealess_b200::check_status(fl_create(&p, &handle_), "fl_create");
+      }
       cap_w_ = p.max_width; cap_h_ = p.max_height; dirty_ = true;
     }
     // host code that fills class_templates directly (the reference's readClass does) is caught by a template-count check
@@ -280,7 +306,8 @@ class Detector {
         class_of.push_back(ci);
       }
     }
-    fealess_b200::check_status(fl_upload_templates(handle_, (int32_t)class_of.size(), hdr.data(), feat.data(), (int32_t)feat.size(), class_of.data(), nullptr), "fl_upload_templates");
+    if (group_) fealess_b200::check_status(fl_group_upload_templates(group_, (int32_t)class_of.size(), hdr.data(), feat.data(), (int32_t)feat.size(), class_of.data(), nullptr), "fl_group_upload_templates");
+    else fealess_b200::check_status(fl_upload_templates(handle_, (int32_t)class_of.size(), hdr.data(), feat.data(), (int32_t)feat.size(), class_of.data(), nullptr), "fl_upload_templates");
     dirty_ = false;
   }
   // class filter named only unknown classes: nothing is matched, but the quantised images are still produced (:1411-1412)
@@ -306,7 +333,14 @@ class Detector {
 #endif
   }
 
+  void release_device() const {
+    if (group_) { fl_group_destroy(group_); group_ = nullptr; handle_ = nullptr; }
+    if (handle_) { fl_destroy(handle_); handle_ = nullptr; }
+  }
   mutable fl_handle* handle_;
+  mutable fl_group* group_;
+  std::vector<int> devices_;
+  int xcap_;
   mutable bool dirty_;
   mutable int cap_w_, cap_h_;
   mutable size_t uploaded_fingerprint_ = 0;

@@ -92,6 +92,72 @@ def test_cpp_mirror_matches_oracle(tmp_path):
     assert "all checks passed" in r.stdout
 
 
+def _case_file(tmp_path, n_templates=500, seed=33):
+    import fl_oracle_py as F
+    W, H, T = 640, 480, (5, 8)
+    b, d = synth.make_frame(W, H, 2)
+    det = F.Detector(T)
+    assert det.process(b, d) == 0
+    q = [det.quantized(l, m) for l in range(2) for m in range(2)]
+    ts = synth.make_templates(n_templates, W, H, T, n_classes=3, seed=seed, quantized=q, planted_fraction=0.05)
+    det.set_templates(ts)
+    thr = 70.0
+    exp = det.match(thr)
+    assert len(exp) > 0
+    blob = b"".join([
+        struct.pack("<ii", W, H), np.ascontiguousarray(b, np.uint8).tobytes(), np.ascontiguousarray(d, np.uint16).tobytes(),
+        struct.pack("<ii", 2, 2), np.asarray(T, np.int32).tobytes(),
+        struct.pack("<i", ts.n_templates), np.ascontiguousarray(ts.headers, np.int32).tobytes(),
+        struct.pack("<i", len(ts.features)), np.ascontiguousarray(ts.features, np.int32).tobytes(),
+        np.ascontiguousarray(ts.class_of, np.int32).tobytes(),
+        struct.pack("<fi", thr, len(exp)), np.ascontiguousarray(exp).tobytes()])
+    case = tmp_path / "group_case.bin"
+    case.write_bytes(blob)
+    return case, b, d, ts, exp, thr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("devices", ["0,0", "0,0,0", "0,1", "0,1,2,3"])
+def test_cpp_detector_over_several_gpus_of_one_process(tmp_path, devices):
+    """cup_linemod::Detector::useDevices -> fl_group_*: template-sharded match from C++ with no Python / torch / NCCL in the process
+    (CadReco/obj_reco_lmicp.cpp:86-204 must be able to use N GPUs).  "0,0": two handles on one GPU (runs on a one-GPU box); the
+    multi-device variants need that many GPUs."""
+    import torch
+    need = max(int(x) for x in devices.split(",")) + 1
+    if torch.cuda.device_count() < need:
+        pytest.skip("%d GPU(s) visible, the case needs %d" % (torch.cuda.device_count(), need))
+    fbuild.build()
+    os.makedirs(OUT_DIR, exist_ok=True)
+    exe = os.path.join(OUT_DIR, "group_test")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    r = subprocess.run([cxx, "-std=c++11", "-O1", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "group_test.cpp"),
+                        "-o", exe, fb.library_path(), "-Wl,-rpath," + os.path.dirname(fb.library_path())], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    case = _case_file(tmp_path)[0]
+    r = subprocess.run([exe, str(case), devices], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "all checks passed" in r.stdout
+
+
+@pytest.mark.gpu
+def test_group_binding_matches_oracle(tmp_path):
+    """fl_group_* through the ctypes binding, three handles on one GPU; an exchange block that is too small is reported."""
+    _, b, d, ts, exp, thr = _case_file(tmp_path, n_templates=700, seed=34)
+    g = fb.Group([0, 0, 0], exchange_capacity=1024)
+    g.upload_templates(ts)
+    for _ in range(3):
+        rc, got = g.match(b, d, thr)
+        assert rc == 0 and np.array_equal(got, exp)
+    rc, got = g.match(b, d, thr, class_filter=[2])
+    assert rc == 0 and np.array_equal(got, exp[exp["class_idx"] == 2])
+    g.close()
+    g = fb.Group([0, 0], exchange_capacity=4)
+    g.upload_templates(ts)
+    rc, got = g.match(b, d, 55.0)
+    assert rc == fb.FL_ERR_CAPACITY
+    g.close()
+
+
 def test_compat_headers_forward_to_the_mirror():
     """`#include "linemod_if.h"` / "detection.h" / "NMS.h" as CadReco writes them resolve to the mirror."""
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
