@@ -39,6 +39,19 @@ def model_depth_to_mm(depth_png: np.ndarray) -> np.ndarray:
     return np.clip(v, 0, 65535).astype(np.uint16)
 
 
+def select_hypotheses(matches, top_k: int = 1, per_class: bool = False):
+    """The matches that go to ICP, in list order: the first ``top_k``, or the first ``top_k`` of every class (test/linemod_acq.cpp:165-184)."""
+    top_k = max(1, int(top_k))
+    if not per_class:
+        return list(matches[:top_k])
+    taken, out = {}, []
+    for m in matches:
+        if taken.get(m.class_id, 0) < top_k:
+            taken[m.class_id] = taken.get(m.class_id, 0) + 1
+            out.append(m)
+    return out
+
+
 class ObjRecoLmICP:
     def __init__(self, device: int = 0, max_width: int = 640, max_height: int = 480):
         self.m_matching_threshold = 75.0                             # :52-55
@@ -107,8 +120,12 @@ class ObjRecoLmICP:
         return np.ascontiguousarray(rgb, np.uint8), np.ascontiguousarray(depth, np.uint16)
 
     # ---- Recognition ----
-    def Recognition(self, rgb: np.ndarray, depth: np.ndarray, K: dict, top_k: int = 1, th_obj_dist: Optional[float] = None):
-        """Returns (status, results); results = list of dicts {strObjTag, tWorld2Cam (4x4 fp32), similarity, template_id, icp}."""
+    def Recognition(self, rgb: np.ndarray, depth: np.ndarray, K: dict, top_k: int = 1, th_obj_dist: Optional[float] = None, per_class: bool = False):
+        """Returns (status, results); results = list of dicts {strObjTag, tWorld2Cam (4x4 fp32), similarity, template_id, icp}.
+
+        Hypotheses: the reference refines ``matches[0]`` only (obj_reco_lmicp.cpp:111) = the default ``top_k=1``; ``top_k`` takes the first
+        top_k matches of the sorted list, ``per_class=True`` the first top_k matches of EVERY class (top_k=1: the "best match per class"
+        walk of the reference's demo, test/linemod_acq.cpp:165-184); ``th_obj_dist`` (mm) runs nonMaximumSuppression over the refined objects."""
         from . import nonMaximumSuppression
         if self.m_lm_detector is None:
             return ERROR_INVALID_PARAM, []
@@ -129,7 +146,7 @@ class ObjRecoLmICP:
         if not matches:
             return 0, []
         hyps = []
-        for m in matches[:max(1, top_k)]:
+        for m in select_hypotheses(matches, top_k, per_class):
             tmpl = det.getTemplates(m.class_id, m.template_id)[0]            # current_template[0] (:111, :127-132)
             w, h, ox, oy = int(tmpl[0]), int(tmpl[1]), int(tmpl[2]), int(tmpl[3])
             md = self._model_depth.get((m.class_id, m.template_id))

@@ -228,6 +228,14 @@ class Detector {
   int addPoseInfo(const float* const pose_info) { TemplatePoseInfo.push_back(std::vector<float>(pose_info, pose_info + 13)); return (int)TemplatePoseInfo.size(); }
   std::vector<float> getPoseInfo(int template_id) { return TemplatePoseInfo.at((size_t)template_id); }
   int numPoseInfos() const { return (int)TemplatePoseInfo.size(); }   // mirror-only: lets writeLinemod stay inside the list
+  // mirror-only: the pose of template `template_id` of class `class_id`.  The flat list holds the classes one after the other when the
+  // detector came from a file (readClass appends class by class; notePoseOffset records where each class starts); without such a
+  // record this is the reference's flat lookup.
+  void notePoseOffset(const String& class_id) { pose_offset_[class_id] = TemplatePoseInfo.size(); }
+  std::vector<float> getPoseInfo(const String& class_id, int template_id) {
+    std::map<String, size_t>::const_iterator it = pose_offset_.find(class_id);
+    return TemplatePoseInfo.at((it == pose_offset_.end() ? 0 : it->second) + (size_t)template_id);
+  }
 
   const std::vector<Ptr<Modality> >& getModalities() const { return modalities; }
   int getT(int pyramid_level) const { return T_at_level[pyramid_level]; }
@@ -337,6 +345,7 @@ class Detector {
     if (group_) { fl_group_destroy(group_); group_ = nullptr; handle_ = nullptr; }
     if (handle_) { fl_destroy(handle_); handle_ = nullptr; }
   }
+  std::map<String, size_t> pose_offset_;
   mutable fl_handle* handle_;
   mutable fl_group* group_;
   std::vector<int> devices_;

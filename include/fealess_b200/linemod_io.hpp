@@ -329,6 +329,7 @@ inline std::string read_class(cup_linemod::Detector& det, const Node& fn) {
   const std::string class_id = fn["class_id"].string();
   if (det.numTemplates(class_id) != 0) throw cv::Exception("readClass: class '" + class_id + "' is already registered");
   const Node& tps = fn["template_pyramids"];
+  det.notePoseOffset(class_id);                                   // (mirror-only bookkeeping for getPoseInfo(class_id, template_id))
   for (size_t e = 0; e < tps.size(); ++e) {
     const Node& tp = tps.items[e];
     if (tp["template_id"].integer() != (int)e) throw cv::Exception("readClass: template_id == expected_id");

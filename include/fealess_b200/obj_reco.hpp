@@ -113,30 +113,68 @@ class CObjRecoLmICP : public CObjRecoCAD {
                                           m_proc_w, m_proc_h, m_matching_threshold, matches))
       return (int)ERROR_INVALID_PARAM;
     if (matches.empty()) return 0;
-    const cup_linemod::Match cur_match = matches[0];                                  // :111
-    const std::vector<cup_linemod::Template>& current_template = m_lm_detector->getTemplates(cur_match.class_id, cur_match.template_id);
-    fl_rect_t rect_ref = {current_template[0].offset_x + (cur_match.x - current_template[0].offset_x),   // :127-132
-                          current_template[0].offset_y + (cur_match.y - current_template[0].offset_y), current_template[0].width, current_template[0].height};
-    const std::vector<float> pose = m_lm_detector->getPoseInfo(cur_match.template_id);   // :140-150: rows of (R | t), then d_match
-    float r_match[9], t_match[3];
-    for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) r_match[3 * i + j] = pose[4 * i + j]; t_match[i] = pose[4 * i + 3]; }
+    // Hypothesis selection.  The reference refines matches[0] only (:111); its demo walks the sorted list and takes the best match of
+    // every class (test/linemod_acq.cpp:165-184).  m_top_k / m_per_class generalise both: the first m_top_k matches, or the first
+    // m_top_k matches of EVERY class, in list order.  The default (1, false) is the reference's behaviour.
+    std::vector<size_t> chosen;
+    if (!m_per_class) {
+      for (size_t i = 0; i < matches.size() && (int)chosen.size() < m_top_k; ++i) chosen.push_back(i);
+    } else {
+      std::map<cv::String, int> taken;
+      for (size_t i = 0; i < matches.size(); ++i)
+        if (taken[matches[i].class_id]++ < m_top_k) chosen.push_back(i);
+    }
     upload_crops();
-    std::map<std::pair<cv::String, int>, int>::const_iterator crop = m_crop_index.find(std::make_pair(cur_match.class_id, cur_match.template_id));
-    if (crop == m_crop_index.end()) return 0;                                         // no depth image for this template
+    std::vector<int32_t> index; std::vector<fl_rect_t> rect_ref; std::vector<float> r_match, t_match; std::vector<size_t> which;
+    for (size_t k = 0; k < chosen.size(); ++k) {
+      const cup_linemod::Match& cur_match = matches[chosen[k]];
+      const std::vector<cup_linemod::Template>& current_template = m_lm_detector->getTemplates(cur_match.class_id, cur_match.template_id);
+      std::map<std::pair<cv::String, int>, int>::const_iterator crop = m_crop_index.find(std::make_pair(cur_match.class_id, cur_match.template_id));
+      if (crop == m_crop_index.end()) continue;                                       // no depth image for this template
+      const fl_rect_t rr = {current_template[0].offset_x + (cur_match.x - current_template[0].offset_x),   // :127-132
+                            current_template[0].offset_y + (cur_match.y - current_template[0].offset_y), current_template[0].width, current_template[0].height};
+      // :140-150: rows of (R | t), then d_match.  The reference's single-hypothesis path looks the pose up by template_id alone (:140);
+      // the multi-hypothesis modes, which it does not have, key it by class as well
+      const std::vector<float> pose = (m_top_k == 1 && !m_per_class) ? m_lm_detector->getPoseInfo(cur_match.template_id)
+                                                                     : m_lm_detector->getPoseInfo(cur_match.class_id, cur_match.template_id);
+      for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) r_match.push_back(pose[4 * i + j]); }
+      for (int i = 0; i < 3; ++i) t_match.push_back(pose[4 * i + 3]);
+      index.push_back(crop->second); rect_ref.push_back(rr); which.push_back(chosen[k]);
+    }
+    if (index.empty()) return 0;
     const fl_intrinsics_t K = {(float)tCamIntrinsic.dFx, (float)tCamIntrinsic.dFy, (float)tCamIntrinsic.dCx, (float)tCamIntrinsic.dCy};   // the caller's (:188)
     const fl_icp_params_t prm = {m_icp_it_thr, m_dist_mean_thr, m_dist_diff_thr};
-    fl_icp_result_t res;
-    const int32_t index = crop->second;
-    fealess_b200::check_status(fl_detection_batch_resident(m_lm_detector->handle(), nullptr, 0, m_proc_w, m_proc_h, K, &index, &rect_ref, r_match, t_match, 1, prm, &res),
-                               "detection");
-    fealess_b200::check_status(res.status, "detection");
-    TObjRecoResult cur_result;
-    cur_result.strObjTag = cur_match.class_id;
-    for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) cur_result.tWorld2Cam[4 * i + j] = res.R[3 * i + j]; cur_result.tWorld2Cam[4 * i + 3] = res.T[i]; }   // Convert :20-30
-    cur_result.tWorld2Cam[12] = cur_result.tWorld2Cam[13] = cur_result.tWorld2Cam[14] = 0.f; cur_result.tWorld2Cam[15] = 1.f;
-    vtResult.push_back(cur_result);
+    std::vector<fl_icp_result_t> res(index.size());
+    fealess_b200::check_status(fl_detection_batch_resident(m_lm_detector->handle(), nullptr, 0, m_proc_w, m_proc_h, K, index.data(), rect_ref.data(), r_match.data(),
+                                                           t_match.data(), (int32_t)index.size(), prm, res.data()), "detection");
+    if (index.size() == 1) fealess_b200::check_status(res[0].status, "detection");   // the reference's single call throws on a box outside the frame (detection.cpp:43-44)
+    // objects that came out of ICP, in hypothesis order; nonMaximumSuppression (ICP/NMS.cpp:6-39) over them when a distance is set
+    std::vector<size_t> ok;
+    for (size_t k = 0; k < res.size(); ++k) if (res[k].status == FL_OK) ok.push_back(k);
+    std::vector<size_t> keep = ok;
+    if (m_th_obj_dist > 0.f && ok.size() > 1) {
+      std::vector<float> t3, dist; std::vector<int32_t> npts, out_idx(ok.size());
+      for (size_t k = 0; k < ok.size(); ++k) { for (int i = 0; i < 3; ++i) t3.push_back(res[ok[k]].T[i]); npts.push_back(res[ok[k]].n_points); dist.push_back(res[ok[k]].dist_mean); }
+      const int n_keep = fl_nms(m_lm_detector->handle(), t3.data(), npts.data(), dist.data(), (int32_t)ok.size(), m_th_obj_dist, out_idx.data());
+      if (n_keep < 0) fealess_b200::check_status(n_keep, "nonMaximumSuppression");
+      keep.clear();
+      for (int k = 0; k < n_keep; ++k) keep.push_back(ok[(size_t)out_idx[k]]);
+    }
+    for (size_t k = 0; k < keep.size(); ++k) {
+      const fl_icp_result_t& r = res[keep[k]];
+      TObjRecoResult cur_result;
+      cur_result.strObjTag = matches[which[keep[k]]].class_id;
+      for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) cur_result.tWorld2Cam[4 * i + j] = r.R[3 * i + j]; cur_result.tWorld2Cam[4 * i + 3] = r.T[i]; }   // Convert :20-30
+      cur_result.tWorld2Cam[12] = cur_result.tWorld2Cam[13] = cur_result.tWorld2Cam[14] = 0.f; cur_result.tWorld2Cam[15] = 1.f;
+      vtResult.push_back(cur_result);
+    }
     return 0;
   }
+
+  // NOT in the reference (its Recognition refines matches[0] only): how many hypotheses go to ICP - the first top_k matches, or the
+  // first top_k of every class (per_class; top_k = 1 is the "best match per class" walk of test/linemod_acq.cpp:165-184) - and the
+  // distance (mm) under which nonMaximumSuppression merges refined objects (0 = no suppression).
+  void SetHypotheses(int top_k, bool per_class = false, float th_obj_dist = 0.f) { m_top_k = top_k < 1 ? 1 : top_k; m_per_class = per_class; m_th_obj_dist = th_obj_dist; }
 
   // mirror-only accessors (tests, callers that want the zoomed intrinsics PrepareInputData stored)
   const TCamIntrinsicParam& processingIntrinsics() const { return m_tCamParam; }
@@ -215,6 +253,7 @@ class CObjRecoLmICP : public CObjRecoCAD {
   std::map<int, ModelDepth> m_model_depth;                       // template_id -> rendered depth in mm
   std::map<std::pair<cv::String, int>, int> m_crop_index;        // (class, template_id) -> crop on the device
   int m_crops_w, m_crops_h;
+  int m_top_k = 1; bool m_per_class = false; float m_th_obj_dist = 0.f;   // SetHypotheses
 };
 
 inline CObjRecoCAD* CObjRecoCAD::Create(EObjRecoType eType) { return eType == EObjReco_LmICP ? new CObjRecoLmICP() : nullptr; }   // obj_reco_temp.cpp:13-30

@@ -4,6 +4,7 @@
 //   reco_test badparams <dir>            Recognition argument checks                                 (no GPU)
 //   reco_test run <dir> <frame.bin>...   Create -> AddObj -> Recognition per frame; frame.bin = int32 W, H, double fx, fy, cx, cy, BGR bytes, depth u16
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -57,10 +58,14 @@ int main(int argc, char** argv) {
       CObjRecoCAD::Destroy(reco);
       return 0;
     }
-    if (argc >= 4 && !std::strcmp(argv[1], "run")) {
+    // run <dir> <frame.bin>...            the reference's behaviour: ICP of matches[0]
+    // hyp <dir> <top_k> <per_class> <th_obj_dist> <frame.bin>...   SetHypotheses: top-K / per-class selection + nonMaximumSuppression
+    const bool hyp_mode = argc >= 7 && !std::strcmp(argv[1], "hyp");
+    if ((argc >= 4 && !std::strcmp(argv[1], "run")) || hyp_mode) {
       CObjRecoCAD* reco = CObjRecoCAD::Create(CObjRecoCAD::EObjReco_LmICP);
       std::printf("addobj %08x\n", (unsigned)reco->AddObj(argv[2]));
-      for (int a = 3; a < argc; ++a) {
+      if (hyp_mode) static_cast<CObjRecoLmICP*>(reco)->SetHypotheses(std::atoi(argv[3]), std::atoi(argv[4]) != 0, (float)std::atof(argv[5]));
+      for (int a = hyp_mode ? 6 : 3; a < argc; ++a) {
         FILE* f = std::fopen(argv[a], "rb");
         if (!f) { std::printf("cannot open %s\n", argv[a]); return 2; }
         int wh[2]; double k[4];
@@ -73,7 +78,7 @@ int main(int argc, char** argv) {
         std::vector<TObjRecoResult> res;
         for (int rep = 0; rep < 2; ++rep) {                        // twice: the second call finds the crops already on the device
           const int rc = reco->Recognition(tRGB, tDepth, K, res);
-          std::printf("frame %d status %08x results %zu", a - 3, (unsigned)rc, res.size());
+          std::printf("frame %d status %08x results %zu", a - (hyp_mode ? 6 : 3), (unsigned)rc, res.size());
           for (size_t i = 0; i < res.size(); ++i) {
             std::printf(" %s", res[i].strObjTag.c_str());
             for (int j = 0; j < 16; ++j) { unsigned u; std::memcpy(&u, &res[i].tWorld2Cam[j], 4); std::printf(" %08x", u); }
@@ -91,6 +96,6 @@ int main(int argc, char** argv) {
     std::printf("exception: %s\n", e.what());
     return 4;
   }
-  std::printf("usage: reco_test png <file> | addobj <dir> | badparams <dir> | run <dir> <frame.bin>...\n");
+  std::printf("usage: reco_test png <file> | addobj <dir> | badparams <dir> | run <dir> <frame.bin>... | hyp <dir> <top_k> <per_class> <th_obj_dist> <frame.bin>...\n");
   return 2;
 }

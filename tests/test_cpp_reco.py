@@ -137,3 +137,34 @@ def test_cpp_recognition_equals_python_mirror(exe, tmp_path):
         assert rc == 0 and len(res) == 1 and py.last_icp_path == "resident"
         want = "frame %d status 00000000 results 1 %s %s" % (i, res[0]["strObjTag"], " ".join("%08x" % v for v in res[0]["tWorld2Cam"].reshape(-1).view(np.uint32)))
         assert lines[1 + 2 * i] == want and lines[2 + 2 * i] == want
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("top_k,per_class,th", [(4, False, 0.0), (1, True, 0.0), (2, True, 25.0), (6, False, 40.0)])
+def test_cpp_multi_hypothesis_equals_python_mirror(exe, tmp_path, top_k, per_class, th):
+    """top-K / best-per-class selection (test/linemod_acq.cpp:165-184) + nonMaximumSuppression wiring
+    (ICP/NMS.cpp:6-39), C++ CObjRecoLmICP::SetHypotheses == the Python mirror, pose for pose and bit for bit."""
+    import fl_oracle_py as F
+    W, H, T = 640, 480, (5, 8)
+    b, d = synth.make_frame(W, H, 0)
+    det = F.Detector(T)
+    assert det.process(b, d) == 0
+    q = [det.quantized(l, m) for l in range(2) for m in range(2)]
+    ts = synth.make_templates(36, W, H, T, n_classes=3, seed=62, quantized=q, planted_fraction=0.5)
+    _feature_dir(tmp_path, ts, d)
+    K = (608.0, 608.0, 320.0, 240.0)
+    _write_frame(str(tmp_path / "frame0.bin"), b, d, K)
+    r = subprocess.run([exe, "hyp", str(tmp_path), str(top_k), "1" if per_class else "0", str(th), str(tmp_path / "frame0.bin")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = r.stdout.strip().split("\n")
+    py = reco.ObjRecoLmICP()
+    assert py.AddObj(str(tmp_path)) == 0
+    rc, res = py.Recognition(b, d, dict(fx=K[0], fy=K[1], cx=K[2], cy=K[3], width=W, height=H), top_k=top_k, per_class=per_class,
+                             th_obj_dist=th if th > 0 else None)
+    assert rc == 0 and len(res) >= 1
+    if per_class and th == 0:
+        tags = [x["strObjTag"] for x in res]
+        assert all(tags.count(t) <= top_k for t in set(tags)) and len(set(tags)) > 1
+    want = "frame 0 status 00000000 results %d" % len(res) + "".join(
+        " %s %s" % (x["strObjTag"], " ".join("%08x" % v for v in x["tWorld2Cam"].reshape(-1).view(np.uint32))) for x in res)
+    assert lines[1] == want and lines[2] == want
