@@ -32,7 +32,8 @@ _SO = os.path.join(_HERE, "libfealess_b200.so")
 
 FL_OK, FL_ERR_SIZE, FL_ERR_GEOMETRY, FL_ERR_ROI, FL_ERR_FEATURES = 0, -1, -2, -3, -4
 FL_ERR_ARG, FL_ERR_CAPACITY, FL_ERR_CUDA, FL_ERR_STATE = -5, -6, -7, -8
-FL_DBG_QUANTIZED, FL_DBG_SPREAD, FL_DBG_LINEAR_MEMORY, FL_DBG_SIMILARITY = 0, 1, 2, 3
+FL_OPT_FE_WAVES, FL_OPT_SPLIT_REFINE, FL_OPT_TRACE, FL_OPT_FE_DEP_TIMEOUT_TEST, FL_OPT_FE_FORCED_WAVES = 0, 1, 2, 3, 4
+FL_DBG_QUANTIZED, FL_DBG_SPREAD, FL_DBG_LINEAR_MEMORY, FL_DBG_SIMILARITY, FL_DBG_STAGED_TRACE, FL_DBG_LAST_COUNTS, FL_DBG_FE_TRACE = 0, 1, 2, 3, 4, 5, 6
 
 MATCH_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("similarity", "<f4"), ("class_idx", "<i4"), ("template_id", "<i4")])
 ICP_RESULT_DTYPE = np.dtype([("R", "<f4", (9,)), ("T", "<f4", (3,)), ("dist_mean", "<f4"), ("inlier_ratio", "<f4"),
@@ -43,7 +44,7 @@ EXPORTED_SYMBOLS = [
     "fl_default_params", "fl_create", "fl_destroy", "fl_last_error", "fl_version", "fl_sync", "fl_stream",
     "fl_upload_templates", "fl_set_template_ids", "fl_num_templates", "fl_get_pose_info", "fl_match", "fl_match_device", "fl_match_device_async", "fl_match_wait", "fl_match_fetch",
     "fl_resize_linear", "fl_match_rescaled", "fl_match_shard_device", "fl_sort_unique_device", "fl_sort_unique_blocks_device", "fl_exchange_buffer_bytes", "fl_exchange_sort_unique_device", "fl_exchange_sort_unique_device_async", "fl_match_shard_exchange_device_async", "fl_depth_to_3d", "fl_icp_cloud_to_cloud_ex",
-    "fl_detection_batch", "fl_upload_model_depths", "fl_detection_batch_resident", "fl_detection_batch_resident_device", "fl_detection", "fl_nms", "fl_nms_ex", "fl_debug_keep_spread", "fl_debug_force_baseline", "fl_debug_uses_staged", "fl_debug_get", "fl_debug_icp_trace", "fl_launch_count",
+    "fl_detection_batch", "fl_upload_model_depths", "fl_detection_batch_resident", "fl_detection_batch_resident_device", "fl_detection", "fl_nms", "fl_nms_ex", "fl_debug_option", "fl_debug_keep_spread", "fl_debug_force_baseline", "fl_debug_uses_staged", "fl_debug_get", "fl_debug_icp_trace", "fl_launch_count",
     "fl_profile", "fl_last_stage_ms", "fl_last_icp_ms",
     "fl_group_create", "fl_group_destroy", "fl_group_size", "fl_group_handle", "fl_group_upload_templates", "fl_group_match",
 ]
@@ -329,6 +330,29 @@ class Handle:
         _check(lib().fl_debug_icp_trace(self._h, _p(out), n_hyp), "fl_debug_icp_trace")
         return out
 
+    def debug_option(self, option: int, value: int = 1) -> int:
+        """fl_debug_option (FL_OPT_*): developer switches of this handle; returns the call's value (query options) or 0."""
+        rc = lib().fl_debug_option(self._h, int(option), int(value))
+        if rc < 0:
+            _check(rc, "fl_debug_option")
+        return rc
+
+    def staged_trace(self):
+        """FL_DBG_STAGED_TRACE: [n_cta, 8] int64 timeline of the staged similarity kernel of the last frame (needs FL_OPT_TRACE)."""
+        buf = np.zeros(1024 * 136 + 8, np.uint64)
+        n = lib().fl_debug_get(self._h, FL_DBG_STAGED_TRACE, 0, 0, 0, C.c_void_p(buf.ctypes.data), C.c_size_t(buf.nbytes))
+        if n < 0:
+            _check(n, "fl_debug_get(FL_DBG_STAGED_TRACE)")
+        return buf[:n * 8].reshape(n, 8).astype(np.int64)
+
+    def fe_trace(self):
+        """FL_DBG_FE_TRACE: [n_jobs, 4] int64 {kind, CTAs, first start ns, last end ns} of the front end of the last frame."""
+        buf = np.zeros(4 * 64, np.uint64)
+        n = lib().fl_debug_get(self._h, FL_DBG_FE_TRACE, 0, 0, 0, C.c_void_p(buf.ctypes.data), C.c_size_t(buf.nbytes))
+        if n < 0:
+            _check(n, "fl_debug_get(FL_DBG_FE_TRACE)")
+        return buf[:n * 4].reshape(n, 4).astype(np.int64)
+
     def keep_spread(self, enable=True):
         _check(lib().fl_debug_keep_spread(self._h, int(enable)), "fl_debug_keep_spread")
 
@@ -479,6 +503,18 @@ class Group:
             self.close()
         except Exception:  # noqa: BLE001
             pass
+
+    def member_option(self, i: int, option: int, value: int = 1) -> int:
+        """fl_debug_option on member handle ``i`` (fl_group_handle)."""
+        L = lib()
+        L.fl_group_handle.restype = C.c_void_p
+        hp = L.fl_group_handle(self._g, int(i))
+        if not hp:
+            raise FealessError(FL_ERR_ARG, "fl_group_handle")
+        rc = L.fl_debug_option(C.c_void_p(hp), int(option), int(value))
+        if rc < 0:
+            _check(rc, "fl_debug_option")
+        return rc
 
     def upload_templates(self, tset) -> None:
         hdr = np.ascontiguousarray(tset.headers, np.int32)

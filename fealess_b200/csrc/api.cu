@@ -16,9 +16,9 @@ void fl_set_error(const char* fmt, ...) {
   va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
 }
 extern "C" const char* fl_last_error(void) { return g_err; }
-// off by default: measured on B200 (8k templates, VGA) the frame takes 126.7 us with PDL and 125.8 us without - the kernel
-// boundaries of this pipeline cost ~1.5 us each and griddepcontrol.wait still has to see the previous grid drain
-bool fl_pdl_enabled() { static const bool on = getenv("FL_PDL") != nullptr; return on; }
+// Programmatic dependent launch for every kernel of the pipeline was measured neutral (126.7 vs 125.8 us per frame: the boundaries
+// cost ~1.5 us each and griddepcontrol.wait still has to see the previous grid drain); only the similarity kernel, whose prologue is
+// long enough to matter, is launched that way (similarity_staged.cu).
 extern "C" const char* fl_version(void) { return "fealess_b200 0.1 (sm_100a)"; }
 
 #define FETCH_FIRST 1024   // matches copied back together with the count in the common case
@@ -54,6 +54,8 @@ struct fl_handle {
   bool pend_sort, pend_match, pend_own, pend_masks_valid, pend_small_fused; fl_lists pend_lists; fl_match_t* pend_out; int pend_out_cap; int* pend_out_count;
   const void* pend_bgr; const void* pend_depth; int pend_W, pend_H; float pend_threshold; const void* pend_masks[FL_MAX_MODALITIES]; std::vector<int32_t> pend_filter;
   unsigned long long* d_fe_trace; int fe_trace_jobs, fe_trace_kind[FL_FE_MAX_JOBS], fe_trace_ctas[FL_FE_MAX_JOBS];
+  bool opt_fe_waves, opt_split_refine, opt_trace, opt_dep_test;   // fl_debug_option
+  int* h_fe_err; int* d_fe_err_host; bool fe_force_waves;   // in-grid dependency time-out: mapped host flag (+ its device alias); true = this handle launches one kernel per wave from now on
   unsigned* d_fe_counters; unsigned fe_counter_base[FL_FE_MAX_JOBS]; unsigned fe_row_base[FL_FE_MAX_JOBS];   // in-grid dependency counters of the single-launch front end (+ 1 error word)
   // candidates / matches
   fl_match_t* d_cand; int* d_count; fl_sort_key* d_keys; int key_cap; uint8_t* d_outblk; fl_match_t* d_out; int* d_out_count;   // d_outblk = [16-int summary][matches]
@@ -145,7 +147,6 @@ extern "C" int fl_create(const fl_params_t* params, fl_handle** out) {
   FL_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   for (int i = 0; i < 5; ++i) FL_CUDA(cudaEventCreate(&h->ev[i]));
   TRY(fl_launch_tables_init());
-  if (getenv("FL_CARVEOUT")) { fl_prefer_smem_carveout_frontend(); fl_prefer_smem_carveout_similarity(); }
   const size_t npx = (size_t)p.max_width * p.max_height;
   TRY(dalloc(&h->d_in_bgr, npx * 3)); TRY(dalloc(&h->d_in_depth, npx));
   TRY(dalloc(&h->d_geom, FL_MAX_LEVELS));
@@ -166,6 +167,9 @@ extern "C" int fl_create(const fl_params_t* params, fl_handle** out) {
   TRY(dalloc(&h->d_fe_counters, FL_FE_MAX_JOBS + 1 + FL_FE_MAX_JOBS * FL_FE_MAX_TILE_ROWS));
   FL_CUDA(cudaMemset(h->d_fe_counters, 0, (FL_FE_MAX_JOBS + 1 + FL_FE_MAX_JOBS * FL_FE_MAX_TILE_ROWS) * sizeof(unsigned)));
   memset(h->fe_counter_base, 0, sizeof h->fe_counter_base); memset(h->fe_row_base, 0, sizeof h->fe_row_base);
+  FL_CUDA(cudaHostAlloc((void**)&h->h_fe_err, 64, cudaHostAllocMapped)); *h->h_fe_err = 0; h->fe_force_waves = false;
+  h->opt_fe_waves = h->opt_split_refine = h->opt_trace = h->opt_dep_test = false;
+  FL_CUDA(cudaHostGetDevicePointer((void**)&h->d_fe_err_host, h->h_fe_err, 0));
   h->pend_sort = h->pend_match = false; h->pend_small_fused = false; h->d_fe_trace = nullptr; h->fe_trace_jobs = 0;                             // [0] candidate count, [1] CTA ticket counter of k_refine_sort
   int kc = 2; while (kc < p.max_candidates) kc <<= 1;
   h->key_cap = kc;
@@ -214,7 +218,7 @@ extern "C" int fl_destroy(fl_handle* h) {
     cudaFree(h->d_bgr[l]); cudaFree(h->d_lm[l]);
     for (int m = 0; m < FL_MAX_MODALITIES; ++m) { cudaFree(h->d_q[l][m]); cudaFree(h->d_qm[l][m]); cudaFree(h->d_mask[l][m]); cudaFree(h->d_spread[l][m]); }
   }
-  cudaFree(h->d_fe_counters); cudaFree(h->d_fe_trace);
+  cudaFree(h->d_fe_counters); cudaFree(h->d_fe_trace); cudaFreeHost(h->h_fe_err);
   cudaFree(h->d_cand); cudaFree(h->d_count); cudaFree(h->d_keys); cudaFree(h->d_outblk);
   cudaFreeHost(h->h_bgr); cudaFreeHost(h->h_depth); cudaFreeHost(h->h_mask); cudaFreeHost(h->h_outblk); cudaFreeHost(h->h_class_enabled);
   for (int i = 0; i < 5; ++i) cudaEventDestroy(h->ev[i]);
@@ -240,6 +244,18 @@ extern "C" int fl_last_stage_ms(fl_handle* h, float out4[4]) { if (!h || !out4) 
 // 1 = always use the baseline (L1/L2-fed) global similarity kernel; 0 = use the shared-memory-staged kernel when eligible
 extern "C" int fl_debug_force_baseline(fl_handle* h, int enable) { if (!h) return FL_ERR_ARG; h->force_baseline = enable != 0; h->packed = false; return FL_OK; }
 extern "C" int fl_debug_uses_staged(fl_handle* h) { return h ? (h->use_staged ? 1 : 0) : FL_ERR_ARG; }
+// developer options of one handle (all off by default; each one is exercised by tests/test_gpu_match.py::test_debug_options)
+extern "C" int fl_debug_option(fl_handle* h, int option, int value) {
+  if (!h) return FL_ERR_ARG;
+  switch (option) {
+    case FL_OPT_FE_WAVES: h->opt_fe_waves = value != 0; return FL_OK;
+    case FL_OPT_SPLIT_REFINE: h->opt_split_refine = value != 0; return FL_OK;
+    case FL_OPT_TRACE: h->opt_trace = value != 0; h->packed = false; return FL_OK;     // (the staged plan allocates its timeline at planning time)
+    case FL_OPT_FE_DEP_TIMEOUT_TEST: h->opt_dep_test = value != 0; return FL_OK;
+    case FL_OPT_FE_FORCED_WAVES: return h->fe_force_waves ? 1 : 0;                      // query: has a dependency time-out switched this handle to wave launches?
+  }
+  return FL_ERR_ARG;
+}
 extern "C" int fl_debug_keep_spread(fl_handle* h, int enable) { if (!h) return FL_ERR_ARG; h->keep_spread = enable != 0; return FL_OK; }
 extern "C" int fl_num_templates(fl_handle* h) { return h ? h->n_templates : FL_ERR_ARG; }
 
@@ -389,7 +405,7 @@ static int ensure_geometry(fl_handle* h, int W, int H) {
       TRY(dalloc(&h->plan.gfeat, (size_t)h->n_templates * 64));
       TRY(dalloc(&h->plan.gpre, (size_t)h->n_templates * plan.pre_stride));
       TRY(dalloc(&h->plan.gmeta, (size_t)h->n_templates));
-      if (getenv("FL_TRACE")) {                                                  // developer timeline of the staged kernel (FL_DBG_STAGED_TRACE)
+      if (h->opt_trace) {                                                        // developer timeline of the staged kernel (FL_DBG_STAGED_TRACE)
         TRY(dalloc(&h->plan.trace, (size_t)plan.n_cta * 136 + 8));                 // + stamps of a 1-thread kernel before / after the launch
         FL_CUDA(cudaMemsetAsync(h->plan.trace, 0, ((size_t)plan.n_cta * 136 + 8) * sizeof(unsigned long long), h->stream));
       }
@@ -400,6 +416,8 @@ static int ensure_geometry(fl_handle* h, int W, int H) {
   }
   return FL_OK;
 }
+
+static void fe_wave_init(fl_fe_wave* w) { memset(w, 0, sizeof *w); }   // an empty launch description (no jobs, no in-grid dependencies)
 
 // front end + matchClass on the handle's templates; candidates land in (cand, count)
 // defer_refine: leave the candidates at the coarsest level; the caller refines them in the same launch that sorts (k_refine_sort)
@@ -444,11 +462,11 @@ static int run_match_stages(fl_handle* h, const uint8_t* d_bgr, const uint16_t* 
     // latency floor of one colour-tile CTA, about 8 us.)
     const int L = p.n_levels;
     fl_fe_wave w;
-    auto wave_begin = [&](bool zero) { w.n_jobs = 0; w.n_ctas = 0; w.smem = 0; w.n_pyr = 0; w.zero_me = zero ? d_count : nullptr; w.counters = nullptr; w.dep_error = nullptr; w.trace = nullptr; };
-    auto wave_flush = [&]() { if (w.n_jobs > 0) { fl_launch_fe_wave(w, s); ++h->launches; } w.n_jobs = 0; w.n_ctas = 0; w.smem = 0; w.n_pyr = 0; w.zero_me = nullptr; };
-    // word-parallel quantisers (frontend_v2.cuh); FL_FE_V1=1 selects the first, byte-granular versions (A/B timing).  The depth
-    // job also writes the NN-downsampled label pyramid when every level halves exactly (then dst_l(y,x) = src(2^l y, 2^l x)).
-    static const bool fe_v1 = getenv("FL_FE_V1") != nullptr;
+    auto wave_begin = [&](bool zero) { w.n_jobs = 0; w.n_ctas = 0; w.smem = 0; w.n_pyr = 0; w.zero_me = zero ? d_count : nullptr; w.counters = nullptr; w.dep_error = nullptr; w.dep_error_host = nullptr; w.trace = nullptr; };
+    bool launch_ok = true;
+    auto wave_flush = [&]() { if (w.n_jobs > 0) { launch_ok &= fl_launch_fe_wave(w, s) == cudaSuccess; ++h->launches; } w.n_jobs = 0; w.n_ctas = 0; w.smem = 0; w.n_pyr = 0; w.zero_me = nullptr; };
+    // word-parallel quantisers (frontend_v2.cuh).  The depth job also writes the NN-downsampled label pyramid when every level
+    // halves exactly (then dst_l(y,x) = src(2^l y, 2^l x)).
     bool depth_pyr_fused[FL_MAX_MODALITIES] = {false, false, false, false};
     bool halves = true;
     for (int l = 0; l + 1 < L; ++l) halves &= (h->geom[l].W % 2 == 0) && (h->geom[l].H % 2 == 0);
@@ -456,24 +474,23 @@ static int run_match_stages(fl_handle* h, const uint8_t* d_bgr, const uint16_t* 
     // ---- single-launch front end: every job of the frame in ONE grid, producers before consumers, dependencies resolved by
     // per-job CTA counters inside the kernel (k_front_end_wave).  Removes L launches + their dependency gaps and lets the
     // level-0 work fill the machine while the short critical chain pyrDown -> colour L(top) -> spread L(top) runs.
-    static const bool fe_waves = getenv("FL_FE_WAVES") != nullptr;               // developer A/B: one launch per wave, as before
+    const bool fe_waves = h->opt_fe_waves;                                       // FL_OPT_FE_WAVES: one launch per wave (also the fallback after a dependency time-out)
     int n_color = 0, n_depth = 0;
     for (int m = 0; m < p.n_modalities; ++m) { n_color += p.modality_kind[m] == FL_MODALITY_COLOR_GRADIENT; n_depth += p.modality_kind[m] == FL_MODALITY_DEPTH_NORMAL; }
     const int n_jobs_single = (n_color ? L - 1 : 0) + n_color * L + n_depth + p.n_modalities * L;
-    const bool single = !fe_v1 && !fe_waves && n_jobs_single <= FL_FE_MAX_JOBS && n_depth <= FL_FE_MAX_DPYR && (L == 1 || (halves && L - 1 <= FL_FE_MAX_PYR));
+    const bool single = !fe_waves && !h->fe_force_waves && n_jobs_single <= FL_FE_MAX_JOBS && n_depth <= FL_FE_MAX_DPYR && (L == 1 || (halves && L - 1 <= FL_FE_MAX_PYR));
     if (single) {
       wave_begin(zero_in_wave);
-      w.counters = h->d_fe_counters; w.dep_error = reinterpret_cast<int*>(h->d_fe_counters + FL_FE_MAX_JOBS);
+      w.counters = h->d_fe_counters; w.dep_error = reinterpret_cast<int*>(h->d_fe_counters + FL_FE_MAX_JOBS); w.dep_error_host = h->d_fe_err_host;
       int slot_pyr[FL_MAX_LEVELS], slot_color[FL_MAX_LEVELS][FL_MAX_MODALITIES], slot_depth[FL_MAX_MODALITIES];
       auto last_job = [&]() -> fl_fe_job& { return w.job[w.n_jobs - 1]; };
       auto job_ctas = [&](int idx) { return (idx + 1 < w.n_jobs ? w.job[idx + 1].cta_begin : w.n_ctas) - w.job[idx].cta_begin; };
       auto produce = [&]() { last_job().signal_slot = w.n_jobs - 1; return w.n_jobs - 1; };
-      static const bool row_deps = getenv("FL_FE_JOB_DEPS") == nullptr;          // FL_FE_JOB_DEPS=1: whole-job waits only (developer A/B)
       // tile jobs (32 x 16 tiles) also count per tile row; returns false when the image has more tile rows than counters
       auto produce_rows = [&](int slot) {
         fl_fe_job& jb = w.job[slot];
         const int rows = (jb.H + 15) / 16;
-        if (!row_deps || rows > FL_FE_MAX_TILE_ROWS) return;
+        if (rows > FL_FE_MAX_TILE_ROWS) return;                 // (then the consumers wait for the whole job)
         jb.row_base = FL_FE_MAX_JOBS + 1 + slot * FL_FE_MAX_TILE_ROWS;
       };
       auto consume_rows = [&](int slot, int shift) {      // spread job: wait per tile row of producer `slot` (level shift for the depth pyramid)
@@ -483,7 +500,10 @@ static int run_match_stages(fl_handle* h, const uint8_t* d_bgr, const uint16_t* 
         jb.wait_row_base = pj.row_base; jb.wait_row_shift = shift; jb.wait_row_count = (pj.H + 15) / 16;
         jb.wait_row_target = h->fe_row_base[slot] + (unsigned)abs(pj.gx);
       };
-      auto consume = [&](int slot) { last_job().wait_slot = slot; last_job().wait_target = h->fe_counter_base[slot] + (unsigned)job_ctas(slot); };
+      // FL_OPT_FE_DEP_TIMEOUT_TEST: the next frame waits for one CTA more than its producer has, i.e. the wait times out (test of the fallback)
+      const unsigned dep_test = h->opt_dep_test ? 1u : 0u;
+      h->opt_dep_test = false;
+      auto consume = [&](int slot) { last_job().wait_slot = slot; last_job().wait_target = h->fe_counter_base[slot] + (unsigned)job_ctas(slot) + dep_test; };
       // 0. the staged similarity kernel's per-template feature lists -> L2 (they would otherwise cost its prologue DRAM round trips)
       if (h->use_staged && h->n_templates > 0 && n_jobs_single + 3 <= FL_FE_MAX_JOBS) {
         fl_fe_add_prefetch(&w, h->plan.gfeat, (size_t)h->n_templates * 64 * sizeof(uint32_t));
@@ -531,10 +551,7 @@ static int run_match_stages(fl_handle* h, const uint8_t* d_bgr, const uint16_t* 
           consume(is_color ? slot_color[l][m] : slot_depth[m]);
           consume_rows(is_color ? slot_color[l][m] : slot_depth[m], is_color ? 0 : l);
         }
-      for (int i = 0; i < w.n_jobs; ++i) if (w.job[i].signal_slot >= 0) h->fe_counter_base[i] += (unsigned)job_ctas(i);
-      for (int i = 0; i < w.n_jobs; ++i) if (w.job[i].row_base >= 0) h->fe_row_base[i] += (unsigned)abs(w.job[i].gx);
-      static const bool fe_trace = getenv("FL_TRACE") != nullptr;                // developer timeline: per job first start / last end
-      if (fe_trace) {
+      if (h->opt_trace) {                                                        // developer timeline: per job first start / last end
         if (!h->d_fe_trace) TRY(dalloc(&h->d_fe_trace, 2 * FL_FE_MAX_JOBS + 2 * FL_FE_MAX_JOBS));
         unsigned long long init[2 * FL_FE_MAX_JOBS];
         for (int i = 0; i < FL_FE_MAX_JOBS; ++i) { init[2 * i] = ~0ull; init[2 * i + 1] = 0; }
@@ -544,7 +561,12 @@ static int run_match_stages(fl_handle* h, const uint8_t* d_bgr, const uint16_t* 
         h->fe_trace_jobs = w.n_jobs;
         for (int i = 0; i < w.n_jobs; ++i) { h->fe_trace_kind[i] = w.job[i].kind; h->fe_trace_ctas[i] = job_ctas(i); }
       }
+      // the monotonic counter bases advance only when the launch really went out (a failed launch bumps no counter)
+      unsigned add_ctr[FL_FE_MAX_JOBS] = {0}, add_row[FL_FE_MAX_JOBS] = {0};
+      for (int i = 0; i < w.n_jobs; ++i) { if (w.job[i].signal_slot >= 0) add_ctr[i] = (unsigned)job_ctas(i); if (w.job[i].row_base >= 0) add_row[i] = (unsigned)abs(w.job[i].gx); }
       wave_flush();
+      if (!launch_ok) { fl_set_error("front-end launch failed: %s", cudaGetErrorString(cudaGetLastError())); return FL_ERR_CUDA; }
+      for (int i = 0; i < FL_FE_MAX_JOBS; ++i) { h->fe_counter_base[i] += add_ctr[i]; h->fe_row_base[i] += add_row[i]; }
     } else
     for (int wv = 0; wv <= L; ++wv) {
       wave_begin(wv == 0 && zero_in_wave);                                        // the candidate counter is reset by the first wave
@@ -554,13 +576,11 @@ static int run_match_stages(fl_handle* h, const uint8_t* d_bgr, const uint16_t* 
         for (int m = 0; m < p.n_modalities; ++m)
           if (p.modality_kind[m] == FL_MODALITY_COLOR_GRADIENT) {
             wave_room();
-            if (fe_v1) fl_fe_add_color(&w, l == 0 ? d_bgr : h->d_bgr[l], g.W, g.H, thr_sq, h->d_q[l][m], 0, 1);
-            else fl_fe_add_color_v2(&w, l == 0 ? d_bgr : h->d_bgr[l], g.W, g.H, thr_sq, h->d_q[l][m]);
+            fl_fe_add_color_v2(&w, l == 0 ? d_bgr : h->d_bgr[l], g.W, g.H, thr_sq, h->d_q[l][m]);
           }
         for (int m = 0; m < p.n_modalities; ++m)
           if (p.modality_kind[m] == FL_MODALITY_DEPTH_NORMAL && l == 0) {
             wave_room();
-            if (fe_v1) { fl_fe_add_depth(&w, d_depth, g.W, g.H, p.distance_threshold, p.difference_threshold, h->d_q[0][m]); continue; }
             fl_depth_pyr pyr; memset(&pyr, 0, sizeof pyr);
             if (halves && L > 1 && L - 1 <= FL_FE_MAX_PYR) {
               pyr.n = L - 1;
@@ -605,9 +625,9 @@ static int run_match_stages(fl_handle* h, const uint8_t* d_bgr, const uint16_t* 
             }
             src = h->d_bgr[l];
           }
-          fl_launch_color_quantize(src, g.W, g.H, thr_sq, h->d_q[l][m], s); ++h->launches;
+          { fl_fe_wave w1; fe_wave_init(&w1); fl_fe_add_color_v2(&w1, src, g.W, g.H, thr_sq, h->d_q[l][m]); fl_launch_fe_wave(w1, s); ++h->launches; }
         } else {
-          if (l == 0) { fl_launch_depth_quantize(d_depth, g.W, g.H, p.distance_threshold, p.difference_threshold, h->d_q[0][m], s); ++h->launches; }
+          if (l == 0) { fl_fe_wave w1; fe_wave_init(&w1); fl_fe_add_depth_v2(&w1, d_depth, g.W, g.H, p.distance_threshold, p.difference_threshold, h->d_q[0][m], nullptr); fl_launch_fe_wave(w1, s); ++h->launches; }
           else { fl_launch_resize_nn_half(h->d_q[l - 1][m], h->geom[l - 1].W, h->geom[l - 1].H, h->d_q[l][m], s); ++h->launches; }
         }
         const uint8_t* qsrc = h->d_q[l][m];
@@ -631,25 +651,16 @@ static int run_match_stages(fl_handle* h, const uint8_t* d_bgr, const uint16_t* 
   if (h->n_templates > 0) {
     fl_tdb db = make_tdb(h);
     const int lowest = p.n_levels - 1;
-    bool refined = false;
     if (h->use_staged) {
-      // the staged kernel refines its own candidates (fused tail, refine_warp.cuh) when FL_FUSE_TAIL=1 was set at planning time (developer variant, off by default)
-      fl_refine_args ra;
-      memset(&ra, 0, sizeof ra);
-      ra.n_levels = p.n_levels;
-      h->plan.fuse_ovf = reinterpret_cast<int*>(h->d_outblk) + 14;                 // posted to h_small[14] and cleared by the sort kernel
-      for (int l = 0; l < p.n_levels; ++l) { ra.g[l] = h->geom[l]; ra.lm[l] = h->d_lm[l]; }
-      if (fl_launch_similarity_staged(db, h->geom[lowest], h->d_lm[lowest], threshold, cand, cap, d_count, h->plan, ra, s) != 0) {
+      if (fl_launch_similarity_staged(db, h->geom[lowest], h->d_lm[lowest], threshold, cand, cap, d_count, h->plan, s) != 0) {
         fl_set_error("staged similarity kernel could not be configured"); return FL_ERR_CUDA;
       }
-      refined = h->plan.fuse_list_cap > 0;
-
     } else {
       fl_launch_similarity_global(db, h->geom[lowest], h->d_lm[lowest], threshold, cand, cap, d_count, s);
     }
     ++h->launches;
     if (h->profile) cudaEventRecord(h->ev[2], s);
-    if (!refined && !defer_refine)
+    if (!defer_refine)
       for (int l = p.n_levels - 2; l >= 0; --l) { fl_launch_refine_level(db, h->geom[l], l, h->d_lm[l], threshold, cand, cap, d_count, s); ++h->launches; }
   } else if (h->profile) cudaEventRecord(h->ev[2], s);
   if (h->profile) cudaEventRecord(h->ev[3], s);
@@ -659,7 +670,7 @@ static int run_match_stages(fl_handle* h, const uint8_t* d_bgr, const uint16_t* 
 
 // sort + unique of candidate lists into (d_out, d_out_count); handles the rare > 8,192-record path; leaves
 // h_small = {count, n_live, flag, raw list counts...} and, for the handle's own output block, the first matches in h_first
-struct fl_refine_req { float threshold; fl_match_t* cand; int cap; const int* d_count; bool small; };   // refine these candidates in the sort launch (k_refine_sort)
+struct fl_refine_req { float threshold; fl_match_t* cand; int cap; const int* d_count; };   // refine these candidates in the sort launch (k_refine_sort)
 // first half of sort + unique (optionally with the refinement in the same launch): enqueue only
 static int sort_launch(fl_handle* h, fl_lists L, fl_match_t* d_out, int out_cap, int* d_out_count, bool fetch_first, const fl_xchg* xchg = nullptr,
                        const fl_refine_req* refine = nullptr) {
@@ -678,10 +689,10 @@ static int sort_launch(fl_handle* h, fl_lists L, fl_match_t* d_out, int out_cap,
     ra.n_levels = h->p.n_levels;
     for (int l = 0; l < h->p.n_levels; ++l) { ra.g[l] = h->geom[l]; ra.lm[l] = h->d_lm[l]; }
     const int nl = fl_launch_refine_sort(make_tdb(h), ra, refine->threshold, refine->cand, refine->cap, refine->d_count, h->d_count + 1, h->n_sm, L, X, h->key_cap,
-                                         d_out, out_cap, d_out_count, d_hdr, h->h_small, own ? h->h_first : nullptr, std::min(FETCH_FIRST, out_cap), refine->small, s);
+                                         d_out, out_cap, d_out_count, d_hdr, h->h_small, own ? h->h_first : nullptr, std::min(FETCH_FIRST, out_cap), s);
     if (nl < 0) { fl_set_error("refinement + sort launch failed: %s", cudaGetErrorString(cudaGetLastError())); return FL_ERR_CUDA; }
     h->launches += nl;
-    h->pend_small_fused = refine->small;
+    h->pend_small_fused = true;
   } else {
     const int nl = fl_launch_sort_unique(L, X, h->key_cap, d_out, out_cap, d_out_count, d_hdr, h->h_small, own ? h->h_first : nullptr,
                                          std::min(FETCH_FIRST, out_cap), s);
@@ -711,13 +722,13 @@ static int sort_finish(fl_handle* h) {
   if (h->h_small[2] && h->pend_small_fused && n_upper <= 8192) {
     // the fused refinement + sort launch sorts up to 1,024 records in its last CTA; this frame has more (already refined in
     // place): run the stand-alone one-CTA sort (8,192 keys) on them.  What the first launch reported about the exchange
-    // (a peer that never arrived) and the fused tail survives the second launch, which knows about neither.
-    const int keep14 = h->h_small[14], keep15 = h->h_small[15];
+    // (a peer that never arrived) survives the second launch, which knows nothing about it.
+    const int keep15 = h->h_small[15];
     const bool keep_overflow = h->overflow;
     h->pend_small_fused = false;
     TRY(sort_launch(h, L, d_out, out_cap, d_out_count, own));
     const int rc = sort_finish(h);
-    h->h_small[14] |= keep14; if (keep15) h->h_small[15] = keep15;
+    if (keep15) h->h_small[15] = keep15;
     h->overflow |= keep_overflow;
     return rc;
   }
@@ -747,18 +758,17 @@ extern "C" int fl_match_device_async(fl_handle* h, const void* d_bgr, const void
   if (!h) return FL_ERR_ARG;
   if (h->pend_sort) { fl_set_error("fl_match_wait has not been called for the previous frame"); return FL_ERR_STATE; }
   h->have_result = false; h->pend_match = false;
-  // refinement and sort + unique share one launch (k_refine_sort<1>: 256-thread CTAs, the last one to finish sorts up to 1,024
-  // records).  FL_SPLIT_REFINE=1: separate launches (developer A/B).  FL_FUSE_REFINE_SORT=1: the variant with 1,024-thread CTAs
-  // and the 8,192-key sort inside (measured slower: those CTAs cost more to launch than the launch they save).
-  static const bool fuse_big = getenv("FL_FUSE_REFINE_SORT") != nullptr, split_refine = getenv("FL_SPLIT_REFINE") != nullptr;
-  const bool defer = !split_refine && h->n_templates > 0 && h->p.n_levels > 1;
+  // refinement and sort + unique share one launch (k_refine_sort: 256-thread CTAs, the last one to finish sorts up to 1,024
+  // records); FL_OPT_SPLIT_REFINE keeps them as separate launches (what fl_match_shard_device needs anyway: its candidates must
+  // be refined before an NCCL gather).  A variant with 1,024-thread CTAs and the 8,192-key sort inside was measured slower (those
+  // CTAs cost more to launch than the launch they save) and removed.
+  const bool defer = !h->opt_split_refine && h->n_templates > 0 && h->p.n_levels > 1;
   TRY(run_match_stages(h, (const uint8_t*)d_bgr, (const uint16_t*)d_depth, W, H, d_masks, threshold, class_filter, n_filter, h->d_cand,
                        h->p.max_candidates, h->d_count, defer));
   const fl_lists lists = {h->d_cand, 1, h->p.max_candidates, h->p.max_candidates, h->d_count, 1};
-  const bool in_sort = defer && !(h->use_staged && h->plan.fuse_list_cap > 0);
-  const fl_refine_req req = {threshold, h->d_cand, h->p.max_candidates, h->d_count, !fuse_big};
-  TRY(sort_launch(h, lists, h->d_out, h->p.max_candidates, h->d_out_count, true, nullptr, in_sort ? &req : nullptr));
-  // kept for fl_match_wait: the fused-tail overflow case re-runs the frame
+  const fl_refine_req req = {threshold, h->d_cand, h->p.max_candidates, h->d_count};
+  TRY(sort_launch(h, lists, h->d_out, h->p.max_candidates, h->d_out_count, true, nullptr, defer ? &req : nullptr));
+  // kept for fl_match_wait: a front-end dependency time-out re-runs the frame
   h->pend_match = true; h->pend_bgr = d_bgr; h->pend_depth = d_depth; h->pend_W = W; h->pend_H = H; h->pend_threshold = threshold;
   h->pend_masks_valid = d_masks != nullptr;
   for (int m = 0; m < FL_MAX_MODALITIES; ++m) h->pend_masks[m] = d_masks ? d_masks[m] : nullptr;
@@ -772,21 +782,23 @@ extern "C" int fl_match_wait(fl_handle* h) {
   const bool was_match = h->pend_match;
   h->pend_match = false;
   TRY(sort_finish(h));
-  if (h->h_small[15]) { fl_set_error("peer exchange timed out waiting for rank %d", h->h_small[15] - 1); return FL_ERR_STATE; }
-  if (h->h_small[14]) {
-    if (!was_match) { fl_set_error("more coarse candidates in one CTA than the fused refinement list holds; raise the threshold or unset FL_FUSE_TAIL"); return FL_ERR_CAPACITY; }
-    // one CTA of the staged kernel found more coarse candidates than its shared-memory list holds (very low thresholds,
-    // FL_FUSE_TAIL only): run the frame again with the refinement as separate launches
-    const int keep = h->plan.fuse_list_cap;
-    h->plan.fuse_list_cap = 0;
+  if (*reinterpret_cast<volatile int*>(h->h_fe_err)) {
+    // an in-grid dependency of the single-launch front end timed out (the producer CTAs were not dispatched before their consumers:
+    // see k_front_end_wave): the frame's result is not trustworthy.  From now on this handle launches one kernel per wave; a frame
+    // submitted through fl_match / fl_match_device* is re-run right away, the shard entry points report the state.
+    const int job = *h->h_fe_err - 1;
+    *h->h_fe_err = 0;
+    FL_CUDA(cudaMemsetAsync(h->d_fe_counters + FL_FE_MAX_JOBS, 0, sizeof(unsigned), h->stream));
+    h->fe_force_waves = true;
+    if (!was_match) { fl_set_error("front end: in-grid dependency of job %d timed out; the handle now uses per-wave launches - resubmit the frame", job); return FL_ERR_STATE; }
     const fl_lists lists = {h->d_cand, 1, h->p.max_candidates, h->p.max_candidates, h->d_count, 1};
     int rc = run_match_stages(h, (const uint8_t*)h->pend_bgr, (const uint16_t*)h->pend_depth, h->pend_W, h->pend_H, h->pend_masks_valid ? h->pend_masks : nullptr,
                               h->pend_threshold, h->pend_filter.empty() ? nullptr : h->pend_filter.data(), (int)h->pend_filter.size(), h->d_cand,
                               h->p.max_candidates, h->d_count);
     if (rc == FL_OK) rc = run_sort_unique(h, lists, h->d_out, h->p.max_candidates, h->d_out_count, true);
-    h->plan.fuse_list_cap = keep;
     if (rc != FL_OK) return rc;
   }
+  if (h->h_small[15]) { fl_set_error("peer exchange timed out waiting for rank %d", h->h_small[15] - 1); return FL_ERR_STATE; }
   h->have_result = true;
   return FL_OK;
 }
@@ -934,8 +946,7 @@ extern "C" int fl_match_shard_exchange_device_async(fl_handle* h, const void* d_
   FL_CUDA(cudaSetDevice(h->p.device));
   if (h->pend_sort) { fl_set_error("fl_match_wait has not been called for the previous frame"); return FL_ERR_STATE; }
   h->have_result = false; h->pend_match = false;
-  static const bool split_refine = getenv("FL_SPLIT_REFINE") != nullptr;
-  const bool defer = !split_refine && h->n_templates > 0 && h->p.n_levels > 1 && !(h->use_staged && h->plan.fuse_list_cap > 0);
+  const bool defer = !h->opt_split_refine && h->n_templates > 0 && h->p.n_levels > 1;
   fl_match_t* recs = d_local_block + 1;
   int* d_cnt = reinterpret_cast<int*>(d_local_block);
   TRY(run_match_stages(h, (const uint8_t*)d_bgr, (const uint16_t*)d_depth, W, H, nullptr, threshold, class_filter, n_filter, recs, capacity, d_cnt, defer));
@@ -945,7 +956,7 @@ extern "C" int fl_match_shard_exchange_device_async(fl_handle* h, const void* d_
   for (int p = 0; p < world; ++p) { if (!peer_buffers[p]) return FL_ERR_ARG; X.peer[p] = static_cast<uint8_t*>(peer_buffers[p]); }
   const uint8_t* own = X.peer[rank] + FL_XCHG_SIGNALS * sizeof(unsigned) + (size_t)(epoch & 1u) * world * ((size_t)capacity + 1) * sizeof(fl_match_t);
   const fl_lists lists = {reinterpret_cast<const fl_match_t*>(own) + 1, world, capacity, capacity + 1, reinterpret_cast<const int*>(own), 5 * (capacity + 1)};
-  const fl_refine_req req = {threshold, recs, capacity, d_cnt, true};
+  const fl_refine_req req = {threshold, recs, capacity, d_cnt};
   return sort_launch(h, lists, h->d_out, h->p.max_candidates, h->d_out_count, true, &X, defer ? &req : nullptr);
 }
 
@@ -963,7 +974,6 @@ extern "C" int fl_sort_unique_blocks_device(fl_handle* h, const fl_match_t* d_bl
   if (h->profile) for (int i = 0; i < 4; ++i) cudaEventRecord(h->ev[i], h->stream);   // stage times are not defined for this entry point
   const fl_lists lists = {d_blocks + 1, n_blocks, capacity, capacity + 1, reinterpret_cast<const int*>(d_blocks), 5 * (capacity + 1)};
   TRY(run_sort_unique(h, lists, h->d_out, h->p.max_candidates, h->d_out_count, true));
-  if (h->h_small[14]) { fl_set_error("more coarse candidates in one CTA than the fused refinement list holds; raise the threshold or unset FL_FUSE_TAIL"); return FL_ERR_CAPACITY; }
   h->have_result = true;
   return FL_OK;
 }
@@ -1008,7 +1018,7 @@ extern "C" int fl_debug_get(fl_handle* h, int what, int32_t a, int32_t b, int32_
     memcpy(host_out, h->h_small, 16 * sizeof(int));
     return FL_OK;
   }
-  if (what == 6) {                                                               // developer: front-end job timeline {kind, ctas, start, end} x jobs (FL_TRACE=1)
+  if (what == FL_DBG_FE_TRACE) {                                                               // developer: front-end job timeline {kind, ctas, start, end} x jobs (FL_OPT_TRACE)
     if (!h->d_fe_trace || h->fe_trace_jobs <= 0) return FL_ERR_STATE;
     if (bytes < (size_t)h->fe_trace_jobs * 4 * sizeof(unsigned long long)) return FL_ERR_CAPACITY;
     unsigned long long raw[2 * FL_FE_MAX_JOBS];

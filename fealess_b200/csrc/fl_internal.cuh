@@ -28,26 +28,21 @@ void fl_set_error(const char* fmt, ...);
 int fl_entries_per_template(const fl_handle* h);   // n_levels * n_modalities of the handle (api.cu)
 
 // ---- programmatic dependent launch (PDL) -------------------------------------------------------------------------
-// Every kernel of the per-frame pipeline can be launched with cudaLaunchAttributeProgrammaticStreamSerialization: its CTAs
-// may become resident while the previous kernel of the stream drains, run their prologue, and block in
-// fl_grid_dep_wait() until the previous kernel has completed and its writes are visible.  Rule: a kernel touches no
-// mutable global buffer before fl_grid_dep_wait(); fl_grid_dep_launch() tells the scheduler that the NEXT kernel may
-// start being placed.  Launched without the attribute both calls are no-ops.  The attribute is only set when the
-// process runs with FL_PDL=1 (measured: no gain for this pipeline, see fl_pdl_enabled in api.cu).
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may have its CTAs resident while the previous kernel
+// of the stream drains: they run their prologue and block in fl_grid_dep_wait() until that kernel has completed and its writes
+// are visible; fl_grid_dep_launch() tells the scheduler that the NEXT kernel may start being placed.  Rule: a kernel touches no
+// mutable global buffer before fl_grid_dep_wait().  Launched without the attribute both calls are no-ops.  Only the staged
+// similarity kernel is launched this way (behind the front end); for every other kernel of the frame the attribute was measured
+// to give nothing or to cost, so they use the plain fl_launch below.
 #ifdef __CUDACC__
 __device__ __forceinline__ void fl_grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void fl_grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #endif
-bool fl_pdl_enabled();
 template <typename... KArgs, typename... Args>
-inline cudaError_t fl_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+inline cudaError_t fl_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = fl_pdl_enabled() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
@@ -62,15 +57,13 @@ inline cudaError_t fl_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, 
 
 // ---- front end (frontend.cu) -------------------------------------------------------------------
 int fl_launch_tables_init();   // uploads the two LUTs to __constant__ memory of the current device
-void fl_launch_color_quantize(const uint8_t* bgr, int W, int H, float thr_sq, uint8_t* q, cudaStream_t s);
 void fl_launch_pyrdown_bgr(const uint8_t* src, int W, int H, uint8_t* dst, cudaStream_t s);
-void fl_launch_depth_quantize(const uint16_t* depth, int W, int H, int dist_thr, int diff_thr, uint8_t* q, cudaStream_t s);
 void fl_launch_resize_nn_half(const uint8_t* src, int W, int H, uint8_t* dst, cudaStream_t s);
 void fl_launch_apply_mask(const uint8_t* q, const uint8_t* mask, int n, uint8_t* out, cudaStream_t s);
 void fl_launch_spread_lm(const uint8_t* q, fl_level_geom g, uint8_t* lm_mod, uint8_t* spread_or_null, cudaStream_t s);
 
 // one launch = several independent front-end jobs (see k_front_end_wave)
-enum { FL_JOB_COLOR = 0, FL_JOB_DEPTH = 1, FL_JOB_PYRDOWN = 2, FL_JOB_RESIZE = 3, FL_JOB_SPREAD = 4, FL_JOB_COLOR2 = 5, FL_JOB_DEPTH2 = 6, FL_JOB_PREFETCH = 7 };
+enum { FL_JOB_PYRDOWN = 2, FL_JOB_RESIZE = 3, FL_JOB_SPREAD = 4, FL_JOB_COLOR2 = 5, FL_JOB_DEPTH2 = 6, FL_JOB_PREFETCH = 7 };
 struct fl_fe_job {
   int kind, cta_begin, gx, W, H, p0, p1;
   float thr_sq;
@@ -93,11 +86,9 @@ struct fl_depth_pyr { int n; int W[FL_FE_MAX_PYR], H[FL_FE_MAX_PYR]; uint8_t* ds
 #define FL_FE_MAX_JOBS 16
 #define FL_FE_MAX_DPYR 2
 struct fl_fe_wave { int n_jobs, n_ctas; size_t smem; int* zero_me; fl_fe_job job[FL_FE_MAX_JOBS]; int n_pyr; fl_depth_pyr pyr[FL_FE_MAX_DPYR];
-                    unsigned* counters; int* dep_error;
-                    unsigned long long* trace; };   // trace (FL_TRACE=1): per job {first CTA start, last CTA end} in globaltimer ns   // zero_me: int reset by CTA 0 (candidate counter), or NULL; counters: FL_FE_MAX_JOBS monotonic CTA counters
-void fl_fe_add_color(fl_fe_wave* w, const uint8_t* bgr, int W, int H, float thr_sq, uint8_t* q, int part, int n_parts);
-void fl_fe_add_depth(fl_fe_wave* w, const uint16_t* depth, int W, int H, int dist_thr, int diff_thr, uint8_t* q);
-// word-parallel variants (frontend_v2.cuh); pyr (nullable, at most FL_FE_MAX_DPYR per wave): also write the NN pyramid of the labels
+                    unsigned* counters; int* dep_error; int* dep_error_host;   // dep_error_host: the same flag in mapped host memory (written only on a time-out)
+                    unsigned long long* trace; };   // trace (FL_OPT_TRACE): per job {first CTA start, last CTA end} in globaltimer ns   // zero_me: int reset by CTA 0 (candidate counter), or NULL; counters: FL_FE_MAX_JOBS monotonic CTA counters
+// word-parallel quantisers (frontend_v2.cuh); pyr (nullable, at most FL_FE_MAX_DPYR per wave): also write the NN pyramid of the labels
 void fl_fe_add_color_v2(fl_fe_wave* w, const uint8_t* bgr, int W, int H, float thr_sq, uint8_t* q);
 bool fl_fe_add_depth_v2(fl_fe_wave* w, const uint16_t* depth, int W, int H, int dist_thr, int diff_thr, uint8_t* q, const fl_depth_pyr* pyr);
 void fl_fe_add_pyrdown(fl_fe_wave* w, const uint8_t* src, int W, int H, uint8_t* dst, bool src_static);
@@ -106,9 +97,7 @@ void fl_fe_add_pyrdown(fl_fe_wave* w, const uint8_t* src, int W, int H, uint8_t*
 void fl_fe_add_prefetch(fl_fe_wave* w, const void* src, size_t bytes);
 void fl_fe_add_resize(fl_fe_wave* w, const uint8_t* src, int W, int H, uint8_t* dst);
 void fl_fe_add_spread(fl_fe_wave* w, const uint8_t* q, fl_level_geom g, uint8_t* lm_mod, uint8_t* spread_or_null);
-void fl_launch_fe_wave(const fl_fe_wave& w, cudaStream_t s);
-void fl_prefer_smem_carveout_frontend();
-void fl_prefer_smem_carveout_similarity();
+cudaError_t fl_launch_fe_wave(const fl_fe_wave& w, cudaStream_t s);
 
 // ---- similarity / refinement / sort (similarity.cu) ---------------------------------------------
 struct fl_tdb {                     // device template database
@@ -135,25 +124,23 @@ struct fl_staged_plan {
   int halo_bytes, buf_bytes, n_buf;        // bytes staged past the last row; size and number of the smem ring buffers
   int n_words, nw_template, tpw;           // 32-bit words per similarity map; template parameters of the instantiation used
   int tpc, n_cta, block_threads;           // templates per CTA, grid, block
-  int cluster, smem_bytes, pre_stride;     // CTAs per cluster (TMA multicast group); dynamic shared memory; bytes per gpre row
+  int smem_bytes, pre_stride;              // dynamic shared memory; bytes per gpre row
   int stage_off;                           // emission staging area (one similarity map, nw_template x 32 words)
-  int fuse_list_off, fuse_list_cap;        // fused refinement tail: per-CTA candidate list in shared memory (offset, records); cap 0 = not fused
-  int* fuse_ovf;                           // device int set to 1 when a CTA's list overflowed (the host then re-runs the frame unfused)
   uint32_t* gfeat;                         // [n_templates][64] feature words sorted by phase: word offset in the phase buffer << 5 | 8 * byte misalignment
   uint8_t* gpre;                           // [n_templates][pre_stride] prefix counts per phase
   int4* gmeta;                             // [n_templates] {template_positions, n_features, class, 0}
-  unsigned long long* trace;               // developer timeline (FL_TRACE=1): 8 words per CTA, or NULL
+  unsigned long long* trace;               // developer timeline (FL_OPT_TRACE): 8 words per CTA, or NULL
 };
 bool fl_plan_staged(const fl_level_geom& g, int M, int n_templates, int max_positions, int n_sm, fl_staged_plan* plan);
 void fl_launch_pack_staged(fl_tdb db, fl_level_geom g, fl_staged_plan plan, cudaStream_t s);
-// every level's geometry and linear memories, for the refinement fused into the staged kernel's tail (refine_warp.cuh)
+// every level's geometry and linear memories, for the refinement that shares a launch with the sort (k_refine_sort)
 struct fl_refine_args {
   int n_levels;
   fl_level_geom g[FL_MAX_LEVELS];
   const uint8_t* lm[FL_MAX_LEVELS];
 };
 int fl_launch_similarity_staged(fl_tdb db, fl_level_geom g, const uint8_t* lm_level, float threshold, fl_match_t* cand, int cap,
-                                int* d_count, fl_staged_plan plan, const fl_refine_args& ra, cudaStream_t s);
+                                int* d_count, fl_staged_plan plan, cudaStream_t s);
 void fl_launch_pack_features(fl_tdb db, const fl_level_geom* d_geom, int n_features_total, cudaStream_t s);
 void fl_launch_similarity_global(fl_tdb db, fl_level_geom g, const uint8_t* lm_level, float threshold,
                                  fl_match_t* cand, int cap, int* d_count, cudaStream_t s);
@@ -185,7 +172,7 @@ int fl_launch_sort_unique(fl_lists L, fl_xchg X, int key_cap, fl_match_t* d_out,
 // refinement of every level + sort + unique in one launch (the last CTA to finish sorts); done_ctr: zero-initialised device int
 int fl_launch_refine_sort(fl_tdb db, const fl_refine_args& ra, float threshold, fl_match_t* cand, int cap, const int* d_count, int* done_ctr, int n_sm,
                           fl_lists L, fl_xchg X, int key_cap, fl_match_t* d_out, int out_cap, int* d_out_count, int* d_hdr,
-                          int* h_hdr, fl_match_t* h_first, int h_first_cap, bool small, cudaStream_t s);
+                          int* h_hdr, fl_match_t* h_first, int h_first_cap, cudaStream_t s);
 int fl_launch_sort_unique_big(fl_lists L, fl_sort_key* keys, int key_cap, int n_upper, fl_match_t* d_out, int out_cap, int* d_out_count, cudaStream_t s);
 
 // ---- ICP (icp.cu) --------------------------------------------------------------------------------

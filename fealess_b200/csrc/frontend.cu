@@ -80,114 +80,6 @@ __device__ __forceinline__ int angle_q16(float x, float y) {
   return min(max(r, 0), 255);
 }
 
-#define CQ_SMEM_BYTES ((CQ_TH + 10) * (CQ_TW + 10) * 3 + (CQ_TH + 10) * (CQ_TW + 4) * 3 * 2 + (CQ_TH + 4) * (CQ_TW + 4) * 3 + (CQ_TH + 2) * (CQ_TW + 2) + 16)
-
-// one CQ_TW x CQ_TH tile; smem = CQ_SMEM_BYTES bytes, 16-byte aligned
-__device__ __forceinline__ void dev_color_quantize(const uint8_t* __restrict__ bgr, int W, int H, float thr_sq, uint8_t* __restrict__ q,
-                                                   int bx, int by, uint8_t* smem) {
-  constexpr int SW = CQ_TW + 10, SH = CQ_TH + 10;   // source tile
-  constexpr int BW = CQ_TW + 4, BH = CQ_TH + 4;     // blurred tile (positions x0-2 .. x0+TW+1)
-  constexpr int QW = CQ_TW + 2, QH = CQ_TH + 2;     // unfiltered-bin tile (positions x0-1 .. x0+TW)
-  constexpr int OFF_H = (SH * SW * 3 + 15) & ~15;
-  uint8_t(*s_src)[SW * 3] = reinterpret_cast<uint8_t(*)[SW * 3]>(smem);
-  uint16_t(*s_h)[BW * 3] = reinterpret_cast<uint16_t(*)[BW * 3]>(smem + OFF_H);
-  uint8_t(*s_b)[BW * 3] = reinterpret_cast<uint8_t(*)[BW * 3]>(smem + OFF_H + SH * BW * 3 * 2);
-  uint8_t(*s_q)[QW] = reinterpret_cast<uint8_t(*)[QW]>(smem + OFF_H + SH * BW * 3 * 2 + BH * BW * 3);   // bits 0-2 bin, bit 7 = magnitude above threshold
-  const int x0 = bx * CQ_TW, y0 = by * CQ_TH;
-  const int tid = threadIdx.x;
-
-  // 1. source tile with BORDER_REPLICATE
-  for (int i = tid; i < SH * SW; i += CQ_THREADS) {
-    int r = i / SW, c = i - r * SW;
-    int sy = clampi(y0 - 5 + r, 0, H - 1), sx = clampi(x0 - 5 + c, 0, W - 1);
-    const uint8_t* p = bgr + ((size_t)sy * W + sx) * 3;
-    s_src[r][c * 3 + 0] = p[0]; s_src[r][c * 3 + 1] = p[1]; s_src[r][c * 3 + 2] = p[2];
-  }
-  __syncthreads();
-  // 2. horizontal 7-tap {8,28,56,72,56,28,8}: exact integers (<= 65280).  A blurred position outside the image stands
-  //    for the replicated border pixel of the BLURRED image (Sobel's own BORDER_REPLICATE), so it is evaluated at the
-  //    clamped position.
-  for (int i = tid; i < SH * BW; i += CQ_THREADS) {
-    int r = i / BW, bx = i - r * BW;
-    int cpx = clampi(x0 - 2 + bx, 0, W - 1);
-    int c0 = cpx - 3 - (x0 - 5);
-#pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
-      const uint8_t* p = &s_src[r][c0 * 3 + ch];
-      int s = 8 * (p[0] + p[18]) + 28 * (p[3] + p[15]) + 56 * (p[6] + p[12]) + 72 * p[9];
-      s_h[r][bx * 3 + ch] = (uint16_t)s;
-    }
-  }
-  __syncthreads();
-  // 3. vertical 7-tap, single rounding (sum + 2^15) >> 16
-  for (int i = tid; i < BH * BW * 3; i += CQ_THREADS) {
-    int by = i / (BW * 3), k = i - by * (BW * 3);
-    int cpy = clampi(y0 - 2 + by, 0, H - 1);
-    int r0 = cpy - 3 - (y0 - 5);
-    int s = 8 * (s_h[r0][k] + s_h[r0 + 6][k]) + 28 * (s_h[r0 + 1][k] + s_h[r0 + 5][k]) + 56 * (s_h[r0 + 2][k] + s_h[r0 + 4][k]) +
-            72 * s_h[r0 + 3][k];
-    s_b[by][k] = (uint8_t)((s + 32768) >> 16);
-  }
-  __syncthreads();
-  // 4. Sobel 3x3 per channel on the blurred tile, strongest channel (ties: first, linemod.cpp:275-292), angle bin
-  for (int i = tid; i < QH * QW; i += CQ_THREADS) {
-    int qy = i / QW, qx = i - qy * QW;
-    int sx = x0 - 1 + qx, sy = y0 - 1 + qy;
-    uint8_t v = 0;
-    if (sx > 0 && sx < W - 1 && sy > 0 && sy < H - 1) {   // the 1-px frame of quantized_unfiltered is zeroed (:318-325)
-      int bx = qx + 1, by = qy + 1;                        // blurred-tile index of this position
-      int best_m = -1, best_dx = 0, best_dy = 0;
-#pragma unroll
-      for (int ch = 0; ch < 3; ++ch) {
-        int a00 = s_b[by - 1][(bx - 1) * 3 + ch], a01 = s_b[by - 1][bx * 3 + ch], a02 = s_b[by - 1][(bx + 1) * 3 + ch];
-        int a10 = s_b[by][(bx - 1) * 3 + ch], a12 = s_b[by][(bx + 1) * 3 + ch];
-        int a20 = s_b[by + 1][(bx - 1) * 3 + ch], a21 = s_b[by + 1][bx * 3 + ch], a22 = s_b[by + 1][(bx + 1) * 3 + ch];
-        int dx = (a02 + 2 * a12 + a22) - (a00 + 2 * a10 + a20);
-        int dy = (a20 + 2 * a21 + a22) - (a00 + 2 * a01 + a02);
-        int m = dx * dx + dy * dy;
-        if (m > best_m) { best_m = m; best_dx = dx; best_dy = dy; }   // strict > keeps the earliest channel on ties
-      }
-      v = (uint8_t)(angle_q16((float)best_dx, (float)best_dy) & 7);
-      if ((float)best_m > thr_sq) v |= 0x80;
-    }
-    s_q[qy][qx] = v;
-  }
-  __syncthreads();
-  // 5. 3x3 histogram vote: majority (>= 5 of 9) of the bins, lowest bin wins ties (:346-381)
-  for (int i = tid; i < CQ_TH * CQ_TW; i += CQ_THREADS) {
-    int oy = i / CQ_TW, ox = i - oy * CQ_TW;
-    int x = x0 + ox, y = y0 + oy;
-    if (x >= W || y >= H) continue;
-    uint8_t out = 0;
-    if (x > 0 && x < W - 1 && y > 0 && y < H - 1 && (s_q[oy + 1][ox + 1] & 0x80)) {
-      uint32_t hist = 0;   // eight 4-bit counters
-#pragma unroll
-      for (int j = 0; j < 3; ++j)
-#pragma unroll
-        for (int k = 0; k < 3; ++k) hist += 1u << (4 * (s_q[oy + j][ox + k] & 7));
-      int best = 0, idx = 0;
-#pragma unroll
-      for (int b = 0; b < 8; ++b) {
-        int c = (hist >> (4 * b)) & 15;
-        if (c > best) { best = c; idx = b; }
-      }
-      if (best >= 5) out = (uint8_t)(1u << idx);
-    }
-    q[(size_t)y * W + x] = out;
-  }
-}
-
-__global__ void __launch_bounds__(CQ_THREADS) k_color_quantize(const uint8_t* __restrict__ bgr, int W, int H, float thr_sq,
-                                                               uint8_t* __restrict__ q) {
-  __shared__ __align__(16) uint8_t smem[CQ_SMEM_BYTES];
-  dev_color_quantize(bgr, W, H, thr_sq, q, blockIdx.x, blockIdx.y, smem);
-}
-
-void fl_launch_color_quantize(const uint8_t* bgr, int W, int H, float thr_sq, uint8_t* q, cudaStream_t s) {
-  dim3 grid((W + CQ_TW - 1) / CQ_TW, (H + CQ_TH - 1) / CQ_TH);
-  k_color_quantize<<<grid, CQ_THREADS, 0, s>>>(bgr, W, H, thr_sq, q);
-}
-
 #include "frontend_v2.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -257,97 +149,6 @@ void fl_launch_pyrdown_bgr(const uint8_t* src, int W, int H, uint8_t* dst, cudaS
 #define DQ_TH 16
 #define DQ_THREADS 256
 
-#define DQ_SMEM_BYTES ((DQ_TH + 14) * (DQ_TW + 14) * 2 + 16 + (((DQ_TH + 4) * (DQ_TW + 4) + 15) & ~15) + DQ_TH * (DQ_TW + 4) * 8)
-
-__device__ __forceinline__ void dev_depth_quantize(const uint16_t* __restrict__ depth, int W, int H, int dist_thr, int diff_thr,
-                                                   uint8_t* __restrict__ q, int bx, int by, uint8_t* smem) {
-  constexpr int RW = DQ_TW + 4, RH = DQ_TH + 4;      // raw label tile (median halo 2)
-  constexpr int SW = RW + 10, SH = RH + 10;          // depth tile (tap radius 5)
-  uint16_t(*s_d)[SW] = reinterpret_cast<uint16_t(*)[SW]>(smem);
-  uint8_t(*s_r)[RW] = reinterpret_cast<uint8_t(*)[RW]>(smem + ((SH * SW * 2 + 15) & ~15));
-  const int x0 = bx * DQ_TW, y0 = by * DQ_TH;
-  const int tid = threadIdx.x;
-  for (int i = tid; i < SH * SW; i += DQ_THREADS) {
-    int r = i / SW, c = i - r * SW;
-    int sy = y0 - 7 + r, sx = x0 - 7 + c;
-    s_d[r][c] = (sx >= 0 && sx < W && sy >= 0 && sy < H) ? depth[(size_t)sy * W + sx] : (uint16_t)0;
-  }
-  __syncthreads();
-  for (int i = tid; i < RH * RW; i += DQ_THREADS) {
-    int ry = i / RW, rx = i - ry * RW;
-    // medianBlur replicates the border of the label image; border labels are 0 (loop bounds :619, :624), so any
-    // position outside [5, W-7] x [5, H-7] - inside or outside the image - contributes 0.
-    int px = x0 - 2 + rx, py = y0 - 2 + ry;
-    uint8_t v = 0;
-    if (px >= 5 && px < W - 6 && py >= 5 && py < H - 6) {
-      int cy = ry + 5, cx = rx + 5;
-      int d = s_d[cy][cx];
-      if (d < dist_thr) {
-        int A0 = 0, A1 = 0, A3 = 0, b0 = 0, b1 = 0;
-#pragma unroll
-        for (int j = -5; j <= 5; j += 5)
-#pragma unroll
-          for (int ii = -5; ii <= 5; ii += 5) {
-            if (ii == 0 && j == 0) continue;
-            int delta = (int)s_d[cy + j][cx + ii] - d;
-            int f = abs(delta) < diff_thr ? 1 : 0;           // accumBilateral :567-579
-            A0 += f * ii * ii; A1 += f * ii * j; A3 += f * j * j;
-            b0 += f * ii * delta; b1 += f * j * delta;
-          }
-        int det = A0 * A3 - A1 * A1;                          // all fit int32
-        int ddx = A3 * b0 - A1 * b1;
-        int ddy = -A1 * b0 + A0 * b1;
-        float nx = (float)(617 * ddx), ny = (float)(617 * ddy), nz = (float)(-det * d);
-        float s = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(nx, nx), __fmul_rn(ny, ny)), __fmul_rn(nz, nz)));
-        if (s > 0.f) {
-          float inv = __fdiv_rn(1.0f, s);
-          nx = __fmul_rn(nx, inv); ny = __fmul_rn(ny, inv);
-          int v1 = (int)__fadd_rn(__fmul_rn(nx, 10.f), 10.f);   // C truncation :665-667
-          int v2 = (int)__fadd_rn(__fmul_rn(ny, 10.f), 10.f);
-          v = c_normal_plane[clampi(v2, 0, 19) * 20 + clampi(v1, 0, 19)];   // table is v3-independent
-        }
-      }
-    }
-    s_r[ry][rx] = v;
-  }
-  __syncthreads();
-  // 5x5 median (cv::medianBlur, :684).  The labels are one-hot bytes or 0 (NORMAL_LUT), i.e. 9 distinct values whose numeric
-  // order is the order of idx = 0 (for 0) or bit position + 1, so the median is read off a 9-bin histogram: bins of 5 bits
-  // packed in a u64, per-column histograms of 5 rows shared by the 5 pixels that overlap them.
-  unsigned long long(*s_ch)[RW] = reinterpret_cast<unsigned long long(*)[RW]>(smem + ((SH * SW * 2 + 15) & ~15) + ((RH * RW + 15) & ~15));
-  for (int i = tid; i < DQ_TH * RW; i += DQ_THREADS) {
-    const int oy = i / RW, rx = i - oy * RW;
-    unsigned long long hsum = 0;
-#pragma unroll
-    for (int j = 0; j < 5; ++j) hsum += 1ull << (5 * (32 - __clz((unsigned)s_r[oy + j][rx])));
-    s_ch[oy][rx] = hsum;
-  }
-  __syncthreads();
-  for (int i = tid; i < DQ_TH * DQ_TW; i += DQ_THREADS) {
-    const int oy = i / DQ_TW, ox = i - oy * DQ_TW;
-    const int x = x0 + ox, y = y0 + oy;
-    if (x >= W || y >= H) continue;
-    const unsigned long long hist = s_ch[oy][ox] + s_ch[oy][ox + 1] + s_ch[oy][ox + 2] + s_ch[oy][ox + 3] + s_ch[oy][ox + 4];
-    int c = 0, med = 0;                                  // 13th smallest of 25
-#pragma unroll
-    for (int b = 0; b < 9; ++b) {
-      c += (int)((hist >> (5 * b)) & 31);
-      if (c < 13) med = b + 1;
-    }
-    q[(size_t)y * W + x] = med == 0 ? (uint8_t)0 : (uint8_t)(1u << (med - 1));
-  }
-}
-
-__global__ void __launch_bounds__(DQ_THREADS) k_depth_quantize(const uint16_t* __restrict__ depth, int W, int H, int dist_thr,
-                                                               int diff_thr, uint8_t* __restrict__ q) {
-  __shared__ __align__(16) uint8_t smem[DQ_SMEM_BYTES];
-  dev_depth_quantize(depth, W, H, dist_thr, diff_thr, q, blockIdx.x, blockIdx.y, smem);
-}
-
-void fl_launch_depth_quantize(const uint16_t* depth, int W, int H, int dist_thr, int diff_thr, uint8_t* q, cudaStream_t s) {
-  dim3 grid((W + DQ_TW - 1) / DQ_TW, (H + DQ_TH - 1) / DQ_TH);
-  k_depth_quantize<<<grid, DQ_THREADS, 0, s>>>(depth, W, H, dist_thr, diff_thr, q);
-}
 
 // ------------------------------------------------------------------------------------------------
 // K4 nearest-neighbour x1/2 (cv::resize INTER_NEAREST to (W/2, H/2)) and mask application (copyTo(dst, mask))
@@ -540,6 +341,16 @@ void fl_launch_spread_lm(const uint8_t* q, fl_level_geom g, uint8_t* lm_mod, uin
 //   wave k >= 1 : colour quantise Lk | NN-downsample depth labels Lk | pyrDown Lk->Lk+1 | spread+LM of level k-1 (all modalities)
 //   last wave   : spread+LM of the coarsest level
 // ------------------------------------------------------------------------------------------------
+// bounded in-grid wait: true = stop waiting (this CTA timed out, or another one already did); see k_front_end_wave
+__device__ __forceinline__ bool fe_dep_give_up(const fl_fe_wave& w, int job, long long t0) {
+  if (w.dep_error && *reinterpret_cast<volatile int*>(w.dep_error) != 0) return true;
+  if (clock64() - t0 <= (1ll << 31)) return false;
+  if (w.dep_error) atomicCAS(w.dep_error, 0, 1 + job);
+  if (w.dep_error_host) *reinterpret_cast<volatile int*>(w.dep_error_host) = 1 + job;
+  __threadfence_system();
+  return true;
+}
+
 __global__ void __launch_bounds__(256, 8) k_front_end_wave(fl_fe_wave w) {
   extern __shared__ __align__(16) uint8_t smem_dyn[];
   const int b = blockIdx.x;
@@ -565,16 +376,19 @@ __global__ void __launch_bounds__(256, 8) k_front_end_wave(fl_fe_wave w) {
         for (;;) {
           asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(c) : "memory");
           if ((int)(v - jb.wait_row_target) >= 0) break;
-          if (clock64() - t0 > (1ll << 31)) { if (w.dep_error) *w.dep_error = 1 + j; __threadfence_system(); __trap(); }
+          if (fe_dep_give_up(w, j, t0)) break;
           __nanosleep(64);
         }
       }
     }
     __syncthreads();
   } else if (jb.wait_slot >= 0) {
-    // In-grid dependency: CTAs are dispatched in blockIdx order and a producing job always precedes its consumers in the grid,
-    // so every producer CTA is resident (or done) before a consumer starts to wait here.  The wait is bounded: after ~1 s it gives
-    // up, records the job in dep_error and traps (the host's next CUDA call fails with FL_ERR_CUDA) instead of hanging the device.
+    // In-grid dependency: a producing job always precedes its consumers in the grid and CTAs are dispatched in blockIdx order on
+    // every configuration this was run on, so every producer CTA is resident (or done) before a consumer starts to wait here.
+    // CUDA does not GUARANTEE that order (MPS time slicing, a debugger, compute-sanitizer, a future scheduler), so the wait is
+    // bounded: after ~1 s the CTA records the job in dep_error (device word for the other waiters, mapped host word for the
+    // library), every waiter of the grid gives up at once, the frame's result is discarded by the host, which re-runs the frame
+    // as one launch per wave (no in-grid waits) and keeps this handle on that path (fe_dep_give_up, fl_match_wait).
     if (threadIdx.x == 0) {
       const unsigned* c = w.counters + jb.wait_slot;
       const long long t0 = clock64();
@@ -582,19 +396,13 @@ __global__ void __launch_bounds__(256, 8) k_front_end_wave(fl_fe_wave w) {
       for (;;) {
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(c) : "memory");
         if ((int)(v - jb.wait_target) >= 0) break;
-        if (clock64() - t0 > (1ll << 31)) {           // never observed; fail loudly (the next CUDA call of the host reports it) instead of computing on stale data
-          if (w.dep_error) *w.dep_error = 1 + j;
-          __threadfence_system();
-          __trap();
-        }
+        if (fe_dep_give_up(w, j, t0)) break;
         __nanosleep(64);
       }
     }
     __syncthreads();
   }
   switch (jb.kind) {
-    case FL_JOB_COLOR: { const int tile = local + jb.p0; dev_color_quantize(jb.src, jb.W, jb.H, jb.thr_sq, jb.dst, tile % jb.gx, tile / jb.gx, smem_dyn); break; }
-    case FL_JOB_DEPTH: dev_depth_quantize(reinterpret_cast<const uint16_t*>(jb.src), jb.W, jb.H, jb.p0, jb.p1, jb.dst, local % jb.gx, local / jb.gx, smem_dyn); break;
     case FL_JOB_PYRDOWN: dev_pyrdown_bgr(jb.src, jb.W, jb.H, jb.dst, local, jb.p0 != 0); break;
     case FL_JOB_RESIZE: dev_resize_nn_half(jb.src, jb.W, jb.H, jb.dst, local); break;
     case FL_JOB_SPREAD: dev_spread_lm_any(jb.src, jb.g, jb.dst, jb.dst2, local % jb.gx, local / jb.gx, smem_dyn, jb.p0); break;
@@ -620,24 +428,6 @@ __global__ void __launch_bounds__(256, 8) k_front_end_wave(fl_fe_wave w) {
   }
 }
 
-// part / n_parts: the tiles of one image may be spread over several waves (the job then covers tiles [first, first + count))
-void fl_fe_add_color(fl_fe_wave* w, const uint8_t* bgr, int W, int H, float thr_sq, uint8_t* q, int part, int n_parts) {
-  const int gx = (W + CQ_TW - 1) / CQ_TW, tiles = gx * ((H + CQ_TH - 1) / CQ_TH);
-  const int first = (int)((long long)tiles * part / n_parts), last = (int)((long long)tiles * (part + 1) / n_parts);
-  if (last <= first) return;
-  fl_fe_job& j = w->job[w->n_jobs++];
-  j.wait_slot = -1; j.signal_slot = -1; j.wait_target = 0; j.row_base = -1; j.wait_row_base = -1; j.wait_row_shift = 0; j.wait_row_count = 0; j.wait_row_target = 0;
-  j.kind = FL_JOB_COLOR; j.src = bgr; j.dst = q; j.dst2 = nullptr; j.W = W; j.H = H; j.thr_sq = thr_sq;
-  j.gx = gx; j.p0 = first; j.p1 = last - first; j.cta_begin = w->n_ctas; w->n_ctas += last - first;
-  w->smem = w->smem > (size_t)CQ_SMEM_BYTES ? w->smem : (size_t)CQ_SMEM_BYTES;
-}
-void fl_fe_add_depth(fl_fe_wave* w, const uint16_t* depth, int W, int H, int dist_thr, int diff_thr, uint8_t* q) {
-  fl_fe_job& j = w->job[w->n_jobs++];
-  j.wait_slot = -1; j.signal_slot = -1; j.wait_target = 0; j.row_base = -1; j.wait_row_base = -1; j.wait_row_shift = 0; j.wait_row_count = 0; j.wait_row_target = 0;
-  j.kind = FL_JOB_DEPTH; j.src = reinterpret_cast<const uint8_t*>(depth); j.dst = q; j.dst2 = nullptr; j.W = W; j.H = H; j.p0 = dist_thr; j.p1 = diff_thr;
-  j.gx = (W + DQ_TW - 1) / DQ_TW; j.cta_begin = w->n_ctas; w->n_ctas += j.gx * ((H + DQ_TH - 1) / DQ_TH);
-  w->smem = w->smem > (size_t)DQ_SMEM_BYTES ? w->smem : (size_t)DQ_SMEM_BYTES;
-}
 void fl_fe_add_color_v2(fl_fe_wave* w, const uint8_t* bgr, int W, int H, float thr_sq, uint8_t* q) {
   fl_fe_job& j = w->job[w->n_jobs++];
   j.wait_slot = -1; j.signal_slot = -1; j.wait_target = 0; j.row_base = -1; j.wait_row_base = -1; j.wait_row_shift = 0; j.wait_row_count = 0; j.wait_row_target = 0;
@@ -693,15 +483,7 @@ void fl_fe_add_spread(fl_fe_wave* w, const uint8_t* q, fl_level_geom g, uint8_t*
   size_t sm = spread_smem_bytes(g.T);
   w->smem = w->smem > sm ? w->smem : sm;
 }
-void fl_launch_fe_wave(const fl_fe_wave& w, cudaStream_t s) {
-  if (w.n_ctas > 0) fl_launch_pdl(k_front_end_wave, dim3(w.n_ctas), dim3(256), w.smem, s, w);
+cudaError_t fl_launch_fe_wave(const fl_fe_wave& w, cudaStream_t s) {
+  return w.n_ctas > 0 ? fl_launch(k_front_end_wave, dim3(w.n_ctas), dim3(256), w.smem, s, w) : cudaSuccess;
 }
 
-// every hot kernel asks for the maximum shared-memory carveout so that the SMs never re-partition L1/shared memory between
-// the launches of one frame (the staged similarity kernel needs > 200 KB)
-void fl_prefer_smem_carveout_frontend() {
-  cudaFuncSetAttribute(k_front_end_wave, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-  cudaFuncSetAttribute(k_spread_lm, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-  cudaFuncSetAttribute(k_color_quantize, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-  cudaFuncSetAttribute(k_depth_quantize, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-}

@@ -145,24 +145,34 @@ extern "C" int fl_group_match(fl_group* g, const uint8_t* bgr, size_t bgr_stride
   *count = 0;
   if (W <= 0 || H <= 0 || W > g->max_w || H > g->max_h) return FL_ERR_SIZE;
   if ((bgr && bgr_stride < (size_t)W * 3) || (depth && depth_stride < (size_t)W * 2)) return FL_ERR_SIZE;
-  ++g->epoch;
-  int first_err = FL_OK;
-  for (int i = 0; i < g->n; ++i) {                              // enqueue on every handle; nothing waits until all are under way
-    GCUDA(cudaSetDevice(g->device[i]));
-    cudaStream_t s = static_cast<cudaStream_t>(fl_stream(g->h[i]));
-    if (depth) GCUDA(cudaMemcpy2DAsync(g->d_depth[i], (size_t)W * 2, depth, depth_stride, (size_t)W * 2, H, cudaMemcpyHostToDevice, s));
-    if (bgr) GCUDA(cudaMemcpy2DAsync(g->d_bgr[i], (size_t)W * 3, bgr, bgr_stride, (size_t)W * 3, H, cudaMemcpyHostToDevice, s));
-    const int rc = fl_match_shard_exchange_device_async(g->h[i], bgr ? g->d_bgr[i] : nullptr, depth ? g->d_depth[i] : nullptr, W, H, threshold, class_filter, n_filter,
-                                                        i, g->n, g->peers.data(), g->cap, g->block[i], g->epoch);
-    if (rc != FL_OK && first_err == FL_OK) first_err = rc;
-    if (rc != FL_OK) break;                                      // (the ranks already launched will report the missing peer instead of hanging)
+  // (a second attempt only when a handle's single-launch front end timed out on an in-grid dependency during the first: that handle
+  //  has switched itself to per-wave launches - fl_match_wait - and asks for the frame again; every rank has to take part in it)
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    ++g->epoch;
+    int first_err = FL_OK;
+    bool switched = false;
+    int launched = 0;
+    for (int i = 0; i < g->n; ++i) {                            // enqueue on every handle; nothing waits until all are under way
+      GCUDA(cudaSetDevice(g->device[i]));
+      cudaStream_t s = static_cast<cudaStream_t>(fl_stream(g->h[i]));
+      if (depth) GCUDA(cudaMemcpy2DAsync(g->d_depth[i], (size_t)W * 2, depth, depth_stride, (size_t)W * 2, H, cudaMemcpyHostToDevice, s));
+      if (bgr) GCUDA(cudaMemcpy2DAsync(g->d_bgr[i], (size_t)W * 3, bgr, bgr_stride, (size_t)W * 3, H, cudaMemcpyHostToDevice, s));
+      const int rc = fl_match_shard_exchange_device_async(g->h[i], bgr ? g->d_bgr[i] : nullptr, depth ? g->d_depth[i] : nullptr, W, H, threshold, class_filter, n_filter,
+                                                          i, g->n, g->peers.data(), g->cap, g->block[i], g->epoch);
+      if (rc != FL_OK) { first_err = rc; break; }                // (the ranks already launched report the missing peer instead of hanging)
+      ++launched;
+    }
+    for (int i = 0; i < launched; ++i) {
+      cudaSetDevice(g->device[i]);
+      const int forced = fl_debug_option(g->h[i], FL_OPT_FE_FORCED_WAVES, 0);
+      const int rc = fl_match_wait(g->h[i]);
+      if (rc == FL_ERR_STATE && !forced && fl_debug_option(g->h[i], FL_OPT_FE_FORCED_WAVES, 0) == 1) switched = true;   // resubmit
+      else if (rc != FL_OK && first_err == FL_OK) first_err = rc;                                                        // (incl. a peer that never arrived)
+    }
+    if (first_err != FL_OK) return first_err;
+    if (!switched) break;
+    if (attempt == 1) { fl_set_error("fl_group_match: the front end timed out twice"); return FL_ERR_STATE; }
   }
-  for (int i = 0; i < g->n; ++i) {
-    cudaSetDevice(g->device[i]);
-    const int rc = fl_match_wait(g->h[i]);
-    if (rc != FL_OK && rc != FL_ERR_STATE && first_err == FL_OK) first_err = rc;
-  }
-  if (first_err != FL_OK) return first_err;
   GCUDA(cudaSetDevice(g->device[0]));
   return fl_match_fetch(g->h[0], out, capacity, count);
 }

@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(SG_THREADS) k_similarity_global(fl_tdb db, fl_
 void fl_launch_similarity_global(fl_tdb db, fl_level_geom g, const uint8_t* lm_level, float threshold, fl_match_t* cand, int cap,
                                  int* d_count, cudaStream_t s) {
   if (db.n_templates > 0)
-    fl_launch_pdl(k_similarity_global<false>, dim3(db.n_templates), dim3(SG_THREADS), 0, s, db, g, lm_level, threshold, cand, cap, d_count, 0, (uint16_t*)nullptr);
+    fl_launch(k_similarity_global<false>, dim3(db.n_templates), dim3(SG_THREADS), 0, s, db, g, lm_level, threshold, cand, cap, d_count, 0, (uint16_t*)nullptr);
 }
 void fl_launch_similarity_debug(fl_tdb db, fl_level_geom g, const uint8_t* lm_level, int t, uint16_t* out, cudaStream_t s) {
   k_similarity_global<true><<<1, SG_THREADS, 0, s>>>(db, g, lm_level, 0.f, nullptr, 0, nullptr, t, out);
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(RF_THREADS) k_refine_level(fl_tdb db, fl_level
 void fl_launch_refine_level(fl_tdb db, fl_level_geom g, int level, const uint8_t* lm_level, float threshold, fl_match_t* cand,
                             int cap, const int* d_count, cudaStream_t s) {
   int grid = min(cap, 148 * 4);
-  if (grid > 0) fl_launch_pdl(k_refine_level, dim3(grid), dim3(RF_THREADS), 0, s, db, g, level, lm_level, threshold, cand, cap, d_count);
+  if (grid > 0) fl_launch(k_refine_level, dim3(grid), dim3(RF_THREADS), 0, s, db, g, level, lm_level, threshold, cand, cap, d_count);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -728,14 +728,13 @@ __global__ void __launch_bounds__(1024) k_unique_big(const fl_sort_key* __restri
 // on different devices may be driven by different host threads.
 static bool fl_once_per_device(int which) {
   static std::mutex mu;
-  static bool done[2][FL_MAX_DEVICES];
+  static bool done[1][FL_MAX_DEVICES];
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= FL_MAX_DEVICES) return false;
   std::lock_guard<std::mutex> lk(mu);
   if (done[which][dev]) return true;
   const int bytes = SORT_SMEM_LARGE * (int)sizeof(fl_sort_key);
-  const cudaError_t e = which == 0 ? cudaFuncSetAttribute(k_sort_unique_small, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)
-                                   : cudaFuncSetAttribute(k_refine_sort<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  const cudaError_t e = cudaFuncSetAttribute(k_sort_unique_small, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e != cudaSuccess) return false;
   done[which][dev] = true;
   return true;
@@ -745,32 +744,24 @@ static bool fl_once_per_device(int which) {
 int fl_launch_sort_unique(fl_lists L, fl_xchg X, int key_cap, fl_match_t* d_out, int out_cap, int* d_out_count, int* d_hdr,
                           int* h_hdr, fl_match_t* h_first, int h_first_cap, cudaStream_t s) {
   if (!fl_once_per_device(0)) return -1;
-  return fl_launch_pdl(k_sort_unique_small, dim3(1), dim3(1024), (size_t)SORT_SMEM_LARGE * sizeof(fl_sort_key), s, L, X, key_cap, (int)SORT_SMEM_LARGE, d_out,
+  return fl_launch(k_sort_unique_small, dim3(1), dim3(1024), (size_t)SORT_SMEM_LARGE * sizeof(fl_sort_key), s, L, X, key_cap, (int)SORT_SMEM_LARGE, d_out,
                        out_cap, d_out_count, d_hdr, h_hdr, h_first, h_first_cap) == cudaSuccess ? 1 : -1;
 }
 
-// small = true: one 256-thread group per CTA, 592 CTAs, shared memory for 1,024 keys + staging (no opt-in needed): as cheap
-// to launch as k_refine_level; lists with more than 1,024 records come back flagged and the host runs the stand-alone sort.
-// small = false: four groups per CTA and the full 8,192-key sort (developer A/B, slower to launch).
+// One 256-thread group per CTA, 4 CTAs per SM, shared memory for 1,024 keys + staging (no opt-in needed): as cheap to launch as
+// k_refine_level; lists with more than 1,024 records come back flagged and the host runs the stand-alone sort.  (A variant with four
+// groups per CTA and the full 8,192-key sort inside was measured slower to launch than the launch it saved, and removed; launching
+// this kernel programmatically behind the similarity kernel was slower too - 80.4 vs 76.3 us per frame: its 592 pre-launched CTAs
+// take SM slots the similarity CTAs' tails still need.)
 int fl_launch_refine_sort(fl_tdb db, const fl_refine_args& ra, float threshold, fl_match_t* cand, int cap, const int* d_count, int* done_ctr, int n_sm,
                           fl_lists L, fl_xchg X, int key_cap, fl_match_t* d_out, int out_cap, int* d_out_count, int* d_hdr,
-                          int* h_hdr, fl_match_t* h_first, int h_first_cap, bool small, cudaStream_t s) {
-  if (small) {
-    const int keys = 1024;
-    static const bool pdl_refine = getenv("FL_PDL_REFINE") != nullptr;       // developer A/B: pre-launch behind the similarity kernel
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof cfg);
-    cfg.gridDim = dim3(4 * (n_sm > 0 ? n_sm : 148)); cfg.blockDim = dim3(RF_THREADS); cfg.dynamicSmemBytes = (size_t)(keys + 1280) * sizeof(fl_sort_key); cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = (fl_pdl_enabled() || pdl_refine) ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, k_refine_sort<1>, db, ra, threshold, cand, cap, d_count, done_ctr, L, X, key_cap, keys, d_out, out_cap, d_out_count, d_hdr, h_hdr,
-                              h_first, h_first_cap) == cudaSuccess ? 1 : -1;
-  }
-  if (!fl_once_per_device(1)) return -1;
-  return fl_launch_pdl(k_refine_sort<4>, dim3(n_sm > 0 ? n_sm : 148), dim3(4 * RF_THREADS), (size_t)SORT_SMEM_LARGE * sizeof(fl_sort_key), s, db, ra, threshold, cand,
-                       cap, d_count, done_ctr, L, X, key_cap, (int)SORT_SMEM_LARGE, d_out, out_cap, d_out_count, d_hdr, h_hdr, h_first, h_first_cap) == cudaSuccess ? 1 : -1;
+                          int* h_hdr, fl_match_t* h_first, int h_first_cap, cudaStream_t s) {
+  const int keys = 1024;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(4 * (n_sm > 0 ? n_sm : 148)); cfg.blockDim = dim3(RF_THREADS); cfg.dynamicSmemBytes = (size_t)(keys + 1280) * sizeof(fl_sort_key); cfg.stream = s;
+  return cudaLaunchKernelEx(&cfg, k_refine_sort<1>, db, ra, threshold, cand, cap, d_count, done_ctr, L, X, key_cap, keys, d_out, out_cap, d_out_count, d_hdr, h_hdr,
+                            h_first, h_first_cap) == cudaSuccess ? 1 : -1;
 }
 
 // second stage, only when the one-CTA kernel reported more records than its shared memory holds (the host has read the flag and the
@@ -791,9 +782,3 @@ int fl_launch_sort_unique_big(fl_lists L, fl_sort_key* keys, int key_cap, int n_
   return launches;
 }
 
-void fl_prefer_smem_carveout_similarity() {
-  cudaFuncSetAttribute(k_refine_level, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-  cudaFuncSetAttribute(k_sort_unique_small, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-  cudaFuncSetAttribute(k_build_keys, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-  cudaFuncSetAttribute(k_similarity_global<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-}

@@ -1,6 +1,5 @@
 // K6, staged variant: global similarity of all templates at the coarsest pyramid level with the linear memories staged
-// through shared memory by TMA bulk copies (cp.async.bulk + mbarrier, multicast across a thread-block cluster),
-// accumulators in registers.
+// through shared memory by TMA bulk copies (cp.async.bulk + mbarrier), accumulators in registers.
 //
 // Why: one template reads 62 byte streams of ~1,200 B from 62 of the 1,024 linear-memory rows (2 modalities x 8 labels x
 // T*T rows); over 8,000 templates that is ~0.6 GB of byte traffic per frame against a 1.2 MB working set, so the bound is
@@ -9,10 +8,10 @@
 //
 //   * a persistent CTA owns a batch of templates (one warp per template slot, TPW slots per warp) and keeps their
 //     packed-u8 similarity accumulators in registers for the whole kernel;
-//   * one elected thread per CTA streams phase q + n_buf into the buffer that was just released; with a cluster of CL
-//     CTAs every CTA fetches 1/CL of the phase and multicasts it into the shared memory of all CL CTAs, so the L2 -> SM
-//     traffic of the kernel is (working set) x (number of CTAs) / CL.  Completion is counted in bytes on an mbarrier
-//     (expect_tx); a buffer is released when every consumer warp of every CTA of the cluster has arrived on "empty";
+//   * one elected thread per CTA streams phase q + n_buf into the buffer that was just released.  Completion is counted in
+//     bytes on an mbarrier (expect_tx); a buffer is released when every consumer warp has arrived on "empty".  (A variant
+//     that fetched 1/CL of a phase per CTA of a CL-CTA cluster and multicast it was measured SLOWER - 30 vs 25 us loop: the
+//     L2 -> SM stream is not the limiter, the cluster-wide buffer release is - and was removed.)
 //   * features were sorted by phase once per frame geometry (k_pack_staged).  A CTA copies its templates' feature words
 //     and per-phase prefix counts into shared memory, so the inner loop is: one broadcast LDS for the next feature word,
 //     NW + 1 LDS of linear-memory words, NW funnel shifts, NW adds;
@@ -25,7 +24,6 @@
 // template has <= 63 coarsest-level features over all modalities (so one u8 lane holds the total, 63*4 = 252) and the same
 // width/height for all modalities at that level (what cropTemplates :52-96 produces); otherwise the baseline kernel runs.
 #include "fl_internal.cuh"
-#include "refine_warp.cuh"
 #include <stdlib.h>
 #include <mutex>
 
@@ -51,45 +49,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "WAIT_DONE:\n"
       "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-// wait with cluster-scope acquire: the arrivals may come from the other CTAs of the cluster
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAITC_LOOP:\n"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAITC_DONE;\n"
-      "bra WAITC_LOOP;\n"
-      "WAITC_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
-__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
-  asm volatile(
-      "{\n"
-      ".reg .b32 ra;\n"
-      "mapa.shared::cluster.u32 ra, %0, %1;\n"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(cta) : "memory");
 }
 // 1-D TMA: bulk copy global -> shared, completion counted in bytes on the mbarrier
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
                "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-// the same copy delivered to the same offsets (data and barrier) of every CTA in cta_mask
-__device__ __forceinline__ void bulk_g2s_multicast(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t cta_mask) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask) : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
 __device__ __forceinline__ unsigned long long globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
@@ -150,13 +116,9 @@ void fl_launch_pack_staged(fl_tdb db, fl_level_geom g, fl_staged_plan plan, cuda
 // One feature of one template: lane g owns the NW consecutive 32-bit words [g*NW, (g+1)*NW) of the similarity map, so
 // its window is the NW + 1 consecutive words starting at its base + the feature's word offset: NW + 1 loads (instead of
 // two per word), one funnel shift and one add per word.  NW is odd, so the 32 lanes of one load hit 32 different banks.
-#ifndef FL_SS_IMAD
-#define FL_SS_IMAD 0      // 1: every other add goes to the FMA pipe as IMAD (x * one + acc, `one` a run-time 1) to take load off the ALU pipe the
-                          // funnel shifts use.  Measured on B200: SLOWER (loop 27.3 vs 25.9 us) - two-operand IADD3s fold two adds into one
-                          // issue slot, IMADs do not, and issue slots matter more here than the ALU pipe.
-#endif
+// (Moving every other add to the FMA pipe as an IMAD was measured slower - loop 27.3 vs 25.9 us: IADD3 folds two adds into one issue slot.)
 template <int NW>
-__device__ __forceinline__ void accumulate_feature(const uint8_t* __restrict__ lane_base, uint32_t fw, uint32_t (&acc)[NW], uint32_t one) {
+__device__ __forceinline__ void accumulate_feature(const uint8_t* __restrict__ lane_base, uint32_t fw, uint32_t (&acc)[NW]) {
   const uint32_t* w = reinterpret_cast<const uint32_t*>(lane_base + (fw >> 5));
   constexpr int CH = 12;                                      // loads in flight per chunk (register budget)
   uint32_t carry = w[0];
@@ -170,26 +132,21 @@ __device__ __forceinline__ void accumulate_feature(const uint8_t* __restrict__ l
     for (int i = 0; i < CH; ++i)
       if (c + i < NW) {
         const uint32_t x = __funnelshift_r(v[i], v[i + 1], fw);   // shift = low 5 bits; four u8 lanes, no carry (sums <= 252)
-        if (FL_SS_IMAD && ((c + i) & 1)) asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc[c + i]) : "r"(x), "r"(one));
-        else acc[c + i] += x;
+        acc[c + i] += x;
       }
     carry = v[(NW - c) < CH ? (NW - c) : CH];
   }
 }
 
-// FUSE: the kernel also refines its candidates up the pyramid (fl_refine_candidate_warp) and appends FINAL matches to the
-// list: coarsest-level candidates go to a per-CTA list in shared memory, then every warp of the CTA takes candidates off
-// that list.  Candidates beyond the list's capacity are refined on the spot by the warp that found them.
-template <int NW, int TPW, int CL>
+// (Refining the candidates in this kernel's own tail was measured much slower than the separate launch - stage 143 us vs 43 + 11 us:
+// candidates cluster in the few CTAs that own a matching template while the other 140 CTAs idle - and was removed.)
+template <int NW, int TPW>
 __global__ void __launch_bounds__(1024, 1) k_similarity_staged(const __grid_constant__ fl_tdb db, fl_level_geom g, const uint8_t* __restrict__ lm_level, float threshold,
-                                                               fl_match_t* __restrict__ cand, int cap, int* __restrict__ d_count,
-                                                               fl_staged_plan plan, const __grid_constant__ fl_refine_args ra) {
-  extern __shared__ __align__(128) uint8_t s_dyn[];          // [n_buf x buf_bytes][tpc x int4 meta][tpc x 64 feature words + 4][tpc x pre_stride][fuse_list_cap x int4]
+                                                               fl_match_t* __restrict__ cand, int cap, int* __restrict__ d_count, fl_staged_plan plan) {
+  extern __shared__ __align__(128) uint8_t s_dyn[];          // [n_buf x buf_bytes][tpc x int4 meta][tpc x 64 feature words + 4][tpc x pre_stride][emission staging]
   __shared__ __align__(8) uint64_t s_full[SS_NBUF_MAX], s_empty[SS_NBUF_MAX];
-  __shared__ int s_ncand;
   __shared__ int s_emit_lock;                                 // the CTA's emission staging area is taken by one warp at a time
   __shared__ __align__(8) uint64_t s_aux;                     // completion of the bulk copy of this CTA's feature lists
-  const bool fuse = plan.fuse_list_cap > 0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_cwarps = (blockDim.x >> 5) - 1;                 // consumer warps; the last warp is the TMA producer
   const int t_begin = blockIdx.x * plan.tpc;
@@ -199,22 +156,19 @@ __global__ void __launch_bounds__(1024, 1) k_similarity_staged(const __grid_cons
   int4* s_meta = reinterpret_cast<int4*>(s_dyn + (size_t)n_buf * plan.buf_bytes);
   uint32_t* s_feat = reinterpret_cast<uint32_t*>(s_meta + plan.tpc);
   uint8_t* s_pre = reinterpret_cast<uint8_t*>(s_feat + plan.tpc * SS_MAXF + 4);
-  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
-  // clusters walk the phases in rotated order so that, at any moment, different SMs pull different linear-memory rows
+  // CTAs walk the phases in rotated order so that, at any moment, different SMs pull different linear-memory rows
   // out of L2 instead of all hammering the same lines (the sums are order independent)
-  const int rot = (int)(((blockIdx.x / CL) * 7u) % (unsigned)n_phases);
+  const int rot = (int)((blockIdx.x * 7u) % (unsigned)n_phases);
   unsigned long long* trace = plan.trace ? plan.trace + (size_t)blockIdx.x * 8 : nullptr;
   if (trace && tid == 0) { trace[0] = globaltimer(); unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); trace[5] = smid; }
 
-  int4* s_list = reinterpret_cast<int4*>(s_dyn + plan.fuse_list_off);      // {template, x | y << 16, similarity bits, class}
   if (tid == 0) {
-    s_ncand = 0; s_emit_lock = 0;
-    for (int b = 0; b < n_buf; ++b) { mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], n_cwarps * CL); }
+    s_emit_lock = 0;
+    for (int b = 0; b < n_buf; ++b) { mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], n_cwarps); }
     mbar_init(&s_aux, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (CL > 1) cluster_sync_all();                             // every CTA's barriers are initialised before any peer touches them
   if (warp != n_cwarps) {
     // consumers: this CTA's per-template records, feature words and prefix counts -> shared memory while the producer
     // already streams the first phases; slots past the end / of disabled classes get no features and no positions
@@ -223,7 +177,7 @@ __global__ void __launch_bounds__(1024, 1) k_similarity_staged(const __grid_cons
       int4 m = make_int4(0, 0, 0, 0);
       if (t < t_end) {
         m = plan.gmeta[t];
-        m.w = (db.L == 1 && !fuse) ? db.tid_of[t] : t;        // the id candidates carry (see k_similarity_global); fused: always local
+        m.w = db.L == 1 ? db.tid_of[t] : t;                   // the id candidates carry (see k_similarity_global)
         if (!db.class_enabled[m.z]) m.x = 0;                  // no positions -> no candidates
         // raw threshold int(2 nf + (threshold / 100) 2 nf + 0.5f) in fp32 (:1487); stored biased by 1, clamped to [-1, 255]
         const int nf = m.y;
@@ -264,7 +218,7 @@ __global__ void __launch_bounds__(1024, 1) k_similarity_staged(const __grid_cons
       fl_grid_dep_wait();                                     // the linear memories are written by the previous kernel of the stream
       for (int q = 0; q < n_phases; ++q) {
         const int b = q % n_buf;
-        if (q >= n_buf) { if (CL > 1) mbar_wait_cluster(&s_empty[b], ((q / n_buf) - 1) & 1); else mbar_wait(&s_empty[b], ((q / n_buf) - 1) & 1); }
+        if (q >= n_buf) mbar_wait(&s_empty[b], ((q / n_buf) - 1) & 1);
         int p = q + rot; if (p >= n_phases) p -= n_phases;
         const int ml = p / plan.n_rowblocks, rb = p - ml * plan.n_rowblocks;
         const int m = ml >> 3, lab = ml & 7;
@@ -272,13 +226,7 @@ __global__ void __launch_bounds__(1024, 1) k_similarity_staged(const __grid_cons
         const int rows = min(plan.phase_rows, g.T * g.T - rb * plan.phase_rows);
         const uint32_t bytes = (uint32_t)(((size_t)rows * g.cells + plan.halo_bytes + 15) & ~(size_t)15);
         mbar_expect_tx(&s_full[b], bytes);                    // the whole phase lands here, whoever fetches it
-        if (CL == 1) {
-          bulk_g2s(s_buf + (size_t)b * plan.buf_bytes, src, bytes, &s_full[b]);
-        } else {
-          const uint32_t chunk = ((bytes / CL) + 15) & ~15u;
-          const uint32_t o = crank * chunk;
-          if (o < bytes) bulk_g2s_multicast(s_buf + (size_t)b * plan.buf_bytes + o, src + o, min(chunk, bytes - o), &s_full[b], (uint16_t)((1u << CL) - 1));
-        }
+        bulk_g2s(s_buf + (size_t)b * plan.buf_bytes, src, bytes, &s_full[b]);
       }
       if (trace) trace[7] = globaltimer();
     }
@@ -302,7 +250,6 @@ __global__ void __launch_bounds__(1024, 1) k_similarity_staged(const __grid_cons
     }
     int b = 0, p = rot;
     uint32_t par = 0;
-    const uint32_t one = (uint32_t)(plan.cluster > 0);        // 1, but not provably so: keeps the IMADs of accumulate_feature
     const uint8_t* lane_base0 = s_buf + lane * (NW * 4);
     for (int q = 0; q < n_phases; ++q) {
       mbar_wait(&s_full[b], par);
@@ -319,19 +266,13 @@ __global__ void __launch_bounds__(1024, 1) k_similarity_staged(const __grid_cons
           uint32_t fw = *fp;
           do {
             const uint32_t nx = fp[1];                        // next feature word (one past the list is a valid pad word)
-            accumulate_feature<NW>(lane_base, fw, acc[s], one);
+            accumulate_feature<NW>(lane_base, fw, acc[s]);
             fw = nx; ++fp;
           } while (fp < fe);
         }
       }
       __syncwarp();
-      if (lane == 0) {                                        // this warp is done with buffer b, in every CTA that writes into it
-        if (CL == 1) mbar_arrive(&s_empty[b]);
-        else {
-#pragma unroll
-          for (uint32_t c = 0; c < (uint32_t)CL; ++c) mbar_arrive_remote(&s_empty[b], c);
-        }
-      }
+      if (lane == 0) mbar_arrive(&s_empty[b]);                // this warp is done with buffer b
       if (++b == n_buf) { b = 0; par ^= 1; }
       if (++p == n_phases) p = 0;
     }
@@ -403,12 +344,10 @@ __global__ void __launch_bounds__(1024, 1) k_similarity_staged(const __grid_cons
         }
         if (trace && lane == 0) plan.trace[(size_t)plan.n_cta * 8 + 8 + ((size_t)blockIdx.x * 32 + warp) * 4 + 2] = globaltimer();   // before the atomic
         int base = 0;
-        if (lane == 0) base = fuse ? atomicAdd(&s_ncand, total) : atomicAdd(d_count, total);
+        if (lane == 0) base = atomicAdd(d_count, total);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (trace && lane == 0) plan.trace[(size_t)plan.n_cta * 8 + 8 + ((size_t)blockIdx.x * 32 + warp) * 4 + 3] = globaltimer();   // after the atomic
-        const int lim = fuse ? plan.fuse_list_cap : cap;
-        // list full (> fuse_list_cap coarse candidates from this CTA's templates): flag it; the host re-runs the frame unfused
-        if (fuse && base + total > lim && lane == 0 && plan.fuse_ovf) *plan.fuse_ovf = 1;
+        const int lim = cap;
         // pass 2: one lane per candidate
         for (int k = lane; k < total; k += 32) {
           const int slot = base + k;
@@ -418,12 +357,9 @@ __global__ void __launch_bounds__(1024, 1) k_similarity_staged(const __grid_cons
           const int r = j / g.Wd, c = j - r * g.Wd;
           const int mx = c * g.T + off, my = r * g.T + off;
           const float msim = __fadd_rn(__fdiv_rn(__fmul_rn((float)raw, 100.f), (float)(4 * nf)), 0.5f);
-          if (fuse) s_list[slot] = make_int4(meta.w, (mx & 0xFFFF) | (my << 16), __float_as_int(msim), meta.z);
-          else {
-            fl_match_t mt;
-            mt.x = mx; mt.y = my; mt.similarity = msim; mt.class_idx = meta.z; mt.template_id = meta.w;
-            cand[slot] = mt;
-          }
+          fl_match_t mt;
+          mt.x = mx; mt.y = my; mt.similarity = msim; mt.class_idx = meta.z; mt.template_id = meta.w;
+          cand[slot] = mt;
         }
       }
       __syncwarp();
@@ -431,27 +367,15 @@ __global__ void __launch_bounds__(1024, 1) k_similarity_staged(const __grid_cons
     }
     if (trace && lane == 0) { atomicMax(&trace[6], globaltimer()); plan.trace[(size_t)plan.n_cta * 8 + 8 + ((size_t)blockIdx.x * 32 + warp) * 4 + 1] = globaltimer(); }
   }
-  if (fuse) {
-    // ===== fused tail: every warp of the CTA (the producer warp too) refines candidates off the CTA's list =====
-    __syncwarp();                                             // the producer warp's lanes arrive separately
-    __syncthreads();
-    const int n_list = min(s_ncand, plan.fuse_list_cap);
-    const int n_warps = blockDim.x >> 5;
-    for (int i = warp; i < n_list; i += n_warps) {
-      const int4 c = s_list[i];
-      fl_refine_and_emit_warp(db, ra, threshold, c.x, c.w, (int)(short)(c.y & 0xFFFF), c.y >> 16, __int_as_float(c.z), cand, cap, d_count);
-    }
-  }
-  if (CL > 1) { __syncwarp(); cluster_sync_all(); }           // no CTA leaves while a peer may still write into it or signal it
   if (trace && tid == 0) trace[4] = globaltimer();
 }
 
 __global__ void k_stamp(unsigned long long* p) { *p = globaltimer(); }
 
-template <int NW, int TPW, int CL>
-static int launch_staged_cl(fl_tdb db, fl_level_geom g, const uint8_t* lm_level, float threshold, fl_match_t* cand, int cap, int* d_count,
-                            fl_staged_plan plan, const fl_refine_args& ra, cudaStream_t s) {
-  auto kern = k_similarity_staged<NW, TPW, CL>;
+template <int NW, int TPW>
+static int launch_staged(fl_tdb db, fl_level_geom g, const uint8_t* lm_level, float threshold, fl_match_t* cand, int cap, int* d_count,
+                         fl_staged_plan plan, cudaStream_t s) {
+  auto kern = k_similarity_staged<NW, TPW>;
   {   // the opt-in belongs to the (device, function) pair; per-device table, locked (handles on several devices / host threads)
     static std::mutex mu;
     static size_t configured[FL_MAX_DEVICES];
@@ -466,48 +390,22 @@ static int launch_staged_cl(fl_tdb db, fl_level_geom g, const uint8_t* lm_level,
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDim = dim3(plan.n_cta); cfg.blockDim = dim3(plan.block_threads); cfg.dynamicSmemBytes = plan.smem_bytes; cfg.stream = s;
-  cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // prologue (feature lists -> shared memory) overlaps the front end's tail
-  attr[1].val.programmaticStreamSerializationAllowed = 1;
-  // no cluster attribute for CL == 1: a plain launch (the attribute alone selects the cluster launch path)
-  // Programmatic dependent launch for THIS kernel: its CTAs become resident and run their prologue (barrier init, bulk copy of the
-  // feature lists, per-template thresholds) while the front-end launch drains; they touch the linear memories and the candidate
-  // list only after griddepcontrol.wait.  Measured: 79.9 -> 77.3 us per frame.  FL_NO_PDL_SIM=1 switches it off (A/B).
-  static const bool pdl_sim = getenv("FL_NO_PDL_SIM") == nullptr;
-  const bool pdl = (fl_pdl_enabled() || pdl_sim) && !plan.trace;
-  if (CL == 1) { attr[0] = attr[1]; cfg.numAttrs = pdl ? 1 : 0; }
-  else cfg.numAttrs = pdl ? 2 : 1;
-  cfg.attrs = attr;
+  // Programmatic dependent launch: the CTAs become resident and run their prologue (barrier init, bulk copy of the feature lists,
+  // per-template thresholds) while the front-end launch drains; they touch the linear memories and the candidate list only after
+  // griddepcontrol.wait.  Measured: 79.9 -> 77.3 us per frame.  Off while the developer timeline is recorded.
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = plan.trace ? 0 : 1;
   if (plan.trace) k_stamp<<<1, 1, 0, s>>>(plan.trace + (size_t)plan.n_cta * 8);
-  const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, db, g, lm_level, threshold, cand, cap, d_count, plan, ra);
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, db, g, lm_level, threshold, cand, cap, d_count, plan);
   if (plan.trace) k_stamp<<<1, 1, 0, s>>>(plan.trace + (size_t)plan.n_cta * 8 + 1);
   return e == cudaSuccess ? 0 : -1;
-}
-
-template <int NW, int TPW>
-static int launch_staged(fl_tdb db, fl_level_geom g, const uint8_t* lm_level, float threshold, fl_match_t* cand, int cap, int* d_count,
-                         fl_staged_plan plan, const fl_refine_args& ra, cudaStream_t s) {
-  switch (plan.cluster) {
-    case 1: return launch_staged_cl<NW, TPW, 1>(db, g, lm_level, threshold, cand, cap, d_count, plan, ra, s);
-    case 2: return launch_staged_cl<NW, TPW, 2>(db, g, lm_level, threshold, cand, cap, d_count, plan, ra, s);
-    case 4: return launch_staged_cl<NW, TPW, 4>(db, g, lm_level, threshold, cand, cap, d_count, plan, ra, s);
-  }
-  return -1;
-}
-
-static int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return (v && *v) ? atoi(v) : dflt;
 }
 
 // host planning: returns false if the geometry is not supported by the staged kernel.  max_positions = the largest
 // template_positions (linemod.cpp:1155) over the uploaded templates: only that many cells of a similarity map are ever
 // looked at, so the per-lane accumulator count NW is sized for it rather than for the whole grid.
-// Developer knobs (environment, read at planning time): FL_SS_CLUSTER = 1 | 2 | 4 CTAs per TMA-multicast cluster (default 1:
-// measured, multicast is slower here - the L2 -> SM stream is not the limiter and the cluster-wide buffer release costs more
-// than it saves), FL_SS_NBUF = 2..4 ring buffers (default 2).
 bool fl_plan_staged(const fl_level_geom& g, int M, int n_templates, int max_positions, int n_sm, fl_staged_plan* plan) {
   static const int kNW[] = {5, 7, 9, 11, 13, 15, 19, 23, 29, 37};
   fl_staged_plan p;
@@ -525,27 +423,19 @@ bool fl_plan_staged(const fl_level_geom& g, int M, int n_templates, int max_posi
   // unconditionally over 32 * NW + 1 words
   p.halo_bytes = 32 * p.nw_template * 4 + 16;
   if (p.halo_bytes + 16 > FL_LM_PAD) return false;
-  p.cluster = env_int("FL_SS_CLUSTER", 1);
-  if (p.cluster != 1 && p.cluster != 2 && p.cluster != 4) p.cluster = 1;
   // CTAs: whole waves of the SM count, up to 31 consumer warps x TPW templates each (+ 1 producer warp)
   const int per_cta_max = 31 * p.tpw;
   int n_cta = (n_templates + per_cta_max - 1) / per_cta_max;
   n_cta = ((n_cta + n_sm - 1) / n_sm) * n_sm;
   p.tpc = (n_templates + n_cta - 1) / n_cta;
   p.n_cta = (n_templates + p.tpc - 1) / p.tpc;
-  p.n_cta = ((p.n_cta + p.cluster - 1) / p.cluster) * p.cluster;   // whole clusters (trailing CTAs own no templates)
   const int warps = (p.tpc + p.tpw - 1) / p.tpw;
   p.block_threads = 32 * ((warps < 1 ? 1 : warps) + 1);
   // rows per phase: the ring has n_buf (default 2) buffers that share the CTA's shared memory with the feature lists; a phase
   // is the largest block of rows of one (modality, label) that fits a buffer; a row block must start 16-byte aligned in
   // global memory.  (Measured at VGA, 8k templates: 2 x 78 KB / 16 phases beats 4 x 46 KB / 32 phases, 24.6 vs 29.9 us.)
-  int nbuf = env_int("FL_SS_NBUF", 2);
-  if (nbuf < 2 || nbuf > SS_NBUF_MAX) nbuf = 2;
-  // Fused refinement tail (developer knob FL_FUSE_TAIL=1, OFF by default): measured on B200 at 8k templates it is SLOWER than the
-  // separate refinement launch (stage 143 us vs 43 + 11 us): candidates cluster in the few CTAs that own a matching template,
-  // one warp per candidate leaves ~2 features' loads in flight under the 64-register cap, and the other 140 CTAs idle.
-  const int fuse_cap = env_int("FL_FUSE_TAIL", 0) ? 2048 : 0;                    // candidates per CTA list (16 B each)
-  const size_t lists = (size_t)p.tpc * 16 + ((size_t)p.tpc * SS_MAXF + 4) * 4 + (size_t)p.tpc * (SS_MAX_PHASES + 2) + 32 + (size_t)fuse_cap * 16 + (size_t)p.nw_template * 128 * 5;   // upper bound (n_phases <= SS_MAX_PHASES)
+  const int nbuf = 2;
+  const size_t lists = (size_t)p.tpc * 16 + ((size_t)p.tpc * SS_MAXF + 4) * 4 + (size_t)p.tpc * (SS_MAX_PHASES + 2) + 32 + (size_t)p.nw_template * 128 * 5;   // upper bound (n_phases <= SS_MAX_PHASES)
   const size_t avail = 227 * 1024 - 1024;
   if (lists + 4096 > avail) return false;
   const size_t budget = ((avail - lists) / nbuf) & ~(size_t)127;
@@ -566,9 +456,7 @@ bool fl_plan_staged(const fl_level_geom& g, int M, int n_templates, int max_posi
   p.buf_bytes = (int)((((size_t)pr * g.cells + p.halo_bytes + 15) & ~(size_t)15) + 127) & ~127;
   p.pre_stride = (p.n_phases + 1 + 3) & ~3;
   p.smem_bytes = p.n_buf * p.buf_bytes + p.tpc * 16 + (p.tpc * SS_MAXF + 4) * 4 + p.tpc * p.pre_stride;
-  p.fuse_list_off = (p.smem_bytes + 15) & ~15;
-  p.fuse_list_cap = fuse_cap;
-  p.stage_off = (p.fuse_list_off + fuse_cap * 16 + 15) & ~15;              // emission staging: one similarity map (NW x 32 words)
+  p.stage_off = (p.smem_bytes + 15) & ~15;                                 // emission staging: one similarity map (NW x 32 words)
   p.smem_bytes = p.stage_off + p.nw_template * 128 * 5;                     // the map (NW x 32 words) + one list word per cell
   if (p.smem_bytes > 227 * 1024 - 512) return false;
   *plan = p;
@@ -576,18 +464,18 @@ bool fl_plan_staged(const fl_level_geom& g, int M, int n_templates, int max_posi
 }
 
 int fl_launch_similarity_staged(fl_tdb db, fl_level_geom g, const uint8_t* lm_level, float threshold, fl_match_t* cand, int cap,
-                                int* d_count, fl_staged_plan plan, const fl_refine_args& ra, cudaStream_t s) {
+                                int* d_count, fl_staged_plan plan, cudaStream_t s) {
   switch (plan.nw_template) {
-    case 5: return launch_staged<5, 2>(db, g, lm_level, threshold, cand, cap, d_count, plan, ra, s);
-    case 7: return launch_staged<7, 2>(db, g, lm_level, threshold, cand, cap, d_count, plan, ra, s);
-    case 9: return launch_staged<9, 2>(db, g, lm_level, threshold, cand, cap, d_count, plan, ra, s);
-    case 11: return launch_staged<11, 2>(db, g, lm_level, threshold, cand, cap, d_count, plan, ra, s);
-    case 13: return launch_staged<13, 1>(db, g, lm_level, threshold, cand, cap, d_count, plan, ra, s);
-    case 15: return launch_staged<15, 1>(db, g, lm_level, threshold, cand, cap, d_count, plan, ra, s);
-    case 19: return launch_staged<19, 1>(db, g, lm_level, threshold, cand, cap, d_count, plan, ra, s);
-    case 23: return launch_staged<23, 1>(db, g, lm_level, threshold, cand, cap, d_count, plan, ra, s);
-    case 29: return launch_staged<29, 1>(db, g, lm_level, threshold, cand, cap, d_count, plan, ra, s);
-    case 37: return launch_staged<37, 1>(db, g, lm_level, threshold, cand, cap, d_count, plan, ra, s);
+    case 5: return launch_staged<5, 2>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
+    case 7: return launch_staged<7, 2>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
+    case 9: return launch_staged<9, 2>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
+    case 11: return launch_staged<11, 2>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
+    case 13: return launch_staged<13, 1>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
+    case 15: return launch_staged<15, 1>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
+    case 19: return launch_staged<19, 1>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
+    case 23: return launch_staged<23, 1>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
+    case 29: return launch_staged<29, 1>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
+    case 37: return launch_staged<37, 1>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
   }
   return -1;
 }

@@ -264,10 +264,21 @@ enum {
   FL_DBG_SIMILARITY = 3,    /* (template index)          -> (W/T)*(H/T) u16 total similarity at the coarsest level */
   FL_DBG_LAST_COUNTS = 5,   /* ()                        -> 16 ints of the last sort+unique: {matches, live candidates after refinement,
                                multi-kernel-sort flag, raw candidates emitted by the global stage per list (up to 12)} */
-  FL_DBG_STAGED_TRACE = 4   /* ()                        -> 8 u64 per CTA of the staged similarity kernel {t_start, t_ready, t_first_data,
-                               t_loop_end, t_end (globaltimer ns), smid, 0, 0}; only when the process was started with FL_TRACE=1;
+  FL_DBG_STAGED_TRACE = 4,  /* ()                        -> 8 u64 per CTA of the staged similarity kernel {t_start, t_ready, t_first_data,
+                               t_loop_end, t_end (globaltimer ns), smid, 0, 0}; only after fl_debug_option(h, FL_OPT_TRACE, 1);
                                returns the number of CTAs */
+  FL_DBG_FE_TRACE = 6       /* ()                        -> 4 u64 per front-end job {kind, CTAs, first CTA start, last CTA end (globaltimer ns)};
+                               only after fl_debug_option(h, FL_OPT_TRACE, 1); returns the number of jobs */
 };
+/* developer options of one handle; every one is off by default and covered by a test */
+enum {
+  FL_OPT_FE_WAVES = 0,            /* front end as one launch per pyramid wave instead of ONE launch with in-grid dependencies */
+  FL_OPT_SPLIT_REFINE = 1,        /* refinement and sort + unique as separate launches instead of one */
+  FL_OPT_TRACE = 2,               /* record the in-kernel timelines (FL_DBG_STAGED_TRACE, front-end job timeline); slows the frame down */
+  FL_OPT_FE_DEP_TIMEOUT_TEST = 3, /* the next frame's first in-grid dependency can never be satisfied: exercises the time-out fallback (takes ~1 s) */
+  FL_OPT_FE_FORCED_WAVES = 4      /* query (value ignored): 1 if a dependency time-out has switched this handle to per-wave launches */
+};
+int fl_debug_option(fl_handle* h, int option, int value);
 int fl_debug_keep_spread(fl_handle* h, int enable);
 /* kernel selection of the global similarity stage: the shared-memory-staged kernel is used when the template set is
  * eligible; force_baseline(1) pins the L1/L2-fed kernel (parity tests run both); uses_staged reports the

@@ -150,6 +150,14 @@ def test_group_binding_matches_oracle(tmp_path):
         assert rc == 0 and np.array_equal(got, exp)
     rc, got = g.match(b, d, thr, class_filter=[2])
     assert rc == 0 and np.array_equal(got, exp[exp["class_idx"] == 2])
+    # one member's single-launch front end gives up on an in-grid dependency: the group resubmits the frame (that member on
+    # per-wave launches from then on) and the caller sees the same list
+    g.member_option(1, fb.FL_OPT_FE_DEP_TIMEOUT_TEST, 1)
+    rc, got = g.match(b, d, thr)
+    assert rc == 0 and np.array_equal(got, exp)
+    assert g.member_option(1, fb.FL_OPT_FE_FORCED_WAVES) == 1 and g.member_option(0, fb.FL_OPT_FE_FORCED_WAVES) == 0
+    rc, got = g.match(b, d, thr)
+    assert rc == 0 and np.array_equal(got, exp)
     g.close()
     g = fb.Group([0, 0], exchange_capacity=4)
     g.upload_templates(ts)

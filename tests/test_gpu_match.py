@@ -125,24 +125,74 @@ def test_staged_and_baseline_similarity_kernels_agree(vga):
     assert np.array_equal(staged, want) and np.array_equal(base, want)
 
 
-def test_fused_refinement_tail_equals_separate_refinement_launches(vga):
-    """FL_FUSE_TAIL=1 at planning time makes the staged kernel refine its own candidates (fused tail, a developer variant); the
-    default keeps the refinement outside.  Both must give the oracle's list, also when one CTA's shared-memory candidate list
-    overflows (low threshold -> the frame is re-run unfused)."""
-    W, H, b, d, det, ts, h = vga
-    os.environ["FL_FUSE_TAIL"] = "1"
-    try:
-        h2 = fb.Handle((5, 8), (0, 1), W, H, max_candidates=1 << 17)   # fused variant
-        h2.upload_templates(ts)
-        for thr in (75.0, 50.0, 25.0):
-            want = det.match(thr)
-            rc_a, plain = h.match(b, d, thr, capacity=1 << 16)
-            rc_b, fused = h2.match(b, d, thr, capacity=1 << 16)
-            assert rc_a == 0 and rc_b == 0
-            assert np.array_equal(fused, want) and np.array_equal(plain, want), thr
-        h2.close()
-    finally:
-        del os.environ["FL_FUSE_TAIL"]
+def test_debug_options_leave_the_match_list_unchanged(vga):
+    """fl_debug_option: every developer switch of a handle (include/fealess_b200.h FL_OPT_*) gives the oracle's list - per-wave
+    front-end launches, refinement and sort as separate launches, the in-kernel timelines - alone and together."""
+    W, H, b, d, det, ts, _ = vga
+    want = {thr: det.match(thr) for thr in (75.0, 50.0)}
+    for opts in ([fb.FL_OPT_FE_WAVES], [fb.FL_OPT_SPLIT_REFINE], [fb.FL_OPT_TRACE], [fb.FL_OPT_FE_WAVES, fb.FL_OPT_SPLIT_REFINE, fb.FL_OPT_TRACE]):
+        h = fb.Handle((5, 8), (0, 1), W, H, max_candidates=1 << 17)
+        for o in opts:
+            assert h.debug_option(o, 1) == 0
+        h.upload_templates(ts)
+        n0 = h.launch_count()
+        for thr, w in want.items():
+            rc, got = h.match(b, d, thr, capacity=1 << 16)
+            assert rc == 0 and np.array_equal(got, w), (opts, thr)
+        per_frame = (h.launch_count() - n0) / 2
+        if fb.FL_OPT_FE_WAVES in opts or fb.FL_OPT_SPLIT_REFINE in opts:
+            assert per_frame > 3                                   # the default frame is 3 launches: front end, similarity, refine + sort
+        if fb.FL_OPT_TRACE in opts:
+            tr = h.staged_trace()
+            assert len(tr) > 0 and (tr[:, 4] >= tr[:, 0]).all() and (tr[:, 0] > 0).all()
+            if fb.FL_OPT_FE_WAVES not in opts:                     # the job timeline belongs to the single-launch front end
+                fe = h.fe_trace()
+                assert len(fe) >= 4 and (fe[:, 3] >= fe[:, 2]).all() and (fe[:, 1] > 0).all()
+        else:
+            with pytest.raises(RuntimeError):
+                h.staged_trace()
+        # switching an option off again restores the default path
+        for o in opts:
+            assert h.debug_option(o, 0) == 0
+        assert h.match(b, d, 75.0)[0] == 0                         # (re-plans the staged kernel after a change of FL_OPT_TRACE)
+        n0 = h.launch_count()
+        rc, got = h.match(b, d, 75.0)
+        assert rc == 0 and np.array_equal(got, want[75.0]) and h.launch_count() - n0 == 3
+        assert h.debug_option(fb.FL_OPT_FE_FORCED_WAVES) == 0
+        h.close()
+    with pytest.raises(RuntimeError):
+        fb.Handle((5, 8), (0, 1), W, H).debug_option(99, 1)
+
+
+def test_in_grid_dependency_timeout_falls_back_to_wave_launches(vga):
+    """The single-launch front end waits in-grid for producer tiles.  If a dependency never arrives (FL_OPT_FE_DEP_TIMEOUT_TEST makes
+    the next frame's first one unsatisfiable) the kernel gives up instead of trapping the context, the host re-runs the frame with one
+    launch per wave, and the handle stays on wave launches: the caller sees a correct frame and a usable handle."""
+    W, H, b, d, det, ts, _ = vga
+    h = fb.Handle((5, 8), (0, 1), W, H)
+    h.upload_templates(ts)
+    want = det.match(75.0)
+    rc, got = h.match(b, d, 75.0)
+    assert rc == 0 and np.array_equal(got, want) and h.debug_option(fb.FL_OPT_FE_FORCED_WAVES) == 0
+    h.debug_option(fb.FL_OPT_FE_DEP_TIMEOUT_TEST, 1)
+    rc, got = h.match(b, d, 75.0)                              # times out in the grid (~1 s), re-run in wave mode
+    assert rc == 0 and np.array_equal(got, want)
+    assert h.debug_option(fb.FL_OPT_FE_FORCED_WAVES) == 1
+    b2, d2 = synth.make_frame(W, H, 3)
+    det.process(b2, d2)
+    rc, got = h.match(b2, d2, 75.0)                            # later frames: wave launches, still right, context alive
+    assert rc == 0 and np.array_equal(got, det.match(75.0))
+    det.process(b, d)
+    # the device-resident entry points take the same path
+    import torch
+    tb, td = torch.from_numpy(b).cuda(), torch.from_numpy(d).cuda()
+    h2 = fb.Handle((5, 8), (0, 1), W, H)
+    h2.upload_templates(ts)
+    h2.debug_option(fb.FL_OPT_FE_DEP_TIMEOUT_TEST, 1)
+    h2.match_device_async(tb.data_ptr(), td.data_ptr(), W, H, 75.0)
+    h2.match_wait()
+    assert np.array_equal(h2.match_fetch(1 << 14), want) and h2.debug_option(fb.FL_OPT_FE_FORCED_WAVES) == 1
+    h.close(); h2.close()
 
 
 def test_templates_with_features_on_the_box_border_and_ragged_sets(vga):

@@ -1,8 +1,7 @@
-"""Developer experiment: per-warp end times inside the staged kernel (FL_TRACE)."""
+"""Developer experiment: per-warp end times inside the staged kernel (fl_debug_option FL_OPT_TRACE)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-os.environ["FL_TRACE"] = "1"
 import ctypes as C
 import numpy as np
 import fealess_b200 as fb
@@ -10,6 +9,7 @@ from fealess_b200 import synth
 W, H, T = 640, 480, (5, 8)
 frames = [synth.make_frame(W, H, i) for i in range(4)]
 h = fb.Handle(T, (0, 1), W, H)
+h.debug_option(fb.FL_OPT_TRACE, 1)
 h.upload_templates(synth.make_templates(0))
 rc, _, q = h.match(frames[0][0], frames[0][1], 75.0, want_quantized=True)
 ts = synth.make_templates(8000, W, H, T, seed=1, quantized=q, planted_fraction=0.01)

@@ -17,5 +17,5 @@ ncu --set full --clock-control none --import-source on -k regex:k_similarity_sta
 ncu --set full --clock-control none --import-source on -k regex:k_front_end_wave -s 4 -c 1 -f -o gpurun_out/prof_fe_$TAG \
   python bench.py --steps 3 --warmup 3 --no-cpu --no-icp > gpurun_out/ncu_full_fe.log 2>&1; echo "ncu full fe rc=$?"
 # the ICP loop kernel (C3 batch inside bench.py's icp leg; the Recognition leg launches it with 5 hypotheses)
-ncu --set full --clock-control none --import-source on -k regex:k_icp_run -s 1 -c 1 -f -o gpurun_out/prof_icp_$TAG \
+ncu --set full --clock-control none --import-source on -k regex:k_icp_fused -s 1 -c 1 -f -o gpurun_out/prof_icp_$TAG \
   python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/ncu_full_icp.log 2>&1; echo "ncu full icp rc=$?"
