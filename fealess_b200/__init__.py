@@ -47,6 +47,8 @@ EXPORTED_SYMBOLS = [
     "fl_detection_batch", "fl_upload_model_depths", "fl_detection_batch_resident", "fl_detection_batch_resident_device", "fl_detection", "fl_nms", "fl_nms_ex", "fl_debug_option", "fl_debug_keep_spread", "fl_debug_force_baseline", "fl_debug_uses_staged", "fl_debug_get", "fl_debug_icp_trace", "fl_launch_count",
     "fl_profile", "fl_last_stage_ms", "fl_last_icp_ms",
     "fl_group_create", "fl_group_destroy", "fl_group_size", "fl_group_handle", "fl_group_upload_templates", "fl_group_match",
+    "fl_match_async", "fl_pipe_create", "fl_pipe_destroy", "fl_pipe_depth", "fl_pipe_in_flight", "fl_pipe_handle", "fl_pipe_upload_templates",
+    "fl_pipe_submit", "fl_pipe_collect", "fl_pipe_match_batch",
 ]
 
 
@@ -535,6 +537,104 @@ class Group:
         if rc not in (FL_OK, FL_ERR_CAPACITY):
             _check(rc, "fl_group_match")
         return rc, out[:min(cnt.value, capacity)].copy()
+
+
+class Pipe:
+    """fl_pipe: Detector::match over a stream of frames with ``depth`` frames in flight on one GPU; lists come back in submission
+    order and equal ``Handle.match``'s."""
+
+    def __init__(self, depth: int = 3, T: Sequence[int] = (5, 8), modality_kind: Sequence[int] = (0, 1), max_width=640, max_height=480, device: int = 0,
+                 max_candidates: Optional[int] = None):
+        L = lib()
+        p = Params()
+        L.fl_default_params(C.byref(p))
+        p.n_levels = len(T)
+        for i, t in enumerate(T):
+            p.T[i] = int(t)
+        p.n_modalities = len(modality_kind)
+        for i, k in enumerate(modality_kind):
+            p.modality_kind[i] = int(k)
+        p.max_width, p.max_height, p.device = max_width, max_height, device
+        if max_candidates:
+            p.max_candidates = int(max_candidates)
+        self._p = C.c_void_p()
+        rc = L.fl_pipe_create(C.byref(p), int(depth), C.byref(self._p))
+        if rc != FL_OK:
+            self._p = None
+            raise FealessError(rc, "fl_pipe_create", L.fl_last_error().decode(errors="replace"))
+        self.depth = int(depth)
+        self._keep = {}                                          # frames in flight: the arrays the DMA reads stay referenced
+        self._seq = 0
+        self._out = {}
+
+    def close(self):
+        if getattr(self, "_p", None):
+            lib().fl_pipe_destroy(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def in_flight(self) -> int:
+        return int(lib().fl_pipe_in_flight(self._p))
+
+    def upload_templates(self, tset) -> None:
+        hdr = np.ascontiguousarray(tset.headers, np.int32)
+        ft = np.ascontiguousarray(tset.features, np.int32)
+        co = np.ascontiguousarray(tset.class_of, np.int32)
+        pose = np.ascontiguousarray(tset.pose13, np.float32)
+        _check(lib().fl_pipe_upload_templates(self._p, tset.n_templates, _p(hdr), _p(ft), ft.shape[0], _p(co), _p(pose)), "fl_pipe_upload_templates")
+
+    def submit(self, bgr, depth, threshold: float, class_filter=None) -> None:
+        """Host frame (numpy arrays; page-locked ones are read by DMA while in flight)."""
+        H, W = (depth if depth is not None else bgr).shape[:2]
+        b = None if bgr is None else np.ascontiguousarray(bgr, np.uint8)
+        d = None if depth is None else np.ascontiguousarray(depth, np.uint16)
+        cf = None if not class_filter else np.ascontiguousarray(class_filter, np.int32)
+        _check(lib().fl_pipe_submit(self._p, _p(b), C.c_size_t(W * 3), _p(d), C.c_size_t(W * 2), W, H, C.c_float(threshold), _p(cf),
+                                    0 if cf is None else int(cf.size), 0), "fl_pipe_submit")
+        self._keep[self._seq % self.depth] = (b, d)
+        self._seq += 1
+
+    def submit_device(self, d_bgr: int, d_depth: int, W: int, H: int, threshold: float, class_filter=None) -> None:
+        cf = None if not class_filter else np.ascontiguousarray(class_filter, np.int32)
+        _check(lib().fl_pipe_submit(self._p, C.c_void_p(d_bgr), C.c_size_t(W * 3), C.c_void_p(d_depth), C.c_size_t(W * 2), W, H, C.c_float(threshold), _p(cf),
+                                    0 if cf is None else int(cf.size), 1), "fl_pipe_submit")
+        self._seq += 1
+
+    def collect(self, capacity: int = 1 << 14, copy: bool = True):
+        """(rc, matches) of the oldest frame in flight; rc is FL_OK or FL_ERR_CAPACITY (truncated list)."""
+        out = self._out.get(capacity)
+        if out is None:
+            out = self._out[capacity] = np.zeros(capacity, MATCH_DTYPE)
+        cnt = C.c_int32(0)
+        rc = lib().fl_pipe_collect(self._p, _p(out), capacity, C.byref(cnt))
+        if rc not in (FL_OK, FL_ERR_CAPACITY):
+            _check(rc, "fl_pipe_collect")
+        m = out[:min(cnt.value, capacity)]
+        return rc, (m.copy() if copy else m)
+
+    def match_batch(self, frames, threshold: float, class_filter=None, capacity_per_frame: int = 1 << 12):
+        """``frames``: sequence of (bgr, depth) numpy pairs of one geometry.  Returns (rc, [matches per frame])."""
+        n = len(frames)
+        if n == 0:
+            return FL_OK, []
+        H, W = frames[0][1].shape[:2]
+        bs = [np.ascontiguousarray(f[0], np.uint8) for f in frames]
+        ds = [np.ascontiguousarray(f[1], np.uint16) for f in frames]
+        pb = (C.c_void_p * n)(*[x.ctypes.data for x in bs])
+        pd = (C.c_void_p * n)(*[x.ctypes.data for x in ds])
+        out = np.zeros(n * capacity_per_frame, MATCH_DTYPE)
+        counts = np.zeros(n, np.int32)
+        cf = None if not class_filter else np.ascontiguousarray(class_filter, np.int32)
+        rc = lib().fl_pipe_match_batch(self._p, n, pb, C.c_size_t(W * 3), pd, C.c_size_t(W * 2), W, H, C.c_float(threshold), _p(cf), 0 if cf is None else int(cf.size), 0,
+                                       _p(out), capacity_per_frame, _p(counts))
+        if rc not in (FL_OK, FL_ERR_CAPACITY):
+            _check(rc, "fl_pipe_match_batch")
+        return rc, [out[f * capacity_per_frame:f * capacity_per_frame + min(int(counts[f]), capacity_per_frame)].copy() for f in range(n)]
 
 
 # --------------------------------------------------------------------------------------------------

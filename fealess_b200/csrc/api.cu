@@ -826,24 +826,17 @@ extern "C" int fl_match_fetch(fl_handle* h, fl_match_t* out, int32_t capacity, i
   return (n > capacity || n > h->p.max_candidates || h->overflow) ? FL_ERR_CAPACITY : FL_OK;
 }
 
-extern "C" int fl_match(fl_handle* h, const uint8_t* bgr, size_t bgr_stride, const uint16_t* depth, size_t depth_stride, int32_t W, int32_t H,
-                        const uint8_t* const* masks, float threshold, const int32_t* class_filter, int32_t n_filter, fl_match_t* out,
-                        int32_t capacity, int32_t* count, uint8_t* const* quantized_out) {
-  if (!h || !count) return FL_ERR_ARG;
-  *count = 0;
+// Frame upload of the host-buffer entry points.  A caller buffer that is already page-locked (cudaHostAlloc / cudaHostRegister /
+// torch pin_memory) is DMA'd directly, strided rows included, and has to stay valid until the frame has been waited for; pageable
+// memory goes through the handle's pinned staging buffer first (copied before this returns).
+static int stage_frame(fl_handle* h, const uint8_t* bgr, size_t bgr_stride, const uint16_t* depth, size_t depth_stride, int W, int H, const uint8_t* const* masks,
+                       const uint8_t** d_bgr_out, const uint16_t** d_depth_out, const void** d_masks, bool* any_mask) {
   const fl_params_t& p = h->p;
-  // an asynchronous frame still in flight may be reading the staging buffers this call is about to overwrite
-  if (h->pend_sort) { fl_set_error("fl_match_wait has not been called for the previous frame"); return FL_ERR_STATE; }
-  h->in_depth_W = h->in_depth_H = 0;                                               // d_in_depth counts as "the matched frame" only once this call has succeeded
-  if (W <= 0 || H <= 0 || W > p.max_width || H > p.max_height) return FL_ERR_SIZE;
-  FL_CUDA(cudaSetDevice(p.device));
   cudaStream_t s = h->stream;
-  const uint8_t* d_bgr = nullptr; const uint16_t* d_depth = nullptr;
-  // Frame upload.  A caller buffer that is already page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory) is
-  // DMA'd directly, strided rows included; pageable memory goes through the handle's pinned staging buffer first.
-  auto is_pinned = [](const void* p) {
+  *d_bgr_out = nullptr; *d_depth_out = nullptr; *any_mask = false;
+  auto is_pinned = [](const void* q) {
     cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (cudaPointerGetAttributes(&a, q) != cudaSuccess) { cudaGetLastError(); return false; }
     return a.type == cudaMemoryTypeHost;
   };
   if (depth) {                                                                     // depth first: it is the smaller image
@@ -856,7 +849,7 @@ extern "C" int fl_match(fl_handle* h, const uint8_t* bgr, size_t bgr_stride, con
       for (int y = 0; y < H; ++y) memcpy(h->h_depth + (size_t)y * W, (const uint8_t*)depth + (size_t)y * depth_stride, (size_t)W * 2);
       FL_CUDA(cudaMemcpyAsync(h->d_in_depth, h->h_depth, (size_t)W * H * 2, cudaMemcpyHostToDevice, s));
     }
-    d_depth = h->d_in_depth;
+    *d_depth_out = h->d_in_depth;
   }
   if (bgr) {
     if (bgr_stride < (size_t)W * 3) return FL_ERR_SIZE;
@@ -872,19 +865,48 @@ extern "C" int fl_match(fl_handle* h, const uint8_t* bgr, size_t bgr_stride, con
         if (y1 > y0) FL_CUDA(cudaMemcpyAsync(h->d_in_bgr + (size_t)y0 * W * 3, h->h_bgr + (size_t)y0 * W * 3, (size_t)(y1 - y0) * W * 3, cudaMemcpyHostToDevice, s));
       }
     }
-    d_bgr = h->d_in_bgr;
+    *d_bgr_out = h->d_in_bgr;
   }
-  const void* d_masks[FL_MAX_MODALITIES] = {nullptr, nullptr, nullptr, nullptr};
-  bool any_mask = false;
+  for (int m = 0; m < FL_MAX_MODALITIES; ++m) d_masks[m] = nullptr;
   if (masks) for (int m = 0; m < p.n_modalities; ++m) if (masks[m]) {
     if (!h->d_mask[0][m]) { size_t n = (size_t)p.max_width * p.max_height; TRY(dalloc(&h->d_mask[0][m], n)); TRY(dalloc(&h->d_qm[0][m], n)); }
     memcpy(h->h_mask + (size_t)m * W * H, masks[m], (size_t)W * H);
     FL_CUDA(cudaMemcpyAsync(h->d_mask[0][m], h->h_mask + (size_t)m * W * H, (size_t)W * H, cudaMemcpyHostToDevice, s));
-    d_masks[m] = h->d_mask[0][m]; any_mask = true;
+    d_masks[m] = h->d_mask[0][m]; *any_mask = true;
   }
-  int rc = fl_match_device(h, d_bgr, d_depth, W, H, any_mask ? d_masks : nullptr, threshold, class_filter, n_filter);
-  if (rc != FL_OK) return rc;
+  return FL_OK;
+}
+
+// enqueue-only half of fl_match: upload + every kernel of the frame on the handle's stream; fl_match_wait / fl_match_fetch finish it
+extern "C" int fl_match_async(fl_handle* h, const uint8_t* bgr, size_t bgr_stride, const uint16_t* depth, size_t depth_stride, int32_t W, int32_t H,
+                              const uint8_t* const* masks, float threshold, const int32_t* class_filter, int32_t n_filter) {
+  if (!h) return FL_ERR_ARG;
+  const fl_params_t& p = h->p;
+  // an asynchronous frame still in flight may be reading the staging buffers this call is about to overwrite
+  if (h->pend_sort) { fl_set_error("fl_match_wait has not been called for the previous frame"); return FL_ERR_STATE; }
+  h->in_depth_W = h->in_depth_H = 0;                                               // d_in_depth counts as "the matched frame" only once this call has succeeded
+  if (W <= 0 || H <= 0 || W > p.max_width || H > p.max_height) return FL_ERR_SIZE;
+  FL_CUDA(cudaSetDevice(p.device));
+  const uint8_t* d_bgr; const uint16_t* d_depth;
+  const void* d_masks[FL_MAX_MODALITIES];
+  bool any_mask;
+  TRY(stage_frame(h, bgr, bgr_stride, depth, depth_stride, W, H, masks, &d_bgr, &d_depth, d_masks, &any_mask));
+  TRY(fl_match_device_async(h, d_bgr, d_depth, W, H, any_mask ? d_masks : nullptr, threshold, class_filter, n_filter));
   if (d_depth) { h->in_depth_W = W; h->in_depth_H = H; }
+  return FL_OK;
+}
+
+extern "C" int fl_match(fl_handle* h, const uint8_t* bgr, size_t bgr_stride, const uint16_t* depth, size_t depth_stride, int32_t W, int32_t H,
+                        const uint8_t* const* masks, float threshold, const int32_t* class_filter, int32_t n_filter, fl_match_t* out,
+                        int32_t capacity, int32_t* count, uint8_t* const* quantized_out) {
+  if (!h || !count) return FL_ERR_ARG;
+  *count = 0;
+  const fl_params_t& p = h->p;
+  int rc = fl_match_async(h, bgr, bgr_stride, depth, depth_stride, W, H, masks, threshold, class_filter, n_filter);
+  if (rc != FL_OK) return rc;
+  rc = fl_match_wait(h);
+  if (rc != FL_OK) { h->in_depth_W = h->in_depth_H = 0; return rc; }
+  cudaStream_t s = h->stream;
   rc = fl_match_fetch(h, out, capacity, count);
   if (quantized_out) {
     for (int l = 0; l < p.n_levels; ++l) for (int m = 0; m < p.n_modalities; ++m) {

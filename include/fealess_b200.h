@@ -138,6 +138,37 @@ int fl_match_fetch(fl_handle* h, fl_match_t* out, int32_t capacity, int32_t* cou
 int fl_match_device_async(fl_handle* h, const void* d_bgr, const void* d_depth, int32_t W, int32_t H,
                           const void* const* d_masks, float threshold, const int32_t* class_filter, int32_t n_filter);
 int fl_match_wait(fl_handle* h);
+/* enqueue-only half of fl_match (host buffers): the upload and the frame's kernels go on the handle's stream; finish with
+ * fl_match_wait + fl_match_fetch.  Page-locked caller buffers are read by DMA and must stay valid until fl_match_wait returns;
+ * pageable ones are copied before this returns. */
+int fl_match_async(fl_handle* h, const uint8_t* bgr, size_t bgr_stride, const uint16_t* depth, size_t depth_stride, int32_t W, int32_t H,
+                   const uint8_t* const* masks, float threshold, const int32_t* class_filter, int32_t n_filter);
+
+/* ---- several frames in flight on one GPU -----------------------------------------------------------
+ * The reference's callers run Detector::match once per camera frame in a loop (CadReco/obj_reco_lmicp.cpp:86-204,
+ * test/linemod_acq.cpp:120-190); the frames are independent.  A pipe owns `depth` handles on params->device (each holds the whole
+ * template set) and deals submitted frames round-robin, so that the front end of frame i+1, the upload of frame i+2 and the result
+ * copy of frame i-1 overlap the similarity kernel of frame i.  Lists come back in submission order and equal fl_match's.
+ * fl_pipe_submit: FL_ERR_STATE when `depth` frames are in flight already.  on_device != 0: bgr / depth are device pointers with
+ * dense rows (the strides must say so); otherwise host pointers as in fl_match_async (page-locked buffers must stay valid until the
+ * frame has been collected).  fl_pipe_collect: waits for the OLDEST frame in flight and writes its list (status as fl_match_fetch).
+ * fl_pipe_match_batch: n_frames frames of one geometry (arrays of n_frames pointers), frame f's list at out + f *
+ * capacity_per_frame and its length in counts[f]; FL_ERR_CAPACITY if some list was truncated. */
+typedef struct fl_pipe fl_pipe;
+#define FL_PIPE_MAX_DEPTH 8
+int fl_pipe_create(const fl_params_t* params, int32_t depth, fl_pipe** out);
+int fl_pipe_destroy(fl_pipe* p);
+int32_t fl_pipe_depth(const fl_pipe* p);
+int32_t fl_pipe_in_flight(const fl_pipe* p);
+fl_handle* fl_pipe_handle(fl_pipe* p, int32_t i);
+int fl_pipe_upload_templates(fl_pipe* p, int32_t n_templates, const fl_template_hdr_t* headers, const fl_feature_t* features,
+                             int32_t n_features, const int32_t* class_of, const float* pose13);   /* layout of fl_upload_templates */
+int fl_pipe_submit(fl_pipe* p, const void* bgr, size_t bgr_stride, const void* depth, size_t depth_stride, int32_t W, int32_t H,
+                   float threshold, const int32_t* class_filter, int32_t n_filter, int32_t on_device);
+int fl_pipe_collect(fl_pipe* p, fl_match_t* out, int32_t capacity, int32_t* count);
+int fl_pipe_match_batch(fl_pipe* p, int32_t n_frames, const void* const* bgr, size_t bgr_stride, const void* const* depth, size_t depth_stride,
+                        int32_t W, int32_t H, float threshold, const int32_t* class_filter, int32_t n_filter, int32_t on_device,
+                        fl_match_t* out, int32_t capacity_per_frame, int32_t* counts);
 
 /* Template-sharded matching (one handle per GPU holds a shard of the templates):
  * fl_match_shard_device runs the front end + matchClass over this handle's templates and writes the UNSORTED

@@ -1,0 +1,96 @@
+"""GPU (-m gpu): fl_pipe - several frames in flight on one GPU (include/fealess_b200.h).  Every frame's list has to equal the
+oracle's Detector::match list for THAT frame, in submission order, whatever the depth; the state errors have to be reported."""
+import numpy as np
+import pytest
+
+import fealess_b200 as fb
+import fl_oracle_py as F
+from fealess_b200 import synth
+
+pytestmark = pytest.mark.gpu
+W, H, T = 640, 480, (5, 8)
+
+
+@pytest.fixture(scope="module")
+def stream_case():
+    frames = [synth.make_frame(W, H, i) for i in range(5)]
+    det = F.Detector(T)
+    assert det.process(*frames[0]) == 0
+    q = [det.quantized(l, m) for l in range(2) for m in range(2)]
+    ts = synth.make_templates(700, W, H, T, n_classes=3, seed=5, quantized=q, planted_fraction=0.05)
+    det.set_templates(ts)
+    want = []
+    for b, d in frames:
+        assert det.process(b, d) == 0
+        want.append(det.match(70.0))
+    assert sum(len(w) for w in want) > 20 and len({len(w) for w in want}) > 1
+    return frames, ts, want
+
+
+@pytest.mark.parametrize("depth", [1, 2, 4])
+def test_stream_of_frames_in_order(stream_case, depth):
+    frames, ts, want = stream_case
+    p = fb.Pipe(depth, T, (0, 1), W, H)
+    p.upload_templates(ts)
+    n = 23
+    got = []
+    for i in range(n):
+        if p.in_flight() == depth:
+            got.append(p.collect())
+        p.submit(*frames[i % 5], 70.0)
+    assert p.in_flight() == min(depth, n)
+    while p.in_flight():
+        got.append(p.collect())
+    assert len(got) == n
+    for i, (rc, m) in enumerate(got):
+        assert rc == 0 and np.array_equal(m, want[i % 5]), i
+    p.close()
+
+
+def test_state_errors_and_batch(stream_case):
+    import torch
+    frames, ts, want = stream_case
+    p = fb.Pipe(2, T, (0, 1), W, H)
+    with pytest.raises(fb.FealessError) as e:
+        p.collect()                                              # nothing in flight
+    assert e.value.rc == fb.FL_ERR_STATE
+    p.upload_templates(ts)
+    p.submit(*frames[0], 70.0)
+    p.submit(*frames[1], 70.0)
+    with pytest.raises(fb.FealessError) as e:
+        p.submit(*frames[2], 70.0)                               # depth frames in flight already
+    assert e.value.rc == fb.FL_ERR_STATE
+    with pytest.raises(fb.FealessError) as e:
+        p.upload_templates(ts)                                   # not while frames are in flight
+    assert e.value.rc == fb.FL_ERR_STATE
+    assert np.array_equal(p.collect()[1], want[0]) and np.array_equal(p.collect()[1], want[1])
+    # a frame with a bad geometry is refused at submit and does not occupy a slot
+    bb, dd = synth.make_frame(640, 488, 0)
+    p2 = fb.Pipe(2, T, (0, 1), 640, 488)
+    with pytest.raises(fb.FealessError) as e:
+        p2.submit(bb, dd, 70.0)
+    assert e.value.rc == fb.FL_ERR_GEOMETRY and p2.in_flight() == 0
+    p2.close()
+    # batch entry: 11 frames through 2 slots, a class filter, and a capacity that truncates some lists
+    order = [i % 5 for i in range(11)]
+    rc, lists = p.match_batch([frames[i] for i in order], 70.0)
+    assert rc == 0 and all(np.array_equal(lists[k], want[i]) for k, i in enumerate(order))
+    rc, lists = p.match_batch([frames[i] for i in order], 70.0, class_filter=[1])
+    assert rc == 0 and all(np.array_equal(lists[k], want[i][want[i]["class_idx"] == 1]) for k, i in enumerate(order))
+    cap = min(len(w) for w in want) + 1
+    rc, lists = p.match_batch([frames[i] for i in order], 70.0, capacity_per_frame=cap)
+    assert rc == fb.FL_ERR_CAPACITY and all(np.array_equal(lists[k], want[i][:cap]) for k, i in enumerate(order))
+    assert p.match_batch([], 70.0) == (0, [])
+    # page-locked host frames (read by DMA while in flight) and device-resident frames
+    pinned = [(torch.from_numpy(b).pin_memory().numpy(), torch.from_numpy(d.view(np.int16)).pin_memory().numpy().view(np.uint16)) for b, d in frames]
+    dev = [(torch.from_numpy(b).cuda(), torch.from_numpy(d.view(np.int16)).cuda()) for b, d in frames]
+    for k in range(8):
+        if p.in_flight() == 2:
+            i = k - 2
+            assert np.array_equal(p.collect()[1], want[i % 5])
+        if k % 2:
+            p.submit(*pinned[k % 5], 70.0)
+        else:
+            p.submit_device(dev[k % 5][0].data_ptr(), dev[k % 5][1].data_ptr(), W, H, 70.0)
+    assert np.array_equal(p.collect()[1], want[6 % 5]) and np.array_equal(p.collect()[1], want[7 % 5])
+    p.close()
