@@ -44,6 +44,7 @@ FEATURES_COARSE = 62            # 2 modalities x 31 features at the coarsest of 
 CELLS = (W // 2 // T[1]) * (H // 2 // T[1])     # 40 x 30 = 1,200
 FRONT_END_BYTES = 5 * W * H + 2 * 8 * (W * H + (W // 2) * (H // 2))   # 7,680,000 B
 N_FRAMES = 8                    # distinct synthetic frames cycled through the steps
+N_INPUT_SLOTS = 160             # device copies of them at distinct addresses: 160 x 1.536 MB = 246 MB > 126 MB L2
 METRIC = "template.px evals/s (LINE-MOD match, 640x480, 8k templates/GPU)"
 WORKLOAD = "C2: LINE-MOD match-only, 640x480, %d templates per GPU, L=2, T={5,8}, threshold 75"   # same string in both arms
 
@@ -257,19 +258,32 @@ def run_ours(args):
     frames, synth = make_inputs(args.templates)
     n_total = args.templates * world                                   # weak scaling: per-GPU work fixed
     cap = 2048                                                          # candidate records per rank in the all-gather block (41 KB)
-    h = fb.Handle(T, (0, 1), W, H, max_candidates=max(1 << 16, world * (cap + 1) + 16), device=local)
+    depth = max(1, args.in_flight)
+
+    def make_handle():
+        return fb.Handle(T, (0, 1), W, H, max_candidates=max(1 << 16, world * (cap + 1) + 16), device=local)
     # quantised images for planting come from the product's own front end (empty template set)
-    h.upload_templates(synth.make_templates(0))
-    rc, _, q = h.match(frames[0][0], frames[0][1], THRESHOLD, want_quantized=True)
+    h0 = make_handle()
+    h0.upload_templates(synth.make_templates(0))
+    rc, _, q = h0.match(frames[0][0], frames[0][1], THRESHOLD, want_quantized=True)
     assert rc == 0
+    h0.close()
     tset = synth.make_templates(n_total, W, H, T, seed=1, quantized=q, planted_fraction=0.01)
-    sm = sharded.ShardedMatcher(h, tset, rank, world, capacity=cap, device=dev, exchange=args.exchange)
+    # `depth` frames in flight per GPU: depth handles (own stream, linear memories, candidate / result blocks, exchange buffer),
+    # frames dealt round-robin, lists collected in order (fealess_b200.sharded.ShardedPipe; fl_pipe is the same schedule in C)
+    pipe = sharded.ShardedPipe(make_handle, tset, rank, world, depth=depth, capacity=cap, device=dev, exchange=args.exchange)
+    sm = pipe.slots[0]
+    h = sm.h
     stream = sm.stream
-    d_frames = [(torch.from_numpy(b).to(dev), torch.from_numpy(d.view(np.int16)).to(dev)) for b, d in frames]
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+    # inputs larger than L2: N_INPUT_SLOTS device copies of the frames at distinct addresses (160 x 1.5 MB = 246 MB > 126 MB L2),
+    # visited in turn, so that no frame's bytes are L2-resident when its step starts
+    d_inputs = [(torch.from_numpy(frames[j % N_FRAMES][0]).to(dev), torch.from_numpy(frames[j % N_FRAMES][1].view(np.int16)).to(dev)) for j in range(N_INPUT_SLOTS)]
+    d_frames = d_inputs[:N_FRAMES]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2 (latency-mode pass)
     torch.cuda.synchronize()
 
     def step(i, timed):
+        """latency mode: ONE frame in flight, L2 flushed before it, events around exactly its device work"""
         tb, td = d_frames[i % N_FRAMES]
         with torch.cuda.stream(stream):
             flush.zero_()                                               # L2 flush between steps, outside the timed events
@@ -278,77 +292,111 @@ def run_ours(args):
             e0.record(stream)
         # enqueue the frame, record the end event right behind its last kernel, THEN let the host wait: the events bracket the
         # device work only (the synchronous call would put the host's wake-up + event-enqueue latency, ~20 us, inside them)
-        if world == 1:
-            h.match_device_async(tb.data_ptr(), td.data_ptr(), W, H, THRESHOLD)
+        whole = sm.match_device_async(tb.data_ptr(), td.data_ptr(), W, H, THRESHOLD) if world > 1 else (h.match_device_async(tb.data_ptr(), td.data_ptr(), W, H, THRESHOLD) or True)
+        if whole:
             e1.record(stream)
-            h.match_wait()
-        else:
-            whole = sm.match_device_async(tb.data_ptr(), td.data_ptr(), W, H, THRESHOLD)
-            if whole:
-                e1.record(stream)
-            sm.match_wait()
-            if not whole:                                              # NCCL exchange: the collective + merge are issued by match_wait
-                e1.record(stream)
+        (sm if world > 1 else h).match_wait()
+        if not whole:                                                  # NCCL exchange: the collective + merge are issued by match_wait
+            e1.record(stream)
         return e0, e1
 
-    for i in range(args.warmup):
-        step(i, False)
+    seq = [0]
+
+    def stream_frames(n, mark=None):
+        """n more frames through the pipe without draining it; mark(slot) is called right before the first of them is enqueued"""
+        for k in range(n):
+            if pipe.in_flight() == depth:
+                pipe.collect()
+            tb, td = d_inputs[seq[0] % N_INPUT_SLOTS]
+            seq[0] += 1
+            if k == 0 and mark is not None:
+                mark(pipe.slots[pipe.submitted % depth])
+            pipe.submit_device(tb.data_ptr(), td.data_ptr(), W, H, THRESHOLD)
+
+    def drain():
+        last = None
+        while pipe.in_flight():
+            last = pipe.collect()
+        return last
+
+    stream_frames(max(args.warmup, 3))
+    drain()
     torch.cuda.synchronize()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start_and_wait()                                        # NVML init takes ~10 ms: before the barrier, or every peer's first step waits for rank 0
     if world > 1:
         dist.barrier()
-        for i in range(2):                                              # re-align the ranks on the device after the host barrier
-            step(i, False)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    launches0 = h.launch_count()
-    evs = []
+    launches0 = pipe.launch_count()
     import gc
     gc.collect()
     gc.disable()                                                        # no collector pauses inside the timed region
     wall0 = time.perf_counter()
-    if world > 1:
-        # ranks leave the host barrier up to ~1 ms apart; two untimed steps let the on-device exchange re-align them, so that the
-        # first TIMED step does not absorb the barrier's skew (it did: 0.6 ms at N = 2, 1-2.6 ms at N = 8 in one step of 500)
-        for i in range(2):
-            step(i, False)
-    for i in range(args.steps):
-        evs.append(step(args.warmup + i, True))
+    # Timed region = EXACTLY args.steps frames of a running stream.  The ranks leave the host barrier up to ~1 ms apart, so the pipe
+    # is first filled with 2 x depth untimed frames (the on-device exchange re-aligns the ranks) and NOT drained; the start event
+    # is recorded on the stream of the slot that receives the first timed frame, right in front of it (so it fires when that
+    # slot's previous frame has finished - up to depth - 1 untimed frames are still running then and their remaining work is
+    # counted: the figure errs on the slow side by < depth / steps); the end event is recorded after the host has collected the
+    # last timed frame, on an idle stream.
+    stream_frames(2 * depth)
+    e_start = torch.cuda.Event(enable_timing=True)
+    e_end = torch.cuda.Event(enable_timing=True)
+    stream_frames(args.steps, mark=lambda slot: e_start.record(slot.stream))
+    last = drain()
+    e_end.record(last.stream)
     torch.cuda.synchronize()
     gc.enable()
     if world > 1:
         dist.barrier()
     wall1 = time.perf_counter()
-    launches = h.launch_count() - launches0
+    launches = pipe.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
-    per_step = np.array([a.elapsed_time(b) for a, b in evs])
-    if args.per_step:
-        slow = np.nonzero(per_step > 3 * np.median(per_step))[0]
-        sys.stderr.write("rank %d per-step device ms: p10 %.4f p50 %.4f p90 %.4f max %.4f mean %.4f | steps > 3x median: %s\n"
-                         % (rank, *np.percentile(per_step, [10, 50, 90]), per_step.max(), per_step.mean(),
-                            ", ".join("%d (%.2f ms)" % (i, per_step[i]) for i in slow[:8]) or "none"))
-    dev_ms = float(per_step.sum())
+    n_matches = len(last.fetch())
+    dev_ms = float(e_start.elapsed_time(e_end))
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms = float(t.item())
-    n_matches = len(h.match_fetch()) if world == 1 else len(sm.fetch())
+    # ---- latency mode (one frame in flight, L2 flushed before every frame, per-frame events): what a caller that needs each
+    # list before it submits the next frame sees; the headline of rounds 1-2a ----
+    n_lat = min(args.steps, 300)
+    for i in range(3):
+        step(i, False)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        for i in range(2):
+            step(i, False)
+    gc.disable()
+    evs = [step(args.warmup + i, True) for i in range(n_lat)]
+    torch.cuda.synchronize()
+    gc.enable()
+    per_step = np.array([a.elapsed_time(b) for a, b in evs])
+    if args.per_step:
+        slow = np.nonzero(per_step > 3 * np.median(per_step))[0]
+        sys.stderr.write("rank %d latency-mode per-frame device ms: p10 %.4f p50 %.4f p90 %.4f max %.4f mean %.4f | frames > 3x median: %s\n"
+                         % (rank, *np.percentile(per_step, [10, 50, 90]), per_step.max(), per_step.mean(),
+                            ", ".join("%d (%.2f ms)" % (i, per_step[i]) for i in slow[:8]) or "none"))
+    lat = torch.tensor([float(per_step.sum())], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(lat, op=dist.ReduceOp.MAX)
+    lat_ms = float(lat.item()) / n_lat
     # ---- correctness, outside the timed region: the match list of frame 0 must equal the CPU arm's list (every rank holds the
     # merged list; the CPU side is the C restatement over ALL n_total templates, OpenMP over templates, pinned bit for bit on
     # the reference's own code by tests/test_oracle_ref.py) ----
-    step(0, False)
-    torch.cuda.synchronize()
-    got0 = h.match_fetch() if world == 1 else sm.fetch()
+    for _ in range(depth):                                          # frame 0 through EVERY slot of the pipe
+        pipe.submit_device(d_frames[0][0].data_ptr(), d_frames[0][1].data_ptr(), W, H, THRESHOLD)
+    got_all = []
+    while pipe.in_flight():
+        got_all.append(pipe.collect().fetch().copy())
+    got0 = got_all[0]
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import fl_oracle_py as F
     odet = F.Detector(T)
     odet.set_templates(tset)
     odet.process(*frames[0])
     want0 = odet.match(THRESHOLD, n_threads=os.cpu_count() or 1)
-    list_ok = len(got0) == len(want0) and bool(np.array_equal(got0, want0))
+    list_ok = all(len(g) == len(want0) and bool(np.array_equal(g, want0)) for g in got_all)
     ok_t = torch.tensor([1 if list_ok else 0], device=dev)
     if world > 1:
         dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
@@ -369,46 +417,70 @@ def run_ours(args):
         h.profile(False)
     value = evals_per_step * args.steps / (dev_ms * 1e-3)
 
-    # ---- e2e: host buffers through the C ABI (rank-local; N > 1 adds the host copies to the sharded path) ----
+    # ---- e2e: HOST buffers in, HOST match lists out, through the C ABI; the same stream of frames with `depth` in flight ----
+    # the frames live in page-locked host memory (what a capture pipeline hands over) and are DMA'd from there
+    pinned = [(torch.from_numpy(b).pin_memory().numpy(), torch.from_numpy(d.view(np.int16)).pin_memory().numpy().view(np.uint16)) for b, d in frames]
     e2e = None
     if world == 1:
-        # the frames live in page-locked host memory (what a capture pipeline hands over); fl_match DMAs them from there
-        pinned = [(torch.from_numpy(b).pin_memory().numpy(), torch.from_numpy(d.view(np.int16)).pin_memory().numpy().view(np.uint16)) for b, d in frames]
+        cpipe = fb.Pipe(depth, T, (0, 1), W, H, device=local)            # fl_pipe_*: the C entry points a host application calls
+        cpipe.upload_templates(tset)
+
+        def host_stream(n, src):
+            m = None
+            for i in range(n):
+                if cpipe.in_flight() == depth:
+                    rc, m = cpipe.collect(4096, copy=False)
+                    assert rc == 0
+                cpipe.submit(src[i % N_FRAMES][0], src[i % N_FRAMES][1], THRESHOLD)
+            while cpipe.in_flight():
+                rc, m = cpipe.collect(4096, copy=False)
+                assert rc == 0
+            return m
+        host_stream(8, pinned)
+        t0 = time.perf_counter()
+        m = host_stream(args.steps, pinned)
+        t1 = time.perf_counter()
+        # the synchronous call, one frame in flight (fl_match: what the reference's Detector::match signature gives a caller)
         for i in range(3):
             h.match(pinned[i % N_FRAMES][0], pinned[i % N_FRAMES][1], THRESHOLD, capacity=4096)
-        t0 = time.perf_counter()
-        for i in range(args.steps):
-            b, d = pinned[i % N_FRAMES]
-            rc, m = h.match(b, d, THRESHOLD, capacity=4096)
-        t1 = time.perf_counter()
-        for i in range(5):
-            h.match(frames[i % N_FRAMES][0], frames[i % N_FRAMES][1], THRESHOLD, capacity=4096)
+        n_sync = min(args.steps, 300)
+        ts0 = time.perf_counter()
+        for i in range(n_sync):
+            rc, m1 = h.match(pinned[i % N_FRAMES][0], pinned[i % N_FRAMES][1], THRESHOLD, capacity=4096)
+        ts1 = time.perf_counter()
+        host_stream(8, frames)
+        n_page = min(args.steps, 200)
         tp0 = time.perf_counter()
-        for i in range(min(args.steps, 100)):
-            b, d = frames[i % N_FRAMES]
-            rc, m2 = h.match(b, d, THRESHOLD, capacity=4096)
+        host_stream(n_page, frames)
         tp1 = time.perf_counter()
+        cpipe.close()
         e2e = {"value": evals_per_step * args.steps / (t1 - t0), "unit": "evals/s", "h2d_bytes_per_step": W * H * 5,
-               "d2h_bytes_per_step": 64 + len(m) * 20, "frames_per_s": args.steps / (t1 - t0),
-               "timer": "host wall clock around fl_match (C ABI, host buffers in pinned memory; H2D and result read-back inside)",
-               "frames_per_s_pageable_input": min(args.steps, 100) / (tp1 - tp0)}
+               "d2h_bytes_per_step": 64 + len(m) * 20, "frames_per_s": args.steps / (t1 - t0), "frames_in_flight": depth,
+               "timer": "host wall clock around a stream of fl_pipe_submit / fl_pipe_collect calls (C ABI; host frames in page-locked memory, "
+                        "H2D and the read-back of every frame's match list inside)",
+               "frames_per_s_one_frame_in_flight": n_sync / (ts1 - ts0), "frames_per_s_pageable_input": n_page / (tp1 - tp0)}
     else:
-        pin = [(torch.from_numpy(b).pin_memory(), torch.from_numpy(d.view(np.int16)).pin_memory()) for b, d in frames]
-        tb, td = d_frames[0]
+        def host_stream(n):
+            m = None
+            for i in range(n):
+                if pipe.in_flight() == depth:
+                    m = pipe.collect().fetch()
+                pipe.submit_host(pinned[i % N_FRAMES][0], pinned[i % N_FRAMES][1], THRESHOLD)
+            while pipe.in_flight():
+                m = pipe.collect().fetch()
+            return m
+        host_stream(2 * depth)
         torch.cuda.synchronize(); dist.barrier()
         t0 = time.perf_counter()
-        for i in range(args.steps):
-            pb, pd = pin[i % N_FRAMES]
-            with torch.cuda.stream(stream):
-                tb.copy_(pb, non_blocking=True); td.copy_(pd, non_blocking=True)
-            sm.match_device(tb.data_ptr(), td.data_ptr(), W, H, THRESHOLD)
-            m = sm.fetch()
+        m = host_stream(args.steps)
         torch.cuda.synchronize(); dist.barrier()
         t1 = time.perf_counter()
         tt = torch.tensor([t1 - t0], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": evals_per_step * args.steps / float(tt.item()), "unit": "evals/s", "h2d_bytes_per_step": W * H * 5,
-               "d2h_bytes_per_step": 4 + len(m) * 20, "frames_per_s": args.steps / float(tt.item()), "timer": "host wall clock, max over ranks"}
+               "d2h_bytes_per_step": 64 + len(m) * 20, "frames_per_s": args.steps / float(tt.item()), "frames_in_flight": depth,
+               "timer": "host wall clock, max over ranks, around a stream of fl_match_shard_exchange_async / fl_match_wait / fl_match_fetch calls per rank "
+                        "(host frames in page-locked memory; H2D and the read-back of every frame's merged list inside)"}
 
     if rank != 0:
         if world > 1:
@@ -462,11 +534,17 @@ def run_ours(args):
         icp = bench_icp(h, synth, cpu=not args.no_cpu)
 
     line = {"metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms / args.steps, "ms_per_step_p50": float(np.median(per_step)), "ms_per_step_p90": float(np.percentile(per_step, 90)),
-            "ms_per_step_p95": float(np.percentile(per_step, 95)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD % args.templates, "templates_total": n_total,
-                       "l2": "flushed between steps (256 MB write)", "frames_per_s": args.steps / (dev_ms * 1e-3),
+            "latency_mode": {"what": "ONE frame in flight, L2 flushed (256 MB write) before every frame, CUDA events around each frame's device work; %d frames" % n_lat,
+                             "ms_per_frame": lat_ms, "ms_per_frame_p50": float(np.median(per_step)), "ms_per_frame_p90": float(np.percentile(per_step, 90)),
+                             "ms_per_frame_p95": float(np.percentile(per_step, 95)), "value": evals_per_step / (lat_ms * 1e-3), "unit": "evals/s"},
+            "config": {"workload": WORKLOAD % args.templates, "templates_total": n_total, "frames_in_flight": depth,
+                       "l2": "inputs larger than L2: the steps walk over %d device copies of the frames at distinct addresses (%.0f MB > 126 MB L2); "
+                             "no flush, the stream of frames is not interrupted" % (N_INPUT_SLOTS, N_INPUT_SLOTS * W * H * 5 / 1e6),
+                       "timed_region": "exactly `steps` frames of a running stream with `frames_in_flight` frames in flight per GPU; start event in front of the "
+                                       "first timed frame on its stream, end event after the last list has been collected; max over ranks",
+                       "frames_per_s": args.steps / (dev_ms * 1e-3),
                        "matches_last_frame": n_matches, "match_list_frame0": {"records": int(len(want0)), "sha256_16": list_sha,
                                                                               "equals_cpu_arm": True}, "parallelism": ("template-sharded x%d, candidate exchange: %s" % (world, "peer-memory push fused into the sort kernel (NVLink)" if sm.exchange == "p2p" else "1 NCCL all-gather/frame")) if world > 1 else "single GPU"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
@@ -864,6 +942,7 @@ def main():
     ap.add_argument("--templates", type=int, default=8000, help="templates per GPU")
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"], help="candidate exchange of the template-sharded path (N > 1)")
     ap.add_argument("--per-step", action="store_true", help="print the distribution of per-step device times of every rank to stderr")
+    ap.add_argument("--in-flight", type=int, default=4, help="frames in flight per GPU (1 = the synchronous Detector::match loop)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-icp", action="store_true", help="skip the ICP side benchmark")
     ap.add_argument("--config", default="C2", choices=["C2", "C4", "C5"], help="C2: the headline match-only benchmark (weak scaling); C4 / C5: the "

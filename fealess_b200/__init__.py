@@ -47,7 +47,7 @@ EXPORTED_SYMBOLS = [
     "fl_detection_batch", "fl_upload_model_depths", "fl_detection_batch_resident", "fl_detection_batch_resident_device", "fl_detection", "fl_nms", "fl_nms_ex", "fl_debug_option", "fl_debug_keep_spread", "fl_debug_force_baseline", "fl_debug_uses_staged", "fl_debug_get", "fl_debug_icp_trace", "fl_launch_count",
     "fl_profile", "fl_last_stage_ms", "fl_last_icp_ms",
     "fl_group_create", "fl_group_destroy", "fl_group_size", "fl_group_handle", "fl_group_upload_templates", "fl_group_match",
-    "fl_match_async", "fl_pipe_create", "fl_pipe_destroy", "fl_pipe_depth", "fl_pipe_in_flight", "fl_pipe_handle", "fl_pipe_upload_templates",
+    "fl_match_async", "fl_match_shard_exchange_async", "fl_pipe_create", "fl_pipe_destroy", "fl_pipe_depth", "fl_pipe_in_flight", "fl_pipe_handle", "fl_pipe_upload_templates",
     "fl_pipe_submit", "fl_pipe_collect", "fl_pipe_match_batch",
 ]
 
@@ -255,6 +255,14 @@ class Handle:
         _check(lib().fl_match_device_async(self._h, C.c_void_p(d_bgr), C.c_void_p(d_depth), W, H, None, C.c_float(threshold), _p(cf),
                                            0 if cf is None else int(cf.size)), "fl_match_device_async")
 
+    def match_async(self, bgr, depth, threshold: float, class_filter=None) -> None:
+        """fl_match_async: enqueue-only half of ``match`` for a frame in host memory (dense numpy arrays; page-locked ones are read
+        by DMA and have to stay alive until ``match_wait``)."""
+        H, W = (depth if depth is not None else bgr).shape[:2]
+        cf = None if not class_filter else np.ascontiguousarray(class_filter, np.int32)
+        _check(lib().fl_match_async(self._h, _p(bgr), C.c_size_t(W * 3), _p(depth), C.c_size_t(W * 2), W, H, None, C.c_float(threshold), _p(cf),
+                                    0 if cf is None else int(cf.size)), "fl_match_async")
+
     def match_wait(self) -> None:
         _check(lib().fl_match_wait(self._h), "fl_match_wait")
 
@@ -302,6 +310,17 @@ class Handle:
         _check(lib().fl_match_shard_exchange_device_async(self._h, C.c_void_p(d_bgr), C.c_void_p(d_depth), W, H, C.c_float(threshold), _p(cf),
                                                           0 if cf is None else int(cf.size), rank, world, arr, capacity, C.c_void_p(d_local_block),
                                                           C.c_uint32(epoch)), "fl_match_shard_exchange_device_async")
+
+    def match_shard_exchange_async(self, bgr, depth, threshold: float, rank: int, world: int, peer_buffers: Sequence[int], capacity: int,
+                                   d_local_block: int, epoch: int, class_filter=None) -> None:
+        """fl_match_shard_exchange_async: the frame in HOST memory (numpy arrays, dense rows; page-locked ones are read by DMA and have
+        to stay alive until ``match_wait``)."""
+        H, W = (depth if depth is not None else bgr).shape[:2]
+        cf = None if not class_filter else np.ascontiguousarray(class_filter, np.int32)
+        arr = (C.c_void_p * world)(*[int(p) for p in peer_buffers])
+        _check(lib().fl_match_shard_exchange_async(self._h, _p(bgr), C.c_size_t(W * 3), _p(depth), C.c_size_t(W * 2), W, H, C.c_float(threshold), _p(cf),
+                                                   0 if cf is None else int(cf.size), rank, world, arr, capacity, C.c_void_p(d_local_block),
+                                                   C.c_uint32(epoch)), "fl_match_shard_exchange_async")
 
     def sync(self):
         _check(lib().fl_sync(self._h), "fl_sync")

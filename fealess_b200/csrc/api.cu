@@ -982,6 +982,23 @@ extern "C" int fl_match_shard_exchange_device_async(fl_handle* h, const void* d_
   return sort_launch(h, lists, h->d_out, h->p.max_candidates, h->d_out_count, true, &X, defer ? &req : nullptr);
 }
 
+extern "C" int fl_match_shard_exchange_async(fl_handle* h, const uint8_t* bgr, size_t bgr_stride, const uint16_t* depth, size_t depth_stride, int32_t W, int32_t H,
+                                             float threshold, const int32_t* class_filter, int32_t n_filter, int32_t rank, int32_t world,
+                                             void* const* peer_buffers, int32_t capacity, fl_match_t* d_local_block, uint32_t epoch) {
+  if (!h) return FL_ERR_ARG;
+  if (h->pend_sort) { fl_set_error("fl_match_wait has not been called for the previous frame"); return FL_ERR_STATE; }
+  h->in_depth_W = h->in_depth_H = 0;
+  if (W <= 0 || H <= 0 || W > h->p.max_width || H > h->p.max_height) return FL_ERR_SIZE;
+  FL_CUDA(cudaSetDevice(h->p.device));
+  const uint8_t* d_bgr; const uint16_t* d_depth;
+  const void* d_masks[FL_MAX_MODALITIES];
+  bool any_mask;
+  TRY(stage_frame(h, bgr, bgr_stride, depth, depth_stride, W, H, nullptr, &d_bgr, &d_depth, d_masks, &any_mask));
+  TRY(fl_match_shard_exchange_device_async(h, d_bgr, d_depth, W, H, threshold, class_filter, n_filter, rank, world, peer_buffers, capacity, d_local_block, epoch));
+  if (d_depth) { h->in_depth_W = W; h->in_depth_H = H; }
+  return FL_OK;
+}
+
 extern "C" int fl_exchange_sort_unique_device(fl_handle* h, int32_t rank, int32_t world, void* const* peer_buffers, int32_t capacity,
                                               const fl_match_t* d_local_block, uint32_t epoch) {
   int rc = fl_exchange_sort_unique_device_async(h, rank, world, peer_buffers, capacity, d_local_block, epoch);

@@ -7,7 +7,7 @@
 // peers' epochs, sort the union - the last CTA of k_refine_sort<1>) is the same one the one-process-per-GPU path uses with torch
 // symmetric memory.  Templates are dealt round-robin by global index (gid % N) and carry their global per-class ids, so the
 // merged list equals a single handle's.  One fl_group_match = the frame copied to every device from the caller's
-// buffers, ONE enqueue per handle, one wait per handle, the merged list read from handle 0.
+// buffers (fl_match_shard_exchange_async), ONE enqueue per handle, one wait per handle, the merged list read from handle 0.
 #include "fl_internal.cuh"
 #include <algorithm>
 #include <vector>
@@ -18,8 +18,6 @@ struct fl_group {
   std::vector<int> device;
   std::vector<uint8_t*> xbuf;          // exchange buffer of handle i (on device[i])
   std::vector<fl_match_t*> block;      // candidate block [count | cap records] of handle i
-  std::vector<uint8_t*> d_bgr;
-  std::vector<uint16_t*> d_depth;
   std::vector<void*> peers;            // xbuf as void* (the same array for every rank: unified addressing)
   int max_w, max_h;
   uint32_t epoch;
@@ -41,8 +39,6 @@ extern "C" int fl_group_destroy(fl_group* g) {
     if (i < (int)g->h.size() && g->h[i]) { fl_sync(g->h[i]); }
     if (i < (int)g->xbuf.size()) cudaFree(g->xbuf[i]);
     if (i < (int)g->block.size()) cudaFree(g->block[i]);
-    if (i < (int)g->d_bgr.size()) cudaFree(g->d_bgr[i]);
-    if (i < (int)g->d_depth.size()) cudaFree(g->d_depth[i]);
     if (i < (int)g->h.size() && g->h[i]) fl_destroy(g->h[i]);
   }
   delete g;
@@ -55,7 +51,7 @@ extern "C" int fl_group_create(const fl_params_t* params, const int32_t* devices
   fl_group* g = new fl_group;
   g->n = n; g->cap = exchange_capacity; g->epoch = 0; g->max_w = params->max_width; g->max_h = params->max_height;
   g->h.assign(n, nullptr); g->device.assign(devices, devices + n); g->xbuf.assign(n, nullptr); g->block.assign(n, nullptr);
-  g->d_bgr.assign(n, nullptr); g->d_depth.assign(n, nullptr); g->peers.assign(n, nullptr);
+  g->peers.assign(n, nullptr);
   auto fail = [&](int rc) { fl_group_destroy(g); return rc; };
   // peer access between every pair of distinct devices (already enabled is fine)
   for (int i = 0; i < n; ++i)
@@ -81,9 +77,7 @@ extern "C" int fl_group_create(const fl_params_t* params, const int32_t* devices
     if (cudaSetDevice(devices[i]) != cudaSuccess) return fail(FL_ERR_CUDA);
     if (cudaMalloc(&g->xbuf[i], xbytes) != cudaSuccess || cudaMemset(g->xbuf[i], 0, xbytes) != cudaSuccess ||
         cudaMalloc(&g->block[i], sizeof(fl_match_t) * ((size_t)exchange_capacity + 1)) != cudaSuccess ||
-        cudaMemset(g->block[i], 0, sizeof(fl_match_t) * ((size_t)exchange_capacity + 1)) != cudaSuccess ||
-        cudaMalloc(&g->d_bgr[i], (size_t)p.max_width * p.max_height * 3) != cudaSuccess ||
-        cudaMalloc(&g->d_depth[i], (size_t)p.max_width * p.max_height * 2) != cudaSuccess) {
+        cudaMemset(g->block[i], 0, sizeof(fl_match_t) * ((size_t)exchange_capacity + 1)) != cudaSuccess) {
       fl_set_error("fl_group_create: device allocation failed on device %d: %s", devices[i], cudaGetErrorString(cudaGetLastError()));
       return fail(FL_ERR_CUDA);
     }
@@ -154,11 +148,8 @@ extern "C" int fl_group_match(fl_group* g, const uint8_t* bgr, size_t bgr_stride
     int launched = 0;
     for (int i = 0; i < g->n; ++i) {                            // enqueue on every handle; nothing waits until all are under way
       GCUDA(cudaSetDevice(g->device[i]));
-      cudaStream_t s = static_cast<cudaStream_t>(fl_stream(g->h[i]));
-      if (depth) GCUDA(cudaMemcpy2DAsync(g->d_depth[i], (size_t)W * 2, depth, depth_stride, (size_t)W * 2, H, cudaMemcpyHostToDevice, s));
-      if (bgr) GCUDA(cudaMemcpy2DAsync(g->d_bgr[i], (size_t)W * 3, bgr, bgr_stride, (size_t)W * 3, H, cudaMemcpyHostToDevice, s));
-      const int rc = fl_match_shard_exchange_device_async(g->h[i], bgr ? g->d_bgr[i] : nullptr, depth ? g->d_depth[i] : nullptr, W, H, threshold, class_filter, n_filter,
-                                                          i, g->n, g->peers.data(), g->cap, g->block[i], g->epoch);
+      const int rc = fl_match_shard_exchange_async(g->h[i], bgr, bgr_stride, depth, depth_stride, W, H, threshold, class_filter, n_filter,
+                                                   i, g->n, g->peers.data(), g->cap, g->block[i], g->epoch);
       if (rc != FL_OK) { first_err = rc; break; }                // (the ranks already launched report the missing peer instead of hanging)
       ++launched;
     }

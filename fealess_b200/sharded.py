@@ -132,6 +132,9 @@ class ShardedMatcher:
         """One frame, enqueue only: the local match and (p2p exchange) the exchange + merge kernel go onto the handle's stream.
         Returns True when ``match_wait`` is all that is left (p2p); with the NCCL exchange the collective and the merge are
         issued by ``match_wait``."""
+        if self.world == 1:                                      # nothing to exchange: the plain three-launch frame
+            self.h.match_device_async(d_bgr, d_depth, W, H, threshold)
+            return True
         if self.exchange == "p2p":
             # front end + matchClass, then ONE launch: refinement, push to the peers, wait, sort of the union
             self.epoch += 1
@@ -143,10 +146,32 @@ class ShardedMatcher:
         self.h.match_shard_device(d_bgr, d_depth, W, H, threshold, recs.data_ptr(), self.cap, self.block.data_ptr())
         return False
 
+    def match_host_async(self, bgr: np.ndarray, depth: np.ndarray, threshold: float) -> bool:
+        """``match_device_async`` for a frame in host memory: with the p2p exchange ONE C call uploads the frame and enqueues the
+        local match and the exchange (fl_match_shard_exchange_async); with the NCCL exchange the frame is copied into the rank's
+        device buffers first."""
+        H, W = depth.shape[:2]
+        if self.world == 1:
+            self._host_frame = (bgr, depth)
+            self.h.match_async(bgr, depth, threshold)
+            return True
+        if self.exchange == "p2p":
+            self.epoch += 1
+            self._host_frame = (bgr, depth)                     # page-locked buffers are read by DMA until match_wait
+            self.h.match_shard_exchange_async(bgr, depth, threshold, self.rank, self.world, self._peers, self.cap, self.block.data_ptr(), self.epoch)
+            return True
+        torch = self._torch
+        if getattr(self, "_d_in", None) is None or self._d_in[0].numel() != H * W * 3:
+            self._d_in = (torch.empty(H * W * 3, dtype=torch.uint8, device=self.block.device), torch.empty(H * W, dtype=torch.int16, device=self.block.device))
+        with torch.cuda.stream(self.stream):
+            self._d_in[0].copy_(torch.from_numpy(bgr).view(-1), non_blocking=True)
+            self._d_in[1].copy_(torch.from_numpy(depth.view(np.int16)).view(-1), non_blocking=True)
+        return self.match_device_async(self._d_in[0].data_ptr(), self._d_in[1].data_ptr(), W, H, threshold)
+
     def match_wait(self) -> None:
         torch = self._torch
         import torch.distributed as dist
-        if self.exchange == "p2p":
+        if self.exchange == "p2p" or self.world == 1:
             self.h.match_wait()
             return
         with torch.cuda.stream(self.stream):
@@ -163,6 +188,59 @@ class ShardedMatcher:
 
     def fetch(self) -> np.ndarray:
         return self.h.match_fetch()
+
+
+class ShardedPipe:
+    """Several frames in flight on every rank of a template-sharded detector: ``depth`` ShardedMatchers (each with its own handle,
+    stream, candidate block and exchange buffer), frames dealt round-robin, lists collected in submission order.  Every rank has
+    to submit and collect the same sequence of frames (frame i's exchange pairs slot i % depth of all ranks); a kernel that waits
+    for a peer's block holds one CTA, so the other slots' frames keep the GPU busy meanwhile.  With one rank this is fl_pipe's
+    schedule driven from Python (the bench uses it at N = 1 too, so that every N runs the same loop)."""
+
+    def __init__(self, make_handle, tset, rank: int, world: int, depth: int = 4, capacity: int = 2048, device=None, exchange: str = "auto"):
+        self.depth = int(depth)
+        self.slots = [ShardedMatcher(make_handle(), tset, rank, world, capacity=capacity, device=device, exchange=exchange) for _ in range(self.depth)]
+        modes = {s.exchange for s in self.slots}
+        if len(modes) != 1:
+            raise RuntimeError("the slots of a ShardedPipe disagree on the exchange mode: %s" % sorted(modes))
+        self.exchange = self.slots[0].exchange
+        self.submitted = self.collected = 0
+
+    def in_flight(self) -> int:
+        return self.submitted - self.collected
+
+    def _next_slot(self) -> "ShardedMatcher":
+        if self.in_flight() >= self.depth:
+            raise RuntimeError("ShardedPipe: %d frames in flight already - collect one first" % self.depth)
+        s = self.slots[self.submitted % self.depth]
+        self.submitted += 1
+        return s
+
+    def submit_device(self, d_bgr: int, d_depth: int, W: int, H: int, threshold: float) -> "ShardedMatcher":
+        s = self._next_slot()
+        s.match_device_async(d_bgr, d_depth, W, H, threshold)
+        return s
+
+    def submit_host(self, bgr: np.ndarray, depth: np.ndarray, threshold: float) -> "ShardedMatcher":
+        s = self._next_slot()
+        s.match_host_async(bgr, depth, threshold)
+        return s
+
+    def collect(self) -> "ShardedMatcher":
+        """Waits for the oldest frame in flight; returns its slot (``slot.fetch()`` = the merged match list)."""
+        if self.in_flight() == 0:
+            raise RuntimeError("ShardedPipe: no frame in flight")
+        s = self.slots[self.collected % self.depth]
+        self.collected += 1
+        s.match_wait()
+        return s
+
+    def launch_count(self) -> int:
+        return sum(s.h.launch_count() for s in self.slots)
+
+    def close(self) -> None:
+        for s in self.slots:
+            s.h.close()
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -205,6 +205,11 @@ int fl_exchange_sort_unique_device(fl_handle* h, int32_t rank, int32_t world, vo
 int fl_match_shard_exchange_device_async(fl_handle* h, const void* d_bgr, const void* d_depth, int32_t W, int32_t H, float threshold,
                                          const int32_t* class_filter, int32_t n_filter, int32_t rank, int32_t world,
                                          void* const* peer_buffers, int32_t capacity, fl_match_t* d_local_block, uint32_t epoch);
+/* the same with the frame in HOST memory (buffers as in fl_match_async): upload + local match + exchange in one call, so that a
+ * rank's per-frame host work is this call, fl_match_wait and fl_match_fetch */
+int fl_match_shard_exchange_async(fl_handle* h, const uint8_t* bgr, size_t bgr_stride, const uint16_t* depth, size_t depth_stride, int32_t W, int32_t H,
+                                  float threshold, const int32_t* class_filter, int32_t n_filter, int32_t rank, int32_t world,
+                                  void* const* peer_buffers, int32_t capacity, fl_match_t* d_local_block, uint32_t epoch);
 /* enqueue-only half; finish with fl_match_wait */
 int fl_exchange_sort_unique_device_async(fl_handle* h, int32_t rank, int32_t world, void* const* peer_buffers, int32_t capacity,
                                          const fl_match_t* d_local_block, uint32_t epoch);
