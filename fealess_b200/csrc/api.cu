@@ -48,7 +48,7 @@ struct fl_handle {
   uint8_t* d_qm[FL_MAX_LEVELS][FL_MAX_MODALITIES];         // masked copies (allocated on first use)
   uint8_t* d_mask[FL_MAX_LEVELS][FL_MAX_MODALITIES];
   uint8_t* d_spread[FL_MAX_LEVELS][FL_MAX_MODALITIES];     // debug only
-  uint8_t* d_lm[FL_MAX_LEVELS]; size_t lm_bytes[FL_MAX_LEVELS];
+  uint8_t* d_lm[FL_MAX_LEVELS]; size_t lm_bytes[FL_MAX_LEVELS]; uint8_t* d_lm4;   // d_lm4: 4-bit copy of the coarsest level's linear memories
   bool used_mask[FL_MAX_MODALITIES]; bool keep_spread;
   // state between the enqueue half (fl_match_device_async, ..._async) and fl_match_wait
   bool pend_sort, pend_match, pend_own, pend_masks_valid, pend_small_fused; fl_lists pend_lists; fl_match_t* pend_out; int pend_out_cap; int* pend_out_count;
@@ -105,7 +105,7 @@ static size_t level_lm_bytes(const fl_params_t& p, int l, int W, int H, fl_level
   gg.W = W >> l; gg.H = H >> l; gg.T = p.T[l];
   gg.Wd = gg.W / gg.T; gg.Hd = gg.H / gg.T; gg.cells = gg.Wd * gg.Hd;
   size_t ls = (size_t)gg.T * gg.T * gg.cells + FL_LM_PAD;
-  gg.label_stride = (ls + 15) & ~(size_t)15;
+  gg.label_stride = (ls + 31) & ~(size_t)31;
   gg.mod_stride = gg.label_stride * 8;
   if (g) *g = gg;
   return gg.mod_stride * p.n_modalities;
@@ -141,7 +141,7 @@ extern "C" int fl_create(const fl_params_t* params, fl_handle** out) {
   memset(&h->rz, 0, sizeof h->rz); h->rz_sW = h->rz_sH = h->rz_dW = h->rz_dH = 0;
   h->d_src_bgr = nullptr; h->d_src_depth = nullptr; h->src_cap = 0;
   memset(h->d_bgr, 0, sizeof h->d_bgr); memset(h->d_q, 0, sizeof h->d_q); memset(h->d_qm, 0, sizeof h->d_qm);
-  memset(h->d_mask, 0, sizeof h->d_mask); memset(h->d_spread, 0, sizeof h->d_spread); memset(h->d_lm, 0, sizeof h->d_lm);
+  memset(h->d_mask, 0, sizeof h->d_mask); memset(h->d_spread, 0, sizeof h->d_spread); memset(h->d_lm, 0, sizeof h->d_lm); h->d_lm4 = nullptr;
   memset(h->used_mask, 0, sizeof h->used_mask); memset(h->stage_ms, 0, sizeof h->stage_ms); h->icp_ms = 0.f;
   *out = h;
   FL_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -157,9 +157,14 @@ extern "C" int fl_create(const fl_params_t* params, fl_handle** out) {
     // linear memories: T need not divide the maximum size, so bound the cell count from above
     int T = p.T[l];
     size_t cells = (size_t)(((p.max_width >> l) + T - 1) / T) * (((p.max_height >> l) + T - 1) / T);
-    size_t ls = (((size_t)T * T * cells + FL_LM_PAD) + 15) & ~(size_t)15;
+    size_t ls = (((size_t)T * T * cells + FL_LM_PAD) + 31) & ~(size_t)31;
     h->lm_bytes[l] = ls * 8 * p.n_modalities + cells + 256;   // slack: windowed reads may run one map past the last label
     TRY(dalloc(&h->d_lm[l], h->lm_bytes[l]));
+    if (l == p.n_levels - 1) {
+      // 4-bit copy of the coarsest level's linear memories (two cells per byte), read by the staged similarity kernel
+      TRY(dalloc(&h->d_lm4, h->lm_bytes[l] / 2 + 256));
+      FL_CUDA(cudaMemset(h->d_lm4, 0, h->lm_bytes[l] / 2 + 256));
+    }
   }
   TRY(dalloc(&h->d_cand, (size_t)p.max_candidates)); TRY(dalloc(&h->d_count, 4));
   FL_CUDA(cudaMemset(h->d_count, 0, 4 * sizeof(int)));
@@ -215,7 +220,7 @@ extern "C" int fl_destroy(fl_handle* h) {
   cudaFree(h->d_src_bgr); cudaFree(h->d_src_depth);
   cudaFree(h->d_in_bgr); cudaFree(h->d_in_depth); cudaFree(h->d_geom);
   for (int l = 0; l < FL_MAX_LEVELS; ++l) {
-    cudaFree(h->d_bgr[l]); cudaFree(h->d_lm[l]);
+    cudaFree(h->d_bgr[l]); cudaFree(h->d_lm[l]); if (l == 0) cudaFree(h->d_lm4);
     for (int m = 0; m < FL_MAX_MODALITIES; ++m) { cudaFree(h->d_q[l][m]); cudaFree(h->d_qm[l][m]); cudaFree(h->d_mask[l][m]); cudaFree(h->d_spread[l][m]); }
   }
   cudaFree(h->d_fe_counters); cudaFree(h->d_fe_trace); cudaFreeHost(h->h_fe_err);
@@ -378,6 +383,7 @@ static int ensure_geometry(fl_handle* h, int W, int H) {
       size_t need = level_lm_bytes(p, l, W, H, &h->geom[l]);
       if (need > h->lm_bytes[l]) { fl_set_error("internal: LM capacity"); return FL_ERR_CAPACITY; }
       FL_CUDA(cudaMemsetAsync(h->d_lm[l], 0, h->lm_bytes[l], h->stream));       // pads must read as zero
+      if (l == p.n_levels - 1) FL_CUDA(cudaMemsetAsync(h->d_lm4, 0, h->lm_bytes[l] / 2 + 256, h->stream));
     }
     FL_CUDA(cudaMemcpyAsync(h->d_geom, h->geom, sizeof(fl_level_geom) * p.n_levels, cudaMemcpyHostToDevice, h->stream));
     FL_CUDA(cudaStreamSynchronize(h->stream));                                  // h->geom is pageable
@@ -417,6 +423,10 @@ static int ensure_geometry(fl_handle* h, int W, int H) {
   return FL_OK;
 }
 
+// the 4-bit linear memories of (level, modality): only the coarsest level has them, and only grids of even width (two cells per byte)
+static uint8_t* lm4_of(fl_handle* h, int l, int m) {
+  return (l == h->p.n_levels - 1 && (h->geom[l].Wd & 1) == 0) ? h->d_lm4 + (((size_t)m * h->geom[l].mod_stride) >> 1) : nullptr;
+}
 static void fe_wave_init(fl_fe_wave* w) { memset(w, 0, sizeof *w); }   // an empty launch description (no jobs, no in-grid dependencies)
 
 // front end + matchClass on the handle's templates; candidates land in (cand, count)
@@ -546,7 +556,7 @@ static int run_match_stages(fl_handle* h, const uint8_t* d_bgr, const uint16_t* 
         for (int m = 0; m < p.n_modalities; ++m) {
           uint8_t* spread = nullptr;
           if (h->keep_spread) { if (!h->d_spread[l][m]) TRY(dalloc(&h->d_spread[l][m], (size_t)(p.max_width >> l) * (p.max_height >> l))); spread = h->d_spread[l][m]; }
-          fl_fe_add_spread(&w, h->d_q[l][m], h->geom[l], h->d_lm[l] + (size_t)m * h->geom[l].mod_stride, spread);
+          fl_fe_add_spread(&w, h->d_q[l][m], h->geom[l], h->d_lm[l] + (size_t)m * h->geom[l].mod_stride, spread, lm4_of(h, l, m));
           const bool is_color = p.modality_kind[m] == FL_MODALITY_COLOR_GRADIENT;
           consume(is_color ? slot_color[l][m] : slot_depth[m]);
           consume_rows(is_color ? slot_color[l][m] : slot_depth[m], is_color ? 0 : l);
@@ -596,7 +606,7 @@ static int run_match_stages(fl_handle* h, const uint8_t* d_bgr, const uint16_t* 
           uint8_t* spread = nullptr;
           if (h->keep_spread) { if (!h->d_spread[l - 1][m]) TRY(dalloc(&h->d_spread[l - 1][m], (size_t)(p.max_width >> (l - 1)) * (p.max_height >> (l - 1)))); spread = h->d_spread[l - 1][m]; }
           wave_room();
-          fl_fe_add_spread(&w, h->d_q[l - 1][m], g, h->d_lm[l - 1] + (size_t)m * g.mod_stride, spread);
+          fl_fe_add_spread(&w, h->d_q[l - 1][m], g, h->d_lm[l - 1] + (size_t)m * g.mod_stride, spread, lm4_of(h, l - 1, m));
         }
       }
       if (l < L) {
@@ -641,7 +651,7 @@ static int run_match_stages(fl_handle* h, const uint8_t* d_bgr, const uint16_t* 
         }
         uint8_t* spread = nullptr;
         if (h->keep_spread) { if (!h->d_spread[l][m]) TRY(dalloc(&h->d_spread[l][m], (size_t)(p.max_width >> l) * (p.max_height >> l))); spread = h->d_spread[l][m]; }
-        fl_launch_spread_lm(qsrc, g, h->d_lm[l] + (size_t)m * g.mod_stride, spread, s); ++h->launches;
+        fl_launch_spread_lm(qsrc, g, h->d_lm[l] + (size_t)m * g.mod_stride, spread, lm4_of(h, l, m), s); ++h->launches;
       }
       color_pyr_done = false;
     }
@@ -652,7 +662,7 @@ static int run_match_stages(fl_handle* h, const uint8_t* d_bgr, const uint16_t* 
     fl_tdb db = make_tdb(h);
     const int lowest = p.n_levels - 1;
     if (h->use_staged) {
-      if (fl_launch_similarity_staged(db, h->geom[lowest], h->d_lm[lowest], threshold, cand, cap, d_count, h->plan, s) != 0) {
+      if (fl_launch_similarity_staged(db, h->geom[lowest], h->d_lm4, threshold, cand, cap, d_count, h->plan, s) != 0) {
         fl_set_error("staged similarity kernel could not be configured"); return FL_ERR_CUDA;
       }
     } else {

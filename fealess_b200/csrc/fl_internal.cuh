@@ -18,7 +18,7 @@ struct __align__(8) fl_pfeat { uint32_t lm_off; int16_t x, y; };
 
 struct fl_level_geom {
   int W, H, T, Wd, Hd, cells;      // image size at the level, sampling step, decimated size
-  size_t label_stride;             // bytes per label (T*T*cells + pad, 16-aligned)
+  size_t label_stride;             // bytes per label (T*T*cells + pad, 32-aligned: the 4-bit copy of a label starts 16-byte aligned)
   size_t mod_stride;               // bytes per modality = 8 * label_stride
 };
 
@@ -60,14 +60,14 @@ int fl_launch_tables_init();   // uploads the two LUTs to __constant__ memory of
 void fl_launch_pyrdown_bgr(const uint8_t* src, int W, int H, uint8_t* dst, cudaStream_t s);
 void fl_launch_resize_nn_half(const uint8_t* src, int W, int H, uint8_t* dst, cudaStream_t s);
 void fl_launch_apply_mask(const uint8_t* q, const uint8_t* mask, int n, uint8_t* out, cudaStream_t s);
-void fl_launch_spread_lm(const uint8_t* q, fl_level_geom g, uint8_t* lm_mod, uint8_t* spread_or_null, cudaStream_t s);
+void fl_launch_spread_lm(const uint8_t* q, fl_level_geom g, uint8_t* lm_mod, uint8_t* spread_or_null, uint8_t* lm4_mod_or_null, cudaStream_t s);
 
 // one launch = several independent front-end jobs (see k_front_end_wave)
 enum { FL_JOB_PYRDOWN = 2, FL_JOB_RESIZE = 3, FL_JOB_SPREAD = 4, FL_JOB_COLOR2 = 5, FL_JOB_DEPTH2 = 6, FL_JOB_PREFETCH = 7 };
 struct fl_fe_job {
   int kind, cta_begin, gx, W, H, p0, p1;
   float thr_sq;
-  const uint8_t* src; uint8_t* dst; uint8_t* dst2;
+  const uint8_t* src; uint8_t* dst; uint8_t* dst2; uint8_t* dst3;   // spread job: dst = linear memories, dst2 = spread image (or NULL), dst3 = 4-bit linear memories (or NULL)
   fl_level_geom g;
   // in-grid dependencies (single-launch front end): a CTA of this job first waits until counters[wait_slot] has reached
   // wait_target (all CTAs of the producing job have finished), and bumps counters[signal_slot] when it is done; -1 = none
@@ -96,7 +96,7 @@ void fl_fe_add_pyrdown(fl_fe_wave* w, const uint8_t* src, int W, int H, uint8_t*
 // in the shadow of the front end so that its prologue does not start with DRAM round trips
 void fl_fe_add_prefetch(fl_fe_wave* w, const void* src, size_t bytes);
 void fl_fe_add_resize(fl_fe_wave* w, const uint8_t* src, int W, int H, uint8_t* dst);
-void fl_fe_add_spread(fl_fe_wave* w, const uint8_t* q, fl_level_geom g, uint8_t* lm_mod, uint8_t* spread_or_null);
+void fl_fe_add_spread(fl_fe_wave* w, const uint8_t* q, fl_level_geom g, uint8_t* lm_mod, uint8_t* spread_or_null, uint8_t* lm4_mod_or_null);
 cudaError_t fl_launch_fe_wave(const fl_fe_wave& w, cudaStream_t s);
 
 // ---- similarity / refinement / sort (similarity.cu) ---------------------------------------------
@@ -139,7 +139,7 @@ struct fl_refine_args {
   fl_level_geom g[FL_MAX_LEVELS];
   const uint8_t* lm[FL_MAX_LEVELS];
 };
-int fl_launch_similarity_staged(fl_tdb db, fl_level_geom g, const uint8_t* lm_level, float threshold, fl_match_t* cand, int cap,
+int fl_launch_similarity_staged(fl_tdb db, fl_level_geom g, const uint8_t* lm4_level, float threshold, fl_match_t* cand, int cap,
                                 int* d_count, fl_staged_plan plan, cudaStream_t s);
 void fl_launch_pack_features(fl_tdb db, const fl_level_geom* d_geom, int n_features_total, cudaStream_t s);
 void fl_launch_similarity_global(fl_tdb db, fl_level_geom g, const uint8_t* lm_level, float threshold,

@@ -215,7 +215,7 @@ __device__ __forceinline__ uint32_t or_window(const uint32_t* __restrict__ w, in
 
 template <int TT>
 __device__ __forceinline__ void dev_spread_lm(const uint8_t* __restrict__ q, const fl_level_geom& g, uint8_t* __restrict__ lm,
-                                              uint8_t* __restrict__ spread_out, int bx, int by, uint8_t* smem, int cw) {
+                                              uint8_t* __restrict__ spread_out, uint8_t* __restrict__ lm4, int bx, int by, uint8_t* smem, int cw) {
   const int T = TT > 0 ? TT : g.T;
   const int W = g.W, H = g.H, Wd = g.Wd;
   const int gy = by, cx0 = bx * cw;                     // cw <= SL_CW cells per CTA (fewer on small levels: more CTAs in flight)
@@ -308,29 +308,38 @@ __device__ __forceinline__ void dev_spread_lm(const uint8_t* __restrict__ q, con
       uint8_t* dst = lm + (size_t)lab * g.label_stride + off;
       if (nvalid == 4 && (((uintptr_t)dst) & 3) == 0) *reinterpret_cast<uint32_t*>(dst) = w;
       else for (int k = 0; k < nvalid; ++k) dst[k] = (uint8_t)(w >> (8 * k));
+      if (lm4) {
+        // the same four responses (each 0, 1, 2 or 4) as nibbles, cell j of the label in nibble j: what the staged similarity
+        // kernel reads (half the bytes).  Only passed for grids of even width, so `off` is even and nvalid is 2 or 4.
+        const uint32_t p2 = (w | (w >> 4)) & 0x00FF00FFu;
+        const uint32_t p4 = (p2 | (p2 >> 8)) & 0xFFFFu;
+        uint8_t* d4 = lm4 + (((size_t)lab * g.label_stride + off) >> 1);
+        if (nvalid == 4) *reinterpret_cast<uint16_t*>(d4) = (uint16_t)p4;
+        else *d4 = (uint8_t)p4;
+      }
     }
   }
 }
 
 __device__ __forceinline__ void dev_spread_lm_any(const uint8_t* __restrict__ q, const fl_level_geom& g, uint8_t* __restrict__ lm,
-                                                  uint8_t* __restrict__ spread_out, int bx, int by, uint8_t* smem, int cw) {
+                                                  uint8_t* __restrict__ spread_out, uint8_t* __restrict__ lm4, int bx, int by, uint8_t* smem, int cw) {
   switch (g.T) {
-    case 5: dev_spread_lm<5>(q, g, lm, spread_out, bx, by, smem, cw); break;
-    case 8: dev_spread_lm<8>(q, g, lm, spread_out, bx, by, smem, cw); break;
-    case 4: dev_spread_lm<4>(q, g, lm, spread_out, bx, by, smem, cw); break;
-    default: dev_spread_lm<0>(q, g, lm, spread_out, bx, by, smem, cw); break;
+    case 5: dev_spread_lm<5>(q, g, lm, spread_out, lm4, bx, by, smem, cw); break;
+    case 8: dev_spread_lm<8>(q, g, lm, spread_out, lm4, bx, by, smem, cw); break;
+    case 4: dev_spread_lm<4>(q, g, lm, spread_out, lm4, bx, by, smem, cw); break;
+    default: dev_spread_lm<0>(q, g, lm, spread_out, lm4, bx, by, smem, cw); break;
   }
 }
 
 __global__ void __launch_bounds__(SL_THREADS) k_spread_lm(const uint8_t* __restrict__ q, fl_level_geom g, uint8_t* __restrict__ lm,
-                                                          uint8_t* __restrict__ spread_out) {
+                                                          uint8_t* __restrict__ spread_out, uint8_t* __restrict__ lm4) {
   extern __shared__ __align__(16) uint8_t smem_dyn[];
-  dev_spread_lm_any(q, g, lm, spread_out, blockIdx.x, blockIdx.y, smem_dyn, SL_CW);
+  dev_spread_lm_any(q, g, lm, spread_out, lm4, blockIdx.x, blockIdx.y, smem_dyn, SL_CW);
 }
 
-void fl_launch_spread_lm(const uint8_t* q, fl_level_geom g, uint8_t* lm_mod, uint8_t* spread_or_null, cudaStream_t s) {
+void fl_launch_spread_lm(const uint8_t* q, fl_level_geom g, uint8_t* lm_mod, uint8_t* spread_or_null, uint8_t* lm4_mod_or_null, cudaStream_t s) {
   dim3 grid((g.Wd + SL_CW - 1) / SL_CW, g.Hd);
-  k_spread_lm<<<grid, SL_THREADS, spread_smem_bytes(g.T), s>>>(q, g, lm_mod, spread_or_null);
+  k_spread_lm<<<grid, SL_THREADS, spread_smem_bytes(g.T), s>>>(q, g, lm_mod, spread_or_null, lm4_mod_or_null);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -405,7 +414,7 @@ __global__ void __launch_bounds__(256, 8) k_front_end_wave(fl_fe_wave w) {
   switch (jb.kind) {
     case FL_JOB_PYRDOWN: dev_pyrdown_bgr(jb.src, jb.W, jb.H, jb.dst, local, jb.p0 != 0); break;
     case FL_JOB_RESIZE: dev_resize_nn_half(jb.src, jb.W, jb.H, jb.dst, local); break;
-    case FL_JOB_SPREAD: dev_spread_lm_any(jb.src, jb.g, jb.dst, jb.dst2, local % jb.gx, local / jb.gx, smem_dyn, jb.p0); break;
+    case FL_JOB_SPREAD: dev_spread_lm_any(jb.src, jb.g, jb.dst, jb.dst2, jb.dst3, local % jb.gx, local / jb.gx, smem_dyn, jb.p0); break;
     case FL_JOB_PREFETCH: {
       const size_t line = (size_t)local * 256 + threadIdx.x;
       if (line * 128 < (size_t)jb.W * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(jb.src + line * 128));
@@ -472,10 +481,10 @@ void fl_fe_add_resize(fl_fe_wave* w, const uint8_t* src, int W, int H, uint8_t* 
   j.kind = FL_JOB_RESIZE; j.src = src; j.dst = dst; j.dst2 = nullptr; j.W = W; j.H = H; j.gx = 1;
   j.cta_begin = w->n_ctas; w->n_ctas += ((W / 2) * (H / 2) + 255) / 256;
 }
-void fl_fe_add_spread(fl_fe_wave* w, const uint8_t* q, fl_level_geom g, uint8_t* lm_mod, uint8_t* spread_or_null) {
+void fl_fe_add_spread(fl_fe_wave* w, const uint8_t* q, fl_level_geom g, uint8_t* lm_mod, uint8_t* spread_or_null, uint8_t* lm4_mod_or_null) {
   fl_fe_job& j = w->job[w->n_jobs++];
   j.wait_slot = -1; j.signal_slot = -1; j.wait_target = 0; j.row_base = -1; j.wait_row_base = -1; j.wait_row_shift = 0; j.wait_row_count = 0; j.wait_row_target = 0;
-  j.kind = FL_JOB_SPREAD; j.src = q; j.dst = lm_mod; j.dst2 = spread_or_null; j.g = g; j.W = g.W; j.H = g.H;
+  j.kind = FL_JOB_SPREAD; j.src = q; j.dst = lm_mod; j.dst2 = spread_or_null; j.dst3 = lm4_mod_or_null; j.g = g; j.W = g.W; j.H = g.H;
   int cw = SL_CW;                                       // small levels: narrower CTAs so that the job still fills the SMs
   while (cw > 8 && ((g.Wd + cw - 1) / cw) * g.Hd < 148) cw >>= 1;
   j.p0 = cw;

@@ -15,9 +15,12 @@
 //   * features were sorted by phase once per frame geometry (k_pack_staged).  A CTA copies its templates' feature words
 //     and per-phase prefix counts into shared memory, so the inner loop is: one broadcast LDS for the next feature word,
 //     NW + 1 LDS of linear-memory words, NW funnel shifts, NW adds;
-//   * lane g owns the NW consecutive 32-bit words [g NW, (g+1) NW) of the similarity map (NW odd, so the 32 lanes of one
-//     LDS fall into 32 different banks at any feature offset); a byte-misaligned window costs NW + 1 loads, not 2 NW: the
-//     high word of one funnel shift is the low word of the next.
+//   * the kernel reads the 4-BIT copy of the linear memories (two cells per byte, written by the spread job beside the byte
+//     version: a response is 0, 1, 2 or 4): half the shared-memory bytes per feature, which is what bounds this kernel.  Lane g
+//     owns the NW consecutive 32-bit words [g NW, (g+1) NW) of a template's similarity map, 8 cells per word (NW odd, so the 32
+//     lanes of one LDS fall into 32 different banks at any feature offset); a window that does not start on a word boundary costs
+//     NW + 1 loads, not 2 NW: the high word of one funnel shift is the low word of the next.  Nibble sums of up to 3 features
+//     (<= 12) are kept packed; every third feature of a template they are spilled into byte accumulators (even cells / odd cells).
 //
 // Semantics are those of similarity() / addSimilarities / the scan in matchClass (reference linemod/linemod.cpp:1130-1214,
 // 1322-1338, 1487-1506) including flat addressing past a row end.  Eligibility (checked on the host): every
@@ -62,7 +65,7 @@ __device__ __forceinline__ unsigned long long globaltimer() { unsigned long long
 // ------------------------------------------------------------------------------------------------
 // per-geometry packing for the staged kernel, one thread per template:
 //   gfeat[t][0..63]  coarsest-level features of all modalities sorted by phase; word = (byte offset of the 32-bit word
-//                    holding the feature's first response inside the phase buffer) << 5 | (8 x misalignment in bytes)
+//                    holding the feature's first response inside the 4-bit phase buffer) << 5 | (4 x misalignment in cells)
 //   gpre[t][0..P]    prefix counts: the features of phase p are gfeat[t][gpre[t][p] .. gpre[t][p+1])
 //   gmeta[t]         {template_positions (linemod.cpp:1155), number of features, class index, 0}
 // ------------------------------------------------------------------------------------------------
@@ -98,7 +101,7 @@ __global__ void __launch_bounds__(128) k_pack_staged(fl_tdb db, fl_level_geom g,
       const int rb = row / plan.phase_rows;
       const int ph = (m * 8 + f.label) * plan.n_rowblocks + rb;
       const uint32_t a = (uint32_t)((row - rb * plan.phase_rows) * g.cells + (f.y / g.T) * g.Wd + f.x / g.T);
-      out[cur[ph]++] = ((a & ~3u) << 5) | ((a & 3u) << 3);
+      out[cur[ph]++] = (((a >> 3) * 4u) << 5) | ((a & 7u) << 2);                        // a = cell (= nibble) index inside the phase buffer
     }
   for (int k = total; k < SS_MAXF; ++k) out[k] = 0;
   const int wf = (hdr[0].width - 1) / g.T + 1, hf = (hdr[0].height - 1) / g.T + 1;
@@ -113,12 +116,12 @@ void fl_launch_pack_staged(fl_tdb db, fl_level_geom g, fl_staged_plan plan, cuda
 // ------------------------------------------------------------------------------------------------
 #define SS_NBUF_MAX 4
 
-// One feature of one template: lane g owns the NW consecutive 32-bit words [g*NW, (g+1)*NW) of the similarity map, so
-// its window is the NW + 1 consecutive words starting at its base + the feature's word offset: NW + 1 loads (instead of
-// two per word), one funnel shift and one add per word.  NW is odd, so the 32 lanes of one load hit 32 different banks.
-// (Moving every other add to the FMA pipe as an IMAD was measured slower - loop 27.3 vs 25.9 us: IADD3 folds two adds into one issue slot.)
+// One feature of one template: lane g owns the NW consecutive 32-bit words [g*NW, (g+1)*NW) of the similarity map (8 cells per
+// word), so its window is the NW + 1 consecutive words starting at its base + the feature's word offset: NW + 1 loads (instead
+// of two per word), one funnel shift and one add per word.  NW is odd, so the 32 lanes of one load hit 32 different banks.
+// (Moving every other add to the FMA pipe as an IMAD was measured slower: IADD3 folds two adds into one issue slot.)
 template <int NW>
-__device__ __forceinline__ void accumulate_feature(const uint8_t* __restrict__ lane_base, uint32_t fw, uint32_t (&acc)[NW]) {
+__device__ __forceinline__ void accumulate_feature(const uint8_t* __restrict__ lane_base, uint32_t fw, uint32_t (&nib)[NW]) {
   const uint32_t* w = reinterpret_cast<const uint32_t*>(lane_base + (fw >> 5));
   constexpr int CH = 12;                                      // loads in flight per chunk (register budget)
   uint32_t carry = w[0];
@@ -130,18 +133,26 @@ __device__ __forceinline__ void accumulate_feature(const uint8_t* __restrict__ l
     for (int i = 0; i < CH; ++i) if (c + i < NW) v[i + 1] = w[c + i + 1];
 #pragma unroll
     for (int i = 0; i < CH; ++i)
-      if (c + i < NW) {
-        const uint32_t x = __funnelshift_r(v[i], v[i + 1], fw);   // shift = low 5 bits; four u8 lanes, no carry (sums <= 252)
-        acc[c + i] += x;
-      }
+      if (c + i < NW) nib[c + i] += __funnelshift_r(v[i], v[i + 1], fw);   // shift = low 5 bits; eight 4-bit lanes, no carry (<= 3 x 4)
     carry = v[(NW - c) < CH ? (NW - c) : CH];
+  }
+}
+// nibble sums -> byte accumulators: lo takes the even cells of each word, hi the odd ones (byte totals <= 63 x 4 = 252)
+template <int NW>
+__device__ __forceinline__ void spill_nibbles(uint32_t (&nib)[NW], uint32_t (&lo)[NW], uint32_t (&hi)[NW]) {
+#pragma unroll
+  for (int i = 0; i < NW; ++i) {
+    const uint32_t n = nib[i];
+    lo[i] += n & 0x0F0F0F0Fu;
+    hi[i] += (n >> 4) & 0x0F0F0F0Fu;
+    nib[i] = 0;
   }
 }
 
 // (Refining the candidates in this kernel's own tail was measured much slower than the separate launch - stage 143 us vs 43 + 11 us:
 // candidates cluster in the few CTAs that own a matching template while the other 140 CTAs idle - and was removed.)
 template <int NW, int TPW>
-__global__ void __launch_bounds__(1024, 1) k_similarity_staged(const __grid_constant__ fl_tdb db, fl_level_geom g, const uint8_t* __restrict__ lm_level, float threshold,
+__global__ void __launch_bounds__(1024, 1) k_similarity_staged(const __grid_constant__ fl_tdb db, fl_level_geom g, const uint8_t* __restrict__ lm4_level, float threshold,
                                                                fl_match_t* __restrict__ cand, int cap, int* __restrict__ d_count, fl_staged_plan plan) {
   extern __shared__ __align__(128) uint8_t s_dyn[];          // [n_buf x buf_bytes][tpc x int4 meta][tpc x 64 feature words + 4][tpc x pre_stride][emission staging]
   __shared__ __align__(8) uint64_t s_full[SS_NBUF_MAX], s_empty[SS_NBUF_MAX];
@@ -222,9 +233,9 @@ __global__ void __launch_bounds__(1024, 1) k_similarity_staged(const __grid_cons
         int p = q + rot; if (p >= n_phases) p -= n_phases;
         const int ml = p / plan.n_rowblocks, rb = p - ml * plan.n_rowblocks;
         const int m = ml >> 3, lab = ml & 7;
-        const uint8_t* src = lm_level + (size_t)m * g.mod_stride + (size_t)lab * g.label_stride + (size_t)rb * plan.phase_rows * g.cells;
+        const uint8_t* src = lm4_level + (((size_t)m * g.mod_stride + (size_t)lab * g.label_stride + (size_t)rb * plan.phase_rows * g.cells) >> 1);   // two cells per byte
         const int rows = min(plan.phase_rows, g.T * g.T - rb * plan.phase_rows);
-        const uint32_t bytes = (uint32_t)(((size_t)rows * g.cells + plan.halo_bytes + 15) & ~(size_t)15);
+        const uint32_t bytes = (uint32_t)((((size_t)rows * g.cells >> 1) + plan.halo_bytes + 15) & ~(size_t)15);
         mbar_expect_tx(&s_full[b], bytes);                    // the whole phase lands here, whoever fetches it
         bulk_g2s(s_buf + (size_t)b * plan.buf_bytes, src, bytes, &s_full[b]);
       }
@@ -235,7 +246,8 @@ __global__ void __launch_bounds__(1024, 1) k_similarity_staged(const __grid_cons
     bool live[TPW];
     const uint8_t* pre[TPW];
     const uint32_t* fl[TPW];
-    uint32_t acc[TPW][NW];
+    uint32_t nib[TPW][NW], lo[TPW][NW], hi[TPW][NW];
+    int pending[TPW];                                         // features added to nib[s] since the last spill (warp-uniform)
 #pragma unroll
     for (int s = 0; s < TPW; ++s) {
       const int slot = warp + s * n_cwarps;
@@ -245,8 +257,9 @@ __global__ void __launch_bounds__(1024, 1) k_similarity_staged(const __grid_cons
       pre[s] = s_pre + (in ? slot : 0) * plan.pre_stride;
       fl[s] = s_feat + (in ? slot : 0) * SS_MAXF;
       if (!in) pre[s] = nullptr;
+      pending[s] = 0;
 #pragma unroll
-      for (int i = 0; i < NW; ++i) acc[s][i] = 0;
+      for (int i = 0; i < NW; ++i) { nib[s][i] = 0; lo[s][i] = 0; hi[s][i] = 0; }
     }
     int b = 0, p = rot;
     uint32_t par = 0;
@@ -266,7 +279,8 @@ __global__ void __launch_bounds__(1024, 1) k_similarity_staged(const __grid_cons
           uint32_t fw = *fp;
           do {
             const uint32_t nx = fp[1];                        // next feature word (one past the list is a valid pad word)
-            accumulate_feature<NW>(lane_base, fw, acc[s]);
+            accumulate_feature<NW>(lane_base, fw, nib[s]);
+            if (++pending[s] == 3) { spill_nibbles<NW>(nib[s], lo[s], hi[s]); pending[s] = 0; }
             fw = nx; ++fp;
           } while (fp < fe);
         }
@@ -276,6 +290,8 @@ __global__ void __launch_bounds__(1024, 1) k_similarity_staged(const __grid_cons
       if (++b == n_buf) { b = 0; par ^= 1; }
       if (++p == n_phases) p = 0;
     }
+#pragma unroll
+    for (int s = 0; s < TPW; ++s) spill_nibbles<NW>(nib[s], lo[s], hi[s]);
     if (trace && tid == 0) trace[3] = globaltimer();
     if (trace && lane == 0) plan.trace[(size_t)plan.n_cta * 8 + 8 + ((size_t)blockIdx.x * 32 + warp) * 4] = globaltimer();       // per-warp loop end
 
@@ -300,20 +316,23 @@ __global__ void __launch_bounds__(1024, 1) k_similarity_staged(const __grid_cons
         const uint32_t k = (uint32_t)(255 - raw_thr) * 0x00010001u;
 #pragma unroll
         for (int i = 0; i < NW; ++i) {
-          const uint32_t v = acc[s][i];
-          anyw |= (((v & 0x00FF00FFu) + k) | (((v >> 8) & 0x00FF00FFu) + k)) & 0x01000100u;
+          const uint32_t v = lo[s][i], u = hi[s][i];
+          anyw |= (((v & 0x00FF00FFu) + k) | (((v >> 8) & 0x00FF00FFu) + k) | ((u & 0x00FF00FFu) + k) | (((u >> 8) & 0x00FF00FFu) + k)) & 0x01000100u;
         }
       }
       if (!__any_sync(0xffffffffu, anyw != 0)) continue;      // (cells past template_positions are filtered below)
       if (lane == 0) { while (atomicCAS(&s_emit_lock, 0, 1) != 0) __nanosleep(100); }
       __syncwarp();
 #pragma unroll
-      for (int i = 0; i < NW; ++i) s_stage[lane * NW + i] = acc[s][i];
+      for (int i = 0; i < NW; ++i) {                          // back to one byte per cell in cell order: even cells come from lo, odd ones from hi
+        s_stage[(lane * NW + i) * 2] = __byte_perm(lo[s][i], hi[s][i], 0x5140);
+        s_stage[(lane * NW + i) * 2 + 1] = __byte_perm(lo[s][i], hi[s][i], 0x7362);
+      }
       __syncwarp();
       // pass 1 (cheap, ~20 instructions per 128 cells): compact the (cell, raw) pairs above the threshold into a list.  A lone
       // warp runs dependent code at ~5 cycles per instruction, so the expensive per-candidate work (division, IEEE divide,
       // record stores) is done ONCE for up to 32 candidates in pass 2 instead of once per group of 32 cells.
-      uint32_t* s_hits = s_stage + NW * 32;
+      uint32_t* s_hits = s_stage + 2 * NW * 32;
       const int n_words_tp = (tp + 3) >> 2;
       int total = 0;
       for (int w0 = 0; w0 < n_words_tp; w0 += 32) {
@@ -373,7 +392,7 @@ __global__ void __launch_bounds__(1024, 1) k_similarity_staged(const __grid_cons
 __global__ void k_stamp(unsigned long long* p) { *p = globaltimer(); }
 
 template <int NW, int TPW>
-static int launch_staged(fl_tdb db, fl_level_geom g, const uint8_t* lm_level, float threshold, fl_match_t* cand, int cap, int* d_count,
+static int launch_staged(fl_tdb db, fl_level_geom g, const uint8_t* lm4_level, float threshold, fl_match_t* cand, int cap, int* d_count,
                          fl_staged_plan plan, cudaStream_t s) {
   auto kern = k_similarity_staged<NW, TPW>;
   {   // the opt-in belongs to the (device, function) pair; per-device table, locked (handles on several devices / host threads)
@@ -398,7 +417,7 @@ static int launch_staged(fl_tdb db, fl_level_geom g, const uint8_t* lm_level, fl
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = plan.trace ? 0 : 1;
   if (plan.trace) k_stamp<<<1, 1, 0, s>>>(plan.trace + (size_t)plan.n_cta * 8);
-  const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, db, g, lm_level, threshold, cand, cap, d_count, plan);
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, db, g, lm4_level, threshold, cand, cap, d_count, plan);
   if (plan.trace) k_stamp<<<1, 1, 0, s>>>(plan.trace + (size_t)plan.n_cta * 8 + 1);
   return e == cudaSuccess ? 0 : -1;
 }
@@ -407,22 +426,23 @@ static int launch_staged(fl_tdb db, fl_level_geom g, const uint8_t* lm_level, fl
 // template_positions (linemod.cpp:1155) over the uploaded templates: only that many cells of a similarity map are ever
 // looked at, so the per-lane accumulator count NW is sized for it rather than for the whole grid.
 bool fl_plan_staged(const fl_level_geom& g, int M, int n_templates, int max_positions, int n_sm, fl_staged_plan* plan) {
-  static const int kNW[] = {5, 7, 9, 11, 13, 15, 19, 23, 29, 37};
+  static const int kNW[] = {3, 5, 7, 9, 11, 13, 15, 19};
   fl_staged_plan p;
   memset(&p, 0, sizeof p);
   const int T2 = g.T * g.T;
   if (max_positions < 1 || n_templates < 1) return false;
+  if (g.Wd & 1) return false;                                  // the 4-bit linear memories exist for grids of even width only (two cells per byte)
   if (max_positions > g.cells) max_positions = g.cells;
-  p.n_words = (max_positions + 3) / 4;
+  p.n_words = (max_positions + 7) / 8;                         // 8 cells per 32-bit word
   const int nw_min = (p.n_words + 31) / 32;
   p.nw_template = 0;
   for (int nw : kNW) if (nw >= nw_min) { p.nw_template = nw; break; }
   if (!p.nw_template) return false;                            // accumulators would not fit the register budget
-  p.tpw = p.nw_template > 11 ? 1 : 2;                          // register budget: 64 per thread at 1,024 threads
+  p.tpw = p.nw_template > 5 ? 1 : 2;                           // register budget: 64 per thread at 1,024 threads, 3 NW accumulator words per slot
   // bytes staged past the last row of a phase: a window starts at most at the last cell of the last row and the loads run
   // unconditionally over 32 * NW + 1 words
   p.halo_bytes = 32 * p.nw_template * 4 + 16;
-  if (p.halo_bytes + 16 > FL_LM_PAD) return false;
+  if (p.halo_bytes + 16 > FL_LM_PAD / 2) return false;
   // CTAs: whole waves of the SM count, up to 31 consumer warps x TPW templates each (+ 1 producer warp)
   const int per_cta_max = 31 * p.tpw;
   int n_cta = (n_templates + per_cta_max - 1) / per_cta_max;
@@ -431,18 +451,19 @@ bool fl_plan_staged(const fl_level_geom& g, int M, int n_templates, int max_posi
   p.n_cta = (n_templates + p.tpc - 1) / p.tpc;
   const int warps = (p.tpc + p.tpw - 1) / p.tpw;
   p.block_threads = 32 * ((warps < 1 ? 1 : warps) + 1);
-  // rows per phase: the ring has n_buf (default 2) buffers that share the CTA's shared memory with the feature lists; a phase
-  // is the largest block of rows of one (modality, label) that fits a buffer; a row block must start 16-byte aligned in
-  // global memory.  (Measured at VGA, 8k templates: 2 x 78 KB / 16 phases beats 4 x 46 KB / 32 phases, 24.6 vs 29.9 us.)
-  const int nbuf = 2;
-  const size_t lists = (size_t)p.tpc * 16 + ((size_t)p.tpc * SS_MAXF + 4) * 4 + (size_t)p.tpc * (SS_MAX_PHASES + 2) + 32 + (size_t)p.nw_template * 128 * 5;   // upper bound (n_phases <= SS_MAX_PHASES)
+  // rows per phase: the ring's buffers share the CTA's shared memory with the feature lists; a phase is the largest block of rows
+  // of one (modality, label) that fits a buffer of a 2-buffer ring (fewer, larger phases beat more, smaller ones: every phase
+  // boundary is a CTA-wide hand-over); a row block must start 16-byte aligned in global memory, i.e. at a multiple of 32 cells.
+  // If whole labels fit with room to spare the ring gets up to 4 buffers (deeper prefetch).
+  const size_t stage_bytes = (size_t)p.nw_template * (256 + 1024);   // emission staging: the map as bytes (2 NW x 32 words) + one list word per cell
+  const size_t lists = (size_t)p.tpc * 16 + ((size_t)p.tpc * SS_MAXF + 4) * 4 + (size_t)p.tpc * (SS_MAX_PHASES + 2) + 32 + stage_bytes;   // upper bound (n_phases <= SS_MAX_PHASES)
   const size_t avail = 227 * 1024 - 1024;
   if (lists + 4096 > avail) return false;
-  const size_t budget = ((avail - lists) / nbuf) & ~(size_t)127;
+  const size_t budget = ((avail - lists) / 2) & ~(size_t)127;
   int pr = 0;
   for (int cand_pr = T2; cand_pr >= 1; --cand_pr) {
-    if ((size_t)cand_pr * g.cells + p.halo_bytes + 128 > budget) continue;
-    if (cand_pr != T2 && ((size_t)cand_pr * g.cells) % 16 != 0) continue;
+    if (((size_t)cand_pr * g.cells >> 1) + p.halo_bytes + 128 > budget) continue;
+    if (cand_pr != T2 && ((size_t)cand_pr * g.cells) % 32 != 0) continue;
     pr = cand_pr;
     break;
   }
@@ -451,31 +472,32 @@ bool fl_plan_staged(const fl_level_geom& g, int M, int n_templates, int max_posi
   p.n_rowblocks = (T2 + pr - 1) / pr;
   p.n_phases = M * 8 * p.n_rowblocks;
   if (p.n_phases > SS_MAX_PHASES) return false;
-  if ((size_t)pr * g.cells + p.halo_bytes >= (1u << 24)) return false;
-  p.n_buf = p.n_phases < nbuf ? p.n_phases : nbuf;
-  p.buf_bytes = (int)((((size_t)pr * g.cells + p.halo_bytes + 15) & ~(size_t)15) + 127) & ~127;
+  if (((size_t)pr * g.cells >> 1) + p.halo_bytes >= (1u << 24)) return false;
+  p.buf_bytes = (int)((((((size_t)pr * g.cells >> 1) + p.halo_bytes + 15) & ~(size_t)15) + 127) & ~(size_t)127);
   p.pre_stride = (p.n_phases + 1 + 3) & ~3;
+  const int fixed = p.tpc * 16 + (p.tpc * SS_MAXF + 4) * 4 + p.tpc * p.pre_stride + 16 + (int)stage_bytes;
+  int nbuf = 2;
+  while (nbuf < SS_NBUF_MAX && (size_t)(nbuf + 1) * p.buf_bytes + fixed <= 227 * 1024 - 512) ++nbuf;
+  p.n_buf = p.n_phases < nbuf ? p.n_phases : nbuf;
   p.smem_bytes = p.n_buf * p.buf_bytes + p.tpc * 16 + (p.tpc * SS_MAXF + 4) * 4 + p.tpc * p.pre_stride;
-  p.stage_off = (p.smem_bytes + 15) & ~15;                                 // emission staging: one similarity map (NW x 32 words)
-  p.smem_bytes = p.stage_off + p.nw_template * 128 * 5;                     // the map (NW x 32 words) + one list word per cell
+  p.stage_off = (p.smem_bytes + 15) & ~15;
+  p.smem_bytes = p.stage_off + (int)stage_bytes;
   if (p.smem_bytes > 227 * 1024 - 512) return false;
   *plan = p;
   return true;
 }
 
-int fl_launch_similarity_staged(fl_tdb db, fl_level_geom g, const uint8_t* lm_level, float threshold, fl_match_t* cand, int cap,
+int fl_launch_similarity_staged(fl_tdb db, fl_level_geom g, const uint8_t* lm4_level, float threshold, fl_match_t* cand, int cap,
                                 int* d_count, fl_staged_plan plan, cudaStream_t s) {
   switch (plan.nw_template) {
-    case 5: return launch_staged<5, 2>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
-    case 7: return launch_staged<7, 2>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
-    case 9: return launch_staged<9, 2>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
-    case 11: return launch_staged<11, 2>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
-    case 13: return launch_staged<13, 1>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
-    case 15: return launch_staged<15, 1>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
-    case 19: return launch_staged<19, 1>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
-    case 23: return launch_staged<23, 1>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
-    case 29: return launch_staged<29, 1>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
-    case 37: return launch_staged<37, 1>(db, g, lm_level, threshold, cand, cap, d_count, plan, s);
+    case 3: return launch_staged<3, 2>(db, g, lm4_level, threshold, cand, cap, d_count, plan, s);
+    case 5: return launch_staged<5, 2>(db, g, lm4_level, threshold, cand, cap, d_count, plan, s);
+    case 7: return launch_staged<7, 1>(db, g, lm4_level, threshold, cand, cap, d_count, plan, s);
+    case 9: return launch_staged<9, 1>(db, g, lm4_level, threshold, cand, cap, d_count, plan, s);
+    case 11: return launch_staged<11, 1>(db, g, lm4_level, threshold, cand, cap, d_count, plan, s);
+    case 13: return launch_staged<13, 1>(db, g, lm4_level, threshold, cand, cap, d_count, plan, s);
+    case 15: return launch_staged<15, 1>(db, g, lm4_level, threshold, cand, cap, d_count, plan, s);
+    case 19: return launch_staged<19, 1>(db, g, lm4_level, threshold, cand, cap, d_count, plan, s);
   }
   return -1;
 }

@@ -46,8 +46,44 @@ for mode in ("p2p", "nccl"):
     print("rank", rank, "mode", mode, "(effective %s)" % sm.exchange, "PASS" if ok else "FAIL", "matches/frame", [len(w) for w in want], flush=True)
     ok_all &= ok
     h.close()
+# several frames in flight per rank (sharded.ShardedPipe): device frames and host frames (page-locked and pageable), both exchanges
+pinned = [(torch.from_numpy(b).pin_memory().numpy(), torch.from_numpy(d.view(np.int16)).pin_memory().numpy().view(np.uint16)) for b, d in frames]
+for mode in ("p2p", "nccl"):
+    try:
+        pipe = sharded.ShardedPipe(lambda: fb.Handle(T, (0, 1), W, H, device=local), ts, rank, world, depth=3, capacity=1024, device=dev, exchange=mode)
+    except Exception as e:
+        print("rank", rank, "pipe mode", mode, "unavailable:", repr(e)[:300], flush=True)
+        ok_all = False
+        continue
+    torch.cuda.synchronize(); dist.barrier()
+    ok, got = True, []
+    n = 20
+    for i in range(n):
+        if pipe.in_flight() == 3:
+            got.append(pipe.collect().fetch().copy())
+        k = i % 6
+        if i % 3 == 0:
+            pipe.submit_device(d_frames[k][0].data_ptr(), d_frames[k][1].data_ptr(), W, H, 70.0)
+        elif i % 3 == 1:
+            pipe.submit_host(pinned[k][0], pinned[k][1], 70.0)
+        else:
+            pipe.submit_host(frames[k][0], frames[k][1], 70.0)
+    while pipe.in_flight():
+        got.append(pipe.collect().fetch().copy())
+    for i in range(n):
+        same = len(got[i]) == len(want[i % 6]) and bool((got[i] == want[i % 6]).all())
+        ok &= same
+        if not same:
+            print("rank", rank, "pipe mode", mode, "frame", i, "MISMATCH", len(got[i]), len(want[i % 6]), flush=True)
+    print("rank", rank, "pipe mode", mode, "(effective %s)" % pipe.exchange, "PASS" if ok else "FAIL", flush=True)
+    ok_all &= ok
+    pipe.close()
 t = torch.tensor([1 if ok_all else 0], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:
     print("MULTI-GPU PARITY", "PASS" if int(t.item()) else "FAIL", flush=True)
+code = 0 if int(t.item()) else 1
+del pinned, d_frames                                            # page-locked / device buffers go before the CUDA context does
+torch.cuda.synchronize()
 dist.destroy_process_group()
-sys.exit(0 if int(t.item()) else 1)
+sys.stdout.flush(); sys.stderr.flush()
+os._exit(code)                                                  # (interpreter teardown would free torch tensors after the context)

@@ -34,3 +34,8 @@ for c in worst:
     print("cta", c, "smid", tr[c, 5], "warp loop ends", np.round(le[c], 1).tolist())
 print("per-CTA max loop end sorted (last 10):", np.round(np.sort(le.max(1))[-10:], 1).tolist())
 print("per-CTA max loop end sorted (first 10):", np.round(np.sort(le.max(1))[:10], 1).tolist())
+rel = (tr[:, :5] - t0) / 1e3
+print("per-CTA timeline (us since first CTA start), mean / max: start %.1f/%.1f ready %.1f/%.1f first data %.1f/%.1f loop end %.1f/%.1f end %.1f/%.1f"
+      % tuple(x for k in range(5) for x in (rel[:, k].mean(), rel[:, k].max())))
+st = buf[n * 8:n * 8 + 2].astype(np.int64)
+print("stamp before launch -> first CTA start %.1f us; last CTA end -> stamp after %.1f us; whole %.1f us" % ((t0 - st[0]) / 1e3, (st[1] - tr[:, 4].max()) / 1e3, (st[1] - st[0]) / 1e3))
