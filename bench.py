@@ -556,11 +556,40 @@ def run_ours(args):
         try:                                                    # a side measurement: it must never cost the headline line
             line["recognition"] = bench_recognition(synth, frames, q, cpu=not args.no_cpu)
             # BASELINE.json's first metric, "frames/s (LINE-MOD match+ICP, 640x480)", on configs[0] (C1), host buffers in, poses out
-            line["frames_per_s_match_icp_640x480"] = {"value": line["recognition"]["frames_per_s"], "unit": "frames/s",
+            line["frames_per_s_match_icp_640x480"] = {"value": line["recognition"]["frames_per_s_stream"], "unit": "frames/s",
+                                                      "frames_in_flight": line["recognition"]["frames_in_flight"],
+                                                      "one_frame_in_flight": line["recognition"]["frames_per_s"],
                                                       "cpu_baseline": (line["recognition"].get("cpu_baseline") or {}).get("frames_per_s"),
-                                                      "workload": line["recognition"]["workload"]}
+                                                      "workload": line["recognition"]["workload"],
+                                                      "timer": "host wall clock; host frames in, poses out; `frames_in_flight` host threads, each calling the "
+                                                               "synchronous ObjRecoLmICP.Recognition mirror on its own instance"}
         except Exception as e:  # noqa: BLE001
             line["recognition"] = {"error": "%s: %s" % (type(e).__name__, e)}
+    if world == 1:
+        try:                                                    # the front end where its HBM roofline means something: 1920x1080
+            Wf, Hf, Tf = 1920, 1080, (5, 5, 5, 5)                 # the C5 geometry (T = {5, 8} does not divide 540)
+            hf = fb.Handle(Tf, (0, 1), Wf, Hf, device=local)
+            hf.upload_templates(synth.make_templates(0, Wf, Hf, Tf))
+            fb_, fd_ = synth.make_frame(Wf, Hf, 0)
+            tbf, tdf = torch.from_numpy(fb_).to(dev), torch.from_numpy(fd_.view(np.int16)).to(dev)
+            hf.profile(True)
+            acc, nfe = 0.0, 30
+            for i in range(nfe + 3):
+                flush.zero_()
+                torch.cuda.synchronize()
+                hf.match_device(tbf.data_ptr(), tdf.data_ptr(), Wf, Hf, THRESHOLD)
+                if i >= 3:
+                    acc += hf.last_stage_ms()[0]
+            hf.profile(False)
+            fe_bytes = 5 * Wf * Hf + 2 * 8 * sum((Wf >> l) * (Hf >> l) for l in range(len(Tf)))
+            fe_ms = acc / nfe
+            line["roofline_front_end_1080p"] = {"kernels": "k_front_end_wave, one launch, 1920x1080, L=4, T={5,5,5,5} (the C5 geometry)", "bound": "hbm", "algorithmic_bytes": fe_bytes,
+                                                "stage_ms": fe_ms, "achieved": fe_bytes / (fe_ms * 1e-3) / 1e9, "peak": hbm_gbs, "unit": "GB/s",
+                                                "frac": fe_bytes / (fe_ms * 1e-3) / 1e9 / hbm_gbs, "l2": "flushed before every frame",
+                                                "timer": "the library's CUDA events around the stage, mean of %d frames" % nfe}
+            hf.close()
+        except Exception as e:  # noqa: BLE001
+            line["roofline_front_end_1080p"] = {"error": "%s: %s" % (type(e).__name__, e)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -621,6 +650,19 @@ def run_pipeline(args):
     d_frames = [(torch.from_numpy(b).to(dev), torch.from_numpy(d.view(np.int16)).to(dev)) for b, d in frames]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     K = (608.0 * Wp / 640, 608.0 * Wp / 640, Wp / 2.0, Hp / 2.0)
+    # throughput mode: `depth` frames in flight per GPU, one host thread + handle + exchange buffer each (slot 0 is the handle above)
+    depth = max(1, args.in_flight)
+    slots = [(h, sm)]
+    for _ in range(depth - 1):
+        hk = fb.Handle(Tp, (0, 1), Wp, Hp, max_candidates=max(1 << 16, world * (cap + 1) + 16), device=local)
+        smk = sharded.ShardedMatcher(hk, tset, rank, world, capacity=cap, device=dev, exchange=args.exchange)
+        hk.upload_model_depths([frames[0][1]] * n_total, rects_model)
+        slots.append((hk, smk))
+    if world > 1 and any(s_[1].exchange != "p2p" for s_ in slots):
+        slots = slots[:1]                                              # the NCCL exchange is issued from one host thread only
+    depth = len(slots)
+    n_in = max(2, int(np.ceil(150e6 / (Wp * Hp * 5))))                 # inputs larger than L2: device copies of the frames at distinct addresses
+    d_inputs = [(d_frames[j % 2][0].clone(), d_frames[j % 2][1].clone()) for j in range(n_in)]
     torch.cuda.synchronize()
     stamps = np.zeros(4)
 
@@ -684,8 +726,104 @@ def run_pipeline(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, match_ms = float(t[0].item()), float(t[1].item())
+    # ---- throughput mode: `depth` frames in flight per GPU.  Host thread k of every rank owns slot k and takes frames k, k + depth,
+    # ...: front end + matchClass on the shard, peer-memory exchange, then ICP of ALL top-5 hypotheses and NMS on this rank (a
+    # hypothesis is latency-, not throughput-bound, so sharding hypotheses buys nothing once frames overlap; no second collective).
+    # The ICP of frame i (5 CTAs, milliseconds) runs beside the match stages of the following frames. ----
+    import threading
+
+    def refine_local(hk, matches, d_depth_ptr):
+        top = matches[:TOP_K]
+        n = len(top)
+        if n == 0:
+            return np.zeros(0, fb.ICP_RESULT_DTYPE), np.zeros(0, np.int32)
+        gidx = (class_first[top["class_idx"]] + top["template_id"]).astype(np.int64)
+        rr = np.stack([top["x"], top["y"], rects_model[gidx, 2], rects_model[gidx, 3]], axis=1).astype(np.int32)
+        P = tset.pose13[gidx][:, :12].reshape(n, 3, 4)
+        res = hk.detection_batch_resident_device(d_depth_ptr, Wp, Hp, K, gidx.astype(np.int32), rr, np.ascontiguousarray(P[:, :, :3]), np.ascontiguousarray(P[:, :, 3]))
+        ok = np.nonzero(res["status"] == 0)[0]
+        keep = hk.nms(res["T"][ok], res["n_points"][ok], res["dist_mean"][ok], 30.0) if len(ok) else np.zeros(0, np.int32)
+        return res, ok[keep] if len(ok) else keep
+
+    last_of = [None] * depth
+    errors = []
+
+    def worker(k, first, n_frames, host_frames=None):
+        try:
+            torch.cuda.set_device(local)
+            hk, smk = slots[k]
+            for i in range(first + k, first + n_frames, depth):
+                if host_frames is not None:
+                    pb, pd = host_frames[i % len(host_frames)]
+                    smk.match_host_async(pb, pd, THRESHOLD)
+                    smk.match_wait()
+                    ref_ptr = None
+                else:
+                    tb, td = d_inputs[i % n_in]
+                    smk.match_device(tb.data_ptr(), td.data_ptr(), Wp, Hp, THRESHOLD)
+                    ref_ptr = td.data_ptr()
+                m = smk.fetch()
+                if ref_ptr is None:                                    # the depth frame fl_match*_async left on the device
+                    top = m[:TOP_K]
+                    if len(top):
+                        gidx = (class_first[top["class_idx"]] + top["template_id"]).astype(np.int64)
+                        rr = np.stack([top["x"], top["y"], rects_model[gidx, 2], rects_model[gidx, 3]], axis=1).astype(np.int32)
+                        P = tset.pose13[gidx][:, :12].reshape(len(top), 3, 4)
+                        res = hk.detection_batch_resident(None, K, gidx.astype(np.int32), rr, np.ascontiguousarray(P[:, :, :3]), np.ascontiguousarray(P[:, :, 3]), frame_size=(Wp, Hp))
+                        ok = np.nonzero(res["status"] == 0)[0]
+                        keep = hk.nms(res["T"][ok], res["n_points"][ok], res["dist_mean"][ok], 30.0) if len(ok) else np.zeros(0, np.int32)
+                        last_of[k] = (m, res, ok[keep] if len(ok) else keep)
+                else:
+                    res, keep = refine_local(hk, m, ref_ptr)
+                    last_of[k] = (m, res, keep)
+        except Exception as e:  # noqa: BLE001
+            errors.append("slot %d: %s: %s" % (k, type(e).__name__, e))
+
+    def run_threads(first, n_frames, host_frames=None):
+        ths = [threading.Thread(target=worker, args=(k, first, n_frames, host_frames)) for k in range(depth)]
+        for t_ in ths:
+            t_.start()
+        for t_ in ths:
+            t_.join()
+        if errors:
+            raise SystemExit("bench.py: rank %d: %s" % (rank, "; ".join(errors)))
+
+    # first use of every slot from the main thread, in the same order on every rank: workspaces that grow on first use (a cudaMalloc /
+    # cudaFree synchronises the whole device; with another slot's exchange kernel waiting for the peer that would stall both ranks)
+    for k in range(depth):
+        hk, smk = slots[k]
+        for f in range(2):
+            smk.match_device(d_frames[f][0].data_ptr(), d_frames[f][1].data_ptr(), Wp, Hp, THRESHOLD)
+            refine_local(hk, smk.fetch(), d_frames[f][1].data_ptr())
+        hk.sync()
+    n_tp = max(args.steps, 4 * depth)
+    run_threads(0, 2 * depth)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches_tp0 = sum(s_[0].launch_count() for s_ in slots)
+    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    tw0 = time.perf_counter()
+    run_threads(2 * depth, n_tp)
+    torch.cuda.synchronize()
+    ev1.record(); ev1.synchronize()
+    tw1 = time.perf_counter()
+    launches_tp = sum(s_[0].launch_count() for s_ in slots) - launches_tp0
+    tp = torch.tensor([float(ev0.elapsed_time(ev1))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+    tp_ms = float(tp.item())
+    # every slot's last frame against slot 0's result for the same frame content (frames alternate between two images)
     # ---- correctness outside the timed region: merged list of frame 0 == the CPU arm's list over ALL templates ----
     _, _, got0, res0, keep0, _ = step(0, False)
+    for k in range(depth):
+        hk, smk = slots[k]
+        smk.match_device(d_frames[0][0].data_ptr(), d_frames[0][1].data_ptr(), Wp, Hp, THRESHOLD)
+        mk = smk.fetch()
+        rk, kk = refine_local(hk, mk, d_frames[0][1].data_ptr())
+        if not (np.array_equal(mk, got0) and np.array_equal(kk, keep0) and np.array_equal(rk["T"], res0["T"]) and np.array_equal(rk["R"], res0["R"])):
+            raise SystemExit("bench.py: rank %d: slot %d's frame-0 result differs from slot 0's" % (rank, k))
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import fl_oracle_py as F
     odet = F.Detector(Tp)
@@ -697,32 +835,28 @@ def run_pipeline(args):
         dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
     if int(ok_t.item()) != 1:
         raise SystemExit("bench.py: rank %d: merged match list of frame 0 (%d) differs from the CPU arm's (%d)" % (rank, len(got0), len(want0)))
-    # ---- e2e: the frame starts in pinned host memory, the poses end on the host ----
-    pin = [(torch.from_numpy(b).pin_memory(), torch.from_numpy(d.view(np.int16)).pin_memory()) for b, d in frames]
-    tb, td = d_frames[0]
-    n_e2e = min(args.steps, 50)
+    # ---- e2e: every frame starts in page-locked host memory, the poses end on the host; same threads, same frames in flight ----
+    pin = [(torch.from_numpy(b).pin_memory().numpy(), torch.from_numpy(d.view(np.int16)).pin_memory().numpy().view(np.uint16)) for b, d in frames]
+    n_e2e = n_tp
+    run_threads(0, 2 * depth, pin)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     w0 = time.perf_counter()
-    for i in range(n_e2e):
-        pb, pd = pin[i % len(pin)]
-        with torch.cuda.stream(stream):
-            tb.copy_(pb, non_blocking=True); td.copy_(pd, non_blocking=True)
-        sm.match_device(tb.data_ptr(), td.data_ptr(), Wp, Hp, THRESHOLD)
-        m = sm.fetch()
-        res, keep = refine_top(m, td.data_ptr())
+    run_threads(2 * depth, n_e2e, pin)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     tt = torch.tensor([time.perf_counter() - w0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    m = last_of[0][0] if last_of[0] is not None else got0
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    fps = args.steps / (dev_ms * 1e-3)
+    fps = n_tp / (tp_ms * 1e-3)
+    lat_fps = args.steps / (dev_ms * 1e-3)
     cpu = None
     if world == 1 and not args.no_cpu:                                   # one whole frame on one thread: the reference's own code when oracle/_ref is there
         import fl_ref_py as R
@@ -750,28 +884,37 @@ def run_pipeline(args):
             R.remove_hooks()
         cpu = {"value": 1.0 / ct, "unit": "frames/s", "cores": 1, "kind": "reference" if use_ref else "port",
                "sample": "ONE whole frame on one thread: %s over all %d templates + %d x detection()" % ("the reference's own Detector::match (oracle/_ref)" if use_ref else "the C restatement", n_total, min(TOP_K, len(ms)))}
+    cells_c = ((Wp >> (L - 1)) // Tp[-1]) * ((Hp >> (L - 1)) // Tp[-1])
     line = {"metric": "frames/s (LINE-MOD match + top-%d ICP + NMS, %dx%d, %d templates sharded over the GPUs)" % (TOP_K, Wp, Hp, n_total),
-            "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
-            "ms_per_step_p50": float(np.median(per_step)), "ms_per_step_p95": float(np.percentile(per_step, 95)), "higher_is_better": True, "scaling": "strong",
+            "value": fps, "unit": "frames/s", "n_gpus": world, "steps": n_tp, "warmup": 2 * depth, "ms_per_step": tp_ms / n_tp,
+            "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u8 (match) / f32 (ICP)", "data": "synthetic",
-            "config": {"workload": cfg["desc"], "templates_total": n_total, "templates_per_gpu": sm.n_local, "l2": "flushed between steps (256 MB write)",
-                       "evals_per_s": n_total * (Wp >> (L - 1)) // Tp[-1] * ((Hp >> (L - 1)) // Tp[-1]) * fps,
-                       "matches_frame0": int(len(got0)), "poses_frame0": int(len(keep0)), "match_list_frame0_equals_cpu_arm": True,
-                       "parallelism": ("template-sharded x%d (gid %% world), exchange: %s; ICP hypotheses k %% world, one all-gather of pose records" % (world, sm.exchange)) if world > 1 else "single GPU",
-                       "match_exchange_ms_per_step": match_ms / args.steps, "match_exchange_frames_per_s": args.steps / (match_ms * 1e-3),
-                       "limiter": "ICP of the top-%d hypotheses: a hypothesis is three serial fp32 sums per iteration over its %s paired points (exactness), i.e. milliseconds for 100..200-pixel templates; "
-                                  "it does not shrink with more GPUs once every hypothesis has its own (%.2f of %.2f ms per frame here)" % (TOP_K, "15k..40k", (dev_ms - match_ms) / args.steps, dev_ms / args.steps),
-                       "host_wall_ms_per_step_rank0": {"match_exchange_fetch": 1e3 * stamps[0] / max(stamps[2], 1), "icp_gather_nms": 1e3 * stamps[1] / max(stamps[2], 1)}},
-            "clocks": clocks, "gpu_launches": int(launches),
+            "latency_mode": {"what": "ONE frame in flight: match + exchange, then the top-%d hypotheses dealt over the ranks (k %% world) with one all-gather of the pose records, NMS; "
+                                     "L2 flushed before every frame; CUDA events around each frame, max over ranks; %d frames" % (TOP_K, args.steps),
+                             "frames_per_s": lat_fps, "ms_per_frame": dev_ms / args.steps, "ms_per_frame_p50": float(np.median(per_step)), "ms_per_frame_p95": float(np.percentile(per_step, 95)),
+                             "match_exchange_ms_per_frame": match_ms / args.steps, "icp_nms_ms_per_frame": (dev_ms - match_ms) / args.steps,
+                             "limiter": "ICP of the top-%d hypotheses: a hypothesis is three serial fp32 sums per iteration over its 15k..40k paired points (exactness), i.e. milliseconds for "
+                                        "100..200-pixel templates; it does not shrink with more GPUs once every hypothesis has its own CTA" % TOP_K,
+                             "host_wall_ms_per_frame_rank0": {"match_exchange_fetch": 1e3 * stamps[0] / max(stamps[2], 1), "icp_gather_nms": 1e3 * stamps[1] / max(stamps[2], 1)}},
+            "config": {"workload": cfg["desc"], "templates_total": n_total, "templates_per_gpu": sm.n_local, "frames_in_flight": depth,
+                       "l2": "inputs larger than L2: %d device copies of the frames at distinct addresses (%.0f MB); no flush, the stream is not interrupted" % (n_in, n_in * Wp * Hp * 5 / 1e6),
+                       "timed_region": "`steps` frames dealt over `frames_in_flight` host threads per rank (one handle, stream and exchange buffer each), between two device-wide "
+                                       "synchronisations; CUDA events on the default stream around it, max over ranks (wall clock on rank 0: %.3f s)" % (tw1 - tw0),
+                       "evals_per_s": n_total * cells_c * fps,
+                       "matches_frame0": int(len(got0)), "poses_frame0": int(len(keep0)), "match_list_frame0_equals_cpu_arm": True, "all_slots_equal_on_frame0": True,
+                       "parallelism": ("template-sharded x%d (gid %% world), exchange: %s; every rank refines the top-%d of its merged list" % (world, sm.exchange, TOP_K)) if world > 1 else "single GPU",
+                       "limiter": "throughput mode: the match stage (front end replicated on every rank + 1/N of the templates) and the host threads' per-frame calls; "
+                                  "the ICP's latency is hidden behind the following frames"},
+            "clocks": clocks, "gpu_launches": int(launches_tp),
             "e2e": {"value": n_e2e / float(tt.item()), "unit": "frames/s", "h2d_bytes_per_step": Wp * Hp * 5, "d2h_bytes_per_step": 64 + 20 * int(len(m)) + 68 * TOP_K,
-                    "timer": "host wall clock, max over ranks; frame from pinned host memory, poses to the host"},
+                    "frames_in_flight": depth, "timer": "host wall clock, max over ranks; every frame from page-locked host memory (fl_match*_async), poses to the host"},
             "roofline": None, "cpu_baseline": cpu}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def bench_recognition(synth, frames, q, cpu: bool = True, n_templates: int = 2000, top_k: int = 5, n_timed: int = 100):
+def bench_recognition(synth, frames, q, cpu: bool = True, n_templates: int = 2000, top_k: int = 5, n_timed: int = 100, in_flight: int = 8):
     """C1 (BASELINE configs[0]): the reference's whole ``Recognition`` call - PrepareInputData, match at 75 %, ICP of the top-5
     hypotheses - on a 640x480 frame with 1 object x 2,000 templates, through the product API mirror (fealess_b200.reco), host
     buffers in, poses out.  The templates are planted on frame 0, so frame 0 is the frame every timed call processes (each call
@@ -800,6 +943,36 @@ def bench_recognition(synth, frames, q, cpu: bool = True, n_templates: int = 200
         out["frames_per_s" + tag] = 1.0 / dt
         out["ms_per_frame" + tag] = 1e3 * dt
         out["poses_per_frame" + tag] = len(res)
+    # a stream of frames: `in_flight` instances of the mirror (own detector handle, stream, ICP workspace), one host thread each -
+    # the ICP of one frame (5 CTAs, latency-bound serial sums) runs beside the match stages and ICPs of the other frames
+    import threading
+    recos = [r]
+    for _ in range(in_flight - 1):
+        dk = fb.Detector()
+        dk.add_template_set(tset)
+        rk = reco.ObjRecoLmICP()
+        rk.add_detector(dk, {(None, tid): d for tid in range(n_templates)})
+        recos.append(rk)
+    bad = []
+
+    def stream(rk, n):
+        for _ in range(n):
+            rc_, res_ = rk.Recognition(b, d, K, top_k=top_k)
+            if rc_ != 0 or len(res_) != len(res0):
+                bad.append((rc_, len(res_)))
+    rc, res0 = r.Recognition(b, d, K, top_k=top_k)
+    for n_each in (5, max(n_timed // 2, 20)):                      # warm-up round, timed round
+        ths = [threading.Thread(target=stream, args=(rk, n_each)) for rk in recos]
+        t0 = time.perf_counter()
+        for t_ in ths:
+            t_.start()
+        for t_ in ths:
+            t_.join()
+        dt = time.perf_counter() - t0
+    if bad:
+        raise RuntimeError("Recognition stream: %d calls returned another result than the single-threaded call: %s" % (len(bad), bad[:3]))
+    out["frames_per_s_stream"] = in_flight * n_each / dt
+    out["frames_in_flight"] = in_flight
     out.update({"workload": "C1: Recognition (match at 75 %% + ICP of the top-%d matches) on one 640x480 RGB-D frame, 1 object x %d templates, L=2, T={5,8}" % (top_k, n_templates),
                 "icp_path": r.last_icp_path,
                 "timer": "host wall clock around ObjRecoLmICP.Recognition (H2D of the frame, 3 match launches, 2 ICP launches, poses back), mean of %d calls" % n_timed})

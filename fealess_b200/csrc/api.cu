@@ -73,6 +73,7 @@ struct fl_handle {
   // last host-input fl_match left in d_in_depth (0 x 0 = none)
   uint16_t* d_resident; std::vector<size_t> res_off; std::vector<fl_rect_t> res_rect; int res_W, res_H;
   int in_depth_W, in_depth_H;
+  int32_t* d_nms; int nms_cap;   // fl_nms workspace (hypotheses)
   // input rescale: device tables of the current (source -> destination) geometry, source-frame staging
   fl_resize_tables rz; int rz_sW, rz_sH, rz_dW, rz_dH;
   uint8_t* d_src_bgr; uint16_t* d_src_depth; size_t src_cap;
@@ -141,7 +142,7 @@ extern "C" int fl_create(const fl_params_t* params, fl_handle** out) {
   memset(&h->rz, 0, sizeof h->rz); h->rz_sW = h->rz_sH = h->rz_dW = h->rz_dH = 0;
   h->d_src_bgr = nullptr; h->d_src_depth = nullptr; h->src_cap = 0;
   memset(h->d_bgr, 0, sizeof h->d_bgr); memset(h->d_q, 0, sizeof h->d_q); memset(h->d_qm, 0, sizeof h->d_qm);
-  memset(h->d_mask, 0, sizeof h->d_mask); memset(h->d_spread, 0, sizeof h->d_spread); memset(h->d_lm, 0, sizeof h->d_lm); h->d_lm4 = nullptr;
+  memset(h->d_mask, 0, sizeof h->d_mask); memset(h->d_spread, 0, sizeof h->d_spread); memset(h->d_lm, 0, sizeof h->d_lm); h->d_lm4 = nullptr; h->d_nms = nullptr; h->nms_cap = 0;
   memset(h->used_mask, 0, sizeof h->used_mask); memset(h->stage_ms, 0, sizeof h->stage_ms); h->icp_ms = 0.f;
   *out = h;
   FL_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -215,7 +216,7 @@ extern "C" int fl_destroy(fl_handle* h) {
   cudaSetDevice(h->p.device);
   cudaStreamSynchronize(h->stream);
   free_templates(h); icp_free(h);
-  cudaFree(h->d_ref_depth); cudaFree(h->d_resident);
+  cudaFree(h->d_ref_depth); cudaFree(h->d_resident); cudaFree(h->d_nms);
   cudaFree(h->rz.xofs); cudaFree(h->rz.yofs); cudaFree(h->rz.ialpha); cudaFree(h->rz.ibeta); cudaFree(h->rz.alpha); cudaFree(h->rz.beta);
   cudaFree(h->d_src_bgr); cudaFree(h->d_src_depth);
   cudaFree(h->d_in_bgr); cudaFree(h->d_in_depth); cudaFree(h->d_geom);
@@ -1332,6 +1333,12 @@ extern "C" int fl_upload_model_depths(fl_handle* h, int32_t n_models, const uint
   h->res_off.assign(off.begin(), off.end() - 1);
   h->res_rect.assign(rect_model, rect_model + n_models);
   h->res_W = W; h->res_H = H;
+  // size the ICP workspace for the largest crop now (8 hypotheses; more grow it again): growing it later means cudaFree / cudaMalloc,
+  // which synchronise the whole device - harmless for one handle, a stall for the other frames in flight on this GPU, and with a
+  // peer-memory exchange in flight on another handle a cross-rank stall until that exchange times out
+  int max_pts = 16;
+  for (int i = 0; i < n_models; ++i) max_pts = std::max(max_pts, rect_model[i].width * rect_model[i].height);
+  TRY(icp_reserve(h, std::max(h->icp_hyp_cap, 8), max_pts));
   return FL_OK;
 }
 
@@ -1396,8 +1403,19 @@ extern "C" int fl_nms_ex(fl_handle* h, const float* t3, const int32_t* n_model_p
   if (n == 0) return 0;
   FL_CUDA(cudaSetDevice(h->p.device));
   cudaStream_t s = h->stream;
-  float* d_t = nullptr; int32_t* d_n = nullptr; float* d_d = nullptr; int32_t* d_o = nullptr;
-  TRY(dalloc(&d_t, (size_t)n * 3)); TRY(dalloc(&d_n, (size_t)n)); TRY(dalloc(&d_d, (size_t)n)); TRY(dalloc(&d_o, (size_t)2 * n + 2));
+  // handle-owned workspace, grown on demand: a cudaMalloc / cudaFree pair per call would synchronise the whole device - with other
+  // handles' frames in flight on the same GPU that serialises them, and a kernel of theirs that is waiting for a peer rank's
+  // block turns it into a cross-rank stall until the exchange times out
+  if (h->nms_cap < n) {
+    cudaFree(h->d_nms); h->d_nms = nullptr; h->nms_cap = 0;
+    const int cap = std::max(64, 2 * n);
+    TRY(dalloc(&h->d_nms, (size_t)cap * 7 + 2));
+    h->nms_cap = cap;
+  }
+  float* d_t = reinterpret_cast<float*>(h->d_nms);
+  int32_t* d_n = h->d_nms + (size_t)h->nms_cap * 3;
+  float* d_d = reinterpret_cast<float*>(h->d_nms + (size_t)h->nms_cap * 4);
+  int32_t* d_o = h->d_nms + (size_t)h->nms_cap * 5;                        // [n out_idx][n absorbed bytes (n words reserved)][count]
   FL_CUDA(cudaMemcpyAsync(d_t, t3, (size_t)n * 12, cudaMemcpyHostToDevice, s));
   FL_CUDA(cudaMemcpyAsync(d_n, n_model_pts, (size_t)n * 4, cudaMemcpyHostToDevice, s));
   FL_CUDA(cudaMemcpyAsync(d_d, icp_dist, (size_t)n * 4, cudaMemcpyHostToDevice, s));
@@ -1408,7 +1426,6 @@ extern "C" int fl_nms_ex(fl_handle* h, const float* t3, const int32_t* n_model_p
   if (absorbed) FL_CUDA(cudaMemcpyAsync(absorbed, d_o + n, (size_t)n, cudaMemcpyDeviceToHost, s));
   FL_CUDA(cudaMemcpyAsync(&cnt, d_cnt, 4, cudaMemcpyDeviceToHost, s));
   FL_CUDA(cudaStreamSynchronize(s));
-  cudaFree(d_t); cudaFree(d_n); cudaFree(d_d); cudaFree(d_o);
   return cnt;
 }
 

@@ -16,12 +16,12 @@ ts = synth.make_templates(8000, W, H, T, seed=1, quantized=q, planted_fraction=0
 h.upload_templates(ts)
 for it in range(8):
     rc, m = h.match(*frames[it % 4], 75.0)
-buf = np.zeros(200 * 72 + 8, np.uint64)
+buf = np.zeros(1024 * 136 + 8, np.uint64)
 n = fb.lib().fl_debug_get(h._h, 4, 0, 0, 0, C.c_void_p(buf.ctypes.data), C.c_size_t(buf.nbytes))
 tr = buf[:n * 8].reshape(n, 8).astype(np.int64)
-pw = buf[n * 8 + 8:n * 8 + 8 + n * 64].reshape(n, 32, 2).astype(np.int64)
+pw = buf[n * 8 + 8:n * 8 + 8 + n * 128].reshape(n, 32, 4).astype(np.int64)
 t0 = tr[:, 0].min()
-nw = 28
+nw = int((pw[:, :, 0] > 0).sum(1).max())
 le = (pw[:, :nw, 0] - t0) / 1e3
 fe = (pw[:, :nw, 1] - t0) / 1e3
 print("matches", len(m), "n_cta", n)
