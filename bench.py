@@ -258,7 +258,7 @@ def run_ours(args):
     frames, synth = make_inputs(args.templates)
     n_total = args.templates * world                                   # weak scaling: per-GPU work fixed
     cap = 2048                                                          # candidate records per rank in the all-gather block (41 KB)
-    depth = max(1, args.in_flight)
+    depth = args.in_flight if args.in_flight > 0 else 4
 
     def make_handle():
         return fb.Handle(T, (0, 1), W, H, max_candidates=max(1 << 16, world * (cap + 1) + 16), device=local)
@@ -651,7 +651,7 @@ def run_pipeline(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     K = (608.0 * Wp / 640, 608.0 * Wp / 640, Wp / 2.0, Hp / 2.0)
     # throughput mode: `depth` frames in flight per GPU, one host thread + handle + exchange buffer each (slot 0 is the handle above)
-    depth = max(1, args.in_flight)
+    depth = args.in_flight if args.in_flight > 0 else 8
     slots = [(h, sm)]
     for _ in range(depth - 1):
         hk = fb.Handle(Tp, (0, 1), Wp, Hp, max_candidates=max(1 << 16, world * (cap + 1) + 16), device=local)
@@ -1115,7 +1115,7 @@ def main():
     ap.add_argument("--templates", type=int, default=8000, help="templates per GPU")
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"], help="candidate exchange of the template-sharded path (N > 1)")
     ap.add_argument("--per-step", action="store_true", help="print the distribution of per-step device times of every rank to stderr")
-    ap.add_argument("--in-flight", type=int, default=4, help="frames in flight per GPU (1 = the synchronous Detector::match loop)")
+    ap.add_argument("--in-flight", type=int, default=0, help="frames in flight per GPU (1 = the synchronous Detector::match loop); default 4 for C2, 8 for the C4 / C5 pipelines")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-icp", action="store_true", help="skip the ICP side benchmark")
     ap.add_argument("--config", default="C2", choices=["C2", "C4", "C5"], help="C2: the headline match-only benchmark (weak scaling); C4 / C5: the "

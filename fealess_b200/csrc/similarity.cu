@@ -600,7 +600,8 @@ __device__ __forceinline__ void sort_unique_body(fl_lists L, fl_xchg X, int key_
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts[3]));
     s_hdr[0] = n_unique; s_hdr[1] = n; s_hdr[2] = 0;
     if (n_lists == 1) { s_hdr[4] = (int)(ts[0] - t_body0); s_hdr[5] = (int)(ts[1] - ts[0]); s_hdr[6] = (int)(ts[2] - ts[1]); s_hdr[7] = (int)(ts[3] - ts[2]); }   // developer timeline (ns)
-    if (X.world == 0) { s_hdr[8] = dbg_a; s_hdr[9] = dbg_b; s_hdr[10] = (int)(ts[3] - t_body0); s_hdr[11] = dbg_n; }
+    // (words 3 .. 3 + n_lists - 1 are the per-list raw counts the host checks for overflow: developer values only go where no list lives)
+    if (X.world == 0 && n_lists <= 4) { s_hdr[8] = dbg_a; s_hdr[9] = dbg_b; s_hdr[10] = (int)(ts[3] - t_body0); s_hdr[11] = dbg_n; }
     if (X.world > 0 && X.world <= 4) {                           // developer timing of the exchange (ns): push, wait, sort
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_dbg[3]));
       s_hdr[8] = (int)(t_dbg[1] - t_dbg[0]); s_hdr[9] = (int)(t_dbg[2] - t_dbg[1]); s_hdr[10] = (int)(t_dbg[3] - t_dbg[2]);

@@ -164,6 +164,20 @@ def test_group_binding_matches_oracle(tmp_path):
     rc, got = g.match(b, d, 55.0)
     assert rc == fb.FL_ERR_CAPACITY
     g.close()
+    # eight members and a threshold low enough for more than 1,024 candidates in the union: the exchange kernel hands the merge
+    # over to the stand-alone sort (8 lists), whose per-list counts must not read as an overflow
+    h = fb.Handle((5, 8), (0, 1), 640, 480, max_candidates=1 << 17)
+    h.upload_templates(ts)
+    g = fb.Group([0] * 8, exchange_capacity=4096)
+    g.upload_templates(ts)
+    sizes = []
+    for t in (thr, 30.0, 20.0, 12.0):
+        rc1, want = h.match(b, d, t, capacity=1 << 16)
+        rc, got = g.match(b, d, t)
+        assert rc1 == 0 and rc == 0 and np.array_equal(got, want), (t, rc1, rc, len(got), len(want))
+        sizes.append(len(want))
+    assert max(sizes) > 1024, sizes
+    g.close(); h.close()
 
 
 def test_compat_headers_forward_to_the_mirror():

@@ -530,8 +530,9 @@ def test_exchange_block_overflow_is_reported():
     h.close()
 
 
-def test_two_rank_gather_layout_on_one_gpu():
-    """The multi-GPU data path with the collective replaced by a concatenation: two handles hold the two template shards,
+@pytest.mark.parametrize("world", [2, 8])
+def test_gather_layout_on_one_gpu(world):
+    """The multi-GPU data path with the collective replaced by a concatenation: `world` handles hold the template shards,
     each writes its candidate block [header | records]; the blocks laid out as all_gather_into_tensor would lay them out
     are merged by fl_sort_unique_blocks_device and must equal the single-handle result and the oracle."""
     import torch
@@ -547,10 +548,10 @@ def test_two_rank_gather_layout_on_one_gpu():
     tb = torch.from_numpy(b).cuda()
     td = torch.from_numpy(d.view(np.int16)).cuda()
     cap = 512
-    blocks = torch.zeros(2 * sharded.block_ints(cap), dtype=torch.int32, device="cuda")
+    blocks = torch.zeros(world * sharded.block_ints(cap), dtype=torch.int32, device="cuda")
     handles = []
-    for r in range(2):
-        sh, gids = sharded.shard_template_set(ts, r, 2)
+    for r in range(world):
+        sh, gids = sharded.shard_template_set(ts, r, world)
         hs = fb.Handle(T, (0, 1), W, H)
         hs.upload_templates(sh)
         hs.set_template_ids(gids)
@@ -559,10 +560,10 @@ def test_two_rank_gather_layout_on_one_gpu():
         hs.match_shard_device(tb.data_ptr(), td.data_ptr(), W, H, 65.0, sharded.records_view(blk).data_ptr(), cap, blk.data_ptr())
         hs.sync()
         handles.append(hs)
-    counts = blocks.view(2, -1)[:, 0].cpu().numpy()
+    counts = blocks.view(world, -1)[:, 0].cpu().numpy()
     assert counts.sum() >= len(want) and counts.max() <= cap
-    handles[0].sort_unique_blocks_device(blocks.data_ptr(), 2, cap)
-    got = handles[0].match_fetch()
+    handles[0].sort_unique_blocks_device(blocks.data_ptr(), world, cap)
+    got = handles[0].match_fetch()                     # (raises if any per-list count reads as an overflow)
     assert np.array_equal(got, want)
     for hs in handles:
         hs.close()
