@@ -661,6 +661,12 @@ def run_pipeline(args):
     if world > 1 and any(s_[1].exchange != "p2p" for s_ in slots):
         slots = slots[:1]                                              # the NCCL exchange is issued from one host thread only
     depth = len(slots)
+    # more waiting host threads than cores (8 ranks x 8 frames in flight on a 16-core box): sleep on the GPU's interrupt instead of spinning
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    blocking = depth * int(os.environ.get("LOCAL_WORLD_SIZE", world)) > cores
+    if blocking:
+        for hk, _ in slots:
+            hk.set_blocking_wait(True)
     n_in = max(2, int(np.ceil(150e6 / (Wp * Hp * 5))))                 # inputs larger than L2: device copies of the frames at distinct addresses
     d_inputs = [(d_frames[j % 2][0].clone(), d_frames[j % 2][1].clone()) for j in range(n_in)]
     torch.cuda.synchronize()
@@ -897,6 +903,7 @@ def run_pipeline(args):
                                         "100..200-pixel templates; it does not shrink with more GPUs once every hypothesis has its own CTA" % TOP_K,
                              "host_wall_ms_per_frame_rank0": {"match_exchange_fetch": 1e3 * stamps[0] / max(stamps[2], 1), "icp_gather_nms": 1e3 * stamps[1] / max(stamps[2], 1)}},
             "config": {"workload": cfg["desc"], "templates_total": n_total, "templates_per_gpu": sm.n_local, "frames_in_flight": depth,
+                       "host_wait": "blocking (cudaEventBlockingSync): %d waiting threads on %d cores" % (depth * int(os.environ.get("LOCAL_WORLD_SIZE", world)), cores) if blocking else "spinning",
                        "l2": "inputs larger than L2: %d device copies of the frames at distinct addresses (%.0f MB); no flush, the stream is not interrupted" % (n_in, n_in * Wp * Hp * 5 / 1e6),
                        "timed_region": "`steps` frames dealt over `frames_in_flight` host threads per rank (one handle, stream and exchange buffer each), between two device-wide "
                                        "synchronisations; CUDA events on the default stream around it, max over ranks (wall clock on rank 0: %.3f s)" % (tw1 - tw0),

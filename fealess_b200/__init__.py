@@ -47,7 +47,7 @@ EXPORTED_SYMBOLS = [
     "fl_detection_batch", "fl_upload_model_depths", "fl_detection_batch_resident", "fl_detection_batch_resident_device", "fl_detection", "fl_nms", "fl_nms_ex", "fl_debug_option", "fl_debug_keep_spread", "fl_debug_force_baseline", "fl_debug_uses_staged", "fl_debug_get", "fl_debug_icp_trace", "fl_launch_count",
     "fl_profile", "fl_last_stage_ms", "fl_last_icp_ms",
     "fl_group_create", "fl_group_destroy", "fl_group_size", "fl_group_handle", "fl_group_upload_templates", "fl_group_match",
-    "fl_match_async", "fl_match_shard_exchange_async", "fl_pipe_create", "fl_pipe_destroy", "fl_pipe_depth", "fl_pipe_in_flight", "fl_pipe_handle", "fl_pipe_upload_templates",
+    "fl_match_async", "fl_set_blocking_wait", "fl_match_shard_exchange_async", "fl_pipe_create", "fl_pipe_destroy", "fl_pipe_depth", "fl_pipe_in_flight", "fl_pipe_handle", "fl_pipe_upload_templates",
     "fl_pipe_submit", "fl_pipe_collect", "fl_pipe_match_batch",
 ]
 
@@ -265,6 +265,10 @@ class Handle:
 
     def match_wait(self) -> None:
         _check(lib().fl_match_wait(self._h), "fl_match_wait")
+
+    def set_blocking_wait(self, enable: bool = True) -> None:
+        """fl_set_blocking_wait: sleep instead of spinning while waiting for the GPU (many host threads on few cores)."""
+        _check(lib().fl_set_blocking_wait(self._h, int(enable)), "fl_set_blocking_wait")
 
     def match_fetch(self, capacity: int = 1 << 16, allow_truncated: bool = False) -> np.ndarray:
         """The merged match list of the last frame.  An overflow (a candidate buffer, an exchange block or ``capacity`` too small)

@@ -74,11 +74,16 @@ struct fl_handle {
   uint16_t* d_resident; std::vector<size_t> res_off; std::vector<fl_rect_t> res_rect; int res_W, res_H;
   int in_depth_W, in_depth_H;
   int32_t* d_nms; int nms_cap;   // fl_nms workspace (hypotheses)
+  bool blocking_wait; cudaEvent_t ev_block;   // fl_set_blocking_wait
   // input rescale: device tables of the current (source -> destination) geometry, source-frame staging
   fl_resize_tables rz; int rz_sW, rz_sH, rz_dW, rz_dH;
   uint8_t* d_src_bgr; uint16_t* d_src_depth; size_t src_cap;
 };
 
+// The host waits for the handle's stream.  Default: cudaStreamSynchronize (the runtime spins - lowest latency, one busy core per
+// waiting thread).  fl_set_blocking_wait(h, 1): an event created with cudaEventBlockingSync, so the thread sleeps until the GPU's
+// interrupt - for hosts that keep more frames in flight (threads) than they have cores to spin on.
+static cudaError_t wait_stream(fl_handle* h);
 template <typename T> static int dalloc(T** p, size_t n) {
   *p = nullptr;
   if (n == 0) n = 1;
@@ -142,7 +147,7 @@ extern "C" int fl_create(const fl_params_t* params, fl_handle** out) {
   memset(&h->rz, 0, sizeof h->rz); h->rz_sW = h->rz_sH = h->rz_dW = h->rz_dH = 0;
   h->d_src_bgr = nullptr; h->d_src_depth = nullptr; h->src_cap = 0;
   memset(h->d_bgr, 0, sizeof h->d_bgr); memset(h->d_q, 0, sizeof h->d_q); memset(h->d_qm, 0, sizeof h->d_qm);
-  memset(h->d_mask, 0, sizeof h->d_mask); memset(h->d_spread, 0, sizeof h->d_spread); memset(h->d_lm, 0, sizeof h->d_lm); h->d_lm4 = nullptr; h->d_nms = nullptr; h->nms_cap = 0;
+  memset(h->d_mask, 0, sizeof h->d_mask); memset(h->d_spread, 0, sizeof h->d_spread); memset(h->d_lm, 0, sizeof h->d_lm); h->d_lm4 = nullptr; h->d_nms = nullptr; h->nms_cap = 0; h->blocking_wait = false; h->ev_block = nullptr;
   memset(h->used_mask, 0, sizeof h->used_mask); memset(h->stage_ms, 0, sizeof h->stage_ms); h->icp_ms = 0.f;
   *out = h;
   FL_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -216,7 +221,7 @@ extern "C" int fl_destroy(fl_handle* h) {
   cudaSetDevice(h->p.device);
   cudaStreamSynchronize(h->stream);
   free_templates(h); icp_free(h);
-  cudaFree(h->d_ref_depth); cudaFree(h->d_resident); cudaFree(h->d_nms);
+  cudaFree(h->d_ref_depth); cudaFree(h->d_resident); cudaFree(h->d_nms); if (h->ev_block) cudaEventDestroy(h->ev_block);
   cudaFree(h->rz.xofs); cudaFree(h->rz.yofs); cudaFree(h->rz.ialpha); cudaFree(h->rz.ibeta); cudaFree(h->rz.alpha); cudaFree(h->rz.beta);
   cudaFree(h->d_src_bgr); cudaFree(h->d_src_depth);
   cudaFree(h->d_in_bgr); cudaFree(h->d_in_depth); cudaFree(h->d_geom);
@@ -233,6 +238,18 @@ extern "C" int fl_destroy(fl_handle* h) {
   return FL_OK;
 }
 
+static cudaError_t wait_stream(fl_handle* h) {
+  if (!h->blocking_wait) return cudaStreamSynchronize(h->stream);
+  cudaError_t e = cudaEventRecord(h->ev_block, h->stream);
+  return e == cudaSuccess ? cudaEventSynchronize(h->ev_block) : e;
+}
+extern "C" int fl_set_blocking_wait(fl_handle* h, int enable) {
+  if (!h) return FL_ERR_ARG;
+  FL_CUDA(cudaSetDevice(h->p.device));
+  if (enable && !h->ev_block) FL_CUDA(cudaEventCreateWithFlags(&h->ev_block, cudaEventBlockingSync | cudaEventDisableTiming));
+  h->blocking_wait = enable != 0;
+  return FL_OK;
+}
 extern "C" int fl_sync(fl_handle* h) { if (!h) return FL_ERR_ARG; FL_CUDA(cudaStreamSynchronize(h->stream)); return FL_OK; }
 extern "C" void* fl_stream(fl_handle* h) { return h ? (void*)h->stream : nullptr; }
 extern "C" int64_t fl_launch_count(fl_handle* h) { return h ? h->launches : 0; }
@@ -725,7 +742,7 @@ static int sort_finish(fl_handle* h) {
   const fl_lists L = h->pend_lists;
   fl_match_t* d_out = h->pend_out; const int out_cap = h->pend_out_cap; int* d_out_count = h->pend_out_count; const bool own = h->pend_own;
   const int n_lists = L.n_lists, list_cap = L.list_cap;
-  FL_CUDA(cudaStreamSynchronize(s));
+  FL_CUDA(wait_stream(h));
   h->overflow = false;
   int n_upper = 0;
   for (int i = 0; i < std::min(n_lists, 11); ++i) { if (h->h_small[3 + i] > list_cap) h->overflow = true; n_upper += std::min(std::max(h->h_small[3 + i], 0), list_cap); }
@@ -751,7 +768,7 @@ static int sort_finish(fl_handle* h) {
     FL_CUDA(cudaMemcpyAsync(h->h_small, d_out_count, sizeof(int), cudaMemcpyDeviceToHost, s));
     if (own) FL_CUDA(cudaMemcpyAsync(h->h_first, d_out, sizeof(fl_match_t) * (size_t)std::min(FETCH_FIRST, out_cap), cudaMemcpyDeviceToHost, s));
     if (h->profile) cudaEventRecord(h->ev[4], s);
-    FL_CUDA(cudaStreamSynchronize(s));
+    FL_CUDA(wait_stream(h));
   }
   if (h->profile) for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&h->stage_ms[i], h->ev[i], h->ev[i + 1]);
   FL_CUDA(cudaGetLastError());
@@ -831,7 +848,7 @@ extern "C" int fl_match_fetch(fl_handle* h, fl_match_t* out, int32_t capacity, i
   if (nfirst > 0) memcpy(out, h->h_first, sizeof(fl_match_t) * nfirst);
   if (ncopy > nfirst) {
     FL_CUDA(cudaMemcpyAsync(out + nfirst, h->d_out + nfirst, sizeof(fl_match_t) * (size_t)(ncopy - nfirst), cudaMemcpyDeviceToHost, h->stream));
-    FL_CUDA(cudaStreamSynchronize(h->stream));
+    FL_CUDA(wait_stream(h));
   }
   // overflow: matchClass produced more candidates than the device buffer holds (the list is then incomplete)
   return (n > capacity || n > h->p.max_candidates || h->overflow) ? FL_ERR_CAPACITY : FL_OK;
@@ -1262,7 +1279,7 @@ static int icp_run_batch(fl_handle* h, const uint16_t* d_ref, int W, int H, fl_i
     h->launches += nl; }
   if (h->profile) cudaEventRecord(h->ev[1], s);
   FL_CUDA(cudaMemcpyAsync(h->h_results, h->d_results, sizeof(fl_icp_result_t) * (size_t)n, cudaMemcpyDeviceToHost, s));
-  FL_CUDA(cudaStreamSynchronize(s));
+  FL_CUDA(wait_stream(h));
   if (h->profile) cudaEventElapsedTime(&h->icp_ms, h->ev[0], h->ev[1]);
   FL_CUDA(cudaGetLastError());
   memcpy(out, h->h_results, sizeof(fl_icp_result_t) * (size_t)n);
@@ -1407,7 +1424,7 @@ extern "C" int fl_nms_ex(fl_handle* h, const float* t3, const int32_t* n_model_p
   // handles' frames in flight on the same GPU that serialises them, and a kernel of theirs that is waiting for a peer rank's
   // block turns it into a cross-rank stall until the exchange times out
   if (h->nms_cap < n) {
-    cudaFree(h->d_nms); h->d_nms = nullptr; h->nms_cap = 0;
+    cudaFree(h->d_nms); h->d_nms = nullptr; h->nms_cap = 0; h->blocking_wait = false; h->ev_block = nullptr;
     const int cap = std::max(64, 2 * n);
     TRY(dalloc(&h->d_nms, (size_t)cap * 7 + 2));
     h->nms_cap = cap;
@@ -1425,7 +1442,7 @@ extern "C" int fl_nms_ex(fl_handle* h, const float* t3, const int32_t* n_model_p
   FL_CUDA(cudaMemcpyAsync(out_idx, d_o, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
   if (absorbed) FL_CUDA(cudaMemcpyAsync(absorbed, d_o + n, (size_t)n, cudaMemcpyDeviceToHost, s));
   FL_CUDA(cudaMemcpyAsync(&cnt, d_cnt, 4, cudaMemcpyDeviceToHost, s));
-  FL_CUDA(cudaStreamSynchronize(s));
+  FL_CUDA(wait_stream(h));
   return cnt;
 }
 

@@ -163,9 +163,13 @@ class ShardedMatcher:
         torch = self._torch
         if getattr(self, "_d_in", None) is None or self._d_in[0].numel() != H * W * 3:
             self._d_in = (torch.empty(H * W * 3, dtype=torch.uint8, device=self.block.device), torch.empty(H * W, dtype=torch.int16, device=self.block.device))
-        with torch.cuda.stream(self.stream):
-            self._d_in[0].copy_(torch.from_numpy(bgr).view(-1), non_blocking=True)
-            self._d_in[1].copy_(torch.from_numpy(depth.view(np.int16)).view(-1), non_blocking=True)
+        # the copies go on torch's current stream and the handle's stream waits for them: torch remembers on which stream a
+        # page-locked block was used and records an event there when the block is freed - that must not be a handle's stream,
+        # which may be gone by then
+        cur = torch.cuda.current_stream()
+        self._d_in[0].copy_(torch.from_numpy(bgr).view(-1), non_blocking=True)
+        self._d_in[1].copy_(torch.from_numpy(depth.view(np.int16)).view(-1), non_blocking=True)
+        self.stream.wait_stream(cur)
         return self.match_device_async(self._d_in[0].data_ptr(), self._d_in[1].data_ptr(), W, H, threshold)
 
     def match_wait(self) -> None:
@@ -188,6 +192,22 @@ class ShardedMatcher:
 
     def fetch(self) -> np.ndarray:
         return self.h.match_fetch()
+
+    def close(self) -> None:
+        """Releases the matcher's device tensors, THEN the handle: torch's allocator notes on which streams a tensor was used and
+        records an event there when the tensor is freed - the handle's stream must still exist at that point."""
+        if self.h is None:
+            return
+        self._torch.cuda.synchronize()
+        self.block = self.gathered = None
+        self._d_in = None
+        self._host_frame = None
+        self._xhdl = None
+        self._xbuf = None
+        self.stream = None
+        self._torch.cuda.synchronize()
+        self.h.close()
+        self.h = None
 
 
 class ShardedPipe:
@@ -240,7 +260,7 @@ class ShardedPipe:
 
     def close(self) -> None:
         for s in self.slots:
-            s.h.close()
+            s.close()
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -138,6 +138,10 @@ int fl_match_fetch(fl_handle* h, fl_match_t* out, int32_t capacity, int32_t* cou
 int fl_match_device_async(fl_handle* h, const void* d_bgr, const void* d_depth, int32_t W, int32_t H,
                           const void* const* d_masks, float threshold, const int32_t* class_filter, int32_t n_filter);
 int fl_match_wait(fl_handle* h);
+/* How the host waits for this handle's frames (fl_match_wait, fl_match_fetch, fl_detection_batch*, fl_nms): by default the CUDA
+ * runtime spins (lowest latency, one busy core per waiting thread); enable = 1 makes the calling thread sleep until the GPU's
+ * interrupt (cudaEventBlockingSync) - for hosts that keep more frames in flight, one thread each, than they have cores. */
+int fl_set_blocking_wait(fl_handle* h, int enable);
 /* enqueue-only half of fl_match (host buffers): the upload and the frame's kernels go on the handle's stream; finish with
  * fl_match_wait + fl_match_fetch.  Page-locked caller buffers are read by DMA and must stay valid until fl_match_wait returns;
  * pageable ones are copied before this returns. */

@@ -94,3 +94,18 @@ def test_state_errors_and_batch(stream_case):
             p.submit_device(dev[k % 5][0].data_ptr(), dev[k % 5][1].data_ptr(), W, H, 70.0)
     assert np.array_equal(p.collect()[1], want[6 % 5]) and np.array_equal(p.collect()[1], want[7 % 5])
     p.close()
+
+
+def test_blocking_wait_gives_the_same_lists(stream_case):
+    """fl_set_blocking_wait: the host thread sleeps on a blocking event instead of spinning; nothing else changes."""
+    frames, ts, want = stream_case
+    h = fb.Handle(T, (0, 1), W, H)
+    h.upload_templates(ts)
+    h.set_blocking_wait(True)
+    for i in (0, 3, 1):
+        rc, got = h.match(*frames[i], 70.0)
+        assert rc == 0 and np.array_equal(got, want[i])
+    h.set_blocking_wait(False)
+    rc, got = h.match(*frames[2], 70.0)
+    assert rc == 0 and np.array_equal(got, want[2])
+    h.close()

@@ -45,7 +45,7 @@ for mode in ("p2p", "nccl"):
                 print("rank", rank, "mode", mode, "frame", i, "MISMATCH", len(got), len(want[i]), flush=True)
     print("rank", rank, "mode", mode, "(effective %s)" % sm.exchange, "PASS" if ok else "FAIL", "matches/frame", [len(w) for w in want], flush=True)
     ok_all &= ok
-    h.close()
+    sm.close()
 # several frames in flight per rank (sharded.ShardedPipe): device frames and host frames (page-locked and pageable), both exchanges
 pinned = [(torch.from_numpy(b).pin_memory().numpy(), torch.from_numpy(d.view(np.int16)).pin_memory().numpy().view(np.uint16)) for b, d in frames]
 for mode in ("p2p", "nccl"):
@@ -82,8 +82,7 @@ t = torch.tensor([1 if ok_all else 0], device=dev); dist.all_reduce(t, op=dist.R
 if rank == 0:
     print("MULTI-GPU PARITY", "PASS" if int(t.item()) else "FAIL", flush=True)
 code = 0 if int(t.item()) else 1
-del pinned, d_frames                                            # page-locked / device buffers go before the CUDA context does
 torch.cuda.synchronize()
 dist.destroy_process_group()
 sys.stdout.flush(); sys.stderr.flush()
-os._exit(code)                                                  # (interpreter teardown would free torch tensors after the context)
+os._exit(code)                                                  # (no interpreter teardown: it frees torch tensors in arbitrary order)
