@@ -579,7 +579,7 @@ def run_ours(args):
                 torch.cuda.synchronize()
                 hf.match_device(tbf.data_ptr(), tdf.data_ptr(), Wf, Hf, THRESHOLD)
                 if i >= 3:
-                    acc += hf.last_stage_ms()[0]
+                    acc += float(hf.last_stage_ms()[0])
             hf.profile(False)
             fe_bytes = 5 * Wf * Hf + 2 * 8 * sum((Wf >> l) * (Hf >> l) for l in range(len(Tf)))
             fe_ms = acc / nfe

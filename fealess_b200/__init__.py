@@ -310,7 +310,7 @@ class Handle:
     def match_shard_exchange_device_async(self, d_bgr: int, d_depth: int, W: int, H: int, threshold: float, rank: int, world: int,
                                           peer_buffers: Sequence[int], capacity: int, d_local_block: int, epoch: int, class_filter=None) -> None:
         cf = None if not class_filter else np.ascontiguousarray(class_filter, np.int32)
-        arr = (C.c_void_p * world)(*[int(p) for p in peer_buffers])
+        arr = peer_buffers if isinstance(peer_buffers, C.Array) else (C.c_void_p * world)(*[int(p) for p in peer_buffers])
         _check(lib().fl_match_shard_exchange_device_async(self._h, C.c_void_p(d_bgr), C.c_void_p(d_depth), W, H, C.c_float(threshold), _p(cf),
                                                           0 if cf is None else int(cf.size), rank, world, arr, capacity, C.c_void_p(d_local_block),
                                                           C.c_uint32(epoch)), "fl_match_shard_exchange_device_async")
@@ -321,7 +321,7 @@ class Handle:
         to stay alive until ``match_wait``)."""
         H, W = (depth if depth is not None else bgr).shape[:2]
         cf = None if not class_filter else np.ascontiguousarray(class_filter, np.int32)
-        arr = (C.c_void_p * world)(*[int(p) for p in peer_buffers])
+        arr = peer_buffers if isinstance(peer_buffers, C.Array) else (C.c_void_p * world)(*[int(p) for p in peer_buffers])
         _check(lib().fl_match_shard_exchange_async(self._h, _p(bgr), C.c_size_t(W * 3), _p(depth), C.c_size_t(W * 2), W, H, C.c_float(threshold), _p(cf),
                                                    0 if cf is None else int(cf.size), rank, world, arr, capacity, C.c_void_p(d_local_block),
                                                    C.c_uint32(epoch)), "fl_match_shard_exchange_async")

@@ -116,7 +116,9 @@ class ShardedMatcher:
                 self._xbuf.zero_()
                 torch.cuda.synchronize()
                 dist.barrier()
-                self._peers = [int(p) for p in self._xhdl.buffer_ptrs]
+                import ctypes
+                self._peers = (ctypes.c_void_p * world)(*[int(p) for p in self._xhdl.buffer_ptrs])   # built once: the per-frame calls pass it as is
+                self._block_ptr = self.block.data_ptr()
                 self.exchange = "p2p"
             except Exception as e:  # noqa: BLE001  (no peer mapping available: fall back to the collective)
                 self.exchange_error = repr(e)
@@ -139,7 +141,7 @@ class ShardedMatcher:
             # front end + matchClass, then ONE launch: refinement, push to the peers, wait, sort of the union
             self.epoch += 1
             self.h.match_shard_exchange_device_async(d_bgr, d_depth, W, H, threshold, self.rank, self.world, self._peers, self.cap,
-                                                     self.block.data_ptr(), self.epoch)
+                                                     self._block_ptr, self.epoch)
             return True
         recs = records_view(self.block)
         # the count lives in the header record of the block, so the candidates + count travel together
@@ -158,7 +160,7 @@ class ShardedMatcher:
         if self.exchange == "p2p":
             self.epoch += 1
             self._host_frame = (bgr, depth)                     # page-locked buffers are read by DMA until match_wait
-            self.h.match_shard_exchange_async(bgr, depth, threshold, self.rank, self.world, self._peers, self.cap, self.block.data_ptr(), self.epoch)
+            self.h.match_shard_exchange_async(bgr, depth, threshold, self.rank, self.world, self._peers, self.cap, self._block_ptr, self.epoch)
             return True
         torch = self._torch
         if getattr(self, "_d_in", None) is None or self._d_in[0].numel() != H * W * 3:
