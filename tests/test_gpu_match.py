@@ -567,3 +567,14 @@ def test_gather_layout_on_one_gpu(world):
     assert np.array_equal(got, want)
     for hs in handles:
         hs.close()
+
+
+def test_sanitizer_case_passes_without_the_tool():
+    """tools/racecheck_case.py is the pass compute-sanitizer is pointed at (tools/gpu_check.sh); it checks itself against the oracle,
+    so it also has to pass on its own."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "racecheck_case.py")], cwd=root, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       text=True, timeout=600)
+    assert r.returncode == 0 and "RACECHECK CASE PASS" in r.stdout, r.stdout[-2000:]
