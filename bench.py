@@ -448,6 +448,14 @@ def run_ours(args):
         for i in range(n_sync):
             rc, m1 = h.match(pinned[i % N_FRAMES][0], pinned[i % N_FRAMES][1], THRESHOLD, capacity=4096)
         ts1 = time.perf_counter()
+        # the batch entry (fl_pipe_match_batch: B frames in, B lists out, one call): B = 64
+        batch = [pinned[i % N_FRAMES] for i in range(64)]
+        rcb, lists_b = cpipe.match_batch(batch, THRESHOLD)
+        tb0 = time.perf_counter()
+        rcb, lists_b = cpipe.match_batch(batch, THRESHOLD)
+        tb1 = time.perf_counter()
+        if rcb != 0 or any(len(lists_b[k]) != len(lists_b[k % N_FRAMES]) for k in range(64)):
+            raise SystemExit("bench.py: fl_pipe_match_batch returned status %d or lists that differ between repeats of a frame" % rcb)
         host_stream(8, frames)
         n_page = min(args.steps, 200)
         tp0 = time.perf_counter()
@@ -458,7 +466,8 @@ def run_ours(args):
                "d2h_bytes_per_step": 64 + len(m) * 20, "frames_per_s": args.steps / (t1 - t0), "frames_in_flight": depth,
                "timer": "host wall clock around a stream of fl_pipe_submit / fl_pipe_collect calls (C ABI; host frames in page-locked memory, "
                         "H2D and the read-back of every frame's match list inside)",
-               "frames_per_s_one_frame_in_flight": n_sync / (ts1 - ts0), "frames_per_s_pageable_input": n_page / (tp1 - tp0)}
+               "frames_per_s_one_frame_in_flight": n_sync / (ts1 - ts0), "frames_per_s_pageable_input": n_page / (tp1 - tp0),
+               "frames_per_s_batch64": 64 / (tb1 - tb0), "latency_ms_one_frame": 1e3 * (ts1 - ts0) / n_sync}
     else:
         def host_stream(n):
             m = None
