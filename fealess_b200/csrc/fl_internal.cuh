@@ -120,7 +120,8 @@ __host__ __device__ inline int fl_rrec_bytes(int M) { return (32 + M * 64 * 8 + 
 void fl_launch_pack_refine_records(fl_tdb db, const fl_level_geom* d_geom, cudaStream_t s);
 // plan of the shared-memory-staged global similarity kernel (similarity_staged.cu) for one frame geometry
 struct fl_staged_plan {
-  int phase_rows, n_rowblocks, n_phases;   // a phase = phase_rows linear-memory rows of one (modality, label)
+  int phase_rows, n_rowblocks, n_phases;   // a phase = phase_rows linear-memory rows of one (modality, label) ...
+  int labels_per_phase;                    // ... or, when whole labels fit, this many consecutive labels of one modality (1, 2 or 4)
   int halo_bytes, buf_bytes, n_buf;        // bytes staged past the last row; size and number of the smem ring buffers
   int n_words, nw_template, tpw;           // 32-bit words per similarity map; template parameters of the instantiation used
   int tpc, n_cta, block_threads;           // templates per CTA, grid, block

@@ -16,11 +16,16 @@
 //     and per-phase prefix counts into shared memory, so the inner loop is: one broadcast LDS for the next feature word,
 //     NW + 1 LDS of linear-memory words, NW funnel shifts, NW adds;
 //   * the kernel reads the 4-BIT copy of the linear memories (two cells per byte, written by the spread job beside the byte
-//     version: a response is 0, 1, 2 or 4): half the shared-memory bytes per feature, which is what bounds this kernel.  Lane g
-//     owns the NW consecutive 32-bit words [g NW, (g+1) NW) of a template's similarity map, 8 cells per word (NW odd, so the 32
-//     lanes of one LDS fall into 32 different banks at any feature offset); a window that does not start on a word boundary costs
-//     NW + 1 loads, not 2 NW: the high word of one funnel shift is the low word of the next.  Nibble sums of up to 3 features
-//     (<= 12) are kept packed; every third feature of a template they are spilled into byte accumulators (even cells / odd cells).
+//     version: a response is 0, 1, 2 or 4): half the shared-memory bytes per feature.  Lane g owns the NW consecutive 32-bit words
+//     [g NW, (g+1) NW) of a template's similarity map, 8 cells per word (NW odd, so the 32 lanes of one LDS fall into 32 different
+//     banks at any feature offset); a window that does not start on a word boundary costs NW + 1 loads, not 2 NW: the high word of
+//     one funnel shift is the low word of the next;
+//   * a phase's features are taken THREE at a time: their shifted words are added as packed nibbles with one three-input add (3 x 4
+//     cannot carry) and the sum is split into byte accumulators (even cells / odd cells) on the spot - no nibble state is carried, no
+//     counter, no data-dependent spill branch.  When whole labels fit a buffer, 2 (or 4) consecutive labels of a modality form one
+//     phase: half the per-phase bookkeeping and longer runs, i.e. more triples and fewer remainders.  Measured at C2 (in-kernel
+//     timeline): loop 26.0 us with one feature at a time and nibble sums spilled every third, 22.9 us with triples, 18.5 us with
+//     triples and label pairs (8 phases instead of 16).
 //
 // Semantics are those of similarity() / addSimilarities / the scan in matchClass (reference linemod/linemod.cpp:1130-1214,
 // 1322-1338, 1487-1506) including flat addressing past a row end.  Eligibility (checked on the host): every
@@ -86,7 +91,7 @@ __global__ void __launch_bounds__(128) k_pack_staged(fl_tdb db, fl_level_geom g,
       const fl_feature_t f = db.feat[hdr[m].feature_begin + k];
       if (f.x < 0 || f.y < 0 || f.x >= g.W || f.y >= g.H) continue;                     // linemod.cpp:1179
       const int row = (f.y % g.T) * g.T + (f.x % g.T);
-      const int ph = (m * 8 + f.label) * plan.n_rowblocks + row / plan.phase_rows;
+      const int ph = ((m * 8 + f.label) / plan.labels_per_phase) * plan.n_rowblocks + row / plan.phase_rows;
       ++cur[ph + 1];
     }
   }
@@ -99,8 +104,9 @@ __global__ void __launch_bounds__(128) k_pack_staged(fl_tdb db, fl_level_geom g,
       if (f.x < 0 || f.y < 0 || f.x >= g.W || f.y >= g.H) continue;
       const int row = (f.y % g.T) * g.T + (f.x % g.T);
       const int rb = row / plan.phase_rows;
-      const int ph = (m * 8 + f.label) * plan.n_rowblocks + rb;
-      const uint32_t a = (uint32_t)((row - rb * plan.phase_rows) * g.cells + (f.y / g.T) * g.Wd + f.x / g.T);
+      const int ph = ((m * 8 + f.label) / plan.labels_per_phase) * plan.n_rowblocks + rb;
+      // cell (= nibble) index inside the phase buffer; a later label of a label group starts label_stride cells further on
+      const uint32_t a = (uint32_t)((f.label % plan.labels_per_phase) * g.label_stride + (row - rb * plan.phase_rows) * g.cells + (f.y / g.T) * g.Wd + f.x / g.T);
       out[cur[ph]++] = (((a >> 3) * 4u) << 5) | ((a & 7u) << 2);                        // a = cell (= nibble) index inside the phase buffer
     }
   for (int k = total; k < SS_MAXF; ++k) out[k] = 0;
@@ -120,32 +126,37 @@ void fl_launch_pack_staged(fl_tdb db, fl_level_geom g, fl_staged_plan plan, cuda
 // word), so its window is the NW + 1 consecutive words starting at its base + the feature's word offset: NW + 1 loads (instead
 // of two per word), one funnel shift and one add per word.  NW is odd, so the 32 lanes of one load hit 32 different banks.
 // (Moving every other add to the FMA pipe as an IMAD was measured slower: IADD3 folds two adds into one issue slot.)
-template <int NW>
-__device__ __forceinline__ void accumulate_feature(const uint8_t* __restrict__ lane_base, uint32_t fw, uint32_t (&nib)[NW]) {
-  const uint32_t* w = reinterpret_cast<const uint32_t*>(lane_base + (fw >> 5));
-  constexpr int CH = 12;                                      // loads in flight per chunk (register budget)
-  uint32_t carry = w[0];
+// NF (1..3) features of one template at once.  Per feature the lane's window is NW + 1 consecutive words (one funnel shift per
+// owned word; the high word of one shift is the low word of the next).  The NF shifted words are added as packed nibbles (a response is
+// <= 4, so three of them cannot carry) and the sum goes straight into the byte accumulators: lo takes the even cells of each word, hi
+// the odd ones (byte totals <= 63 x 4 = 252).  Three features per spill is what keeps the kernel off the ALU pipe: per owned word
+// 3 shifts + 1 three-input add + 5 spill instructions instead of 3 x (shift + add) + 5.  Words are processed in chunks of CH so that
+// the loads of all NF features of a chunk are in flight together within the register budget.
+template <int NW, int NF>
+__device__ __forceinline__ void accumulate_features(const uint8_t* __restrict__ lane_base, const uint32_t (&fw)[3], uint32_t (&lo)[NW], uint32_t (&hi)[NW]) {
+  constexpr int CH = NW <= 7 ? NW : 6;
+  const uint32_t* w0 = reinterpret_cast<const uint32_t*>(lane_base + (fw[0] >> 5));
+  const uint32_t* w1 = reinterpret_cast<const uint32_t*>(lane_base + (fw[NF > 1 ? 1 : 0] >> 5));
+  const uint32_t* w2 = reinterpret_cast<const uint32_t*>(lane_base + (fw[NF > 2 ? 2 : 0] >> 5));
 #pragma unroll
   for (int c = 0; c < NW; c += CH) {
-    uint32_t v[CH + 1];
-    v[0] = carry;
+    uint32_t v0[CH + 1], v1[CH + 1], v2[CH + 1];
 #pragma unroll
-    for (int i = 0; i < CH; ++i) if (c + i < NW) v[i + 1] = w[c + i + 1];
+    for (int i = 0; i <= CH; ++i)
+      if (c + i <= NW) {
+        v0[i] = w0[c + i];
+        if (NF > 1) v1[i] = w1[c + i];
+        if (NF > 2) v2[i] = w2[c + i];
+      }
 #pragma unroll
     for (int i = 0; i < CH; ++i)
-      if (c + i < NW) nib[c + i] += __funnelshift_r(v[i], v[i + 1], fw);   // shift = low 5 bits; eight 4-bit lanes, no carry (<= 3 x 4)
-    carry = v[(NW - c) < CH ? (NW - c) : CH];
-  }
-}
-// nibble sums -> byte accumulators: lo takes the even cells of each word, hi the odd ones (byte totals <= 63 x 4 = 252)
-template <int NW>
-__device__ __forceinline__ void spill_nibbles(uint32_t (&nib)[NW], uint32_t (&lo)[NW], uint32_t (&hi)[NW]) {
-#pragma unroll
-  for (int i = 0; i < NW; ++i) {
-    const uint32_t n = nib[i];
-    lo[i] += n & 0x0F0F0F0Fu;
-    hi[i] += (n >> 4) & 0x0F0F0F0Fu;
-    nib[i] = 0;
+      if (c + i < NW) {
+        uint32_t n = __funnelshift_r(v0[i], v0[i + 1], fw[0]);            // shift = low 5 bits of the feature word
+        if (NF > 1) n += __funnelshift_r(v1[i], v1[i + 1], fw[1]);
+        if (NF > 2) n += __funnelshift_r(v2[i], v2[i + 1], fw[2]);
+        lo[c + i] += n & 0x0F0F0F0Fu;
+        hi[c + i] += (n >> 4) & 0x0F0F0F0Fu;
+      }
   }
 }
 
@@ -231,11 +242,13 @@ __global__ void __launch_bounds__(1024, 1) k_similarity_staged(const __grid_cons
         const int b = q % n_buf;
         if (q >= n_buf) mbar_wait(&s_empty[b], ((q / n_buf) - 1) & 1);
         int p = q + rot; if (p >= n_phases) p -= n_phases;
-        const int ml = p / plan.n_rowblocks, rb = p - ml * plan.n_rowblocks;
+        const int grp = p / plan.n_rowblocks, rb = p - grp * plan.n_rowblocks;
+        const int ml = grp * plan.labels_per_phase;             // first (modality, label) of the group; a group never straddles modalities
         const int m = ml >> 3, lab = ml & 7;
         const uint8_t* src = lm4_level + (((size_t)m * g.mod_stride + (size_t)lab * g.label_stride + (size_t)rb * plan.phase_rows * g.cells) >> 1);   // two cells per byte
         const int rows = min(plan.phase_rows, g.T * g.T - rb * plan.phase_rows);
-        const uint32_t bytes = (uint32_t)((((size_t)rows * g.cells >> 1) + plan.halo_bytes + 15) & ~(size_t)15);
+        // (the labels of a group are contiguous in memory, pads included: one copy)
+        const uint32_t bytes = (uint32_t)(((((size_t)(plan.labels_per_phase - 1) * g.label_stride + (size_t)rows * g.cells) >> 1) + plan.halo_bytes + 15) & ~(size_t)15);
         mbar_expect_tx(&s_full[b], bytes);                    // the whole phase lands here, whoever fetches it
         bulk_g2s(s_buf + (size_t)b * plan.buf_bytes, src, bytes, &s_full[b]);
       }
@@ -246,8 +259,7 @@ __global__ void __launch_bounds__(1024, 1) k_similarity_staged(const __grid_cons
     bool live[TPW];
     const uint8_t* pre[TPW];
     const uint32_t* fl[TPW];
-    uint32_t nib[TPW][NW], lo[TPW][NW], hi[TPW][NW];
-    int pending[TPW];                                         // features added to nib[s] since the last spill (warp-uniform)
+    uint32_t lo[TPW][NW], hi[TPW][NW];
 #pragma unroll
     for (int s = 0; s < TPW; ++s) {
       const int slot = warp + s * n_cwarps;
@@ -257,9 +269,8 @@ __global__ void __launch_bounds__(1024, 1) k_similarity_staged(const __grid_cons
       pre[s] = s_pre + (in ? slot : 0) * plan.pre_stride;
       fl[s] = s_feat + (in ? slot : 0) * SS_MAXF;
       if (!in) pre[s] = nullptr;
-      pending[s] = 0;
 #pragma unroll
-      for (int i = 0; i < NW; ++i) { nib[s][i] = 0; lo[s][i] = 0; hi[s][i] = 0; }
+      for (int i = 0; i < NW; ++i) { lo[s][i] = 0; hi[s][i] = 0; }
     }
     int p = rot;
     uint32_t par = 0;
@@ -289,14 +300,19 @@ __global__ void __launch_bounds__(1024, 1) k_similarity_staged(const __grid_cons
         const int k1 = pre[s][p + 1];
         if (k < k1) {                                         // warp-uniform
           const uint32_t* fp = fl[s] + k;
-          const uint32_t* fe = fl[s] + k1;
-          uint32_t fw = *fp;
-          do {
-            const uint32_t nx = fp[1];                        // next feature word (one past the list is a valid pad word)
-            accumulate_feature<NW>(lane_base, fw, nib[s]);
-            if (++pending[s] == 3) { spill_nibbles<NW>(nib[s], lo[s], hi[s]); pending[s] = 0; }
-            fw = nx; ++fp;
-          } while (fp < fe);
+          int n = k1 - k;
+          while (n >= 3) {                                    // the phase's features three at a time
+            const uint32_t fw[3] = {fp[0], fp[1], fp[2]};
+            accumulate_features<NW, 3>(lane_base, fw, lo[s], hi[s]);
+            fp += 3; n -= 3;
+          }
+          if (n == 2) {
+            const uint32_t fw[3] = {fp[0], fp[1], 0u};
+            accumulate_features<NW, 2>(lane_base, fw, lo[s], hi[s]);
+          } else if (n == 1) {
+            const uint32_t fw[3] = {fp[0], 0u, 0u};
+            accumulate_features<NW, 1>(lane_base, fw, lo[s], hi[s]);
+          }
         }
       }
       __syncwarp();
@@ -306,8 +322,6 @@ __global__ void __launch_bounds__(1024, 1) k_similarity_staged(const __grid_cons
       if (++p == n_phases) p = 0;
     }
     (void)lane_end;
-#pragma unroll
-    for (int s = 0; s < TPW; ++s) spill_nibbles<NW>(nib[s], lo[s], hi[s]);
     if (trace && tid == 0) trace[3] = globaltimer();
     if (trace && lane == 0) plan.trace[(size_t)plan.n_cta * 8 + 8 + ((size_t)blockIdx.x * 32 + warp) * 4] = globaltimer();       // per-warp loop end
 
@@ -486,10 +500,17 @@ bool fl_plan_staged(const fl_level_geom& g, int M, int n_templates, int max_posi
   if (!pr) return false;
   p.phase_rows = pr;
   p.n_rowblocks = (T2 + pr - 1) / pr;
-  p.n_phases = M * 8 * p.n_rowblocks;
+  // whole labels fit a buffer: put 2 or 4 consecutive labels of a modality into one phase if a 2-buffer ring still fits - every
+  // phase costs each warp ~45 instructions of bookkeeping whatever it holds, and longer runs of features split into more triples
+  p.labels_per_phase = 1;
+  if (p.n_rowblocks == 1)
+    for (int G = 4; G >= 2; G >>= 1)
+      if ((((size_t)(G - 1) * g.label_stride + (size_t)T2 * g.cells) >> 1) + p.halo_bytes + 128 <= budget) { p.labels_per_phase = G; break; }
+  p.n_phases = M * (8 / p.labels_per_phase) * p.n_rowblocks;
   if (p.n_phases > SS_MAX_PHASES) return false;
-  if (((size_t)pr * g.cells >> 1) + p.halo_bytes >= (1u << 24)) return false;
-  p.buf_bytes = (int)((((((size_t)pr * g.cells >> 1) + p.halo_bytes + 15) & ~(size_t)15) + 127) & ~(size_t)127);
+  const size_t phase_bytes = (((size_t)(p.labels_per_phase - 1) * g.label_stride + (size_t)pr * g.cells) >> 1) + p.halo_bytes;
+  if (phase_bytes >= (1u << 24)) return false;
+  p.buf_bytes = (int)((((phase_bytes + 15) & ~(size_t)15) + 127) & ~(size_t)127);
   p.pre_stride = (p.n_phases + 1 + 3) & ~3;
   const int fixed = p.tpc * 16 + (p.tpc * SS_MAXF + 4) * 4 + p.tpc * p.pre_stride + 16 + (int)stage_bytes;
   int nbuf = 2;
