@@ -366,9 +366,17 @@ __global__ void __launch_bounds__(256, 8) k_front_end_wave(fl_fe_wave w) {
   fl_grid_dep_wait();                                   // the previous kernel of the stream wrote this wave's inputs
   fl_grid_dep_launch();
   if (w.zero_me && b == 0 && threadIdx.x == 0) *w.zero_me = 0;
+  // the job this CTA belongs to: last job whose first CTA is <= b.  Binary search over the (<= 16) jobs: every warp of the grid runs
+  // this, and the linear walk it replaces was 10 % of the launch's instructions (ncu, round 2)
   int j = 0;
+  {
+    int hi = w.n_jobs - 1;
 #pragma unroll 1
-  while (j + 1 < w.n_jobs && b >= w.job[j + 1].cta_begin) ++j;
+    while (j < hi) {
+      const int mid = (j + hi + 1) >> 1;
+      if (b >= w.job[mid].cta_begin) j = mid; else hi = mid - 1;
+    }
+  }
   const fl_fe_job& jb = w.job[j];
   const int local = b - jb.cta_begin;
   if (w.trace && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); atomicMin(w.trace + 2 * j, t); }

@@ -154,8 +154,15 @@ __device__ __forceinline__ void accumulate_features(const uint8_t* __restrict__ 
         uint32_t n = __funnelshift_r(v0[i], v0[i + 1], fw[0]);            // shift = low 5 bits of the feature word
         if (NF > 1) n += __funnelshift_r(v1[i], v1[i + 1], fw[1]);
         if (NF > 2) n += __funnelshift_r(v2[i], v2[i + 1], fw[2]);
-        lo[c + i] += n & 0x0F0F0F0Fu;
-        hi[c + i] += (n >> 4) & 0x0F0F0F0Fu;
+        // odd cells (hi) and the whole word (lo).  The ALU pipe (funnel shifts, IADD3, LOP3) is the busiest unit of this kernel, the
+        // FMA pipe nearly idle: the shift by 4 is a multiply-high and the two accumulations are IMADs, which leaves ONE LOP3 per
+        // word on the ALU pipe instead of two LOP3 and a shift.  lo collects n itself: the even cells are lo - 16 hi, exact in
+        // 32-bit wrap-around arithmetic because the true packed value fits the word
+        uint32_t t;
+        asm("mul.hi.u32 %0, %1, 0x10000000;" : "=r"(t) : "r"(n));
+        const uint32_t h = t & 0x0F0F0F0Fu;
+        lo[c + i] += n;                                                    // = even cells + 16 x odd cells (mod 2^32); the caller takes 16 x hi off at the end
+        hi[c + i] += h;
       }
   }
 }
@@ -322,6 +329,10 @@ __global__ void __launch_bounds__(1024, 1) k_similarity_staged(const __grid_cons
       if (++p == n_phases) p = 0;
     }
     (void)lane_end;
+#pragma unroll
+    for (int s = 0; s < TPW; ++s)
+#pragma unroll
+      for (int i = 0; i < NW; ++i) lo[s][i] -= hi[s][i] << 4;          // (see accumulate_features)
     if (trace && tid == 0) trace[3] = globaltimer();
     if (trace && lane == 0) plan.trace[(size_t)plan.n_cta * 8 + 8 + ((size_t)blockIdx.x * 32 + warp) * 4] = globaltimer();       // per-warp loop end
 
