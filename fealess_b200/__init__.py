@@ -31,7 +31,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libfealess_b200.so")
 
 FL_OK, FL_ERR_SIZE, FL_ERR_GEOMETRY, FL_ERR_ROI, FL_ERR_FEATURES = 0, -1, -2, -3, -4
-FL_ERR_ARG, FL_ERR_CAPACITY, FL_ERR_CUDA, FL_ERR_STATE = -5, -6, -7, -8
+FL_ERR_ARG, FL_ERR_CAPACITY, FL_ERR_CUDA, FL_ERR_STATE, FL_ERR_TRAIN = -5, -6, -7, -8, -9
 FL_OPT_FE_WAVES, FL_OPT_SPLIT_REFINE, FL_OPT_TRACE, FL_OPT_FE_DEP_TIMEOUT_TEST, FL_OPT_FE_FORCED_WAVES = 0, 1, 2, 3, 4
 FL_DBG_QUANTIZED, FL_DBG_SPREAD, FL_DBG_LINEAR_MEMORY, FL_DBG_SIMILARITY, FL_DBG_STAGED_TRACE, FL_DBG_LAST_COUNTS, FL_DBG_FE_TRACE = 0, 1, 2, 3, 4, 5, 6
 
@@ -48,7 +48,7 @@ EXPORTED_SYMBOLS = [
     "fl_profile", "fl_last_stage_ms", "fl_last_icp_ms",
     "fl_group_create", "fl_group_destroy", "fl_group_size", "fl_group_handle", "fl_group_upload_templates", "fl_group_match",
     "fl_match_async", "fl_set_blocking_wait", "fl_match_shard_exchange_async", "fl_pipe_create", "fl_pipe_destroy", "fl_pipe_depth", "fl_pipe_in_flight", "fl_pipe_handle", "fl_pipe_upload_templates",
-    "fl_pipe_submit", "fl_pipe_collect", "fl_pipe_match_batch",
+    "fl_pipe_submit", "fl_pipe_collect", "fl_pipe_match_batch", "fl_default_train_params", "fl_add_template",
 ]
 
 
@@ -262,6 +262,34 @@ class Handle:
         cf = None if not class_filter else np.ascontiguousarray(class_filter, np.int32)
         _check(lib().fl_match_async(self._h, _p(bgr), C.c_size_t(W * 3), _p(depth), C.c_size_t(W * 2), W, H, None, C.c_float(threshold), _p(cf),
                                     0 if cf is None else int(cf.size)), "fl_match_async")
+
+    def add_template(self, bgr, depth, mask=None, num_features=None, strong_threshold: float = 55.0, extract_threshold: int = 2,
+                     feature_capacity: int = 4096):
+        """fl_add_template = Detector::addTemplate on one view (linemod.cpp:1579-1615).  Returns (rc, headers[L*M, 7], features[n, 3],
+        bbox[4]); rc is FL_OK or FL_ERR_TRAIN (too few candidates on a level: the reference returns -1)."""
+        H, W = (depth if depth is not None else bgr).shape[:2]
+        b = None if bgr is None else np.ascontiguousarray(bgr, np.uint8)
+        d = None if depth is None else np.ascontiguousarray(depth, np.uint16)
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+
+        class TrainParams(C.Structure):
+            _fields_ = [("num_features", C.c_int32 * 4), ("strong_threshold", C.c_float), ("extract_threshold", C.c_int32)]
+        tp = TrainParams()
+        lib().fl_default_train_params(C.byref(tp))
+        if num_features is not None:
+            for i, v in enumerate(num_features):
+                tp.num_features[i] = int(v)
+        tp.strong_threshold, tp.extract_threshold = float(strong_threshold), int(extract_threshold)
+        n_entries = self.L * self.M
+        hdr = np.zeros((n_entries, 7), np.int32)
+        ft = np.zeros((feature_capacity, 3), np.int32)
+        nf = C.c_int32(0)
+        bb = np.zeros(4, np.int32)
+        rc = lib().fl_add_template(self._h, _p(b), C.c_size_t(W * 3), _p(d), C.c_size_t(W * 2), _p(m), C.c_size_t(W), W, H, C.byref(tp), _p(hdr), _p(ft),
+                                   feature_capacity, C.byref(nf), _p(bb))
+        if rc not in (FL_OK, FL_ERR_TRAIN):
+            _check(rc, "fl_add_template")
+        return rc, hdr, ft[:nf.value].copy(), bb
 
     def match_wait(self) -> None:
         _check(lib().fl_match_wait(self._h), "fl_match_wait")

@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <new>
 #include <vector>
@@ -946,6 +947,146 @@ extern "C" int fl_match(fl_handle* h, const uint8_t* bgr, size_t bgr_stride, con
     FL_CUDA(cudaStreamSynchronize(s));
   }
   return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Detector::addTemplate (linemod.cpp:1579-1615)
+// ---------------------------------------------------------------------------------------------------
+extern "C" void fl_default_train_params(fl_train_params_t* p) {
+  if (!p) return;
+  for (int m = 0; m < FL_MAX_MODALITIES; ++m) p->num_features[m] = 63;
+  p->strong_threshold = 55.0f; p->extract_threshold = 2;
+}
+
+namespace {
+struct train_cand { int x, y, label; float score; };
+// QuantizedPyramid::selectScatteredFeatures (linemod.cpp:134-163), candidates already sorted
+void select_scattered(const std::vector<train_cand>& cands, std::vector<fl_feature_t>& out, size_t num_features, float distance) {
+  out.clear();
+  float distance_sq = distance * distance;
+  int i = 0;
+  while (out.size() < num_features) {
+    const train_cand& c = cands[i];
+    bool keep = true;
+    for (int j = 0; j < (int)out.size() && keep; ++j)
+      keep = (float)((c.x - out[j].x) * (c.x - out[j].x) + (c.y - out[j].y) * (c.y - out[j].y)) >= distance_sq;
+    if (keep) { fl_feature_t f = {c.x, c.y, c.label}; out.push_back(f); }
+    if (++i == (int)cands.size()) { i = 0; distance -= 1.0f; distance_sq = distance * distance; }   // start over with a relaxed distance
+  }
+}
+struct dev_buf {                                          // frees what a training call allocated, on every exit path
+  std::vector<void*> p;
+  ~dev_buf() { for (void* q : p) cudaFree(q); }
+  template <typename T> int get(T** out, size_t n) { int rc = dalloc(out, n); if (rc == FL_OK) p.push_back(*out); return rc; }
+};
+}  // namespace
+
+extern "C" int fl_add_template(fl_handle* h, const uint8_t* bgr, size_t bgr_stride, const uint16_t* depth, size_t depth_stride, const uint8_t* mask,
+                               size_t mask_stride, int32_t W, int32_t H, const fl_train_params_t* params_or_null, fl_template_hdr_t* headers,
+                               fl_feature_t* features, int32_t feature_capacity, int32_t* n_features, fl_rect_t* bounding_box) {
+  if (!h || !headers || !n_features || feature_capacity < 0 || (feature_capacity > 0 && !features)) return FL_ERR_ARG;
+  *n_features = 0;
+  fl_train_params_t tp;
+  if (params_or_null) tp = *params_or_null; else fl_default_train_params(&tp);
+  const fl_params_t& p = h->p;
+  const int L = p.n_levels, M = p.n_modalities;
+  if (mask && mask_stride < (size_t)W) return FL_ERR_SIZE;
+  // 1. the front end: quantised images of every level and modality (unmasked, as the pyramids' `angle` / `normal` members), the colour
+  //    pyramid.  A threshold above 100 % keeps matchClass from emitting anything if templates are loaded.
+  TRY(fl_match_async(h, bgr, bgr_stride, depth, depth_stride, W, H, nullptr, 200.f, nullptr, 0));
+  TRY(fl_match_wait(h));
+  cudaStream_t s = h->stream;
+  dev_buf tmp;
+  const size_t npx = (size_t)W * H;
+  float* d_mag; float* d_score; uint8_t* d_er1; uint8_t* d_er2; uint16_t* d_hd; int* d_cnt; uint8_t* d_maskpyr = nullptr;
+  TRY(tmp.get(&d_mag, npx)); TRY(tmp.get(&d_score, npx)); TRY(tmp.get(&d_er1, npx)); TRY(tmp.get(&d_er2, npx)); TRY(tmp.get(&d_hd, 8 * npx)); TRY(tmp.get(&d_cnt, 16));
+  std::vector<const uint8_t*> d_mask(L, nullptr);
+  if (mask) {
+    TRY(tmp.get(&d_maskpyr, 2 * npx));
+    FL_CUDA(cudaMemcpy2DAsync(d_maskpyr, W, mask, mask_stride, W, H, cudaMemcpyHostToDevice, s));
+    d_mask[0] = d_maskpyr;
+    size_t off = npx;
+    for (int l = 1; l < L; ++l) {                           // resize(mask, next_mask, size / 2, INTER_NEAREST) (:447-450, :734-738)
+      uint8_t* dst = d_maskpyr + off;
+      fl_launch_resize_nn_half(d_mask[l - 1], W >> (l - 1), H >> (l - 1), dst, s); ++h->launches;
+      d_mask[l] = dst; off += (size_t)(W >> l) * (H >> l);
+    }
+  }
+  std::vector<std::vector<fl_feature_t> > feats((size_t)L * M);
+  std::vector<float> h_score(npx);
+  std::vector<uint8_t> h_q(npx), h_lmask(npx);
+  for (int m = 0; m < M; ++m) {
+    const bool is_color = p.modality_kind[m] == FL_MODALITY_COLOR_GRADIENT;
+    for (int l = 0; l < L; ++l) {
+      const int w = W >> l, hh = H >> l;
+      const size_t n = (size_t)w * hh;
+      const size_t num_features = (size_t)tp.num_features[m] >> l;              // num_features /= 2 per pyrDown (:429, :724)
+      const uint8_t* d_q = h->d_q[l][m];
+      std::vector<train_cand> cands;
+      float distance;
+      int counts[16] = {0};
+      if (is_color) {
+        const uint8_t* d_bgr_l = l == 0 ? h->d_in_bgr : h->d_bgr[l];
+        fl_launch_train_magnitude(d_bgr_l, w, hh, d_mag, s); ++h->launches;
+        if (d_mask[l]) { fl_launch_train_erode3(d_mask[l], w, hh, d_er1, s); ++h->launches; }
+        fl_launch_train_color_score(d_q, d_mag, d_mask[l], d_mask[l] ? d_er1 : nullptr, w, hh, tp.strong_threshold * tp.strong_threshold, d_score, s); ++h->launches;
+      } else {
+        const uint8_t* d_local = nullptr;
+        if (d_mask[l]) {                                     // erode(mask, local_mask, Mat(), Point(-1,-1), 2, BORDER_REPLICATE) (:753)
+          fl_launch_train_erode3(d_mask[l], w, hh, d_er1, s); fl_launch_train_erode3(d_er1, w, hh, d_er2, s); h->launches += 2;
+          d_local = d_er2;
+          FL_CUDA(cudaMemcpyAsync(h_lmask.data(), d_er2, n, cudaMemcpyDeviceToHost, s));
+        }
+        fl_launch_train_depth_score(d_q, d_local, d_hd, d_cnt, w, hh, tp.extract_threshold >> l, d_score, d_cnt + 8, s); h->launches += 2;   // extract_threshold /= 2 per level (:725)
+        FL_CUDA(cudaMemcpyAsync(counts, d_cnt, sizeof counts, cudaMemcpyDeviceToHost, s));
+      }
+      FL_CUDA(cudaMemcpyAsync(h_score.data(), d_score, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+      FL_CUDA(cudaMemcpyAsync(h_q.data(), d_q, n, cudaMemcpyDeviceToHost, s));
+      FL_CUDA(wait_stream(h));
+      for (int y = 0; y < hh; ++y)                            // candidates in row-major order: the order std::stable_sort keeps among ties
+        for (int x = 0; x < w; ++x) {
+          const float sc = h_score[(size_t)y * w + x];
+          if (sc < 0.f) continue;
+          const int q = h_q[(size_t)y * w + x];
+          int label = 0; while (label < 7 && !(q & (1 << label))) ++label;      // getLabel: the set bit
+          train_cand c = {x, y, label, sc};
+          cands.push_back(c);
+        }
+      if (cands.size() < num_features) return FL_ERR_TRAIN;                       // (:500-501, :803-804)
+      if (is_color) {
+        distance = num_features ? static_cast<float>(cands.size() / num_features + 1) : 0.f;                         // (:506)
+      } else {
+        for (train_cand& c : cands) c.score /= (float)counts[8 + c.label];         // penalise labels with many candidates (:808-812)
+        size_t area = n;
+        if (d_mask[l]) { area = 0; for (size_t i = 0; i < n; ++i) area += h_lmask[i] != 0; }
+        distance = num_features ? sqrtf((float)area) / sqrtf((float)num_features) + 1.5f : 0.f;                       // (:816-817)
+      }
+      std::stable_sort(cands.begin(), cands.end(), [](const train_cand& a, const train_cand& b) { return a.score > b.score; });   // Candidate::operator< (linemod.hpp:124-128)
+      select_scattered(cands, feats[(size_t)l * M + m], num_features, distance);
+    }
+  }
+  // cropTemplates (linemod.cpp:52-96)
+  int min_x = INT_MAX, min_y = INT_MAX, max_x = INT_MIN, max_y = INT_MIN;
+  for (int l = 0; l < L; ++l) for (int m = 0; m < M; ++m) for (const fl_feature_t& f : feats[(size_t)l * M + m]) {
+    const int x = f.x << l, y = f.y << l;
+    min_x = std::min(min_x, x); min_y = std::min(min_y, y); max_x = std::max(max_x, x); max_y = std::max(max_y, y);
+  }
+  if (min_x % 2 == 1) --min_x;
+  if (min_y % 2 == 1) --min_y;
+  int nf = 0;
+  for (int l = 0; l < L; ++l) for (int m = 0; m < M; ++m) {
+    fl_template_hdr_t& hd = headers[(size_t)l * M + m];
+    hd.width = (max_x - min_x) >> l; hd.height = (max_y - min_y) >> l; hd.offset_x = min_x >> l; hd.offset_y = min_y >> l; hd.pyramid_level = l;
+    hd.feature_begin = nf; hd.feature_count = (int)feats[(size_t)l * M + m].size();
+    for (const fl_feature_t& f : feats[(size_t)l * M + m]) {
+      if (nf >= feature_capacity) return FL_ERR_CAPACITY;
+      fl_feature_t g = {f.x - hd.offset_x, f.y - hd.offset_y, f.label};
+      features[nf++] = g;
+    }
+  }
+  *n_features = nf;
+  if (bounding_box) { bounding_box->x = min_x; bounding_box->y = min_y; bounding_box->width = max_x - min_x; bounding_box->height = max_y - min_y; }
+  return FL_OK;
 }
 
 extern "C" int fl_match_shard_device(fl_handle* h, const void* d_bgr, const void* d_depth, int32_t W, int32_t H, const void* const* d_masks,

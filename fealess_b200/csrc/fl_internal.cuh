@@ -99,6 +99,14 @@ void fl_fe_add_resize(fl_fe_wave* w, const uint8_t* src, int W, int H, uint8_t* 
 void fl_fe_add_spread(fl_fe_wave* w, const uint8_t* q, fl_level_geom g, uint8_t* lm_mod, uint8_t* spread_or_null, uint8_t* lm4_mod_or_null);
 cudaError_t fl_launch_fe_wave(const fl_fe_wave& w, cudaStream_t s);
 
+// ---- template training, per-pixel half (train.cu) -----------------------------------------------
+void fl_launch_train_magnitude(const uint8_t* bgr, int W, int H, float* mag, cudaStream_t s);
+void fl_launch_train_erode3(const uint8_t* src, int W, int H, uint8_t* dst, cudaStream_t s);
+void fl_launch_train_color_score(const uint8_t* angle, const float* mag, const uint8_t* mask, const uint8_t* eroded, int W, int H, float threshold_sq,
+                                 float* score, cudaStream_t s);
+void fl_launch_train_depth_score(const uint8_t* normal, const uint8_t* local_mask, uint16_t* hd, int* any_zero8, int W, int H, int extract_threshold,
+                                 float* score, int* label_counts8, cudaStream_t s);
+
 // ---- similarity / refinement / sort (similarity.cu) ---------------------------------------------
 struct fl_tdb {                     // device template database
   int n_templates, L, M, n_classes;

@@ -46,7 +46,8 @@ enum {
   FL_ERR_ARG = -5,         /* null / out-of-range argument */
   FL_ERR_CAPACITY = -6,    /* an internal or caller buffer was too small; *count still reports the needed size */
   FL_ERR_CUDA = -7,        /* CUDA runtime error or no device; fl_last_error() has the text */
-  FL_ERR_STATE = -8        /* call order violated (e.g. match before upload) */
+  FL_ERR_STATE = -8,       /* call order violated (e.g. match before upload) */
+  FL_ERR_TRAIN = -9        /* fl_add_template: a pyramid level has fewer candidate features than requested (addTemplate returns -1, linemod.cpp:1600-1602) */
 };
 
 enum { FL_MODALITY_COLOR_GRADIENT = 0, FL_MODALITY_DEPTH_NORMAL = 1 };
@@ -113,6 +114,26 @@ int fl_upload_templates(fl_handle* h, int32_t n_templates, const fl_template_hdr
 int fl_set_template_ids(fl_handle* h, const int32_t* template_ids);
 int fl_num_templates(fl_handle* h);
 int fl_get_pose_info(fl_handle* h, int32_t class_idx, int32_t template_id, float out13[13]);
+
+/* ---- Detector::addTemplate (template training) ------------------------------------------------------
+ * One view of an object -> one template pyramid (linemod.cpp:1579-1615 with ColorGradientPyramid / DepthNormalPyramid::extractTemplate
+ * :461-513, :747-825, selectScatteredFeatures :134-163, cropTemplates :52-96).  The per-pixel work runs on the device: the front end's
+ * quantised images, the gradient magnitude, the mask erosions, eight chessboard distance transforms, the candidate tests; the stable
+ * sort and the greedy scattered selection are sequential and run on the host.  bgr / depth / mask: host images of the handle's
+ * modalities (mask nullable; 8UC1, nonzero = object).  headers: n_levels * n_modalities entries (index level * n_modalities + modality),
+ * feature_begin pointing into `features` (at most feature_capacity; 63 per entry by default).  The result is what the reference's
+ * addTemplate stores (bit-exact; tests/test_gpu_train.py) and can be handed to fl_upload_templates as it is.
+ * FL_ERR_TRAIN: too few candidates on some level (the reference returns -1 and adds nothing). */
+typedef struct {
+  int32_t num_features[FL_MAX_MODALITIES];  /* per modality at level 0, halved per level; default 63 (:518, :830) */
+  float   strong_threshold;                 /* ColorGradient: 55 (:519) */
+  int32_t extract_threshold;                /* DepthNormal: 2, halved per level (:725, :831) */
+} fl_train_params_t;
+void fl_default_train_params(fl_train_params_t* p);
+int fl_add_template(fl_handle* h, const uint8_t* bgr, size_t bgr_stride, const uint16_t* depth, size_t depth_stride,
+                    const uint8_t* mask, size_t mask_stride, int32_t W, int32_t H, const fl_train_params_t* params_or_null,
+                    fl_template_hdr_t* headers, fl_feature_t* features, int32_t feature_capacity, int32_t* n_features,
+                    fl_rect_t* bounding_box);
 
 /* ---- Detector::match -------------------------------------------------------------------------------
  * Host buffers in, host matches out (sorted by the canonical total order, duplicates pruned).

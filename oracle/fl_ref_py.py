@@ -268,6 +268,34 @@ def svd3_rot(cov):
 
 
 # ---- the shim's primitives, one by one (pinned on cv2 by tests/test_oracle_ref.py) ----
+def add_template(det: "Detector", bgr, depth, mask=None, feature_cap: int = 4096):
+    """The reference's own Detector::addTemplate on one view.  Returns (rc, headers[L*M, 7], features[n, 3], bbox[4]); rc = -1 when a
+    pyramid level has too few candidates (the reference's return value)."""
+    H, W = depth.shape[:2]
+    b = np.ascontiguousarray(bgr, np.uint8); d = np.ascontiguousarray(depth, np.uint16)
+    m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+    hdr = np.zeros((det.L * det.M, 7), np.int32)
+    ft = np.zeros((feature_cap, 3), np.int32)
+    nf = C.c_int(0)
+    bb = np.zeros(4, np.int32)
+    rc = lib().flr_detector_add_template(det._h, _p(b), _p(d), _p(m) if m is not None else None, W, H, _p(hdr), _p(ft), feature_cap, C.byref(nf), _p(bb))
+    return rc, hdr, ft[:nf.value].copy(), bb
+
+
+def prim_erode3(img, iterations=1):
+    H, W = img.shape
+    out = np.zeros((H, W), np.uint8)
+    lib().flr_prim_erode3(_p(np.ascontiguousarray(img, np.uint8)), W, H, int(iterations), _p(out))
+    return out
+
+
+def prim_distance_c3(img):
+    H, W = img.shape
+    out = np.zeros((H, W), np.float32)
+    lib().flr_prim_distance_c3(_p(np.ascontiguousarray(img, np.uint8)), W, H, _p(out))
+    return out
+
+
 def prim_gaussian7(bgr):
     H, W = bgr.shape[:2]
     out = np.empty_like(bgr)

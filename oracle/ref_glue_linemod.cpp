@@ -284,4 +284,50 @@ int flr_detector_match_raw(flr_detector* d, float threshold, const int32_t* clas
   } catch (const cv::Exception& e) { d->last_error = e.what(); return -2; }
 }
 
+// Detector::addTemplate (linemod.cpp:1579-1615): the reference's own template extraction on one view.  A scratch detector with the
+// same modalities / pyramid receives the template; its pyramid comes back in the layout of flr_detector_set_templates: 7 ints per
+// (level, modality) = width, height, offset_x, offset_y, pyramid_level, feature_begin, feature_count; features x, y, label.
+// Returns the reference's return value (template id 0, or -1 when a level has too few candidates); bbox = x, y, w, h.
+int flr_detector_add_template(flr_detector* d, const uint8_t* bgr, const uint16_t* depth, const uint8_t* mask_or_null, int W, int H,
+                              int32_t* headers, int32_t* features, int feature_cap, int* n_features, int32_t bbox[4]) {
+  try {
+    std::vector<cv::Ptr<cup_linemod::Modality> > mods = d->det->getModalities();
+    Probe scratch(mods, d->det->Ts());
+    std::vector<cv::Mat> sources;
+    for (int i = 0; i < d->M; ++i)
+      sources.push_back(d->kinds[i] == 0 ? cv::Mat(H, W, CV_8UC3, const_cast<uint8_t*>(bgr)) : cv::Mat(H, W, CV_16UC1, const_cast<uint16_t*>(depth)));
+    cv::Mat mask;
+    if (mask_or_null) mask = cv::Mat(H, W, CV_8UC1, const_cast<uint8_t*>(mask_or_null));
+    float pose[13] = {0};
+    cv::Rect bb;
+    const int id = scratch.addTemplate(sources, "train", mask, pose, &bb);
+    *n_features = 0;
+    if (id < 0) return id;
+    const std::vector<cup_linemod::Template>& tp = scratch.getTemplates("train", id);
+    int nf = 0;
+    for (size_t k = 0; k < tp.size(); ++k) {
+      int32_t* h = headers + k * 7;
+      h[0] = tp[k].width; h[1] = tp[k].height; h[2] = tp[k].offset_x; h[3] = tp[k].offset_y; h[4] = tp[k].pyramid_level; h[5] = nf; h[6] = (int)tp[k].features.size();
+      for (size_t j = 0; j < tp[k].features.size(); ++j, ++nf) {
+        if (nf >= feature_cap) return -3;
+        features[3 * nf] = tp[k].features[j].x; features[3 * nf + 1] = tp[k].features[j].y; features[3 * nf + 2] = tp[k].features[j].label;
+      }
+    }
+    *n_features = nf;
+    bbox[0] = bb.x; bbox[1] = bb.y; bbox[2] = bb.width; bbox[3] = bb.height;
+    return id;
+  } catch (const cv::Exception& e) { d->last_error = e.what(); return -2; }
+}
+// the two OpenCV primitives only template training calls (linemod.cpp:466, 753, 765), for pinning the stand-ins on cv2
+void flr_prim_erode3(const uint8_t* src, int W, int H, int iterations, uint8_t* out) {
+  cv::Mat s(H, W, CV_8UC1, const_cast<uint8_t*>(src)), o;
+  cv::erode(s, o, cv::Mat(), cv::Point(-1, -1), iterations, cv::BORDER_REPLICATE);
+  std::memcpy(out, o.ptr(0), (size_t)W * H);
+}
+void flr_prim_distance_c3(const uint8_t* src, int W, int H, float* out) {
+  cv::Mat s(H, W, CV_8UC1, const_cast<uint8_t*>(src)), o;
+  cv::distanceTransform(s, o, cv::DIST_C, 3);
+  std::memcpy(out, o.ptr(0), (size_t)W * H * sizeof(float));
+}
+
 }  // extern "C"

@@ -649,6 +649,12 @@ void distanceTransform(InputArray src_, OutputArray dst_, int distanceType, int 
   Mat src = continuous(src_.getMat());
   CV_Assert(src.type() == CV_8UC1 && distanceType == DIST_C && maskSize == 3 && dstType == CV_32F);
   int W = src.cols, H = src.rows;
+  {   // an image without a single zero pixel: OpenCV 4.13's own code returns 65535 everywhere (its IPP path FLT_MAX); as for the resize,
+      // the stand-in follows OpenCV's code (cv2.ipp.setUseIPP(False))
+    bool any_zero = false;
+    for (int y = 0; y < H && !any_zero; ++y) for (int x = 0; x < W; ++x) if (!src.ptr(y)[x]) { any_zero = true; break; }
+    if (!any_zero) { Mat out(H, W, CV_32F); for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) out.ptr<float>(y)[x] = 65535.f; out.copyTo(dst_); return; }
+  }
   const unsigned INIT = (unsigned)(INT_MAX >> 2), HV = 1u << 16, DIAG = 1u << 16;
   size_t step = (size_t)W + 2;
   std::vector<unsigned> tmp((size_t)(H + 2) * step, INIT);

@@ -1,0 +1,67 @@
+"""GPU (-m gpu): fl_add_template = Detector::addTemplate against the REFERENCE'S OWN addTemplate
+(oracle/_ref: linemod.cpp:1579-1615 compiled unmodified; its erode / distanceTransform stand-ins are pinned on cv2 by
+tests/test_oracle_ref.py).  The template pyramid - every feature, the cropped boxes, the bounding box - has to be identical."""
+import numpy as np
+import pytest
+
+import fealess_b200 as fb
+import fl_ref_py as R
+from fealess_b200 import synth
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not R.available(), reason="oracle/_ref/libfl_ref.so is not in this checkout")]
+
+
+def _ellipse(W, H, cx, cy, a, b, value=255):
+    yy, xx = np.mgrid[0:H, 0:W]
+    return (((xx - cx) / a) ** 2 + ((yy - cy) / b) ** 2 <= 1.0).astype(np.uint8) * value
+
+
+CASES = [
+    dict(W=640, H=480, T=(5, 8), mask=lambda W, H: _ellipse(W, H, 320, 240, 110, 80), frame=0),
+    dict(W=640, H=480, T=(5, 8), mask=lambda W, H: _ellipse(W, H, 200, 300, 60, 140, value=1), frame=1),     # mask values other than 255
+    dict(W=640, H=480, T=(5, 8), mask=None, frame=2),                                                        # no mask: the whole view
+    dict(W=640, H=480, T=(4, 8, 8), mask=lambda W, H: _ellipse(W, H, 400, 200, 150, 120), frame=3),          # three levels
+    dict(W=1280, H=720, T=(5, 8), mask=lambda W, H: _ellipse(W, H, 640, 360, 300, 200), frame=0),
+    dict(W=640, H=480, T=(5, 8), mask=lambda W, H: np.pad(np.full((200, 260), 255, np.uint8), ((0, 280), (0, 380))), frame=1),   # object touching the image border
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_add_template_equals_reference(case):
+    W, H, T = case["W"], case["H"], case["T"]
+    b, d = synth.make_frame(W, H, case["frame"])
+    mask = case["mask"](W, H) if case["mask"] else None
+    ref = R.Detector(T)
+    rrc, rhdr, rft, rbb = R.add_template(ref, b, d, mask)
+    h = fb.Handle(T, (0, 1), W, H)
+    rc, hdr, ft, bb = h.add_template(b, d, mask)
+    assert (rc == 0) == (rrc >= 0), (rc, rrc)
+    if rrc >= 0:
+        assert np.array_equal(hdr, rhdr), (hdr, rhdr)
+        assert np.array_equal(ft, rft)
+        assert np.array_equal(bb, rbb)
+        assert len(ft) == sum(63 >> l for l in range(len(T))) * 2
+    h.close()
+
+
+def test_too_few_candidates_and_trained_template_matches_its_own_view():
+    """addTemplate's failure mode, and the trained pyramid going straight back into fl_upload_templates."""
+    W, H, T = 640, 480, (5, 8)
+    b, d = synth.make_frame(W, H, 0)
+    h = fb.Handle(T, (0, 1), W, H)
+    ref = R.Detector(T)
+    tiny = _ellipse(W, H, 320, 240, 6, 5)                                   # too small for 63 features: both return "no template"
+    assert R.add_template(ref, b, d, tiny)[0] == -1
+    assert h.add_template(b, d, tiny)[0] == fb.FL_ERR_TRAIN
+    # a trained template, uploaded as it comes back, matches the view it was cut from at 100 % at its own position
+    mask = _ellipse(W, H, 320, 240, 110, 80)
+    rc, hdr, ft, bb = h.add_template(b, d, mask)
+    assert rc == 0
+    ts = synth.TemplateSet(n_levels=2, n_modalities=2, T=T, class_names=["obj"], headers=hdr.copy(), features=ft.copy(), class_of=np.zeros(1, np.int32),
+                           pose13=np.zeros((1, 13), np.float32))
+    h.upload_templates(ts)
+    rc, got = h.match(b, d, 90.0)
+    assert rc == 0 and len(got) >= 1
+    # (positions live on the T = 5 grid of level 0, so the best match sits within one cell of the template's box corner)
+    assert abs(int(got[0]["x"]) - int(bb[0])) <= 5 and abs(int(got[0]["y"]) - int(bb[1])) <= 5 and got[0]["similarity"] >= 90.0
+    h.close()

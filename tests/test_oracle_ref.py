@@ -358,3 +358,46 @@ def test_reference_on_real_cv2_primitives_is_identical():
     assert all(np.array_equal(a, b) for a, b in zip(lms0, lms1))
     assert np.array_equal(d0["R"], d1["R"]) and np.array_equal(d0["T"], d1["T"])
     assert fr.process(bgr, depth) == 0
+
+
+def test_training_primitives_of_the_shim_equal_cv2():
+    """cv::erode (3x3, BORDER_REPLICATE, 1 and 2 iterations) and cv::distanceTransform(DIST_C, 3) are called by template training only
+    (linemod.cpp:466, 753, 765); the stand-ins the reference is compiled against equal the real cv2, including the image without a
+    zero pixel (65535 in OpenCV 4.13's own code; with IPP on, Intel's routine returns FLT_MAX there - the stand-in follows OpenCV's code)."""
+    cv2 = pytest.importorskip("cv2")
+    use_ipp = cv2.ipp.useIPP()
+    cv2.ipp.setUseIPP(False)
+    try:
+        _check_training_primitives(cv2)
+    finally:
+        cv2.ipp.setUseIPP(use_ipp)
+
+
+def _check_training_primitives(cv2):
+    rng = np.random.default_rng(0)
+    for t in range(20):
+        H, W = int(rng.integers(8, 90)), int(rng.integers(8, 120))
+        m = (rng.random((H, W)) < rng.uniform(0.5, 0.98)).astype(np.uint8) * 255
+        if t % 5 == 0:
+            m[:] = 255
+        for it in (1, 2):
+            assert np.array_equal(R.prim_erode3(m, it), cv2.erode(m, None, iterations=it, borderType=cv2.BORDER_REPLICATE))
+        assert np.array_equal(R.prim_distance_c3(m), cv2.distanceTransform(m, cv2.DIST_C, 3))
+
+
+def test_reference_add_template_runs_and_is_deterministic():
+    """Detector::addTemplate of the reference through the glue: 63 + 63 features at level 0, 31 + 31 at level 1, boxes cropped to the
+    features; a mask too small for 63 features returns -1."""
+    from fealess_b200 import synth
+    W, H = 640, 480
+    b, d = synth.make_frame(W, H, 0)
+    yy, xx = np.mgrid[0:H, 0:W]
+    mask = ((((xx - 320) / 110.0) ** 2 + ((yy - 240) / 80.0) ** 2) <= 1.0).astype(np.uint8) * 255
+    det = R.Detector((5, 8))
+    rc, hdr, ft, bb = R.add_template(det, b, d, mask)
+    assert rc == 0 and hdr[:, 6].tolist() == [63, 63, 31, 31] and len(ft) == 188
+    assert (hdr[:2, 0] == bb[2]).all() and (hdr[:2, 1] == bb[3]).all() and bb[0] % 2 == 0 and bb[1] % 2 == 0
+    rc2, hdr2, ft2, bb2 = R.add_template(det, b, d, mask)
+    assert rc2 == 0 and np.array_equal(hdr, hdr2) and np.array_equal(ft, ft2)
+    tiny = ((((xx - 320) / 6.0) ** 2 + ((yy - 240) / 5.0) ** 2) <= 1.0).astype(np.uint8) * 255
+    assert R.add_template(det, b, d, tiny)[0] == -1
