@@ -758,6 +758,24 @@ class Detector:
         cid = class_id if class_id is not None else self.classIds()[0]
         return self._poses[cid][template_id]
 
+    def addTemplate(self, sources, class_id, object_mask=None, pose_info=None):
+        """Detector::addTemplate (linemod.hpp:338-339, linemod.cpp:1579-1615): extract a template pyramid from one view (``sources`` in
+        modality order) and append it to ``class_id``.  Returns (template_id, bounding_box (x, y, w, h)); template_id is -1 when a
+        pyramid level has too few candidate features (nothing is added)."""
+        if len(sources) != len(self.modalities):
+            return -1, None
+        bgr = depth = None
+        for name, src in zip(self.modalities, sources):
+            if name == "ColorGradient":
+                bgr = src
+            else:
+                depth = src
+        rc, hdr, ft, bb = self._handle.add_template(bgr, depth, object_mask)
+        if rc != FL_OK:
+            return -1, None
+        pyr = [(int(h[0]), int(h[1]), int(h[2]), int(h[3]), int(h[4]), [tuple(int(v) for v in f) for f in ft[h[5]:h[5] + h[6]]]) for h in hdr]
+        return self.addSyntheticTemplate(pyr, class_id, pose_info), tuple(int(v) for v in bb)
+
     def addSyntheticTemplate(self, templates, class_id, pose_info=None) -> int:
         lst = self._classes.setdefault(class_id, [])
         self._poses.setdefault(class_id, []).append(np.zeros(13, np.float32) if pose_info is None else np.asarray(pose_info, np.float32))

@@ -12,7 +12,7 @@
 //                                                     numTemplates, numClasses, classIds, getModalities
 //   getDefaultLINE / getDefaultLINEMOD .............. linemod.cpp:1822-1835
 //   readLinemod / writeLinemod ...................... linemod_if.cpp:36-66: in linemod_io.hpp (own FileStorage-YAML reader / writer)
-// Not provided (out of scope): addTemplate (training), colormap/drawResponse.
+// addTemplate (training) goes through fl_add_template.  Not provided (out of scope): colormap / drawResponse.
 #ifndef FEALESS_B200_LINEMOD_HPP
 #define FEALESS_B200_LINEMOD_HPP
 
@@ -215,6 +215,49 @@ class Detector {
     return 0;
   }
 
+  // Detector::addTemplate (linemod.hpp:338-339, linemod.cpp:1579-1615): extract one template pyramid from a view of the object and
+  // append it to class_id.  Returns the template id, or -1 when some pyramid level has too few candidate features (nothing is added).
+  // The per-pixel work runs on the device (fl_add_template); the result is the reference's, feature for feature.
+  int addTemplate(const std::vector<Mat>& sources, const String& class_id, const Mat& object_mask, const float* const pose_info,
+                  cv::Rect* bounding_box = nullptr) {
+    if (sources.size() != modalities.size()) return -1;
+    const int M = (int)modalities.size(), L = pyramid_levels;
+    const uint8_t* bgr = nullptr; size_t bgr_step = 0; const uint16_t* depth = nullptr; size_t depth_step = 0;
+    int W = 0, H = 0;
+    fl_train_params_t tp;
+    fl_default_train_params(&tp);
+    for (int m = 0; m < M; ++m) {
+      const Mat& s = sources[m];
+      if (s.empty() || (W && (s.cols != W || s.rows != H))) return -1;
+      W = s.cols; H = s.rows;
+      if (const ColorGradient* cg = dynamic_cast<const ColorGradient*>(modalities[m].get())) {
+        if (s.type() != CV_8UC3) throw cv::Exception("ColorGradient source must be CV_8UC3");
+        bgr = s.ptr<uint8_t>(0); bgr_step = s.step; tp.num_features[m] = (int32_t)cg->num_features; tp.strong_threshold = cg->strong_threshold;
+      } else if (const DepthNormal* dn = dynamic_cast<const DepthNormal*>(modalities[m].get())) {
+        if (s.type() != CV_16UC1) throw cv::Exception("DepthNormal source must be CV_16UC1");
+        depth = s.ptr<uint16_t>(0); depth_step = s.step; tp.num_features[m] = (int32_t)dn->num_features; tp.extract_threshold = dn->extract_threshold;
+      }
+    }
+    if (!object_mask.empty() && (object_mask.type() != CV_8UC1 || object_mask.cols != W || object_mask.rows != H)) throw cv::Exception("addTemplate: mask must be CV_8UC1 of the sources' size");
+    ensure_uploaded(W, H);
+    std::vector<fl_template_hdr_t> hdr((size_t)L * M);
+    std::vector<fl_feature_t> feat((size_t)L * M * 64 + 64);
+    int32_t nf = 0;
+    fl_rect_t bb = {0, 0, 0, 0};
+    const int rc = fl_add_template(handle_, bgr, bgr_step, depth, depth_step, object_mask.empty() ? nullptr : object_mask.ptr<uint8_t>(0),
+                                   object_mask.empty() ? 0 : object_mask.step, W, H, &tp, hdr.data(), feat.data(), (int32_t)feat.size(), &nf, &bb);
+    if (rc == FL_ERR_TRAIN) return -1;
+    fealess_b200::check_status(rc, "Detector::addTemplate");
+    std::vector<Template> pyr((size_t)L * M);
+    for (size_t e = 0; e < pyr.size(); ++e) {
+      pyr[e].width = hdr[e].width; pyr[e].height = hdr[e].height; pyr[e].offset_x = hdr[e].offset_x; pyr[e].offset_y = hdr[e].offset_y; pyr[e].pyramid_level = hdr[e].pyramid_level;
+      for (int k = 0; k < hdr[e].feature_count; ++k) { const fl_feature_t& f = feat[(size_t)hdr[e].feature_begin + k]; pyr[e].features.push_back(Feature(f.x, f.y, f.label)); }
+    }
+    if (pose_info) addPoseInfo(pose_info);                       // (:1586; the reference appends the pose BEFORE it knows whether the
+                                                                 //  extraction succeeds and so desynchronises its flat list on a -1; the mirror does not)
+    if (bounding_box) *bounding_box = cv::Rect(bb.x, bb.y, bb.width, bb.height);
+    return addSyntheticTemplate(pyr, class_id);
+  }
   // Detector::addSyntheticTemplate (linemod.cpp:1636-1642): templates = one TemplatePyramid, (L0 M0, L0 M1, L1 M0, ...)
   int addSyntheticTemplate(const std::vector<Template>& templates, const String& class_id) {
     std::vector<TemplatePyramid>& tp = class_templates[class_id];

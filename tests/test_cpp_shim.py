@@ -140,6 +140,36 @@ def test_cpp_detector_over_several_gpus_of_one_process(tmp_path, devices):
 
 
 @pytest.mark.gpu
+def test_cpp_add_template_equals_the_c_abi(tmp_path):
+    """cup_linemod::Detector::addTemplate of the C++ mirror (reference signature) returns the pyramid fl_add_template returns through the
+    ctypes binding (tests/test_gpu_train.py ties that one to the reference's own addTemplate), -1 and no side effect for a view with too
+    few candidates, and the trained template matches its own view."""
+    W, H = 640, 480
+    b, d = synth.make_frame(W, H, 0)
+    yy, xx = np.mgrid[0:H, 0:W]
+    mask = ((((xx - 320) / 110.0) ** 2 + ((yy - 240) / 80.0) ** 2) <= 1.0).astype(np.uint8) * 255
+    tiny = ((((xx - 320) / 6.0) ** 2 + ((yy - 240) / 5.0) ** 2) <= 1.0).astype(np.uint8) * 255
+    h = fb.Handle((5, 8), (0, 1), W, H)
+    rc, hdr, ft, bb = h.add_template(b, d, mask)
+    assert rc == 0
+    h.close()
+    case = tmp_path / "train_case.bin"
+    with open(case, "wb") as f:
+        f.write(struct.pack("<ii", W, H)); f.write(b.tobytes()); f.write(d.tobytes()); f.write(mask.tobytes()); f.write(tiny.tobytes())
+        f.write(struct.pack("<i", len(hdr))); f.write(np.ascontiguousarray(hdr, np.int32).tobytes())
+        f.write(struct.pack("<i", len(ft))); f.write(np.ascontiguousarray(ft, np.int32).tobytes()); f.write(np.ascontiguousarray(bb, np.int32).tobytes())
+    fbuild.build()
+    os.makedirs(OUT_DIR, exist_ok=True)
+    exe = os.path.join(OUT_DIR, "train_test")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    r = subprocess.run([cxx, "-std=c++11", "-O1", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "train_test.cpp"),
+                        "-o", exe, fb.library_path(), "-Wl,-rpath," + os.path.dirname(fb.library_path())], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    r = subprocess.run([exe, str(case)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "all checks passed" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
 def test_group_binding_matches_oracle(tmp_path):
     """fl_group_* through the ctypes binding, three handles on one GPU; an exchange block that is too small is reported."""
     _, b, d, ts, exp, thr = _case_file(tmp_path, n_templates=700, seed=34)

@@ -65,3 +65,18 @@ def test_too_few_candidates_and_trained_template_matches_its_own_view():
     # (positions live on the T = 5 grid of level 0, so the best match sits within one cell of the template's box corner)
     assert abs(int(got[0]["x"]) - int(bb[0])) <= 5 and abs(int(got[0]["y"]) - int(bb[1])) <= 5 and got[0]["similarity"] >= 90.0
     h.close()
+
+
+def test_python_mirror_add_template_then_match():
+    """cup_linemod::Detector mirror: addTemplate -> match on the same view finds the new class; a failed addTemplate adds nothing."""
+    W, H = 640, 480
+    b, d = synth.make_frame(W, H, 0)
+    det = fb.Detector()
+    tid, bb = det.addTemplate([b, d], "obj", _ellipse(W, H, 320, 240, 6, 5))
+    assert tid == -1 and det.numTemplates() == 0
+    tid, bb = det.addTemplate([b, d], "obj", _ellipse(W, H, 320, 240, 110, 80), pose_info=np.arange(13, dtype=np.float32))
+    assert tid == 0 and det.numTemplates("obj") == 1 and bb[0] % 2 == 0 and bb[1] % 2 == 0
+    tid2, _ = det.addTemplate([b, d], "obj", _ellipse(W, H, 200, 300, 60, 140))
+    assert tid2 == 1
+    rc, ms = det.match([b, d], 90.0)
+    assert rc == 0 and len(ms) >= 2 and {m.template_id for m in ms[:4]} >= {0, 1} and ms[0].class_id == "obj"
