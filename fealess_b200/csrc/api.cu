@@ -98,6 +98,12 @@ template <typename T> static int halloc(T** p, size_t n) {
   return FL_OK;
 }
 #define TRY(x) do { int rc__ = (x); if (rc__ != FL_OK) return rc__; } while (0)
+// temporary device buffers of one call (debug, conversion and training entry points - never the per-frame path): freed on every exit path
+struct dev_buf {
+  std::vector<void*> p;
+  ~dev_buf() { for (void* q : p) cudaFree(q); }
+  template <typename T> int get(T** out, size_t n) { int rc = dalloc(out, n); if (rc == FL_OK) p.push_back(*out); return rc; }
+};
 
 extern "C" void fl_default_params(fl_params_t* p) {
   memset(p, 0, sizeof *p);
@@ -974,11 +980,6 @@ void select_scattered(const std::vector<train_cand>& cands, std::vector<fl_featu
     if (++i == (int)cands.size()) { i = 0; distance -= 1.0f; distance_sq = distance * distance; }   // start over with a relaxed distance
   }
 }
-struct dev_buf {                                          // frees what a training call allocated, on every exit path
-  std::vector<void*> p;
-  ~dev_buf() { for (void* q : p) cudaFree(q); }
-  template <typename T> int get(T** out, size_t n) { int rc = dalloc(out, n); if (rc == FL_OK) p.push_back(*out); return rc; }
-};
 }  // namespace
 
 extern "C" int fl_add_template(fl_handle* h, const uint8_t* bgr, size_t bgr_stride, const uint16_t* depth, size_t depth_stride, const uint8_t* mask,
@@ -1282,14 +1283,13 @@ extern "C" int fl_resize_linear(fl_handle* h, const void* src, size_t src_stride
   TRY(resize_tables(h, sW, sH, W, H));
   TRY(resize_staging(h, (size_t)sW * sH));
   void* d_src = type == FL_IMG_8UC3 ? (void*)h->d_src_bgr : (void*)h->d_src_depth;
-  void* d_dst = nullptr;
-  FL_CUDA(cudaMalloc(&d_dst, (size_t)W * H * px));
+  uint8_t* d_dst = nullptr;
+  dev_buf tmp;
+  TRY(tmp.get(&d_dst, (size_t)W * H * px));
   FL_CUDA(cudaMemcpy2DAsync(d_src, (size_t)sW * px, src, src_stride, (size_t)sW * px, sH, cudaMemcpyHostToDevice, s));
   fl_launch_resize_linear(d_src, sW, sH, type, d_dst, W, H, h->rz, s); ++h->launches;
-  cudaError_t e = cudaMemcpyAsync(dst, d_dst, (size_t)W * H * px, cudaMemcpyDeviceToHost, s);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-  cudaFree(d_dst);
-  FL_CUDA(e);
+  FL_CUDA(cudaMemcpyAsync(dst, d_dst, (size_t)W * H * px, cudaMemcpyDeviceToHost, s));
+  FL_CUDA(cudaStreamSynchronize(s));
   FL_CUDA(cudaGetLastError());
   return FL_OK;
 }
@@ -1355,12 +1355,12 @@ extern "C" int fl_depth_to_3d(fl_handle* h, const uint16_t* depth, size_t depth_
   FL_CUDA(cudaSetDevice(h->p.device));
   size_t n = (size_t)W * H;
   uint16_t* d_d = nullptr; float* d_o = nullptr;
-  TRY(dalloc(&d_d, n)); TRY(dalloc(&d_o, n * 3));
+  dev_buf tmp;
+  TRY(tmp.get(&d_d, n)); TRY(tmp.get(&d_o, n * 3));
   FL_CUDA(cudaMemcpy2DAsync(d_d, (size_t)W * 2, depth, depth_stride, (size_t)W * 2, H, cudaMemcpyHostToDevice, h->stream));
   fl_launch_depth_to_3d(d_d, W, H, K, d_o, h->stream); ++h->launches;
   FL_CUDA(cudaMemcpyAsync(out3, d_o, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   FL_CUDA(cudaStreamSynchronize(h->stream));
-  cudaFree(d_d); cudaFree(d_o);
   return FL_OK;
 }
 

@@ -15,7 +15,7 @@ rc, _, q = h0.match(frames[0][0], frames[0][1], 75.0, want_quantized=True)
 ts = synth.make_templates(NT, W, H, T, seed=1, quantized=q, planted_fraction=0.01)
 dev = [(torch.from_numpy(b).cuda(), torch.from_numpy(d.view(np.int16)).cuda()) for b, d in frames]
 want = None
-for K in (1, 2, 3, 4):
+for K in (1, 2, 4, 6, 8):
     hs = [fb.Handle(T, (0, 1), W, H) for _ in range(K)]
     for h in hs: h.upload_templates(ts)
     N = 2000
