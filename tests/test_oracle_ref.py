@@ -401,3 +401,20 @@ def test_reference_add_template_runs_and_is_deterministic():
     assert rc2 == 0 and np.array_equal(hdr, hdr2) and np.array_equal(ft, ft2)
     tiny = ((((xx - 320) / 6.0) ** 2 + ((yy - 240) / 5.0) ** 2) <= 1.0).astype(np.uint8) * 255
     assert R.add_template(det, b, d, tiny)[0] == -1
+
+
+def test_training_fixture_is_what_the_reference_returns():
+    """tests/golden/train_vga.npz (oracle/make_train_golden.py) = the reference's own addTemplate on four synthetic views; the GPU test
+    compares fl_add_template with the fixture, so it also runs where oracle/_ref is not built."""
+    from fealess_b200 import synth
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "train_vga.npz"))
+    W, H = 640, 480
+    det = R.Detector((5, 8))
+    yy, xx = np.mgrid[0:H, 0:W]
+    for i, c in enumerate(g["cases"]):
+        b, d = synth.make_frame(W, H, int(c[0]))
+        mask = None if c[3] == 0 else ((((xx - c[1]) / c[3]) ** 2 + ((yy - c[2]) / c[4]) ** 2) <= 1.0).astype(np.uint8) * int(c[5])
+        rc, hdr, ft, bb = R.add_template(det, b, d, mask)
+        assert rc == int(g["rc%d" % i])
+        if rc >= 0:
+            assert np.array_equal(hdr, g["hdr%d" % i]) and np.array_equal(ft, g["ft%d" % i]) and np.array_equal(bb, g["bb%d" % i])
