@@ -48,7 +48,7 @@ EXPORTED_SYMBOLS = [
     "fl_profile", "fl_last_stage_ms", "fl_last_icp_ms",
     "fl_group_create", "fl_group_destroy", "fl_group_size", "fl_group_handle", "fl_group_upload_templates", "fl_group_match",
     "fl_match_async", "fl_set_blocking_wait", "fl_match_shard_exchange_async", "fl_pipe_create", "fl_pipe_destroy", "fl_pipe_depth", "fl_pipe_in_flight", "fl_pipe_handle", "fl_pipe_upload_templates",
-    "fl_pipe_submit", "fl_pipe_collect", "fl_pipe_match_batch", "fl_default_train_params", "fl_add_template",
+    "fl_pipe_submit", "fl_pipe_collect", "fl_pipe_match_batch", "fl_pipe_set_exchange", "fl_default_train_params", "fl_add_template",
 ]
 
 
@@ -639,6 +639,28 @@ class Pipe:
         pose = np.ascontiguousarray(tset.pose13, np.float32)
         _check(lib().fl_pipe_upload_templates(self._p, tset.n_templates, _p(hdr), _p(ft), ft.shape[0], _p(co), _p(pose)), "fl_pipe_upload_templates")
 
+    def set_template_ids(self, template_ids) -> None:
+        """fl_set_template_ids on every slot's handle (global per-class ids of a template shard)."""
+        ids = np.ascontiguousarray(template_ids, np.int32)
+        L = lib()
+        L.fl_pipe_handle.restype = C.c_void_p
+        for i in range(self.depth):
+            _check(L.fl_set_template_ids(C.c_void_p(L.fl_pipe_handle(self._p, i)), _p(ids)), "fl_set_template_ids")
+
+    def set_exchange(self, rank: int, world: int, capacity: int, peer_buffers: Sequence[Sequence[int]], local_blocks: Sequence[int]) -> None:
+        """fl_pipe_set_exchange: ``peer_buffers[i][r]`` = address of rank r's exchange buffer of slot i in this process,
+        ``local_blocks[i]`` = slot i's candidate block (device memory, capacity + 1 records)."""
+        flat = [int(peer_buffers[i][r]) for i in range(self.depth) for r in range(world)]
+        pa = (C.c_void_p * len(flat))(*flat)
+        ba = (C.c_void_p * self.depth)(*[int(b) for b in local_blocks])
+        _check(lib().fl_pipe_set_exchange(self._p, int(rank), int(world), int(capacity), pa, ba), "fl_pipe_set_exchange")
+
+    def launch_count(self) -> int:
+        L = lib()
+        L.fl_pipe_handle.restype = C.c_void_p
+        L.fl_launch_count.restype = C.c_int64
+        return sum(int(L.fl_launch_count(C.c_void_p(L.fl_pipe_handle(self._p, i)))) for i in range(self.depth))
+
     def submit(self, bgr, depth, threshold: float, class_filter=None) -> None:
         """Host frame (numpy arrays; page-locked ones are read by DMA while in flight)."""
         H, W = (depth if depth is not None else bgr).shape[:2]
@@ -668,8 +690,9 @@ class Pipe:
         m = out[:min(cnt.value, capacity)]
         return rc, (m.copy() if copy else m)
 
-    def match_batch(self, frames, threshold: float, class_filter=None, capacity_per_frame: int = 1 << 12):
-        """``frames``: sequence of (bgr, depth) numpy pairs of one geometry.  Returns (rc, [matches per frame])."""
+    def match_batch(self, frames, threshold: float, class_filter=None, capacity_per_frame: int = 1 << 12, out=None, copy: bool = True):
+        """``frames``: sequence of (bgr, depth) numpy pairs of one geometry.  Returns (rc, [matches per frame]).  ``out`` (optional):
+        a reusable MATCH_DTYPE array of at least len(frames) * capacity_per_frame records; ``copy=False`` returns views into it."""
         n = len(frames)
         if n == 0:
             return FL_OK, []
@@ -678,14 +701,18 @@ class Pipe:
         ds = [np.ascontiguousarray(f[1], np.uint16) for f in frames]
         pb = (C.c_void_p * n)(*[x.ctypes.data for x in bs])
         pd = (C.c_void_p * n)(*[x.ctypes.data for x in ds])
-        out = np.zeros(n * capacity_per_frame, MATCH_DTYPE)
+        if out is None:
+            out = np.zeros(n * capacity_per_frame, MATCH_DTYPE)
+        elif out.dtype != MATCH_DTYPE or out.size < n * capacity_per_frame or not out.flags.c_contiguous:
+            raise ValueError("match_batch: `out` must be a contiguous MATCH_DTYPE array of at least len(frames) * capacity_per_frame records")
         counts = np.zeros(n, np.int32)
         cf = None if not class_filter else np.ascontiguousarray(class_filter, np.int32)
         rc = lib().fl_pipe_match_batch(self._p, n, pb, C.c_size_t(W * 3), pd, C.c_size_t(W * 2), W, H, C.c_float(threshold), _p(cf), 0 if cf is None else int(cf.size), 0,
                                        _p(out), capacity_per_frame, _p(counts))
         if rc not in (FL_OK, FL_ERR_CAPACITY):
             _check(rc, "fl_pipe_match_batch")
-        return rc, [out[f * capacity_per_frame:f * capacity_per_frame + min(int(counts[f]), capacity_per_frame)].copy() for f in range(n)]
+        views = [out[f * capacity_per_frame:f * capacity_per_frame + min(int(counts[f]), capacity_per_frame)] for f in range(n)]
+        return rc, ([v.copy() for v in views] if copy else views)
 
 
 # --------------------------------------------------------------------------------------------------

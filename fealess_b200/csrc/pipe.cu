@@ -14,6 +14,12 @@ struct fl_pipe {
   int depth, device;
   std::vector<fl_handle*> h;
   long long submitted, collected;
+  // template-sharded mode (fl_pipe_set_exchange): this pipe is rank `rank` of `world`; slot i owns exchange buffers peers[i * world ..]
+  // and the candidate block blocks[i]; its frames carry the epochs 1, 2, 3 ... of that slot
+  int rank, world, xcap;
+  std::vector<void*> peers;
+  std::vector<fl_match_t*> blocks;
+  std::vector<uint32_t> epoch;
 };
 
 extern "C" int fl_pipe_destroy(fl_pipe* p) {
@@ -27,7 +33,7 @@ extern "C" int fl_pipe_create(const fl_params_t* params, int32_t depth, fl_pipe*
   if (!params || !out || depth < 1 || depth > FL_PIPE_MAX_DEPTH) return FL_ERR_ARG;
   *out = nullptr;
   fl_pipe* p = new fl_pipe;
-  p->depth = depth; p->device = params->device; p->submitted = p->collected = 0;
+  p->depth = depth; p->device = params->device; p->submitted = p->collected = 0; p->rank = 0; p->world = 1; p->xcap = 0;
   p->h.assign(depth, nullptr);
   for (int i = 0; i < depth; ++i) {
     const int rc = fl_create(params, &p->h[i]);
@@ -52,14 +58,41 @@ extern "C" int fl_pipe_upload_templates(fl_pipe* p, int32_t n_templates, const f
   return FL_OK;
 }
 
+// Template-sharded pipe: every rank (process or fl_pipe) of a `world`-way sharded detector calls this once, after uploading its shard
+// (fl_pipe_upload_templates) and its global template ids (fl_set_template_ids on fl_pipe_handle(p, i)).  peer_buffers: depth x world
+// pointers - entry [i * world + r] is rank r's exchange buffer OF SLOT i as mapped into this process (fl_exchange_buffer_bytes each,
+// zeroed once); local_blocks: depth device blocks of exchange_capacity + 1 records.  From then on fl_pipe_submit runs
+// fl_match_shard_exchange_(device_)async: all ranks have to submit the same sequence of frames.
+extern "C" int fl_pipe_set_exchange(fl_pipe* p, int32_t rank, int32_t world, int32_t exchange_capacity, void* const* peer_buffers, fl_match_t* const* local_blocks) {
+  if (!p || world < 1 || rank < 0 || rank >= world || exchange_capacity < 1 || !peer_buffers || !local_blocks) return FL_ERR_ARG;
+  if (p->submitted != p->collected) { fl_set_error("fl_pipe_set_exchange: %lld frame(s) still in flight", p->submitted - p->collected); return FL_ERR_STATE; }
+  for (int i = 0; i < p->depth; ++i) {
+    if (!local_blocks[i]) return FL_ERR_ARG;
+    for (int r = 0; r < world; ++r) if (!peer_buffers[(size_t)i * world + r]) return FL_ERR_ARG;
+  }
+  p->rank = rank; p->world = world; p->xcap = exchange_capacity;
+  p->peers.assign(peer_buffers, peer_buffers + (size_t)p->depth * world);
+  p->blocks.assign(local_blocks, local_blocks + p->depth);
+  p->epoch.assign(p->depth, 0u);
+  return FL_OK;
+}
+
 extern "C" int fl_pipe_submit(fl_pipe* p, const void* bgr, size_t bgr_stride, const void* depth, size_t depth_stride, int32_t W, int32_t H, float threshold,
                               const int32_t* class_filter, int32_t n_filter, int32_t on_device) {
   if (!p || (!bgr && !depth)) return FL_ERR_ARG;
   if (p->submitted - p->collected >= p->depth) { fl_set_error("fl_pipe_submit: %d frames in flight already - collect one first", p->depth); return FL_ERR_STATE; }
-  fl_handle* h = p->h[p->submitted % p->depth];
+  const int slot = (int)(p->submitted % p->depth);
+  fl_handle* h = p->h[slot];
+  if (on_device && ((bgr && bgr_stride != (size_t)W * 3) || (depth && depth_stride != (size_t)W * 2))) { fl_set_error("fl_pipe_submit: device frames must have dense rows"); return FL_ERR_SIZE; }
   int rc;
-  if (on_device) {
-    if ((bgr && bgr_stride != (size_t)W * 3) || (depth && depth_stride != (size_t)W * 2)) { fl_set_error("fl_pipe_submit: device frames must have dense rows"); return FL_ERR_SIZE; }
+  if (p->world > 1) {                                           // template-sharded: local match + peer-memory exchange + merge, one enqueue
+    void* const* peers = p->peers.data() + (size_t)slot * p->world;
+    const uint32_t e = p->epoch[slot] + 1;
+    rc = on_device ? fl_match_shard_exchange_device_async(h, bgr, depth, W, H, threshold, class_filter, n_filter, p->rank, p->world, peers, p->xcap, p->blocks[slot], e)
+                   : fl_match_shard_exchange_async(h, static_cast<const uint8_t*>(bgr), bgr_stride, static_cast<const uint16_t*>(depth), depth_stride, W, H, threshold,
+                                                   class_filter, n_filter, p->rank, p->world, peers, p->xcap, p->blocks[slot], e);
+    if (rc == FL_OK) p->epoch[slot] = e;
+  } else if (on_device) {
     rc = fl_match_device_async(h, bgr, depth, W, H, nullptr, threshold, class_filter, n_filter);
   } else {
     rc = fl_match_async(h, static_cast<const uint8_t*>(bgr), bgr_stride, static_cast<const uint16_t*>(depth), depth_stride, W, H, nullptr, threshold, class_filter, n_filter);

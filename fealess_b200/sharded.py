@@ -265,6 +265,50 @@ class ShardedPipe:
             s.close()
 
 
+class NativeShardedPipe:
+    """The same schedule as ``ShardedPipe`` with the per-frame host work inside the library: one ``fl_pipe`` per rank in template-sharded
+    mode (``fl_pipe_set_exchange``).  torch only provides the symmetric-memory exchange buffers (one per slot, mapped into every process)
+    and the rendezvous; ``match_batch`` is ONE C call for any number of frames.  Peer-memory exchange only."""
+
+    def __init__(self, tset, rank: int, world: int, depth: int = 4, capacity: int = 2048, device=None, T=(5, 8), modality_kind=(0, 1),
+                 max_width: int = 640, max_height: int = 480, max_candidates: int = 1 << 16):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import Pipe, lib
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.rank, self.world, self.depth, self.cap = rank, world, int(depth), capacity
+        self.pipe = Pipe(self.depth, T, modality_kind, max_width, max_height, device=dev.index or 0,
+                         max_candidates=max(max_candidates, world * (capacity + 1) + 16))
+        shard, gids = shard_template_set(tset, rank, world)
+        self.pipe.upload_templates(shard)
+        if shard.n_templates:
+            self.pipe.set_template_ids(gids)
+        self.n_local = shard.n_templates
+        nbytes = int(lib().fl_exchange_buffer_bytes(world, capacity))
+        self._xbufs, self._xhdls, peers = [], [], []
+        for _ in range(self.depth):
+            xb = symm_mem.empty(nbytes, dtype=torch.uint8, device=dev)
+            xh = symm_mem.rendezvous(xb, dist.group.WORLD)
+            xb.zero_()
+            self._xbufs.append(xb); self._xhdls.append(xh)
+            peers.append([int(p) for p in xh.buffer_ptrs])
+        self._blocks = [torch.zeros(block_ints(capacity), dtype=torch.int32, device=dev) for _ in range(self.depth)]
+        torch.cuda.synchronize()
+        dist.barrier()
+        self.pipe.set_exchange(rank, world, capacity, peers, [b.data_ptr() for b in self._blocks])
+        self.exchange = "p2p"
+
+    def match_batch(self, frames, threshold: float, capacity_per_frame: int = 1 << 12, out=None, copy: bool = True):
+        return self.pipe.match_batch(frames, threshold, capacity_per_frame=capacity_per_frame, out=out, copy=copy)
+
+    def close(self) -> None:
+        import torch
+        torch.cuda.synchronize()
+        self.pipe.close()                                          # (the exchange buffers are only ever touched through raw pointers)
+        self._blocks = self._xbufs = self._xhdls = None
+
+
 # ---------------------------------------------------------------------------------------------------
 # Hypothesis-sharded pose refinement (SURVEY.md 8e: "ICP hypotheses are dealt across GPUs; small all-gather of the refined
 # poses before NMS").  After the candidate exchange every rank holds the SAME sorted match list, so hypothesis k of the top-K

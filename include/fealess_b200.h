@@ -123,7 +123,8 @@ int fl_get_pose_info(fl_handle* h, int32_t class_idx, int32_t template_id, float
  * modalities (mask nullable; 8UC1, nonzero = object).  headers: n_levels * n_modalities entries (index level * n_modalities + modality),
  * feature_begin pointing into `features` (at most feature_capacity; 63 per entry by default).  The result is what the reference's
  * addTemplate stores (bit-exact; tests/test_gpu_train.py) and can be handed to fl_upload_templates as it is.
- * FL_ERR_TRAIN: too few candidates on some level (the reference returns -1 and adds nothing). */
+ * FL_ERR_TRAIN: too few candidates on some level (the reference returns -1 and adds nothing).  The view goes through the handle's front
+ * end, so its size has to satisfy the matching geometry (W, H divisible by T at every level: FL_ERR_GEOMETRY otherwise). */
 typedef struct {
   int32_t num_features[FL_MAX_MODALITIES];  /* per modality at level 0, halved per level; default 63 (:518, :830) */
   float   strong_threshold;                 /* ColorGradient: 55 (:519) */
@@ -188,6 +189,13 @@ int32_t fl_pipe_in_flight(const fl_pipe* p);
 fl_handle* fl_pipe_handle(fl_pipe* p, int32_t i);
 int fl_pipe_upload_templates(fl_pipe* p, int32_t n_templates, const fl_template_hdr_t* headers, const fl_feature_t* features,
                              int32_t n_features, const int32_t* class_of, const float* pose13);   /* layout of fl_upload_templates */
+/* Template-sharded pipe (rank `rank` of `world`): after the shard has been uploaded (fl_pipe_upload_templates + fl_set_template_ids on
+ * every fl_pipe_handle), hand over the exchange buffers - peer_buffers[i * world + r] = rank r's buffer of slot i as mapped into this
+ * process (fl_exchange_buffer_bytes(world, capacity) each, zeroed once), local_blocks[i] = slot i's candidate block (capacity + 1
+ * records, device memory).  fl_pipe_submit / fl_pipe_match_batch then run the fused match + exchange per frame; every rank has to
+ * submit the same sequence of frames.  With this a rank's per-frame host work is inside the library (no Python / caller loop). */
+int fl_pipe_set_exchange(fl_pipe* p, int32_t rank, int32_t world, int32_t exchange_capacity, void* const* peer_buffers,
+                         fl_match_t* const* local_blocks);
 int fl_pipe_submit(fl_pipe* p, const void* bgr, size_t bgr_stride, const void* depth, size_t depth_stride, int32_t W, int32_t H,
                    float threshold, const int32_t* class_filter, int32_t n_filter, int32_t on_device);
 int fl_pipe_collect(fl_pipe* p, fl_match_t* out, int32_t capacity, int32_t* count);

@@ -109,3 +109,40 @@ def test_blocking_wait_gives_the_same_lists(stream_case):
     rc, got = h.match(*frames[2], 70.0)
     assert rc == 0 and np.array_equal(got, want[2])
     h.close()
+
+
+def test_template_sharded_pipes_on_one_gpu(stream_case):
+    """fl_pipe_set_exchange: two pipes = the two ranks of a template-sharded detector, both on this GPU, exchange buffers in plain device
+    memory; driven in lock-step from one thread, every frame's merged list on both ranks equals the single detector's."""
+    import torch
+    from fealess_b200 import sharded
+    frames, ts, want = stream_case
+    world, depth, cap = 2, 3, 1024
+    nbytes = int(fb.lib().fl_exchange_buffer_bytes(world, cap))
+    xbuf = [[torch.zeros(nbytes, dtype=torch.uint8, device="cuda") for _ in range(world)] for _ in range(depth)]     # [slot][rank]
+    blocks = [[torch.zeros(sharded.block_ints(cap), dtype=torch.int32, device="cuda") for _ in range(depth)] for _ in range(world)]
+    pipes = []
+    for r in range(world):
+        p = fb.Pipe(depth, T, (0, 1), W, H)
+        shard, gids = sharded.shard_template_set(ts, r, world)
+        p.upload_templates(shard)
+        p.set_template_ids(gids)
+        p.set_exchange(r, world, cap, [[xbuf[i][q].data_ptr() for q in range(world)] for i in range(depth)], [b.data_ptr() for b in blocks[r]])
+        pipes.append(p)
+    torch.cuda.synchronize()
+    n, got = 14, [[], []]
+    for i in range(n):
+        if pipes[0].in_flight() == depth:
+            for r in range(world):
+                got[r].append(pipes[r].collect())
+        for r in range(world):                                   # both ranks submit frame i before either is waited for
+            pipes[r].submit(*frames[i % 5], 70.0)
+    while pipes[0].in_flight():
+        for r in range(world):
+            got[r].append(pipes[r].collect())
+    for r in range(world):
+        assert len(got[r]) == n
+        for i, (rc, m) in enumerate(got[r]):
+            assert rc == 0 and np.array_equal(m, want[i % 5]), (r, i)
+    for p in pipes:
+        p.close()
