@@ -49,6 +49,20 @@ METRIC = "template.px evals/s (LINE-MOD match, 640x480, 8k templates/GPU)"
 WORKLOAD = "C2: LINE-MOD match-only, 640x480, %d templates per GPU, L=2, T={5,8}, threshold 75"   # same string in both arms
 
 
+def host_info():
+    """nproc and CPU model of the box the CPU legs run on."""
+    model = ""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.lower().startswith("model name"):
+                    model = ln.split(":", 1)[1].strip()
+                    break
+    except Exception:  # noqa: BLE001
+        pass
+    return {"nproc": os.cpu_count() or 1, "cpu_model": model}
+
+
 def load_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -218,7 +232,7 @@ def run_reference(args):
             "ms_per_step_p95": 1e3 * float(np.percentile(times, 95)), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": WORKLOAD % args.templates, "frames_per_s": steps / tot, "matches_last_frame": n_matches},
-            "cpu_baseline": {"value": v, "unit": "evals/s", "cores": cores, "kind": kind, "sample": sample,
+            "cpu_baseline": {"value": v, "unit": "evals/s", "cores": cores, "kind": kind, "sample": sample, "host": host_info(),
                              "port_all_cores": {"value": port_all, "unit": "evals/s", "cores": cores_all,
                                                 "note": "C restatement with OpenMP over templates on every host core - not the reference's execution model"}},
             "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -584,7 +598,7 @@ def run_ours(args):
             ct, _ = cpu_time_frames(frames, tset, 1, 8, 2)
             kind, sample = "port", "8 whole frames (after 2 warm-up) of the same workload, all %d templates, single thread (oracle/_ref not in this checkout)" % args.templates
         cv = args.templates * CELLS * len(ct) / float(np.sum(ct))
-        cpu = {"value": cv, "unit": "evals/s", "cores": 1, "kind": kind, "frames_per_s": len(ct) / float(np.sum(ct)), "sample": sample}
+        cpu = {"value": cv, "unit": "evals/s", "cores": 1, "kind": kind, "frames_per_s": len(ct) / float(np.sum(ct)), "sample": sample, "host": host_info()}
 
     # ---- ICP (BASELINE configs[2], C3): 256 hypotheses x ~10k points, reported beside the headline ----
     icp = None
@@ -603,6 +617,7 @@ def run_ours(args):
                        "timed_region": "exactly `steps` frames of a running stream with `frames_in_flight` frames in flight per GPU; start event in front of the "
                                        "first timed frame on its stream, end event after the last list has been collected; max over ranks",
                        "frames_per_s": args.steps / (dev_ms * 1e-3),
+                       "full_resolution_equivalent_evals_per_s": value * (W * H) / CELLS,     # N_templates x W0 x H0 per frame, NOT the headline unit
                        "matches_last_frame": n_matches, "match_list_frame0": {"records": int(len(want0)), "sha256_16": list_sha,
                                                                               "equals_cpu_arm": True}, "parallelism": ("template-sharded x%d, candidate exchange: %s" % (world, "peer-memory push fused into the sort kernel (NVLink)" if sm.exchange == "p2p" else "1 NCCL all-gather/frame")) if world > 1 else "single GPU"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
