@@ -44,6 +44,12 @@ def test_no_cpu_fallback_without_gpu():
     assert e.value.rc == fb.FL_ERR_CUDA
     with pytest.raises(fb.FealessError):
         fb.icpCloudToCloud_Ex(np.zeros((10, 3), np.float32), np.zeros((10, 3), np.float32))
+    with pytest.raises(fb.FealessError) as e:                 # frames in flight / several GPUs: the same, no device -> no object
+        fb.Pipe(2)
+    assert e.value.rc == fb.FL_ERR_CUDA
+    with pytest.raises(fb.FealessError) as e:
+        fb.Group([0, 0])
+    assert e.value.rc == fb.FL_ERR_CUDA
 
 
 def test_product_package_does_not_import_the_oracle():
@@ -51,7 +57,7 @@ def test_product_package_does_not_import_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".cpp")):
                 txt = open(os.path.join(root, f), errors="replace").read()
-                assert "fl_oracle" not in txt and "oracle_cv2" not in txt, "%s references the oracle" % f
+                assert "fl_oracle" not in txt and "oracle_cv2" not in txt and "fl_ref_py" not in txt and "libfl_ref" not in txt, "%s references the oracle" % f
 
 
 def test_detector_argument_errors_mirror_the_reference():
