@@ -278,22 +278,34 @@ class NativeShardedPipe:
         from . import Pipe, lib
         dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.rank, self.world, self.depth, self.cap = rank, world, int(depth), capacity
-        self.pipe = Pipe(self.depth, T, modality_kind, max_width, max_height, device=dev.index or 0,
-                         max_candidates=max(max_candidates, world * (capacity + 1) + 16))
-        shard, gids = shard_template_set(tset, rank, world)
-        self.pipe.upload_templates(shard)
-        if shard.n_templates:
-            self.pipe.set_template_ids(gids)
-        self.n_local = shard.n_templates
-        nbytes = int(lib().fl_exchange_buffer_bytes(world, capacity))
-        self._xbufs, self._xhdls, peers = [], [], []
-        for _ in range(self.depth):
-            xb = symm_mem.empty(nbytes, dtype=torch.uint8, device=dev)
+        # Everything that can fail on ONE rank alone (device allocations, the template upload) happens before the first collective, and
+        # the ranks agree on the outcome: a rank that failed must not leave its peers waiting inside the rendezvous that follows.
+        self.pipe, self._xbufs, self._xhdls, self._blocks, err = None, [], [], [], None
+        try:
+            self.pipe = Pipe(self.depth, T, modality_kind, max_width, max_height, device=dev.index or 0,
+                             max_candidates=max(max_candidates, world * (capacity + 1) + 16))
+            shard, gids = shard_template_set(tset, rank, world)
+            self.pipe.upload_templates(shard)
+            if shard.n_templates:
+                self.pipe.set_template_ids(gids)
+            self.n_local = shard.n_templates
+            nbytes = int(lib().fl_exchange_buffer_bytes(world, capacity))
+            self._xbufs = [symm_mem.empty(nbytes, dtype=torch.uint8, device=dev) for _ in range(self.depth)]
+            self._blocks = [torch.zeros(block_ints(capacity), dtype=torch.int32, device=dev) for _ in range(self.depth)]
+        except Exception as e:  # noqa: BLE001
+            err = e
+        flag = torch.tensor([0 if err else 1], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            if self.pipe is not None:
+                self.pipe.close()
+            raise RuntimeError("NativeShardedPipe: set-up failed on %s: %r" % ("this rank" if err else "another rank", err))
+        peers = []
+        for xb in self._xbufs:
             xh = symm_mem.rendezvous(xb, dist.group.WORLD)
             xb.zero_()
-            self._xbufs.append(xb); self._xhdls.append(xh)
+            self._xhdls.append(xh)
             peers.append([int(p) for p in xh.buffer_ptrs])
-        self._blocks = [torch.zeros(block_ints(capacity), dtype=torch.int32, device=dev) for _ in range(self.depth)]
         torch.cuda.synchronize()
         dist.barrier()
         self.pipe.set_exchange(rank, world, capacity, peers, [b.data_ptr() for b in self._blocks])
