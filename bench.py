@@ -663,6 +663,37 @@ def run_ours(args):
             hf.close()
         except Exception as e:  # noqa: BLE001
             line["roofline_front_end_1080p"] = {"error": "%s: %s" % (type(e).__name__, e)}
+    if world == 1 and not args.no_icp:
+        try:                                                    # template training, one view -> one template pyramid
+            yy, xx = np.mgrid[0:H, 0:W]
+            tmask = ((((xx - 320) / 110.0) ** 2 + ((yy - 240) / 80.0) ** 2) <= 1.0).astype(np.uint8) * 255
+            ht = fb.Handle(T, (0, 1), W, H, device=local)
+            rct, hdr_t, ft_t, bb_t = ht.add_template(frames[0][0], frames[0][1], tmask)
+            n_views = 20
+            tt0 = time.perf_counter()
+            for i in range(n_views):
+                rct, hdr_t, ft_t, bb_t = ht.add_template(frames[0][0], frames[0][1], tmask)
+            tt1 = time.perf_counter()
+            ht.close()
+            tr = {"workload": "Detector::addTemplate on one 640x480 RGB-D view with an elliptic object mask (63 + 63 + 31 + 31 features)",
+                  "views_per_s": n_views / (tt1 - tt0), "ms_per_view": 1e3 * (tt1 - tt0) / n_views, "status": int(rct), "features": int(len(ft_t)),
+                  "timer": "host wall clock around fl_add_template (upload, front end, magnitude / erosion / distance-transform kernels, candidate "
+                           "read-back, host-side stable sort + scattered selection)"}
+            if not args.no_cpu:
+                import fl_ref_py as R
+                if R.available():
+                    rdet = R.Detector(T)
+                    R.add_template(rdet, frames[0][0], frames[0][1], tmask)
+                    tc0 = time.perf_counter()
+                    for i in range(3):
+                        rrc, rhdr, rft, rbb = R.add_template(rdet, frames[0][0], frames[0][1], tmask)
+                    tc1 = time.perf_counter()
+                    tr["cpu_baseline"] = {"views_per_s": 3 / (tc1 - tc0), "cores": 1, "kind": "reference",
+                                          "sample": "3 views through the reference's own addTemplate (oracle/_ref)",
+                                          "identical_result": bool(rrc >= 0 and rct == 0 and np.array_equal(rhdr, hdr_t) and np.array_equal(rft, ft_t) and np.array_equal(rbb, bb_t))}
+            line["training"] = tr
+        except Exception as e:  # noqa: BLE001
+            line["training"] = {"error": "%s: %s" % (type(e).__name__, e)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

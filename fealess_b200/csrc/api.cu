@@ -76,6 +76,7 @@ struct fl_handle {
   int in_depth_W, in_depth_H;
   int32_t* d_nms; int nms_cap;   // fl_nms workspace (hypotheses)
   bool blocking_wait; cudaEvent_t ev_block;   // fl_set_blocking_wait
+  uint8_t* d_train;                           // fl_add_template workspace (allocated at the first call)
   // input rescale: device tables of the current (source -> destination) geometry, source-frame staging
   fl_resize_tables rz; int rz_sW, rz_sH, rz_dW, rz_dH;
   uint8_t* d_src_bgr; uint16_t* d_src_depth; size_t src_cap;
@@ -154,7 +155,7 @@ extern "C" int fl_create(const fl_params_t* params, fl_handle** out) {
   memset(&h->rz, 0, sizeof h->rz); h->rz_sW = h->rz_sH = h->rz_dW = h->rz_dH = 0;
   h->d_src_bgr = nullptr; h->d_src_depth = nullptr; h->src_cap = 0;
   memset(h->d_bgr, 0, sizeof h->d_bgr); memset(h->d_q, 0, sizeof h->d_q); memset(h->d_qm, 0, sizeof h->d_qm);
-  memset(h->d_mask, 0, sizeof h->d_mask); memset(h->d_spread, 0, sizeof h->d_spread); memset(h->d_lm, 0, sizeof h->d_lm); h->d_lm4 = nullptr; h->d_nms = nullptr; h->nms_cap = 0; h->blocking_wait = false; h->ev_block = nullptr;
+  memset(h->d_mask, 0, sizeof h->d_mask); memset(h->d_spread, 0, sizeof h->d_spread); memset(h->d_lm, 0, sizeof h->d_lm); h->d_lm4 = nullptr; h->d_nms = nullptr; h->nms_cap = 0; h->blocking_wait = false; h->ev_block = nullptr; h->d_train = nullptr;
   memset(h->used_mask, 0, sizeof h->used_mask); memset(h->stage_ms, 0, sizeof h->stage_ms); h->icp_ms = 0.f;
   *out = h;
   FL_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -228,7 +229,7 @@ extern "C" int fl_destroy(fl_handle* h) {
   cudaSetDevice(h->p.device);
   cudaStreamSynchronize(h->stream);
   free_templates(h); icp_free(h);
-  cudaFree(h->d_ref_depth); cudaFree(h->d_resident); cudaFree(h->d_nms); if (h->ev_block) cudaEventDestroy(h->ev_block);
+  cudaFree(h->d_ref_depth); cudaFree(h->d_resident); cudaFree(h->d_nms); cudaFree(h->d_train); if (h->ev_block) cudaEventDestroy(h->ev_block);
   cudaFree(h->rz.xofs); cudaFree(h->rz.yofs); cudaFree(h->rz.ialpha); cudaFree(h->rz.ibeta); cudaFree(h->rz.alpha); cudaFree(h->rz.beta);
   cudaFree(h->d_src_bgr); cudaFree(h->d_src_depth);
   cudaFree(h->d_in_bgr); cudaFree(h->d_in_depth); cudaFree(h->d_geom);
@@ -997,13 +998,24 @@ extern "C" int fl_add_template(fl_handle* h, const uint8_t* bgr, size_t bgr_stri
   TRY(fl_match_async(h, bgr, bgr_stride, depth, depth_stride, W, H, nullptr, 200.f, nullptr, 0));
   TRY(fl_match_wait(h));
   cudaStream_t s = h->stream;
-  dev_buf tmp;
   const size_t npx = (size_t)W * H;
-  float* d_mag; float* d_score; uint8_t* d_er1; uint8_t* d_er2; uint16_t* d_hd; int* d_cnt; uint8_t* d_maskpyr = nullptr;
-  TRY(tmp.get(&d_mag, npx)); TRY(tmp.get(&d_score, npx)); TRY(tmp.get(&d_er1, npx)); TRY(tmp.get(&d_er2, npx)); TRY(tmp.get(&d_hd, 8 * npx)); TRY(tmp.get(&d_cnt, 16));
+  // training workspace of the handle: one block sized for the largest frame, allocated at the first call (a database generator calls
+  // this thousands of times; a malloc / free round per view cost more than the kernels)
+  if (!h->d_train) {
+    const size_t cap = (size_t)p.max_width * p.max_height;
+    TRY(dalloc(&h->d_train, cap * (4 + 4 + 1 + 1 + 16 + 2) + 256));
+  }
+  uint8_t* base = h->d_train;
+  const size_t cap_px = (size_t)p.max_width * p.max_height;
+  float* d_mag = reinterpret_cast<float*>(base); base += cap_px * 4;
+  float* d_score = reinterpret_cast<float*>(base); base += cap_px * 4;
+  uint16_t* d_hd = reinterpret_cast<uint16_t*>(base); base += cap_px * 16;
+  int* d_cnt = reinterpret_cast<int*>(base); base += 256;
+  uint8_t* d_er1 = base; base += cap_px;
+  uint8_t* d_er2 = base; base += cap_px;
+  uint8_t* d_maskpyr = base;
   std::vector<const uint8_t*> d_mask(L, nullptr);
   if (mask) {
-    TRY(tmp.get(&d_maskpyr, 2 * npx));
     FL_CUDA(cudaMemcpy2DAsync(d_maskpyr, W, mask, mask_stride, W, H, cudaMemcpyHostToDevice, s));
     d_mask[0] = d_maskpyr;
     size_t off = npx;
@@ -1565,7 +1577,7 @@ extern "C" int fl_nms_ex(fl_handle* h, const float* t3, const int32_t* n_model_p
   // handles' frames in flight on the same GPU that serialises them, and a kernel of theirs that is waiting for a peer rank's
   // block turns it into a cross-rank stall until the exchange times out
   if (h->nms_cap < n) {
-    cudaFree(h->d_nms); h->d_nms = nullptr; h->nms_cap = 0; h->blocking_wait = false; h->ev_block = nullptr;
+    cudaFree(h->d_nms); h->d_nms = nullptr; h->nms_cap = 0; h->blocking_wait = false; h->ev_block = nullptr; h->d_train = nullptr;
     const int cap = std::max(64, 2 * n);
     TRY(dalloc(&h->d_nms, (size_t)cap * 7 + 2));
     h->nms_cap = cap;
