@@ -7,6 +7,9 @@
 // candidate and result blocks), deals the submitted frames round-robin and hands the match lists back in submission order.  The GPU
 // runs the front end of frame i+1 in the SM slots the similarity kernel of frame i leaves free and under its tail; the upload of
 // frame i+1 and the result copy of frame i-1 ride on the copy engines meanwhile.  Nothing here synchronises more than one stream.
+// fl_pipe_set_exchange turns the pipe into ONE RANK of a template-sharded detector: every slot then runs the fused local match +
+// peer-memory exchange (fl_match_shard_exchange_*) with its own exchange buffers and epoch sequence, so a rank's whole per-frame host
+// loop - upload, enqueue, wait, fetch - lives in fl_pipe_match_batch.
 #include "fl_internal.cuh"
 #include <vector>
 
