@@ -948,3 +948,185 @@ int flo_nms(const float* t3, const int32_t* n_model_pts, const float* icp_dist, 
   free(done);
   return cnt;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* template training: Detector::addTemplate (linemod.cpp:1579-1615)                            */
+/* ------------------------------------------------------------------------------------------ */
+void flo_erode3_u8(const uint8_t* src, int W, int H, int iterations, uint8_t* dst) {
+  /* cv::erode, default 3x3 rectangle, BORDER_REPLICATE (linemod.cpp:466, 753) */
+  size_t n = (size_t)W * H;
+  uint8_t* cur = (uint8_t*)malloc(n); uint8_t* nxt = (uint8_t*)malloc(n);
+  memcpy(cur, src, n);
+  for (int it = 0; it < iterations; ++it) {
+    for (int y = 0; y < H; ++y)
+      for (int x = 0; x < W; ++x) {
+        int m = 255;
+        for (int j = -1; j <= 1; ++j) for (int i = -1; i <= 1; ++i) { int v = cur[(size_t)clampi(y + j, 0, H - 1) * W + clampi(x + i, 0, W - 1)]; if (v < m) m = v; }
+        nxt[(size_t)y * W + x] = (uint8_t)m;
+      }
+    uint8_t* t = cur; cur = nxt; nxt = t;
+  }
+  memcpy(dst, cur, n);
+  free(cur); free(nxt);
+}
+
+void flo_distance_c3(const uint8_t* src, int W, int H, float* dst) {
+  /* cv::distanceTransform(DIST_C, 3) (linemod.cpp:765): chessboard distance to the nearest zero pixel, as the exact two-pass 3x3
+   * chamfer with unit weights computes it; an image without a zero pixel gives 65535 (OpenCV 4.13's own code). */
+  size_t n = (size_t)W * H;
+  int any_zero = 0;
+  for (size_t i = 0; i < n; ++i) if (!src[i]) { any_zero = 1; break; }
+  if (!any_zero) { for (size_t i = 0; i < n; ++i) dst[i] = 65535.f; return; }
+  const int INF = 1 << 28;
+  int* t = (int*)malloc(sizeof(int) * n);
+  for (int y = 0; y < H; ++y)
+    for (int x = 0; x < W; ++x) {
+      int v = INF;
+      if (!src[(size_t)y * W + x]) v = 0;
+      else {
+        if (y > 0) { for (int i = -1; i <= 1; ++i) { int xx = x + i; if (xx >= 0 && xx < W) { int u = t[(size_t)(y - 1) * W + xx] + 1; if (u < v) v = u; } } }
+        if (x > 0) { int u = t[(size_t)y * W + x - 1] + 1; if (u < v) v = u; }
+      }
+      t[(size_t)y * W + x] = v;
+    }
+  for (int y = H - 1; y >= 0; --y)
+    for (int x = W - 1; x >= 0; --x) {
+      int v = t[(size_t)y * W + x];
+      if (y < H - 1) { for (int i = -1; i <= 1; ++i) { int xx = x + i; if (xx >= 0 && xx < W) { int u = t[(size_t)(y + 1) * W + xx] + 1; if (u < v) v = u; } } }
+      if (x < W - 1) { int u = t[(size_t)y * W + x + 1] + 1; if (u < v) v = u; }
+      t[(size_t)y * W + x] = v;
+      dst[(size_t)y * W + x] = (float)v;
+    }
+  free(t);
+}
+
+typedef struct { int x, y, label; float score; int order; } train_cand;
+static int cand_cmp(const void* a, const void* b) {
+  /* Candidate::operator< (linemod.hpp:124-128): higher score first; std::stable_sort keeps the row-major order among ties */
+  const train_cand* p = (const train_cand*)a; const train_cand* q = (const train_cand*)b;
+  if (p->score > q->score) return -1;
+  if (p->score < q->score) return 1;
+  return p->order - q->order;
+}
+/* QuantizedPyramid::selectScatteredFeatures (linemod.cpp:134-163); out = x, y, label triples */
+static void select_scattered(const train_cand* c, int n_cand, int32_t* out, int num_features, float distance) {
+  float distance_sq = distance * distance;
+  int n = 0, i = 0;
+  while (n < num_features) {
+    int keep = 1;
+    for (int j = 0; j < n && keep; ++j) {
+      int dx = c[i].x - out[3 * j], dy = c[i].y - out[3 * j + 1];
+      keep = (float)(dx * dx + dy * dy) >= distance_sq;
+    }
+    if (keep) { out[3 * n] = c[i].x; out[3 * n + 1] = c[i].y; out[3 * n + 2] = c[i].label; ++n; }
+    if (++i == n_cand) { i = 0; distance -= 1.0f; distance_sq = distance * distance; }
+  }
+}
+static int label_of(int q) { int l = 0; while (l < 7 && !(q & (1 << l))) ++l; return l; }
+
+int flo_add_template(const flo_detector* d, const uint8_t* bgr, const uint16_t* depth, const uint8_t* mask_or_null, int W, int H,
+                     const int* num_features_per_modality, float strong_threshold, int extract_threshold,
+                     int32_t* headers, int32_t* features, int feature_cap, int* n_features, int32_t bbox[4]) {
+  const int L = d->L, M = d->M;
+  *n_features = 0;
+  int32_t* sel = (int32_t*)malloc(sizeof(int32_t) * 3 * 64 * (size_t)L * M);   /* [L*M][<= 63][3] */
+  int* n_sel = (int*)calloc((size_t)L * M, sizeof(int));
+  int rc = 0;
+  for (int m = 0; m < M && rc == 0; ++m) {
+    int w = W, h = H;
+    uint8_t* cur_bgr = NULL; uint8_t* cur_q = NULL; uint8_t* cur_mask = NULL;
+    if (mask_or_null) { cur_mask = (uint8_t*)malloc((size_t)W * H); memcpy(cur_mask, mask_or_null, (size_t)W * H); }
+    size_t num_features = (size_t)num_features_per_modality[m];
+    int extract_thr = extract_threshold;
+    for (int l = 0; l < L && rc == 0; ++l) {
+      if (l > 0) {                                                  /* qp->pyrDown() (:1595-1596; :427-453, :721-739) */
+        int nw = w / 2, nh = h / 2;
+        num_features /= 2; extract_thr /= 2;
+        if (d->kind[m] == 0) { uint8_t* nb = (uint8_t*)malloc((size_t)nw * nh * 3); flo_pyrdown_bgr(cur_bgr ? cur_bgr : bgr, w, h, nb); free(cur_bgr); cur_bgr = nb; }
+        else { uint8_t* nq = (uint8_t*)malloc((size_t)nw * nh); flo_resize_nn_half_u8(cur_q, w, h, nq); free(cur_q); cur_q = nq; }
+        if (cur_mask) { uint8_t* nm = (uint8_t*)malloc((size_t)nw * nh); flo_resize_nn_half_u8(cur_mask, w, h, nm); free(cur_mask); cur_mask = nm; }
+        w = nw; h = nh;
+      }
+      const size_t n = (size_t)w * h;
+      train_cand* cand = (train_cand*)malloc(sizeof(train_cand) * n);
+      int nc = 0;
+      float distance = 0.f;
+      if (d->kind[m] == 0) {                                        /* ColorGradientPyramid::extractTemplate :461-513 */
+        uint8_t* q = (uint8_t*)malloc(n); float* mag = (float*)malloc(sizeof(float) * n);
+        flo_color_quantize(l == 0 ? bgr : cur_bgr, w, h, d->weak_thr, q, mag);
+        uint8_t* er = NULL;
+        if (cur_mask) { er = (uint8_t*)malloc(n); flo_erode3_u8(cur_mask, w, h, 1, er); }
+        const float thr_sq = strong_threshold * strong_threshold;
+        for (int y = 0; y < h; ++y) for (int x = 0; x < w; ++x) {
+          size_t i = (size_t)y * w + x;
+          if (cur_mask && !((int)cur_mask[i] - (int)er[i] > 0)) continue;      /* subtract(mask, erode(mask)) saturates */
+          if (q[i] > 0 && mag[i] > thr_sq) { cand[nc].x = x; cand[nc].y = y; cand[nc].label = label_of(q[i]); cand[nc].score = mag[i]; cand[nc].order = nc; ++nc; }
+        }
+        free(q); free(mag); free(er);
+        if ((size_t)nc < num_features) rc = -1;
+        else if (num_features) distance = (float)((size_t)nc / num_features + 1);
+      } else {                                                      /* DepthNormalPyramid::extractTemplate :747-825 */
+        if (l == 0) { cur_q = (uint8_t*)malloc(n); flo_depth_quantize(depth, w, h, d->dist_thr, d->diff_thr, cur_q); }
+        uint8_t* local = NULL;
+        if (cur_mask) { local = (uint8_t*)malloc(n); flo_erode3_u8(cur_mask, w, h, 2, local); }
+        float* dist8 = (float*)malloc(sizeof(float) * n * 8);
+        uint8_t* plane = (uint8_t*)malloc(n);
+        for (int lab = 0; lab < 8; ++lab) {
+          for (size_t i = 0; i < n; ++i) plane[i] = (uint8_t)(((!local || local[i]) ? (1 << lab) : 0) & cur_q[i]);
+          flo_distance_c3(plane, w, h, dist8 + (size_t)lab * n);
+        }
+        int counts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int y = 0; y < h; ++y) for (int x = 0; x < w; ++x) {
+          size_t i = (size_t)y * w + x;
+          if (local && !local[i]) continue;
+          int q = cur_q[i];
+          if (q == 0 || q == 255) continue;
+          int lab = label_of(q);
+          float sc = dist8[(size_t)lab * n + i];
+          if (sc >= (float)extract_thr) { cand[nc].x = x; cand[nc].y = y; cand[nc].label = lab; cand[nc].score = sc; cand[nc].order = nc; ++nc; ++counts[lab]; }
+        }
+        if ((size_t)nc < num_features) rc = -1;
+        else {
+          for (int i = 0; i < nc; ++i) cand[i].score /= (float)counts[cand[i].label];
+          size_t area = n;
+          if (local) { area = 0; for (size_t i = 0; i < n; ++i) area += local[i] != 0; }
+          if (num_features) distance = sqrtf((float)area) / sqrtf((float)num_features) + 1.5f;
+        }
+        free(local); free(dist8); free(plane);
+      }
+      if (rc == 0) {
+        qsort(cand, (size_t)nc, sizeof(train_cand), cand_cmp);
+        select_scattered(cand, nc, sel + (size_t)(l * M + m) * 3 * 64, (int)num_features, distance);
+        n_sel[l * M + m] = (int)num_features;
+      }
+      free(cand);
+    }
+    free(cur_bgr); free(cur_q); free(cur_mask);
+  }
+  if (rc == 0) {                                                    /* cropTemplates :52-96 */
+    int min_x = INT32_MAX, min_y = INT32_MAX, max_x = INT32_MIN, max_y = INT32_MIN;
+    for (int l = 0; l < L; ++l) for (int m = 0; m < M; ++m) for (int k = 0; k < n_sel[l * M + m]; ++k) {
+      const int32_t* f = sel + ((size_t)(l * M + m) * 64 + k) * 3;
+      int x = f[0] << l, y = f[1] << l;
+      if (x < min_x) min_x = x;
+      if (y < min_y) min_y = y;
+      if (x > max_x) max_x = x;
+      if (y > max_y) max_y = y;
+    }
+    if (min_x % 2 == 1) --min_x;
+    if (min_y % 2 == 1) --min_y;
+    int nf = 0;
+    for (int l = 0; l < L && rc == 0; ++l) for (int m = 0; m < M && rc == 0; ++m) {
+      int32_t* hd = headers + (size_t)(l * M + m) * 7;
+      hd[0] = (max_x - min_x) >> l; hd[1] = (max_y - min_y) >> l; hd[2] = min_x >> l; hd[3] = min_y >> l; hd[4] = l; hd[5] = nf; hd[6] = n_sel[l * M + m];
+      for (int k = 0; k < n_sel[l * M + m]; ++k, ++nf) {
+        if (nf >= feature_cap) { rc = -3; break; }
+        const int32_t* f = sel + ((size_t)(l * M + m) * 64 + k) * 3;
+        features[3 * nf] = f[0] - hd[2]; features[3 * nf + 1] = f[1] - hd[3]; features[3 * nf + 2] = f[2];
+      }
+    }
+    if (rc == 0) { *n_features = nf; bbox[0] = min_x; bbox[1] = min_y; bbox[2] = max_x - min_x; bbox[3] = max_y - min_y; }
+  }
+  free(sel); free(n_sel);
+  return rc;
+}

@@ -68,6 +68,16 @@ int flo_detector_similarity(const flo_detector* d, int template_idx, uint16_t* o
 int flo_detector_match_templates(const flo_detector* d, float threshold, const int32_t* class_filter, int n_filter,
                                  int canonical, int n_threads, flo_match_t* out, int cap, int* n_total);
 
+/* ---- template training: Detector::addTemplate (linemod.cpp:1579-1615; extractTemplate :461-513, :747-825; selectScatteredFeatures
+ * :134-163; cropTemplates :52-96) ---- */
+void flo_erode3_u8(const uint8_t* src, int W, int H, int iterations, uint8_t* dst);      /* cv::erode 3x3 BORDER_REPLICATE, :466, 753 */
+void flo_distance_c3(const uint8_t* src, int W, int H, float* dst);                      /* cv::distanceTransform(DIST_C, 3), :765 */
+/* one view -> one template pyramid (headers / features in the layout of flo_detector_set_templates, one template); num_features per
+ * modality at level 0 (default 63), strong_threshold 55, extract_threshold 2.  Returns 0, or -1 when a level has too few candidates. */
+int flo_add_template(const flo_detector* d, const uint8_t* bgr, const uint16_t* depth, const uint8_t* mask_or_null, int W, int H,
+                     const int* num_features_per_modality, float strong_threshold, int extract_threshold,
+                     int32_t* headers, int32_t* features, int feature_cap, int* n_features, int32_t bbox[4]);
+
 /* ---- ICP (ICP/depth_to_3d.cpp, common.cpp, ICP.cpp, detection.cpp, NMS.cpp) ---- */
 void flo_depth_to_3d_mm(const uint16_t* depth, int W, int H, float fx, float fy, float cx, float cy, float* out3);
 int flo_pair_points(const float* ref3, const float* mod3, int W, int H, const int rect_ref[4], const int rect_mod[4],

@@ -235,6 +235,42 @@ def icp_cloud_to_cloud_ex(pts_ref, pts_model, icp_it_thr=10, dist_mean_thr=0.5, 
     return res
 
 
+def add_template(det: "Detector", bgr, depth, mask=None, num_features=(63, 63, 63, 63), strong_threshold=55.0, extract_threshold=2,
+                 feature_cap: int = 4096):
+    """flo_add_template = Detector::addTemplate (linemod.cpp:1579-1615) on one view.  Returns (rc, headers[L*M, 7], features[n, 3],
+    bbox[4]); rc = -1 when a pyramid level has too few candidates."""
+    H, W = depth.shape[:2]
+    b = np.ascontiguousarray(bgr, np.uint8); d = np.ascontiguousarray(depth, np.uint16)
+    m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+    hdr = np.zeros((det.L * det.M, 7), np.int32)
+    ft = np.zeros((feature_cap, 3), np.int32)
+    nf = C.c_int(0)
+    bb = np.zeros(4, np.int32)
+    nfm = (C.c_int * 4)(*[int(v) for v in num_features][:4])
+    f = lib().flo_add_template
+    f.restype = C.c_int
+    rc = f(det._h, C.c_void_p(b.ctypes.data), C.c_void_p(d.ctypes.data), C.c_void_p(m.ctypes.data) if m is not None else None, W, H, nfm,
+           C.c_float(strong_threshold), int(extract_threshold), C.c_void_p(hdr.ctypes.data), C.c_void_p(ft.ctypes.data), feature_cap, C.byref(nf),
+           C.c_void_p(bb.ctypes.data))
+    return rc, hdr, ft[:nf.value].copy(), bb
+
+
+def erode3(img, iterations=1):
+    H, W = img.shape
+    src = np.ascontiguousarray(img, np.uint8)
+    out = np.zeros((H, W), np.uint8)
+    lib().flo_erode3_u8(C.c_void_p(src.ctypes.data), W, H, int(iterations), C.c_void_p(out.ctypes.data))
+    return out
+
+
+def distance_c3(img):
+    H, W = img.shape
+    src = np.ascontiguousarray(img, np.uint8)
+    out = np.zeros((H, W), np.float32)
+    lib().flo_distance_c3(C.c_void_p(src.ctypes.data), W, H, C.c_void_p(out.ctypes.data))
+    return out
+
+
 def detection(model_depth, ref_depth, K_ref, rect_model, rect_ref, icp_it_thr=10, dist_mean_thr=0.5, dist_diff_thr=0.01,
               r_match=None, t_match=None, d_match=0.0):
     H, W = ref_depth.shape

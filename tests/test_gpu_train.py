@@ -12,6 +12,26 @@ pytestmark = pytest.mark.gpu
 needs_ref = pytest.mark.skipif(not R.available(), reason="oracle/_ref/libfl_ref.so is not in this checkout")
 
 
+@pytest.mark.parametrize("case", [0, 1, 2, 3, 5])
+def test_add_template_equals_the_c_oracle(case):
+    """Against oracle/fl_oracle.c (flo_add_template, which tests/test_oracle_ref.py shows equal to the reference's addTemplate): runs with
+    or without oracle/_ref on the box."""
+    import fl_oracle_py as F
+    c = CASES[case]
+    W, H, T = c["W"], c["H"], c["T"]
+    b, d = synth.make_frame(W, H, c["frame"])
+    mask = c["mask"](W, H) if c["mask"] else None
+    orc, ohdr, oft, obb = F.add_template(F.Detector(T), b, d, mask)
+    h = fb.Handle(T, (0, 1), W, H)
+    rc, hdr, ft, bb = h.add_template(b, d, mask)
+    assert (rc == 0) == (orc == 0), (rc, orc)                    # (case 5, an object on the image border, has too few colour candidates: both say so)
+    if orc == 0:
+        assert np.array_equal(hdr, ohdr) and np.array_equal(ft, oft) and np.array_equal(bb, obb)
+    else:
+        assert rc == fb.FL_ERR_TRAIN
+    h.close()
+
+
 def test_add_template_equals_the_committed_fixture():
     """The fixture tests/golden/train_vga.npz holds the reference's own addTemplate results (oracle/make_train_golden.py; pinned by
     tests/test_oracle_ref.py); this comparison needs no oracle/_ref on the GPU box."""

@@ -418,3 +418,39 @@ def test_training_fixture_is_what_the_reference_returns():
         assert rc == int(g["rc%d" % i])
         if rc >= 0:
             assert np.array_equal(hdr, g["hdr%d" % i]) and np.array_equal(ft, g["ft%d" % i]) and np.array_equal(bb, g["bb%d" % i])
+
+
+def test_c_oracle_training_equals_the_reference():
+    """flo_add_template (oracle/fl_oracle.c) == the reference's own Detector::addTemplate: every feature, cropped box and bounding box, for
+    masks of several shapes and values, no mask, two and three pyramid levels, and the too-few-candidates case; its erode / distance
+    transform equal cv2 (IPP off: OpenCV's own code)."""
+    cv2 = pytest.importorskip("cv2")
+    from fealess_b200 import synth
+    use_ipp = cv2.ipp.useIPP()
+    cv2.ipp.setUseIPP(False)
+    try:
+        rng = np.random.default_rng(1)
+        for t in range(12):
+            H, W = int(rng.integers(8, 90)), int(rng.integers(8, 120))
+            m = (rng.random((H, W)) < rng.uniform(0.5, 0.98)).astype(np.uint8) * 255
+            if t % 4 == 0:
+                m[:] = 255
+            for it in (1, 2):
+                assert np.array_equal(F.erode3(m, it), cv2.erode(m, None, iterations=it, borderType=cv2.BORDER_REPLICATE))
+            assert np.array_equal(F.distance_c3(m), cv2.distanceTransform(m, cv2.DIST_C, 3))
+    finally:
+        cv2.ipp.setUseIPP(use_ipp)
+    W, H = 640, 480
+    yy, xx = np.mgrid[0:H, 0:W]
+    n_ok = 0
+    for T in ((5, 8), (4, 8, 8)):
+        fd, rd = F.Detector(T), R.Detector(T)
+        for frame, ell, val in ((0, (320, 240, 110, 80), 255), (0, (300, 250, 120, 90), 1), (2, None, 0), (3, (320, 240, 6, 5), 255)):
+            b, d = synth.make_frame(W, H, frame)
+            mask = None if ell is None else ((((xx - ell[0]) / ell[2]) ** 2 + ((yy - ell[1]) / ell[3]) ** 2) <= 1.0).astype(np.uint8) * val
+            a, r = F.add_template(fd, b, d, mask), R.add_template(rd, b, d, mask)
+            assert (a[0] == 0) == (r[0] >= 0), (T, frame)
+            if r[0] >= 0:
+                assert np.array_equal(a[1], r[1]) and np.array_equal(a[2], r[2]) and np.array_equal(a[3], r[3]), (T, frame)
+                n_ok += 1
+    assert n_ok == 6
