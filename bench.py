@@ -691,6 +691,16 @@ def run_ours(args):
                     tr["cpu_baseline"] = {"views_per_s": 3 / (tc1 - tc0), "cores": 1, "kind": "reference",
                                           "sample": "3 views through the reference's own addTemplate (oracle/_ref)",
                                           "identical_result": bool(rrc >= 0 and rct == 0 and np.array_equal(rhdr, hdr_t) and np.array_equal(rft, ft_t) and np.array_equal(rbb, bb_t))}
+                else:                                                    # oracle/_ref not in this checkout: the C restatement
+                    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+                    import fl_oracle_py as Fo
+                    odt = Fo.Detector(T)
+                    tc0 = time.perf_counter()
+                    for i in range(3):
+                        orc, ohdr, oft, obb = Fo.add_template(odt, frames[0][0], frames[0][1], tmask)
+                    tc1 = time.perf_counter()
+                    tr["cpu_baseline"] = {"views_per_s": 3 / (tc1 - tc0), "cores": 1, "kind": "port", "sample": "3 views through flo_add_template (oracle/fl_oracle.c)",
+                                          "identical_result": bool(orc == 0 and rct == 0 and np.array_equal(ohdr, hdr_t) and np.array_equal(oft, ft_t) and np.array_equal(obb, bb_t))}
             line["training"] = tr
         except Exception as e:  # noqa: BLE001
             line["training"] = {"error": "%s: %s" % (type(e).__name__, e)}
