@@ -589,16 +589,18 @@ def run_ours(args):
     if world == 1 and not args.no_cpu:
         import fl_ref_py as R
         if R.available():                                       # the reference's own Detector::match on one thread (its execution model)
-            ct, last, prims = ref_time_frames(frames, tset, 8, 2)
-            fi = (2 + 8 - 1) % len(frames)                       # the frame of the reference's last timed step
+            n_cpu, w_cpu = 40, 4                                  # ~2.5 s of CPU work: a bounded sample of the same workload
+            ct, last, prims = ref_time_frames(frames, tset, n_cpu, w_cpu)
+            fi = (w_cpu + n_cpu - 1) % len(frames)               # the frame of the reference's last timed step
             if set(map(tuple, last.tolist())) != set(map(tuple, h.match(frames[fi][0], frames[fi][1], THRESHOLD)[1].tolist())):   # (its std::unique may keep non-adjacent duplicates: compare as sets)
                 raise SystemExit("bench.py: the reference's own match list of frame %d differs from the GPU's" % fi)
-            kind, sample = "reference", "8 whole frames (after 2 warm-up), all %d templates, the reference's own Detector::match (oracle/_ref) on one thread; OpenCV = %s" % (args.templates, prims)
+            kind, sample = "reference", "%d whole frames (after %d warm-up), all %d templates, the reference's own Detector::match (oracle/_ref) on one thread; OpenCV = %s" % (n_cpu, w_cpu, args.templates, prims)
         else:
-            ct, _ = cpu_time_frames(frames, tset, 1, 8, 2)
-            kind, sample = "port", "8 whole frames (after 2 warm-up) of the same workload, all %d templates, single thread (oracle/_ref not in this checkout)" % args.templates
+            ct, _ = cpu_time_frames(frames, tset, 1, 40, 4)
+            kind, sample = "port", "40 whole frames (after 4 warm-up) of the same workload, all %d templates, single thread (oracle/_ref not in this checkout)" % args.templates
         cv = args.templates * CELLS * len(ct) / float(np.sum(ct))
-        cpu = {"value": cv, "unit": "evals/s", "cores": 1, "kind": kind, "frames_per_s": len(ct) / float(np.sum(ct)), "sample": sample, "host": host_info()}
+        cpu = {"value": cv, "unit": "evals/s", "cores": 1, "kind": kind, "frames_per_s": len(ct) / float(np.sum(ct)), "ms_per_frame_p50": 1e3 * float(np.median(ct)),
+               "ms_per_frame_p95": 1e3 * float(np.percentile(ct, 95)), "sample": sample, "host": host_info()}
 
     # ---- ICP (BASELINE configs[2], C3): 256 hypotheses x ~10k points, reported beside the headline ----
     icp = None
